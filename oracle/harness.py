@@ -1,0 +1,84 @@
+"""TEST INFRASTRUCTURE ONLY -- runs the compiled, unmodified reference (``oracle/_ref``).
+
+``oracle/_ref/alga_ref_harness`` is ``oracle/ref_harness.cpp`` linked against the reference's own
+sources (built by ``oracle/Makefile`` in the dev container; the binary travels to the GPU box).
+"""
+from __future__ import annotations
+
+import json
+import os
+import struct
+import subprocess
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HARNESS = os.path.join(HERE, "_ref", "alga_ref_harness")
+
+
+def available() -> bool:
+    return os.path.isfile(HARNESS) and os.access(HARNESS, os.X_OK)
+
+
+def write_reads(path, reads, min_overlap, rs_min_overlap, min_offset=0):
+    """ALGR: magic, u32 n, i32 x4 (min_overlap, rs, min_offset, 0), len, from, to, word_off, words."""
+    with open(path, "wb") as f:
+        f.write(b"ALGR")
+        f.write(struct.pack("<I4i", reads.n, min_overlap, rs_min_overlap, min_offset, 0))
+        f.write(reads.len_nt.astype("<u4").tobytes())
+        f.write(reads.align_from.astype("u1").tobytes())
+        f.write(reads.align_to.astype("u1").tobytes())
+        f.write(reads.word_off.astype("<u8").tobytes())
+        f.write(reads.words.astype("<u4").tobytes())
+
+
+def read_edges(path) -> np.ndarray:
+    """ALGE: magic, u32 n, u64 E, E x (i32 src, i32 dst, i32 offset) -> (E, 3) int32 sorted."""
+    with open(path, "rb") as f:
+        assert f.read(4) == b"ALGE"
+        _n, e = struct.unpack("<IQ", f.read(12))
+        arr = np.frombuffer(f.read(12 * e), dtype="<i4").reshape(-1, 3).copy()
+    return sort_edges(arr)
+
+
+def sort_edges(e: np.ndarray) -> np.ndarray:
+    e = np.asarray(e, dtype=np.int32).reshape(-1, 3)
+    if e.shape[0] == 0:
+        return e
+    order = np.lexsort((e[:, 2], e[:, 1], e[:, 0]))
+    return np.ascontiguousarray(e[order])
+
+
+def run_prefsuf(reads, min_overlap, rs_min_overlap, min_offset=0, threads=1, want_edges=True):
+    """Run the reference's GraphCreatorPrefSuf + retainOnlySmallestOffset; returns (edges, info)."""
+    if not available():
+        raise RuntimeError("oracle/_ref/alga_ref_harness is not built (make -C oracle ref)")
+    with tempfile.TemporaryDirectory() as d:
+        rp = os.path.join(d, "in.algr")
+        ep = os.path.join(d, "out.alge")
+        write_reads(rp, reads, min_overlap, rs_min_overlap, min_offset)
+        out = subprocess.run([HARNESS, "prefsuf", rp, ep if want_edges else "-", str(threads)], check=True,
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, cwd=d)
+        info = json.loads(out.stdout.decode().strip().splitlines()[-1])
+        edges = read_edges(ep) if want_edges else None
+    return edges, info
+
+
+def run_verify(reads, pairs, thr, max_offset_pct, min_overlap_area, min_offset=0) -> np.ndarray:
+    """Run the reference's AlignmentControllerHybrid::canAlign on (a, b, offset) triples."""
+    if not available():
+        raise RuntimeError("oracle/_ref/alga_ref_harness is not built (make -C oracle ref)")
+    pairs = np.ascontiguousarray(pairs, dtype="<i4").reshape(-1, 3)
+    with tempfile.TemporaryDirectory() as d:
+        rp = os.path.join(d, "in.algr")
+        pp = os.path.join(d, "pairs.algp")
+        vp = os.path.join(d, "verdict.bin")
+        write_reads(rp, reads, 0, 0, 0)
+        with open(pp, "wb") as f:
+            f.write(b"ALGP")
+            f.write(struct.pack("<Q4i", pairs.shape[0], thr, max_offset_pct, min_overlap_area, min_offset))
+            f.write(pairs.tobytes())
+        subprocess.run([HARNESS, "verify", rp, pp, vp], check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, cwd=d)
+        return np.fromfile(vp, dtype=np.uint8)

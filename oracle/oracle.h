@@ -1,0 +1,55 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's hot path.
+ *
+ * Plain-C restatement of swacisko/ALGA's GraphCreatorPrefSuf (exact prefix/suffix overlaps with
+ * on-the-fly transitive reduction) and of AlignmentControllerHybrid::canAlign, in the canonical
+ * single-threaded order of the reference.  Pinned against the unmodified reference itself
+ * (oracle/_ref/alga_ref_harness; fixtures under tests/golden/).  Only tests/, smoke() and the CPU
+ * legs of bench.py may link or load this; the product library never does.
+ */
+#ifndef ALGA_ORACLE_H
+#define ALGA_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    uint32_t n;               /* number of graph nodes (strand-reads) */
+    const uint32_t *words;    /* packed 2-bit blocks, reference layout (Read.cpp:40-68) */
+    const uint64_t *word_off; /* n+1 offsets into words */
+    const uint32_t *len_nt;   /* n lengths, 0 = removed read */
+    const uint8_t *align_from, *align_to; /* n flags (GraphCreator.h:46-62) */
+} oracle_reads;
+
+/* GraphCreatorPrefSuf.cpp:73-126 followed by Graph::retainOnlySmallestOffset (main.cpp:291).
+ * Returns a malloc'ed array of (src, dst, offset) int32 triples sorted by (src, dst); *n_edges = count.
+ * Free with oracle_free. */
+int32_t *oracle_prefsuf(const oracle_reads *r, int32_t min_overlap, int32_t rs_min_overlap, int32_t min_offset,
+                        int32_t max_len_cap, uint64_t *n_edges);
+
+/* Fingerprints of the length-L prefix and suffix of every read (GraphCreatorPrefSuf.cpp:213-236):
+ * h64 = sum s_j 4^j mod 10^18+3, h32 = sum s_j 4^j mod 10^9+7.  Entries of reads shorter than L are
+ * left untouched.  Arrays have n entries each. */
+void oracle_fingerprints(const oracle_reads *r, int32_t L, uint64_t *pre64, uint32_t *pre32, uint64_t *suf64,
+                         uint32_t *suf32);
+
+/* AlignmentControllerHybrid.cpp:46-83 -> AlignmentControllerLowErrorRate.cpp:15-49 for n_pairs
+ * (a, b, offset) triples. verdict[i] in {0,1}. */
+typedef struct {
+    int32_t max_offset_pct;   /* Params::MAX_OFFSET_CONSIDERED_FOR_ALIGNMENT */
+    int32_t min_offset;       /* Params::MIN_OFFSET_FOR_ALIGNMENT */
+    int32_t min_overlap_area; /* Params::MIN_OVERLAP_AREA */
+    int32_t threshold_pct;    /* Params::MINIMAL_OVERLAP_FOR_LCS_LOW_ERROR */
+    int32_t same_ends;        /* Params::ALIGNMENT_CONTROLLER_SAME_ENDS_LENGTH (3) */
+} oracle_verify_params;
+
+void oracle_verify_pairs(const oracle_reads *r, const int32_t *pairs, uint64_t n_pairs,
+                         const oracle_verify_params *p, uint8_t *verdict);
+
+void oracle_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,86 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes binding of oracle/liboracle.so (the plain-C restatement)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "liboracle.so")
+
+
+class _Reads(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("words", C.c_void_p), ("word_off", C.c_void_p), ("len_nt", C.c_void_p),
+                ("align_from", C.c_void_p), ("align_to", C.c_void_p)]
+
+
+class _VerifyParams(C.Structure):
+    _fields_ = [("max_offset_pct", C.c_int32), ("min_offset", C.c_int32), ("min_overlap_area", C.c_int32),
+                ("threshold_pct", C.c_int32), ("same_ends", C.c_int32)]
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(HERE, f) for f in ("prefsuf_oracle.c", "verify_oracle.c", "oracle.h", "Makefile")]
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
+        subprocess.run(["make", "-C", HERE, "liboracle.so"], check=True, stdout=subprocess.DEVNULL)
+    return LIB
+
+
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB)
+        _lib.oracle_prefsuf.restype = C.POINTER(C.c_int32)
+        _lib.oracle_prefsuf.argtypes = [C.POINTER(_Reads), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.POINTER(C.c_uint64)]
+        _lib.oracle_fingerprints.restype = None
+        _lib.oracle_fingerprints.argtypes = [C.POINTER(_Reads), C.c_int32] + [C.c_void_p] * 4
+        _lib.oracle_verify_pairs.restype = None
+        _lib.oracle_verify_pairs.argtypes = [C.POINTER(_Reads), C.c_void_p, C.c_uint64, C.POINTER(_VerifyParams),
+                                             C.c_void_p]
+        _lib.oracle_free.argtypes = [C.c_void_p]
+    return _lib
+
+
+def _reads_struct(reads):
+    return _Reads(reads.n, reads.words.ctypes.data, reads.word_off.ctypes.data, reads.len_nt.ctypes.data,
+                  reads.align_from.ctypes.data, reads.align_to.ctypes.data)
+
+
+def prefsuf(reads, min_overlap, rs_min_overlap, min_offset=0, max_len_cap=500) -> np.ndarray:
+    """(E, 3) int32 edges (src, dst, offset) sorted by (src, dst)."""
+    lib = _load()
+    rs = _reads_struct(reads)
+    ne = C.c_uint64(0)
+    p = lib.oracle_prefsuf(C.byref(rs), min_overlap, rs_min_overlap, min_offset, max_len_cap, C.byref(ne))
+    if not p:
+        raise ValueError("oracle_prefsuf rejected the parameters")
+    out = np.ctypeslib.as_array(p, shape=(max(ne.value, 1) * 3,))[: ne.value * 3].reshape(-1, 3).copy()
+    lib.oracle_free(p)
+    return out
+
+
+def fingerprints(reads, L):
+    lib = _load()
+    rs = _reads_struct(reads)
+    n = reads.n
+    p64 = np.zeros(n, np.uint64); p32 = np.zeros(n, np.uint32)
+    s64 = np.zeros(n, np.uint64); s32 = np.zeros(n, np.uint32)
+    lib.oracle_fingerprints(C.byref(rs), L, p64.ctypes.data, p32.ctypes.data, s64.ctypes.data, s32.ctypes.data)
+    return p64, p32, s64, s32
+
+
+def verify_pairs(reads, pairs, threshold_pct, max_offset_pct, min_overlap_area, min_offset=0, same_ends=3):
+    lib = _load()
+    rs = _reads_struct(reads)
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 3)
+    vp = _VerifyParams(max_offset_pct, min_offset, min_overlap_area, threshold_pct, same_ends)
+    out = np.zeros(pairs.shape[0], np.uint8)
+    lib.oracle_verify_pairs(C.byref(rs), pairs.ctypes.data, pairs.shape[0], C.byref(vp), out.ctypes.data)
+    return out

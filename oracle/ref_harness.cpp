@@ -1,0 +1,194 @@
+// TEST INFRASTRUCTURE ONLY -- not part of the product path.
+//
+// Harness around the UNMODIFIED reference sources (compiled where they lie under
+// /root/reference by oracle/Makefile; outputs only into oracle/_ref/).  It feeds
+// an already-preprocessed packed read set (the exact input of the hot path)
+// into the reference's own GraphCreatorPrefSuf and dumps the resulting edge set.
+//
+// It reproduces the call sequence of the reference driver around the hot path:
+//   main.cpp:239      Global::GRAPH = Graph(N)
+//   main.cpp:249      new GraphCreatorPrefSuf(READS, G, false)
+//   main.cpp:253-280  setAlignFrom / setAlignTo
+//   main.cpp:282      startAlignmentGraphCreation()
+//   main.cpp:286-291  clear(); delete; G->retainOnlySmallestOffset()
+// and, with --verify, AlignmentControllerLowErrorRate::canAlign on a pair list
+// (AlignmentControllerHybrid.cpp:46-83 -> AlignmentControllerLowErrorRate.cpp:15-49).
+//
+// File formats are documented in oracle/README.md (ALGR = reads, ALGE = edges).
+#include <Global.h>
+#include <Params.h>
+#include <DataStructures/Bitset.h>
+#include <DataStructures/Read.h>
+#include <DataStructures/Graph.h>
+#include <GraphCreators/GraphCreatorPrefSuf.h>
+#include <AlignmentControllers/AlignmentControllerHybrid.h>
+#include <AlignmentControllers/AlignmentControllerLowErrorRate.h>
+
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct ReadsFile {
+    uint32_t n = 0;
+    int32_t min_overlap = 0, rs = 0, min_offset = 0, reserved = 0;
+    std::vector<uint32_t> len;
+    std::vector<uint8_t> align_from, align_to;
+    std::vector<uint64_t> word_off;
+    std::vector<uint32_t> words;
+};
+
+void die(const char *msg) {
+    fprintf(stderr, "ref_harness: %s\n", msg);
+    exit(2);
+}
+
+template <class T>
+void read_vec(FILE *f, std::vector<T> &v, size_t n) {
+    v.resize(n);
+    if (n && fread(v.data(), sizeof(T), n, f) != n) die("short read");
+}
+
+ReadsFile load_reads(const char *path) {
+    FILE *f = fopen(path, "rb");
+    if (!f) die("cannot open reads file");
+    char magic[4];
+    if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "ALGR", 4) != 0) die("bad magic");
+    ReadsFile r;
+    if (fread(&r.n, 4, 1, f) != 1) die("short header");
+    int32_t p[4];
+    if (fread(p, 4, 4, f) != 4) die("short header");
+    r.min_overlap = p[0];
+    r.rs = p[1];
+    r.min_offset = p[2];
+    r.reserved = p[3];
+    read_vec(f, r.len, r.n);
+    read_vec(f, r.align_from, r.n);
+    read_vec(f, r.align_to, r.n);
+    read_vec(f, r.word_off, (size_t) r.n + 1);
+    read_vec(f, r.words, (size_t) r.word_off[r.n]);
+    fclose(f);
+    return r;
+}
+
+std::string decode(const ReadsFile &r, uint32_t i) {
+    static const char nt[4] = {'A', 'C', 'G', 'T'};
+    std::string s(r.len[i], 'A');
+    const uint32_t *w = r.words.data() + r.word_off[i];
+    for (uint32_t j = 0; j < r.len[i]; j++) s[j] = nt[(w[j >> 4] >> ((j & 15) * 2)) & 3];
+    return s;
+}
+
+void build_reads(const ReadsFile &r) {
+    Global::READS.assign(r.n, nullptr);
+    for (uint32_t i = 0; i < r.n; i++) {
+        if (r.len[i] == 0) continue;
+        Global::READS[i] = new Read((int) i, decode(r, i));
+    }
+}
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int run_prefsuf(const char *in_path, const char *out_path, int threads) {
+    ReadsFile r = load_reads(in_path);
+    Params::THREADS = threads;
+    Params::MIN_OVERLAP_PREF_SUF = r.min_overlap;
+    Params::REMOVE_SMALL_OVERLAP_EDGES_MIN_OVERLAP = r.rs;
+    Params::MIN_OFFSET_FOR_ALIGNMENT = r.min_offset;
+    build_reads(r);
+
+    Global::GRAPH = Graph((int) r.n);
+    Graph *G = &Global::GRAPH;
+
+    double t0 = now_s();
+    GraphCreator *gc = new GraphCreatorPrefSuf(&Global::READS, G, false);
+    for (uint32_t i = 0; i < r.n; i++) {
+        gc->setAlignFrom((int) i, r.align_from[i] != 0 && r.len[i] != 0);
+        gc->setAlignTo((int) i, r.align_to[i] != 0 && r.len[i] != 0);
+    }
+    double t1 = now_s();
+    gc->startAlignmentGraphCreation();
+    static_cast<GraphCreatorPrefSuf *>(gc)->clear();
+    delete gc;
+    G->retainOnlySmallestOffset();
+    double t2 = now_s();
+
+    uint64_t E = 0;
+    for (int i = 0; i < G->size(); i++) E += (*G)[i].size();
+    if (out_path && strcmp(out_path, "-") != 0) {
+        FILE *f = fopen(out_path, "wb");
+        if (!f) die("cannot open output");
+        fwrite("ALGE", 1, 4, f);
+        uint32_t n = r.n;
+        fwrite(&n, 4, 1, f);
+        fwrite(&E, 8, 1, f);
+        for (int i = 0; i < G->size(); i++) {
+            for (auto &e : (*G)[i]) {
+                int32_t t[3] = {i, e.first, e.second};
+                fwrite(t, 4, 3, f);
+            }
+        }
+        fclose(f);
+    }
+    printf("{\"n\": %u, \"edges\": %llu, \"threads\": %d, \"setup_s\": %.6f, \"graph_s\": %.6f}\n", r.n,
+           (unsigned long long) E, threads, t1 - t0, t2 - t1);
+    return 0;
+}
+
+// pairs file: "ALGP", u64 n, i32 thr (MINIMAL_OVERLAP_FOR_LCS_LOW_ERROR), i32 max_offset_pct
+// (MAX_OFFSET_CONSIDERED_FOR_ALIGNMENT), i32 min_overlap_area (MIN_OVERLAP_AREA), i32 min_offset,
+// then n x (i32 a, i32 b, i32 off)
+int run_verify(const char *in_path, const char *pairs_path, const char *out_path) {
+    ReadsFile r = load_reads(in_path);
+    Params::THREADS = 1;
+    build_reads(r);
+    FILE *f = fopen(pairs_path, "rb");
+    if (!f) die("cannot open pairs file");
+    char magic[4];
+    uint64_t n;
+    int32_t hp[4];
+    if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "ALGP", 4) != 0) die("bad pairs magic");
+    if (fread(&n, 8, 1, f) != 1 || fread(hp, 4, 4, f) != 4) die("short pairs header");
+    std::vector<int32_t> p(3 * n);
+    if (n && fread(p.data(), 4, 3 * n, f) != 3 * n) die("short pairs");
+    fclose(f);
+    Params::MINIMAL_OVERLAP_FOR_LCS_LOW_ERROR = hp[0];
+    Params::MAX_OFFSET_CONSIDERED_FOR_ALIGNMENT = hp[1];
+    Params::MIN_OVERLAP_AREA = hp[2];
+    Params::MIN_OFFSET_FOR_ALIGNMENT = hp[3];
+    AlignmentControllerHybrid ac;
+    std::vector<uint8_t> verdict(n);
+    for (uint64_t i = 0; i < n; i++) {
+        verdict[i] = ac.canAlign(Global::READS[p[3 * i]], Global::READS[p[3 * i + 1]], p[3 * i + 2]) ? 1 : 0;
+    }
+    FILE *o = fopen(out_path, "wb");
+    if (!o) die("cannot open verdict output");
+    fwrite(verdict.data(), 1, n, o);
+    fclose(o);
+    printf("{\"pairs\": %llu}\n", (unsigned long long) n);
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    Read::priorities = {0, 1, 2, 3};
+    Bitset::initializeStaticBlock();
+    if (argc >= 4 && strcmp(argv[1], "prefsuf") == 0) {
+        int threads = argc >= 5 ? atoi(argv[4]) : 1;
+        return run_prefsuf(argv[2], argv[3], threads);
+    }
+    if (argc >= 5 && strcmp(argv[1], "verify") == 0) return run_verify(argv[2], argv[3], argv[4]);
+    fprintf(stderr,
+            "usage: %s prefsuf <reads.algr> <edges.alge|-> [threads]\n"
+            "       %s verify  <reads.algr> <pairs.algp> <verdict.bin>\n",
+            argv[0], argv[0]);
+    return 2;
+}
