@@ -1,0 +1,97 @@
+"""ctypes binding of libalga_gpu.so -- the C ABI declared in include/alga_gpu.h.
+
+The library is built in-tree (``alga_b200/libalga_gpu.so``) by ``__graft_entry__.build()`` /
+``make -C alga_b200/csrc``.  Loading fails loudly when it is missing: there is no other code path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libalga_gpu.so")
+
+ALGA_OK = 0
+ERRORS = {-1: "ALGA_E_INVALID", -2: "ALGA_E_CUDA", -3: "ALGA_E_NOMEM", -4: "ALGA_E_CAPACITY"}
+
+
+class AlgaGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class Reads(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("words", C.c_void_p), ("word_off", C.c_void_p),
+                ("stride_words", C.c_uint32), ("len_nt", C.c_void_p), ("align_from", C.c_void_p),
+                ("align_to", C.c_void_p)]
+
+
+class PsParams(C.Structure):
+    _fields_ = [("min_overlap", C.c_int32), ("rs_min_overlap", C.c_int32), ("min_offset", C.c_int32),
+                ("max_len_cap", C.c_int32), ("device", C.c_int32), ("list_cap", C.c_int32)]
+
+
+class Csr(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_edges", C.c_uint64), ("row_off", C.POINTER(C.c_uint64)),
+                ("nbr", C.POINTER(C.c_int32)), ("off", C.POINTER(C.c_int32))]
+
+
+class Timing(C.Structure):
+    _fields_ = [("h2d_ms", C.c_double), ("device_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
+                ("kernel_launches", C.c_uint64), ("n_spilled_targets", C.c_uint64)]
+
+
+class VerifyParams(C.Structure):
+    _fields_ = [("max_offset_pct", C.c_int32), ("min_offset", C.c_int32), ("min_overlap_area", C.c_int32),
+                ("threshold_pct", C.c_int32), ("same_ends", C.c_int32), ("device", C.c_int32)]
+
+
+# every symbol include/alga_gpu.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "alga_gpu_prefsuf_build": (C.c_int, [C.POINTER(Reads), C.POINTER(PsParams), C.POINTER(Csr), C.POINTER(Timing)]),
+    "alga_gpu_free_csr": (None, [C.POINTER(Csr)]),
+    "alga_ps_plan_create": (C.c_int, [C.POINTER(_P), C.POINTER(PsParams)]),
+    "alga_ps_plan_destroy": (None, [_P]),
+    "alga_ps_plan_bind_reads_device": (C.c_int, [_P, C.POINTER(Reads), C.c_uint32]),
+    "alga_ps_plan_upload_reads": (C.c_int, [_P, C.POINTER(Reads)]),
+    "alga_ps_plan_run": (C.c_int, [_P, _P]),
+    "alga_ps_stage_index": (C.c_int, [_P, _P]),
+    "alga_ps_stage_phase1": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    "alga_ps_stage_phase2": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint64, _P, C.POINTER(_P),
+                                       C.POINTER(C.c_uint64)]),
+    "alga_ps_stage_csr": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint64, C.c_int, _P]),
+    "alga_ps_plan_result_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    "alga_ps_plan_result_host": (C.c_int, [_P, C.POINTER(Csr)]),
+    "alga_ps_plan_stats": (C.c_int, [_P, C.POINTER(Timing)]),
+    "alga_gpu_fingerprints": (C.c_int, [C.POINTER(Reads), C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "alga_gpu_pack_reads": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_int32, _P]),
+    "alga_gpu_verify_pairs": (C.c_int, [C.POINTER(Reads), _P, C.c_uint64, C.POINTER(VerifyParams), _P]),
+    "alga_gpu_device_count": (C.c_int, []),
+    "alga_gpu_last_error": (C.c_char_p, []),
+    "alga_gpu_version": (C.c_char_p, []),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libalga_gpu.so; raises if the CUDA library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "or `make -C alga_b200/csrc` (there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(code: int):
+    if code != ALGA_OK:
+        raise AlgaGpuError(code, load().alga_gpu_last_error().decode(errors="replace"))

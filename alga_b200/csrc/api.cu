@@ -1,0 +1,714 @@
+// C ABI of libalga_gpu.so (include/alga_gpu.h): plan / workspace management and the host-side
+// orchestration of the overlap-graph pipeline.  No CPU fallback: every compute entry point needs a
+// CUDA device and fails with ALGA_E_CUDA otherwise.
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "../../include/alga_gpu.h"
+#include "launch.h"
+
+using namespace alga;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(e_ == cudaErrorMemoryAllocation ? ALGA_E_NOMEM : ALGA_E_CUDA, "%s failed: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                     \
+    } while (0)
+#define CKR(expr)              \
+    do {                       \
+        int r_ = (expr);       \
+        if (r_ != ALGA_OK) return r_; \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap && p) return ALGA_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes + 256;
+            e = cudaMalloc(&p, want);
+        }
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(ALGA_E_NOMEM, "cudaMalloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return ALGA_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+struct Counters {
+    unsigned long long n_edges;
+    unsigned long long n_triples;
+    uint32_t n_spill;
+    uint32_t n_big;
+};
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+struct alga_ps_plan {
+    alga_ps_params params{};
+    int sm_count = 148;
+    LaunchCfg cfg;
+    uint64_t launches = 0;
+    uint64_t spilled = 0;
+
+    // bound read set
+    bool bound = false;
+    ReadsDev R{};
+    ReadStats stats{};
+    PsDev P{};
+    bool swap_direction = false;  // rs > max_l + 1 corner of the reference (SURVEY.md A.1 note 2)
+    bool index_valid = false;
+
+    // owned copies (upload path)
+    DevBuf words, word_off, len, from, to;
+    // workspace
+    DevBuf stats_d, counters_d, tp, ts, fwd, indeg, rev_off, rev, triples, triples1, outdeg, scan_ws, spill_queue, caps,
+        spill_off, spill_store, row_off, nbr, off, big_rows, tmp_nbr, tmp_off;
+    SeedTable Tp{}, Ts{};
+    Counters *h_counters = nullptr;  // pinned
+    ReadStats *h_stats = nullptr;    // pinned
+    uint64_t *h_u64 = nullptr;       // pinned
+
+    // result
+    uint32_t res_lo = 0, res_hi = 0;
+    uint64_t n_edges = 0;
+    double last_device_ms = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    ~alga_ps_plan() {
+        DevBuf *all[] = {&words, &word_off, &len, &from, &to, &stats_d, &counters_d, &tp, &ts, &fwd, &indeg, &rev_off, &rev,
+                         &triples, &triples1, &outdeg, &scan_ws, &spill_queue, &caps, &spill_off, &spill_store, &row_off,
+                         &nbr, &off, &big_rows, &tmp_nbr, &tmp_off};
+        for (DevBuf *b : all) b->release();
+        if (h_counters) cudaFreeHost(h_counters);
+        if (h_stats) cudaFreeHost(h_stats);
+        if (h_u64) cudaFreeHost(h_u64);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+    }
+};
+
+namespace {
+
+int use_device(alga_ps_plan *plan) {
+    CK(cudaSetDevice(plan->params.device));
+    return ALGA_OK;
+}
+
+int read_counters(alga_ps_plan *plan, cudaStream_t s) {
+    CK(cudaMemcpyAsync(plan->h_counters, plan->counters_d.p, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ALGA_OK;
+}
+
+int resolve_params(alga_ps_plan *plan) {
+    const alga_ps_params &pp = plan->params;
+    if (pp.min_overlap < 1) return fail(ALGA_E_INVALID, "min_overlap must be >= 1 (got %d)", pp.min_overlap);
+    if (pp.min_offset < 0) return fail(ALGA_E_INVALID, "min_offset must be >= 0 (got %d)", pp.min_offset);
+    const int cap = pp.max_len_cap > 0 ? pp.max_len_cap : 500;
+    PsDev &P = plan->P;
+    P.lmin = pp.min_overlap;
+    P.rs = pp.rs_min_overlap;
+    P.min_offset = pp.min_offset;
+    // The reference loop `while (L <= min(maxReadLength, 500)) { L++; ... }` (GraphCreatorPrefSuf.cpp:92-95)
+    // also runs the iteration L = min(maxReadLength, cap) + 1, which is a real overlap length for reads
+    // longer than the cap.  max_l is that last iterated length.
+    P.max_l = (int32_t) (plan->stats.max_len < (uint32_t) cap ? plan->stats.max_len : (uint32_t) cap) + 1;
+    P.seed_nt = P.lmin < 32 ? P.lmin : 32;
+    P.seed_mask = P.seed_nt == 32 ? ~0ull : ((1ull << (2 * P.seed_nt)) - 1ull);
+    // the reference transposes the phase-1 graph when L reaches rs (GraphCreatorPrefSuf.cpp:288).  If
+    // that never happens the single final transpose leaves the phase-1 edges reversed.
+    plan->swap_direction = P.rs > P.max_l && P.max_l >= P.lmin;
+    return ALGA_OK;
+}
+
+int compute_stats(alga_ps_plan *plan, cudaStream_t s, uint32_t max_len_hint) {
+    CKR(plan->stats_d.ensure(sizeof(ReadStats)));
+    launch_read_stats(plan->R, plan->params.min_overlap, plan->params.min_offset, plan->stats_d.as<ReadStats>(), s,
+                      plan->cfg);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(plan->h_stats, plan->stats_d.p, sizeof(ReadStats), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    plan->stats = *plan->h_stats;
+    if (max_len_hint && max_len_hint != plan->stats.max_len)
+        return fail(ALGA_E_INVALID, "max_len_nt hint %u does not match the read set (%u)", max_len_hint,
+                    plan->stats.max_len);
+    return resolve_params(plan);
+}
+
+uint32_t buckets_for(uint32_t entries) {
+    // load factor <= 0.5 with 4-slot buckets
+    uint64_t nb = ((uint64_t) entries * 2 + kSlotsPerBucket - 1) / kSlotsPerBucket;
+    if (nb < 64) nb = 64;
+    return (uint32_t) nb;
+}
+
+int stage_index(alga_ps_plan *plan, cudaStream_t s) {
+    if (!plan->bound) return fail(ALGA_E_INVALID, "no read set bound to the plan");
+    plan->Tp.n_buckets = buckets_for(plan->stats.n_prefix);
+    plan->Ts.n_buckets = buckets_for(plan->stats.n_suffix);
+    const size_t bp = (size_t) plan->Tp.n_buckets * kSlotsPerBucket * 8, bs = (size_t) plan->Ts.n_buckets * kSlotsPerBucket * 8;
+    CKR(plan->tp.ensure(bp));
+    CKR(plan->ts.ensure(bs));
+    plan->Tp.slots = plan->tp.as<uint64_t>();
+    plan->Ts.slots = plan->ts.as<uint64_t>();
+    CK(cudaMemsetAsync(plan->tp.p, 0xFF, bp, s));
+    CK(cudaMemsetAsync(plan->ts.p, 0xFF, bs, s));
+    launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, s, plan->cfg);
+    CK(cudaGetLastError());
+    plan->index_valid = true;
+    return ALGA_OK;
+}
+
+// phase 2 (+ spill path) for targets [lo,hi) given rev rows; leaves triples in plan->triples, count in h_counters
+int run_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, uint32_t *outdeg, cudaStream_t s) {
+    const uint32_t n = hi - lo;
+    int list_cap = plan->params.list_cap > 0 ? plan->params.list_cap : 64;
+    if (list_cap > 2048) list_cap = 2048;
+    uint64_t edge_cap = (uint64_t) n * 3 + (1u << 16);
+    CKR(plan->spill_queue.ensure((size_t) (n ? n : 1) * 4));
+    for (int attempt = 0; attempt < 3; attempt++) {
+        CKR(plan->triples.ensure((size_t) edge_cap * 12));
+        CK(cudaMemsetAsync(plan->counters_d.p, 0, sizeof(Counters), s));
+        if (outdeg) CK(cudaMemsetAsync(outdeg, 0, (size_t) plan->R.n * 4, s));
+        Counters *dc = plan->counters_d.as<Counters>();
+        Phase2Out out{plan->triples.as<int32_t>(), &dc->n_edges, edge_cap, outdeg, plan->spill_queue.as<uint32_t>(),
+                      &dc->n_spill};
+        launch_phase2(plan->R, plan->Ts, plan->P, lo, hi, plan->rev_off.as<uint32_t>(), plan->rev.as<int2>(), list_cap,
+                      out, s, plan->cfg);
+        CK(cudaGetLastError());
+        CKR(read_counters(plan, s));
+        const uint32_t n_spill = plan->h_counters->n_spill;
+        plan->spilled = n_spill;
+        if (n_spill) {
+            // targets whose in-neighbour list outgrew shared memory: exact capacity, lists in HBM
+            CKR(plan->caps.ensure((size_t) n_spill * 4));
+            CKR(plan->spill_off.ensure(((size_t) n_spill + 1) * 8));
+            CKR(plan->scan_ws.ensure(scan_workspace_bytes(n_spill)));
+            launch_phase2_count(plan->R, plan->Ts, plan->P, lo, plan->rev_off.as<uint32_t>(),
+                                plan->spill_queue.as<uint32_t>(), n_spill, plan->caps.as<uint32_t>(), s, plan->cfg);
+            launch_scan_u64(plan->caps.as<uint32_t>(), plan->spill_off.as<uint64_t>(), n_spill, plan->scan_ws.p, s,
+                            plan->cfg);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(plan->h_u64, plan->spill_off.as<uint64_t>() + n_spill, 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            const uint64_t total = *plan->h_u64;
+            CKR(plan->spill_store.ensure((size_t) total * 12 + 16));
+            launch_phase2_spill(plan->R, plan->Ts, plan->P, lo, plan->rev_off.as<uint32_t>(), plan->rev.as<int2>(),
+                                plan->spill_queue.as<uint32_t>(), n_spill, plan->spill_off.as<uint64_t>(),
+                                plan->spill_store.as<uint32_t>(), out, s, plan->cfg);
+            CK(cudaGetLastError());
+            CKR(read_counters(plan, s));
+        }
+        if (plan->h_counters->n_edges <= edge_cap) return ALGA_OK;
+        edge_cap = plan->h_counters->n_edges + 1024;  // retry with the exact size
+    }
+    return fail(ALGA_E_CAPACITY, "edge buffer overflow persisted after retries");
+}
+
+int build_rev_from_counts(alga_ps_plan *plan, uint32_t n_targets, cudaStream_t s) {
+    CKR(plan->rev_off.ensure(((size_t) n_targets + 1) * 4));
+    CKR(plan->scan_ws.ensure(scan_workspace_bytes(n_targets)));
+    launch_scan_u32(plan->indeg.as<uint32_t>(), plan->rev_off.as<uint32_t>(), n_targets, plan->scan_ws.p, s, plan->cfg);
+    CK(cudaGetLastError());
+    return ALGA_OK;
+}
+
+int stage_csr(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int32_t *triples, uint64_t n_tr, int swap,
+              bool outdeg_ready, cudaStream_t s) {
+    const uint32_t n = hi - lo;
+    CKR(plan->outdeg.ensure((size_t) (plan->R.n ? plan->R.n : 1) * 4));
+    uint32_t *outdeg = plan->outdeg.as<uint32_t>();
+    if (!outdeg_ready) {
+        CK(cudaMemsetAsync(outdeg, 0, (size_t) (n ? n : 1) * 4, s));
+        launch_count_sources(triples, n_tr, lo, hi, swap, outdeg, s, plan->cfg);
+    } else {
+        outdeg += lo;  // counted by global id
+    }
+    CKR(plan->row_off.ensure(((size_t) n + 1) * 8));
+    CKR(plan->scan_ws.ensure(scan_workspace_bytes(n)));
+    launch_scan_u64(outdeg, plan->row_off.as<uint64_t>(), n, plan->scan_ws.p, s, plan->cfg);
+    CKR(plan->nbr.ensure((size_t) (n_tr ? n_tr : 1) * 4));
+    CKR(plan->off.ensure((size_t) (n_tr ? n_tr : 1) * 4));
+    CKR(plan->big_rows.ensure((size_t) (n ? n : 1) * 4));
+    launch_scatter_csr(triples, n_tr, lo, hi, swap, plan->row_off.as<uint64_t>(), outdeg, plan->nbr.as<int32_t>(),
+                       plan->off.as<int32_t>(), s, plan->cfg);
+    Counters *dc = plan->counters_d.as<Counters>();
+    CK(cudaMemsetAsync(&dc->n_big, 0, 4, s));
+    launch_sort_rows(plan->row_off.as<uint64_t>(), n, plan->nbr.as<int32_t>(), plan->off.as<int32_t>(),
+                     plan->big_rows.as<uint32_t>(), &dc->n_big, s, plan->cfg);
+    CK(cudaGetLastError());
+    CKR(read_counters(plan, s));
+    if (plan->h_counters->n_big) {
+        CKR(plan->tmp_nbr.ensure((size_t) n_tr * 4));
+        CKR(plan->tmp_off.ensure((size_t) n_tr * 4));
+        launch_sort_big_rows(plan->row_off.as<uint64_t>(), plan->big_rows.as<uint32_t>(), plan->h_counters->n_big,
+                             plan->nbr.as<int32_t>(), plan->off.as<int32_t>(), plan->tmp_nbr.as<int32_t>(),
+                             plan->tmp_off.as<int32_t>(), s, plan->cfg);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(plan->h_u64, plan->row_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    plan->n_edges = *plan->h_u64;
+    plan->res_lo = lo;
+    plan->res_hi = hi;
+    return ALGA_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char *alga_gpu_last_error(void) { return g_err; }
+const char *alga_gpu_version(void) { return "alga_b200 0.1.0 (sm_100a)"; }
+
+int alga_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int alga_ps_plan_create(alga_ps_plan **out, const alga_ps_params *params) {
+    if (!out || !params) return fail(ALGA_E_INVALID, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(ALGA_E_CUDA, "no CUDA device available (%s); libalga_gpu has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (params->device < 0 || params->device >= ndev) return fail(ALGA_E_INVALID, "device %d out of range", params->device);
+    alga_ps_plan *plan = new (std::nothrow) alga_ps_plan();
+    if (!plan) return fail(ALGA_E_NOMEM, "out of host memory");
+    plan->params = *params;
+    plan->cfg.launches = &plan->launches;
+    int r = [&]() -> int {
+        CK(cudaSetDevice(params->device));
+        int sm = 0;
+        CK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, params->device));
+        plan->sm_count = plan->cfg.sm_count = sm;
+        CK(cudaMallocHost((void **) &plan->h_counters, sizeof(Counters)));
+        CK(cudaMallocHost((void **) &plan->h_stats, sizeof(ReadStats)));
+        CK(cudaMallocHost((void **) &plan->h_u64, 8));
+        CK(cudaEventCreate(&plan->ev0));
+        CK(cudaEventCreate(&plan->ev1));
+        CKR(plan->counters_d.ensure(sizeof(Counters)));
+        return ALGA_OK;
+    }();
+    if (r != ALGA_OK) {
+        delete plan;
+        return r;
+    }
+    *out = plan;
+    return ALGA_OK;
+}
+
+void alga_ps_plan_destroy(alga_ps_plan *plan) {
+    if (!plan) return;
+    cudaSetDevice(plan->params.device);
+    delete plan;
+}
+
+int alga_ps_plan_bind_reads_device(alga_ps_plan *plan, const alga_reads *r, uint32_t max_len_nt) {
+    if (!plan || !r) return fail(ALGA_E_INVALID, "null argument");
+    if (r->n_reads && (!r->words || !r->len_nt)) return fail(ALGA_E_INVALID, "words / len_nt must not be null");
+    if (!r->word_off && r->stride_words == 0 && r->n_reads) return fail(ALGA_E_INVALID, "word_off is null and stride_words is 0");
+    if (r->n_reads >= 0xFFFFFFF0u) return fail(ALGA_E_INVALID, "too many reads");
+    CKR(use_device(plan));
+    plan->R.words = r->words;
+    plan->R.word_off = r->word_off;
+    plan->R.len = r->len_nt;
+    plan->R.from = r->align_from;
+    plan->R.to = r->align_to;
+    plan->R.n = r->n_reads;
+    plan->R.stride = r->word_off ? 0 : r->stride_words;
+    plan->bound = true;
+    plan->index_valid = false;
+    return compute_stats(plan, 0, max_len_nt);
+}
+
+int alga_ps_plan_upload_reads(alga_ps_plan *plan, const alga_reads *h) {
+    if (!plan || !h) return fail(ALGA_E_INVALID, "null argument");
+    if (h->n_reads && (!h->words || !h->len_nt)) return fail(ALGA_E_INVALID, "words / len_nt must not be null");
+    if (!h->word_off && h->stride_words == 0 && h->n_reads) return fail(ALGA_E_INVALID, "word_off is null and stride_words is 0");
+    CKR(use_device(plan));
+    const uint32_t n = h->n_reads;
+    const uint64_t n_words = h->word_off ? h->word_off[n] : (uint64_t) n * h->stride_words;
+    CKR(plan->words.ensure((size_t) n_words * 4 + 16));
+    CKR(plan->len.ensure((size_t) (n ? n : 1) * 4));
+    cudaStream_t s = 0;
+    CK(cudaMemcpyAsync(plan->words.p, h->words, (size_t) n_words * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync((char *) plan->words.p + (size_t) n_words * 4, 0, 16, s));
+    CK(cudaMemcpyAsync(plan->len.p, h->len_nt, (size_t) n * 4, cudaMemcpyHostToDevice, s));
+    alga_reads d = *h;
+    d.words = plan->words.as<uint32_t>();
+    d.len_nt = plan->len.as<uint32_t>();
+    if (h->word_off) {
+        CKR(plan->word_off.ensure(((size_t) n + 1) * 8));
+        CK(cudaMemcpyAsync(plan->word_off.p, h->word_off, ((size_t) n + 1) * 8, cudaMemcpyHostToDevice, s));
+        d.word_off = plan->word_off.as<uint64_t>();
+    }
+    if (h->align_from) {
+        CKR(plan->from.ensure(n ? n : 1));
+        CK(cudaMemcpyAsync(plan->from.p, h->align_from, n, cudaMemcpyHostToDevice, s));
+        d.align_from = plan->from.as<uint8_t>();
+    }
+    if (h->align_to) {
+        CKR(plan->to.ensure(n ? n : 1));
+        CK(cudaMemcpyAsync(plan->to.p, h->align_to, n, cudaMemcpyHostToDevice, s));
+        d.align_to = plan->to.as<uint8_t>();
+    }
+    return alga_ps_plan_bind_reads_device(plan, &d, 0);
+}
+
+int alga_ps_stage_index(alga_ps_plan *plan, void *stream) {
+    if (!plan) return fail(ALGA_E_INVALID, "null plan");
+    CKR(use_device(plan));
+    return stage_index(plan, (cudaStream_t) stream);
+}
+
+int alga_ps_stage_phase1(alga_ps_plan *plan, uint32_t lo, uint32_t hi, void *stream, const int32_t **dev_triples,
+                         uint64_t *n_triples) {
+    if (!plan || !dev_triples || !n_triples) return fail(ALGA_E_INVALID, "null argument");
+    if (!plan->index_valid) return fail(ALGA_E_INVALID, "seed index not built (call alga_ps_stage_index)");
+    if (lo > hi || hi > plan->R.n) return fail(ALGA_E_INVALID, "bad range [%u,%u)", lo, hi);
+    CKR(use_device(plan));
+    cudaStream_t s = (cudaStream_t) stream;
+    const uint32_t n = hi - lo;
+    CKR(plan->fwd.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * sizeof(int2)));
+    CKR(plan->triples1.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * 12));
+    launch_phase1(plan->R, plan->Tp, plan->P, lo, hi, plan->fwd.as<int2>(), nullptr, s, plan->cfg);
+    Counters *dc = plan->counters_d.as<Counters>();
+    CK(cudaMemsetAsync(&dc->n_triples, 0, 8, s));
+    launch_compact_slots(plan->fwd.as<int2>(), lo, hi, plan->triples1.as<int32_t>(), &dc->n_triples, s, plan->cfg);
+    CK(cudaGetLastError());
+    CKR(read_counters(plan, s));
+    *dev_triples = plan->triples1.as<int32_t>();
+    *n_triples = plan->h_counters->n_triples;
+    return ALGA_OK;
+}
+
+int alga_ps_stage_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int32_t *tin, uint64_t n_in, void *stream,
+                         const int32_t **dev_triples_out, uint64_t *n_out) {
+    if (!plan || !dev_triples_out || !n_out) return fail(ALGA_E_INVALID, "null argument");
+    if (!plan->index_valid) return fail(ALGA_E_INVALID, "seed index not built (call alga_ps_stage_index)");
+    if (lo > hi || hi > plan->R.n) return fail(ALGA_E_INVALID, "bad range [%u,%u)", lo, hi);
+    if (n_in && !tin) return fail(ALGA_E_INVALID, "null triples");
+    CKR(use_device(plan));
+    cudaStream_t s = (cudaStream_t) stream;
+    const uint32_t n = hi - lo;
+    CKR(plan->indeg.ensure((size_t) (n ? n : 1) * 4));
+    CK(cudaMemsetAsync(plan->indeg.p, 0, (size_t) (n ? n : 1) * 4, s));
+    launch_count_targets(tin, n_in, lo, hi, plan->indeg.as<uint32_t>(), s, plan->cfg);
+    CKR(build_rev_from_counts(plan, n, s));
+    CKR(plan->rev.ensure((size_t) (n_in ? n_in : 1) * sizeof(int2)));
+    launch_scatter_rev_triples(tin, n_in, lo, hi, plan->rev_off.as<uint32_t>(), plan->indeg.as<uint32_t>(),
+                               plan->rev.as<int2>(), s, plan->cfg);
+    CK(cudaGetLastError());
+    CKR(run_phase2(plan, lo, hi, nullptr, s));
+    *dev_triples_out = plan->triples.as<int32_t>();
+    *n_out = plan->h_counters->n_edges;
+    return ALGA_OK;
+}
+
+int alga_ps_stage_csr(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int32_t *triples, uint64_t n, int swap,
+                      void *stream) {
+    if (!plan) return fail(ALGA_E_INVALID, "null plan");
+    if (!plan->bound) return fail(ALGA_E_INVALID, "no read set bound to the plan");
+    if (lo > hi || hi > plan->R.n) return fail(ALGA_E_INVALID, "bad range [%u,%u)", lo, hi);
+    if (n && !triples) return fail(ALGA_E_INVALID, "null triples");
+    CKR(use_device(plan));
+    return stage_csr(plan, lo, hi, triples, n, swap, false, (cudaStream_t) stream);
+}
+
+int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
+    if (!plan) return fail(ALGA_E_INVALID, "null plan");
+    if (!plan->bound) return fail(ALGA_E_INVALID, "no read set bound to the plan");
+    CKR(use_device(plan));
+    cudaStream_t s = (cudaStream_t) stream;
+    const uint32_t n = plan->R.n;
+    plan->launches = 0;
+    plan->spilled = 0;
+    CK(cudaEventRecord(plan->ev0, s));
+    CKR(stage_index(plan, s));
+    // phase 1 with fused in-degree counting
+    CKR(plan->fwd.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * sizeof(int2)));
+    CKR(plan->indeg.ensure((size_t) (n ? n : 1) * 4));
+    CK(cudaMemsetAsync(plan->indeg.p, 0, (size_t) (n ? n : 1) * 4, s));
+    launch_phase1(plan->R, plan->Tp, plan->P, 0, n, plan->fwd.as<int2>(), plan->indeg.as<uint32_t>(), s, plan->cfg);
+    // reversed phase-1 graph (rows by target)
+    CKR(build_rev_from_counts(plan, n, s));
+    CKR(plan->rev.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * sizeof(int2)));
+    launch_scatter_rev_slots(plan->fwd.as<int2>(), 0, n, 0, n, plan->rev_off.as<uint32_t>(), plan->indeg.as<uint32_t>(),
+                             plan->rev.as<int2>(), s, plan->cfg);
+    CK(cudaGetLastError());
+    // phase 2 with fused out-degree counting (not in the reversed-result corner)
+    CKR(plan->outdeg.ensure((size_t) (n ? n : 1) * 4));
+    const bool fuse_outdeg = !plan->swap_direction;
+    CKR(run_phase2(plan, 0, n, fuse_outdeg ? plan->outdeg.as<uint32_t>() : nullptr, s));
+    CKR(stage_csr(plan, 0, n, plan->triples.as<int32_t>(), plan->h_counters->n_edges, plan->swap_direction ? 1 : 0,
+                  fuse_outdeg, s));
+    CK(cudaEventRecord(plan->ev1, s));
+    CK(cudaEventSynchronize(plan->ev1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, plan->ev0, plan->ev1));
+    plan->last_device_ms = ms;
+    return ALGA_OK;
+}
+
+int alga_ps_plan_result_device(alga_ps_plan *plan, const uint64_t **row_off, const int32_t **nbr, const int32_t **off,
+                               uint64_t *n_edges) {
+    if (!plan) return fail(ALGA_E_INVALID, "null plan");
+    if (row_off) *row_off = plan->row_off.as<uint64_t>();
+    if (nbr) *nbr = plan->nbr.as<int32_t>();
+    if (off) *off = plan->off.as<int32_t>();
+    if (n_edges) *n_edges = plan->n_edges;
+    return ALGA_OK;
+}
+
+int alga_ps_plan_result_host(alga_ps_plan *plan, alga_csr *out) {
+    if (!plan || !out) return fail(ALGA_E_INVALID, "null argument");
+    CKR(use_device(plan));
+    const uint32_t n = plan->res_hi - plan->res_lo;
+    const uint64_t E = plan->n_edges;
+    out->n_reads = n;
+    out->n_edges = E;
+    out->row_off = (uint64_t *) malloc(((size_t) n + 1) * 8);
+    out->nbr = (int32_t *) malloc((size_t) (E ? E : 1) * 4);
+    out->off = (int32_t *) malloc((size_t) (E ? E : 1) * 4);
+    if (!out->row_off || !out->nbr || !out->off) {
+        alga_gpu_free_csr(out);
+        return fail(ALGA_E_NOMEM, "out of host memory for %llu edges", (unsigned long long) E);
+    }
+    CK(cudaMemcpy(out->row_off, plan->row_off.p, ((size_t) n + 1) * 8, cudaMemcpyDeviceToHost));
+    if (E) {
+        CK(cudaMemcpy(out->nbr, plan->nbr.p, (size_t) E * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(out->off, plan->off.p, (size_t) E * 4, cudaMemcpyDeviceToHost));
+    }
+    return ALGA_OK;
+}
+
+int alga_ps_plan_stats(alga_ps_plan *plan, alga_timing *t) {
+    if (!plan || !t) return fail(ALGA_E_INVALID, "null argument");
+    memset(t, 0, sizeof(*t));
+    t->device_ms = plan->last_device_ms;
+    t->kernel_launches = plan->launches;
+    t->n_spilled_targets = plan->spilled;
+    return ALGA_OK;
+}
+
+void alga_gpu_free_csr(alga_csr *csr) {
+    if (!csr) return;
+    free(csr->row_off);
+    free(csr->nbr);
+    free(csr->off);
+    csr->row_off = nullptr;
+    csr->nbr = csr->off = nullptr;
+    csr->n_edges = 0;
+}
+
+// One cached plan per process for the one-call entry point (the reference's graph creator is not
+// re-entrant either: it works on process-wide statics).
+static std::mutex g_build_mutex;
+static alga_ps_plan *g_build_plan = nullptr;
+
+int alga_gpu_prefsuf_build(const alga_reads *reads, const alga_ps_params *params, alga_csr *out, alga_timing *timing) {
+    if (!reads || !params || !out) return fail(ALGA_E_INVALID, "null argument");
+    std::lock_guard<std::mutex> lock(g_build_mutex);
+    memset(out, 0, sizeof(*out));
+    const double t0 = now_ms();
+    if (g_build_plan && g_build_plan->params.device != params->device) {
+        alga_ps_plan_destroy(g_build_plan);
+        g_build_plan = nullptr;
+    }
+    if (!g_build_plan) CKR(alga_ps_plan_create(&g_build_plan, params));
+    g_build_plan->params = *params;
+    CKR(alga_ps_plan_upload_reads(g_build_plan, reads));
+    const double t1 = now_ms();
+    CKR(alga_ps_plan_run(g_build_plan, nullptr));
+    const double t2 = now_ms();
+    CKR(alga_ps_plan_result_host(g_build_plan, out));
+    const double t3 = now_ms();
+    if (timing) {
+        alga_ps_plan_stats(g_build_plan, timing);
+        timing->h2d_ms = t1 - t0;
+        timing->d2h_ms = t3 - t2;
+        timing->total_ms = t3 - t0;
+    }
+    return ALGA_OK;
+}
+
+// ---- fingerprints / pack / verify: host buffers in, host buffers out -------------------------------
+namespace {
+struct TmpReads {
+    DevBuf words, word_off, len;
+    ReadsDev R{};
+    int upload(const alga_reads *h) {
+        const uint32_t n = h->n_reads;
+        if (n && (!h->words || !h->len_nt)) return fail(ALGA_E_INVALID, "words / len_nt must not be null");
+        if (!h->word_off && h->stride_words == 0 && n) return fail(ALGA_E_INVALID, "word_off is null and stride_words is 0");
+        const uint64_t n_words = h->word_off ? h->word_off[n] : (uint64_t) n * h->stride_words;
+        CKR(words.ensure((size_t) n_words * 4 + 16));
+        CKR(len.ensure((size_t) (n ? n : 1) * 4));
+        CK(cudaMemcpy(words.p, h->words, (size_t) n_words * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemset((char *) words.p + (size_t) n_words * 4, 0, 16));
+        CK(cudaMemcpy(len.p, h->len_nt, (size_t) n * 4, cudaMemcpyHostToDevice));
+        R.words = words.as<uint32_t>();
+        R.len = len.as<uint32_t>();
+        R.n = n;
+        R.stride = h->word_off ? 0 : h->stride_words;
+        R.word_off = nullptr;
+        if (h->word_off) {
+            CKR(word_off.ensure(((size_t) n + 1) * 8));
+            CK(cudaMemcpy(word_off.p, h->word_off, ((size_t) n + 1) * 8, cudaMemcpyHostToDevice));
+            R.word_off = word_off.as<uint64_t>();
+        }
+        return ALGA_OK;
+    }
+    ~TmpReads() {
+        words.release();
+        word_off.release();
+        len.release();
+    }
+};
+
+int pick_device(int device, LaunchCfg *cfg) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(ALGA_E_CUDA, "no CUDA device available; libalga_gpu has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(ALGA_E_INVALID, "device %d out of range", device);
+    CK(cudaSetDevice(device));
+    CK(cudaDeviceGetAttribute(&cfg->sm_count, cudaDevAttrMultiProcessorCount, device));
+    return ALGA_OK;
+}
+}  // namespace
+
+int alga_gpu_fingerprints(const alga_reads *reads, int32_t L, int32_t device, uint64_t *pre64, uint32_t *pre32,
+                          uint64_t *suf64, uint32_t *suf32) {
+    if (!reads || !pre64 || !pre32 || !suf64 || !suf32) return fail(ALGA_E_INVALID, "null argument");
+    LaunchCfg cfg;
+    CKR(pick_device(device, &cfg));
+    TmpReads t;
+    CKR(t.upload(reads));
+    const uint32_t n = reads->n_reads;
+    DevBuf a, b, c, d;
+    int r = [&]() -> int {
+        CKR(a.ensure((size_t) (n ? n : 1) * 8));
+        CKR(b.ensure((size_t) (n ? n : 1) * 4));
+        CKR(c.ensure((size_t) (n ? n : 1) * 8));
+        CKR(d.ensure((size_t) (n ? n : 1) * 4));
+        CK(cudaMemcpy(a.p, pre64, (size_t) n * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(b.p, pre32, (size_t) n * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c.p, suf64, (size_t) n * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d.p, suf32, (size_t) n * 4, cudaMemcpyHostToDevice));
+        launch_fingerprints(t.R, L, a.as<uint64_t>(), b.as<uint32_t>(), c.as<uint64_t>(), d.as<uint32_t>(), 0, cfg);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(pre64, a.p, (size_t) n * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(pre32, b.p, (size_t) n * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(suf64, c.p, (size_t) n * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(suf32, d.p, (size_t) n * 4, cudaMemcpyDeviceToHost));
+        return ALGA_OK;
+    }();
+    a.release();
+    b.release();
+    c.release();
+    d.release();
+    return r;
+}
+
+int alga_gpu_pack_reads(const uint8_t *ascii, uint32_t n_reads, uint32_t len_nt, int32_t device, uint32_t *words) {
+    if (n_reads && len_nt && (!ascii || !words)) return fail(ALGA_E_INVALID, "null argument");
+    if (len_nt > 16 * 1024) return fail(ALGA_E_INVALID, "len_nt %u too large for the packing kernel", len_nt);
+    LaunchCfg cfg;
+    CKR(pick_device(device, &cfg));
+    const size_t nbytes = (size_t) n_reads * len_nt;
+    const size_t nwords = (size_t) n_reads * ((len_nt + 15) / 16);
+    DevBuf in, out;
+    int r = [&]() -> int {
+        CKR(in.ensure(nbytes + 32));
+        CKR(out.ensure((nwords ? nwords : 1) * 4));
+        CK(cudaMemcpy(in.p, ascii, nbytes, cudaMemcpyHostToDevice));
+        launch_pack_reads(in.as<uint8_t>(), n_reads, len_nt, out.as<uint32_t>(), 0, cfg);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(words, out.p, nwords * 4, cudaMemcpyDeviceToHost));
+        return ALGA_OK;
+    }();
+    in.release();
+    out.release();
+    return r;
+}
+
+int alga_gpu_verify_pairs(const alga_reads *reads, const int32_t *pairs, uint64_t n_pairs,
+                          const alga_verify_params *params, uint8_t *verdict) {
+    if (!reads || !params || (n_pairs && (!pairs || !verdict))) return fail(ALGA_E_INVALID, "null argument");
+    LaunchCfg cfg;
+    CKR(pick_device(params->device, &cfg));
+    TmpReads t;
+    CKR(t.upload(reads));
+    DevBuf dp, dv;
+    int r = [&]() -> int {
+        CKR(dp.ensure((size_t) (n_pairs ? n_pairs : 1) * 12));
+        CKR(dv.ensure((size_t) (n_pairs ? n_pairs : 1)));
+        CK(cudaMemcpy(dp.p, pairs, (size_t) n_pairs * 12, cudaMemcpyHostToDevice));
+        VerifyDev V{params->max_offset_pct, params->min_offset, params->min_overlap_area, params->threshold_pct,
+                    params->same_ends};
+        launch_verify_pairs(t.R, dp.as<int32_t>(), n_pairs, V, dv.as<uint8_t>(), 0, cfg);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(verdict, dv.p, (size_t) n_pairs, cudaMemcpyDeviceToHost));
+        return ALGA_OK;
+    }();
+    dp.release();
+    dv.release();
+    return r;
+}
+
+}  // extern "C"

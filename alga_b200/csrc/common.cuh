@@ -1,0 +1,132 @@
+// Device-side building blocks shared by the overlap-graph kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace alga {
+
+constexpr uint64_t kEmptySlot = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr int kSlotsPerBucket = 4;  // 4 x 8 B = one 32-byte DRAM sector
+constexpr int kSmallEdgesKept = 3;  // SOES, GraphCreatorPrefSuf.h:62
+
+// Packed read set resident in HBM, reference layout (Bitset.h:38-45).  `words` is padded with at
+// least 16 readable bytes so that a 3-word window read at the very end stays in bounds.
+struct ReadsDev {
+    const uint32_t *__restrict__ words;
+    const uint64_t *__restrict__ word_off;  // nullptr in fixed-stride mode
+    const uint32_t *__restrict__ len;
+    const uint8_t *__restrict__ from;  // may be nullptr (all true)
+    const uint8_t *__restrict__ to;    // may be nullptr (all true)
+    uint32_t n;
+    uint32_t stride;  // words per read when word_off == nullptr
+};
+
+__device__ __forceinline__ const uint32_t *read_ptr(const ReadsDev &r, uint32_t i) {
+    return r.words + (r.word_off ? r.word_off[i] : (uint64_t) i * r.stride);
+}
+__device__ __forceinline__ bool flag_from(const ReadsDev &r, uint32_t i) { return r.from ? r.from[i] != 0 : true; }
+__device__ __forceinline__ bool flag_to(const ReadsDev &r, uint32_t i) { return r.to ? r.to[i] != 0 : true; }
+
+// Parameters of one GraphCreatorPrefSuf run, resolved on the host.
+struct PsDev {
+    int32_t lmin;        // MIN_OVERLAP_PREF_SUF
+    int32_t rs;          // REMOVE_SMALL_OVERLAP_EDGES_MIN_OVERLAP
+    int32_t min_offset;  // MIN_OFFSET_FOR_ALIGNMENT
+    int32_t max_l;       // last overlap length the reference iterates: min(max read length, cap) + 1  (GraphCreatorPrefSuf.cpp:92-95)
+    int32_t seed_nt;     // K = min(lmin, 32): nucleotides hashed into the seed index
+    uint64_t seed_mask;  // low 2K bits
+};
+
+// Seed index: open addressing, 4-slot buckets, entry = (tag << 32) | read id.
+struct SeedTable {
+    uint64_t *slots;
+    uint32_t n_buckets;
+};
+
+// 32 bits of a packed read starting at bit position `bit`.
+__device__ __forceinline__ uint32_t bits32(const uint32_t *__restrict__ p, uint32_t bit) {
+    const uint32_t w = bit >> 5;
+    return __funnelshift_r(__ldg(p + w), __ldg(p + w + 1), bit & 31u);
+}
+// 64 bits of a packed read starting at bit position `bit`.
+__device__ __forceinline__ uint64_t bits64(const uint32_t *__restrict__ p, uint32_t bit) {
+    const uint32_t w = bit >> 5, s = bit & 31u;
+    const uint32_t a = __ldg(p + w), b = __ldg(p + w + 1), c = __ldg(p + w + 2);
+    return (uint64_t) __funnelshift_r(a, b, s) | ((uint64_t) __funnelshift_r(b, c, s) << 32);
+}
+
+// nbits of pa starting at bit offset bita == nbits of pb starting at word boundary 0 ?
+__device__ __forceinline__ bool equal_bits_aligned(const uint32_t *__restrict__ pa, uint32_t bita,
+                                                   const uint32_t *__restrict__ pb, uint32_t nbits) {
+    const uint32_t s = bita & 31u;
+    const uint32_t *q = pa + (bita >> 5);
+    uint32_t lo = __ldg(q);
+    uint32_t k = 0;
+    for (; k + 32 <= nbits; k += 32) {
+        const uint32_t hi = __ldg(q + (k >> 5) + 1);
+        if (__funnelshift_r(lo, hi, s) != __ldg(pb + (k >> 5))) return false;
+        lo = hi;
+    }
+    const uint32_t rem = nbits - k;
+    if (rem) {
+        const uint32_t hi = __ldg(q + (k >> 5) + 1);
+        const uint32_t m = (1u << rem) - 1u;
+        if ((__funnelshift_r(lo, hi, s) ^ __ldg(pb + (k >> 5))) & m) return false;
+    }
+    return true;
+}
+
+// splitmix64-style finaliser over the 2K-bit seed window
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 31;
+    x *= 0x7fb5d329728ea185ull;
+    x ^= x >> 27;
+    x *= 0x81dadef4bc2dd44dull;
+    x ^= x >> 33;
+    return x;
+}
+__device__ __forceinline__ uint32_t bucket_of(uint64_t h, uint32_t n_buckets) {
+    return __umulhi((uint32_t) (h >> 32), n_buckets);
+}
+__device__ __forceinline__ uint32_t tag_of(uint64_t h) { return (uint32_t) h; }
+
+// One 32-byte bucket = one 256-bit load (LDG.E.256 on sm_100a).
+__device__ __forceinline__ void load_bucket(const uint64_t *__restrict__ p, uint64_t (&e)[4]) {
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(e[0]), "=l"(e[1]), "=l"(e[2]), "=l"(e[3])
+                 : "l"(p));
+}
+
+// Walk the bucket chain of hash h and call f(read_id) for every entry whose tag matches.
+template <class F>
+__device__ __forceinline__ void probe_seed(const SeedTable &t, uint64_t h, F &&f) {
+    const uint32_t tag = tag_of(h);
+    uint32_t bk = bucket_of(h, t.n_buckets);
+    while (true) {
+        uint64_t e[4];
+        load_bucket(t.slots + (uint64_t) bk * kSlotsPerBucket, e);
+#pragma unroll
+        for (int s = 0; s < kSlotsPerBucket; s++) {
+            if (e[s] == kEmptySlot) return;
+            if ((uint32_t) (e[s] >> 32) == tag) f((uint32_t) e[s]);
+        }
+        bk = (bk + 1 == t.n_buckets) ? 0u : bk + 1;
+    }
+}
+
+__device__ __forceinline__ void insert_seed(const SeedTable &t, uint64_t h, uint32_t id) {
+    const uint64_t entry = ((uint64_t) tag_of(h) << 32) | id;
+    uint32_t bk = bucket_of(h, t.n_buckets);
+    while (true) {
+        unsigned long long *base = (unsigned long long *) (t.slots + (uint64_t) bk * kSlotsPerBucket);
+#pragma unroll
+        for (int s = 0; s < kSlotsPerBucket; s++) {
+            if (base[s] != kEmptySlot) continue;
+            if (atomicCAS(base + s, (unsigned long long) kEmptySlot, (unsigned long long) entry) == kEmptySlot) return;
+        }
+        bk = (bk + 1 == t.n_buckets) ? 0u : bk + 1;
+    }
+}
+
+}  // namespace alga

@@ -1,0 +1,100 @@
+// Host-callable launchers of the sm_100a kernels (implemented in the .cu files of this directory).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace alga {
+
+struct LaunchCfg {
+    int sm_count = 148;
+    uint64_t *launches = nullptr;  // incremented once per kernel launch
+};
+
+// --- read-set statistics: max length, eligible prefix/suffix counts ----------------------------
+struct ReadStats {
+    uint32_t max_len;
+    uint32_t n_prefix;  // reads that can be the target of an edge (alignTo && len >= lmin)
+    uint32_t n_suffix;  // reads that can be the source of an edge (alignFrom && len - min_offset >= lmin)
+    uint32_t pad;
+};
+void launch_read_stats(const ReadsDev &R, int lmin, int min_offset, ReadStats *d_stats, cudaStream_t s,
+                       const LaunchCfg &cfg);
+
+// --- seed index -------------------------------------------------------------------------------
+void launch_build_index(const ReadsDev &R, const PsDev &P, SeedTable prefix, SeedTable suffix, cudaStream_t s,
+                        const LaunchCfg &cfg);
+
+// --- phase 1: L in [lmin, min(rs-1, max_l)], keeps the 3 largest (L, c) per source read ----------
+// fwd: 3 slots per b in [lo,hi): (c, offset), c = -1 when empty.  indeg (nullable): += 1 per target c.
+void launch_phase1(const ReadsDev &R, const SeedTable &prefix, const PsDev &P, uint32_t lo, uint32_t hi, int2 *fwd,
+                   uint32_t *indeg, cudaStream_t s, const LaunchCfg &cfg);
+// compact the slots of [lo,hi) into (b, c, o) triples; *d_count must be zero on entry
+void launch_compact_slots(const int2 *fwd, uint32_t lo, uint32_t hi, int32_t *triples,
+                          unsigned long long *d_count, cudaStream_t s, const LaunchCfg &cfg);
+
+// --- reversed phase-1 adjacency (rows by target c in [lo,hi)) -------------------------------------
+// counts -> offsets is done with launch_scan; scatter consumes `cursor` (a copy of the counts).
+void launch_count_targets(const int32_t *triples, uint64_t n, uint32_t lo, uint32_t hi, uint32_t *indeg,
+                          cudaStream_t s, const LaunchCfg &cfg);
+void launch_scatter_rev_slots(const int2 *fwd, uint32_t b_lo, uint32_t b_hi, uint32_t c_lo, uint32_t c_hi,
+                              const uint32_t *rev_off, uint32_t *cursor, int2 *rev, cudaStream_t s,
+                              const LaunchCfg &cfg);
+void launch_scatter_rev_triples(const int32_t *triples, uint64_t n, uint32_t c_lo, uint32_t c_hi,
+                                const uint32_t *rev_off, uint32_t *cursor, int2 *rev, cudaStream_t s,
+                                const LaunchCfg &cfg);
+
+// --- phase 2: L in [max(rs,lmin), max_l] with per-target transitive reduction ----------------------
+struct Phase2Out {
+    int32_t *triples;             // (b, c, offset)
+    unsigned long long *n_edges;  // device counter (may exceed edge_cap -> caller retries)
+    uint64_t edge_cap;
+    uint32_t *outdeg;             // nullable, indexed by b (global id)
+    uint32_t *spill_queue;        // targets whose list outgrew the on-chip capacity
+    uint32_t *n_spill;
+};
+void launch_phase2(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo, uint32_t hi,
+                   const uint32_t *rev_off, const int2 *rev, int list_cap, const Phase2Out &out, cudaStream_t s,
+                   const LaunchCfg &cfg);
+// spill path: per queued target count row size + hits -> caps (u32), then replay with global lists
+void launch_phase2_count(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo,
+                         const uint32_t *rev_off, const uint32_t *queue, uint32_t n_queue, uint32_t *caps,
+                         cudaStream_t s, const LaunchCfg &cfg);
+void launch_phase2_spill(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo,
+                         const uint32_t *rev_off, const int2 *rev, const uint32_t *queue, uint32_t n_queue,
+                         const uint64_t *spill_off, uint32_t *spill_store, const Phase2Out &out, cudaStream_t s,
+                         const LaunchCfg &cfg);
+
+// --- CSR assembly -----------------------------------------------------------------------------
+void launch_count_sources(const int32_t *triples, uint64_t n, uint32_t lo, uint32_t hi, int swap, uint32_t *outdeg,
+                          cudaStream_t s, const LaunchCfg &cfg);
+void launch_scatter_csr(const int32_t *triples, uint64_t n, uint32_t lo, uint32_t hi, int swap,
+                        const uint64_t *row_off, uint32_t *cursor, int32_t *nbr, int32_t *off, cudaStream_t s,
+                        const LaunchCfg &cfg);
+// sort every row by (nbr, off); rows longer than 32 go through `big_rows` (queue of row ids) and tmp buffers
+void launch_sort_rows(const uint64_t *row_off, uint32_t n_rows, int32_t *nbr, int32_t *off, uint32_t *big_rows,
+                      uint32_t *n_big, cudaStream_t s, const LaunchCfg &cfg);
+void launch_sort_big_rows(const uint64_t *row_off, const uint32_t *big_rows, uint32_t n_big, int32_t *nbr,
+                          int32_t *off, int32_t *tmp_nbr, int32_t *tmp_off, cudaStream_t s, const LaunchCfg &cfg);
+
+// --- exclusive scan of u32 counts into u32 / u64 offsets (n+1 outputs, out[n] = total) ---------------
+size_t scan_workspace_bytes(uint64_t n);
+void launch_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, void *workspace, cudaStream_t s,
+                     const LaunchCfg &cfg);
+void launch_scan_u64(const uint32_t *in, uint64_t *out, uint64_t n, void *workspace, cudaStream_t s,
+                     const LaunchCfg &cfg);
+
+// --- misc kernels -----------------------------------------------------------------------------
+void launch_fill_u64(uint64_t *p, uint64_t v, uint64_t n, cudaStream_t s, const LaunchCfg &cfg);
+void launch_pack_reads(const uint8_t *ascii, uint32_t n_reads, uint32_t len_nt, uint32_t *words, cudaStream_t s,
+                       const LaunchCfg &cfg);
+void launch_fingerprints(const ReadsDev &R, int L, uint64_t *pre64, uint32_t *pre32, uint64_t *suf64,
+                         uint32_t *suf32, cudaStream_t s, const LaunchCfg &cfg);
+struct VerifyDev {
+    int32_t max_offset_pct, min_offset, min_overlap_area, threshold_pct, same_ends;
+};
+void launch_verify_pairs(const ReadsDev &R, const int32_t *pairs, uint64_t n_pairs, const VerifyDev &V,
+                         uint8_t *verdict, cudaStream_t s, const LaunchCfg &cfg);
+
+}  // namespace alga

@@ -1,0 +1,777 @@
+// Overlap search + transitive reduction kernels of the GraphCreatorPrefSuf hot path (sm_100a).
+//
+// The reference rebuilds a hash table of all length-L prefix fingerprints for every overlap length L
+// and probes it with every length-L suffix fingerprint (GraphCreatorPrefSuf.cpp:238-315, 356-488).
+// Here each read is indexed ONCE by a seed (its first K nucleotides for the prefix side, its last K
+// for the suffix side, K = min(min_overlap, 32)); every (read, L) pair then costs one 32-byte bucket
+// probe plus an exact 2-bit compare of the full overlap on a tag hit.  Acceptance by exact compare
+// equals the reference's acceptance by (mod 10^18+3, mod 10^9+7) fingerprint equality
+// (GraphCreatorPrefSuf.cpp:385-387) up to fingerprint collisions (~1e-27 per pair).
+//
+// Work decomposition: one warp per read, the 32 lanes probe 32 overlap lengths at once.
+//   phase 1 (L <  rs): warp = suffix read b, probes the prefix index, keeps the 3 largest (L, c)
+//                      = "the last 3 pushes" of GraphCreatorPrefSuf.cpp:397-402 in canonical order.
+//   phase 2 (L >= rs): warp = prefix read c, probes the suffix index for L ascending and replays the
+//                      per-target reduction of GraphCreatorPrefSuf.cpp:403-483 in (L, b) order on an
+//                      in-neighbour list kept in shared memory (global memory for spilled targets).
+#include "launch.h"
+
+namespace alga {
+
+namespace {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+
+inline int grid_for(uint64_t n_items, int per_block, const LaunchCfg &cfg, int max_blocks_per_sm = 16) {
+    uint64_t need = (n_items + per_block - 1) / per_block;
+    uint64_t cap = (uint64_t) cfg.sm_count * max_blocks_per_sm;
+    if (need < 1) need = 1;
+    return (int) (need < cap ? need : cap);
+}
+inline void bump(const LaunchCfg &cfg) {
+    if (cfg.launches) (*cfg.launches)++;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void read_stats_kernel(ReadsDev R, int lmin, int min_offset, ReadStats *stats) {
+    uint32_t mx = 0, np = 0, ns = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < R.n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t len = R.len[i];
+        mx = max(mx, len);
+        if (len && flag_to(R, i) && (int64_t) len >= lmin) np++;
+        if (len && flag_from(R, i) && (int64_t) len - min_offset >= lmin) ns++;
+    }
+    for (int d = 16; d; d >>= 1) {
+        mx = max(mx, __shfl_xor_sync(kFull, mx, d));
+        np += __shfl_xor_sync(kFull, np, d);
+        ns += __shfl_xor_sync(kFull, ns, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&stats->max_len, mx);
+        atomicAdd(&stats->n_prefix, np);
+        atomicAdd(&stats->n_suffix, ns);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Seed index build: one thread per read, two inserts (prefix side, suffix side).
+__global__ void build_index_kernel(ReadsDev R, PsDev P, SeedTable tp, SeedTable ts) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < R.n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t len = R.len[i];
+        if (len == 0 || (int64_t) len < P.lmin) continue;
+        const uint32_t *p = read_ptr(R, (uint32_t) i);
+        if (flag_to(R, (uint32_t) i)) {
+            const uint64_t w = bits64(p, 0) & P.seed_mask;
+            insert_seed(tp, mix64(w), (uint32_t) i);
+        }
+        if (flag_from(R, (uint32_t) i) && (int64_t) len - P.min_offset >= P.lmin) {
+            const uint64_t w = bits64(p, 2u * (len - (uint32_t) P.seed_nt)) & P.seed_mask;
+            insert_seed(ts, mix64(w), (uint32_t) i);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase 1.  Canonical order of the reference pushes is (L asc, c asc) and only the last 3 survive,
+// so the result is the 3 largest (L, c): scan L downwards 32 lengths at a time and stop at 3 hits.
+__global__ void __launch_bounds__(kThreads)
+phase1_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, int2 *__restrict__ fwd,
+              uint32_t *__restrict__ indeg) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const uint32_t n_warps = gridDim.x * kWarpsPerBlock;
+    for (uint64_t bb = (uint64_t) lo + warp; bb < hi; bb += n_warps) {
+        const uint32_t b = (uint32_t) bb;
+        const uint32_t lenb = R.len[b];
+        int32_t rc[kSmallEdgesKept], ro[kSmallEdgesKept];
+#pragma unroll
+        for (int k = 0; k < kSmallEdgesKept; k++) rc[k] = -1, ro[k] = 0;
+        int found = 0;
+        int64_t l_hi = (int64_t) lenb - P.min_offset;
+        if (l_hi > P.rs - 1) l_hi = P.rs - 1;
+        if (l_hi > P.max_l) l_hi = P.max_l;
+        if (lenb != 0 && flag_from(R, b) && l_hi >= P.lmin) {
+            const uint32_t *pb = read_ptr(R, b);
+            for (int32_t l_top = (int32_t) l_hi; l_top >= P.lmin && found < kSmallEdgesKept; l_top -= 32) {
+                const int32_t L = l_top - lane;
+                // per-lane: the (up to) 3 largest matching c at this L, t0 > t1 > t2 (kNone = empty)
+                uint32_t t0 = kNone, t1 = kNone, t2 = kNone;
+                int nh = 0;
+                if (L >= P.lmin) {
+                    const uint32_t o = lenb - (uint32_t) L;
+                    const uint64_t w = bits64(pb, 2u * o) & P.seed_mask;
+                    probe_seed(T, mix64(w), [&](uint32_t c) {
+                        if (c == b) return;
+                        if ((int64_t) R.len[c] < L) return;
+                        // prefix(c, L) == suffix(b, L)
+                        if (!equal_bits_aligned(pb, 2u * o, read_ptr(R, c), 2u * (uint32_t) L)) return;
+                        nh++;
+                        if (t0 == kNone || c > t0) { t2 = t1; t1 = t0; t0 = c; }
+                        else if (t1 == kNone || c > t1) { t2 = t1; t1 = c; }
+                        else if (t2 == kNone || c > t2) { t2 = c; }
+                    });
+                    if (nh > kSmallEdgesKept) nh = kSmallEdgesKept;
+                }
+                unsigned m = __ballot_sync(kFull, nh > 0);
+                while (m && found < kSmallEdgesKept) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int cnt = __shfl_sync(kFull, nh, src);
+                    const uint32_t s0 = __shfl_sync(kFull, t0, src);
+                    const uint32_t s1 = __shfl_sync(kFull, t1, src);
+                    const uint32_t s2 = __shfl_sync(kFull, t2, src);
+                    const int32_t off = (int32_t) lenb - (l_top - src);
+                    for (int k = 0; k < cnt && found < kSmallEdgesKept; k++) {
+                        const uint32_t c = k == 0 ? s0 : (k == 1 ? s1 : s2);
+#pragma unroll
+                        for (int q = 0; q < kSmallEdgesKept; q++)
+                            if (q == found) rc[q] = (int32_t) c, ro[q] = off;
+                        found++;
+                    }
+                }
+            }
+        }
+        if (lane < kSmallEdgesKept) {
+            int32_t c = -1, o = 0;
+#pragma unroll
+            for (int q = 0; q < kSmallEdgesKept; q++)
+                if (q == lane) c = rc[q], o = ro[q];
+            fwd[(uint64_t) (b - lo) * kSmallEdgesKept + lane] = make_int2(c, o);
+            if (c >= 0 && indeg) atomicAdd(indeg + c, 1u);
+        }
+    }
+}
+
+__global__ void compact_slots_kernel(const int2 *__restrict__ fwd, uint32_t lo, uint64_t n_slots,
+                                     int32_t *__restrict__ triples, unsigned long long *count) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
+    const uint64_t n_round = (n_slots + 31) & ~31ull;
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        int2 e = make_int2(-1, 0);
+        if (i < n_slots) e = fwd[i];
+        const unsigned m = __ballot_sync(kFull, e.x >= 0);
+        unsigned long long base = 0;
+        if (lane == 0 && m) base = atomicAdd(count, (unsigned long long) __popc(m));
+        base = __shfl_sync(kFull, base, 0);
+        if (e.x >= 0) {
+            const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
+            triples[3 * pos] = (int32_t) (lo + i / kSmallEdgesKept);
+            triples[3 * pos + 1] = e.x;
+            triples[3 * pos + 2] = e.y;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void count_targets_kernel(const int32_t *__restrict__ triples, uint64_t n, uint32_t lo, uint32_t hi,
+                                     uint32_t *indeg) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t) triples[3 * i + 1];
+        if (c >= lo && c < hi) atomicAdd(indeg + (c - lo), 1u);
+    }
+}
+
+__global__ void scatter_rev_slots_kernel(const int2 *__restrict__ fwd, uint32_t b_lo, uint64_t n_slots, uint32_t c_lo,
+                                         uint32_t c_hi, const uint32_t *__restrict__ rev_off, uint32_t *cursor,
+                                         int2 *__restrict__ rev) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t) gridDim.x * blockDim.x) {
+        const int2 e = fwd[i];
+        if (e.x < 0) continue;
+        const uint32_t c = (uint32_t) e.x;
+        if (c < c_lo || c >= c_hi) continue;
+        const uint32_t pos = rev_off[c - c_lo] + atomicSub(cursor + (c - c_lo), 1u) - 1u;
+        rev[pos] = make_int2((int32_t) (b_lo + i / kSmallEdgesKept), e.y);
+    }
+}
+
+__global__ void scatter_rev_triples_kernel(const int32_t *__restrict__ triples, uint64_t n, uint32_t c_lo, uint32_t c_hi,
+                                           const uint32_t *__restrict__ rev_off, uint32_t *cursor, int2 *__restrict__ rev) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t) triples[3 * i + 1];
+        if (c < c_lo || c >= c_hi) continue;
+        const uint32_t pos = rev_off[c - c_lo] + atomicSub(cursor + (c - c_lo), 1u) - 1u;
+        rev[pos] = make_int2(triples[3 * i], triples[3 * i + 2]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase 2 helpers.
+
+// In-neighbour list of one target read: entries (a, offset of c in a, len(a)).
+struct NbrList {
+    uint32_t *a;
+    uint32_t *o;
+    uint32_t *len;
+    uint32_t cap;
+};
+
+// Lane-local: among the suffix-index candidates of window (c, L), the smallest verified source read
+// b > floor (floor = -1 for the first call); *n_hits = number of verified candidates > floor.
+__device__ __forceinline__ uint32_t scan_hits(const ReadsDev &R, const SeedTable &T, const PsDev &P,
+                                              const uint32_t *__restrict__ pc, uint32_t c, int32_t L, int64_t floor_b,
+                                              int *n_hits) {
+    uint32_t best = kNone;
+    int nh = 0;
+    const uint64_t w = bits64(pc, 2u * (uint32_t) (L - P.seed_nt)) & P.seed_mask;
+    probe_seed(T, mix64(w), [&](uint32_t b) {
+        if (b == c || (int64_t) b <= floor_b) return;
+        const uint32_t lenb = R.len[b];
+        if ((int64_t) lenb - P.min_offset < L) return;
+        // suffix(b, L) == prefix(c, L)
+        if (!equal_bits_aligned(read_ptr(R, b), 2u * (lenb - (uint32_t) L), pc, 2u * (uint32_t) L)) return;
+        nh++;
+        if (b < best) best = b;
+    });
+    *n_hits = nh;
+    return best;
+}
+
+// Warp-cooperative replay of one accepted overlap (b -> c, overlap L): GraphCreatorPrefSuf.cpp:403-483.
+// Removes b itself and every in-neighbour a whose edge (a -> c) is implied by (a -> b) + (b -> c), i.e.
+// a[d .. d+o) == b[0 .. o) with d = offset(a,c) - o, then appends (b, o).  Returns false on overflow.
+__device__ __forceinline__ bool replay_hit(const ReadsDev &R, uint32_t b, int32_t L, NbrList &lst, uint32_t &cnt,
+                                           int lane) {
+    const uint32_t lenb = R.len[b];
+    const int32_t o = (int32_t) lenb - L;
+    const uint32_t *pb = read_ptr(R, b);
+    uint32_t w = 0;
+    for (uint32_t base = 0; base < cnt; base += 32) {
+        const uint32_t j = base + lane;
+        bool keep = false;
+        uint32_t a = 0, oa = 0, lena = 0;
+        if (j < cnt) {
+            a = lst.a[j];
+            oa = lst.o[j];
+            lena = lst.len[j];
+            bool rm = (a == b);
+            if (!rm && o > 0) {
+                const int64_t d = (int64_t) oa - o;
+                if (d >= 0 && (int64_t) lenb + d - (int64_t) lena >= 0)
+                    rm = equal_bits_aligned(read_ptr(R, a), 2u * (uint32_t) d, pb, 2u * (uint32_t) o);
+            }
+            keep = !rm;
+        }
+        const unsigned m = __ballot_sync(kFull, keep);
+        __syncwarp();
+        if (keep) {
+            const uint32_t pos = w + __popc(m & ((1u << lane) - 1u));
+            lst.a[pos] = a;
+            lst.o[pos] = oa;
+            lst.len[pos] = lena;
+        }
+        w += __popc(m);
+        __syncwarp();
+    }
+    if (w >= lst.cap) return false;
+    if (lane == 0) {
+        lst.a[w] = b;
+        lst.o[w] = (uint32_t) o;
+        lst.len[w] = lenb;
+    }
+    __syncwarp();
+    cnt = w + 1;
+    return true;
+}
+
+// Load row c of the reversed phase-1 graph and apply Graph::retainOnlySmallestOffset (Graph.cpp:348-387):
+// one entry per source read, smallest offset wins.  Returns false when the row does not fit.
+__device__ __forceinline__ bool load_rev_row(const ReadsDev &R, const int2 *__restrict__ row, uint32_t deg,
+                                             NbrList &lst, uint32_t &cnt, int lane) {
+    cnt = 0;
+    if (deg > lst.cap) return false;
+    for (uint32_t j = lane; j < deg; j += 32) {
+        const int2 e = row[j];
+        lst.a[j] = (uint32_t) e.x;
+        lst.o[j] = (uint32_t) e.y;
+        lst.len[j] = 0;
+    }
+    __syncwarp();
+    if (deg > 1) {
+        for (uint32_t j = lane; j < deg; j += 32) {
+            const uint32_t a = lst.a[j], o = lst.o[j];
+            bool dup = false;
+            for (uint32_t k = 0; k < deg; k++) {
+                if (k == j || lst.a[k] != a) continue;
+                const uint32_t ok = lst.o[k];
+                if (ok < o || (ok == o && k < j)) dup = true;
+            }
+            if (dup) lst.len[j] = kNone;
+        }
+        __syncwarp();
+    }
+    uint32_t w = 0;
+    for (uint32_t base = 0; base < deg; base += 32) {
+        const uint32_t j = base + lane;
+        bool keep = false;
+        uint32_t a = 0, o = 0;
+        if (j < deg) {
+            a = lst.a[j];
+            o = lst.o[j];
+            keep = lst.len[j] != kNone;
+        }
+        const unsigned m = __ballot_sync(kFull, keep);
+        __syncwarp();
+        if (keep) {
+            const uint32_t pos = w + __popc(m & ((1u << lane) - 1u));
+            lst.a[pos] = a;
+            lst.o[pos] = o;
+            lst.len[pos] = R.len[a];
+        }
+        w += __popc(m);
+        __syncwarp();
+    }
+    cnt = w;
+    return true;
+}
+
+// All of phase 2 for one target read c on one warp.  Returns false when the list overflowed.
+__device__ __forceinline__ bool phase2_target(const ReadsDev &R, const SeedTable &T, const PsDev &P, uint32_t c,
+                                              const int2 *__restrict__ row, uint32_t deg, NbrList &lst,
+                                              const Phase2Out &out, int lane) {
+    uint32_t cnt = 0;
+    if (!load_rev_row(R, row, deg, lst, cnt, lane)) return false;
+    const uint32_t lenc = R.len[c];
+    const int32_t l_lo = P.rs > P.lmin ? P.rs : P.lmin;
+    int64_t l_hi = lenc;
+    if (l_hi > P.max_l) l_hi = P.max_l;
+    if (lenc != 0 && flag_to(R, c) && l_hi >= l_lo) {
+        const uint32_t *pc = read_ptr(R, c);
+        for (int32_t l_base = l_lo; l_base <= (int32_t) l_hi; l_base += 32) {
+            const int32_t L = l_base + lane;
+            int nh = 0;
+            uint32_t bmin = kNone;
+            if (L <= (int32_t) l_hi) bmin = scan_hits(R, T, P, pc, c, L, -1, &nh);
+            unsigned m = __ballot_sync(kFull, nh > 0);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int32_t l_src = l_base + src;
+                int left = __shfl_sync(kFull, nh, src);
+                uint32_t b = __shfl_sync(kFull, bmin, src);
+                while (true) {
+                    if (!replay_hit(R, b, l_src, lst, cnt, lane)) return false;
+                    if (--left == 0) break;
+                    // several source reads share this (c, L): take them in ascending id order
+                    uint32_t nxt = kNone;
+                    if (lane == src) {
+                        int dummy;
+                        nxt = scan_hits(R, T, P, pc, c, l_src, (int64_t) b, &dummy);
+                    }
+                    b = __shfl_sync(kFull, nxt, src);
+                    if (b == kNone) break;
+                }
+            }
+        }
+    }
+    // emit the surviving in-neighbours of c as forward triples (a, c, offset)
+    if (cnt) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(out.n_edges, (unsigned long long) cnt);
+        base = __shfl_sync(kFull, base, 0);
+        for (uint32_t j = lane; j < cnt; j += 32) {
+            const unsigned long long pos = base + j;
+            const uint32_t a = lst.a[j];
+            if (pos < out.edge_cap) {
+                out.triples[3 * pos] = (int32_t) a;
+                out.triples[3 * pos + 1] = (int32_t) c;
+                out.triples[3 * pos + 2] = (int32_t) lst.o[j];
+            }
+            if (out.outdeg) atomicAdd(out.outdeg + a, 1u);
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
+__global__ void __launch_bounds__(kThreads)
+phase2_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, const uint32_t *__restrict__ rev_off,
+              const int2 *__restrict__ rev, int list_cap, Phase2Out out) {
+    extern __shared__ uint32_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    NbrList lst;
+    lst.a = smem + (size_t) wib * 3 * list_cap;
+    lst.o = lst.a + list_cap;
+    lst.len = lst.o + list_cap;
+    lst.cap = (uint32_t) list_cap;
+    const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib;
+    const uint32_t n_warps = gridDim.x * kWarpsPerBlock;
+    for (uint64_t cc = (uint64_t) lo + warp; cc < hi; cc += n_warps) {
+        const uint32_t c = (uint32_t) cc;
+        const uint32_t r0 = rev_off[c - lo], r1 = rev_off[c - lo + 1];
+        if (!phase2_target(R, T, P, c, rev + r0, r1 - r0, lst, out, lane)) {
+            if (lane == 0) out.spill_queue[atomicAdd(out.n_spill, 1u)] = c;
+        }
+        __syncwarp();
+    }
+}
+
+// spill path, pass 1: upper bound of the list length of each queued target = row size + accepted overlaps
+__global__ void __launch_bounds__(kThreads)
+phase2_count_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, const uint32_t *__restrict__ rev_off,
+                    const uint32_t *__restrict__ queue, uint32_t n_queue, uint32_t *__restrict__ caps) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const uint32_t n_warps = gridDim.x * kWarpsPerBlock;
+    for (uint32_t q = warp; q < n_queue; q += n_warps) {
+        const uint32_t c = queue[q];
+        const uint32_t lenc = R.len[c];
+        const int32_t l_lo = P.rs > P.lmin ? P.rs : P.lmin;
+        int64_t l_hi = lenc;
+        if (l_hi > P.max_l) l_hi = P.max_l;
+        uint32_t total = 0;
+        if (lenc != 0 && flag_to(R, c) && l_hi >= l_lo) {
+            const uint32_t *pc = read_ptr(R, c);
+            for (int32_t L = l_lo + lane; L <= (int32_t) l_hi; L += 32) {
+                int nh = 0;
+                scan_hits(R, T, P, pc, c, L, -1, &nh);
+                total += (uint32_t) nh;
+            }
+        }
+        for (int d = 16; d; d >>= 1) total += __shfl_xor_sync(kFull, total, d);
+        if (lane == 0) caps[q] = total + (rev_off[c - lo + 1] - rev_off[c - lo]) + 1u;
+    }
+}
+
+// spill path, pass 2: same replay with the list in global memory (capacity from pass 1)
+__global__ void __launch_bounds__(kThreads)
+phase2_spill_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, const uint32_t *__restrict__ rev_off,
+                    const int2 *__restrict__ rev, const uint32_t *__restrict__ queue, uint32_t n_queue,
+                    const uint64_t *__restrict__ spill_off, uint32_t *spill_store, Phase2Out out) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const uint32_t n_warps = gridDim.x * kWarpsPerBlock;
+    for (uint32_t q = warp; q < n_queue; q += n_warps) {
+        const uint32_t c = queue[q];
+        const uint64_t s0 = spill_off[q], s1 = spill_off[q + 1];
+        NbrList lst;
+        lst.cap = (uint32_t) (s1 - s0);
+        lst.a = spill_store + 3 * s0;
+        lst.o = lst.a + lst.cap;
+        lst.len = lst.o + lst.cap;
+        const uint32_t r0 = rev_off[c - lo], r1 = rev_off[c - lo + 1];
+        phase2_target(R, T, P, c, rev + r0, r1 - r0, lst, out, lane);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CSR assembly
+__global__ void count_sources_kernel(const int32_t *__restrict__ triples, uint64_t n, uint32_t lo, uint32_t hi, int swap,
+                                     uint32_t *outdeg) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t b = (uint32_t) triples[3 * i + (swap ? 1 : 0)];
+        if (b >= lo && b < hi) atomicAdd(outdeg + (b - lo), 1u);
+    }
+}
+
+__global__ void scatter_csr_kernel(const int32_t *__restrict__ triples, uint64_t n, uint32_t lo, uint32_t hi, int swap,
+                                   const uint64_t *__restrict__ row_off, uint32_t *cursor, int32_t *__restrict__ nbr,
+                                   int32_t *__restrict__ off) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t b = (uint32_t) triples[3 * i + (swap ? 1 : 0)];
+        if (b < lo || b >= hi) continue;
+        const uint64_t pos = row_off[b - lo] + atomicSub(cursor + (b - lo), 1u) - 1u;
+        nbr[pos] = triples[3 * i + (swap ? 0 : 1)];
+        off[pos] = triples[3 * i + 2];
+    }
+}
+
+__device__ __forceinline__ bool edge_less(int32_t n1, int32_t o1, int32_t n2, int32_t o2) {
+    return n1 < n2 || (n1 == n2 && o1 < o2);
+}
+
+__global__ void sort_rows_kernel(const uint64_t *__restrict__ row_off, uint32_t n_rows, int32_t *nbr, int32_t *off,
+                                 uint32_t *big_rows, uint32_t *n_big) {
+    for (uint64_t r = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; r < n_rows; r += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t s = row_off[r];
+        const uint32_t d = (uint32_t) (row_off[r + 1] - s);
+        if (d < 2) continue;
+        if (d > 32) {
+            big_rows[atomicAdd(n_big, 1u)] = (uint32_t) r;
+            continue;
+        }
+        for (uint32_t i = 1; i < d; i++) {
+            const int32_t kn = nbr[s + i], ko = off[s + i];
+            uint32_t j = i;
+            while (j > 0 && edge_less(kn, ko, nbr[s + j - 1], off[s + j - 1])) {
+                nbr[s + j] = nbr[s + j - 1];
+                off[s + j] = off[s + j - 1];
+                j--;
+            }
+            nbr[s + j] = kn;
+            off[s + j] = ko;
+        }
+    }
+}
+
+// rank sort of long rows, one block per row (entries of a row are distinct by (nbr, off) or tie-broken by index)
+__global__ void sort_big_rows_kernel(const uint64_t *__restrict__ row_off, const uint32_t *__restrict__ big_rows,
+                                     uint32_t n_big, int32_t *nbr, int32_t *off, int32_t *tmp_nbr, int32_t *tmp_off) {
+    for (uint32_t q = blockIdx.x; q < n_big; q += gridDim.x) {
+        const uint32_t r = big_rows[q];
+        const uint64_t s = row_off[r];
+        const uint32_t d = (uint32_t) (row_off[r + 1] - s);
+        for (uint32_t i = threadIdx.x; i < d; i += blockDim.x) {
+            const int32_t kn = nbr[s + i], ko = off[s + i];
+            uint32_t rank = 0;
+            for (uint32_t k = 0; k < d; k++) {
+                const int32_t n2 = nbr[s + k], o2 = off[s + k];
+                if (edge_less(n2, o2, kn, ko) || (n2 == kn && o2 == ko && k < i)) rank++;
+            }
+            tmp_nbr[s + rank] = kn;
+            tmp_off[s + rank] = ko;
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < d; i += blockDim.x) {
+            nbr[s + i] = tmp_nbr[s + i];
+            off[s + i] = tmp_off[s + i];
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exclusive scan: tile sums -> scan of tile sums (single block) -> per-tile scan.
+constexpr int kScanThreads = 512;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t *total, uint64_t *sh /*[33]*/) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t x = v;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t y = __shfl_up_sync(kFull, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) sh[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t s = lane < (int) (blockDim.x >> 5) ? sh[lane] : 0;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t y = __shfl_up_sync(kFull, s, d);
+            if (lane >= d) s += y;
+        }
+        sh[lane] = s;  // inclusive warp totals
+    }
+    __syncthreads();
+    const uint64_t warp_base = wid ? sh[wid - 1] : 0;
+    *total = sh[(blockDim.x >> 5) - 1];
+    __syncthreads();
+    return warp_base + x - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint32_t *__restrict__ in, uint64_t n,
+                                                                      uint64_t *__restrict__ tile_sums) {
+    __shared__ uint64_t sh[33];
+    const uint64_t base = (uint64_t) blockIdx.x * kScanTile;
+    uint64_t v = 0;
+    for (int k = 0; k < kScanItems; k++) {
+        const uint64_t i = base + (uint64_t) k * kScanThreads + threadIdx.x;
+        if (i < n) v += in[i];
+    }
+    uint64_t total;
+    block_exclusive_scan(v, &total, sh);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(uint64_t *tile_sums, uint64_t n_tiles) {
+    __shared__ uint64_t sh[33];
+    uint64_t carry = 0;
+    for (uint64_t base = 0; base < n_tiles; base += kScanThreads) {
+        const uint64_t i = base + threadIdx.x;
+        const uint64_t v = i < n_tiles ? tile_sums[i] : 0;
+        uint64_t total;
+        const uint64_t ex = block_exclusive_scan(v, &total, sh);
+        if (i < n_tiles) tile_sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) tile_sums[n_tiles] = carry;
+}
+
+template <class OutT>
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t *__restrict__ in, OutT *__restrict__ out,
+                                                                  uint64_t n, const uint64_t *__restrict__ tile_sums,
+                                                                  uint64_t n_tiles) {
+    __shared__ uint64_t sh[33];
+    const uint64_t base = (uint64_t) blockIdx.x * kScanTile + (uint64_t) threadIdx.x * kScanItems;
+    uint32_t item[kScanItems];
+    uint64_t v = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        item[k] = base + k < n ? in[base + k] : 0u;
+        v += item[k];
+    }
+    uint64_t total;
+    uint64_t run = tile_sums[blockIdx.x] + block_exclusive_scan(v, &total, sh);
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        if (base + k < n) out[base + k] = (OutT) run;
+        run += item[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = (OutT) tile_sums[n_tiles];
+}
+
+__global__ void fill_u64_kernel(uint64_t *p, uint64_t v, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace
+
+// ================================================================================================
+// launchers
+
+void launch_read_stats(const ReadsDev &R, int lmin, int min_offset, ReadStats *d_stats, cudaStream_t s,
+                       const LaunchCfg &cfg) {
+    cudaMemsetAsync(d_stats, 0, sizeof(ReadStats), s);
+    read_stats_kernel<<<grid_for(R.n, 256, cfg), 256, 0, s>>>(R, lmin, min_offset, d_stats);
+    bump(cfg);
+}
+
+void launch_build_index(const ReadsDev &R, const PsDev &P, SeedTable prefix, SeedTable suffix, cudaStream_t s,
+                        const LaunchCfg &cfg) {
+    build_index_kernel<<<grid_for(R.n, 256, cfg), 256, 0, s>>>(R, P, prefix, suffix);
+    bump(cfg);
+}
+
+void launch_phase1(const ReadsDev &R, const SeedTable &prefix, const PsDev &P, uint32_t lo, uint32_t hi, int2 *fwd,
+                   uint32_t *indeg, cudaStream_t s, const LaunchCfg &cfg) {
+    if (hi <= lo) return;
+    phase1_kernel<<<grid_for(hi - lo, kWarpsPerBlock, cfg, 8), kThreads, 0, s>>>(R, prefix, P, lo, hi, fwd, indeg);
+    bump(cfg);
+}
+
+void launch_compact_slots(const int2 *fwd, uint32_t lo, uint32_t hi, int32_t *triples, unsigned long long *d_count,
+                          cudaStream_t s, const LaunchCfg &cfg) {
+    if (hi <= lo) return;
+    const uint64_t n_slots = (uint64_t) (hi - lo) * kSmallEdgesKept;
+    compact_slots_kernel<<<grid_for(n_slots, 256, cfg), 256, 0, s>>>(fwd, lo, n_slots, triples, d_count);
+    bump(cfg);
+}
+
+void launch_count_targets(const int32_t *triples, uint64_t n, uint32_t lo, uint32_t hi, uint32_t *indeg,
+                          cudaStream_t s, const LaunchCfg &cfg) {
+    if (!n) return;
+    count_targets_kernel<<<grid_for(n, 256, cfg), 256, 0, s>>>(triples, n, lo, hi, indeg);
+    bump(cfg);
+}
+
+void launch_scatter_rev_slots(const int2 *fwd, uint32_t b_lo, uint32_t b_hi, uint32_t c_lo, uint32_t c_hi,
+                              const uint32_t *rev_off, uint32_t *cursor, int2 *rev, cudaStream_t s,
+                              const LaunchCfg &cfg) {
+    if (b_hi <= b_lo) return;
+    const uint64_t n_slots = (uint64_t) (b_hi - b_lo) * kSmallEdgesKept;
+    scatter_rev_slots_kernel<<<grid_for(n_slots, 256, cfg), 256, 0, s>>>(fwd, b_lo, n_slots, c_lo, c_hi, rev_off,
+                                                                           cursor, rev);
+    bump(cfg);
+}
+
+void launch_scatter_rev_triples(const int32_t *triples, uint64_t n, uint32_t c_lo, uint32_t c_hi,
+                                const uint32_t *rev_off, uint32_t *cursor, int2 *rev, cudaStream_t s,
+                                const LaunchCfg &cfg) {
+    if (!n) return;
+    scatter_rev_triples_kernel<<<grid_for(n, 256, cfg), 256, 0, s>>>(triples, n, c_lo, c_hi, rev_off, cursor, rev);
+    bump(cfg);
+}
+
+void launch_phase2(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo, uint32_t hi,
+                   const uint32_t *rev_off, const int2 *rev, int list_cap, const Phase2Out &out, cudaStream_t s,
+                   const LaunchCfg &cfg) {
+    if (hi <= lo) return;
+    const size_t smem = (size_t) kWarpsPerBlock * 3 * list_cap * sizeof(uint32_t);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    phase2_kernel<<<grid_for(hi - lo, kWarpsPerBlock, cfg, 8), kThreads, smem, s>>>(R, suffix, P, lo, hi, rev_off, rev,
+                                                                                      list_cap, out);
+    bump(cfg);
+}
+
+void launch_phase2_count(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo,
+                         const uint32_t *rev_off, const uint32_t *queue, uint32_t n_queue, uint32_t *caps,
+                         cudaStream_t s, const LaunchCfg &cfg) {
+    if (!n_queue) return;
+    phase2_count_kernel<<<grid_for(n_queue, kWarpsPerBlock, cfg, 8), kThreads, 0, s>>>(R, suffix, P, lo, rev_off, queue,
+                                                                                         n_queue, caps);
+    bump(cfg);
+}
+
+void launch_phase2_spill(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo,
+                         const uint32_t *rev_off, const int2 *rev, const uint32_t *queue, uint32_t n_queue,
+                         const uint64_t *spill_off, uint32_t *spill_store, const Phase2Out &out, cudaStream_t s,
+                         const LaunchCfg &cfg) {
+    if (!n_queue) return;
+    phase2_spill_kernel<<<grid_for(n_queue, kWarpsPerBlock, cfg, 8), kThreads, 0, s>>>(
+        R, suffix, P, lo, rev_off, rev, queue, n_queue, spill_off, spill_store, out);
+    bump(cfg);
+}
+
+void launch_count_sources(const int32_t *triples, uint64_t n, uint32_t lo, uint32_t hi, int swap, uint32_t *outdeg,
+                          cudaStream_t s, const LaunchCfg &cfg) {
+    if (!n) return;
+    count_sources_kernel<<<grid_for(n, 256, cfg), 256, 0, s>>>(triples, n, lo, hi, swap, outdeg);
+    bump(cfg);
+}
+
+void launch_scatter_csr(const int32_t *triples, uint64_t n, uint32_t lo, uint32_t hi, int swap, const uint64_t *row_off,
+                        uint32_t *cursor, int32_t *nbr, int32_t *off, cudaStream_t s, const LaunchCfg &cfg) {
+    if (!n) return;
+    scatter_csr_kernel<<<grid_for(n, 256, cfg), 256, 0, s>>>(triples, n, lo, hi, swap, row_off, cursor, nbr, off);
+    bump(cfg);
+}
+
+void launch_sort_rows(const uint64_t *row_off, uint32_t n_rows, int32_t *nbr, int32_t *off, uint32_t *big_rows,
+                      uint32_t *n_big, cudaStream_t s, const LaunchCfg &cfg) {
+    if (!n_rows) return;
+    sort_rows_kernel<<<grid_for(n_rows, 256, cfg), 256, 0, s>>>(row_off, n_rows, nbr, off, big_rows, n_big);
+    bump(cfg);
+}
+
+void launch_sort_big_rows(const uint64_t *row_off, const uint32_t *big_rows, uint32_t n_big, int32_t *nbr, int32_t *off,
+                          int32_t *tmp_nbr, int32_t *tmp_off, cudaStream_t s, const LaunchCfg &cfg) {
+    if (!n_big) return;
+    sort_big_rows_kernel<<<grid_for(n_big, 1, cfg, 8), 256, 0, s>>>(row_off, big_rows, n_big, nbr, off, tmp_nbr,
+                                                                      tmp_off);
+    bump(cfg);
+}
+
+size_t scan_workspace_bytes(uint64_t n) {
+    const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
+    return (size_t) (tiles + 2) * sizeof(uint64_t);
+}
+
+template <class OutT>
+static void launch_scan_impl(const uint32_t *in, OutT *out, uint64_t n, void *workspace, cudaStream_t s,
+                             const LaunchCfg &cfg) {
+    uint64_t *tile_sums = (uint64_t *) workspace;
+    const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
+    if (n == 0) {
+        cudaMemsetAsync(out, 0, sizeof(OutT), s);
+        return;
+    }
+    scan_tile_sums_kernel<<<(unsigned) tiles, kScanThreads, 0, s>>>(in, n, tile_sums);
+    scan_spine_kernel<<<1, kScanThreads, 0, s>>>(tile_sums, tiles);
+    scan_apply_kernel<OutT><<<(unsigned) tiles, kScanThreads, 0, s>>>(in, out, n, tile_sums, tiles);
+    bump(cfg);
+    bump(cfg);
+    bump(cfg);
+}
+
+void launch_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, void *workspace, cudaStream_t s,
+                     const LaunchCfg &cfg) {
+    launch_scan_impl<uint32_t>(in, out, n, workspace, s, cfg);
+}
+void launch_scan_u64(const uint32_t *in, uint64_t *out, uint64_t n, void *workspace, cudaStream_t s,
+                     const LaunchCfg &cfg) {
+    launch_scan_impl<uint64_t>(in, out, n, workspace, s, cfg);
+}
+
+void launch_fill_u64(uint64_t *p, uint64_t v, uint64_t n, cudaStream_t s, const LaunchCfg &cfg) {
+    if (!n) return;
+    fill_u64_kernel<<<grid_for(n, 256, cfg), 256, 0, s>>>(p, v, n);
+    bump(cfg);
+}
+
+}  // namespace alga

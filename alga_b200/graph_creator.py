@@ -1,0 +1,148 @@
+"""Host-side mirror of the reference's graph-creator interface over the C ABI.
+
+``GraphCreatorPrefSuf`` follows the reference class of the same name
+(``include/GraphCreators/GraphCreator.h:12-62``, ``include/GraphCreators/GraphCreatorPrefSuf.h:22-28``):
+constructed from the read set, ``setAlignFrom`` / ``setAlignTo`` / ``getAlignFrom`` / ``getAlignTo``,
+``startAlignmentGraphCreation()``, ``clear()``.  The result is what ``Graph::V`` holds after
+``main.cpp:282-291`` (graph creation + ``retainOnlySmallestOffset``), as a CSR.
+
+All compute happens in ``libalga_gpu.so`` (hand-written CUDA, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from .readset import ReadSet
+
+
+@dataclass
+class Graph:
+    """Forward adjacency: row b holds (nbr, off) = "read nbr starts at position off of read b"."""
+
+    n: int
+    row_off: np.ndarray  # uint64, n+1
+    nbr: np.ndarray  # int32, E
+    off: np.ndarray  # int32, E
+
+    @property
+    def n_edges(self) -> int:
+        return int(self.nbr.shape[0])
+
+    def edges(self) -> np.ndarray:
+        """(E, 3) int32 array of (src, dst, offset) sorted by (src, dst)."""
+        deg = np.diff(self.row_off.astype(np.int64))
+        src = np.repeat(np.arange(self.n, dtype=np.int32), deg)
+        return np.stack([src, self.nbr, self.off], axis=1).astype(np.int32)
+
+    def neighbors(self, b: int):
+        s, e = int(self.row_off[b]), int(self.row_off[b + 1])
+        return list(zip(self.nbr[s:e].tolist(), self.off[s:e].tolist()))
+
+
+def _reads_struct(reads: ReadSet, stride_hint: bool = True) -> _lib.Reads:
+    n = reads.n
+    stride = 0
+    word_off = reads.word_off.ctypes.data
+    if stride_hint and n:
+        # fixed-stride layout lets the library skip the offset array (alga_gpu.h: word_off == NULL)
+        w = int(reads.word_off[1] - reads.word_off[0]) if n else 0
+        if w > 0 and np.array_equal(reads.word_off, np.arange(n + 1, dtype=np.uint64) * np.uint64(w)):
+            stride, word_off = w, None
+    return _lib.Reads(n, reads.words.ctypes.data, word_off, stride, reads.len_nt.ctypes.data,
+                      reads.align_from.ctypes.data, reads.align_to.ctypes.data)
+
+
+def _csr_to_graph(csr: _lib.Csr) -> Graph:
+    n, e = csr.n_reads, csr.n_edges
+    row_off = np.ctypeslib.as_array(csr.row_off, shape=(n + 1,)).copy()
+    if e:
+        nbr = np.ctypeslib.as_array(csr.nbr, shape=(e,)).copy()
+        off = np.ctypeslib.as_array(csr.off, shape=(e,)).copy()
+    else:
+        nbr = np.zeros(0, np.int32)
+        off = np.zeros(0, np.int32)
+    return Graph(n, row_off, nbr, off)
+
+
+class GraphCreatorPrefSuf:
+    """Drop-in for the reference's ``GraphCreatorPrefSuf`` (GraphCreatorPrefSuf.cpp:15-126)."""
+
+    def __init__(self, reads: ReadSet, min_overlap: int, rs_min_overlap: int, min_offset: int = 0,
+                 max_len_cap: int = 500, device: int = 0, list_cap: int = 0):
+        self.reads = reads
+        self.params = _lib.PsParams(min_overlap, rs_min_overlap, min_offset, max_len_cap, device, list_cap)
+        # GraphCreator::GraphCreator (GraphCreator.cpp:9-17): flags start as true for every read
+        self.alignFrom = reads.align_from.copy()
+        self.alignTo = reads.align_to.copy()
+        self.graph: Graph | None = None
+        self.timing: dict | None = None
+
+    # GraphCreator.h:22-43
+    def setAlignTo(self, i: int, val: bool):
+        self.alignTo[i] = 1 if val else 0
+
+    def setAlignFrom(self, i: int, val: bool):
+        self.alignFrom[i] = 1 if val else 0
+
+    def getAlignFrom(self, i: int) -> bool:
+        return bool(self.alignFrom[i])
+
+    def getAlignTo(self, i: int) -> bool:
+        return bool(self.alignTo[i])
+
+    def startAlignmentGraphCreation(self) -> Graph:
+        """GraphCreatorPrefSuf.cpp:73-126 + Graph::retainOnlySmallestOffset (main.cpp:291)."""
+        lib = _lib.load()
+        rs = ReadSet(self.reads.words, self.reads.word_off, self.reads.len_nt, self.alignFrom, self.alignTo)
+        st = _reads_struct(rs)
+        csr = _lib.Csr()
+        tm = _lib.Timing()
+        _lib.check(lib.alga_gpu_prefsuf_build(C.byref(st), C.byref(self.params), C.byref(csr), C.byref(tm)))
+        try:
+            self.graph = _csr_to_graph(csr)
+        finally:
+            lib.alga_gpu_free_csr(C.byref(csr))
+        self.timing = {k: getattr(tm, k) for k, _ in _lib.Timing._fields_}
+        return self.graph
+
+    def clear(self):
+        """GraphCreatorPrefSuf::clear (GraphCreatorPrefSuf.cpp:62-71): drop the working state."""
+        self.graph = None
+
+
+def fingerprints(reads: ReadSet, L: int, device: int = 0):
+    """(pre64, pre32, suf64, suf32) of every read with len >= L (GraphCreatorPrefSuf.cpp:213-236)."""
+    lib = _lib.load()
+    n = reads.n
+    p64 = np.zeros(n, np.uint64); p32 = np.zeros(n, np.uint32)
+    s64 = np.zeros(n, np.uint64); s32 = np.zeros(n, np.uint32)
+    st = _reads_struct(reads)
+    _lib.check(lib.alga_gpu_fingerprints(C.byref(st), L, device, p64.ctypes.data, p32.ctypes.data, s64.ctypes.data,
+                                         s32.ctypes.data))
+    return p64, p32, s64, s32
+
+
+def pack_reads(ascii_reads: np.ndarray, device: int = 0) -> np.ndarray:
+    """2-bit pack an (n, len) uint8 matrix of ASCII nucleotides (Read::createSequence, Read.cpp:40-68)."""
+    lib = _lib.load()
+    a = np.ascontiguousarray(ascii_reads, dtype=np.uint8)
+    n, ln = a.shape
+    words = np.zeros((n, (ln + 15) // 16), np.uint32)
+    _lib.check(lib.alga_gpu_pack_reads(a.ctypes.data, n, ln, device, words.ctypes.data))
+    return words
+
+
+def verify_pairs(reads: ReadSet, pairs: np.ndarray, threshold_pct: int, max_offset_pct: int, min_overlap_area: int,
+                 min_offset: int = 0, same_ends: int = 3, device: int = 0) -> np.ndarray:
+    """Batch ``AlignmentControllerHybrid::canAlign`` (AlignmentControllerHybrid.cpp:46-83)."""
+    lib = _lib.load()
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 3)
+    out = np.zeros(pairs.shape[0], np.uint8)
+    st = _reads_struct(reads)
+    vp = _lib.VerifyParams(max_offset_pct, min_offset, min_overlap_area, threshold_pct, same_ends, device)
+    _lib.check(lib.alga_gpu_verify_pairs(C.byref(st), pairs.ctypes.data, pairs.shape[0], C.byref(vp), out.ctypes.data))
+    return out

@@ -1,0 +1,162 @@
+/* alga_gpu.h -- C ABI of libalga_gpu.so: the B200 (sm_100a) overlap-graph hot path of ALGA.
+ *
+ * Every entry point replaces one piece of the reference's CPU hot path and is what a binding of
+ * that path (the C++ shim in shim/, cgo, JNI, ctypes ...) would call.  Plain pointers and sizes
+ * only; no CUDA or torch types.  All functions return 0 on success and a negative ALGA_E_* code
+ * on failure; alga_gpu_last_error() returns a thread-local message.  There is no CPU fallback:
+ * without a CUDA device every compute entry point fails with ALGA_E_CUDA.
+ *
+ * Packed read layout = the reference's Bitset/Read layout (include/DataStructures/Bitset.h:38-45,
+ * src/DataStructures/Read.cpp:40-68): A=0 C=1 G=2 T=3, nucleotide j in bits [2(j%16), 2(j%16)+1]
+ * of 32-bit block j/16, tail bits zero.  len_nt[i] == 0 marks a removed (nullptr) read.
+ */
+#ifndef ALGA_GPU_H
+#define ALGA_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALGA_OK 0
+#define ALGA_E_INVALID (-1)  /* bad argument */
+#define ALGA_E_CUDA (-2)     /* CUDA runtime error / no device */
+#define ALGA_E_NOMEM (-3)    /* host or device allocation failed */
+#define ALGA_E_CAPACITY (-4) /* internal buffer overflow that a retry could not fix */
+
+/* ---- read set --------------------------------------------------------------------------- */
+/* Replaces the vector<Read*>* argument of GraphCreator::GraphCreator (GraphCreator.cpp:9-17) plus the
+ * alignFrom/alignTo bit vectors (GraphCreator.h:46-62).  Host or device pointers depending on the
+ * entry point.  word_off may be NULL when every read occupies exactly stride_words blocks
+ * (read i starts at block i*stride_words). */
+typedef struct {
+    uint32_t n_reads;           /* N = G->size() */
+    const uint32_t *words;      /* concatenated Bitset blocks (Bitset.h:175 getBlock) */
+    const uint64_t *word_off;   /* N+1 block offsets, or NULL with stride_words > 0 */
+    uint32_t stride_words;      /* blocks per read when word_off == NULL */
+    const uint32_t *len_nt;     /* N read lengths in nucleotides (Read::size), 0 = nullptr read */
+    const uint8_t *align_from;  /* N flags, may be NULL (= all true) -- GraphCreator::setAlignFrom */
+    const uint8_t *align_to;    /* N flags, may be NULL (= all true) -- GraphCreator::setAlignTo */
+} alga_reads;
+
+/* ---- GraphCreatorPrefSuf ---------------------------------------------------------------- */
+/* The Params statics GraphCreatorPrefSuf reads: */
+typedef struct {
+    int32_t min_overlap;      /* Params::MIN_OVERLAP_PREF_SUF  (main.cpp:103-107) */
+    int32_t rs_min_overlap;   /* Params::REMOVE_SMALL_OVERLAP_EDGES_MIN_OVERLAP (main.cpp:108) */
+    int32_t min_offset;       /* Params::MIN_OFFSET_FOR_ALIGNMENT (Params.cpp:709), default 0 */
+    int32_t max_len_cap;      /* overlap length cap, 500 in GraphCreatorPrefSuf.cpp:92; <=0 means 500 */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t list_cap;         /* tuning/testing: on-chip in-neighbour list capacity per target read;
+                                 <=0 = default.  Targets that exceed it take the global-memory path. */
+} alga_ps_params;
+
+/* Forward adjacency in CSR form: row b lists (nbr[k], off[k]) for row_off[b] <= k < row_off[b+1],
+ * meaning "read nbr starts at position off of read b" -- exactly what Graph::V[b] holds after
+ * main.cpp:282-291 (startAlignmentGraphCreation + retainOnlySmallestOffset): rows sorted by nbr,
+ * one entry per nbr.  Library-allocated (host); release with alga_gpu_free_csr. */
+typedef struct {
+    uint32_t n_reads;
+    uint64_t n_edges;
+    uint64_t *row_off; /* N+1 */
+    int32_t *nbr;      /* E */
+    int32_t *off;      /* E */
+} alga_csr;
+
+typedef struct {
+    double h2d_ms;     /* host -> device copies */
+    double device_ms;  /* CUDA-event time: packed reads resident -> CSR resident */
+    double d2h_ms;     /* device -> host copies */
+    double total_ms;   /* wall time of the call */
+    uint64_t kernel_launches;
+    uint64_t n_spilled_targets; /* targets that took the global-memory list path */
+} alga_timing;
+
+/* One-call drop-in for GraphCreatorPrefSuf::startAlignmentGraphCreation (GraphCreatorPrefSuf.cpp:73-126)
+ * followed by Graph::retainOnlySmallestOffset (main.cpp:291).  Host buffers in, host CSR out. */
+int alga_gpu_prefsuf_build(const alga_reads *reads, const alga_ps_params *params, alga_csr *out,
+                           alga_timing *timing /* may be NULL */);
+void alga_gpu_free_csr(alga_csr *csr);
+
+/* ---- staged, device-resident interface (bench, multi-GPU harness) ------------------------- */
+/* A plan owns the device workspace of one GPU.  Device pointers passed in are borrowed. */
+typedef struct alga_ps_plan alga_ps_plan;
+
+int alga_ps_plan_create(alga_ps_plan **plan, const alga_ps_params *params);
+void alga_ps_plan_destroy(alga_ps_plan *plan);
+/* Bind a read set that is already resident on the plan's device (all pointers are device pointers;
+ * `words` must be followed by at least 16 readable bytes).  max_len_nt = longest read (calculateMaxReadLength,
+ * GraphCreatorPrefSuf.cpp:52-56); pass 0 to have it computed on the device. */
+int alga_ps_plan_bind_reads_device(alga_ps_plan *plan, const alga_reads *dev_reads, uint32_t max_len_nt);
+/* Copy a host read set to the device and bind it. */
+int alga_ps_plan_upload_reads(alga_ps_plan *plan, const alga_reads *host_reads);
+
+/* Whole single-GPU pipeline on `stream` (a cudaStream_t passed as void*, NULL = default stream):
+ * seed index build, phase 1 (L < rs_min_overlap), transpose, phase 2 (L >= rs_min_overlap) with
+ * transitive reduction, CSR assembly.  Asynchronous except for a few scalar read-backs. */
+int alga_ps_plan_run(alga_ps_plan *plan, void *stream);
+
+/* Stages of the same pipeline for key-range / id-range sharding across GPUs (one process per GPU;
+ * the exchange between stages is done by the caller, e.g. with torch.distributed all_to_all over NCCL).
+ * Ranges are read-id ranges [lo, hi) owned by this rank. */
+int alga_ps_stage_index(alga_ps_plan *plan, void *stream);
+/* phase 1 for suffix reads b in [lo,hi): emits (b, c, offset) int32 triples, device-resident.  */
+int alga_ps_stage_phase1(alga_ps_plan *plan, uint32_t lo, uint32_t hi, void *stream,
+                         const int32_t **dev_triples, uint64_t *n_triples);
+/* phase 2 for target reads c in [lo,hi) given the phase-1 triples whose target lies in [lo,hi)
+ * (device pointer, any order); emits the surviving (b, c, offset) triples, device-resident. */
+int alga_ps_stage_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int32_t *dev_triples_in,
+                         uint64_t n_in, void *stream, const int32_t **dev_triples_out, uint64_t *n_out);
+/* CSR assembly for source reads b in [lo,hi) from (b, c, offset) triples (device pointer, any order).
+ * With swap_direction != 0 the triples are inserted as (c -> b) instead (the RS > maxL+1 corner of the
+ * reference, SURVEY.md A.1 note 2). */
+int alga_ps_stage_csr(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int32_t *dev_triples, uint64_t n,
+                      int swap_direction, void *stream);
+
+/* Result of the last run / stage_csr: device pointers (row_off has hi-lo+1 entries, relative to lo). */
+int alga_ps_plan_result_device(alga_ps_plan *plan, const uint64_t **row_off, const int32_t **nbr,
+                               const int32_t **off, uint64_t *n_edges);
+/* Copy the result to freshly allocated host arrays. */
+int alga_ps_plan_result_host(alga_ps_plan *plan, alga_csr *out);
+/* Counters of the last run. */
+int alga_ps_plan_stats(alga_ps_plan *plan, alga_timing *timing);
+
+/* ---- fingerprints (GraphCreatorPrefSuf::updatePrefixHash / updateSuffixHash, :213-236) ---- */
+/* For every read i with len >= L: pre64/pre32 = fingerprints of its length-L prefix, suf64/suf32 of its
+ * length-L suffix, h64 = sum s_j 4^j mod 10^18+3, h32 = sum s_j 4^j mod 10^9+7 (Params.cpp:721,
+ * GraphCreatorPrefSuf.h:42).  Host buffers; entries of shorter reads are left untouched. */
+int alga_gpu_fingerprints(const alga_reads *reads, int32_t L, int32_t device, uint64_t *pre64, uint32_t *pre32,
+                          uint64_t *suf64, uint32_t *suf32);
+
+/* ---- 2-bit packing (Read::createSequence, Read.cpp:40-68) ----------------------------------- */
+/* ascii: n_reads sequences of fixed length len_nt stored back to back (no separators); words: n_reads *
+ * ceil(len_nt/16) blocks.  Host buffers. */
+int alga_gpu_pack_reads(const uint8_t *ascii, uint32_t n_reads, uint32_t len_nt, int32_t device, uint32_t *words);
+
+/* ---- candidate verification (AlignmentControllerHybrid::canAlign, AlignmentControllerHybrid.cpp:46-83
+ *      -> AlignmentControllerLowErrorRate::canAlign, AlignmentControllerLowErrorRate.cpp:15-49) ---- */
+typedef struct {
+    int32_t max_offset_pct;   /* Params::MAX_OFFSET_CONSIDERED_FOR_ALIGNMENT */
+    int32_t min_offset;       /* Params::MIN_OFFSET_FOR_ALIGNMENT */
+    int32_t min_overlap_area; /* Params::MIN_OVERLAP_AREA */
+    int32_t threshold_pct;    /* Params::MINIMAL_OVERLAP_FOR_LCS_LOW_ERROR */
+    int32_t same_ends;        /* Params::ALIGNMENT_CONTROLLER_SAME_ENDS_LENGTH */
+    int32_t device;
+} alga_verify_params;
+
+/* pairs: n_pairs x (a, b, offset) int32 triples; verdict[i] = canAlign(reads[a], reads[b], offset).
+ * One candidate pair per warp.  Host buffers. */
+int alga_gpu_verify_pairs(const alga_reads *reads, const int32_t *pairs, uint64_t n_pairs,
+                          const alga_verify_params *params, uint8_t *verdict);
+
+/* ---- misc ---------------------------------------------------------------------------------- */
+int alga_gpu_device_count(void);
+const char *alga_gpu_last_error(void);
+const char *alga_gpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALGA_GPU_H */
