@@ -39,7 +39,7 @@ class Csr(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("device_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
-                ("kernel_launches", C.c_uint64), ("n_spilled_targets", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("n_spilled_targets", C.c_uint64), ("stage_ms", C.c_double * 8)]
 
 
 class VerifyParams(C.Structure):
@@ -63,6 +63,7 @@ SYMBOLS = {
                                        C.POINTER(C.c_uint64)]),
     "alga_ps_stage_csr": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint64, C.c_int, _P]),
     "alga_ps_plan_result_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    "alga_ps_plan_result_rows": (C.c_uint32, [_P]),
     "alga_ps_plan_result_host": (C.c_int, [_P, C.POINTER(Csr)]),
     "alga_ps_plan_stats": (C.c_int, [_P, C.POINTER(Timing)]),
     "alga_gpu_fingerprints": (C.c_int, [C.POINTER(Reads), C.c_int32, C.c_int32, _P, _P, _P, _P]),

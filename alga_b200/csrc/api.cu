@@ -114,7 +114,9 @@ struct alga_ps_plan {
     uint32_t res_lo = 0, res_hi = 0;
     uint64_t n_edges = 0;
     double last_device_ms = 0;
+    double stage_ms[8] = {0};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     ~alga_ps_plan() {
         DevBuf *all[] = {&words, &word_off, &len, &from, &to, &stats_d, &counters_d, &tp, &ts, &fwd, &indeg, &rev_off, &rev,
@@ -126,6 +128,8 @@ struct alga_ps_plan {
         if (h_u64) cudaFreeHost(h_u64);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        for (cudaEvent_t e : ev_stage)
+            if (e) cudaEventDestroy(e);
     }
 };
 
@@ -338,6 +342,7 @@ int alga_ps_plan_create(alga_ps_plan **out, const alga_ps_params *params) {
         CK(cudaMallocHost((void **) &plan->h_u64, 8));
         CK(cudaEventCreate(&plan->ev0));
         CK(cudaEventCreate(&plan->ev1));
+        for (cudaEvent_t &e : plan->ev_stage) CK(cudaEventCreate(&e));
         CKR(plan->counters_d.ensure(sizeof(Counters)));
         return ALGA_OK;
     }();
@@ -477,21 +482,25 @@ int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
     plan->spilled = 0;
     CK(cudaEventRecord(plan->ev0, s));
     CKR(stage_index(plan, s));
+    CK(cudaEventRecord(plan->ev_stage[0], s));
     // phase 1 with fused in-degree counting
     CKR(plan->fwd.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * sizeof(int2)));
     CKR(plan->indeg.ensure((size_t) (n ? n : 1) * 4));
     CK(cudaMemsetAsync(plan->indeg.p, 0, (size_t) (n ? n : 1) * 4, s));
     launch_phase1(plan->R, plan->Tp, plan->P, 0, n, plan->fwd.as<int2>(), plan->indeg.as<uint32_t>(), s, plan->cfg);
+    CK(cudaEventRecord(plan->ev_stage[1], s));
     // reversed phase-1 graph (rows by target)
     CKR(build_rev_from_counts(plan, n, s));
     CKR(plan->rev.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * sizeof(int2)));
     launch_scatter_rev_slots(plan->fwd.as<int2>(), 0, n, 0, n, plan->rev_off.as<uint32_t>(), plan->indeg.as<uint32_t>(),
                              plan->rev.as<int2>(), s, plan->cfg);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(plan->ev_stage[2], s));
     // phase 2 with fused out-degree counting (not in the reversed-result corner)
     CKR(plan->outdeg.ensure((size_t) (n ? n : 1) * 4));
     const bool fuse_outdeg = !plan->swap_direction;
     CKR(run_phase2(plan, 0, n, fuse_outdeg ? plan->outdeg.as<uint32_t>() : nullptr, s));
+    CK(cudaEventRecord(plan->ev_stage[3], s));
     CKR(stage_csr(plan, 0, n, plan->triples.as<int32_t>(), plan->h_counters->n_edges, plan->swap_direction ? 1 : 0,
                   fuse_outdeg, s));
     CK(cudaEventRecord(plan->ev1, s));
@@ -499,6 +508,11 @@ int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, plan->ev0, plan->ev1));
     plan->last_device_ms = ms;
+    cudaEvent_t marks[6] = {plan->ev0, plan->ev_stage[0], plan->ev_stage[1], plan->ev_stage[2], plan->ev_stage[3], plan->ev1};
+    for (int k = 0; k < 5; k++) {
+        CK(cudaEventElapsedTime(&ms, marks[k], marks[k + 1]));
+        plan->stage_ms[k] = ms;
+    }
     return ALGA_OK;
 }
 
@@ -511,6 +525,8 @@ int alga_ps_plan_result_device(alga_ps_plan *plan, const uint64_t **row_off, con
     if (n_edges) *n_edges = plan->n_edges;
     return ALGA_OK;
 }
+
+uint32_t alga_ps_plan_result_rows(alga_ps_plan *plan) { return plan ? plan->res_hi - plan->res_lo : 0u; }
 
 int alga_ps_plan_result_host(alga_ps_plan *plan, alga_csr *out) {
     if (!plan || !out) return fail(ALGA_E_INVALID, "null argument");
@@ -540,6 +556,7 @@ int alga_ps_plan_stats(alga_ps_plan *plan, alga_timing *t) {
     t->device_ms = plan->last_device_ms;
     t->kernel_launches = plan->launches;
     t->n_spilled_targets = plan->spilled;
+    for (int k = 0; k < 8; k++) t->stage_ms[k] = plan->stage_ms[k];
     return ALGA_OK;
 }
 

@@ -9,9 +9,12 @@ constexpr uint64_t kEmptySlot = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr int kSlotsPerBucket = 4;  // 4 x 8 B = one 32-byte DRAM sector
 constexpr int kSmallEdgesKept = 3;  // SOES, GraphCreatorPrefSuf.h:62
+constexpr int kHeadWords = 4;       // cached head of a read: first 64 nucleotides
+constexpr int kHeadNt = kHeadWords * 16;
+constexpr int kReadPadBytes = 256;  // readable bytes required after the packed words (speculative window loads)
 
-// Packed read set resident in HBM, reference layout (Bitset.h:38-45).  `words` is padded with at
-// least 16 readable bytes so that a 3-word window read at the very end stays in bounds.
+// Packed read set resident in HBM, reference layout (Bitset.h:38-45).  `words` is followed by at
+// least kReadPadBytes readable bytes so that window / compare loads near the end stay in bounds.
 struct ReadsDev {
     const uint32_t *__restrict__ words;
     const uint64_t *__restrict__ word_off;  // nullptr in fixed-stride mode
@@ -57,24 +60,55 @@ __device__ __forceinline__ uint64_t bits64(const uint32_t *__restrict__ p, uint3
 }
 
 // nbits of pa starting at bit offset bita == nbits of pb starting at word boundary 0 ?
+// Loads are issued 8 words at a time with no data-dependent branch in between, so that the (mostly
+// successful) comparisons cost one memory round trip per 128 nucleotides instead of one per word.
+// May read up to 9 words past the compared range (the read buffer is padded, see kReadPadBytes).
 __device__ __forceinline__ bool equal_bits_aligned(const uint32_t *__restrict__ pa, uint32_t bita,
                                                    const uint32_t *__restrict__ pb, uint32_t nbits) {
     const uint32_t s = bita & 31u;
     const uint32_t *q = pa + (bita >> 5);
-    uint32_t lo = __ldg(q);
-    uint32_t k = 0;
-    for (; k + 32 <= nbits; k += 32) {
-        const uint32_t hi = __ldg(q + (k >> 5) + 1);
-        if (__funnelshift_r(lo, hi, s) != __ldg(pb + (k >> 5))) return false;
-        lo = hi;
-    }
-    const uint32_t rem = nbits - k;
-    if (rem) {
-        const uint32_t hi = __ldg(q + (k >> 5) + 1);
-        const uint32_t m = (1u << rem) - 1u;
-        if ((__funnelshift_r(lo, hi, s) ^ __ldg(pb + (k >> 5))) & m) return false;
+    const uint32_t n_words = (nbits + 31u) >> 5;
+    for (uint32_t k0 = 0; k0 < n_words; k0 += 8) {
+        uint32_t wa[9], wb[8];
+#pragma unroll
+        for (int j = 0; j < 9; j++) wa[j] = (k0 + j <= n_words) ? __ldg(q + k0 + j) : 0u;
+#pragma unroll
+        for (int j = 0; j < 8; j++) wb[j] = (k0 + j < n_words) ? __ldg(pb + k0 + j) : 0u;
+        uint32_t diff = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t k = k0 + j;
+            uint32_t x = __funnelshift_r(wa[j], wa[j + 1], s) ^ wb[j];
+            const uint32_t bits_left = k < n_words ? nbits - 32u * k : 0u;
+            const uint32_t m = bits_left >= 32u ? 0xFFFFFFFFu : ((1u << bits_left) - 1u);
+            diff |= x & m;
+        }
+        if (diff) return false;
     }
     return true;
+}
+
+// Same test on cached 128-bit heads (first 64 nucleotides): bits [bita, bita+nbits) of `a` against bits
+// [0, nbits) of `b`; requires bita + nbits <= 128.
+__device__ __forceinline__ bool equal_bits_head(const uint32_t (&a)[4], uint32_t bita, const uint32_t (&b)[4],
+                                                uint32_t nbits) {
+    const uint32_t ws = bita >> 5, s = bita & 31u;
+    uint32_t diff = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        // word (ws + j) and (ws + j + 1) of a, zero beyond the head
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            if ((uint32_t) t == ws + j) lo = a[t];
+            if ((uint32_t) t == ws + j + 1) hi = a[t];
+        }
+        const uint32_t x = __funnelshift_r(lo, hi, s) ^ b[j];
+        const uint32_t bits_left = nbits > 32u * j ? nbits - 32u * j : 0u;
+        const uint32_t m = bits_left >= 32u ? 0xFFFFFFFFu : ((1u << bits_left) - 1u);
+        diff |= x & m;
+    }
+    return diff == 0;
 }
 
 // splitmix64-style finaliser over the 2K-bit seed window

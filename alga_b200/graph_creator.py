@@ -106,7 +106,8 @@ class GraphCreatorPrefSuf:
             self.graph = _csr_to_graph(csr)
         finally:
             lib.alga_gpu_free_csr(C.byref(csr))
-        self.timing = {k: getattr(tm, k) for k, _ in _lib.Timing._fields_}
+        self.timing = {k: getattr(tm, k) for k, _ in _lib.Timing._fields_ if k != "stage_ms"}
+        self.timing["stage_ms"] = dict(zip(("index", "phase1", "transpose", "phase2", "csr"), list(tm.stage_ms)[:5]))
         return self.graph
 
     def clear(self):

@@ -72,7 +72,16 @@ typedef struct {
     double total_ms;   /* wall time of the call */
     uint64_t kernel_launches;
     uint64_t n_spilled_targets; /* targets that took the global-memory list path */
+    /* CUDA-event time of each stage of alga_ps_plan_run on its stream (sums to ~device_ms):
+     * [0] seed index build, [1] phase 1 (L < rs), [2] transpose of the phase-1 graph,
+     * [3] phase 2 (L >= rs, transitive reduction), [4] CSR assembly, [5..7] reserved (0). */
+    double stage_ms[8];
 } alga_timing;
+#define ALGA_STAGE_INDEX 0
+#define ALGA_STAGE_PHASE1 1
+#define ALGA_STAGE_TRANSPOSE 2
+#define ALGA_STAGE_PHASE2 3
+#define ALGA_STAGE_CSR 4
 
 /* One-call drop-in for GraphCreatorPrefSuf::startAlignmentGraphCreation (GraphCreatorPrefSuf.cpp:73-126)
  * followed by Graph::retainOnlySmallestOffset (main.cpp:291).  Host buffers in, host CSR out. */
@@ -118,6 +127,8 @@ int alga_ps_stage_csr(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int32_
 /* Result of the last run / stage_csr: device pointers (row_off has hi-lo+1 entries, relative to lo). */
 int alga_ps_plan_result_device(alga_ps_plan *plan, const uint64_t **row_off, const int32_t **nbr,
                                const int32_t **off, uint64_t *n_edges);
+/* Number of rows (hi - lo) of the last result; 0 before any run. */
+uint32_t alga_ps_plan_result_rows(alga_ps_plan *plan);
 /* Copy the result to freshly allocated host arrays. */
 int alga_ps_plan_result_host(alga_ps_plan *plan, alga_csr *out);
 /* Counters of the last run. */

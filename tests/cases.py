@@ -94,3 +94,38 @@ def build_case(name):
 CASES = ["cfg1_small", "cfg2_small", "cfg3_small", "cfg5_small", "varlen", "varlen_dups", "rs_eq_lmin",
          "rs_below_lmin", "rs_eq_maxl_plus1", "rs_above_maxl", "min_offset", "flags", "nulls", "long_reads",
          "long_reads_rs", "periodic_dups", "periodic", "short_lmin", "tiny", "empty", "all_null"]
+
+
+def verify_case(seed=31, n_reads=4000, genome=20000, read_len=144, error=0.01):
+    """Candidate pairs for AlignmentControllerHybrid::canAlign: overlapping same-strand reads with 1 %
+    substitutions (true offsets, offsets off by one, random pairs), supplement parameters of config 3
+    (main.cpp:332-340: threshold 97 %, max offset 32 % of the read, min overlap area 111)."""
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, 4, size=genome, dtype=np.uint8)
+    lens = np.where(rng.random(n_reads) < 0.8, read_len, rng.integers(120, read_len + 1, size=n_reads))
+    pos = rng.integers(0, genome - read_len, size=n_reads)
+    order = np.argsort(pos, kind="stable")
+    pos, lens = pos[order], lens[order]
+    reads = []
+    for p, ln in zip(pos, lens):
+        r = g[p:p + ln].copy()
+        hit = rng.random(ln) < error
+        r = np.where(hit, (r + rng.integers(1, 4, size=ln)) & 3, r).astype(np.uint8)
+        reads.append(r)
+    rs = readset.from_code_list(reads)
+    pairs = []
+    for i in range(n_reads):
+        for j in range(i + 1, min(i + 12, n_reads)):
+            off = int(pos[j] - pos[i])
+            if off > 60:
+                break
+            pairs.append((i, j, off))
+            if rng.random() < 0.2:
+                pairs.append((i, j, off + int(rng.integers(-1, 2))))
+            if rng.random() < 0.1:
+                pairs.append((j, i, off))
+    for _ in range(2000):
+        pairs.append((int(rng.integers(0, n_reads)), int(rng.integers(0, n_reads)), int(rng.integers(0, 50))))
+    pairs = np.array([p for p in pairs if p[2] >= 0], dtype=np.int32)
+    vp = dict(threshold_pct=97, max_offset_pct=32, min_overlap_area=111, min_offset=0)
+    return rs, pairs, vp

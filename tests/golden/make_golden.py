@@ -1,0 +1,55 @@
+"""Generates the golden fixtures of tests/golden/ by running the UNMODIFIED reference.
+
+Run in the dev container (needs oracle/_ref/alga_ref_harness, i.e. /root/reference compiled by
+`make -C oracle ref`):   python tests/golden/make_golden.py
+
+For every seeded case of tests/cases.py the reference's own GraphCreatorPrefSuf +
+Graph::retainOnlySmallestOffset (main.cpp:282-291, --threads=1 order) is executed on the packed read
+set and the edge set is stored as `<case>.npz`:
+    edges      (E, 3) int32  (src, dst, offset) sorted
+    input_sha  sha256 over len_nt | align_from | align_to | word_off | words  -- guards generator drift
+    params     (min_overlap, rs_min_overlap, min_offset)
+`verify_pairs.npz` holds (pairs, verdicts) of AlignmentControllerHybrid::canAlign evaluated by the
+reference on candidate pairs of the cfg3_small read set.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import harness  # noqa: E402
+from tests.cases import CASES, build_case, verify_case  # noqa: E402
+
+
+def input_sha(rs) -> str:
+    h = hashlib.sha256()
+    for a in (rs.len_nt, rs.align_from, rs.align_to, rs.word_off, rs.words):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def main():
+    assert harness.available(), "build the reference harness first: make -C oracle ref"
+    for name in CASES:
+        rs, lmin, rsmin, mo = build_case(name)
+        if rs.n == 0:
+            edges = np.zeros((0, 3), np.int32)  # the reference itself crashes on an empty read vector
+        else:
+            edges, _ = harness.run_prefsuf(rs, lmin, rsmin, mo, threads=1)
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), edges=edges, input_sha=np.array(input_sha(rs)),
+                            params=np.array([lmin, rsmin, mo], np.int32))
+        print(f"{name}: n={rs.n} E={edges.shape[0]}")
+    rs, pairs, vp = verify_case()
+    verdict = harness.run_verify(rs, pairs, vp["threshold_pct"], vp["max_offset_pct"], vp["min_overlap_area"],
+                                 vp["min_offset"])
+    np.savez_compressed(os.path.join(HERE, "verify_pairs.npz"), pairs=pairs, verdict=verdict,
+                        input_sha=np.array(input_sha(rs)))
+    print(f"verify_pairs: {pairs.shape[0]} pairs, {int(verdict.sum())} accepted")
+
+
+if __name__ == "__main__":
+    main()

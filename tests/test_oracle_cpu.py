@@ -1,0 +1,79 @@
+"""CPU tests: the oracle (plain-C restatement) against the golden fixtures produced by the UNMODIFIED
+reference (tests/golden/make_golden.py), and -- when the compiled reference travels with the repo --
+against the reference run live."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import harness, oracle
+from tests.cases import CASES, build_case, verify_case
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def input_sha(rs) -> str:
+    h = hashlib.sha256()
+    for a in (rs.len_nt, rs.align_from, rs.align_to, rs.word_off, rs.words):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    return z
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_golden(name):
+    rs, lmin, rsmin, mo = build_case(name)
+    z = load_golden(name)
+    assert str(z["input_sha"]) == input_sha(rs), "seeded generator drifted: regenerate tests/golden"
+    assert z["params"].tolist() == [lmin, rsmin, mo]
+    got = oracle.prefsuf(rs, lmin, rsmin, mo)
+    assert np.array_equal(got, z["edges"])
+
+
+def test_oracle_verify_matches_reference_golden():
+    rs, pairs, vp = verify_case()
+    z = np.load(os.path.join(GOLDEN, "verify_pairs.npz"))
+    assert str(z["input_sha"]) == input_sha(rs)
+    assert np.array_equal(z["pairs"], pairs)
+    got = oracle.verify_pairs(rs, pairs, **vp)
+    assert np.array_equal(got, z["verdict"])
+    assert 0 < got.sum() < got.shape[0]
+
+
+@pytest.mark.skipif(not harness.available(), reason="oracle/_ref/alga_ref_harness not present")
+@pytest.mark.parametrize("name", ["cfg1_small", "cfg3_small", "varlen_dups", "periodic_dups", "long_reads"])
+def test_oracle_matches_reference_live(name):
+    rs, lmin, rsmin, mo = build_case(name)
+    want, info = harness.run_prefsuf(rs, lmin, rsmin, mo, threads=1)
+    assert np.array_equal(oracle.prefsuf(rs, lmin, rsmin, mo), want)
+    assert info["edges"] == want.shape[0]
+
+
+def test_fingerprint_definition():
+    """oracle_fingerprints follows GraphCreatorPrefSuf.cpp:213-236: sum s_j 4^j mod (10^18+3, 10^9+7)."""
+    rs, lmin, _, _ = build_case("tiny")
+    for L in (1, 7, lmin, 60):
+        p64, p32, s64, s32 = oracle.fingerprints(rs, L)
+        for i in range(rs.n):
+            if rs.len_nt[i] < L:
+                continue
+            c = [int(x) for x in rs.codes(i)]
+            pre = sum(c[j] * 4 ** j for j in range(L))
+            suf = sum(c[len(c) - L + j] * 4 ** j for j in range(L))
+            assert int(p64[i]) == pre % (10 ** 18 + 3) and int(p32[i]) == pre % (10 ** 9 + 7)
+            assert int(s64[i]) == suf % (10 ** 18 + 3) and int(s32[i]) == suf % (10 ** 9 + 7)
+
+
+def test_edges_are_exact_overlaps():
+    """Global::checkOLCGraphCorrectness (Global.cpp:121-145): every edge is an exact suffix/prefix overlap."""
+    rs, lmin, rsmin, mo = build_case("varlen")
+    e = oracle.prefsuf(rs, lmin, rsmin, mo)
+    for b, c, o in e[:: max(1, e.shape[0] // 300)]:
+        sb, sc = rs.sequence(int(b)), rs.sequence(int(c))
+        L = len(sb) - int(o)
+        assert L >= lmin and sb[int(o):] == sc[:L]
