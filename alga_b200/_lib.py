@@ -34,7 +34,7 @@ class PsParams(C.Structure):
 
 class Csr(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_edges", C.c_uint64), ("row_off", C.POINTER(C.c_uint64)),
-                ("nbr", C.POINTER(C.c_int32)), ("off", C.POINTER(C.c_int32))]
+                ("nbr", C.POINTER(C.c_int32)), ("off", C.POINTER(C.c_int32)), ("borrowed", C.c_int32)]
 
 
 class Timing(C.Structure):
@@ -65,6 +65,9 @@ SYMBOLS = {
     "alga_ps_plan_result_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64)]),
     "alga_ps_plan_result_rows": (C.c_uint32, [_P]),
     "alga_ps_plan_result_host": (C.c_int, [_P, C.POINTER(Csr)]),
+    "alga_ps_plan_result_host_pinned": (C.c_int, [_P, C.POINTER(Csr)]),
+    "alga_gpu_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "alga_gpu_host_free": (None, [_P]),
     "alga_ps_plan_stats": (C.c_int, [_P, C.POINTER(Timing)]),
     "alga_gpu_fingerprints": (C.c_int, [C.POINTER(Reads), C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "alga_gpu_pack_reads": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_int32, _P]),

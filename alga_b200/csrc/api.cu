@@ -72,6 +72,31 @@ struct DevBuf {
     }
 };
 
+struct HostBuf {  // page-locked staging buffer
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap && p) return ALGA_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            return fail(ALGA_E_NOMEM, "cudaMallocHost of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return ALGA_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
 struct Counters {
     unsigned long long n_edges;
     unsigned long long n_triples;
@@ -109,6 +134,7 @@ struct alga_ps_plan {
     Counters *h_counters = nullptr;  // pinned
     ReadStats *h_stats = nullptr;    // pinned
     uint64_t *h_u64 = nullptr;       // pinned
+    HostBuf h_row_off, h_nbr, h_off; // pinned result staging (alga_ps_plan_result_host_pinned)
 
     // result
     uint32_t res_lo = 0, res_hi = 0;
@@ -123,6 +149,9 @@ struct alga_ps_plan {
                          &triples, &triples1, &outdeg, &scan_ws, &spill_queue, &caps, &spill_off, &spill_store, &row_off,
                          &nbr, &off, &big_rows, &tmp_nbr, &tmp_off};
         for (DevBuf *b : all) b->release();
+        h_row_off.release();
+        h_nbr.release();
+        h_off.release();
         if (h_counters) cudaFreeHost(h_counters);
         if (h_stats) cudaFreeHost(h_stats);
         if (h_u64) cudaFreeHost(h_u64);
@@ -535,6 +564,7 @@ int alga_ps_plan_result_host(alga_ps_plan *plan, alga_csr *out) {
     const uint64_t E = plan->n_edges;
     out->n_reads = n;
     out->n_edges = E;
+    out->borrowed = 0;
     out->row_off = (uint64_t *) malloc(((size_t) n + 1) * 8);
     out->nbr = (int32_t *) malloc((size_t) (E ? E : 1) * 4);
     out->off = (int32_t *) malloc((size_t) (E ? E : 1) * 4);
@@ -550,6 +580,43 @@ int alga_ps_plan_result_host(alga_ps_plan *plan, alga_csr *out) {
     return ALGA_OK;
 }
 
+int alga_ps_plan_result_host_pinned(alga_ps_plan *plan, alga_csr *out) {
+    if (!plan || !out) return fail(ALGA_E_INVALID, "null argument");
+    CKR(use_device(plan));
+    const uint32_t n = plan->res_hi - plan->res_lo;
+    const uint64_t E = plan->n_edges;
+    CKR(plan->h_row_off.ensure(((size_t) n + 1) * 8));
+    CKR(plan->h_nbr.ensure((size_t) (E ? E : 1) * 4));
+    CKR(plan->h_off.ensure((size_t) (E ? E : 1) * 4));
+    out->n_reads = n;
+    out->n_edges = E;
+    out->row_off = (uint64_t *) plan->h_row_off.p;
+    out->nbr = (int32_t *) plan->h_nbr.p;
+    out->off = (int32_t *) plan->h_off.p;
+    out->borrowed = 1;
+    cudaStream_t s = 0;
+    CK(cudaMemcpyAsync(out->row_off, plan->row_off.p, ((size_t) n + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if (E) {
+        CK(cudaMemcpyAsync(out->nbr, plan->nbr.p, (size_t) E * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(out->off, plan->off.p, (size_t) E * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    return ALGA_OK;
+}
+
+void *alga_gpu_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        fail(ALGA_E_NOMEM, "cudaMallocHost of %zu bytes failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+void alga_gpu_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
 int alga_ps_plan_stats(alga_ps_plan *plan, alga_timing *t) {
     if (!plan || !t) return fail(ALGA_E_INVALID, "null argument");
     memset(t, 0, sizeof(*t));
@@ -562,9 +629,12 @@ int alga_ps_plan_stats(alga_ps_plan *plan, alga_timing *t) {
 
 void alga_gpu_free_csr(alga_csr *csr) {
     if (!csr) return;
-    free(csr->row_off);
-    free(csr->nbr);
-    free(csr->off);
+    if (!csr->borrowed) {
+        free(csr->row_off);
+        free(csr->nbr);
+        free(csr->off);
+    }
+    csr->borrowed = 0;
     csr->row_off = nullptr;
     csr->nbr = csr->off = nullptr;
     csr->n_edges = 0;
@@ -590,7 +660,7 @@ int alga_gpu_prefsuf_build(const alga_reads *reads, const alga_ps_params *params
     const double t1 = now_ms();
     CKR(alga_ps_plan_run(g_build_plan, nullptr));
     const double t2 = now_ms();
-    CKR(alga_ps_plan_result_host(g_build_plan, out));
+    CKR(alga_ps_plan_result_host_pinned(g_build_plan, out));
     const double t3 = now_ms();
     if (timing) {
         alga_ps_plan_stats(g_build_plan, timing);

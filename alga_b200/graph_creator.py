@@ -57,27 +57,64 @@ def _reads_struct(reads: ReadSet, stride_hint: bool = True) -> _lib.Reads:
 
 
 def _csr_to_graph(csr: _lib.Csr) -> Graph:
+    """Borrowed (page-locked, library-owned) results are wrapped without a copy: they stay valid until the next
+    build in this process, exactly like the alga_csr they came from."""
     n, e = csr.n_reads, csr.n_edges
-    row_off = np.ctypeslib.as_array(csr.row_off, shape=(n + 1,)).copy()
+    keep = (lambda a: a) if csr.borrowed else (lambda a: a.copy())
+    row_off = keep(np.ctypeslib.as_array(csr.row_off, shape=(n + 1,)))
     if e:
-        nbr = np.ctypeslib.as_array(csr.nbr, shape=(e,)).copy()
-        off = np.ctypeslib.as_array(csr.off, shape=(e,)).copy()
+        nbr = keep(np.ctypeslib.as_array(csr.nbr, shape=(e,)))
+        off = keep(np.ctypeslib.as_array(csr.off, shape=(e,)))
     else:
         nbr = np.zeros(0, np.int32)
         off = np.zeros(0, np.int32)
     return Graph(n, row_off, nbr, off)
 
 
+class _PinnedArray:
+    """numpy array over page-locked host memory from ``alga_gpu_host_alloc`` (freed with the object)."""
+
+    def __init__(self, src: np.ndarray):
+        self._lib = _lib.load()
+        nbytes = max(int(src.nbytes), 1)
+        self._ptr = self._lib.alga_gpu_host_alloc(nbytes)
+        if not self._ptr:
+            raise MemoryError(self._lib.alga_gpu_last_error().decode(errors="replace"))
+        buf = (C.c_uint8 * nbytes).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=src.dtype, count=src.size).reshape(src.shape)
+        self.array[...] = src
+
+    def __del__(self):
+        try:
+            if self._ptr:
+                self._lib.alga_gpu_host_free(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
+
+
 class GraphCreatorPrefSuf:
-    """Drop-in for the reference's ``GraphCreatorPrefSuf`` (GraphCreatorPrefSuf.cpp:15-126)."""
+    """Drop-in for the reference's ``GraphCreatorPrefSuf`` (GraphCreatorPrefSuf.cpp:15-126).
+
+    ``pinned=True`` stages the packed reads in page-locked host memory (``alga_gpu_host_alloc``), which is what
+    the C++ shim does when it gathers ``vector<Read*>``; the upload then runs at full host->device rate."""
 
     def __init__(self, reads: ReadSet, min_overlap: int, rs_min_overlap: int, min_offset: int = 0,
-                 max_len_cap: int = 500, device: int = 0, list_cap: int = 0):
-        self.reads = reads
+                 max_len_cap: int = 500, device: int = 0, list_cap: int = 0, pinned: bool = False):
         self.params = _lib.PsParams(min_overlap, rs_min_overlap, min_offset, max_len_cap, device, list_cap)
-        # GraphCreator::GraphCreator (GraphCreator.cpp:9-17): flags start as true for every read
-        self.alignFrom = reads.align_from.copy()
-        self.alignTo = reads.align_to.copy()
+        self._pins = []
+        if pinned:
+            def pin(a):
+                self._pins.append(_PinnedArray(a))
+                return self._pins[-1].array
+            reads = ReadSet(pin(reads.words), pin(reads.word_off), pin(reads.len_nt), reads.align_from, reads.align_to)
+            # GraphCreator::GraphCreator (GraphCreator.cpp:9-17): flags start as true for every read
+            self.alignFrom = pin(reads.align_from)
+            self.alignTo = pin(reads.align_to)
+        else:
+            self.alignFrom = reads.align_from.copy()
+            self.alignTo = reads.align_to.copy()
+        self.reads = reads
         self.graph: Graph | None = None
         self.timing: dict | None = None
 

@@ -53,9 +53,23 @@ class DeviceReads:
             self.word_off = torch.from_numpy(reads.word_off.view(np.int64)).to(device)
         self.max_len = int(reads.len_nt.max()) if reads.n else 0
 
+    @classmethod
+    def from_tensors(cls, words: torch.Tensor, len_nt: torch.Tensor, stride: int, n: int, max_len: int,
+                     word_off: torch.Tensor | None = None, align_from: torch.Tensor | None = None,
+                     align_to: torch.Tensor | None = None) -> "DeviceReads":
+        """Wrap device tensors that already hold a packed read set (``words`` padded by READ_PAD_BYTES)."""
+        self = cls.__new__(cls)
+        self.n, self.device = n, words.device
+        self.words, self.len_nt, self.stride, self.word_off = words, len_nt, stride, word_off
+        self.align_from, self.align_to = align_from, align_to
+        self.max_len = max_len
+        return self
+
     def struct(self) -> _lib.Reads:
         return _lib.Reads(self.n, self.words.data_ptr(), self.word_off.data_ptr() if self.word_off is not None else None,
-                          self.stride, self.len_nt.data_ptr(), self.align_from.data_ptr(), self.align_to.data_ptr())
+                          self.stride, self.len_nt.data_ptr(),
+                          self.align_from.data_ptr() if self.align_from is not None else None,
+                          self.align_to.data_ptr() if self.align_to is not None else None)
 
 
 class PrefSufPlan:

@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the overlap-graph hot path (GraphCreatorPrefSuf + retainOnlySmallestOffset).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg4]
+
+A "step" is one complete overlap-graph build over one synthetic read set (SURVEY.md §8-d generator):
+packed reads resident in HBM -> CSR adjacency resident in HBM.  Metric: graph nodes (strand-reads) per second.
+
+* N = 1 : BASELINE.json configs[1] (4.6 Mbp genome, 2x150 bp, 50x, error-free; seed 2).
+* N > 1 : weak scaling -- N chromosomes of 4.6 Mbp (seeds 2 + 100 r), read ids interleaved so that every
+          rank's id range holds reads of every chromosome; each rank starts with its own shard of the packed
+          reads in HBM.  The timed region contains the NCCL all-gather of the packed reads, the index build,
+          phase 1, the all-to-all of phase-1 edges to the owner of the target read, phase 2, the all-to-all of
+          surviving edges to the owner of the source read and the CSR assembly (alga_b200/distributed.py).
+* --impl reference : the reference's own CPU GraphCreatorPrefSuf (oracle/_ref/alga_ref_harness = the unmodified
+          reference sources behind a file-reading main; else the plain-C oracle port), all host threads, on a
+          bounded sample of the same workload.
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definition of every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "reads/sec overlap-graph build"
+UNIT = "reads/s"
+
+
+# --------------------------------------------------------------------------------------------------------
+def alg_bytes_per_node(len_nt: int, lmin: int, edges_per_node: float) -> float:
+    """B_alg = 4 W + 64 n_L + 8 E/N + 8."""
+    W = (len_nt + 15) // 16
+    n_l = len_nt - lmin + 1
+    return 4 * W + 64 * n_l + 8 * edges_per_node + 8
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks line of B200_PROFILING.md, sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="alga_clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=float(max(power)))
+        return out
+
+
+# --------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's CPU graph creator on a bounded sample
+def _cpu_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def _cpu_build(reads, params, threads):
+    """-> (seconds of the replaced region main.cpp:282-291, kind, threads used)."""
+    from oracle import harness, oracle  # the CPU legs are the only place bench.py touches oracle/
+
+    if harness.available():
+        _, info = harness.run_prefsuf(reads, params.min_overlap, params.rs_min_overlap, params.min_offset,
+                                      threads=threads, want_edges=False)
+        return float(info["graph_s"]), "reference", threads
+    t = time.perf_counter()
+    oracle.prefsuf(reads, params.min_overlap, params.rs_min_overlap, params.min_offset)
+    return time.perf_counter() - t, "port", 1
+
+
+def cpu_sample(workload: str, target_s: float):
+    """Pick a genome-scale so that one CPU build of the sample takes about target_s; returns (Workload, calib)."""
+    from alga_b200 import synth
+
+    threads = _cpu_threads()
+    probe = synth.make_config(workload, scale=0.01 if workload != "cfg1" else 0.05)
+    s, kind, used = _cpu_build(probe.reads, probe.params, threads)
+    rate = probe.reads.n / max(s, 1e-3)  # nodes/s on the tiny probe (pessimistic for the threaded reference)
+    full_nodes = probe.reads.n / (0.01 if workload != "cfg1" else 0.05)
+    scale = min(1.0, max(0.01, rate * target_s / full_nodes))
+    return synth.make_config(workload, scale=scale), dict(kind=kind, threads=used, scale=scale)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    total = args.steps + args.warmup
+    target = min(10.0, max(1.0, 150.0 / max(total, 1)))
+    w, cal = cpu_sample(args.workload, target)
+    times = []
+    for i in range(total):
+        s, kind, used = _cpu_build(w.reads, w.params, cal["threads"])
+        if i >= args.warmup:
+            times.append(s)
+    ms = 1e3 * float(np.mean(times))
+    value = w.reads.n / (ms / 1e3)
+    sample = (f"{w.name}: {w.reads.n} nodes ({w.records} records, genome {w.genome_size} bp), region main.cpp:282-291 "
+              f"timed by steady_clock inside the harness")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64/u32 (polynomial hashes mod 1e18+3, 1e9+7)", "data": "synthetic",
+        "config": workload_config(args.workload, args.gpus, sample=True),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cal["threads"], "kind": cal["kind"], "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(workload: str, n_gpus: int, sample: bool = False) -> dict:
+    from alga_b200 import synth
+
+    kw = synth.CONFIGS[workload]
+    desc = (f"{workload}: synthetic {kw['genome_size'] / 1e6:g} Mbp random genome, "
+            f"{'2x' if kw['paired'] else ''}{kw['read_len']} bp {'paired' if kw['paired'] else 'single-end'} reads at "
+            f"{kw['coverage']}x, error {kw.get('error', 0.0):g}, --error_rate=0 (GraphCreatorPrefSuf only)")
+    if n_gpus > 1:
+        desc += f"; weak scaling: {n_gpus} such chromosomes (seeds {kw['seed']}+100r), reads interleaved over ranks"
+    if sample:
+        desc += "; CPU arm runs a bounded genome-scaled sample of it (same read length and coverage)"
+    return {"workload": desc, "l2": "explicit flush (256 MiB write) between timed steps; step inputs+index also exceed L2",
+            "sharding": "1 GPU" if n_gpus == 1 else f"read-id ranges over {n_gpus} GPUs, replicated packed reads + seed index"}
+
+
+# --------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from alga_b200 import _lib, synth
+    from alga_b200.plan import DeviceReads, PrefSufPlan
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the overlap-graph path has no CPU fallback")
+    _lib.load()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    kw = dict(synth.CONFIGS[args.workload])
+    kw["genome_size"] = max(20_000, int(kw["genome_size"] * args.scale))
+    kw["seed"] = kw["seed"] + 100 * rank
+    t0 = time.time()
+    w = synth.make_workload(args.workload, **kw)
+    gen_s = time.time() - t0
+    params = w.params
+    len_nt = int(w.reads.len_nt[0])
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    clocks = ClockSampler(local)
+
+    if world == 1:
+        n_nodes_total = w.reads.n
+        dreads = DeviceReads(w.reads, dev)
+        plan = PrefSufPlan(params.min_overlap, params.rs_min_overlap, params.min_offset, params.max_len_cap, device=dev)
+        plan.bind(dreads)
+
+        def step():
+            plan.run()
+
+        def step_stats():
+            return plan.stats()
+    else:
+        from alga_b200.distributed import ShardedPrefSuf, interleave_shards
+
+        shard_words, n_nodes_total = interleave_shards(w.reads, rank, world, dev)
+        sp = ShardedPrefSuf(params.min_overlap, params.rs_min_overlap, params.min_offset, params.max_len_cap, dev,
+                            rank, world, len_nt=len_nt)
+
+        def step():
+            sp.run(shard_words)
+
+        def step_stats():
+            return sp.stats()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        step()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_acc, launches = {}, 0
+    clocks.start()
+    barrier()
+    wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.fill_(2)  # L2 flush, outside the per-step events
+        if world > 1:
+            dist.barrier()
+        a.record()
+        step()
+        b.record()
+        st = step_stats()
+        launches += int(st["kernel_launches"])
+        for k, v in st["stage_ms"].items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + float(v)
+    barrier()
+    wall_s = time.perf_counter() - wall0
+    clk = clocks.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    value = n_nodes_total / (ms_per_step / 1e3)
+    if world == 1:
+        n_edges = plan.n_edges()
+    else:
+        n_edges = sp.total_edges()
+
+    # ---- e2e: the reference-facing call (GraphCreatorPrefSuf over alga_gpu_prefsuf_build) with host buffers ----
+    e2e = None
+    if world == 1:
+        from alga_b200.graph_creator import GraphCreatorPrefSuf
+
+        gc = GraphCreatorPrefSuf(w.reads, params.min_overlap, params.rs_min_overlap, params.min_offset,
+                                 params.max_len_cap, device=local, pinned=True)
+        for _ in range(max(1, min(args.warmup, 3))):
+            gc.startAlignmentGraphCreation()
+        torch.cuda.synchronize(dev)
+        k_e2e = max(1, min(args.steps, 10))
+        ts = time.perf_counter()
+        for _ in range(k_e2e):
+            g = gc.startAlignmentGraphCreation()
+        torch.cuda.synchronize(dev)
+        e2e_ms = 1e3 * (time.perf_counter() - ts) / k_e2e
+        assert g.n_edges == n_edges, (g.n_edges, n_edges)
+        h2d = int(w.reads.words.nbytes + w.reads.len_nt.nbytes + w.reads.align_from.nbytes + w.reads.align_to.nbytes)
+        d2h = int(g.row_off.nbytes + g.nbr.nbytes + g.off.nbytes)
+        e2e = {"value": n_nodes_total / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": k_e2e,
+               "call": "alga_b200.GraphCreatorPrefSuf.startAlignmentGraphCreation -> alga_gpu_prefsuf_build (host buffers)",
+               "timing": gc.timing}
+    else:
+        e2e = sp.e2e(shard_words, steps=max(1, min(args.steps, 5)), n_nodes_total=n_nodes_total)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak_gbs()
+    b_alg = alg_bytes_per_node(len_nt, params.min_overlap, n_edges / max(n_nodes_total, 1))
+    nodes_per_gpu = n_nodes_total / world
+    achieved = nodes_per_gpu * b_alg / (ms_per_step / 1e3) / 1e9
+    stages = {k: v / args.steps for k, v in stage_acc.items()}
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": (traffic or {}).get("pipeline_dram_bytes_per_step"), "peak_source": peak_src,
+                "kernel": "whole device pipeline of one step (index + phase1 + transpose + phase2 + csr), per GPU",
+                "alg_bytes_per_node": b_alg, "nodes_per_gpu": nodes_per_gpu, "stage_ms": stages,
+                "traffic_detail": traffic}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        sample, cal = cpu_sample(args.workload, 12.0)
+        s, kind, used = _cpu_build(sample.reads, sample.params, cal["threads"])
+        cpu = {"value": sample.reads.n / s, "unit": UNIT, "cores": used, "kind": kind, "seconds": s,
+               "sample": f"{sample.name}: {sample.reads.n} nodes, one build, region main.cpp:282-291 (steady_clock)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 (2-bit packed words, exact compare)", "data": "synthetic",
+        "config": workload_config(args.workload, world),
+        "nodes": n_nodes_total, "records": w.records * world, "edges": n_edges, "gen_s": gen_s, "wall_s_timed_region": wall_s,
+        "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4", "cfg5"])
+    ap.add_argument("--scale", type=float, default=1.0, help="genome scale of the GPU workload (1.0 = the named config)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -63,6 +63,9 @@ typedef struct {
     uint64_t *row_off; /* N+1 */
     int32_t *nbr;      /* E */
     int32_t *off;      /* E */
+    int32_t borrowed;  /* != 0: the arrays are page-locked staging buffers owned by the library, valid until the
+                          next build on the same plan (alga_gpu_prefsuf_build: the next call); alga_gpu_free_csr
+                          then only clears the pointers */
 } alga_csr;
 
 typedef struct {
@@ -84,7 +87,8 @@ typedef struct {
 #define ALGA_STAGE_CSR 4
 
 /* One-call drop-in for GraphCreatorPrefSuf::startAlignmentGraphCreation (GraphCreatorPrefSuf.cpp:73-126)
- * followed by Graph::retainOnlySmallestOffset (main.cpp:291).  Host buffers in, host CSR out. */
+ * followed by Graph::retainOnlySmallestOffset (main.cpp:291).  Host buffers in, host CSR out (borrowed page-locked
+ * buffers of a process-wide cached plan: valid until the next call; release with alga_gpu_free_csr). */
 int alga_gpu_prefsuf_build(const alga_reads *reads, const alga_ps_params *params, alga_csr *out,
                            alga_timing *timing /* may be NULL */);
 void alga_gpu_free_csr(alga_csr *csr);
@@ -131,6 +135,9 @@ int alga_ps_plan_result_device(alga_ps_plan *plan, const uint64_t **row_off, con
 uint32_t alga_ps_plan_result_rows(alga_ps_plan *plan);
 /* Copy the result to freshly allocated host arrays. */
 int alga_ps_plan_result_host(alga_ps_plan *plan, alga_csr *out);
+/* Copy the result into the plan's own page-locked staging buffers (full PCIe/C2C rate, no allocation after the
+ * first call); out->borrowed is set. */
+int alga_ps_plan_result_host_pinned(alga_ps_plan *plan, alga_csr *out);
 /* Counters of the last run. */
 int alga_ps_plan_stats(alga_ps_plan *plan, alga_timing *timing);
 
@@ -163,6 +170,10 @@ int alga_gpu_verify_pairs(const alga_reads *reads, const int32_t *pairs, uint64_
                           const alga_verify_params *params, uint8_t *verdict);
 
 /* ---- misc ---------------------------------------------------------------------------------- */
+/* Page-locked host memory for callers that stage the packed reads themselves (the shim gathers the blocks of
+ * vector<Read*> straight into such a buffer, so the upload runs at full host->device rate).  NULL on failure. */
+void *alga_gpu_host_alloc(size_t bytes);
+void alga_gpu_host_free(void *p);
 int alga_gpu_device_count(void);
 const char *alga_gpu_last_error(void);
 const char *alga_gpu_version(void);

@@ -1,0 +1,141 @@
+"""GPU parity of the remaining entry points of the C ABI: fingerprints, 2-bit packing, candidate verification, the
+device-resident plan, the staged (sharded) pipeline emulated rank by rank on one GPU, and -- at BASELINE.json's
+full config-2 size -- size-independent properties of the result."""
+import numpy as np
+import pytest
+
+from alga_b200 import readset, synth
+from alga_b200.graph_creator import GraphCreatorPrefSuf, fingerprints, pack_reads, verify_pairs
+from oracle import oracle
+from tests.cases import build_case, verify_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,L", [("tiny", 1), ("tiny", 33), ("varlen", 55), ("varlen", 90), ("long_reads", 400),
+                                    ("cfg1_small", 94)])
+def test_fingerprints_match_oracle(gpu, name, L):
+    """updatePrefixHash / updateSuffixHash (GraphCreatorPrefSuf.cpp:213-236): bit-exact u64 / u32 values."""
+    rs, *_ = build_case(name)
+    want = oracle.fingerprints(rs, L)
+    got = fingerprints(rs, L)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+
+
+@pytest.mark.parametrize("n,ln", [(1, 1), (7, 16), (1000, 94), (513, 144), (33, 1000), (3, 16384)])
+def test_pack_reads_matches_host_packing(gpu, n, ln):
+    """Read::createSequence (Read.cpp:40-68) incl. non-ACGT -> 0 and lower case -> 0."""
+    rng = np.random.default_rng(n * 1000 + ln)
+    codes = rng.integers(0, 4, size=(n, ln), dtype=np.uint8)
+    ascii_ = np.frombuffer(b"ACGT", np.uint8)[codes].copy()
+    junk = rng.random(codes.shape) < 0.02
+    ascii_[junk] = rng.choice(np.frombuffer(b"Nacgt-", np.uint8), size=int(junk.sum()))
+    codes[junk] = 0
+    assert np.array_equal(pack_reads(ascii_), readset.pack_matrix(codes))
+
+
+def test_verify_pairs_matches_oracle(gpu):
+    rs, pairs, vp = verify_case()
+    want = oracle.verify_pairs(rs, pairs, **vp)
+    got = verify_pairs(rs, pairs, **vp)
+    assert np.array_equal(got, want)
+    assert 0 < int(got.sum()) < got.shape[0]
+
+
+@pytest.mark.parametrize("thr,max_off,area", [(99, 10, 130), (90, 60, 60), (100, 32, 111)])
+def test_verify_pairs_parameter_sweep(gpu, thr, max_off, area):
+    rs, pairs, _ = verify_case(seed=32, n_reads=1500)
+    vp = dict(threshold_pct=thr, max_offset_pct=max_off, min_overlap_area=area, min_offset=0)
+    assert np.array_equal(verify_pairs(rs, pairs, **vp), oracle.verify_pairs(rs, pairs, **vp))
+
+
+@pytest.mark.parametrize("name", ["cfg2_small", "varlen_dups", "flags", "nulls", "long_reads_rs"])
+def test_device_resident_plan_matches_oracle(gpu, name):
+    import torch
+
+    from alga_b200.plan import DeviceReads, PrefSufPlan
+
+    rs, lmin, rsmin, mo = build_case(name)
+    plan = PrefSufPlan(lmin, rsmin, mo, device=0)
+    plan.bind(DeviceReads(rs, torch.device("cuda", 0)))
+    for _ in range(2):  # the workspace is reused across runs
+        plan.run()
+        assert np.array_equal(plan.result_host().edges(), oracle.prefsuf(rs, lmin, rsmin, mo))
+    ro, nb, of = plan.result_device()
+    assert ro.shape[0] == rs.n + 1 and int(ro[-1].item()) == nb.shape[0] == of.shape[0] == plan.n_edges()
+    plan.close()
+
+
+@pytest.mark.parametrize("name", ["cfg2_small", "cfg3_small", "varlen_dups", "periodic_dups", "flags"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_staged_pipeline_emulated_ranks(gpu, name, world):
+    """The sharded build of alga_b200/distributed.py with the ranks emulated one after another on one GPU:
+    phase 1 per source range -> route by target -> phase 2 per target range -> route by source -> CSR per range."""
+    import torch
+
+    from alga_b200.plan import DeviceReads, PrefSufPlan
+
+    rs, lmin, rsmin, mo = build_case(name)
+    dev = torch.device("cuda", 0)
+    plan = PrefSufPlan(lmin, rsmin, mo, device=0)
+    plan.bind(DeviceReads(rs, dev))
+    plan.stage_index()
+    bounds = [rs.n * r // world for r in range(world + 1)]
+    t1 = torch.cat([plan.stage_phase1(bounds[r], bounds[r + 1]).clone() for r in range(world)])
+    t2 = []
+    for r in range(world):
+        sel = (t1[:, 1] >= bounds[r]) & (t1[:, 1] < bounds[r + 1])
+        t2.append(plan.stage_phase2(bounds[r], bounds[r + 1], t1[sel]).clone())
+    t2 = torch.cat(t2)
+    edges = []
+    for r in range(world):
+        sel = (t2[:, 0] >= bounds[r]) & (t2[:, 0] < bounds[r + 1])
+        plan.stage_csr(bounds[r], bounds[r + 1], t2[sel])
+        e = plan.result_host().edges()
+        e[:, 0] += bounds[r]
+        edges.append(e)
+    got = np.concatenate(edges) if edges else np.zeros((0, 3), np.int32)
+    assert np.array_equal(got, oracle.prefsuf(rs, lmin, rsmin, mo))
+    plan.close()
+
+
+def test_full_config2_properties(gpu):
+    """BASELINE.json configs[1] at full size (2.6 M nodes): properties that do not need the CPU oracle.
+    * rows sorted by target, one entry per target (retainOnlySmallestOffset, Graph.cpp:348-387)
+    * every edge is an exact suffix/prefix overlap >= min overlap (Global::checkOLCGraphCorrectness, Global.cpp:121-145)
+    * strand symmetry: b -> c with overlap L  <=>  c^1 -> b^1 with overlap L (both strands of every read are nodes)
+    * run-to-run determinism (checksum of the CSR)"""
+    w = synth.make_config("cfg2")
+    rs, p = w.reads, w.params
+    gc = GraphCreatorPrefSuf(rs, p.min_overlap, p.rs_min_overlap)
+    g = gc.startAlignmentGraphCreation()
+    e = g.edges()
+    first = (g.row_off.copy(), g.nbr.copy(), g.off.copy())  # the result arrays are borrowed until the next build
+    assert e.shape[0] > rs.n * 0.9
+    same_row = e[1:, 0] == e[:-1, 0]
+    assert np.all(e[1:, 1][same_row] > e[:-1, 1][same_row])
+    ln = rs.len_nt.astype(np.int64)
+    L = ln[e[:, 0]] - e[:, 2]
+    assert np.all(L >= p.min_overlap) and np.all(e[:, 2] >= 0) and np.all(e[:, 0] != e[:, 1])
+    rng = np.random.default_rng(0)
+    W = int(rs.word_off[1])
+    words = rs.words.reshape(rs.n, W)
+    for k in rng.integers(0, e.shape[0], size=3000):
+        b, c, o = (int(x) for x in e[k])
+        sb = _codes(words[b], int(ln[b]))
+        sc = _codes(words[c], int(ln[c]))
+        assert np.array_equal(sb[o:], sc[: ln[b] - o])
+    # equal-length reads: overlap L of (b, c) equals overlap of (c^1, b^1); phase-2 survivors are symmetric, the
+    # phase-1 "last 3" rule is not, so only compare edges whose overlap is >= rs
+    big = e[L >= p.rs_min_overlap]
+    fwd = set(map(tuple, big.tolist()))
+    mirrored = set((int(c) ^ 1, int(b) ^ 1, int(o)) for b, c, o in big.tolist())
+    assert fwd == mirrored
+    g2 = GraphCreatorPrefSuf(rs, p.min_overlap, p.rs_min_overlap).startAlignmentGraphCreation()
+    assert all(np.array_equal(a, b) for a, b in zip((g2.row_off, g2.nbr, g2.off), first))
+
+
+def _codes(words, ln):
+    j = np.arange(ln)
+    return (words[j >> 4] >> ((j & 15) * 2).astype(np.uint32)) & 3
