@@ -29,7 +29,10 @@ class Reads(C.Structure):
 
 class PsParams(C.Structure):
     _fields_ = [("min_overlap", C.c_int32), ("rs_min_overlap", C.c_int32), ("min_offset", C.c_int32),
-                ("max_len_cap", C.c_int32), ("device", C.c_int32), ("list_cap", C.c_int32)]
+                ("max_len_cap", C.c_int32), ("device", C.c_int32), ("list_cap", C.c_int32), ("flags", C.c_int32)]
+
+
+PS_FORCE_GENERIC = 1
 
 
 class Csr(C.Structure):

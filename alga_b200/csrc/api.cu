@@ -102,6 +102,8 @@ struct Counters {
     unsigned long long n_triples;
     uint32_t n_spill;
     uint32_t n_big;
+    uint32_t n_hard1;  // source reads phase 1's fast kernel handed to the generic kernel
+    uint32_t pad;
 };
 
 double now_ms() {
@@ -128,7 +130,7 @@ struct alga_ps_plan {
     // owned copies (upload path)
     DevBuf words, word_off, len, from, to;
     // workspace
-    DevBuf stats_d, counters_d, tp, ts, fwd, indeg, rev_off, rev, triples, triples1, outdeg, scan_ws, spill_queue, caps,
+    DevBuf stats_d, counters_d, tp, ts, fwd, fwd_t, rev_t, hard1, indeg, rev_off, rev, triples, triples1, outdeg, scan_ws, spill_queue, caps,
         spill_off, spill_store, row_off, nbr, off, big_rows, tmp_nbr, tmp_off;
     SeedTable Tp{}, Ts{};
     Counters *h_counters = nullptr;  // pinned
@@ -145,7 +147,7 @@ struct alga_ps_plan {
     cudaEvent_t ev_stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     ~alga_ps_plan() {
-        DevBuf *all[] = {&words, &word_off, &len, &from, &to, &stats_d, &counters_d, &tp, &ts, &fwd, &indeg, &rev_off, &rev,
+        DevBuf *all[] = {&words, &word_off, &len, &from, &to, &stats_d, &counters_d, &tp, &ts, &fwd, &fwd_t, &rev_t, &hard1, &indeg, &rev_off, &rev,
                          &triples, &triples1, &outdeg, &scan_ws, &spill_queue, &caps, &spill_off, &spill_store, &row_off,
                          &nbr, &off, &big_rows, &tmp_nbr, &tmp_off};
         for (DevBuf *b : all) b->release();
@@ -190,6 +192,7 @@ int resolve_params(alga_ps_plan *plan) {
     P.max_l = (int32_t) (plan->stats.max_len < (uint32_t) cap ? plan->stats.max_len : (uint32_t) cap) + 1;
     P.seed_nt = P.lmin < 32 ? P.lmin : 32;
     P.seed_mask = P.seed_nt == 32 ? ~0ull : ((1ull << (2 * P.seed_nt)) - 1ull);
+    P.uniform_len = (plan->stats.min_len == plan->stats.max_len && plan->R.n) ? plan->stats.max_len : 0u;
     // the reference transposes the phase-1 graph when L reaches rs (GraphCreatorPrefSuf.cpp:288).  If
     // that never happens the single final transpose leaves the phase-1 edges reversed.
     plan->swap_direction = P.rs > P.max_l && P.max_l >= P.lmin;
@@ -248,8 +251,13 @@ int run_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, uint32_t *outdeg, c
         Counters *dc = plan->counters_d.as<Counters>();
         Phase2Out out{plan->triples.as<int32_t>(), &dc->n_edges, edge_cap, outdeg, plan->spill_queue.as<uint32_t>(),
                       &dc->n_spill};
-        launch_phase2(plan->R, plan->Ts, plan->P, lo, hi, plan->rev_off.as<uint32_t>(), plan->rev.as<int2>(), list_cap,
-                      out, s, plan->cfg);
+        if (plan->params.list_cap > 0)  // testing: generic kernel with a tiny on-chip list
+            launch_phase2(plan->R, plan->Ts, plan->P, lo, hi, plan->rev_off.as<uint32_t>(), plan->rev.as<int2>(),
+                          list_cap, out, s, plan->cfg);
+        else
+            launch_phase2_fast(plan->R, plan->Ts, plan->P, lo, hi, plan->rev_off.as<uint32_t>(), plan->rev.as<int2>(),
+                               plan->rev_t.as<uint64_t>(), out, plan->params.flags & ALGA_PS_FORCE_GENERIC, s,
+                               plan->cfg);
         CK(cudaGetLastError());
         CKR(read_counters(plan, s));
         const uint32_t n_spill = plan->h_counters->n_spill;
@@ -456,9 +464,13 @@ int alga_ps_stage_phase1(alga_ps_plan *plan, uint32_t lo, uint32_t hi, void *str
     cudaStream_t s = (cudaStream_t) stream;
     const uint32_t n = hi - lo;
     CKR(plan->fwd.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * sizeof(int2)));
+    CKR(plan->fwd_t.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * 8));
+    CKR(plan->hard1.ensure((size_t) (n ? n : 1) * 4));
     CKR(plan->triples1.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * 12));
-    launch_phase1(plan->R, plan->Tp, plan->P, lo, hi, plan->fwd.as<int2>(), nullptr, s, plan->cfg);
     Counters *dc = plan->counters_d.as<Counters>();
+    CK(cudaMemsetAsync(&dc->n_hard1, 0, 4, s));
+    launch_phase1(plan->R, plan->Tp, plan->P, lo, hi, plan->fwd.as<int2>(), plan->fwd_t.as<uint64_t>(), nullptr,
+                  plan->hard1.as<uint32_t>(), &dc->n_hard1, plan->params.flags & ALGA_PS_FORCE_GENERIC, s, plan->cfg);
     CK(cudaMemsetAsync(&dc->n_triples, 0, 8, s));
     launch_compact_slots(plan->fwd.as<int2>(), lo, hi, plan->triples1.as<int32_t>(), &dc->n_triples, s, plan->cfg);
     CK(cudaGetLastError());
@@ -482,8 +494,9 @@ int alga_ps_stage_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int
     launch_count_targets(tin, n_in, lo, hi, plan->indeg.as<uint32_t>(), s, plan->cfg);
     CKR(build_rev_from_counts(plan, n, s));
     CKR(plan->rev.ensure((size_t) (n_in ? n_in : 1) * sizeof(int2)));
-    launch_scatter_rev_triples(tin, n_in, lo, hi, plan->rev_off.as<uint32_t>(), plan->indeg.as<uint32_t>(),
-                               plan->rev.as<int2>(), s, plan->cfg);
+    CKR(plan->rev_t.ensure((size_t) (n_in ? n_in : 1) * 8));
+    launch_scatter_rev_triples(plan->R, tin, n_in, lo, hi, plan->rev_off.as<uint32_t>(), plan->indeg.as<uint32_t>(),
+                               plan->rev.as<int2>(), plan->rev_t.as<uint64_t>(), s, plan->cfg);
     CK(cudaGetLastError());
     CKR(run_phase2(plan, lo, hi, nullptr, s));
     *dev_triples_out = plan->triples.as<int32_t>();
@@ -514,15 +527,21 @@ int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
     CK(cudaEventRecord(plan->ev_stage[0], s));
     // phase 1 with fused in-degree counting
     CKR(plan->fwd.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * sizeof(int2)));
+    CKR(plan->fwd_t.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * 8));
+    CKR(plan->hard1.ensure((size_t) (n ? n : 1) * 4));
     CKR(plan->indeg.ensure((size_t) (n ? n : 1) * 4));
     CK(cudaMemsetAsync(plan->indeg.p, 0, (size_t) (n ? n : 1) * 4, s));
-    launch_phase1(plan->R, plan->Tp, plan->P, 0, n, plan->fwd.as<int2>(), plan->indeg.as<uint32_t>(), s, plan->cfg);
+    CK(cudaMemsetAsync(&plan->counters_d.as<Counters>()->n_hard1, 0, 4, s));
+    launch_phase1(plan->R, plan->Tp, plan->P, 0, n, plan->fwd.as<int2>(), plan->fwd_t.as<uint64_t>(),
+                  plan->indeg.as<uint32_t>(), plan->hard1.as<uint32_t>(), &plan->counters_d.as<Counters>()->n_hard1,
+                  plan->params.flags & ALGA_PS_FORCE_GENERIC, s, plan->cfg);
     CK(cudaEventRecord(plan->ev_stage[1], s));
     // reversed phase-1 graph (rows by target)
     CKR(build_rev_from_counts(plan, n, s));
     CKR(plan->rev.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * sizeof(int2)));
-    launch_scatter_rev_slots(plan->fwd.as<int2>(), 0, n, 0, n, plan->rev_off.as<uint32_t>(), plan->indeg.as<uint32_t>(),
-                             plan->rev.as<int2>(), s, plan->cfg);
+    CKR(plan->rev_t.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * 8));
+    launch_scatter_rev_slots(plan->fwd.as<int2>(), plan->fwd_t.as<uint64_t>(), 0, n, 0, n, plan->rev_off.as<uint32_t>(),
+                             plan->indeg.as<uint32_t>(), plan->rev.as<int2>(), plan->rev_t.as<uint64_t>(), s, plan->cfg);
     CK(cudaGetLastError());
     CK(cudaEventRecord(plan->ev_stage[2], s));
     // phase 2 with fused out-degree counting (not in the reversed-result corner)

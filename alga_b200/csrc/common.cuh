@@ -38,6 +38,7 @@ struct PsDev {
     int32_t min_offset;  // MIN_OFFSET_FOR_ALIGNMENT
     int32_t max_l;       // last overlap length the reference iterates: min(max read length, cap) + 1  (GraphCreatorPrefSuf.cpp:92-95)
     int32_t seed_nt;     // K = min(lmin, 32): nucleotides hashed into the seed index
+    uint32_t uniform_len;  // != 0: every read (none removed) has exactly this length -> no per-candidate length loads
     uint64_t seed_mask;  // low 2K bits
 };
 
@@ -111,14 +112,13 @@ __device__ __forceinline__ bool equal_bits_head(const uint32_t (&a)[4], uint32_t
     return diff == 0;
 }
 
-// splitmix64-style finaliser over the 2K-bit seed window
+// Hash of the 2K-bit seed window: multiply-add of the two 32-bit halves, one xor-fold, one multiply.  The top bits
+// pick the bucket, the low 32 bits are the tag; a false tag hit only costs one exact compare.
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
-    x ^= x >> 31;
-    x *= 0x7fb5d329728ea185ull;
-    x ^= x >> 27;
-    x *= 0x81dadef4bc2dd44dull;
-    x ^= x >> 33;
-    return x;
+    uint64_t h = (uint64_t) (uint32_t) x * 0x9E3779B97F4A7C15ull + (x >> 32) * 0xC2B2AE3D27D4EB4Full;
+    h ^= h >> 32;
+    h *= 0xD6E8FEB86659FD93ull;
+    return h;
 }
 __device__ __forceinline__ uint32_t bucket_of(uint64_t h, uint32_t n_buckets) {
     return __umulhi((uint32_t) (h >> 32), n_buckets);

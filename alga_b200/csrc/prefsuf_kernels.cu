@@ -36,20 +36,23 @@ inline void bump(const LaunchCfg &cfg) {
 
 // ------------------------------------------------------------------------------------------------
 __global__ void read_stats_kernel(ReadsDev R, int lmin, int min_offset, ReadStats *stats) {
-    uint32_t mx = 0, np = 0, ns = 0;
+    uint32_t mx = 0, mn = 0xFFFFFFFFu, np = 0, ns = 0;
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < R.n; i += (uint64_t) gridDim.x * blockDim.x) {
         const uint32_t len = R.len[i];
         mx = max(mx, len);
+        mn = min(mn, len);
         if (len && flag_to(R, i) && (int64_t) len >= lmin) np++;
         if (len && flag_from(R, i) && (int64_t) len - min_offset >= lmin) ns++;
     }
     for (int d = 16; d; d >>= 1) {
         mx = max(mx, __shfl_xor_sync(kFull, mx, d));
+        mn = min(mn, __shfl_xor_sync(kFull, mn, d));
         np += __shfl_xor_sync(kFull, np, d);
         ns += __shfl_xor_sync(kFull, ns, d);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicMax(&stats->max_len, mx);
+        atomicMin(&stats->min_len, mn);
         atomicAdd(&stats->n_prefix, np);
         atomicAdd(&stats->n_suffix, ns);
     }
@@ -74,73 +77,270 @@ __global__ void build_index_kernel(ReadsDev R, PsDev P, SeedTable tp, SeedTable 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Phase 1.  Canonical order of the reference pushes is (L asc, c asc) and only the last 3 survive,
+// Overhang tail of an edge (x -> c, offset o): the last min(o, 32) nucleotides of x[0 .. o), top-aligned in 64
+// bits (nucleotide o-1 in bits 62..63).  Phase 2 decides "x[oa-o .. oa) == b[0 .. o)" from two such tails when o <= 32.
+__device__ __forceinline__ uint64_t overhang_tail(const uint32_t *__restrict__ p, uint32_t o) {
+    if (o == 0) return 0;
+    if (o >= 32) return bits64(p, 2u * (o - 32u));
+    return bits64(p, 0) << (64u - 2u * o);
+}
+
+// Phase 1, generic path.  Canonical order of the reference pushes is (L asc, c asc) and only the last 3 survive,
 // so the result is the 3 largest (L, c): scan L downwards 32 lengths at a time and stop at 3 hits.
-__global__ void __launch_bounds__(kThreads)
-phase1_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, int2 *__restrict__ fwd,
-              uint32_t *__restrict__ indeg) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t warp = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    const uint32_t n_warps = gridDim.x * kWarpsPerBlock;
-    for (uint64_t bb = (uint64_t) lo + warp; bb < hi; bb += n_warps) {
-        const uint32_t b = (uint32_t) bb;
-        const uint32_t lenb = R.len[b];
-        int32_t rc[kSmallEdgesKept], ro[kSmallEdgesKept];
+__device__ __forceinline__ void phase1_generic_read(const ReadsDev &R, const SeedTable &T, const PsDev &P, uint32_t b,
+                                                    int2 *__restrict__ slots, uint64_t *__restrict__ slots_t,
+                                                    uint32_t *__restrict__ indeg, int lane) {
+    const uint32_t lenb = R.len[b];
+    int32_t rc[kSmallEdgesKept], ro[kSmallEdgesKept];
 #pragma unroll
-        for (int k = 0; k < kSmallEdgesKept; k++) rc[k] = -1, ro[k] = 0;
-        int found = 0;
-        int64_t l_hi = (int64_t) lenb - P.min_offset;
-        if (l_hi > P.rs - 1) l_hi = P.rs - 1;
-        if (l_hi > P.max_l) l_hi = P.max_l;
-        if (lenb != 0 && flag_from(R, b) && l_hi >= P.lmin) {
-            const uint32_t *pb = read_ptr(R, b);
-            for (int32_t l_top = (int32_t) l_hi; l_top >= P.lmin && found < kSmallEdgesKept; l_top -= 32) {
-                const int32_t L = l_top - lane;
-                // per-lane: the (up to) 3 largest matching c at this L, t0 > t1 > t2 (kNone = empty)
-                uint32_t t0 = kNone, t1 = kNone, t2 = kNone;
-                int nh = 0;
-                if (L >= P.lmin) {
-                    const uint32_t o = lenb - (uint32_t) L;
-                    const uint64_t w = bits64(pb, 2u * o) & P.seed_mask;
-                    probe_seed(T, mix64(w), [&](uint32_t c) {
-                        if (c == b) return;
-                        if ((int64_t) R.len[c] < L) return;
-                        // prefix(c, L) == suffix(b, L)
-                        if (!equal_bits_aligned(pb, 2u * o, read_ptr(R, c), 2u * (uint32_t) L)) return;
-                        nh++;
-                        if (t0 == kNone || c > t0) { t2 = t1; t1 = t0; t0 = c; }
-                        else if (t1 == kNone || c > t1) { t2 = t1; t1 = c; }
-                        else if (t2 == kNone || c > t2) { t2 = c; }
-                    });
-                    if (nh > kSmallEdgesKept) nh = kSmallEdgesKept;
-                }
-                unsigned m = __ballot_sync(kFull, nh > 0);
-                while (m && found < kSmallEdgesKept) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int cnt = __shfl_sync(kFull, nh, src);
-                    const uint32_t s0 = __shfl_sync(kFull, t0, src);
-                    const uint32_t s1 = __shfl_sync(kFull, t1, src);
-                    const uint32_t s2 = __shfl_sync(kFull, t2, src);
-                    const int32_t off = (int32_t) lenb - (l_top - src);
-                    for (int k = 0; k < cnt && found < kSmallEdgesKept; k++) {
-                        const uint32_t c = k == 0 ? s0 : (k == 1 ? s1 : s2);
+    for (int k = 0; k < kSmallEdgesKept; k++) rc[k] = -1, ro[k] = 0;
+    int found = 0;
+    int64_t l_hi = (int64_t) lenb - P.min_offset;
+    if (l_hi > P.rs - 1) l_hi = P.rs - 1;
+    if (l_hi > P.max_l) l_hi = P.max_l;
+    const uint32_t *pb = read_ptr(R, b);
+    if (lenb != 0 && flag_from(R, b) && l_hi >= P.lmin) {
+        for (int32_t l_top = (int32_t) l_hi; l_top >= P.lmin && found < kSmallEdgesKept; l_top -= 32) {
+            const int32_t L = l_top - lane;
+            // per-lane: the (up to) 3 largest matching c at this L, t0 > t1 > t2 (kNone = empty)
+            uint32_t t0 = kNone, t1 = kNone, t2 = kNone;
+            int nh = 0;
+            if (L >= P.lmin) {
+                const uint32_t o = lenb - (uint32_t) L;
+                const uint64_t w = bits64(pb, 2u * o) & P.seed_mask;
+                probe_seed(T, mix64(w), [&](uint32_t c) {
+                    if (c == b) return;
+                    if ((int64_t) R.len[c] < L) return;
+                    // prefix(c, L) == suffix(b, L)
+                    if (!equal_bits_aligned(pb, 2u * o, read_ptr(R, c), 2u * (uint32_t) L)) return;
+                    nh++;
+                    if (t0 == kNone || c > t0) { t2 = t1; t1 = t0; t0 = c; }
+                    else if (t1 == kNone || c > t1) { t2 = t1; t1 = c; }
+                    else if (t2 == kNone || c > t2) { t2 = c; }
+                });
+                if (nh > kSmallEdgesKept) nh = kSmallEdgesKept;
+            }
+            unsigned m = __ballot_sync(kFull, nh > 0);
+            while (m && found < kSmallEdgesKept) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int cnt = __shfl_sync(kFull, nh, src);
+                const uint32_t s0 = __shfl_sync(kFull, t0, src);
+                const uint32_t s1 = __shfl_sync(kFull, t1, src);
+                const uint32_t s2 = __shfl_sync(kFull, t2, src);
+                const int32_t off = (int32_t) lenb - (l_top - src);
+                for (int k = 0; k < cnt && found < kSmallEdgesKept; k++) {
+                    const uint32_t c = k == 0 ? s0 : (k == 1 ? s1 : s2);
 #pragma unroll
-                        for (int q = 0; q < kSmallEdgesKept; q++)
-                            if (q == found) rc[q] = (int32_t) c, ro[q] = off;
-                        found++;
-                    }
+                    for (int q = 0; q < kSmallEdgesKept; q++)
+                        if (q == found) rc[q] = (int32_t) c, ro[q] = off;
+                    found++;
                 }
             }
         }
-        if (lane < kSmallEdgesKept) {
-            int32_t c = -1, o = 0;
+    }
+    if (lane < kSmallEdgesKept) {
+        int32_t c = -1, o = 0;
 #pragma unroll
-            for (int q = 0; q < kSmallEdgesKept; q++)
-                if (q == lane) c = rc[q], o = ro[q];
-            fwd[(uint64_t) (b - lo) * kSmallEdgesKept + lane] = make_int2(c, o);
-            if (c >= 0 && indeg) atomicAdd(indeg + c, 1u);
+        for (int q = 0; q < kSmallEdgesKept; q++)
+            if (q == lane) c = rc[q], o = ro[q];
+        slots[lane] = make_int2(c, o);
+        if (c >= 0) {
+            slots_t[lane] = overhang_tail(pb, (uint32_t) o);
+            if (indeg) atomicAdd(indeg + c, 1u);
         }
+    }
+}
+
+// generic phase 1 over a queue of source reads (the reads the fast kernel handed back)
+__global__ void __launch_bounds__(kThreads)
+phase1_queue_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, const uint32_t *__restrict__ queue,
+                    const uint32_t *__restrict__ n_queue, int2 *__restrict__ fwd, uint64_t *__restrict__ fwd_t,
+                    uint32_t *__restrict__ indeg) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const uint32_t n_warps = gridDim.x * kWarpsPerBlock;
+    const uint32_t n = *n_queue;
+    for (uint32_t q = warp; q < n; q += n_warps) {
+        const uint32_t b = queue[q];
+        const uint64_t s0 = (uint64_t) (b - lo) * kSmallEdgesKept;
+        phase1_generic_read(R, T, P, b, fwd + s0, fwd_t + s0, indeg, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast paths.  One warp per read; the warp's own read is staged in shared memory, every lane handles one overlap
+// length: one seed-window hash, one 32-byte bucket probe, and -- for the lanes whose tag matched -- one
+// straight-line exact compare.  Anything unusual (more than two tag matches for one window, reads longer than the
+// staged window, too many in-neighbours, ...) hands the read to the generic path through a queue.
+constexpr int kOwnWords = 32;  // staged part of the own read: 512 nucleotides
+constexpr int kOwnPad = 8;
+constexpr int kOwnStride = kOwnWords + kOwnPad;
+constexpr int kMaxArrivals = 32;
+
+__device__ __forceinline__ uint64_t sbits64(const uint32_t *own, uint32_t bit) {
+    const uint32_t w = bit >> 5, s = bit & 31u;
+    const uint32_t a = own[w], b = own[w + 1], c = own[w + 2];
+    return (uint64_t) __funnelshift_r(a, b, s) | ((uint64_t) __funnelshift_r(b, c, s) << 32);
+}
+__device__ __forceinline__ uint64_t overhang_tail_own(const uint32_t *own, uint32_t o) {
+    if (o == 0) return 0;
+    if (o >= 32) return sbits64(own, 2u * (o - 32u));
+    return sbits64(own, 0) << (64u - 2u * o);
+}
+
+// Lane-local probe of one seed window (all 32 lanes must call; `valid` switches a lane off): the first two read
+// ids whose tag matches and the number of tag matches.
+__device__ __forceinline__ void probe_two(const SeedTable &t, uint64_t window, bool valid, uint32_t &c0, uint32_t &c1,
+                                          int &n) {
+    const uint64_t h = mix64(window);
+    const uint32_t tag = tag_of(h);
+    uint32_t bk = bucket_of(h, t.n_buckets);
+    n = 0;
+    c0 = c1 = kNone;
+    bool more = valid;
+    while (__any_sync(kFull, more)) {
+        if (more) {
+            uint64_t e[4];
+            load_bucket(t.slots + (uint64_t) bk * kSlotsPerBucket, e);
+#pragma unroll
+            for (int s = 0; s < kSlotsPerBucket; s++) {
+                if ((uint32_t) (e[s] >> 32) == tag && e[s] != kEmptySlot) {
+                    if (n == 0) c0 = (uint32_t) e[s];
+                    else if (n == 1) c1 = (uint32_t) e[s];
+                    n++;
+                }
+            }
+            more = e[kSlotsPerBucket - 1] != kEmptySlot;  // buckets fill front to back: a full one chains on
+            bk = (bk + 1 == t.n_buckets) ? 0u : bk + 1;
+        }
+    }
+}
+
+// own[bita .. bita+nbits) == pc[0 .. nbits) ?   own = staged read in shared memory, pc = candidate in HBM
+__device__ __forceinline__ bool equal_own_shifted(const uint32_t *own, uint32_t bita, const uint32_t *__restrict__ pc,
+                                                  uint32_t nbits) {
+    const uint32_t s = bita & 31u, wo = bita >> 5, nw = (nbits + 31u) >> 5;
+    uint32_t diff = 0;
+    for (uint32_t k0 = 0; k0 < nw; k0 += 4) {
+        uint32_t wc[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) wc[j] = (k0 + j < nw) ? __ldg(pc + k0 + j) : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t k = k0 + j;
+            const uint32_t x = __funnelshift_r(own[wo + k], own[wo + k + 1], s) ^ wc[j];
+            const uint32_t left = k < nw ? nbits - 32u * k : 0u;
+            diff |= x & (left >= 32u ? 0xFFFFFFFFu : ((1u << left) - 1u));
+        }
+    }
+    return diff == 0;
+}
+
+// pb[bitb .. bitb+nbits) == own[0 .. nbits) ?   pb = candidate in HBM (shifted), own = staged read
+__device__ __forceinline__ bool equal_cand_shifted(const uint32_t *__restrict__ pb, uint32_t bitb, const uint32_t *own,
+                                                   uint32_t nbits) {
+    const uint32_t s = bitb & 31u, nw = (nbits + 31u) >> 5;
+    const uint32_t *q = pb + (bitb >> 5);
+    uint32_t diff = 0;
+    for (uint32_t k0 = 0; k0 < nw; k0 += 4) {
+        uint32_t wb[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++) wb[j] = (k0 + j <= nw) ? __ldg(q + k0 + j) : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t k = k0 + j;
+            const uint32_t x = __funnelshift_r(wb[j], wb[j + 1], s) ^ own[k];
+            const uint32_t left = k < nw ? nbits - 32u * k : 0u;
+            diff |= x & (left >= 32u ? 0xFFFFFFFFu : ((1u << left) - 1u));
+        }
+    }
+    return diff == 0;
+}
+
+__device__ __forceinline__ void stage_own(uint32_t *own, const uint32_t *__restrict__ p, uint32_t n_words, int lane) {
+    __syncwarp();
+    for (int k = lane; k < kOwnStride; k += 32) own[k] = (uint32_t) k < n_words ? __ldg(p + k) : 0u;
+    __syncwarp();
+}
+
+// Phase 1, fast path: source read b, lanes = overlap lengths from min(rs-1, len) downwards.
+template <bool UNIFORM>
+__global__ void __launch_bounds__(kThreads)
+phase1_fast_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, int2 *__restrict__ fwd,
+                   uint64_t *__restrict__ fwd_t, uint32_t *__restrict__ indeg, uint32_t *__restrict__ hard_queue,
+                   uint32_t *n_hard, int force_hard) {
+    __shared__ uint32_t s_own[kWarpsPerBlock][kOwnStride];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t *own = s_own[wib];
+    const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib;
+    const uint32_t n_warps = gridDim.x * kWarpsPerBlock;
+    for (uint64_t bb = (uint64_t) lo + warp; bb < hi; bb += n_warps) {
+        const uint32_t b = (uint32_t) bb;
+        const uint32_t lenb = UNIFORM ? P.uniform_len : R.len[b];
+        int2 *slots = fwd + (uint64_t) (b - lo) * kSmallEdgesKept;
+        uint64_t *slots_t = fwd_t + (uint64_t) (b - lo) * kSmallEdgesKept;
+        int64_t l_hi = (int64_t) lenb - P.min_offset;
+        if (l_hi > P.rs - 1) l_hi = P.rs - 1;
+        if (l_hi > P.max_l) l_hi = P.max_l;
+        int found = 0;
+        bool hard = false;
+        if (lenb != 0 && flag_from(R, b) && l_hi >= P.lmin) {
+            if (force_hard || lenb > (uint32_t) kOwnWords * 16u) {
+                hard = true;
+            } else {
+                stage_own(own, read_ptr(R, b), (lenb + 15u) >> 4, lane);
+                for (int32_t l_top = (int32_t) l_hi; l_top >= P.lmin && found < kSmallEdgesKept; l_top -= 32) {
+                    const int32_t L = l_top - lane;
+                    const bool valid = L >= P.lmin;
+                    const uint32_t o = valid ? lenb - (uint32_t) L : 0u;
+                    const uint64_t win = sbits64(own, 2u * o) & P.seed_mask;
+                    uint32_t c0, c1;
+                    int n;
+                    probe_two(T, win, valid, c0, c1, n);
+                    if (__any_sync(kFull, n > 2)) {
+                        hard = true;
+                        break;
+                    }
+                    bool ok0 = false, ok1 = false;
+                    if (n > 0 && c0 != b && (UNIFORM || (int64_t) R.len[c0] >= L))
+                        ok0 = equal_own_shifted(own, 2u * o, read_ptr(R, c0), 2u * (uint32_t) L);
+                    if (n > 1 && c1 != b && (UNIFORM || (int64_t) R.len[c1] >= L))
+                        ok1 = equal_own_shifted(own, 2u * o, read_ptr(R, c1), 2u * (uint32_t) L);
+                    const int nh = (int) ok0 + (int) ok1;
+                    // within one length the larger target id is the later push
+                    uint32_t h0 = ok0 ? c0 : c1, h1 = c1;
+                    if (nh == 2 && c1 > c0) h0 = c1, h1 = c0;
+                    const unsigned m1 = __ballot_sync(kFull, nh >= 1), m2 = __ballot_sync(kFull, nh >= 2);
+                    if (nh) {
+                        const int rank = found + __popc(m1 & lt) + __popc(m2 & lt);
+                        if (rank < kSmallEdgesKept) {
+                            const uint64_t t = overhang_tail_own(own, o);
+                            slots[rank] = make_int2((int32_t) h0, (int32_t) o);
+                            slots_t[rank] = t;
+                            if (indeg) atomicAdd(indeg + h0, 1u);
+                            if (nh == 2 && rank + 1 < kSmallEdgesKept) {
+                                slots[rank + 1] = make_int2((int32_t) h1, (int32_t) o);
+                                slots_t[rank + 1] = t;
+                                if (indeg) atomicAdd(indeg + h1, 1u);
+                            }
+                        }
+                    }
+                    found += __popc(m1) + __popc(m2);
+                }
+            }
+        }
+        if (found > kSmallEdgesKept) found = kSmallEdgesKept;
+        __syncwarp();
+        if (hard) {
+            // undo what earlier batches already emitted; the generic path redoes the whole read
+            if (lane < found && indeg) atomicSub(indeg + (uint32_t) slots[lane].x, 1u);
+            if (lane == 0) hard_queue[atomicAdd(n_hard, 1u)] = b;
+        } else if (lane >= found && lane < kSmallEdgesKept) {
+            slots[lane] = make_int2(-1, 0);
+        }
+        __syncwarp();
     }
 }
 
@@ -174,9 +374,10 @@ __global__ void count_targets_kernel(const int32_t *__restrict__ triples, uint64
     }
 }
 
-__global__ void scatter_rev_slots_kernel(const int2 *__restrict__ fwd, uint32_t b_lo, uint64_t n_slots, uint32_t c_lo,
-                                         uint32_t c_hi, const uint32_t *__restrict__ rev_off, uint32_t *cursor,
-                                         int2 *__restrict__ rev) {
+__global__ void scatter_rev_slots_kernel(const int2 *__restrict__ fwd, const uint64_t *__restrict__ fwd_t, uint32_t b_lo,
+                                         uint64_t n_slots, uint32_t c_lo, uint32_t c_hi,
+                                         const uint32_t *__restrict__ rev_off, uint32_t *cursor, int2 *__restrict__ rev,
+                                         uint64_t *__restrict__ rev_t) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t) gridDim.x * blockDim.x) {
         const int2 e = fwd[i];
         if (e.x < 0) continue;
@@ -184,16 +385,21 @@ __global__ void scatter_rev_slots_kernel(const int2 *__restrict__ fwd, uint32_t 
         if (c < c_lo || c >= c_hi) continue;
         const uint32_t pos = rev_off[c - c_lo] + atomicSub(cursor + (c - c_lo), 1u) - 1u;
         rev[pos] = make_int2((int32_t) (b_lo + i / kSmallEdgesKept), e.y);
+        rev_t[pos] = fwd_t[i];
     }
 }
 
-__global__ void scatter_rev_triples_kernel(const int32_t *__restrict__ triples, uint64_t n, uint32_t c_lo, uint32_t c_hi,
-                                           const uint32_t *__restrict__ rev_off, uint32_t *cursor, int2 *__restrict__ rev) {
+__global__ void scatter_rev_triples_kernel(ReadsDev R, const int32_t *__restrict__ triples, uint64_t n, uint32_t c_lo,
+                                           uint32_t c_hi, const uint32_t *__restrict__ rev_off, uint32_t *cursor,
+                                           int2 *__restrict__ rev, uint64_t *__restrict__ rev_t) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
         const uint32_t c = (uint32_t) triples[3 * i + 1];
         if (c < c_lo || c >= c_hi) continue;
         const uint32_t pos = rev_off[c - c_lo] + atomicSub(cursor + (c - c_lo), 1u) - 1u;
-        rev[pos] = make_int2(triples[3 * i], triples[3 * i + 2]);
+        const int32_t b = triples[3 * i], o = triples[3 * i + 2];
+        rev[pos] = make_int2(b, o);
+        // the overhang tail does not travel with exchanged triples: rebuild it from the (replicated) read
+        rev_t[pos] = overhang_tail(read_ptr(R, (uint32_t) b), (uint32_t) o);
     }
 }
 
@@ -458,6 +664,172 @@ phase2_spill_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, const uint32_
     }
 }
 
+// Phase 2, fast path: target read c, lanes = overlap lengths from max(rs, lmin) upwards.  Arrivals (b, o) are
+// collected in canonical order (L asc, b asc) behind the in-neighbours of the transposed phase-1 graph; the
+// sequential replay of GraphCreatorPrefSuf.cpp:403-483 is then evaluated in closed form: an entry survives unless
+// a LATER arrival carries the same read id, or a later phase-2 arrival j with offset o_j > 0 has an overhang that
+// is a suffix of the entry's overhang (a[oa-oj .. oa) == b[0 .. oj), right offset >= 0).  The test is independent
+// of the list state because entries never return once removed.  With oj <= 32 it is one XOR + shift on the 64-bit
+// overhang tails.
+template <bool UNIFORM>
+__global__ void __launch_bounds__(kThreads)
+phase2_fast_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, const uint32_t *__restrict__ rev_off,
+                   const int2 *__restrict__ rev, const uint64_t *__restrict__ rev_t, Phase2Out out, int force_hard) {
+    __shared__ uint32_t s_own[kWarpsPerBlock][kOwnStride];
+    __shared__ uint32_t s_id[kWarpsPerBlock][kMaxArrivals], s_o[kWarpsPerBlock][kMaxArrivals],
+        s_len[kWarpsPerBlock][kMaxArrivals];
+    __shared__ uint64_t s_t[kWarpsPerBlock][kMaxArrivals];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t *own = s_own[wib];
+    uint32_t *a_id = s_id[wib], *a_o = s_o[wib], *a_len = s_len[wib];
+    uint64_t *a_t = s_t[wib];
+    const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib;
+    const uint32_t n_warps = gridDim.x * kWarpsPerBlock;
+    const int32_t l_lo = P.rs > P.lmin ? P.rs : P.lmin;
+    for (uint64_t cc = (uint64_t) lo + warp; cc < hi; cc += n_warps) {
+        const uint32_t c = (uint32_t) cc;
+        const uint32_t r0 = rev_off[c - lo], deg = rev_off[c - lo + 1] - r0;
+        const uint32_t lenc = UNIFORM ? P.uniform_len : R.len[c];
+        int64_t l_hi = lenc;
+        if (l_hi > P.max_l) l_hi = P.max_l;
+        const bool active = lenc != 0 && flag_to(R, c) && l_hi >= l_lo;
+        if (!active && deg == 0) continue;
+        bool hard = force_hard || deg > (uint32_t) kMaxArrivals;
+        uint32_t cnt = 0;
+        __syncwarp();
+        if (!hard) {
+            // in-neighbours from phase 1 (row of the transposed graph) take the first slots
+            if ((uint32_t) lane < deg) {
+                const int2 e = rev[r0 + lane];
+                a_id[lane] = (uint32_t) e.x;
+                a_o[lane] = (uint32_t) e.y;
+                a_t[lane] = rev_t[r0 + lane];
+                if (!UNIFORM) a_len[lane] = R.len[e.x];
+                if (deg > 1) {
+                    // the same source twice in one row needs retainOnlySmallestOffset: generic path
+                    const unsigned vm = deg >= 32 ? kFull : ((1u << deg) - 1u);
+                    const unsigned same = __match_any_sync(vm, (uint32_t) e.x);
+                    if (same != (1u << lane)) hard = true;
+                }
+            }
+            hard = __any_sync(kFull, hard);
+            cnt = deg;
+        }
+        if (!hard && active) {
+            const uint32_t need = (uint32_t) ((2 * l_hi + 31) >> 5);
+            const uint32_t have = (lenc + 15u) >> 4;
+            stage_own(own, read_ptr(R, c), need < have ? need : have, lane);
+            for (int32_t l_base = l_lo; l_base <= (int32_t) l_hi; l_base += 32) {
+                const int32_t L = l_base + lane;
+                const bool valid = L <= (int32_t) l_hi;
+                const uint64_t win = sbits64(own, valid ? 2u * (uint32_t) (L - P.seed_nt) : 0u) & P.seed_mask;
+                uint32_t b0, b1;
+                int n;
+                probe_two(T, win, valid, b0, b1, n);
+                bool bad = n > 2;
+                bool ok0 = false, ok1 = false;
+                uint32_t len0 = lenc, len1 = lenc;
+                uint64_t t0 = 0, t1 = 0;
+                if (n > 0 && b0 != c) {
+                    if (!UNIFORM) len0 = R.len[b0];
+                    if ((int64_t) len0 - P.min_offset >= L) {
+                        const uint32_t *pb = read_ptr(R, b0);
+                        const uint32_t o = len0 - (uint32_t) L;
+                        ok0 = equal_cand_shifted(pb, 2u * o, own, 2u * (uint32_t) L);
+                        if (ok0) {
+                            if (o > 32u) bad = true;
+                            else t0 = overhang_tail(pb, o);
+                        }
+                    }
+                }
+                if (n > 1 && b1 != c) {
+                    if (!UNIFORM) len1 = R.len[b1];
+                    if ((int64_t) len1 - P.min_offset >= L) {
+                        const uint32_t *pb = read_ptr(R, b1);
+                        const uint32_t o = len1 - (uint32_t) L;
+                        ok1 = equal_cand_shifted(pb, 2u * o, own, 2u * (uint32_t) L);
+                        if (ok1) {
+                            if (o > 32u) bad = true;
+                            else t1 = overhang_tail(pb, o);
+                        }
+                    }
+                }
+                const int nh = (int) ok0 + (int) ok1;
+                const unsigned m1 = __ballot_sync(kFull, nh >= 1), m2 = __ballot_sync(kFull, nh >= 2);
+                const uint32_t total = __popc(m1) + __popc(m2);
+                if (__any_sync(kFull, bad) || cnt + total > (uint32_t) kMaxArrivals) {
+                    hard = true;
+                    break;
+                }
+                if (nh) {
+                    // within one length the smaller source id arrives first
+                    const bool swap = nh == 2 && b1 < b0;
+                    const uint32_t slot = cnt + __popc(m1 & lt) + __popc(m2 & lt);
+                    const uint32_t f_id = ok0 && !swap ? b0 : b1, f_len = ok0 && !swap ? len0 : len1;
+                    const uint64_t f_t = ok0 && !swap ? t0 : t1;
+                    a_id[slot] = f_id;
+                    a_o[slot] = f_len - (uint32_t) L;
+                    a_len[slot] = f_len;
+                    a_t[slot] = f_t;
+                    if (nh == 2) {
+                        const uint32_t g_id = swap ? b0 : b1, g_len = swap ? len0 : len1;
+                        a_id[slot + 1] = g_id;
+                        a_o[slot + 1] = g_len - (uint32_t) L;
+                        a_len[slot + 1] = g_len;
+                        a_t[slot + 1] = swap ? t0 : t1;
+                    }
+                }
+                cnt += total;
+            }
+        }
+        __syncwarp();
+        if (hard) {
+            if (lane == 0) out.spill_queue[atomicAdd(out.n_spill, 1u)] = c;
+            continue;
+        }
+        if (cnt == 0) continue;
+        // closed-form replay
+        const bool have = (uint32_t) lane < cnt;
+        const uint32_t id = have ? a_id[lane] : kNone, o = have ? a_o[lane] : 0u;
+        const uint32_t len = (have && !UNIFORM) ? a_len[lane] : 0u;
+        const uint64_t t = have ? a_t[lane] : 0ull;
+        bool removed = false;
+        if (cnt > deg && cnt > 1) {
+            const unsigned vm = cnt >= 32 ? kFull : ((1u << cnt) - 1u);
+            if (have) {
+                const unsigned same = __match_any_sync(vm, id);
+                removed = (same >> lane) > 1u;  // a later arrival of the same read replaces this entry
+            }
+            for (int j = (int) cnt - 1; j >= (int) deg; j--) {
+                if (!__any_sync(kFull, have && !removed && lane < j)) break;
+                const uint32_t oj = a_o[j];
+                if (oj == 0) continue;
+                const uint64_t tj = a_t[j];
+                if (have && !removed && lane < j && o >= oj &&
+                    (UNIFORM || (int64_t) a_len[j] + (int64_t) (o - oj) - (int64_t) len >= 0) &&
+                    ((t ^ tj) >> (64u - 2u * oj)) == 0)
+                    removed = true;
+            }
+        }
+        const unsigned keep = __ballot_sync(kFull, have && !removed);
+        if (keep) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(out.n_edges, (unsigned long long) __popc(keep));
+            base = __shfl_sync(kFull, base, 0);
+            if (have && !removed) {
+                const unsigned long long pos = base + __popc(keep & lt);
+                if (pos < out.edge_cap) {
+                    out.triples[3 * pos] = (int32_t) id;
+                    out.triples[3 * pos + 1] = (int32_t) c;
+                    out.triples[3 * pos + 2] = (int32_t) o;
+                }
+                if (out.outdeg) atomicAdd(out.outdeg + id, 1u);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // CSR assembly
 __global__ void count_sources_kernel(const int32_t *__restrict__ triples, uint64_t n, uint32_t lo, uint32_t hi, int swap,
@@ -627,6 +999,7 @@ __global__ void fill_u64_kernel(uint64_t *p, uint64_t v, uint64_t n) {
 void launch_read_stats(const ReadsDev &R, int lmin, int min_offset, ReadStats *d_stats, cudaStream_t s,
                        const LaunchCfg &cfg) {
     cudaMemsetAsync(d_stats, 0, sizeof(ReadStats), s);
+    cudaMemsetAsync(&d_stats->min_len, 0xFF, sizeof(uint32_t), s);
     read_stats_kernel<<<grid_for(R.n, 256, cfg), 256, 0, s>>>(R, lmin, min_offset, d_stats);
     bump(cfg);
 }
@@ -638,9 +1011,20 @@ void launch_build_index(const ReadsDev &R, const PsDev &P, SeedTable prefix, See
 }
 
 void launch_phase1(const ReadsDev &R, const SeedTable &prefix, const PsDev &P, uint32_t lo, uint32_t hi, int2 *fwd,
-                   uint32_t *indeg, cudaStream_t s, const LaunchCfg &cfg) {
+                   uint64_t *fwd_t, uint32_t *indeg, uint32_t *hard_queue, uint32_t *n_hard, int force_hard,
+                   cudaStream_t s, const LaunchCfg &cfg) {
     if (hi <= lo) return;
-    phase1_kernel<<<grid_for(hi - lo, kWarpsPerBlock, cfg, 8), kThreads, 0, s>>>(R, prefix, P, lo, hi, fwd, indeg);
+    const int grid = grid_for(hi - lo, kWarpsPerBlock, cfg, 8);
+    if (P.uniform_len)
+        phase1_fast_kernel<true><<<grid, kThreads, 0, s>>>(R, prefix, P, lo, hi, fwd, fwd_t, indeg, hard_queue, n_hard,
+                                                           force_hard);
+    else
+        phase1_fast_kernel<false><<<grid, kThreads, 0, s>>>(R, prefix, P, lo, hi, fwd, fwd_t, indeg, hard_queue, n_hard,
+                                                            force_hard);
+    bump(cfg);
+    // the reads the fast kernel handed back (device-side count: no host round trip; usually zero)
+    phase1_queue_kernel<<<grid_for(force_hard ? hi - lo : 4096, kWarpsPerBlock, cfg, 8), kThreads, 0, s>>>(
+        R, prefix, P, lo, hard_queue, n_hard, fwd, fwd_t, indeg);
     bump(cfg);
 }
 
@@ -659,21 +1043,34 @@ void launch_count_targets(const int32_t *triples, uint64_t n, uint32_t lo, uint3
     bump(cfg);
 }
 
-void launch_scatter_rev_slots(const int2 *fwd, uint32_t b_lo, uint32_t b_hi, uint32_t c_lo, uint32_t c_hi,
-                              const uint32_t *rev_off, uint32_t *cursor, int2 *rev, cudaStream_t s,
-                              const LaunchCfg &cfg) {
+void launch_scatter_rev_slots(const int2 *fwd, const uint64_t *fwd_t, uint32_t b_lo, uint32_t b_hi, uint32_t c_lo,
+                              uint32_t c_hi, const uint32_t *rev_off, uint32_t *cursor, int2 *rev, uint64_t *rev_t,
+                              cudaStream_t s, const LaunchCfg &cfg) {
     if (b_hi <= b_lo) return;
     const uint64_t n_slots = (uint64_t) (b_hi - b_lo) * kSmallEdgesKept;
-    scatter_rev_slots_kernel<<<grid_for(n_slots, 256, cfg), 256, 0, s>>>(fwd, b_lo, n_slots, c_lo, c_hi, rev_off,
-                                                                           cursor, rev);
+    scatter_rev_slots_kernel<<<grid_for(n_slots, 256, cfg), 256, 0, s>>>(fwd, fwd_t, b_lo, n_slots, c_lo, c_hi, rev_off,
+                                                                           cursor, rev, rev_t);
     bump(cfg);
 }
 
-void launch_scatter_rev_triples(const int32_t *triples, uint64_t n, uint32_t c_lo, uint32_t c_hi,
-                                const uint32_t *rev_off, uint32_t *cursor, int2 *rev, cudaStream_t s,
+void launch_scatter_rev_triples(const ReadsDev &R, const int32_t *triples, uint64_t n, uint32_t c_lo, uint32_t c_hi,
+                                const uint32_t *rev_off, uint32_t *cursor, int2 *rev, uint64_t *rev_t, cudaStream_t s,
                                 const LaunchCfg &cfg) {
     if (!n) return;
-    scatter_rev_triples_kernel<<<grid_for(n, 256, cfg), 256, 0, s>>>(triples, n, c_lo, c_hi, rev_off, cursor, rev);
+    scatter_rev_triples_kernel<<<grid_for(n, 256, cfg), 256, 0, s>>>(R, triples, n, c_lo, c_hi, rev_off, cursor, rev,
+                                                                       rev_t);
+    bump(cfg);
+}
+
+void launch_phase2_fast(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo, uint32_t hi,
+                        const uint32_t *rev_off, const int2 *rev, const uint64_t *rev_t, const Phase2Out &out,
+                        int force_hard, cudaStream_t s, const LaunchCfg &cfg) {
+    if (hi <= lo) return;
+    const int grid = grid_for(hi - lo, kWarpsPerBlock, cfg, 8);
+    if (P.uniform_len)
+        phase2_fast_kernel<true><<<grid, kThreads, 0, s>>>(R, suffix, P, lo, hi, rev_off, rev, rev_t, out, force_hard);
+    else
+        phase2_fast_kernel<false><<<grid, kThreads, 0, s>>>(R, suffix, P, lo, hi, rev_off, rev, rev_t, out, force_hard);
     bump(cfg);
 }
 

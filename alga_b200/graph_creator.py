@@ -100,8 +100,10 @@ class GraphCreatorPrefSuf:
     the C++ shim does when it gathers ``vector<Read*>``; the upload then runs at full host->device rate."""
 
     def __init__(self, reads: ReadSet, min_overlap: int, rs_min_overlap: int, min_offset: int = 0,
-                 max_len_cap: int = 500, device: int = 0, list_cap: int = 0, pinned: bool = False):
-        self.params = _lib.PsParams(min_overlap, rs_min_overlap, min_offset, max_len_cap, device, list_cap)
+                 max_len_cap: int = 500, device: int = 0, list_cap: int = 0, pinned: bool = False,
+                 force_generic: bool = False):
+        self.params = _lib.PsParams(min_overlap, rs_min_overlap, min_offset, max_len_cap, device, list_cap,
+                                    _lib.PS_FORCE_GENERIC if force_generic else 0)
         self._pins = []
         if pinned:
             def pin(a):

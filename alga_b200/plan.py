@@ -76,10 +76,11 @@ class PrefSufPlan:
     """One GPU's workspace for GraphCreatorPrefSuf (GraphCreatorPrefSuf.cpp:73-126 + main.cpp:291)."""
 
     def __init__(self, min_overlap: int, rs_min_overlap: int, min_offset: int = 0, max_len_cap: int = 500,
-                 device: int | torch.device = 0, list_cap: int = 0):
+                 device: int | torch.device = 0, list_cap: int = 0, force_generic: bool = False):
         self.lib = _lib.load()
         self.device = torch.device("cuda", device) if isinstance(device, int) else device
-        self.params = _lib.PsParams(min_overlap, rs_min_overlap, min_offset, max_len_cap, self.device.index or 0, list_cap)
+        self.params = _lib.PsParams(min_overlap, rs_min_overlap, min_offset, max_len_cap, self.device.index or 0, list_cap,
+                                    _lib.PS_FORCE_GENERIC if force_generic else 0)
         self._h = C.c_void_p()
         _lib.check(self.lib.alga_ps_plan_create(C.byref(self._h), C.byref(self.params)))
         self.reads: DeviceReads | None = None

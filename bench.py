@@ -164,7 +164,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64/u32 (polynomial hashes mod 1e18+3, 1e9+7)", "data": "synthetic",
-        "config": workload_config(args.workload, args.gpus, sample=True),
+        "config": workload_config(args.workload, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cal["threads"], "kind": cal["kind"], "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -173,7 +173,7 @@ def run_reference(args):
     return 0
 
 
-def workload_config(workload: str, n_gpus: int, sample: bool = False) -> dict:
+def workload_config(workload: str, n_gpus: int) -> dict:
     from alga_b200 import synth
 
     kw = synth.CONFIGS[workload]
@@ -182,8 +182,6 @@ def workload_config(workload: str, n_gpus: int, sample: bool = False) -> dict:
             f"{kw['coverage']}x, error {kw.get('error', 0.0):g}, --error_rate=0 (GraphCreatorPrefSuf only)")
     if n_gpus > 1:
         desc += f"; weak scaling: {n_gpus} such chromosomes (seeds {kw['seed']}+100r), reads interleaved over ranks"
-    if sample:
-        desc += "; CPU arm runs a bounded genome-scaled sample of it (same read length and coverage)"
     return {"workload": desc, "l2": "explicit flush (256 MiB write) between timed steps; step inputs+index also exceed L2",
             "sharding": "1 GPU" if n_gpus == 1 else f"read-id ranges over {n_gpus} GPUs, replicated packed reads + seed index"}
 

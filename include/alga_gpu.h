@@ -49,9 +49,12 @@ typedef struct {
     int32_t min_offset;       /* Params::MIN_OFFSET_FOR_ALIGNMENT (Params.cpp:709), default 0 */
     int32_t max_len_cap;      /* overlap length cap, 500 in GraphCreatorPrefSuf.cpp:92; <=0 means 500 */
     int32_t device;           /* CUDA device ordinal */
-    int32_t list_cap;         /* tuning/testing: on-chip in-neighbour list capacity per target read;
-                                 <=0 = default.  Targets that exceed it take the global-memory path. */
+    int32_t list_cap;         /* testing: > 0 runs phase 2 on the generic kernel with this on-chip in-neighbour list
+                                 capacity per target read (targets that exceed it take the global-memory path);
+                                 <= 0 = the fast kernel */
+    int32_t flags;            /* ALGA_PS_* bits */
 } alga_ps_params;
+#define ALGA_PS_FORCE_GENERIC 1 /* testing: every read takes the generic (fallback) kernels */
 
 /* Forward adjacency in CSR form: row b lists (nbr[k], off[k]) for row_off[b] <= k < row_off[b+1],
  * meaning "read nbr starts at position off of read b" -- exactly what Graph::V[b] holds after

@@ -32,7 +32,7 @@ def test_header_symbols_exported_and_bound():
 def test_struct_layouts_match_header():
     # sizes the C compiler gives the ABI structs (LP64): guards the ctypes mirrors against drift
     assert C.sizeof(_lib.Reads) == 56
-    assert C.sizeof(_lib.PsParams) == 24
+    assert C.sizeof(_lib.PsParams) == 28
     assert C.sizeof(_lib.Csr) == 48
     assert C.sizeof(_lib.Timing) == 48 + 64
     assert C.sizeof(_lib.VerifyParams) == 24

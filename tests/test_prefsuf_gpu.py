@@ -25,6 +25,15 @@ def test_edge_set_matches_oracle(gpu, name):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_generic_path_matches_oracle(gpu, name):
+    """Every read forced through the fallback kernels (phase-1 queue kernel, phase-2 global-memory lists)."""
+    rs, lmin, rsmin, mo = build_case(name)
+    want = oracle.prefsuf(rs, lmin, rsmin, mo)
+    g, _ = _run(rs, lmin, rsmin, mo, force_generic=True)
+    assert np.array_equal(g.edges(), want)
+
+
 @pytest.mark.parametrize("name", ["cfg3_small", "varlen_dups", "periodic_dups", "periodic", "cfg5_small"])
 @pytest.mark.parametrize("cap", [1, 2, 5])
 def test_spill_path_matches_oracle(gpu, name, cap):
