@@ -214,21 +214,30 @@ int compute_stats(alga_ps_plan *plan, cudaStream_t s, uint32_t max_len_hint) {
 }
 
 uint32_t buckets_for(uint32_t entries) {
-    // load factor <= 0.5 with 4-slot buckets
-    uint64_t nb = ((uint64_t) entries * 2 + kSlotsPerBucket - 1) / kSlotsPerBucket;
+    // mean occupancy 2 of 8 slots: P(bucket full) ~ 1e-3, so a probe rarely chains into a second sector
+    uint64_t nb = ((uint64_t) entries + 1) / 2;
     if (nb < 64) nb = 64;
     return (uint32_t) nb;
 }
 
+void size_table(SeedTable &t, uint32_t entries, uint32_t n_reads) {
+    t.n_buckets = buckets_for(entries);
+    uint32_t bits = 1;
+    while (bits < 31 && (1ull << bits) < (uint64_t) n_reads) bits++;
+    t.id_bits = bits;
+    t.id_mask = (uint32_t) ((1ull << bits) - 1ull);
+    t.tag_mask = (uint32_t) ((1ull << (32 - bits)) - 1ull);
+}
+
 int stage_index(alga_ps_plan *plan, cudaStream_t s) {
     if (!plan->bound) return fail(ALGA_E_INVALID, "no read set bound to the plan");
-    plan->Tp.n_buckets = buckets_for(plan->stats.n_prefix);
-    plan->Ts.n_buckets = buckets_for(plan->stats.n_suffix);
-    const size_t bp = (size_t) plan->Tp.n_buckets * kSlotsPerBucket * 8, bs = (size_t) plan->Ts.n_buckets * kSlotsPerBucket * 8;
+    size_table(plan->Tp, plan->stats.n_prefix, plan->R.n);
+    size_table(plan->Ts, plan->stats.n_suffix, plan->R.n);
+    const size_t bp = (size_t) plan->Tp.n_buckets * kSlotsPerBucket * 4, bs = (size_t) plan->Ts.n_buckets * kSlotsPerBucket * 4;
     CKR(plan->tp.ensure(bp));
     CKR(plan->ts.ensure(bs));
-    plan->Tp.slots = plan->tp.as<uint64_t>();
-    plan->Ts.slots = plan->ts.as<uint64_t>();
+    plan->Tp.slots = plan->tp.as<uint32_t>();
+    plan->Ts.slots = plan->ts.as<uint32_t>();
     CK(cudaMemsetAsync(plan->tp.p, 0xFF, bp, s));
     CK(cudaMemsetAsync(plan->ts.p, 0xFF, bs, s));
     launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, s, plan->cfg);
@@ -401,7 +410,7 @@ int alga_ps_plan_bind_reads_device(alga_ps_plan *plan, const alga_reads *r, uint
     if (!plan || !r) return fail(ALGA_E_INVALID, "null argument");
     if (r->n_reads && (!r->words || !r->len_nt)) return fail(ALGA_E_INVALID, "words / len_nt must not be null");
     if (!r->word_off && r->stride_words == 0 && r->n_reads) return fail(ALGA_E_INVALID, "word_off is null and stride_words is 0");
-    if (r->n_reads >= 0xFFFFFFF0u) return fail(ALGA_E_INVALID, "too many reads");
+    if (r->n_reads > 0x7FFFFFFFu) return fail(ALGA_E_INVALID, "too many reads (ids are int32 in the edge arrays)");
     CKR(use_device(plan));
     plan->R.words = r->words;
     plan->R.word_off = r->word_off;

@@ -5,9 +5,9 @@
 
 namespace alga {
 
-constexpr uint64_t kEmptySlot = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint32_t kEmptySlot = 0xFFFFFFFFu;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
-constexpr int kSlotsPerBucket = 4;  // 4 x 8 B = one 32-byte DRAM sector
+constexpr int kSlotsPerBucket = 8;  // 8 x 4 B = one 32-byte DRAM sector
 constexpr int kSmallEdgesKept = 3;  // SOES, GraphCreatorPrefSuf.h:62
 constexpr int kHeadWords = 4;       // cached head of a read: first 64 nucleotides
 constexpr int kHeadNt = kHeadWords * 16;
@@ -42,10 +42,15 @@ struct PsDev {
     uint64_t seed_mask;  // low 2K bits
 };
 
-// Seed index: open addressing, 4-slot buckets, entry = (tag << 32) | read id.
+// Seed index: open addressing, one 32-byte sector per bucket, 8 entries of (tag << id_bits) | read id.  The tag
+// takes whatever bits the read id leaves free (10 bits for 4 M reads, 5 for 128 M); a false tag hit only costs an
+// exact compare.  Buckets are sized for a mean occupancy of 2 of 8, so a probe almost never leaves its first sector.
 struct SeedTable {
-    uint64_t *slots;
+    uint32_t *slots;
     uint32_t n_buckets;
+    uint32_t id_bits;   // bits of a read id, <= 31 (edge arrays carry int32 ids)
+    uint32_t id_mask;   // (1 << id_bits) - 1
+    uint32_t tag_mask;  // (1 << (32 - id_bits)) - 1; the all-ones tag is never used, so no entry equals kEmptySlot
 };
 
 // 32 bits of a packed read starting at bit position `bit`.
@@ -123,41 +128,46 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 __device__ __forceinline__ uint32_t bucket_of(uint64_t h, uint32_t n_buckets) {
     return __umulhi((uint32_t) (h >> 32), n_buckets);
 }
-__device__ __forceinline__ uint32_t tag_of(uint64_t h) { return (uint32_t) h; }
+// tag already shifted into entry position
+__device__ __forceinline__ uint32_t tag_of(const SeedTable &t, uint64_t h) {
+    uint32_t tag = (uint32_t) h & t.tag_mask;
+    if (tag == t.tag_mask) tag = 0;
+    return tag << t.id_bits;
+}
 
 // One 32-byte bucket = one 256-bit load (LDG.E.256 on sm_100a).
-__device__ __forceinline__ void load_bucket(const uint64_t *__restrict__ p, uint64_t (&e)[4]) {
-    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
-                 : "=l"(e[0]), "=l"(e[1]), "=l"(e[2]), "=l"(e[3])
+__device__ __forceinline__ void load_bucket(const uint32_t *__restrict__ p, uint32_t (&e)[8]) {
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(e[0]), "=r"(e[1]), "=r"(e[2]), "=r"(e[3]), "=r"(e[4]), "=r"(e[5]), "=r"(e[6]), "=r"(e[7])
                  : "l"(p));
 }
 
 // Walk the bucket chain of hash h and call f(read_id) for every entry whose tag matches.
 template <class F>
 __device__ __forceinline__ void probe_seed(const SeedTable &t, uint64_t h, F &&f) {
-    const uint32_t tag = tag_of(h);
+    const uint32_t tag = tag_of(t, h);
     uint32_t bk = bucket_of(h, t.n_buckets);
     while (true) {
-        uint64_t e[4];
+        uint32_t e[8];
         load_bucket(t.slots + (uint64_t) bk * kSlotsPerBucket, e);
 #pragma unroll
         for (int s = 0; s < kSlotsPerBucket; s++) {
             if (e[s] == kEmptySlot) return;
-            if ((uint32_t) (e[s] >> 32) == tag) f((uint32_t) e[s]);
+            if ((e[s] ^ tag) <= t.id_mask) f(e[s] & t.id_mask);
         }
         bk = (bk + 1 == t.n_buckets) ? 0u : bk + 1;
     }
 }
 
 __device__ __forceinline__ void insert_seed(const SeedTable &t, uint64_t h, uint32_t id) {
-    const uint64_t entry = ((uint64_t) tag_of(h) << 32) | id;
+    const uint32_t entry = tag_of(t, h) | id;
     uint32_t bk = bucket_of(h, t.n_buckets);
     while (true) {
-        unsigned long long *base = (unsigned long long *) (t.slots + (uint64_t) bk * kSlotsPerBucket);
+        uint32_t *base = t.slots + (uint64_t) bk * kSlotsPerBucket;
 #pragma unroll
         for (int s = 0; s < kSlotsPerBucket; s++) {
             if (base[s] != kEmptySlot) continue;
-            if (atomicCAS(base + s, (unsigned long long) kEmptySlot, (unsigned long long) entry) == kEmptySlot) return;
+            if (atomicCAS(base + s, kEmptySlot, entry) == kEmptySlot) return;
         }
         bk = (bk + 1 == t.n_buckets) ? 0u : bk + 1;
     }

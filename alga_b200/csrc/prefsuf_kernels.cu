@@ -194,68 +194,32 @@ __device__ __forceinline__ uint64_t overhang_tail_own(const uint32_t *own, uint3
 __device__ __forceinline__ void probe_two(const SeedTable &t, uint64_t window, bool valid, uint32_t &c0, uint32_t &c1,
                                           int &n) {
     const uint64_t h = mix64(window);
-    const uint32_t tag = tag_of(h);
+    const uint32_t tag = tag_of(t, h);
     uint32_t bk = bucket_of(h, t.n_buckets);
     n = 0;
     c0 = c1 = kNone;
     bool more = valid;
-    while (__any_sync(kFull, more)) {
+    do {
         if (more) {
-            uint64_t e[4];
+            uint32_t e[8];
             load_bucket(t.slots + (uint64_t) bk * kSlotsPerBucket, e);
+            uint32_t hm = 0;
 #pragma unroll
-            for (int s = 0; s < kSlotsPerBucket; s++) {
-                if ((uint32_t) (e[s] >> 32) == tag && e[s] != kEmptySlot) {
-                    if (n == 0) c0 = (uint32_t) e[s];
-                    else if (n == 1) c1 = (uint32_t) e[s];
-                    n++;
+            for (int s = 0; s < kSlotsPerBucket; s++) hm |= ((e[s] ^ tag) <= t.id_mask ? 1u : 0u) << s;
+            if (hm) {
+#pragma unroll
+                for (int s = 0; s < kSlotsPerBucket; s++) {
+                    if (hm & (1u << s)) {
+                        if (n == 0) c0 = e[s] & t.id_mask;
+                        else if (n == 1) c1 = e[s] & t.id_mask;
+                        n++;
+                    }
                 }
             }
             more = e[kSlotsPerBucket - 1] != kEmptySlot;  // buckets fill front to back: a full one chains on
             bk = (bk + 1 == t.n_buckets) ? 0u : bk + 1;
         }
-    }
-}
-
-// own[bita .. bita+nbits) == pc[0 .. nbits) ?   own = staged read in shared memory, pc = candidate in HBM
-__device__ __forceinline__ bool equal_own_shifted(const uint32_t *own, uint32_t bita, const uint32_t *__restrict__ pc,
-                                                  uint32_t nbits) {
-    const uint32_t s = bita & 31u, wo = bita >> 5, nw = (nbits + 31u) >> 5;
-    uint32_t diff = 0;
-    for (uint32_t k0 = 0; k0 < nw; k0 += 4) {
-        uint32_t wc[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) wc[j] = (k0 + j < nw) ? __ldg(pc + k0 + j) : 0u;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t k = k0 + j;
-            const uint32_t x = __funnelshift_r(own[wo + k], own[wo + k + 1], s) ^ wc[j];
-            const uint32_t left = k < nw ? nbits - 32u * k : 0u;
-            diff |= x & (left >= 32u ? 0xFFFFFFFFu : ((1u << left) - 1u));
-        }
-    }
-    return diff == 0;
-}
-
-// pb[bitb .. bitb+nbits) == own[0 .. nbits) ?   pb = candidate in HBM (shifted), own = staged read
-__device__ __forceinline__ bool equal_cand_shifted(const uint32_t *__restrict__ pb, uint32_t bitb, const uint32_t *own,
-                                                   uint32_t nbits) {
-    const uint32_t s = bitb & 31u, nw = (nbits + 31u) >> 5;
-    const uint32_t *q = pb + (bitb >> 5);
-    uint32_t diff = 0;
-    for (uint32_t k0 = 0; k0 < nw; k0 += 4) {
-        uint32_t wb[5];
-#pragma unroll
-        for (int j = 0; j < 5; j++) wb[j] = (k0 + j <= nw) ? __ldg(q + k0 + j) : 0u;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t k = k0 + j;
-            const uint32_t x = __funnelshift_r(wb[j], wb[j + 1], s) ^ own[k];
-            const uint32_t left = k < nw ? nbits - 32u * k : 0u;
-            diff |= x & (left >= 32u ? 0xFFFFFFFFu : ((1u << left) - 1u));
-        }
-    }
-    return diff == 0;
+    } while (__any_sync(kFull, more));
 }
 
 __device__ __forceinline__ void stage_own(uint32_t *own, const uint32_t *__restrict__ p, uint32_t n_words, int lane) {
@@ -264,7 +228,38 @@ __device__ __forceinline__ void stage_own(uint32_t *own, const uint32_t *__restr
     __syncwarp();
 }
 
-// Phase 1, fast path: source read b, lanes = overlap lengths from min(rs-1, len) downwards.
+// Warp-cooperative exact compares: the warp is cut into V groups of gs lanes, group g verifies one candidate, lane
+// k of the group compares 32-bit word k.  gs >= number of words of the longest compare of the round.
+struct GroupGeom {
+    int gs, V, g, k;
+};
+__device__ __forceinline__ GroupGeom group_geom(int n_words, int lane) {
+    GroupGeom q;
+    q.gs = n_words <= 8 ? 8 : (n_words <= 10 ? 10 : (n_words <= 16 ? 16 : 32));
+    q.V = n_words <= 8 ? 4 : (n_words <= 10 ? 3 : (n_words <= 16 ? 2 : 1));
+    q.g = (lane >= q.gs) + (lane >= 2 * q.gs) + (lane >= 3 * q.gs);
+    q.k = lane - q.g * q.gs;
+    return q;
+}
+// bit i set <=> group i took part and none of its lanes saw a mismatch
+__device__ __forceinline__ unsigned group_ok(const GroupGeom &q, bool active, bool bad) {
+    const unsigned badm = __ballot_sync(kFull, active && bad);
+    const unsigned actm = __ballot_sync(kFull, active);
+    const unsigned gm = q.gs >= 32 ? kFull : ((1u << q.gs) - 1u);
+    unsigned ok = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (i < q.V) {
+            const unsigned m = gm << (i * q.gs);
+            if ((actm & m) && !(badm & m)) ok |= 1u << i;
+        }
+    }
+    return ok;
+}
+
+// Phase 1, fast path: source read b, lanes = overlap lengths from min(rs-1, len) downwards.  All lanes probe, then
+// the tag hits are verified in priority order (L descending, target id descending), four at a time, until the
+// three largest (L, c) are known -- the candidates ranked behind them are never touched.
 template <bool UNIFORM>
 __global__ void __launch_bounds__(kThreads)
 phase1_fast_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, int2 *__restrict__ fwd,
@@ -303,31 +298,85 @@ phase1_fast_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, i
                         hard = true;
                         break;
                     }
-                    bool ok0 = false, ok1 = false;
-                    if (n > 0 && c0 != b && (UNIFORM || (int64_t) R.len[c0] >= L))
-                        ok0 = equal_own_shifted(own, 2u * o, read_ptr(R, c0), 2u * (uint32_t) L);
-                    if (n > 1 && c1 != b && (UNIFORM || (int64_t) R.len[c1] >= L))
-                        ok1 = equal_own_shifted(own, 2u * o, read_ptr(R, c1), 2u * (uint32_t) L);
-                    const int nh = (int) ok0 + (int) ok1;
-                    // within one length the larger target id is the later push
-                    uint32_t h0 = ok0 ? c0 : c1, h1 = c1;
-                    if (nh == 2 && c1 > c0) h0 = c1, h1 = c0;
-                    const unsigned m1 = __ballot_sync(kFull, nh >= 1), m2 = __ballot_sync(kFull, nh >= 2);
-                    if (nh) {
-                        const int rank = found + __popc(m1 & lt) + __popc(m2 & lt);
-                        if (rank < kSmallEdgesKept) {
-                            const uint64_t t = overhang_tail_own(own, o);
-                            slots[rank] = make_int2((int32_t) h0, (int32_t) o);
-                            slots_t[rank] = t;
-                            if (indeg) atomicAdd(indeg + h0, 1u);
-                            if (nh == 2 && rank + 1 < kSmallEdgesKept) {
-                                slots[rank + 1] = make_int2((int32_t) h1, (int32_t) o);
-                                slots_t[rank + 1] = t;
-                                if (indeg) atomicAdd(indeg + h1, 1u);
+                    if (n == 2 && c1 > c0) {  // within one length the larger target id is the later push
+                        const uint32_t x = c0;
+                        c0 = c1;
+                        c1 = x;
+                    }
+                    unsigned pend = __ballot_sync(kFull, n > 0);
+                    const unsigned two = __ballot_sync(kFull, n > 1);
+                    const GroupGeom q = group_geom((2 * l_top + 31) >> 5, lane);
+                    while (pend && found < kSmallEdgesKept) {
+                        // chunk = the next V candidate lanes in priority order; group i verifies the i-th of them
+                        unsigned chunk = 0;
+                        int src = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            if (i < q.V && pend) {
+                                const int l = __ffs(pend) - 1;
+                                if (i == q.g) src = l;
+                                chunk |= 1u << l;
+                                pend &= pend - 1;
                             }
                         }
+                        const int ng = __popc(chunk);
+                        const int32_t Ls = l_top - src;
+                        const uint32_t os = lenb - (uint32_t) Ls, nbits = 2u * (uint32_t) Ls, nw = (nbits + 31u) >> 5;
+                        const uint32_t sh = (2u * os) & 31u, wo = (2u * os) >> 5;
+                        unsigned okA, okB = 0;
+                        {
+                            const uint32_t cand = __shfl_sync(kFull, c0, src);
+                            const bool act = q.g < ng && q.g < q.V;
+                            bool bad = false;
+                            if (act) {
+                                if (q.k == 0 && (cand == b || (!UNIFORM && (int64_t) R.len[cand] < Ls))) bad = true;
+                                if ((uint32_t) q.k < nw) {
+                                    uint32_t x = __funnelshift_r(own[wo + q.k], own[wo + q.k + 1], sh) ^
+                                                 __ldg(read_ptr(R, cand) + q.k);
+                                    if ((uint32_t) q.k == nw - 1 && (nbits & 31u)) x &= (1u << (nbits & 31u)) - 1u;
+                                    bad |= x != 0;
+                                }
+                            }
+                            okA = group_ok(q, act, bad);
+                        }
+                        if (chunk & two) {
+                            const uint32_t cand = __shfl_sync(kFull, c1, src);
+                            const bool act = q.g < ng && q.g < q.V && ((two >> src) & 1u);
+                            bool bad = false;
+                            if (act) {
+                                if (q.k == 0 && (cand == b || (!UNIFORM && (int64_t) R.len[cand] < Ls))) bad = true;
+                                if ((uint32_t) q.k < nw) {
+                                    uint32_t x = __funnelshift_r(own[wo + q.k], own[wo + q.k + 1], sh) ^
+                                                 __ldg(read_ptr(R, cand) + q.k);
+                                    if ((uint32_t) q.k == nw - 1 && (nbits & 31u)) x &= (1u << (nbits & 31u)) - 1u;
+                                    bad |= x != 0;
+                                }
+                            }
+                            okB = group_ok(q, act, bad);
+                        }
+                        // results back to the candidate lanes, ranks in priority order
+                        const bool mine = (chunk >> lane) & 1u;
+                        const int gi = __popc(chunk & lt);
+                        const bool ok0 = mine && ((okA >> gi) & 1u), ok1 = mine && n > 1 && ((okB >> gi) & 1u);
+                        const int nh = (int) ok0 + (int) ok1;
+                        const unsigned m1 = __ballot_sync(kFull, nh >= 1), m2 = __ballot_sync(kFull, nh >= 2);
+                        if (nh) {
+                            const int rank = found + __popc(m1 & lt) + __popc(m2 & lt);
+                            if (rank < kSmallEdgesKept) {
+                                const uint32_t h0 = ok0 ? c0 : c1;
+                                const uint64_t t = overhang_tail_own(own, o);
+                                slots[rank] = make_int2((int32_t) h0, (int32_t) o);
+                                slots_t[rank] = t;
+                                if (indeg) atomicAdd(indeg + h0, 1u);
+                                if (nh == 2 && rank + 1 < kSmallEdgesKept) {
+                                    slots[rank + 1] = make_int2((int32_t) c1, (int32_t) o);
+                                    slots_t[rank + 1] = t;
+                                    if (indeg) atomicAdd(indeg + c1, 1u);
+                                }
+                            }
+                        }
+                        found += __popc(m1) + __popc(m2);
                     }
-                    found += __popc(m1) + __popc(m2);
                 }
             }
         }
@@ -664,13 +713,18 @@ phase2_spill_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, const uint32_
     }
 }
 
-// Phase 2, fast path: target read c, lanes = overlap lengths from max(rs, lmin) upwards.  Arrivals (b, o) are
-// collected in canonical order (L asc, b asc) behind the in-neighbours of the transposed phase-1 graph; the
-// sequential replay of GraphCreatorPrefSuf.cpp:403-483 is then evaluated in closed form: an entry survives unless
-// a LATER arrival carries the same read id, or a later phase-2 arrival j with offset o_j > 0 has an overhang that
-// is a suffix of the entry's overhang (a[oa-oj .. oa) == b[0 .. oj), right offset >= 0).  The test is independent
-// of the list state because entries never return once removed.  With oj <= 32 it is one XOR + shift on the 64-bit
-// overhang tails.
+// Phase 2, fast path: target read c, lanes = overlap lengths from max(rs, lmin) upwards.  Tag hits become
+// tentative arrivals (b, o) in canonical order (L asc, b asc) behind the in-neighbours of the transposed phase-1
+// graph.  The sequential replay of GraphCreatorPrefSuf.cpp:403-483 is evaluated in closed form: an entry survives
+// unless a LATER arrival j with offset o_j > 0 has an overhang that is a suffix of the entry's overhang
+// (a[oa-oj .. oa) == b[0 .. oj), right offset >= 0) -- the test does not depend on the list state because entries
+// never return once removed, and "is a suffix of" is transitive, so an entry that a removed arrival would remove is
+// also removed by whoever removed that arrival.  Hence verification is lazy: only tentative arrivals that no
+// verified later arrival removes are compared in full (from the last one downwards, up to four per round, one
+// group of lanes per candidate); with o_j <= 32 the removal test is one XOR + shift on the 64-bit overhang tails.
+// Targets with a repeated source id, more than 32 entries or an offset above 32 take the generic path.
+constexpr int kOutBuf = 64;  // staged output triples per warp: one atomicAdd on the edge counter per >= 32 edges
+
 template <bool UNIFORM>
 __global__ void __launch_bounds__(kThreads)
 phase2_fast_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, const uint32_t *__restrict__ rev_off,
@@ -679,14 +733,31 @@ phase2_fast_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, c
     __shared__ uint32_t s_id[kWarpsPerBlock][kMaxArrivals], s_o[kWarpsPerBlock][kMaxArrivals],
         s_len[kWarpsPerBlock][kMaxArrivals];
     __shared__ uint64_t s_t[kWarpsPerBlock][kMaxArrivals];
+    __shared__ int32_t s_out[kWarpsPerBlock][kOutBuf * 3];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     uint32_t *own = s_own[wib];
     uint32_t *a_id = s_id[wib], *a_o = s_o[wib], *a_len = s_len[wib];
     uint64_t *a_t = s_t[wib];
+    int32_t *obuf = s_out[wib];
+    uint32_t n_out = 0;  // staged triples (warp-uniform)
     const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib;
     const uint32_t n_warps = gridDim.x * kWarpsPerBlock;
     const int32_t l_lo = P.rs > P.lmin ? P.rs : P.lmin;
+
+    auto flush = [&]() {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(out.n_edges, (unsigned long long) n_out);
+        base = __shfl_sync(kFull, base, 0);
+        __syncwarp();
+        for (uint32_t i = lane; i < n_out * 3; i += 32) {
+            const unsigned long long pos = base * 3 + i;
+            if (pos < out.edge_cap * 3) out.triples[pos] = obuf[i];
+        }
+        __syncwarp();
+        n_out = 0;
+    };
+
     for (uint64_t cc = (uint64_t) lo + warp; cc < hi; cc += n_warps) {
         const uint32_t c = (uint32_t) cc;
         const uint32_t r0 = rev_off[c - lo], deg = rev_off[c - lo + 1] - r0;
@@ -706,20 +777,13 @@ phase2_fast_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, c
                 a_o[lane] = (uint32_t) e.y;
                 a_t[lane] = rev_t[r0 + lane];
                 if (!UNIFORM) a_len[lane] = R.len[e.x];
-                if (deg > 1) {
-                    // the same source twice in one row needs retainOnlySmallestOffset: generic path
-                    const unsigned vm = deg >= 32 ? kFull : ((1u << deg) - 1u);
-                    const unsigned same = __match_any_sync(vm, (uint32_t) e.x);
-                    if (same != (1u << lane)) hard = true;
-                }
             }
-            hard = __any_sync(kFull, hard);
             cnt = deg;
         }
         if (!hard && active) {
             const uint32_t need = (uint32_t) ((2 * l_hi + 31) >> 5);
-            const uint32_t have = (lenc + 15u) >> 4;
-            stage_own(own, read_ptr(R, c), need < have ? need : have, lane);
+            const uint32_t have_w = (lenc + 15u) >> 4;
+            stage_own(own, read_ptr(R, c), need < have_w ? need : have_w, lane);
             for (int32_t l_base = l_lo; l_base <= (int32_t) l_hi; l_base += 32) {
                 const int32_t L = l_base + lane;
                 const bool valid = L <= (int32_t) l_hi;
@@ -728,34 +792,34 @@ phase2_fast_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, c
                 int n;
                 probe_two(T, win, valid, b0, b1, n);
                 bool bad = n > 2;
-                bool ok0 = false, ok1 = false;
+                if (n == 2 && b1 < b0) {  // within one length the smaller source id arrives first
+                    const uint32_t x = b0;
+                    b0 = b1;
+                    b1 = x;
+                }
+                // tentative arrivals: length / offset checks and the overhang tail (first words of the candidate)
+                bool k0 = false, k1 = false;
                 uint32_t len0 = lenc, len1 = lenc;
                 uint64_t t0 = 0, t1 = 0;
                 if (n > 0 && b0 != c) {
                     if (!UNIFORM) len0 = R.len[b0];
                     if ((int64_t) len0 - P.min_offset >= L) {
-                        const uint32_t *pb = read_ptr(R, b0);
                         const uint32_t o = len0 - (uint32_t) L;
-                        ok0 = equal_cand_shifted(pb, 2u * o, own, 2u * (uint32_t) L);
-                        if (ok0) {
-                            if (o > 32u) bad = true;
-                            else t0 = overhang_tail(pb, o);
-                        }
+                        if (o > 32u) bad = true;
+                        else t0 = overhang_tail(read_ptr(R, b0), o);
+                        k0 = true;
                     }
                 }
                 if (n > 1 && b1 != c) {
                     if (!UNIFORM) len1 = R.len[b1];
                     if ((int64_t) len1 - P.min_offset >= L) {
-                        const uint32_t *pb = read_ptr(R, b1);
                         const uint32_t o = len1 - (uint32_t) L;
-                        ok1 = equal_cand_shifted(pb, 2u * o, own, 2u * (uint32_t) L);
-                        if (ok1) {
-                            if (o > 32u) bad = true;
-                            else t1 = overhang_tail(pb, o);
-                        }
+                        if (o > 32u) bad = true;
+                        else t1 = overhang_tail(read_ptr(R, b1), o);
+                        k1 = true;
                     }
                 }
-                const int nh = (int) ok0 + (int) ok1;
+                const int nh = (int) k0 + (int) k1;
                 const unsigned m1 = __ballot_sync(kFull, nh >= 1), m2 = __ballot_sync(kFull, nh >= 2);
                 const uint32_t total = __popc(m1) + __popc(m2);
                 if (__any_sync(kFull, bad) || cnt + total > (uint32_t) kMaxArrivals) {
@@ -763,71 +827,108 @@ phase2_fast_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, c
                     break;
                 }
                 if (nh) {
-                    // within one length the smaller source id arrives first
-                    const bool swap = nh == 2 && b1 < b0;
                     const uint32_t slot = cnt + __popc(m1 & lt) + __popc(m2 & lt);
-                    const uint32_t f_id = ok0 && !swap ? b0 : b1, f_len = ok0 && !swap ? len0 : len1;
-                    const uint64_t f_t = ok0 && !swap ? t0 : t1;
+                    const uint32_t f_id = k0 ? b0 : b1, f_len = k0 ? len0 : len1;
                     a_id[slot] = f_id;
                     a_o[slot] = f_len - (uint32_t) L;
                     a_len[slot] = f_len;
-                    a_t[slot] = f_t;
+                    a_t[slot] = k0 ? t0 : t1;
                     if (nh == 2) {
-                        const uint32_t g_id = swap ? b0 : b1, g_len = swap ? len0 : len1;
-                        a_id[slot + 1] = g_id;
-                        a_o[slot + 1] = g_len - (uint32_t) L;
-                        a_len[slot + 1] = g_len;
-                        a_t[slot + 1] = swap ? t0 : t1;
+                        a_id[slot + 1] = b1;
+                        a_o[slot + 1] = len1 - (uint32_t) L;
+                        a_len[slot + 1] = len1;
+                        a_t[slot + 1] = t1;
                     }
                 }
                 cnt += total;
             }
         }
         __syncwarp();
+        const bool have = !hard && (uint32_t) lane < cnt;
+        const uint32_t id = have ? a_id[lane] : kNone, o = have ? a_o[lane] : 0u;
+        const uint32_t len = (have && !UNIFORM) ? a_len[lane] : 0u;
+        const uint64_t t = have ? a_t[lane] : 0ull;
+        if (!hard && cnt > 1) {
+            // the same read twice among the entries (same-id replacement / retainOnlySmallestOffset): generic path
+            const unsigned vm = cnt >= 32 ? kFull : ((1u << cnt) - 1u);
+            bool dup = false;
+            if (have) dup = __match_any_sync(vm, id) != (1u << lane);
+            hard = __any_sync(kFull, dup);
+        }
         if (hard) {
             if (lane == 0) out.spill_queue[atomicAdd(out.n_spill, 1u)] = c;
             continue;
         }
         if (cnt == 0) continue;
-        // closed-form replay
-        const bool have = (uint32_t) lane < cnt;
-        const uint32_t id = have ? a_id[lane] : kNone, o = have ? a_o[lane] : 0u;
-        const uint32_t len = (have && !UNIFORM) ? a_len[lane] : 0u;
-        const uint64_t t = have ? a_t[lane] : 0ull;
-        bool removed = false;
-        if (cnt > deg && cnt > 1) {
-            const unsigned vm = cnt >= 32 ? kFull : ((1u << cnt) - 1u);
-            if (have) {
-                const unsigned same = __match_any_sync(vm, id);
-                removed = (same >> lane) > 1u;  // a later arrival of the same read replaces this entry
-            }
-            for (int j = (int) cnt - 1; j >= (int) deg; j--) {
-                if (!__any_sync(kFull, have && !removed && lane < j)) break;
-                const uint32_t oj = a_o[j];
-                if (oj == 0) continue;
-                const uint64_t tj = a_t[j];
-                if (have && !removed && lane < j && o >= oj &&
-                    (UNIFORM || (int64_t) a_len[j] + (int64_t) (o - oj) - (int64_t) len >= 0) &&
-                    ((t ^ tj) >> (64u - 2u * oj)) == 0)
-                    removed = true;
+        bool alive = have, verified = (uint32_t) lane < deg;
+        if (cnt > deg) {
+            const GroupGeom q = group_geom((int) ((2 * l_hi + 31) >> 5), lane);
+            while (true) {
+                const unsigned cm = __ballot_sync(kFull, have && alive && !verified);
+                if (!cm) break;
+                // chunk = the V last unverified candidates that are still alive; group i verifies the i-th of them
+                unsigned chunk = 0, p = cm;
+                int src = 0, js[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (i < q.V && p) {
+                        const int l = 31 - __clz(p);
+                        if (i == q.g) src = l;
+                        js[i] = l;
+                        chunk |= 1u << l;
+                        p &= ~(1u << l);
+                    }
+                }
+                const int ng = __popc(chunk);
+                const bool act = q.g < ng && q.g < q.V;
+                bool bad = false;
+                if (act) {
+                    const uint32_t bj = a_id[src], oj = a_o[src];
+                    const uint32_t lenj = UNIFORM ? lenc : a_len[src];
+                    const uint32_t nbits = 2u * (lenj - oj), nw = (nbits + 31u) >> 5;
+                    if ((uint32_t) q.k < nw) {
+                        const uint32_t *qb = read_ptr(R, bj) + ((2u * oj) >> 5);
+                        uint32_t x = __funnelshift_r(__ldg(qb + q.k), __ldg(qb + q.k + 1), (2u * oj) & 31u) ^ own[q.k];
+                        if ((uint32_t) q.k == nw - 1 && (nbits & 31u)) x &= (1u << (nbits & 31u)) - 1u;
+                        bad = x != 0;
+                    }
+                }
+                const unsigned okbits = group_ok(q, act, bad);
+                if ((chunk >> lane) & 1u) {
+                    verified = true;
+                    const int gi = __popc(chunk >> (lane + 1)) ;
+                    if (!((okbits >> gi) & 1u)) alive = false;
+                }
+                // every arrival confirmed in this round removes the earlier entries whose overhang ends with its own
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (i < ng && ((okbits >> i) & 1u)) {
+                        const int j = js[i];
+                        const uint32_t oj = a_o[j];
+                        if (oj == 0) continue;
+                        const uint64_t tj = a_t[j];
+                        if (have && alive && lane < j && o >= oj &&
+                            (UNIFORM || (int64_t) a_len[j] + (int64_t) (o - oj) - (int64_t) len >= 0) &&
+                            ((t ^ tj) >> (64u - 2u * oj)) == 0)
+                            alive = false;
+                    }
+                }
             }
         }
-        const unsigned keep = __ballot_sync(kFull, have && !removed);
+        const unsigned keep = __ballot_sync(kFull, have && alive);
         if (keep) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(out.n_edges, (unsigned long long) __popc(keep));
-            base = __shfl_sync(kFull, base, 0);
-            if (have && !removed) {
-                const unsigned long long pos = base + __popc(keep & lt);
-                if (pos < out.edge_cap) {
-                    out.triples[3 * pos] = (int32_t) id;
-                    out.triples[3 * pos + 1] = (int32_t) c;
-                    out.triples[3 * pos + 2] = (int32_t) o;
-                }
+            if (have && alive) {
+                const uint32_t pos = n_out + __popc(keep & lt);
+                obuf[3 * pos] = (int32_t) id;
+                obuf[3 * pos + 1] = (int32_t) c;
+                obuf[3 * pos + 2] = (int32_t) o;
                 if (out.outdeg) atomicAdd(out.outdeg + id, 1u);
             }
+            n_out += __popc(keep);
+            if (n_out >= 32) flush();
         }
     }
+    if (n_out) flush();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -14,7 +14,7 @@ if [ "${NCU:-1}" = "1" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${tag}.csv \
       python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_launches_${tag}.log 2>&1
   echo "ncu launches rc=$?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'phase1_kernel|phase2_kernel' -s 2 -c 2 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'phase1_fast|phase2_fast' -s 2 -c 2 \
       -f -o gpurun_out/prof_${tag} python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_full_${tag}.log 2>&1
   echo "ncu full rc=$?"
 fi
