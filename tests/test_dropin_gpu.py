@@ -1,0 +1,71 @@
+"""Drop-in check through the reference's own driver: the stock ALGA binary vs the same sources with
+src/GraphCreators/GraphCreatorPrefSuf.cpp swapped for shim/GraphCreatorPrefSufGpu.cpp (oracle/_ref/ALGA_gpu, built
+by `make -C oracle ref` in the dev container).  Same FASTA in, --threads=1: the contigs must be identical."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from alga_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+REF = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+STOCK, GPU = os.path.join(REF, "ALGA"), os.path.join(REF, "ALGA_gpu")
+
+
+def _write_fasta(path, reads):
+    nt = np.frombuffer(b"ACGT", np.uint8)
+    with open(path, "wb") as f:
+        for i, r in enumerate(reads):
+            f.write(b">r%d\n" % i)
+            f.write(nt[r].tobytes())
+            f.write(b"\n")
+
+
+def _contigs(path):
+    seqs, cur = [], []
+    for line in open(path):
+        if line.startswith(">"):
+            if cur:
+                seqs.append("".join(cur))
+            cur = []
+        else:
+            cur.append(line.strip())
+    if cur:
+        seqs.append("".join(cur))
+    comp = str.maketrans("ACGT", "TGCA")
+    return sorted(min(s, s.translate(comp)[::-1]) for s in seqs)
+
+
+def _run(binary, cwd, args):
+    r = subprocess.run([binary] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    return r.stdout
+
+
+@pytest.mark.skipif(not (os.path.isfile(STOCK) and os.path.isfile(GPU)), reason="oracle/_ref binaries not built")
+@pytest.mark.parametrize("paired,error,extra", [(False, 0.0, []), (True, 0.0, []), (True, 0.01, ["--error_rate=0.02"])])
+def test_contigs_identical_through_reference_driver(gpu, tmp_path, paired, error, extra):
+    rng = np.random.default_rng(77)
+    genome = synth.make_genome(60_000, rng)
+    if paired:
+        m1, m2 = synth.sample_paired_end(genome, 150, 40, rng, error)
+        files = {"x_1.fasta": m1, "x_2.fasta": m2}
+        args = ["--file1=x_1.fasta", "--file2=x_2.fasta"]
+    else:
+        files = {"x_1.fasta": synth.sample_single_end(genome, 100, 30, rng, error)}
+        args = ["--file1=x_1.fasta"]
+    outs = {}
+    for name, binary in (("stock", STOCK), ("gpu", GPU)):
+        d = tmp_path / name
+        d.mkdir()
+        for fn, reads in files.items():
+            _write_fasta(d / fn, reads)
+        log = _run(binary, d, args + ["--threads=1", "--output=contigs.fasta"] + extra)
+        if name == "gpu":
+            assert "alga_gpu:" in log, "the GPU shim did not run"
+        outs[name] = _contigs(d / "contigs.fasta")
+    assert len(outs["stock"]) > 0
+    assert outs["gpu"] == outs["stock"]
