@@ -130,7 +130,7 @@ struct alga_ps_plan {
     // owned copies (upload path)
     DevBuf words, word_off, len, from, to;
     // workspace
-    DevBuf stats_d, counters_d, tp, ts, fwd, fwd_t, rev_t, hard1, indeg, rev_off, rev, triples, triples1, outdeg, scan_ws, spill_queue, caps,
+    DevBuf stats_d, counters_d, tp, ts, fwd, fwd_t, fwd_pos, rev_t, hard1, indeg, rev_off, rev, triples, triples1, outdeg, scan_ws, spill_queue, caps,
         spill_off, spill_store, row_off, nbr, off, big_rows, tmp_nbr, tmp_off;
     SeedTable Tp{}, Ts{};
     Counters *h_counters = nullptr;  // pinned
@@ -147,7 +147,7 @@ struct alga_ps_plan {
     cudaEvent_t ev_stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     ~alga_ps_plan() {
-        DevBuf *all[] = {&words, &word_off, &len, &from, &to, &stats_d, &counters_d, &tp, &ts, &fwd, &fwd_t, &rev_t, &hard1, &indeg, &rev_off, &rev,
+        DevBuf *all[] = {&words, &word_off, &len, &from, &to, &stats_d, &counters_d, &tp, &ts, &fwd, &fwd_t, &fwd_pos, &rev_t, &hard1, &indeg, &rev_off, &rev,
                          &triples, &triples1, &outdeg, &scan_ws, &spill_queue, &caps, &spill_off, &spill_store, &row_off,
                          &nbr, &off, &big_rows, &tmp_nbr, &tmp_off};
         for (DevBuf *b : all) b->release();
@@ -264,9 +264,9 @@ int run_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, uint32_t *outdeg, c
             launch_phase2(plan->R, plan->Ts, plan->P, lo, hi, plan->rev_off.as<uint32_t>(), plan->rev.as<int2>(),
                           list_cap, out, s, plan->cfg);
         else
-            launch_phase2_fast(plan->R, plan->Ts, plan->P, lo, hi, plan->rev_off.as<uint32_t>(), plan->rev.as<int2>(),
-                               plan->rev_t.as<uint64_t>(), out, plan->params.flags & ALGA_PS_FORCE_GENERIC, s,
-                               plan->cfg);
+            launch_phase2_tpr(plan->R, plan->Ts, plan->P, plan->stats.max_len, lo, hi, plan->rev_off.as<uint32_t>(),
+                              plan->rev.as<int2>(), plan->rev_t.as<uint64_t>(), out,
+                              plan->params.flags & ALGA_PS_FORCE_GENERIC, s, plan->cfg);
         CK(cudaGetLastError());
         CKR(read_counters(plan, s));
         const uint32_t n_spill = plan->h_counters->n_spill;
@@ -478,8 +478,14 @@ int alga_ps_stage_phase1(alga_ps_plan *plan, uint32_t lo, uint32_t hi, void *str
     CKR(plan->triples1.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * 12));
     Counters *dc = plan->counters_d.as<Counters>();
     CK(cudaMemsetAsync(&dc->n_hard1, 0, 4, s));
-    launch_phase1(plan->R, plan->Tp, plan->P, lo, hi, plan->fwd.as<int2>(), plan->fwd_t.as<uint64_t>(), nullptr,
-                  plan->hard1.as<uint32_t>(), &dc->n_hard1, plan->params.flags & ALGA_PS_FORCE_GENERIC, s, plan->cfg);
+    CKR(plan->fwd_pos.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * 4));
+    const int force = plan->params.flags & ALGA_PS_FORCE_GENERIC;
+    launch_phase1_tpr(plan->R, plan->Tp, plan->P, plan->stats.max_len, lo, hi, plan->fwd.as<int2>(),
+                      plan->fwd_t.as<uint64_t>(), plan->fwd_pos.as<uint32_t>(), nullptr, plan->hard1.as<uint32_t>(),
+                      &dc->n_hard1, force, s, plan->cfg);
+    launch_phase1_queue(plan->R, plan->Tp, plan->P, lo, force ? n : (n < 4096 ? n : 4096), plan->hard1.as<uint32_t>(),
+                        &dc->n_hard1, plan->fwd.as<int2>(), plan->fwd_t.as<uint64_t>(), plan->fwd_pos.as<uint32_t>(),
+                        nullptr, s, plan->cfg);
     CK(cudaMemsetAsync(&dc->n_triples, 0, 8, s));
     launch_compact_slots(plan->fwd.as<int2>(), lo, hi, plan->triples1.as<int32_t>(), &dc->n_triples, s, plan->cfg);
     CK(cudaGetLastError());
@@ -541,16 +547,21 @@ int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
     CKR(plan->indeg.ensure((size_t) (n ? n : 1) * 4));
     CK(cudaMemsetAsync(plan->indeg.p, 0, (size_t) (n ? n : 1) * 4, s));
     CK(cudaMemsetAsync(&plan->counters_d.as<Counters>()->n_hard1, 0, 4, s));
-    launch_phase1(plan->R, plan->Tp, plan->P, 0, n, plan->fwd.as<int2>(), plan->fwd_t.as<uint64_t>(),
-                  plan->indeg.as<uint32_t>(), plan->hard1.as<uint32_t>(), &plan->counters_d.as<Counters>()->n_hard1,
-                  plan->params.flags & ALGA_PS_FORCE_GENERIC, s, plan->cfg);
+    CKR(plan->fwd_pos.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * 4));
+    const int force = plan->params.flags & ALGA_PS_FORCE_GENERIC;
+    launch_phase1_tpr(plan->R, plan->Tp, plan->P, plan->stats.max_len, 0, n, plan->fwd.as<int2>(),
+                      plan->fwd_t.as<uint64_t>(), plan->fwd_pos.as<uint32_t>(), plan->indeg.as<uint32_t>(),
+                      plan->hard1.as<uint32_t>(), &plan->counters_d.as<Counters>()->n_hard1, force, s, plan->cfg);
+    launch_phase1_queue(plan->R, plan->Tp, plan->P, 0, force ? n : (n < 4096 ? n : 4096), plan->hard1.as<uint32_t>(),
+                        &plan->counters_d.as<Counters>()->n_hard1, plan->fwd.as<int2>(), plan->fwd_t.as<uint64_t>(),
+                        plan->fwd_pos.as<uint32_t>(), plan->indeg.as<uint32_t>(), s, plan->cfg);
     CK(cudaEventRecord(plan->ev_stage[1], s));
     // reversed phase-1 graph (rows by target)
     CKR(build_rev_from_counts(plan, n, s));
     CKR(plan->rev.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * sizeof(int2)));
     CKR(plan->rev_t.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * 8));
-    launch_scatter_rev_slots(plan->fwd.as<int2>(), plan->fwd_t.as<uint64_t>(), 0, n, 0, n, plan->rev_off.as<uint32_t>(),
-                             plan->indeg.as<uint32_t>(), plan->rev.as<int2>(), plan->rev_t.as<uint64_t>(), s, plan->cfg);
+    launch_scatter_rev_slots(plan->fwd.as<int2>(), plan->fwd_t.as<uint64_t>(), plan->fwd_pos.as<uint32_t>(), 0, n, 0, n,
+                             plan->rev_off.as<uint32_t>(), plan->rev.as<int2>(), plan->rev_t.as<uint64_t>(), s, plan->cfg);
     CK(cudaGetLastError());
     CK(cudaEventRecord(plan->ev_stage[2], s));
     // phase 2 with fused out-degree counting (not in the reversed-result corner)

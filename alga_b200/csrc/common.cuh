@@ -173,4 +173,55 @@ __device__ __forceinline__ void insert_seed(const SeedTable &t, uint64_t h, uint
     }
 }
 
+constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr int kOwnWords = 32;  // staged part of a read in the fast kernels: 512 nucleotides
+
+// Overhang tail of an edge (x -> c, offset o): the last min(o, 32) nucleotides of x[0 .. o), top-aligned in 64
+// bits (nucleotide o-1 in bits 62..63).  Phase 2 decides "x[oa-o .. oa) == b[0 .. o)" from two such tails when o <= 32.
+__device__ __forceinline__ uint64_t overhang_tail(const uint32_t *__restrict__ p, uint32_t o) {
+    if (o == 0) return 0;
+    if (o >= 32) return bits64(p, 2u * (o - 32u));
+    return bits64(p, 0) << (64u - 2u * o);
+}
+
+__device__ __forceinline__ uint64_t sbits64(const uint32_t *own, uint32_t bit) {
+    const uint32_t w = bit >> 5, s = bit & 31u;
+    const uint32_t a = own[w], b = own[w + 1], c = own[w + 2];
+    return (uint64_t) __funnelshift_r(a, b, s) | ((uint64_t) __funnelshift_r(b, c, s) << 32);
+}
+__device__ __forceinline__ uint64_t overhang_tail_own(const uint32_t *own, uint32_t o) {
+    if (o == 0) return 0;
+    if (o >= 32) return sbits64(own, 2u * (o - 32u));
+    return sbits64(own, 0) << (64u - 2u * o);
+}
+
+// Warp-cooperative exact compares: the warp is cut into V groups of gs lanes, group g verifies one candidate, lane
+// k of the group compares 32-bit word k.  gs >= number of words of the longest compare of the round.
+struct GroupGeom {
+    int gs, V, g, k;
+};
+__device__ __forceinline__ GroupGeom group_geom(int n_words, int lane) {
+    GroupGeom q;
+    q.gs = n_words <= 8 ? 8 : (n_words <= 10 ? 10 : (n_words <= 16 ? 16 : 32));
+    q.V = n_words <= 8 ? 4 : (n_words <= 10 ? 3 : (n_words <= 16 ? 2 : 1));
+    q.g = (lane >= q.gs) + (lane >= 2 * q.gs) + (lane >= 3 * q.gs);
+    q.k = lane - q.g * q.gs;
+    return q;
+}
+// bit i set <=> group i took part and none of its lanes saw a mismatch
+__device__ __forceinline__ unsigned group_ok(const GroupGeom &q, bool active, bool bad) {
+    const unsigned badm = __ballot_sync(kFull, active && bad);
+    const unsigned actm = __ballot_sync(kFull, active);
+    const unsigned gm = q.gs >= 32 ? kFull : ((1u << q.gs) - 1u);
+    unsigned ok = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (i < q.V) {
+            const unsigned m = gm << (i * q.gs);
+            if ((actm & m) && !(badm & m)) ok |= 1u << i;
+        }
+    }
+    return ok;
+}
+
 }  // namespace alga

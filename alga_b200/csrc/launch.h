@@ -28,11 +28,16 @@ void launch_build_index(const ReadsDev &R, const PsDev &P, SeedTable prefix, See
 
 // --- phase 1: L in [lmin, min(rs-1, max_l)], keeps the 3 largest (L, c) per source read ----------
 // fwd: 3 slots per b in [lo,hi): (c, offset), c = -1 when empty; fwd_t: overhang tail of every filled slot (the last
-// min(offset, 32) nucleotides of b[0 .. offset), top-aligned).  indeg (nullable): += 1 per target c.
-// Fast kernel + generic kernel over the queue of reads the fast one handed back (*n_hard must be 0 on entry).
-void launch_phase1(const ReadsDev &R, const SeedTable &prefix, const PsDev &P, uint32_t lo, uint32_t hi, int2 *fwd,
-                   uint64_t *fwd_t, uint32_t *indeg, uint32_t *hard_queue, uint32_t *n_hard, int force_hard,
-                   cudaStream_t s, const LaunchCfg &cfg);
+// min(offset, 32) nucleotides of b[0 .. offset), top-aligned); indeg (nullable): += 1 per target c, and fwd_pos
+// receives the value the counter had (= position of the entry in c's transposed row).
+// Thread-per-read fast kernel (tpr_kernels.cu); reads it cannot take are appended to hard_queue (*n_hard must be 0).
+void launch_phase1_tpr(const ReadsDev &R, const SeedTable &prefix, const PsDev &P, uint32_t max_len_nt, uint32_t lo,
+                       uint32_t hi, int2 *fwd, uint64_t *fwd_t, uint32_t *fwd_pos, uint32_t *indeg, uint32_t *hard_queue,
+                       uint32_t *n_hard, int force_hard, cudaStream_t s, const LaunchCfg &cfg);
+// generic kernel over the queue (n_max = upper bound of the queue length, used for the grid only)
+void launch_phase1_queue(const ReadsDev &R, const SeedTable &prefix, const PsDev &P, uint32_t lo, uint32_t n_max,
+                         const uint32_t *hard_queue, const uint32_t *n_hard, int2 *fwd, uint64_t *fwd_t, uint32_t *fwd_pos,
+                         uint32_t *indeg, cudaStream_t s, const LaunchCfg &cfg);
 // compact the slots of [lo,hi) into (b, c, o) triples; *d_count must be zero on entry
 void launch_compact_slots(const int2 *fwd, uint32_t lo, uint32_t hi, int32_t *triples,
                           unsigned long long *d_count, cudaStream_t s, const LaunchCfg &cfg);
@@ -41,9 +46,9 @@ void launch_compact_slots(const int2 *fwd, uint32_t lo, uint32_t hi, int32_t *tr
 // counts -> offsets is done with launch_scan; scatter consumes `cursor` (a copy of the counts).
 void launch_count_targets(const int32_t *triples, uint64_t n, uint32_t lo, uint32_t hi, uint32_t *indeg,
                           cudaStream_t s, const LaunchCfg &cfg);
-void launch_scatter_rev_slots(const int2 *fwd, const uint64_t *fwd_t, uint32_t b_lo, uint32_t b_hi, uint32_t c_lo,
-                              uint32_t c_hi, const uint32_t *rev_off, uint32_t *cursor, int2 *rev, uint64_t *rev_t,
-                              cudaStream_t s, const LaunchCfg &cfg);
+void launch_scatter_rev_slots(const int2 *fwd, const uint64_t *fwd_t, const uint32_t *fwd_pos, uint32_t b_lo,
+                              uint32_t b_hi, uint32_t c_lo, uint32_t c_hi, const uint32_t *rev_off, int2 *rev,
+                              uint64_t *rev_t, cudaStream_t s, const LaunchCfg &cfg);
 void launch_scatter_rev_triples(const ReadsDev &R, const int32_t *triples, uint64_t n, uint32_t c_lo, uint32_t c_hi,
                                 const uint32_t *rev_off, uint32_t *cursor, int2 *rev, uint64_t *rev_t, cudaStream_t s,
                                 const LaunchCfg &cfg);
@@ -57,10 +62,10 @@ struct Phase2Out {
     uint32_t *spill_queue;        // targets whose list outgrew the on-chip capacity
     uint32_t *n_spill;
 };
-// fast path: closed-form replay on <= 32 in-neighbours per target; everything else goes to out.spill_queue
-void launch_phase2_fast(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo, uint32_t hi,
-                        const uint32_t *rev_off, const int2 *rev, const uint64_t *rev_t, const Phase2Out &out,
-                        int force_hard, cudaStream_t s, const LaunchCfg &cfg);
+// thread-per-target fast kernel (tpr_kernels.cu); everything it cannot take goes to out.spill_queue
+void launch_phase2_tpr(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t max_len_nt, uint32_t lo,
+                       uint32_t hi, const uint32_t *rev_off, const int2 *rev, const uint64_t *rev_t, const Phase2Out &out,
+                       int force_hard, cudaStream_t s, const LaunchCfg &cfg);
 // generic path: sequential replay on a shared-memory list of list_cap entries per target (spills beyond it)
 void launch_phase2(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo, uint32_t hi,
                    const uint32_t *rev_off, const int2 *rev, int list_cap, const Phase2Out &out, cudaStream_t s,

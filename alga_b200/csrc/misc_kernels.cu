@@ -5,7 +5,6 @@ namespace alga {
 
 namespace {
 
-constexpr unsigned kFull = 0xFFFFFFFFu;
 
 inline int grid_for(uint64_t n_items, int per_block, const LaunchCfg &cfg, int max_blocks_per_sm = 16) {
     uint64_t need = (n_items + per_block - 1) / per_block;

@@ -20,7 +20,6 @@ namespace alga {
 
 namespace {
 
-constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
 
@@ -77,19 +76,12 @@ __global__ void build_index_kernel(ReadsDev R, PsDev P, SeedTable tp, SeedTable 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Overhang tail of an edge (x -> c, offset o): the last min(o, 32) nucleotides of x[0 .. o), top-aligned in 64
-// bits (nucleotide o-1 in bits 62..63).  Phase 2 decides "x[oa-o .. oa) == b[0 .. o)" from two such tails when o <= 32.
-__device__ __forceinline__ uint64_t overhang_tail(const uint32_t *__restrict__ p, uint32_t o) {
-    if (o == 0) return 0;
-    if (o >= 32) return bits64(p, 2u * (o - 32u));
-    return bits64(p, 0) << (64u - 2u * o);
-}
-
 // Phase 1, generic path.  Canonical order of the reference pushes is (L asc, c asc) and only the last 3 survive,
 // so the result is the 3 largest (L, c): scan L downwards 32 lengths at a time and stop at 3 hits.
 __device__ __forceinline__ void phase1_generic_read(const ReadsDev &R, const SeedTable &T, const PsDev &P, uint32_t b,
                                                     int2 *__restrict__ slots, uint64_t *__restrict__ slots_t,
-                                                    uint32_t *__restrict__ indeg, int lane) {
+                                                    uint32_t *__restrict__ slots_pos, uint32_t *__restrict__ indeg,
+                                                    int lane) {
     const uint32_t lenb = R.len[b];
     int32_t rc[kSmallEdgesKept], ro[kSmallEdgesKept];
 #pragma unroll
@@ -147,7 +139,7 @@ __device__ __forceinline__ void phase1_generic_read(const ReadsDev &R, const See
         slots[lane] = make_int2(c, o);
         if (c >= 0) {
             slots_t[lane] = overhang_tail(pb, (uint32_t) o);
-            if (indeg) atomicAdd(indeg + c, 1u);
+            if (indeg) slots_pos[lane] = atomicAdd(indeg + c, 1u);  // position inside the target's transposed row
         }
     }
 }
@@ -156,7 +148,7 @@ __device__ __forceinline__ void phase1_generic_read(const ReadsDev &R, const See
 __global__ void __launch_bounds__(kThreads)
 phase1_queue_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, const uint32_t *__restrict__ queue,
                     const uint32_t *__restrict__ n_queue, int2 *__restrict__ fwd, uint64_t *__restrict__ fwd_t,
-                    uint32_t *__restrict__ indeg) {
+                    uint32_t *__restrict__ fwd_pos, uint32_t *__restrict__ indeg) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const uint32_t n_warps = gridDim.x * kWarpsPerBlock;
@@ -164,232 +156,7 @@ phase1_queue_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, const uint32_
     for (uint32_t q = warp; q < n; q += n_warps) {
         const uint32_t b = queue[q];
         const uint64_t s0 = (uint64_t) (b - lo) * kSmallEdgesKept;
-        phase1_generic_read(R, T, P, b, fwd + s0, fwd_t + s0, indeg, lane);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Fast paths.  One warp per read; the warp's own read is staged in shared memory, every lane handles one overlap
-// length: one seed-window hash, one 32-byte bucket probe, and -- for the lanes whose tag matched -- one
-// straight-line exact compare.  Anything unusual (more than two tag matches for one window, reads longer than the
-// staged window, too many in-neighbours, ...) hands the read to the generic path through a queue.
-constexpr int kOwnWords = 32;  // staged part of the own read: 512 nucleotides
-constexpr int kOwnPad = 8;
-constexpr int kOwnStride = kOwnWords + kOwnPad;
-constexpr int kMaxArrivals = 32;
-
-__device__ __forceinline__ uint64_t sbits64(const uint32_t *own, uint32_t bit) {
-    const uint32_t w = bit >> 5, s = bit & 31u;
-    const uint32_t a = own[w], b = own[w + 1], c = own[w + 2];
-    return (uint64_t) __funnelshift_r(a, b, s) | ((uint64_t) __funnelshift_r(b, c, s) << 32);
-}
-__device__ __forceinline__ uint64_t overhang_tail_own(const uint32_t *own, uint32_t o) {
-    if (o == 0) return 0;
-    if (o >= 32) return sbits64(own, 2u * (o - 32u));
-    return sbits64(own, 0) << (64u - 2u * o);
-}
-
-// Lane-local probe of one seed window (all 32 lanes must call; `valid` switches a lane off): the first two read
-// ids whose tag matches and the number of tag matches.
-__device__ __forceinline__ void probe_two(const SeedTable &t, uint64_t window, bool valid, uint32_t &c0, uint32_t &c1,
-                                          int &n) {
-    const uint64_t h = mix64(window);
-    const uint32_t tag = tag_of(t, h);
-    uint32_t bk = bucket_of(h, t.n_buckets);
-    n = 0;
-    c0 = c1 = kNone;
-    bool more = valid;
-    do {
-        if (more) {
-            uint32_t e[8];
-            load_bucket(t.slots + (uint64_t) bk * kSlotsPerBucket, e);
-            uint32_t hm = 0;
-#pragma unroll
-            for (int s = 0; s < kSlotsPerBucket; s++) hm |= ((e[s] ^ tag) <= t.id_mask ? 1u : 0u) << s;
-            if (hm) {
-#pragma unroll
-                for (int s = 0; s < kSlotsPerBucket; s++) {
-                    if (hm & (1u << s)) {
-                        if (n == 0) c0 = e[s] & t.id_mask;
-                        else if (n == 1) c1 = e[s] & t.id_mask;
-                        n++;
-                    }
-                }
-            }
-            more = e[kSlotsPerBucket - 1] != kEmptySlot;  // buckets fill front to back: a full one chains on
-            bk = (bk + 1 == t.n_buckets) ? 0u : bk + 1;
-        }
-    } while (__any_sync(kFull, more));
-}
-
-__device__ __forceinline__ void stage_own(uint32_t *own, const uint32_t *__restrict__ p, uint32_t n_words, int lane) {
-    __syncwarp();
-    for (int k = lane; k < kOwnStride; k += 32) own[k] = (uint32_t) k < n_words ? __ldg(p + k) : 0u;
-    __syncwarp();
-}
-
-// Warp-cooperative exact compares: the warp is cut into V groups of gs lanes, group g verifies one candidate, lane
-// k of the group compares 32-bit word k.  gs >= number of words of the longest compare of the round.
-struct GroupGeom {
-    int gs, V, g, k;
-};
-__device__ __forceinline__ GroupGeom group_geom(int n_words, int lane) {
-    GroupGeom q;
-    q.gs = n_words <= 8 ? 8 : (n_words <= 10 ? 10 : (n_words <= 16 ? 16 : 32));
-    q.V = n_words <= 8 ? 4 : (n_words <= 10 ? 3 : (n_words <= 16 ? 2 : 1));
-    q.g = (lane >= q.gs) + (lane >= 2 * q.gs) + (lane >= 3 * q.gs);
-    q.k = lane - q.g * q.gs;
-    return q;
-}
-// bit i set <=> group i took part and none of its lanes saw a mismatch
-__device__ __forceinline__ unsigned group_ok(const GroupGeom &q, bool active, bool bad) {
-    const unsigned badm = __ballot_sync(kFull, active && bad);
-    const unsigned actm = __ballot_sync(kFull, active);
-    const unsigned gm = q.gs >= 32 ? kFull : ((1u << q.gs) - 1u);
-    unsigned ok = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        if (i < q.V) {
-            const unsigned m = gm << (i * q.gs);
-            if ((actm & m) && !(badm & m)) ok |= 1u << i;
-        }
-    }
-    return ok;
-}
-
-// Phase 1, fast path: source read b, lanes = overlap lengths from min(rs-1, len) downwards.  All lanes probe, then
-// the tag hits are verified in priority order (L descending, target id descending), four at a time, until the
-// three largest (L, c) are known -- the candidates ranked behind them are never touched.
-template <bool UNIFORM>
-__global__ void __launch_bounds__(kThreads)
-phase1_fast_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, int2 *__restrict__ fwd,
-                   uint64_t *__restrict__ fwd_t, uint32_t *__restrict__ indeg, uint32_t *__restrict__ hard_queue,
-                   uint32_t *n_hard, int force_hard) {
-    __shared__ uint32_t s_own[kWarpsPerBlock][kOwnStride];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const unsigned lt = (1u << lane) - 1u;
-    uint32_t *own = s_own[wib];
-    const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib;
-    const uint32_t n_warps = gridDim.x * kWarpsPerBlock;
-    for (uint64_t bb = (uint64_t) lo + warp; bb < hi; bb += n_warps) {
-        const uint32_t b = (uint32_t) bb;
-        const uint32_t lenb = UNIFORM ? P.uniform_len : R.len[b];
-        int2 *slots = fwd + (uint64_t) (b - lo) * kSmallEdgesKept;
-        uint64_t *slots_t = fwd_t + (uint64_t) (b - lo) * kSmallEdgesKept;
-        int64_t l_hi = (int64_t) lenb - P.min_offset;
-        if (l_hi > P.rs - 1) l_hi = P.rs - 1;
-        if (l_hi > P.max_l) l_hi = P.max_l;
-        int found = 0;
-        bool hard = false;
-        if (lenb != 0 && flag_from(R, b) && l_hi >= P.lmin) {
-            if (force_hard || lenb > (uint32_t) kOwnWords * 16u) {
-                hard = true;
-            } else {
-                stage_own(own, read_ptr(R, b), (lenb + 15u) >> 4, lane);
-                for (int32_t l_top = (int32_t) l_hi; l_top >= P.lmin && found < kSmallEdgesKept; l_top -= 32) {
-                    const int32_t L = l_top - lane;
-                    const bool valid = L >= P.lmin;
-                    const uint32_t o = valid ? lenb - (uint32_t) L : 0u;
-                    const uint64_t win = sbits64(own, 2u * o) & P.seed_mask;
-                    uint32_t c0, c1;
-                    int n;
-                    probe_two(T, win, valid, c0, c1, n);
-                    if (__any_sync(kFull, n > 2)) {
-                        hard = true;
-                        break;
-                    }
-                    if (n == 2 && c1 > c0) {  // within one length the larger target id is the later push
-                        const uint32_t x = c0;
-                        c0 = c1;
-                        c1 = x;
-                    }
-                    unsigned pend = __ballot_sync(kFull, n > 0);
-                    const unsigned two = __ballot_sync(kFull, n > 1);
-                    const GroupGeom q = group_geom((2 * l_top + 31) >> 5, lane);
-                    while (pend && found < kSmallEdgesKept) {
-                        // chunk = the next V candidate lanes in priority order; group i verifies the i-th of them
-                        unsigned chunk = 0;
-                        int src = 0;
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            if (i < q.V && pend) {
-                                const int l = __ffs(pend) - 1;
-                                if (i == q.g) src = l;
-                                chunk |= 1u << l;
-                                pend &= pend - 1;
-                            }
-                        }
-                        const int ng = __popc(chunk);
-                        const int32_t Ls = l_top - src;
-                        const uint32_t os = lenb - (uint32_t) Ls, nbits = 2u * (uint32_t) Ls, nw = (nbits + 31u) >> 5;
-                        const uint32_t sh = (2u * os) & 31u, wo = (2u * os) >> 5;
-                        unsigned okA, okB = 0;
-                        {
-                            const uint32_t cand = __shfl_sync(kFull, c0, src);
-                            const bool act = q.g < ng && q.g < q.V;
-                            bool bad = false;
-                            if (act) {
-                                if (q.k == 0 && (cand == b || (!UNIFORM && (int64_t) R.len[cand] < Ls))) bad = true;
-                                if ((uint32_t) q.k < nw) {
-                                    uint32_t x = __funnelshift_r(own[wo + q.k], own[wo + q.k + 1], sh) ^
-                                                 __ldg(read_ptr(R, cand) + q.k);
-                                    if ((uint32_t) q.k == nw - 1 && (nbits & 31u)) x &= (1u << (nbits & 31u)) - 1u;
-                                    bad |= x != 0;
-                                }
-                            }
-                            okA = group_ok(q, act, bad);
-                        }
-                        if (chunk & two) {
-                            const uint32_t cand = __shfl_sync(kFull, c1, src);
-                            const bool act = q.g < ng && q.g < q.V && ((two >> src) & 1u);
-                            bool bad = false;
-                            if (act) {
-                                if (q.k == 0 && (cand == b || (!UNIFORM && (int64_t) R.len[cand] < Ls))) bad = true;
-                                if ((uint32_t) q.k < nw) {
-                                    uint32_t x = __funnelshift_r(own[wo + q.k], own[wo + q.k + 1], sh) ^
-                                                 __ldg(read_ptr(R, cand) + q.k);
-                                    if ((uint32_t) q.k == nw - 1 && (nbits & 31u)) x &= (1u << (nbits & 31u)) - 1u;
-                                    bad |= x != 0;
-                                }
-                            }
-                            okB = group_ok(q, act, bad);
-                        }
-                        // results back to the candidate lanes, ranks in priority order
-                        const bool mine = (chunk >> lane) & 1u;
-                        const int gi = __popc(chunk & lt);
-                        const bool ok0 = mine && ((okA >> gi) & 1u), ok1 = mine && n > 1 && ((okB >> gi) & 1u);
-                        const int nh = (int) ok0 + (int) ok1;
-                        const unsigned m1 = __ballot_sync(kFull, nh >= 1), m2 = __ballot_sync(kFull, nh >= 2);
-                        if (nh) {
-                            const int rank = found + __popc(m1 & lt) + __popc(m2 & lt);
-                            if (rank < kSmallEdgesKept) {
-                                const uint32_t h0 = ok0 ? c0 : c1;
-                                const uint64_t t = overhang_tail_own(own, o);
-                                slots[rank] = make_int2((int32_t) h0, (int32_t) o);
-                                slots_t[rank] = t;
-                                if (indeg) atomicAdd(indeg + h0, 1u);
-                                if (nh == 2 && rank + 1 < kSmallEdgesKept) {
-                                    slots[rank + 1] = make_int2((int32_t) c1, (int32_t) o);
-                                    slots_t[rank + 1] = t;
-                                    if (indeg) atomicAdd(indeg + c1, 1u);
-                                }
-                            }
-                        }
-                        found += __popc(m1) + __popc(m2);
-                    }
-                }
-            }
-        }
-        if (found > kSmallEdgesKept) found = kSmallEdgesKept;
-        __syncwarp();
-        if (hard) {
-            // undo what earlier batches already emitted; the generic path redoes the whole read
-            if (lane < found && indeg) atomicSub(indeg + (uint32_t) slots[lane].x, 1u);
-            if (lane == 0) hard_queue[atomicAdd(n_hard, 1u)] = b;
-        } else if (lane >= found && lane < kSmallEdgesKept) {
-            slots[lane] = make_int2(-1, 0);
-        }
-        __syncwarp();
+        phase1_generic_read(R, T, P, b, fwd + s0, fwd_t + s0, fwd_pos + s0, indeg, lane);
     }
 }
 
@@ -423,16 +190,18 @@ __global__ void count_targets_kernel(const int32_t *__restrict__ triples, uint64
     }
 }
 
-__global__ void scatter_rev_slots_kernel(const int2 *__restrict__ fwd, const uint64_t *__restrict__ fwd_t, uint32_t b_lo,
-                                         uint64_t n_slots, uint32_t c_lo, uint32_t c_hi,
-                                         const uint32_t *__restrict__ rev_off, uint32_t *cursor, int2 *__restrict__ rev,
-                                         uint64_t *__restrict__ rev_t) {
+// rows of the transposed phase-1 graph; the position of every entry inside its row was fixed by the atomicAdd
+// that counted it (fwd_pos), so the scatter itself needs no atomics
+__global__ void scatter_rev_slots_kernel(const int2 *__restrict__ fwd, const uint64_t *__restrict__ fwd_t,
+                                         const uint32_t *__restrict__ fwd_pos, uint32_t b_lo, uint64_t n_slots,
+                                         uint32_t c_lo, uint32_t c_hi, const uint32_t *__restrict__ rev_off,
+                                         int2 *__restrict__ rev, uint64_t *__restrict__ rev_t) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t) gridDim.x * blockDim.x) {
         const int2 e = fwd[i];
         if (e.x < 0) continue;
         const uint32_t c = (uint32_t) e.x;
         if (c < c_lo || c >= c_hi) continue;
-        const uint32_t pos = rev_off[c - c_lo] + atomicSub(cursor + (c - c_lo), 1u) - 1u;
+        const uint32_t pos = rev_off[c - c_lo] + fwd_pos[i];
         rev[pos] = make_int2((int32_t) (b_lo + i / kSmallEdgesKept), e.y);
         rev_t[pos] = fwd_t[i];
     }
@@ -713,224 +482,6 @@ phase2_spill_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, const uint32_
     }
 }
 
-// Phase 2, fast path: target read c, lanes = overlap lengths from max(rs, lmin) upwards.  Tag hits become
-// tentative arrivals (b, o) in canonical order (L asc, b asc) behind the in-neighbours of the transposed phase-1
-// graph.  The sequential replay of GraphCreatorPrefSuf.cpp:403-483 is evaluated in closed form: an entry survives
-// unless a LATER arrival j with offset o_j > 0 has an overhang that is a suffix of the entry's overhang
-// (a[oa-oj .. oa) == b[0 .. oj), right offset >= 0) -- the test does not depend on the list state because entries
-// never return once removed, and "is a suffix of" is transitive, so an entry that a removed arrival would remove is
-// also removed by whoever removed that arrival.  Hence verification is lazy: only tentative arrivals that no
-// verified later arrival removes are compared in full (from the last one downwards, up to four per round, one
-// group of lanes per candidate); with o_j <= 32 the removal test is one XOR + shift on the 64-bit overhang tails.
-// Targets with a repeated source id, more than 32 entries or an offset above 32 take the generic path.
-constexpr int kOutBuf = 64;  // staged output triples per warp: one atomicAdd on the edge counter per >= 32 edges
-
-template <bool UNIFORM>
-__global__ void __launch_bounds__(kThreads)
-phase2_fast_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, const uint32_t *__restrict__ rev_off,
-                   const int2 *__restrict__ rev, const uint64_t *__restrict__ rev_t, Phase2Out out, int force_hard) {
-    __shared__ uint32_t s_own[kWarpsPerBlock][kOwnStride];
-    __shared__ uint32_t s_id[kWarpsPerBlock][kMaxArrivals], s_o[kWarpsPerBlock][kMaxArrivals],
-        s_len[kWarpsPerBlock][kMaxArrivals];
-    __shared__ uint64_t s_t[kWarpsPerBlock][kMaxArrivals];
-    __shared__ int32_t s_out[kWarpsPerBlock][kOutBuf * 3];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const unsigned lt = (1u << lane) - 1u;
-    uint32_t *own = s_own[wib];
-    uint32_t *a_id = s_id[wib], *a_o = s_o[wib], *a_len = s_len[wib];
-    uint64_t *a_t = s_t[wib];
-    int32_t *obuf = s_out[wib];
-    uint32_t n_out = 0;  // staged triples (warp-uniform)
-    const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib;
-    const uint32_t n_warps = gridDim.x * kWarpsPerBlock;
-    const int32_t l_lo = P.rs > P.lmin ? P.rs : P.lmin;
-
-    auto flush = [&]() {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(out.n_edges, (unsigned long long) n_out);
-        base = __shfl_sync(kFull, base, 0);
-        __syncwarp();
-        for (uint32_t i = lane; i < n_out * 3; i += 32) {
-            const unsigned long long pos = base * 3 + i;
-            if (pos < out.edge_cap * 3) out.triples[pos] = obuf[i];
-        }
-        __syncwarp();
-        n_out = 0;
-    };
-
-    for (uint64_t cc = (uint64_t) lo + warp; cc < hi; cc += n_warps) {
-        const uint32_t c = (uint32_t) cc;
-        const uint32_t r0 = rev_off[c - lo], deg = rev_off[c - lo + 1] - r0;
-        const uint32_t lenc = UNIFORM ? P.uniform_len : R.len[c];
-        int64_t l_hi = lenc;
-        if (l_hi > P.max_l) l_hi = P.max_l;
-        const bool active = lenc != 0 && flag_to(R, c) && l_hi >= l_lo;
-        if (!active && deg == 0) continue;
-        bool hard = force_hard || deg > (uint32_t) kMaxArrivals;
-        uint32_t cnt = 0;
-        __syncwarp();
-        if (!hard) {
-            // in-neighbours from phase 1 (row of the transposed graph) take the first slots
-            if ((uint32_t) lane < deg) {
-                const int2 e = rev[r0 + lane];
-                a_id[lane] = (uint32_t) e.x;
-                a_o[lane] = (uint32_t) e.y;
-                a_t[lane] = rev_t[r0 + lane];
-                if (!UNIFORM) a_len[lane] = R.len[e.x];
-            }
-            cnt = deg;
-        }
-        if (!hard && active) {
-            const uint32_t need = (uint32_t) ((2 * l_hi + 31) >> 5);
-            const uint32_t have_w = (lenc + 15u) >> 4;
-            stage_own(own, read_ptr(R, c), need < have_w ? need : have_w, lane);
-            for (int32_t l_base = l_lo; l_base <= (int32_t) l_hi; l_base += 32) {
-                const int32_t L = l_base + lane;
-                const bool valid = L <= (int32_t) l_hi;
-                const uint64_t win = sbits64(own, valid ? 2u * (uint32_t) (L - P.seed_nt) : 0u) & P.seed_mask;
-                uint32_t b0, b1;
-                int n;
-                probe_two(T, win, valid, b0, b1, n);
-                bool bad = n > 2;
-                if (n == 2 && b1 < b0) {  // within one length the smaller source id arrives first
-                    const uint32_t x = b0;
-                    b0 = b1;
-                    b1 = x;
-                }
-                // tentative arrivals: length / offset checks and the overhang tail (first words of the candidate)
-                bool k0 = false, k1 = false;
-                uint32_t len0 = lenc, len1 = lenc;
-                uint64_t t0 = 0, t1 = 0;
-                if (n > 0 && b0 != c) {
-                    if (!UNIFORM) len0 = R.len[b0];
-                    if ((int64_t) len0 - P.min_offset >= L) {
-                        const uint32_t o = len0 - (uint32_t) L;
-                        if (o > 32u) bad = true;
-                        else t0 = overhang_tail(read_ptr(R, b0), o);
-                        k0 = true;
-                    }
-                }
-                if (n > 1 && b1 != c) {
-                    if (!UNIFORM) len1 = R.len[b1];
-                    if ((int64_t) len1 - P.min_offset >= L) {
-                        const uint32_t o = len1 - (uint32_t) L;
-                        if (o > 32u) bad = true;
-                        else t1 = overhang_tail(read_ptr(R, b1), o);
-                        k1 = true;
-                    }
-                }
-                const int nh = (int) k0 + (int) k1;
-                const unsigned m1 = __ballot_sync(kFull, nh >= 1), m2 = __ballot_sync(kFull, nh >= 2);
-                const uint32_t total = __popc(m1) + __popc(m2);
-                if (__any_sync(kFull, bad) || cnt + total > (uint32_t) kMaxArrivals) {
-                    hard = true;
-                    break;
-                }
-                if (nh) {
-                    const uint32_t slot = cnt + __popc(m1 & lt) + __popc(m2 & lt);
-                    const uint32_t f_id = k0 ? b0 : b1, f_len = k0 ? len0 : len1;
-                    a_id[slot] = f_id;
-                    a_o[slot] = f_len - (uint32_t) L;
-                    a_len[slot] = f_len;
-                    a_t[slot] = k0 ? t0 : t1;
-                    if (nh == 2) {
-                        a_id[slot + 1] = b1;
-                        a_o[slot + 1] = len1 - (uint32_t) L;
-                        a_len[slot + 1] = len1;
-                        a_t[slot + 1] = t1;
-                    }
-                }
-                cnt += total;
-            }
-        }
-        __syncwarp();
-        const bool have = !hard && (uint32_t) lane < cnt;
-        const uint32_t id = have ? a_id[lane] : kNone, o = have ? a_o[lane] : 0u;
-        const uint32_t len = (have && !UNIFORM) ? a_len[lane] : 0u;
-        const uint64_t t = have ? a_t[lane] : 0ull;
-        if (!hard && cnt > 1) {
-            // the same read twice among the entries (same-id replacement / retainOnlySmallestOffset): generic path
-            const unsigned vm = cnt >= 32 ? kFull : ((1u << cnt) - 1u);
-            bool dup = false;
-            if (have) dup = __match_any_sync(vm, id) != (1u << lane);
-            hard = __any_sync(kFull, dup);
-        }
-        if (hard) {
-            if (lane == 0) out.spill_queue[atomicAdd(out.n_spill, 1u)] = c;
-            continue;
-        }
-        if (cnt == 0) continue;
-        bool alive = have, verified = (uint32_t) lane < deg;
-        if (cnt > deg) {
-            const GroupGeom q = group_geom((int) ((2 * l_hi + 31) >> 5), lane);
-            while (true) {
-                const unsigned cm = __ballot_sync(kFull, have && alive && !verified);
-                if (!cm) break;
-                // chunk = the V last unverified candidates that are still alive; group i verifies the i-th of them
-                unsigned chunk = 0, p = cm;
-                int src = 0, js[4] = {0, 0, 0, 0};
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (i < q.V && p) {
-                        const int l = 31 - __clz(p);
-                        if (i == q.g) src = l;
-                        js[i] = l;
-                        chunk |= 1u << l;
-                        p &= ~(1u << l);
-                    }
-                }
-                const int ng = __popc(chunk);
-                const bool act = q.g < ng && q.g < q.V;
-                bool bad = false;
-                if (act) {
-                    const uint32_t bj = a_id[src], oj = a_o[src];
-                    const uint32_t lenj = UNIFORM ? lenc : a_len[src];
-                    const uint32_t nbits = 2u * (lenj - oj), nw = (nbits + 31u) >> 5;
-                    if ((uint32_t) q.k < nw) {
-                        const uint32_t *qb = read_ptr(R, bj) + ((2u * oj) >> 5);
-                        uint32_t x = __funnelshift_r(__ldg(qb + q.k), __ldg(qb + q.k + 1), (2u * oj) & 31u) ^ own[q.k];
-                        if ((uint32_t) q.k == nw - 1 && (nbits & 31u)) x &= (1u << (nbits & 31u)) - 1u;
-                        bad = x != 0;
-                    }
-                }
-                const unsigned okbits = group_ok(q, act, bad);
-                if ((chunk >> lane) & 1u) {
-                    verified = true;
-                    const int gi = __popc(chunk >> (lane + 1)) ;
-                    if (!((okbits >> gi) & 1u)) alive = false;
-                }
-                // every arrival confirmed in this round removes the earlier entries whose overhang ends with its own
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (i < ng && ((okbits >> i) & 1u)) {
-                        const int j = js[i];
-                        const uint32_t oj = a_o[j];
-                        if (oj == 0) continue;
-                        const uint64_t tj = a_t[j];
-                        if (have && alive && lane < j && o >= oj &&
-                            (UNIFORM || (int64_t) a_len[j] + (int64_t) (o - oj) - (int64_t) len >= 0) &&
-                            ((t ^ tj) >> (64u - 2u * oj)) == 0)
-                            alive = false;
-                    }
-                }
-            }
-        }
-        const unsigned keep = __ballot_sync(kFull, have && alive);
-        if (keep) {
-            if (have && alive) {
-                const uint32_t pos = n_out + __popc(keep & lt);
-                obuf[3 * pos] = (int32_t) id;
-                obuf[3 * pos + 1] = (int32_t) c;
-                obuf[3 * pos + 2] = (int32_t) o;
-                if (out.outdeg) atomicAdd(out.outdeg + id, 1u);
-            }
-            n_out += __popc(keep);
-            if (n_out >= 32) flush();
-        }
-    }
-    if (n_out) flush();
-}
-
 // ------------------------------------------------------------------------------------------------
 // CSR assembly
 __global__ void count_sources_kernel(const int32_t *__restrict__ triples, uint64_t n, uint32_t lo, uint32_t hi, int swap,
@@ -1111,21 +662,14 @@ void launch_build_index(const ReadsDev &R, const PsDev &P, SeedTable prefix, See
     bump(cfg);
 }
 
-void launch_phase1(const ReadsDev &R, const SeedTable &prefix, const PsDev &P, uint32_t lo, uint32_t hi, int2 *fwd,
-                   uint64_t *fwd_t, uint32_t *indeg, uint32_t *hard_queue, uint32_t *n_hard, int force_hard,
-                   cudaStream_t s, const LaunchCfg &cfg) {
-    if (hi <= lo) return;
-    const int grid = grid_for(hi - lo, kWarpsPerBlock, cfg, 8);
-    if (P.uniform_len)
-        phase1_fast_kernel<true><<<grid, kThreads, 0, s>>>(R, prefix, P, lo, hi, fwd, fwd_t, indeg, hard_queue, n_hard,
-                                                           force_hard);
-    else
-        phase1_fast_kernel<false><<<grid, kThreads, 0, s>>>(R, prefix, P, lo, hi, fwd, fwd_t, indeg, hard_queue, n_hard,
-                                                            force_hard);
-    bump(cfg);
-    // the reads the fast kernel handed back (device-side count: no host round trip; usually zero)
-    phase1_queue_kernel<<<grid_for(force_hard ? hi - lo : 4096, kWarpsPerBlock, cfg, 8), kThreads, 0, s>>>(
-        R, prefix, P, lo, hard_queue, n_hard, fwd, fwd_t, indeg);
+void launch_phase1_queue(const ReadsDev &R, const SeedTable &prefix, const PsDev &P, uint32_t lo, uint32_t n_max,
+                         const uint32_t *hard_queue, const uint32_t *n_hard, int2 *fwd, uint64_t *fwd_t, uint32_t *fwd_pos,
+                         uint32_t *indeg, cudaStream_t s, const LaunchCfg &cfg) {
+    if (!n_max) return;
+    // the queue length lives on the device (no host round trip; usually zero): size the grid for a short queue
+    // unless the caller knows that every read is in it
+    phase1_queue_kernel<<<grid_for(n_max, kWarpsPerBlock, cfg, 8), kThreads, 0, s>>>(R, prefix, P, lo, hard_queue, n_hard,
+                                                                                       fwd, fwd_t, fwd_pos, indeg);
     bump(cfg);
 }
 
@@ -1144,13 +688,13 @@ void launch_count_targets(const int32_t *triples, uint64_t n, uint32_t lo, uint3
     bump(cfg);
 }
 
-void launch_scatter_rev_slots(const int2 *fwd, const uint64_t *fwd_t, uint32_t b_lo, uint32_t b_hi, uint32_t c_lo,
-                              uint32_t c_hi, const uint32_t *rev_off, uint32_t *cursor, int2 *rev, uint64_t *rev_t,
-                              cudaStream_t s, const LaunchCfg &cfg) {
+void launch_scatter_rev_slots(const int2 *fwd, const uint64_t *fwd_t, const uint32_t *fwd_pos, uint32_t b_lo,
+                              uint32_t b_hi, uint32_t c_lo, uint32_t c_hi, const uint32_t *rev_off, int2 *rev,
+                              uint64_t *rev_t, cudaStream_t s, const LaunchCfg &cfg) {
     if (b_hi <= b_lo) return;
     const uint64_t n_slots = (uint64_t) (b_hi - b_lo) * kSmallEdgesKept;
-    scatter_rev_slots_kernel<<<grid_for(n_slots, 256, cfg), 256, 0, s>>>(fwd, fwd_t, b_lo, n_slots, c_lo, c_hi, rev_off,
-                                                                           cursor, rev, rev_t);
+    scatter_rev_slots_kernel<<<grid_for(n_slots, 256, cfg), 256, 0, s>>>(fwd, fwd_t, fwd_pos, b_lo, n_slots, c_lo, c_hi,
+                                                                           rev_off, rev, rev_t);
     bump(cfg);
 }
 
@@ -1160,18 +704,6 @@ void launch_scatter_rev_triples(const ReadsDev &R, const int32_t *triples, uint6
     if (!n) return;
     scatter_rev_triples_kernel<<<grid_for(n, 256, cfg), 256, 0, s>>>(R, triples, n, c_lo, c_hi, rev_off, cursor, rev,
                                                                        rev_t);
-    bump(cfg);
-}
-
-void launch_phase2_fast(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo, uint32_t hi,
-                        const uint32_t *rev_off, const int2 *rev, const uint64_t *rev_t, const Phase2Out &out,
-                        int force_hard, cudaStream_t s, const LaunchCfg &cfg) {
-    if (hi <= lo) return;
-    const int grid = grid_for(hi - lo, kWarpsPerBlock, cfg, 8);
-    if (P.uniform_len)
-        phase2_fast_kernel<true><<<grid, kThreads, 0, s>>>(R, suffix, P, lo, hi, rev_off, rev, rev_t, out, force_hard);
-    else
-        phase2_fast_kernel<false><<<grid, kThreads, 0, s>>>(R, suffix, P, lo, hi, rev_off, rev, rev_t, out, force_hard);
     bump(cfg);
 }
 
