@@ -130,7 +130,7 @@ struct alga_ps_plan {
     // owned copies (upload path)
     DevBuf words, word_off, len, from, to;
     // workspace
-    DevBuf stats_d, counters_d, tp, ts, fwd, fwd_t, fwd_pos, rev_t, hard1, indeg, rev_off, rev, triples, triples1, outdeg, scan_ws, spill_queue, caps,
+    DevBuf stats_d, counters_d, tp, ts, fwd, fwd_t, fwd_pos, hard1, indeg, rev_off, rev, triples, triples1, outdeg, scan_ws, spill_queue, caps,
         spill_off, spill_store, row_off, nbr, off, big_rows, tmp_nbr, tmp_off;
     SeedTable Tp{}, Ts{};
     Counters *h_counters = nullptr;  // pinned
@@ -147,7 +147,7 @@ struct alga_ps_plan {
     cudaEvent_t ev_stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     ~alga_ps_plan() {
-        DevBuf *all[] = {&words, &word_off, &len, &from, &to, &stats_d, &counters_d, &tp, &ts, &fwd, &fwd_t, &fwd_pos, &rev_t, &hard1, &indeg, &rev_off, &rev,
+        DevBuf *all[] = {&words, &word_off, &len, &from, &to, &stats_d, &counters_d, &tp, &ts, &fwd, &fwd_t, &fwd_pos, &hard1, &indeg, &rev_off, &rev,
                          &triples, &triples1, &outdeg, &scan_ws, &spill_queue, &caps, &spill_off, &spill_store, &row_off,
                          &nbr, &off, &big_rows, &tmp_nbr, &tmp_off};
         for (DevBuf *b : all) b->release();
@@ -215,7 +215,12 @@ int compute_stats(alga_ps_plan *plan, cudaStream_t s, uint32_t max_len_hint) {
 
 uint32_t buckets_for(uint32_t entries) {
     // mean occupancy 2 of 8 slots: P(bucket full) ~ 1e-3, so a probe rarely chains into a second sector
-    uint64_t nb = ((uint64_t) entries + 1) / 2;
+    static const int load = [] {  // tuning knob: mean entries per 8-slot bucket
+        const char *e = getenv("ALGA_PS_BUCKET_LOAD");
+        const int v = e ? atoi(e) : 2;
+        return v >= 1 && v <= 6 ? v : 2;
+    }();
+    uint64_t nb = ((uint64_t) entries + load - 1) / load;
     if (nb < 64) nb = 64;
     return (uint32_t) nb;
 }
@@ -261,12 +266,12 @@ int run_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, uint32_t *outdeg, c
         Phase2Out out{plan->triples.as<int32_t>(), &dc->n_edges, edge_cap, outdeg, plan->spill_queue.as<uint32_t>(),
                       &dc->n_spill};
         if (plan->params.list_cap > 0)  // testing: generic kernel with a tiny on-chip list
-            launch_phase2(plan->R, plan->Ts, plan->P, lo, hi, plan->rev_off.as<uint32_t>(), plan->rev.as<int2>(),
+            launch_phase2(plan->R, plan->Ts, plan->P, lo, hi, plan->rev_off.as<uint32_t>(), plan->rev.as<RevEntry>(),
                           list_cap, out, s, plan->cfg);
         else
             launch_phase2_tpr(plan->R, plan->Ts, plan->P, plan->stats.max_len, lo, hi, plan->rev_off.as<uint32_t>(),
-                              plan->rev.as<int2>(), plan->rev_t.as<uint64_t>(), out,
-                              plan->params.flags & ALGA_PS_FORCE_GENERIC, s, plan->cfg);
+                              plan->rev.as<RevEntry>(), out, plan->params.flags & ALGA_PS_FORCE_GENERIC, s,
+                              plan->cfg);
         CK(cudaGetLastError());
         CKR(read_counters(plan, s));
         const uint32_t n_spill = plan->h_counters->n_spill;
@@ -285,7 +290,7 @@ int run_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, uint32_t *outdeg, c
             CK(cudaStreamSynchronize(s));
             const uint64_t total = *plan->h_u64;
             CKR(plan->spill_store.ensure((size_t) total * 12 + 16));
-            launch_phase2_spill(plan->R, plan->Ts, plan->P, lo, plan->rev_off.as<uint32_t>(), plan->rev.as<int2>(),
+            launch_phase2_spill(plan->R, plan->Ts, plan->P, lo, plan->rev_off.as<uint32_t>(), plan->rev.as<RevEntry>(),
                                 plan->spill_queue.as<uint32_t>(), n_spill, plan->spill_off.as<uint64_t>(),
                                 plan->spill_store.as<uint32_t>(), out, s, plan->cfg);
             CK(cudaGetLastError());
@@ -508,10 +513,9 @@ int alga_ps_stage_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int
     CK(cudaMemsetAsync(plan->indeg.p, 0, (size_t) (n ? n : 1) * 4, s));
     launch_count_targets(tin, n_in, lo, hi, plan->indeg.as<uint32_t>(), s, plan->cfg);
     CKR(build_rev_from_counts(plan, n, s));
-    CKR(plan->rev.ensure((size_t) (n_in ? n_in : 1) * sizeof(int2)));
-    CKR(plan->rev_t.ensure((size_t) (n_in ? n_in : 1) * 8));
+    CKR(plan->rev.ensure((size_t) (n_in ? n_in : 1) * sizeof(RevEntry)));
     launch_scatter_rev_triples(plan->R, tin, n_in, lo, hi, plan->rev_off.as<uint32_t>(), plan->indeg.as<uint32_t>(),
-                               plan->rev.as<int2>(), plan->rev_t.as<uint64_t>(), s, plan->cfg);
+                               plan->rev.as<RevEntry>(), s, plan->cfg);
     CK(cudaGetLastError());
     CKR(run_phase2(plan, lo, hi, nullptr, s));
     *dev_triples_out = plan->triples.as<int32_t>();
@@ -558,10 +562,9 @@ int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
     CK(cudaEventRecord(plan->ev_stage[1], s));
     // reversed phase-1 graph (rows by target)
     CKR(build_rev_from_counts(plan, n, s));
-    CKR(plan->rev.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * sizeof(int2)));
-    CKR(plan->rev_t.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * 8));
+    CKR(plan->rev.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * sizeof(RevEntry)));
     launch_scatter_rev_slots(plan->fwd.as<int2>(), plan->fwd_t.as<uint64_t>(), plan->fwd_pos.as<uint32_t>(), 0, n, 0, n,
-                             plan->rev_off.as<uint32_t>(), plan->rev.as<int2>(), plan->rev_t.as<uint64_t>(), s, plan->cfg);
+                             plan->rev_off.as<uint32_t>(), plan->rev.as<RevEntry>(), s, plan->cfg);
     CK(cudaGetLastError());
     CK(cudaEventRecord(plan->ev_stage[2], s));
     // phase 2 with fused out-degree counting (not in the reversed-result corner)

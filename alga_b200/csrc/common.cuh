@@ -42,6 +42,13 @@ struct PsDev {
     uint64_t seed_mask;  // low 2K bits
 };
 
+// One entry of the transposed phase-1 graph (row of a target read): source read, offset, overhang tail.  16 bytes =
+// one 128-bit load / store.
+struct __align__(16) RevEntry {
+    int32_t b, o;
+    uint64_t t;
+};
+
 // Seed index: open addressing, one 32-byte sector per bucket, 8 entries of (tag << id_bits) | read id.  The tag
 // takes whatever bits the read id leaves free (10 bits for 4 M reads, 5 for 128 M); a false tag hit only costs an
 // exact compare.  Buckets are sized for a mean occupancy of 2 of 8, so a probe almost never leaves its first sector.

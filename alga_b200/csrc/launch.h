@@ -47,10 +47,10 @@ void launch_compact_slots(const int2 *fwd, uint32_t lo, uint32_t hi, int32_t *tr
 void launch_count_targets(const int32_t *triples, uint64_t n, uint32_t lo, uint32_t hi, uint32_t *indeg,
                           cudaStream_t s, const LaunchCfg &cfg);
 void launch_scatter_rev_slots(const int2 *fwd, const uint64_t *fwd_t, const uint32_t *fwd_pos, uint32_t b_lo,
-                              uint32_t b_hi, uint32_t c_lo, uint32_t c_hi, const uint32_t *rev_off, int2 *rev,
-                              uint64_t *rev_t, cudaStream_t s, const LaunchCfg &cfg);
+                              uint32_t b_hi, uint32_t c_lo, uint32_t c_hi, const uint32_t *rev_off, RevEntry *rev,
+                              cudaStream_t s, const LaunchCfg &cfg);
 void launch_scatter_rev_triples(const ReadsDev &R, const int32_t *triples, uint64_t n, uint32_t c_lo, uint32_t c_hi,
-                                const uint32_t *rev_off, uint32_t *cursor, int2 *rev, uint64_t *rev_t, cudaStream_t s,
+                                const uint32_t *rev_off, uint32_t *cursor, RevEntry *rev, cudaStream_t s,
                                 const LaunchCfg &cfg);
 
 // --- phase 2: L in [max(rs,lmin), max_l] with per-target transitive reduction ----------------------
@@ -64,18 +64,18 @@ struct Phase2Out {
 };
 // thread-per-target fast kernel (tpr_kernels.cu); everything it cannot take goes to out.spill_queue
 void launch_phase2_tpr(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t max_len_nt, uint32_t lo,
-                       uint32_t hi, const uint32_t *rev_off, const int2 *rev, const uint64_t *rev_t, const Phase2Out &out,
-                       int force_hard, cudaStream_t s, const LaunchCfg &cfg);
+                       uint32_t hi, const uint32_t *rev_off, const RevEntry *rev, const Phase2Out &out, int force_hard,
+                       cudaStream_t s, const LaunchCfg &cfg);
 // generic path: sequential replay on a shared-memory list of list_cap entries per target (spills beyond it)
 void launch_phase2(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo, uint32_t hi,
-                   const uint32_t *rev_off, const int2 *rev, int list_cap, const Phase2Out &out, cudaStream_t s,
+                   const uint32_t *rev_off, const RevEntry *rev, int list_cap, const Phase2Out &out, cudaStream_t s,
                    const LaunchCfg &cfg);
 // spill path: per queued target count row size + hits -> caps (u32), then replay with global lists
 void launch_phase2_count(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo,
                          const uint32_t *rev_off, const uint32_t *queue, uint32_t n_queue, uint32_t *caps,
                          cudaStream_t s, const LaunchCfg &cfg);
 void launch_phase2_spill(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo,
-                         const uint32_t *rev_off, const int2 *rev, const uint32_t *queue, uint32_t n_queue,
+                         const uint32_t *rev_off, const RevEntry *rev, const uint32_t *queue, uint32_t n_queue,
                          const uint64_t *spill_off, uint32_t *spill_store, const Phase2Out &out, cudaStream_t s,
                          const LaunchCfg &cfg);
 

@@ -195,29 +195,35 @@ __global__ void count_targets_kernel(const int32_t *__restrict__ triples, uint64
 __global__ void scatter_rev_slots_kernel(const int2 *__restrict__ fwd, const uint64_t *__restrict__ fwd_t,
                                          const uint32_t *__restrict__ fwd_pos, uint32_t b_lo, uint64_t n_slots,
                                          uint32_t c_lo, uint32_t c_hi, const uint32_t *__restrict__ rev_off,
-                                         int2 *__restrict__ rev, uint64_t *__restrict__ rev_t) {
+                                         RevEntry *__restrict__ rev) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t) gridDim.x * blockDim.x) {
         const int2 e = fwd[i];
         if (e.x < 0) continue;
         const uint32_t c = (uint32_t) e.x;
         if (c < c_lo || c >= c_hi) continue;
         const uint32_t pos = rev_off[c - c_lo] + fwd_pos[i];
-        rev[pos] = make_int2((int32_t) (b_lo + i / kSmallEdgesKept), e.y);
-        rev_t[pos] = fwd_t[i];
+        RevEntry r;
+        r.b = (int32_t) (b_lo + i / kSmallEdgesKept);
+        r.o = e.y;
+        r.t = fwd_t[i];
+        rev[pos] = r;
     }
 }
 
 __global__ void scatter_rev_triples_kernel(ReadsDev R, const int32_t *__restrict__ triples, uint64_t n, uint32_t c_lo,
                                            uint32_t c_hi, const uint32_t *__restrict__ rev_off, uint32_t *cursor,
-                                           int2 *__restrict__ rev, uint64_t *__restrict__ rev_t) {
+                                           RevEntry *__restrict__ rev) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
         const uint32_t c = (uint32_t) triples[3 * i + 1];
         if (c < c_lo || c >= c_hi) continue;
         const uint32_t pos = rev_off[c - c_lo] + atomicSub(cursor + (c - c_lo), 1u) - 1u;
         const int32_t b = triples[3 * i], o = triples[3 * i + 2];
-        rev[pos] = make_int2(b, o);
+        RevEntry r;
+        r.b = b;
+        r.o = o;
         // the overhang tail does not travel with exchanged triples: rebuild it from the (replicated) read
-        rev_t[pos] = overhang_tail(read_ptr(R, (uint32_t) b), (uint32_t) o);
+        r.t = overhang_tail(read_ptr(R, (uint32_t) b), (uint32_t) o);
+        rev[pos] = r;
     }
 }
 
@@ -302,14 +308,14 @@ __device__ __forceinline__ bool replay_hit(const ReadsDev &R, uint32_t b, int32_
 
 // Load row c of the reversed phase-1 graph and apply Graph::retainOnlySmallestOffset (Graph.cpp:348-387):
 // one entry per source read, smallest offset wins.  Returns false when the row does not fit.
-__device__ __forceinline__ bool load_rev_row(const ReadsDev &R, const int2 *__restrict__ row, uint32_t deg,
+__device__ __forceinline__ bool load_rev_row(const ReadsDev &R, const RevEntry *__restrict__ row, uint32_t deg,
                                              NbrList &lst, uint32_t &cnt, int lane) {
     cnt = 0;
     if (deg > lst.cap) return false;
     for (uint32_t j = lane; j < deg; j += 32) {
-        const int2 e = row[j];
-        lst.a[j] = (uint32_t) e.x;
-        lst.o[j] = (uint32_t) e.y;
+        const RevEntry e = row[j];
+        lst.a[j] = (uint32_t) e.b;
+        lst.o[j] = (uint32_t) e.o;
         lst.len[j] = 0;
     }
     __syncwarp();
@@ -353,7 +359,7 @@ __device__ __forceinline__ bool load_rev_row(const ReadsDev &R, const int2 *__re
 
 // All of phase 2 for one target read c on one warp.  Returns false when the list overflowed.
 __device__ __forceinline__ bool phase2_target(const ReadsDev &R, const SeedTable &T, const PsDev &P, uint32_t c,
-                                              const int2 *__restrict__ row, uint32_t deg, NbrList &lst,
+                                              const RevEntry *__restrict__ row, uint32_t deg, NbrList &lst,
                                               const Phase2Out &out, int lane) {
     uint32_t cnt = 0;
     if (!load_rev_row(R, row, deg, lst, cnt, lane)) return false;
@@ -412,7 +418,7 @@ __device__ __forceinline__ bool phase2_target(const ReadsDev &R, const SeedTable
 
 __global__ void __launch_bounds__(kThreads)
 phase2_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, const uint32_t *__restrict__ rev_off,
-              const int2 *__restrict__ rev, int list_cap, Phase2Out out) {
+              const RevEntry *__restrict__ rev, int list_cap, Phase2Out out) {
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -463,7 +469,7 @@ phase2_count_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, const uint32_
 // spill path, pass 2: same replay with the list in global memory (capacity from pass 1)
 __global__ void __launch_bounds__(kThreads)
 phase2_spill_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, const uint32_t *__restrict__ rev_off,
-                    const int2 *__restrict__ rev, const uint32_t *__restrict__ queue, uint32_t n_queue,
+                    const RevEntry *__restrict__ rev, const uint32_t *__restrict__ queue, uint32_t n_queue,
                     const uint64_t *__restrict__ spill_off, uint32_t *spill_store, Phase2Out out) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -689,26 +695,25 @@ void launch_count_targets(const int32_t *triples, uint64_t n, uint32_t lo, uint3
 }
 
 void launch_scatter_rev_slots(const int2 *fwd, const uint64_t *fwd_t, const uint32_t *fwd_pos, uint32_t b_lo,
-                              uint32_t b_hi, uint32_t c_lo, uint32_t c_hi, const uint32_t *rev_off, int2 *rev,
-                              uint64_t *rev_t, cudaStream_t s, const LaunchCfg &cfg) {
+                              uint32_t b_hi, uint32_t c_lo, uint32_t c_hi, const uint32_t *rev_off, RevEntry *rev,
+                              cudaStream_t s, const LaunchCfg &cfg) {
     if (b_hi <= b_lo) return;
     const uint64_t n_slots = (uint64_t) (b_hi - b_lo) * kSmallEdgesKept;
     scatter_rev_slots_kernel<<<grid_for(n_slots, 256, cfg), 256, 0, s>>>(fwd, fwd_t, fwd_pos, b_lo, n_slots, c_lo, c_hi,
-                                                                           rev_off, rev, rev_t);
+                                                                           rev_off, rev);
     bump(cfg);
 }
 
 void launch_scatter_rev_triples(const ReadsDev &R, const int32_t *triples, uint64_t n, uint32_t c_lo, uint32_t c_hi,
-                                const uint32_t *rev_off, uint32_t *cursor, int2 *rev, uint64_t *rev_t, cudaStream_t s,
+                                const uint32_t *rev_off, uint32_t *cursor, RevEntry *rev, cudaStream_t s,
                                 const LaunchCfg &cfg) {
     if (!n) return;
-    scatter_rev_triples_kernel<<<grid_for(n, 256, cfg), 256, 0, s>>>(R, triples, n, c_lo, c_hi, rev_off, cursor, rev,
-                                                                       rev_t);
+    scatter_rev_triples_kernel<<<grid_for(n, 256, cfg), 256, 0, s>>>(R, triples, n, c_lo, c_hi, rev_off, cursor, rev);
     bump(cfg);
 }
 
 void launch_phase2(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo, uint32_t hi,
-                   const uint32_t *rev_off, const int2 *rev, int list_cap, const Phase2Out &out, cudaStream_t s,
+                   const uint32_t *rev_off, const RevEntry *rev, int list_cap, const Phase2Out &out, cudaStream_t s,
                    const LaunchCfg &cfg) {
     if (hi <= lo) return;
     const size_t smem = (size_t) kWarpsPerBlock * 3 * list_cap * sizeof(uint32_t);
@@ -729,7 +734,7 @@ void launch_phase2_count(const ReadsDev &R, const SeedTable &suffix, const PsDev
 }
 
 void launch_phase2_spill(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo,
-                         const uint32_t *rev_off, const int2 *rev, const uint32_t *queue, uint32_t n_queue,
+                         const uint32_t *rev_off, const RevEntry *rev, const uint32_t *queue, uint32_t n_queue,
                          const uint64_t *spill_off, uint32_t *spill_store, const Phase2Out &out, cudaStream_t s,
                          const LaunchCfg &cfg) {
     if (!n_queue) return;

@@ -265,8 +265,7 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
 template <bool UNIFORM>
 __global__ void __launch_bounds__(kTpr, 3)
 phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, int wp, int nw_max,
-                  const uint32_t *__restrict__ rev_off, const int2 *__restrict__ rev, const uint64_t *__restrict__ rev_t,
-                  Phase2Out out, int force_hard) {
+                  const uint32_t *__restrict__ rev_off, const RevEntry *__restrict__ rev, Phase2Out out, int force_hard) {
     extern __shared__ uint32_t smem[];
     const int tid = threadIdx.x, lane = tid & 31;
     uint32_t *own = smem + tid * wp;
@@ -378,8 +377,8 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
         uint32_t rowmask = 0;
         if (part && !hard) {
             for (uint32_t r = 0; r < deg; r++) {
-                const int2 en = rev[r0 + r];
-                const uint32_t a = (uint32_t) en.x, oa = (uint32_t) en.y;
+                const RevEntry en = rev[r0 + r];
+                const uint32_t a = (uint32_t) en.b, oa = (uint32_t) en.o;
                 for (int k = 0; k < n_ids; k++)
                     if (ids[k * kTpr] == a) hard = true;  // the same read twice for one target: generic path
                 if (n_ids >= kIdCap) {
@@ -388,7 +387,7 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
                 }
                 ids[n_ids * kTpr] = a;
                 n_ids++;
-                const uint64_t ta = rev_t[r0 + r];
+                const uint64_t ta = en.t;
                 const uint32_t lena = UNIFORM ? lenc : R.len[a];
                 bool removed = false;
 #pragma unroll
@@ -440,13 +439,13 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
                 }
             }
             for (uint32_t m = rowmask; m; m &= m - 1) {
-                const int2 en = rev[r0 + (__ffs(m) - 1)];
+                const RevEntry en = rev[r0 + (__ffs(m) - 1)];
                 if (pos < out.edge_cap) {
-                    out.triples[3 * pos] = en.x;
+                    out.triples[3 * pos] = en.b;
                     out.triples[3 * pos + 1] = (int32_t) c;
-                    out.triples[3 * pos + 2] = en.y;
+                    out.triples[3 * pos + 2] = en.o;
                 }
-                if (out.outdeg) atomicAdd(out.outdeg + (uint32_t) en.x, 1u);
+                if (out.outdeg) atomicAdd(out.outdeg + (uint32_t) en.b, 1u);
                 pos++;
             }
         }
@@ -489,8 +488,8 @@ void launch_phase1_tpr(const ReadsDev &R, const SeedTable &prefix, const PsDev &
 }
 
 void launch_phase2_tpr(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t max_len_nt, uint32_t lo,
-                       uint32_t hi, const uint32_t *rev_off, const int2 *rev, const uint64_t *rev_t, const Phase2Out &out,
-                       int force_hard, cudaStream_t s, const LaunchCfg &cfg) {
+                       uint32_t hi, const uint32_t *rev_off, const RevEntry *rev, const Phase2Out &out, int force_hard,
+                       cudaStream_t s, const LaunchCfg &cfg) {
     if (hi <= lo) return;
     int64_t lmax = P.max_l;
     if (lmax > (int64_t) max_len_nt) lmax = max_len_nt;
@@ -501,11 +500,11 @@ void launch_phase2_tpr(const ReadsDev &R, const SeedTable &suffix, const PsDev &
     const int grid = tile_grid(hi - lo, cfg, 5);
     if (P.uniform_len) {
         cudaFuncSetAttribute(phase2_tpr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        phase2_tpr_kernel<true><<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, wp, nw_max, rev_off, rev, rev_t, out,
+        phase2_tpr_kernel<true><<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, wp, nw_max, rev_off, rev, out,
                                                          force_hard);
     } else {
         cudaFuncSetAttribute(phase2_tpr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        phase2_tpr_kernel<false><<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, wp, nw_max, rev_off, rev, rev_t, out,
+        phase2_tpr_kernel<false><<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, wp, nw_max, rev_off, rev, out,
                                                           force_hard);
     }
     bump(cfg);
