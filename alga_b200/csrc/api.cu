@@ -99,12 +99,15 @@ struct HostBuf {  // page-locked staging buffer
 
 struct Counters {
     unsigned long long n_edges;
-    unsigned long long n_triples;
+    uint32_t n_list;   // phase-1 edges in list form (staged interface)
+    uint32_t n_over;   // phase-1 edges that did not fit their fixed-capacity row
     uint32_t n_spill;
     uint32_t n_big;
     uint32_t n_hard1;  // source reads phase 1's fast kernel handed to the generic kernel
     uint32_t pad;
 };
+
+constexpr uint32_t kRowCapDefault = 16;  // entries per target in the fixed-capacity rows of the transposed phase-1 graph
 
 double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -130,8 +133,10 @@ struct alga_ps_plan {
     // owned copies (upload path)
     DevBuf words, word_off, len, from, to;
     // workspace
-    DevBuf stats_d, counters_d, tp, ts, fwd, fwd_t, fwd_pos, hard1, indeg, rev_off, rev, triples, triples1, outdeg, scan_ws, spill_queue, caps,
-        spill_off, spill_store, row_off, nbr, off, big_rows, tmp_nbr, tmp_off;
+    DevBuf stats_d, counters_d, tp, ts, rows, over, list1, hard1, indeg, rev_off, rev, triples, triples1, outdeg, scan_ws,
+        spill_queue, caps, spill_off, spill_store, row_off, nbr, off, big_rows, tmp_nbr, tmp_off;
+    uint32_t over_cap = 0;
+    uint32_t row_cap = kRowCapDefault;  // ALGA_PS_ROW_CAP (testing: small rows force the overflow paths)
     SeedTable Tp{}, Ts{};
     Counters *h_counters = nullptr;  // pinned
     ReadStats *h_stats = nullptr;    // pinned
@@ -147,7 +152,7 @@ struct alga_ps_plan {
     cudaEvent_t ev_stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     ~alga_ps_plan() {
-        DevBuf *all[] = {&words, &word_off, &len, &from, &to, &stats_d, &counters_d, &tp, &ts, &fwd, &fwd_t, &fwd_pos, &hard1, &indeg, &rev_off, &rev,
+        DevBuf *all[] = {&words, &word_off, &len, &from, &to, &stats_d, &counters_d, &tp, &ts, &rows, &over, &list1, &hard1, &indeg, &rev_off, &rev,
                          &triples, &triples1, &outdeg, &scan_ws, &spill_queue, &caps, &spill_off, &spill_store, &row_off,
                          &nbr, &off, &big_rows, &tmp_nbr, &tmp_off};
         for (DevBuf *b : all) b->release();
@@ -252,7 +257,7 @@ int stage_index(alga_ps_plan *plan, cudaStream_t s) {
 }
 
 // phase 2 (+ spill path) for targets [lo,hi) given rev rows; leaves triples in plan->triples, count in h_counters
-int run_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, uint32_t *outdeg, cudaStream_t s) {
+int run_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const RowsView &rows, uint32_t *outdeg, cudaStream_t s) {
     const uint32_t n = hi - lo;
     int list_cap = plan->params.list_cap > 0 ? plan->params.list_cap : 64;
     if (list_cap > 2048) list_cap = 2048;
@@ -260,18 +265,17 @@ int run_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, uint32_t *outdeg, c
     CKR(plan->spill_queue.ensure((size_t) (n ? n : 1) * 4));
     for (int attempt = 0; attempt < 3; attempt++) {
         CKR(plan->triples.ensure((size_t) edge_cap * 12));
-        CK(cudaMemsetAsync(plan->counters_d.p, 0, sizeof(Counters), s));
-        if (outdeg) CK(cudaMemsetAsync(outdeg, 0, (size_t) plan->R.n * 4, s));
         Counters *dc = plan->counters_d.as<Counters>();
+        CK(cudaMemsetAsync(&dc->n_edges, 0, 8, s));
+        CK(cudaMemsetAsync(&dc->n_spill, 0, 4, s));
+        if (outdeg) CK(cudaMemsetAsync(outdeg, 0, (size_t) plan->R.n * 4, s));
         Phase2Out out{plan->triples.as<int32_t>(), &dc->n_edges, edge_cap, outdeg, plan->spill_queue.as<uint32_t>(),
                       &dc->n_spill};
         if (plan->params.list_cap > 0)  // testing: generic kernel with a tiny on-chip list
-            launch_phase2(plan->R, plan->Ts, plan->P, lo, hi, plan->rev_off.as<uint32_t>(), plan->rev.as<RevEntry>(),
-                          list_cap, out, s, plan->cfg);
+            launch_phase2(plan->R, plan->Ts, plan->P, lo, hi, rows, list_cap, out, s, plan->cfg);
         else
-            launch_phase2_tpr(plan->R, plan->Ts, plan->P, plan->stats.max_len, lo, hi, plan->rev_off.as<uint32_t>(),
-                              plan->rev.as<RevEntry>(), out, plan->params.flags & ALGA_PS_FORCE_GENERIC, s,
-                              plan->cfg);
+            launch_phase2_tpr(plan->R, plan->Ts, plan->P, plan->stats.max_len, lo, hi, rows, out,
+                              plan->params.flags & ALGA_PS_FORCE_GENERIC, s, plan->cfg);
         CK(cudaGetLastError());
         CKR(read_counters(plan, s));
         const uint32_t n_spill = plan->h_counters->n_spill;
@@ -281,8 +285,8 @@ int run_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, uint32_t *outdeg, c
             CKR(plan->caps.ensure((size_t) n_spill * 4));
             CKR(plan->spill_off.ensure(((size_t) n_spill + 1) * 8));
             CKR(plan->scan_ws.ensure(scan_workspace_bytes(n_spill)));
-            launch_phase2_count(plan->R, plan->Ts, plan->P, lo, plan->rev_off.as<uint32_t>(),
-                                plan->spill_queue.as<uint32_t>(), n_spill, plan->caps.as<uint32_t>(), s, plan->cfg);
+            launch_phase2_count(plan->R, plan->Ts, plan->P, lo, rows, plan->spill_queue.as<uint32_t>(), n_spill,
+                                plan->caps.as<uint32_t>(), s, plan->cfg);
             launch_scan_u64(plan->caps.as<uint32_t>(), plan->spill_off.as<uint64_t>(), n_spill, plan->scan_ws.p, s,
                             plan->cfg);
             CK(cudaGetLastError());
@@ -290,9 +294,8 @@ int run_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, uint32_t *outdeg, c
             CK(cudaStreamSynchronize(s));
             const uint64_t total = *plan->h_u64;
             CKR(plan->spill_store.ensure((size_t) total * 12 + 16));
-            launch_phase2_spill(plan->R, plan->Ts, plan->P, lo, plan->rev_off.as<uint32_t>(), plan->rev.as<RevEntry>(),
-                                plan->spill_queue.as<uint32_t>(), n_spill, plan->spill_off.as<uint64_t>(),
-                                plan->spill_store.as<uint32_t>(), out, s, plan->cfg);
+            launch_phase2_spill(plan->R, plan->Ts, plan->P, lo, rows, plan->spill_queue.as<uint32_t>(), n_spill,
+                                plan->spill_off.as<uint64_t>(), plan->spill_store.as<uint32_t>(), out, s, plan->cfg);
             CK(cudaGetLastError());
             CKR(read_counters(plan, s));
         }
@@ -383,6 +386,10 @@ int alga_ps_plan_create(alga_ps_plan **out, const alga_ps_params *params) {
     if (!plan) return fail(ALGA_E_NOMEM, "out of host memory");
     plan->params = *params;
     plan->cfg.launches = &plan->launches;
+    if (const char *e = getenv("ALGA_PS_ROW_CAP")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 32) plan->row_cap = (uint32_t) v;
+    }
     int r = [&]() -> int {
         CK(cudaSetDevice(params->device));
         int sm = 0;
@@ -477,26 +484,24 @@ int alga_ps_stage_phase1(alga_ps_plan *plan, uint32_t lo, uint32_t hi, void *str
     CKR(use_device(plan));
     cudaStream_t s = (cudaStream_t) stream;
     const uint32_t n = hi - lo;
-    CKR(plan->fwd.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * sizeof(int2)));
-    CKR(plan->fwd_t.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * 8));
+    const size_t max_edges = (size_t) (n ? n : 1) * kSmallEdgesKept;
+    CKR(plan->list1.ensure(max_edges * sizeof(Edge1)));
     CKR(plan->hard1.ensure((size_t) (n ? n : 1) * 4));
-    CKR(plan->triples1.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * 12));
+    CKR(plan->triples1.ensure(max_edges * 12));
     Counters *dc = plan->counters_d.as<Counters>();
     CK(cudaMemsetAsync(&dc->n_hard1, 0, 4, s));
-    CKR(plan->fwd_pos.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * 4));
+    CK(cudaMemsetAsync(&dc->n_list, 0, 4, s));
     const int force = plan->params.flags & ALGA_PS_FORCE_GENERIC;
-    launch_phase1_tpr(plan->R, plan->Tp, plan->P, plan->stats.max_len, lo, hi, plan->fwd.as<int2>(),
-                      plan->fwd_t.as<uint64_t>(), plan->fwd_pos.as<uint32_t>(), nullptr, plan->hard1.as<uint32_t>(),
+    Phase1Out p1{1, nullptr, nullptr, 0, plan->list1.as<Edge1>(), &dc->n_list, (uint32_t) max_edges};
+    launch_phase1_tpr(plan->R, plan->Tp, plan->P, plan->stats.max_len, lo, hi, p1, plan->hard1.as<uint32_t>(),
                       &dc->n_hard1, force, s, plan->cfg);
-    launch_phase1_queue(plan->R, plan->Tp, plan->P, lo, force ? n : (n < 4096 ? n : 4096), plan->hard1.as<uint32_t>(),
-                        &dc->n_hard1, plan->fwd.as<int2>(), plan->fwd_t.as<uint64_t>(), plan->fwd_pos.as<uint32_t>(),
-                        nullptr, s, plan->cfg);
-    CK(cudaMemsetAsync(&dc->n_triples, 0, 8, s));
-    launch_compact_slots(plan->fwd.as<int2>(), lo, hi, plan->triples1.as<int32_t>(), &dc->n_triples, s, plan->cfg);
+    launch_phase1_queue(plan->R, plan->Tp, plan->P, force ? n : (n < 4096 ? n : 4096), plan->hard1.as<uint32_t>(),
+                        &dc->n_hard1, p1, s, plan->cfg);
+    launch_edges_to_triples(plan->list1.as<Edge1>(), &dc->n_list, max_edges, plan->triples1.as<int32_t>(), s, plan->cfg);
     CK(cudaGetLastError());
     CKR(read_counters(plan, s));
     *dev_triples = plan->triples1.as<int32_t>();
-    *n_triples = plan->h_counters->n_triples;
+    *n_triples = plan->h_counters->n_list;
     return ALGA_OK;
 }
 
@@ -517,7 +522,8 @@ int alga_ps_stage_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int
     launch_scatter_rev_triples(plan->R, tin, n_in, lo, hi, plan->rev_off.as<uint32_t>(), plan->indeg.as<uint32_t>(),
                                plan->rev.as<RevEntry>(), s, plan->cfg);
     CK(cudaGetLastError());
-    CKR(run_phase2(plan, lo, hi, nullptr, s));
+    const RowsView view{nullptr, nullptr, 0, nullptr, nullptr, plan->rev_off.as<uint32_t>(), plan->rev.as<RevEntry>()};
+    CKR(run_phase2(plan, lo, hi, view, nullptr, s));
     *dev_triples_out = plan->triples.as<int32_t>();
     *n_out = plan->h_counters->n_edges;
     return ALGA_OK;
@@ -539,41 +545,56 @@ int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
     CKR(use_device(plan));
     cudaStream_t s = (cudaStream_t) stream;
     const uint32_t n = plan->R.n;
+    if ((uint64_t) n * kSmallEdgesKept > 0xFFFFFFFFull) return fail(ALGA_E_INVALID, "too many reads for one GPU (%u)", n);
     plan->launches = 0;
     plan->spilled = 0;
-    CK(cudaEventRecord(plan->ev0, s));
-    CKR(stage_index(plan, s));
-    CK(cudaEventRecord(plan->ev_stage[0], s));
-    // phase 1 with fused in-degree counting
-    CKR(plan->fwd.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * sizeof(int2)));
-    CKR(plan->fwd_t.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * 8));
-    CKR(plan->hard1.ensure((size_t) (n ? n : 1) * 4));
-    CKR(plan->indeg.ensure((size_t) (n ? n : 1) * 4));
-    CK(cudaMemsetAsync(plan->indeg.p, 0, (size_t) (n ? n : 1) * 4, s));
-    CK(cudaMemsetAsync(&plan->counters_d.as<Counters>()->n_hard1, 0, 4, s));
-    CKR(plan->fwd_pos.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * 4));
     const int force = plan->params.flags & ALGA_PS_FORCE_GENERIC;
-    launch_phase1_tpr(plan->R, plan->Tp, plan->P, plan->stats.max_len, 0, n, plan->fwd.as<int2>(),
-                      plan->fwd_t.as<uint64_t>(), plan->fwd_pos.as<uint32_t>(), plan->indeg.as<uint32_t>(),
-                      plan->hard1.as<uint32_t>(), &plan->counters_d.as<Counters>()->n_hard1, force, s, plan->cfg);
-    launch_phase1_queue(plan->R, plan->Tp, plan->P, 0, force ? n : (n < 4096 ? n : 4096), plan->hard1.as<uint32_t>(),
-                        &plan->counters_d.as<Counters>()->n_hard1, plan->fwd.as<int2>(), plan->fwd_t.as<uint64_t>(),
-                        plan->fwd_pos.as<uint32_t>(), plan->indeg.as<uint32_t>(), s, plan->cfg);
-    CK(cudaEventRecord(plan->ev_stage[1], s));
-    // reversed phase-1 graph (rows by target)
-    CKR(build_rev_from_counts(plan, n, s));
-    CKR(plan->rev.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * sizeof(RevEntry)));
-    launch_scatter_rev_slots(plan->fwd.as<int2>(), plan->fwd_t.as<uint64_t>(), plan->fwd_pos.as<uint32_t>(), 0, n, 0, n,
-                             plan->rev_off.as<uint32_t>(), plan->rev.as<RevEntry>(), s, plan->cfg);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(plan->ev_stage[2], s));
-    // phase 2 with fused out-degree counting (not in the reversed-result corner)
-    CKR(plan->outdeg.ensure((size_t) (n ? n : 1) * 4));
-    const bool fuse_outdeg = !plan->swap_direction;
-    CKR(run_phase2(plan, 0, n, fuse_outdeg ? plan->outdeg.as<uint32_t>() : nullptr, s));
-    CK(cudaEventRecord(plan->ev_stage[3], s));
-    CKR(stage_csr(plan, 0, n, plan->triples.as<int32_t>(), plan->h_counters->n_edges, plan->swap_direction ? 1 : 0,
-                  fuse_outdeg, s));
+    Counters *dc = plan->counters_d.as<Counters>();
+    if (plan->over_cap < kOverScanMax) plan->over_cap = n / 8 + 65536;
+    for (int attempt = 0;; attempt++) {
+        CK(cudaEventRecord(plan->ev0, s));
+        CKR(stage_index(plan, s));
+        CK(cudaEventRecord(plan->ev_stage[0], s));
+        // phase 1 writes every edge straight into the row of its target read (transposed graph, plan->row_cap per target)
+        CKR(plan->rows.ensure((size_t) (n ? n : 1) * plan->row_cap * sizeof(RevEntry)));
+        CKR(plan->over.ensure((size_t) plan->over_cap * sizeof(Edge1)));
+        CKR(plan->hard1.ensure((size_t) (n ? n : 1) * 4));
+        CKR(plan->indeg.ensure((size_t) (n ? n : 1) * 4));
+        CKR(plan->rev_off.ensure(((size_t) n + 1) * 4));
+        CKR(plan->rev.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * sizeof(RevEntry)));
+        CKR(plan->scan_ws.ensure(scan_workspace_bytes(n)));
+        CK(cudaMemsetAsync(plan->indeg.p, 0, (size_t) (n ? n : 1) * 4, s));
+        CK(cudaMemsetAsync(&dc->n_list, 0, 12, s));  // n_list, n_over, n_spill
+        CK(cudaMemsetAsync(&dc->n_hard1, 0, 4, s));
+        Phase1Out p1{0, plan->indeg.as<uint32_t>(), plan->rows.as<RevEntry>(), plan->row_cap, plan->over.as<Edge1>(), &dc->n_over,
+                     plan->over_cap};
+        launch_phase1_tpr(plan->R, plan->Tp, plan->P, plan->stats.max_len, 0, n, p1, plan->hard1.as<uint32_t>(), &dc->n_hard1,
+                          force, s, plan->cfg);
+        launch_phase1_queue(plan->R, plan->Tp, plan->P, force ? n : (n < 4096 ? n : 4096), plan->hard1.as<uint32_t>(),
+                            &dc->n_hard1, p1, s, plan->cfg);
+        CK(cudaEventRecord(plan->ev_stage[1], s));
+        // only when a row overflowed (decided on the device): CSR form of the transposed graph
+        launch_rebuild_rows_csr(&dc->n_over, plan->over_cap, plan->over.as<Edge1>(), plan->indeg.as<uint32_t>(),
+                                plan->rows.as<RevEntry>(), plan->row_cap, n, plan->rev_off.as<uint32_t>(), plan->rev.as<RevEntry>(),
+                                plan->scan_ws.p, s, plan->cfg);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(plan->ev_stage[2], s));
+        // phase 2 with fused out-degree counting (not in the reversed-result corner)
+        CKR(plan->outdeg.ensure((size_t) (n ? n : 1) * 4));
+        const bool fuse_outdeg = !plan->swap_direction;
+        const RowsView view{plan->indeg.as<uint32_t>(), plan->rows.as<RevEntry>(), plan->row_cap, &dc->n_over,
+                            plan->over.as<Edge1>(), plan->rev_off.as<uint32_t>(), plan->rev.as<RevEntry>()};
+        CKR(run_phase2(plan, 0, n, view, fuse_outdeg ? plan->outdeg.as<uint32_t>() : nullptr, s));
+        if (plan->h_counters->n_over > plan->over_cap) {  // the overflow list itself overflowed: size it for the worst case
+            if (attempt) return fail(ALGA_E_CAPACITY, "phase-1 overflow list overflow persisted");
+            plan->over_cap = n * (uint32_t) kSmallEdgesKept;
+            continue;
+        }
+        CK(cudaEventRecord(plan->ev_stage[3], s));
+        CKR(stage_csr(plan, 0, n, plan->triples.as<int32_t>(), plan->h_counters->n_edges, plan->swap_direction ? 1 : 0,
+                      fuse_outdeg, s));
+        break;
+    }
     CK(cudaEventRecord(plan->ev1, s));
     CK(cudaEventSynchronize(plan->ev1));
     float ms = 0;
@@ -584,6 +605,8 @@ int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
         CK(cudaEventElapsedTime(&ms, marks[k], marks[k + 1]));
         plan->stage_ms[k] = ms;
     }
+    plan->stage_ms[5] = plan->h_counters->n_over;   // diagnostics: phase-1 edges beyond their row's capacity,
+    plan->stage_ms[6] = plan->h_counters->n_hard1;  // source reads that took the generic phase-1 kernel
     return ALGA_OK;
 }
 

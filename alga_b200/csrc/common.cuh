@@ -49,6 +49,71 @@ struct __align__(16) RevEntry {
     uint64_t t;
 };
 
+// One phase-1 edge in list form (sharded runs, overflow of the fixed-capacity rows): b -> c at offset o with b's tail.
+struct __align__(8) Edge1 {
+    int32_t c, b, o, pad;
+    uint64_t t;
+};
+
+// Where phase 1 puts its edges (GraphCreatorPrefSuf.cpp:397-402 pushes to G[b]; phase 2 needs them by target c):
+//   mode 0: straight into the row of the target read in the transposed graph -- `row_cap` entries per target,
+//           position = atomicAdd(indeg[c]); entries beyond the capacity go to `list` (then *n_list != 0 and the
+//           rows are rebuilt in CSR form before phase 2);
+//   mode 1: appended to `list` (one warp-aggregated atomicAdd per warp).
+struct Phase1Out {
+    int mode;
+    uint32_t *indeg;
+    RevEntry *rows;
+    uint32_t row_cap;
+    Edge1 *list;
+    uint32_t *n_list;
+    uint32_t list_cap;
+};
+
+// one edge, one thread (generic kernels; the fast kernel aggregates its list appends per warp)
+__device__ __forceinline__ void emit_edge1(const Phase1Out &out, uint32_t b, uint32_t c, uint32_t o, uint64_t t) {
+    if (out.mode == 0) {
+        const uint32_t pos = atomicAdd(out.indeg + c, 1u);
+        if (pos < out.row_cap) {
+            RevEntry r;
+            r.b = (int32_t) b, r.o = (int32_t) o, r.t = t;
+            out.rows[(uint64_t) c * out.row_cap + pos] = r;
+            return;
+        }
+    }
+    const uint32_t i = atomicAdd(out.n_list, 1u);
+    if (i < out.list_cap) {
+        Edge1 x;
+        x.c = (int32_t) c, x.b = (int32_t) b, x.o = (int32_t) o, x.pad = 0, x.t = t;
+        out.list[i] = x;
+    }
+}
+
+// Rows of the transposed phase-1 graph as phase 2 reads them.  Fixed-capacity form: row i holds its first `cap`
+// entries, indeg[i] is its full size, the few entries beyond the capacity sit in the overflow list `over` (targets
+// with indeg > cap take the generic kernels, which pick their entries out of that list).  When cap == 0 or the
+// overflow list is longer than kOverScanMax the CSR form (rev_off, rev) is authoritative.  Indexed by c - lo.
+constexpr uint32_t kOverScanMax = 2048;
+struct RowsView {
+    const uint32_t *indeg;
+    const RevEntry *rows;
+    uint32_t cap;
+    const uint32_t *n_over;
+    const Edge1 *over;
+    const uint32_t *rev_off;
+    const RevEntry *rev;
+};
+__device__ __forceinline__ bool rows_are_csr(const RowsView &v) { return v.cap == 0 || *v.n_over > kOverScanMax; }
+__device__ __forceinline__ const RevEntry *get_row(const RowsView &v, bool csr, uint32_t i, uint32_t &deg) {
+    if (csr) {
+        const uint32_t r0 = v.rev_off[i];
+        deg = v.rev_off[i + 1] - r0;
+        return v.rev + r0;
+    }
+    deg = v.indeg[i];
+    return v.rows + (uint64_t) i * v.cap;
+}
+
 // Seed index: open addressing, one 32-byte sector per bucket, 8 entries of (tag << id_bits) | read id.  The tag
 // takes whatever bits the read id leaves free (10 bits for 4 M reads, 5 for 128 M); a false tag hit only costs an
 // exact compare.  Buckets are sized for a mean occupancy of 2 of 8, so a probe almost never leaves its first sector.
@@ -124,20 +189,17 @@ __device__ __forceinline__ bool equal_bits_head(const uint32_t (&a)[4], uint32_t
     return diff == 0;
 }
 
-// Hash of the 2K-bit seed window: multiply-add of the two 32-bit halves, one xor-fold, one multiply.  The top bits
-// pick the bucket, the low 32 bits are the tag; a false tag hit only costs one exact compare.
+// Hash of the 2K-bit seed window: pair-multiply-shift over its two 32-bit halves (four IMADs).  The high word picks
+// the bucket, the top bits of the low word are the tag; a false tag hit only costs one exact compare.
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
-    uint64_t h = (uint64_t) (uint32_t) x * 0x9E3779B97F4A7C15ull + (x >> 32) * 0xC2B2AE3D27D4EB4Full;
-    h ^= h >> 32;
-    h *= 0xD6E8FEB86659FD93ull;
-    return h;
+    return (uint64_t) (uint32_t) x * 0x9E3779B97F4A7C15ull + (x >> 32) * 0xC2B2AE3D27D4EB4Full;
 }
 __device__ __forceinline__ uint32_t bucket_of(uint64_t h, uint32_t n_buckets) {
     return __umulhi((uint32_t) (h >> 32), n_buckets);
 }
-// tag already shifted into entry position
+// tag already shifted into entry position (the bits of an entry above the read id)
 __device__ __forceinline__ uint32_t tag_of(const SeedTable &t, uint64_t h) {
-    uint32_t tag = (uint32_t) h & t.tag_mask;
+    uint32_t tag = (uint32_t) h >> t.id_bits;
     if (tag == t.tag_mask) tag = 0;
     return tag << t.id_bits;
 }

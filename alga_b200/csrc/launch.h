@@ -27,28 +27,28 @@ void launch_build_index(const ReadsDev &R, const PsDev &P, SeedTable prefix, See
                         const LaunchCfg &cfg);
 
 // --- phase 1: L in [lmin, min(rs-1, max_l)], keeps the 3 largest (L, c) per source read ----------
-// fwd: 3 slots per b in [lo,hi): (c, offset), c = -1 when empty; fwd_t: overhang tail of every filled slot (the last
-// min(offset, 32) nucleotides of b[0 .. offset), top-aligned); indeg (nullable): += 1 per target c, and fwd_pos
-// receives the value the counter had (= position of the entry in c's transposed row).
+// Edges go where `out` says (common.cuh: rows of the transposed graph, or an edge list), each with its overhang tail
+// (the last min(offset, 32) nucleotides of b[0 .. offset), top-aligned).
 // Thread-per-read fast kernel (tpr_kernels.cu); reads it cannot take are appended to hard_queue (*n_hard must be 0).
 void launch_phase1_tpr(const ReadsDev &R, const SeedTable &prefix, const PsDev &P, uint32_t max_len_nt, uint32_t lo,
-                       uint32_t hi, int2 *fwd, uint64_t *fwd_t, uint32_t *fwd_pos, uint32_t *indeg, uint32_t *hard_queue,
-                       uint32_t *n_hard, int force_hard, cudaStream_t s, const LaunchCfg &cfg);
+                       uint32_t hi, const Phase1Out &out, uint32_t *hard_queue, uint32_t *n_hard, int force_hard,
+                       cudaStream_t s, const LaunchCfg &cfg);
 // generic kernel over the queue (n_max = upper bound of the queue length, used for the grid only)
-void launch_phase1_queue(const ReadsDev &R, const SeedTable &prefix, const PsDev &P, uint32_t lo, uint32_t n_max,
-                         const uint32_t *hard_queue, const uint32_t *n_hard, int2 *fwd, uint64_t *fwd_t, uint32_t *fwd_pos,
-                         uint32_t *indeg, cudaStream_t s, const LaunchCfg &cfg);
-// compact the slots of [lo,hi) into (b, c, o) triples; *d_count must be zero on entry
-void launch_compact_slots(const int2 *fwd, uint32_t lo, uint32_t hi, int32_t *triples,
-                          unsigned long long *d_count, cudaStream_t s, const LaunchCfg &cfg);
+void launch_phase1_queue(const ReadsDev &R, const SeedTable &prefix, const PsDev &P, uint32_t n_max,
+                         const uint32_t *hard_queue, const uint32_t *n_hard, const Phase1Out &out, cudaStream_t s,
+                         const LaunchCfg &cfg);
+// edge list -> (b, c, o) triples; the list length is read on the device, n_max bounds the grid
+void launch_edges_to_triples(const Edge1 *list, const uint32_t *n_list, uint64_t n_max, int32_t *triples, cudaStream_t s,
+                             const LaunchCfg &cfg);
+// only if *n_over > kOverScanMax (tested on the device): CSR form of the transposed graph from fixed rows + overflow list
+void launch_rebuild_rows_csr(const uint32_t *n_over, uint32_t over_cap, const Edge1 *over, uint32_t *indeg,
+                             const RevEntry *rows, uint32_t cap, uint32_t n_targets, uint32_t *rev_off, RevEntry *rev,
+                             void *scan_ws, cudaStream_t s, const LaunchCfg &cfg);
 
-// --- reversed phase-1 adjacency (rows by target c in [lo,hi)) -------------------------------------
+// --- reversed phase-1 adjacency from exchanged triples (rows by target c in [lo,hi)) ---------------
 // counts -> offsets is done with launch_scan; scatter consumes `cursor` (a copy of the counts).
 void launch_count_targets(const int32_t *triples, uint64_t n, uint32_t lo, uint32_t hi, uint32_t *indeg,
                           cudaStream_t s, const LaunchCfg &cfg);
-void launch_scatter_rev_slots(const int2 *fwd, const uint64_t *fwd_t, const uint32_t *fwd_pos, uint32_t b_lo,
-                              uint32_t b_hi, uint32_t c_lo, uint32_t c_hi, const uint32_t *rev_off, RevEntry *rev,
-                              cudaStream_t s, const LaunchCfg &cfg);
 void launch_scatter_rev_triples(const ReadsDev &R, const int32_t *triples, uint64_t n, uint32_t c_lo, uint32_t c_hi,
                                 const uint32_t *rev_off, uint32_t *cursor, RevEntry *rev, cudaStream_t s,
                                 const LaunchCfg &cfg);
@@ -64,20 +64,18 @@ struct Phase2Out {
 };
 // thread-per-target fast kernel (tpr_kernels.cu); everything it cannot take goes to out.spill_queue
 void launch_phase2_tpr(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t max_len_nt, uint32_t lo,
-                       uint32_t hi, const uint32_t *rev_off, const RevEntry *rev, const Phase2Out &out, int force_hard,
-                       cudaStream_t s, const LaunchCfg &cfg);
+                       uint32_t hi, const RowsView &rows, const Phase2Out &out, int force_hard, cudaStream_t s,
+                       const LaunchCfg &cfg);
 // generic path: sequential replay on a shared-memory list of list_cap entries per target (spills beyond it)
 void launch_phase2(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo, uint32_t hi,
-                   const uint32_t *rev_off, const RevEntry *rev, int list_cap, const Phase2Out &out, cudaStream_t s,
-                   const LaunchCfg &cfg);
+                   const RowsView &rows, int list_cap, const Phase2Out &out, cudaStream_t s, const LaunchCfg &cfg);
 // spill path: per queued target count row size + hits -> caps (u32), then replay with global lists
-void launch_phase2_count(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo,
-                         const uint32_t *rev_off, const uint32_t *queue, uint32_t n_queue, uint32_t *caps,
-                         cudaStream_t s, const LaunchCfg &cfg);
-void launch_phase2_spill(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo,
-                         const uint32_t *rev_off, const RevEntry *rev, const uint32_t *queue, uint32_t n_queue,
-                         const uint64_t *spill_off, uint32_t *spill_store, const Phase2Out &out, cudaStream_t s,
+void launch_phase2_count(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo, const RowsView &rows,
+                         const uint32_t *queue, uint32_t n_queue, uint32_t *caps, cudaStream_t s,
                          const LaunchCfg &cfg);
+void launch_phase2_spill(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo, const RowsView &rows,
+                         const uint32_t *queue, uint32_t n_queue, const uint64_t *spill_off, uint32_t *spill_store,
+                         const Phase2Out &out, cudaStream_t s, const LaunchCfg &cfg);
 
 // --- CSR assembly -----------------------------------------------------------------------------
 void launch_count_sources(const int32_t *triples, uint64_t n, uint32_t lo, uint32_t hi, int swap, uint32_t *outdeg,
@@ -94,7 +92,7 @@ void launch_sort_big_rows(const uint64_t *row_off, const uint32_t *big_rows, uin
 // --- exclusive scan of u32 counts into u32 / u64 offsets (n+1 outputs, out[n] = total) ---------------
 size_t scan_workspace_bytes(uint64_t n);
 void launch_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, void *workspace, cudaStream_t s,
-                     const LaunchCfg &cfg);
+                     const LaunchCfg &cfg, const uint32_t *run_if = nullptr);  // run_if: device counter, <= kOverScanMax = skip
 void launch_scan_u64(const uint32_t *in, uint64_t *out, uint64_t n, void *workspace, cudaStream_t s,
                      const LaunchCfg &cfg);
 

@@ -79,9 +79,7 @@ __global__ void build_index_kernel(ReadsDev R, PsDev P, SeedTable tp, SeedTable 
 // Phase 1, generic path.  Canonical order of the reference pushes is (L asc, c asc) and only the last 3 survive,
 // so the result is the 3 largest (L, c): scan L downwards 32 lengths at a time and stop at 3 hits.
 __device__ __forceinline__ void phase1_generic_read(const ReadsDev &R, const SeedTable &T, const PsDev &P, uint32_t b,
-                                                    int2 *__restrict__ slots, uint64_t *__restrict__ slots_t,
-                                                    uint32_t *__restrict__ slots_pos, uint32_t *__restrict__ indeg,
-                                                    int lane) {
+                                                    const Phase1Out &out, int lane) {
     const uint32_t lenb = R.len[b];
     int32_t rc[kSmallEdgesKept], ro[kSmallEdgesKept];
 #pragma unroll
@@ -136,48 +134,61 @@ __device__ __forceinline__ void phase1_generic_read(const ReadsDev &R, const See
 #pragma unroll
         for (int q = 0; q < kSmallEdgesKept; q++)
             if (q == lane) c = rc[q], o = ro[q];
-        slots[lane] = make_int2(c, o);
-        if (c >= 0) {
-            slots_t[lane] = overhang_tail(pb, (uint32_t) o);
-            if (indeg) slots_pos[lane] = atomicAdd(indeg + c, 1u);  // position inside the target's transposed row
-        }
+        if (c >= 0) emit_edge1(out, b, (uint32_t) c, (uint32_t) o, overhang_tail(pb, (uint32_t) o));
     }
 }
 
 // generic phase 1 over a queue of source reads (the reads the fast kernel handed back)
 __global__ void __launch_bounds__(kThreads)
-phase1_queue_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, const uint32_t *__restrict__ queue,
-                    const uint32_t *__restrict__ n_queue, int2 *__restrict__ fwd, uint64_t *__restrict__ fwd_t,
-                    uint32_t *__restrict__ fwd_pos, uint32_t *__restrict__ indeg) {
+phase1_queue_kernel(ReadsDev R, SeedTable T, PsDev P, const uint32_t *__restrict__ queue,
+                    const uint32_t *__restrict__ n_queue, Phase1Out out) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const uint32_t n_warps = gridDim.x * kWarpsPerBlock;
     const uint32_t n = *n_queue;
     for (uint32_t q = warp; q < n; q += n_warps) {
-        const uint32_t b = queue[q];
-        const uint64_t s0 = (uint64_t) (b - lo) * kSmallEdgesKept;
-        phase1_generic_read(R, T, P, b, fwd + s0, fwd_t + s0, fwd_pos + s0, indeg, lane);
+        phase1_generic_read(R, T, P, queue[q], out, lane);
     }
 }
 
-__global__ void compact_slots_kernel(const int2 *__restrict__ fwd, uint32_t lo, uint64_t n_slots,
-                                     int32_t *__restrict__ triples, unsigned long long *count) {
-    const int lane = threadIdx.x & 31;
-    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
-    const uint64_t n_round = (n_slots + 31) & ~31ull;
-    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        int2 e = make_int2(-1, 0);
-        if (i < n_slots) e = fwd[i];
-        const unsigned m = __ballot_sync(kFull, e.x >= 0);
-        unsigned long long base = 0;
-        if (lane == 0 && m) base = atomicAdd(count, (unsigned long long) __popc(m));
-        base = __shfl_sync(kFull, base, 0);
-        if (e.x >= 0) {
-            const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
-            triples[3 * pos] = (int32_t) (lo + i / kSmallEdgesKept);
-            triples[3 * pos + 1] = e.x;
-            triples[3 * pos + 2] = e.y;
-        }
+// phase-1 edge list -> (b, c, o) triples (staged interface)
+__global__ void edges_to_triples_kernel(const Edge1 *__restrict__ list, const uint32_t *__restrict__ n_list,
+                                        int32_t *__restrict__ triples) {
+    const uint64_t n = *n_list;
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const Edge1 e = list[i];
+        triples[3 * i] = e.b;
+        triples[3 * i + 1] = e.c;
+        triples[3 * i + 2] = e.o;
+    }
+}
+
+// Many entries overflowed their fixed-capacity rows (*n_over > kOverScanMax): rebuild the transposed graph in CSR form.  rev_off = scan(indeg);
+// the first `cap` entries of every row come from the fixed rows, the rest from the overflow list, which takes its
+// positions by counting indeg[c] down from the row's full size.
+__global__ void rows_to_csr_kernel(const uint32_t *__restrict__ n_over, const uint32_t *__restrict__ indeg,
+                                   const RevEntry *__restrict__ rows, uint32_t cap, uint32_t n_targets,
+                                   const uint32_t *__restrict__ rev_off, RevEntry *__restrict__ rev) {
+    if (*n_over <= kOverScanMax) return;
+    const uint64_t total = (uint64_t) n_targets * cap;
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < total; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t) (i / cap), j = (uint32_t) (i - (uint64_t) c * cap);
+        if (j < indeg[c]) rev[rev_off[c] + j] = rows[i];
+    }
+}
+__global__ void over_to_csr_kernel(const uint32_t *__restrict__ n_over, uint32_t over_cap, const Edge1 *__restrict__ over,
+                                   uint32_t *indeg, const uint32_t *__restrict__ rev_off, RevEntry *__restrict__ rev) {
+    uint32_t n = *n_over;
+    if (n <= kOverScanMax) return;
+    if (n > over_cap) n = over_cap;  // the host notices the overflow of the overflow list and reruns
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const Edge1 e = over[i];
+        const uint32_t pos = rev_off[e.c] + atomicSub(indeg + e.c, 1u) - 1u;
+        RevEntry r;
+        r.b = e.b;
+        r.o = e.o;
+        r.t = e.t;
+        rev[pos] = r;
     }
 }
 
@@ -187,26 +198,6 @@ __global__ void count_targets_kernel(const int32_t *__restrict__ triples, uint64
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
         const uint32_t c = (uint32_t) triples[3 * i + 1];
         if (c >= lo && c < hi) atomicAdd(indeg + (c - lo), 1u);
-    }
-}
-
-// rows of the transposed phase-1 graph; the position of every entry inside its row was fixed by the atomicAdd
-// that counted it (fwd_pos), so the scatter itself needs no atomics
-__global__ void scatter_rev_slots_kernel(const int2 *__restrict__ fwd, const uint64_t *__restrict__ fwd_t,
-                                         const uint32_t *__restrict__ fwd_pos, uint32_t b_lo, uint64_t n_slots,
-                                         uint32_t c_lo, uint32_t c_hi, const uint32_t *__restrict__ rev_off,
-                                         RevEntry *__restrict__ rev) {
-    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t) gridDim.x * blockDim.x) {
-        const int2 e = fwd[i];
-        if (e.x < 0) continue;
-        const uint32_t c = (uint32_t) e.x;
-        if (c < c_lo || c >= c_hi) continue;
-        const uint32_t pos = rev_off[c - c_lo] + fwd_pos[i];
-        RevEntry r;
-        r.b = (int32_t) (b_lo + i / kSmallEdgesKept);
-        r.o = e.y;
-        r.t = fwd_t[i];
-        rev[pos] = r;
     }
 }
 
@@ -308,15 +299,38 @@ __device__ __forceinline__ bool replay_hit(const ReadsDev &R, uint32_t b, int32_
 
 // Load row c of the reversed phase-1 graph and apply Graph::retainOnlySmallestOffset (Graph.cpp:348-387):
 // one entry per source read, smallest offset wins.  Returns false when the row does not fit.
-__device__ __forceinline__ bool load_rev_row(const ReadsDev &R, const RevEntry *__restrict__ row, uint32_t deg,
+__device__ __forceinline__ bool load_rev_row(const ReadsDev &R, const RowsView &rows, bool csr, uint32_t ci, uint32_t c,
                                              NbrList &lst, uint32_t &cnt, int lane) {
     cnt = 0;
+    uint32_t deg;
+    const RevEntry *row = get_row(rows, csr, ci, deg);
     if (deg > lst.cap) return false;
-    for (uint32_t j = lane; j < deg; j += 32) {
+    const uint32_t in_row = (!csr && deg > rows.cap) ? rows.cap : deg;
+    for (uint32_t j = lane; j < in_row; j += 32) {
         const RevEntry e = row[j];
         lst.a[j] = (uint32_t) e.b;
         lst.o[j] = (uint32_t) e.o;
         lst.len[j] = 0;
+    }
+    if (in_row < deg) {  // the rest of this row is in the (short) overflow list
+        uint32_t w = in_row;
+        const uint32_t n_over = *rows.n_over;
+        for (uint32_t base = 0; base < n_over; base += 32) {
+            Edge1 e;
+            e.c = -1;
+            if (base + lane < n_over) e = rows.over[base + lane];
+            const bool mine = (uint32_t) e.c == c;
+            const unsigned m = __ballot_sync(kFull, mine);
+            if (mine) {
+                const uint32_t pos = w + __popc(m & ((1u << lane) - 1u));
+                if (pos < deg) {
+                    lst.a[pos] = (uint32_t) e.b;
+                    lst.o[pos] = (uint32_t) e.o;
+                    lst.len[pos] = 0;
+                }
+            }
+            w += __popc(m);
+        }
     }
     __syncwarp();
     if (deg > 1) {
@@ -359,10 +373,10 @@ __device__ __forceinline__ bool load_rev_row(const ReadsDev &R, const RevEntry *
 
 // All of phase 2 for one target read c on one warp.  Returns false when the list overflowed.
 __device__ __forceinline__ bool phase2_target(const ReadsDev &R, const SeedTable &T, const PsDev &P, uint32_t c,
-                                              const RevEntry *__restrict__ row, uint32_t deg, NbrList &lst,
+                                              const RowsView &rows, bool csr, uint32_t ci, NbrList &lst,
                                               const Phase2Out &out, int lane) {
     uint32_t cnt = 0;
-    if (!load_rev_row(R, row, deg, lst, cnt, lane)) return false;
+    if (!load_rev_row(R, rows, csr, ci, c, lst, cnt, lane)) return false;
     const uint32_t lenc = R.len[c];
     const int32_t l_lo = P.rs > P.lmin ? P.rs : P.lmin;
     int64_t l_hi = lenc;
@@ -417,8 +431,7 @@ __device__ __forceinline__ bool phase2_target(const ReadsDev &R, const SeedTable
 }
 
 __global__ void __launch_bounds__(kThreads)
-phase2_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, const uint32_t *__restrict__ rev_off,
-              const RevEntry *__restrict__ rev, int list_cap, Phase2Out out) {
+phase2_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, RowsView rows, int list_cap, Phase2Out out) {
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -429,10 +442,10 @@ phase2_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, const 
     lst.cap = (uint32_t) list_cap;
     const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib;
     const uint32_t n_warps = gridDim.x * kWarpsPerBlock;
+    const bool csr = rows_are_csr(rows);
     for (uint64_t cc = (uint64_t) lo + warp; cc < hi; cc += n_warps) {
         const uint32_t c = (uint32_t) cc;
-        const uint32_t r0 = rev_off[c - lo], r1 = rev_off[c - lo + 1];
-        if (!phase2_target(R, T, P, c, rev + r0, r1 - r0, lst, out, lane)) {
+        if (!phase2_target(R, T, P, c, rows, csr, c - lo, lst, out, lane)) {
             if (lane == 0) out.spill_queue[atomicAdd(out.n_spill, 1u)] = c;
         }
         __syncwarp();
@@ -441,8 +454,8 @@ phase2_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, const 
 
 // spill path, pass 1: upper bound of the list length of each queued target = row size + accepted overlaps
 __global__ void __launch_bounds__(kThreads)
-phase2_count_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, const uint32_t *__restrict__ rev_off,
-                    const uint32_t *__restrict__ queue, uint32_t n_queue, uint32_t *__restrict__ caps) {
+phase2_count_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, RowsView rows, const uint32_t *__restrict__ queue,
+                    uint32_t n_queue, uint32_t *__restrict__ caps) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const uint32_t n_warps = gridDim.x * kWarpsPerBlock;
@@ -462,15 +475,18 @@ phase2_count_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, const uint32_
             }
         }
         for (int d = 16; d; d >>= 1) total += __shfl_xor_sync(kFull, total, d);
-        if (lane == 0) caps[q] = total + (rev_off[c - lo + 1] - rev_off[c - lo]) + 1u;
+        if (lane == 0) {
+            uint32_t deg;
+            get_row(rows, rows_are_csr(rows), c - lo, deg);
+            caps[q] = total + deg + 1u;
+        }
     }
 }
 
 // spill path, pass 2: same replay with the list in global memory (capacity from pass 1)
 __global__ void __launch_bounds__(kThreads)
-phase2_spill_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, const uint32_t *__restrict__ rev_off,
-                    const RevEntry *__restrict__ rev, const uint32_t *__restrict__ queue, uint32_t n_queue,
-                    const uint64_t *__restrict__ spill_off, uint32_t *spill_store, Phase2Out out) {
+phase2_spill_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, RowsView rows, const uint32_t *__restrict__ queue,
+                    uint32_t n_queue, const uint64_t *__restrict__ spill_off, uint32_t *spill_store, Phase2Out out) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const uint32_t n_warps = gridDim.x * kWarpsPerBlock;
@@ -482,8 +498,7 @@ phase2_spill_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, const uint32_
         lst.a = spill_store + 3 * s0;
         lst.o = lst.a + lst.cap;
         lst.len = lst.o + lst.cap;
-        const uint32_t r0 = rev_off[c - lo], r1 = rev_off[c - lo + 1];
-        phase2_target(R, T, P, c, rev + r0, r1 - r0, lst, out, lane);
+        phase2_target(R, T, P, c, rows, rows_are_csr(rows), c - lo, lst, out, lane);
         __syncwarp();
     }
 }
@@ -595,8 +610,10 @@ __device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t *t
 }
 
 __global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint32_t *__restrict__ in, uint64_t n,
-                                                                      uint64_t *__restrict__ tile_sums) {
+                                                                      uint64_t *__restrict__ tile_sums,
+                                                                      const uint32_t *__restrict__ run_if) {
     __shared__ uint64_t sh[33];
+    if (run_if && *run_if <= kOverScanMax) return;
     const uint64_t base = (uint64_t) blockIdx.x * kScanTile;
     uint64_t v = 0;
     for (int k = 0; k < kScanItems; k++) {
@@ -608,8 +625,10 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(uint64_t *tile_sums, uint64_t n_tiles) {
+__global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(uint64_t *tile_sums, uint64_t n_tiles,
+                                                                  const uint32_t *__restrict__ run_if) {
     __shared__ uint64_t sh[33];
+    if (run_if && *run_if <= kOverScanMax) return;
     uint64_t carry = 0;
     for (uint64_t base = 0; base < n_tiles; base += kScanThreads) {
         const uint64_t i = base + threadIdx.x;
@@ -625,8 +644,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(uint64_t *tile
 template <class OutT>
 __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t *__restrict__ in, OutT *__restrict__ out,
                                                                   uint64_t n, const uint64_t *__restrict__ tile_sums,
-                                                                  uint64_t n_tiles) {
+                                                                  uint64_t n_tiles, const uint32_t *__restrict__ run_if) {
     __shared__ uint64_t sh[33];
+    if (run_if && *run_if <= kOverScanMax) return;
     const uint64_t base = (uint64_t) blockIdx.x * kScanTile + (uint64_t) threadIdx.x * kScanItems;
     uint32_t item[kScanItems];
     uint64_t v = 0;
@@ -668,22 +688,33 @@ void launch_build_index(const ReadsDev &R, const PsDev &P, SeedTable prefix, See
     bump(cfg);
 }
 
-void launch_phase1_queue(const ReadsDev &R, const SeedTable &prefix, const PsDev &P, uint32_t lo, uint32_t n_max,
-                         const uint32_t *hard_queue, const uint32_t *n_hard, int2 *fwd, uint64_t *fwd_t, uint32_t *fwd_pos,
-                         uint32_t *indeg, cudaStream_t s, const LaunchCfg &cfg) {
+void launch_phase1_queue(const ReadsDev &R, const SeedTable &prefix, const PsDev &P, uint32_t n_max,
+                         const uint32_t *hard_queue, const uint32_t *n_hard, const Phase1Out &out, cudaStream_t s,
+                         const LaunchCfg &cfg) {
     if (!n_max) return;
     // the queue length lives on the device (no host round trip; usually zero): size the grid for a short queue
     // unless the caller knows that every read is in it
-    phase1_queue_kernel<<<grid_for(n_max, kWarpsPerBlock, cfg, 8), kThreads, 0, s>>>(R, prefix, P, lo, hard_queue, n_hard,
-                                                                                       fwd, fwd_t, fwd_pos, indeg);
+    phase1_queue_kernel<<<grid_for(n_max, kWarpsPerBlock, cfg, 8), kThreads, 0, s>>>(R, prefix, P, hard_queue, n_hard, out);
     bump(cfg);
 }
 
-void launch_compact_slots(const int2 *fwd, uint32_t lo, uint32_t hi, int32_t *triples, unsigned long long *d_count,
-                          cudaStream_t s, const LaunchCfg &cfg) {
-    if (hi <= lo) return;
-    const uint64_t n_slots = (uint64_t) (hi - lo) * kSmallEdgesKept;
-    compact_slots_kernel<<<grid_for(n_slots, 256, cfg), 256, 0, s>>>(fwd, lo, n_slots, triples, d_count);
+void launch_edges_to_triples(const Edge1 *list, const uint32_t *n_list, uint64_t n_max, int32_t *triples, cudaStream_t s,
+                             const LaunchCfg &cfg) {
+    if (!n_max) return;
+    edges_to_triples_kernel<<<grid_for(n_max, 256, cfg), 256, 0, s>>>(list, n_list, triples);
+    bump(cfg);
+}
+
+void launch_rebuild_rows_csr(const uint32_t *n_over, uint32_t over_cap, const Edge1 *over, uint32_t *indeg,
+                             const RevEntry *rows, uint32_t cap, uint32_t n_targets, uint32_t *rev_off, RevEntry *rev,
+                             void *scan_ws, cudaStream_t s, const LaunchCfg &cfg) {
+    if (!n_targets) return;
+    launch_scan_u32(indeg, rev_off, n_targets, scan_ws, s, cfg, n_over);
+    rows_to_csr_kernel<<<grid_for((uint64_t) n_targets * cap, 256, cfg), 256, 0, s>>>(n_over, indeg, rows, cap, n_targets,
+                                                                                       rev_off, rev);
+    over_to_csr_kernel<<<grid_for(over_cap < 65536 ? over_cap : 65536, 256, cfg), 256, 0, s>>>(n_over, over_cap, over, indeg,
+                                                                                                rev_off, rev);
+    bump(cfg);
     bump(cfg);
 }
 
@@ -691,16 +722,6 @@ void launch_count_targets(const int32_t *triples, uint64_t n, uint32_t lo, uint3
                           cudaStream_t s, const LaunchCfg &cfg) {
     if (!n) return;
     count_targets_kernel<<<grid_for(n, 256, cfg), 256, 0, s>>>(triples, n, lo, hi, indeg);
-    bump(cfg);
-}
-
-void launch_scatter_rev_slots(const int2 *fwd, const uint64_t *fwd_t, const uint32_t *fwd_pos, uint32_t b_lo,
-                              uint32_t b_hi, uint32_t c_lo, uint32_t c_hi, const uint32_t *rev_off, RevEntry *rev,
-                              cudaStream_t s, const LaunchCfg &cfg) {
-    if (b_hi <= b_lo) return;
-    const uint64_t n_slots = (uint64_t) (b_hi - b_lo) * kSmallEdgesKept;
-    scatter_rev_slots_kernel<<<grid_for(n_slots, 256, cfg), 256, 0, s>>>(fwd, fwd_t, fwd_pos, b_lo, n_slots, c_lo, c_hi,
-                                                                           rev_off, rev);
     bump(cfg);
 }
 
@@ -713,33 +734,31 @@ void launch_scatter_rev_triples(const ReadsDev &R, const int32_t *triples, uint6
 }
 
 void launch_phase2(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo, uint32_t hi,
-                   const uint32_t *rev_off, const RevEntry *rev, int list_cap, const Phase2Out &out, cudaStream_t s,
-                   const LaunchCfg &cfg) {
+                   const RowsView &rows, int list_cap, const Phase2Out &out, cudaStream_t s, const LaunchCfg &cfg) {
     if (hi <= lo) return;
     const size_t smem = (size_t) kWarpsPerBlock * 3 * list_cap * sizeof(uint32_t);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    phase2_kernel<<<grid_for(hi - lo, kWarpsPerBlock, cfg, 8), kThreads, smem, s>>>(R, suffix, P, lo, hi, rev_off, rev,
-                                                                                      list_cap, out);
+    phase2_kernel<<<grid_for(hi - lo, kWarpsPerBlock, cfg, 8), kThreads, smem, s>>>(R, suffix, P, lo, hi, rows, list_cap,
+                                                                                      out);
     bump(cfg);
 }
 
-void launch_phase2_count(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo,
-                         const uint32_t *rev_off, const uint32_t *queue, uint32_t n_queue, uint32_t *caps,
-                         cudaStream_t s, const LaunchCfg &cfg) {
+void launch_phase2_count(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo, const RowsView &rows,
+                         const uint32_t *queue, uint32_t n_queue, uint32_t *caps, cudaStream_t s,
+                         const LaunchCfg &cfg) {
     if (!n_queue) return;
-    phase2_count_kernel<<<grid_for(n_queue, kWarpsPerBlock, cfg, 8), kThreads, 0, s>>>(R, suffix, P, lo, rev_off, queue,
+    phase2_count_kernel<<<grid_for(n_queue, kWarpsPerBlock, cfg, 8), kThreads, 0, s>>>(R, suffix, P, lo, rows, queue,
                                                                                          n_queue, caps);
     bump(cfg);
 }
 
-void launch_phase2_spill(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo,
-                         const uint32_t *rev_off, const RevEntry *rev, const uint32_t *queue, uint32_t n_queue,
-                         const uint64_t *spill_off, uint32_t *spill_store, const Phase2Out &out, cudaStream_t s,
-                         const LaunchCfg &cfg) {
+void launch_phase2_spill(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo, const RowsView &rows,
+                         const uint32_t *queue, uint32_t n_queue, const uint64_t *spill_off, uint32_t *spill_store,
+                         const Phase2Out &out, cudaStream_t s, const LaunchCfg &cfg) {
     if (!n_queue) return;
     phase2_spill_kernel<<<grid_for(n_queue, kWarpsPerBlock, cfg, 8), kThreads, 0, s>>>(
-        R, suffix, P, lo, rev_off, rev, queue, n_queue, spill_off, spill_store, out);
+        R, suffix, P, lo, rows, queue, n_queue, spill_off, spill_store, out);
     bump(cfg);
 }
 
@@ -779,24 +798,24 @@ size_t scan_workspace_bytes(uint64_t n) {
 
 template <class OutT>
 static void launch_scan_impl(const uint32_t *in, OutT *out, uint64_t n, void *workspace, cudaStream_t s,
-                             const LaunchCfg &cfg) {
+                             const LaunchCfg &cfg, const uint32_t *run_if = nullptr) {
     uint64_t *tile_sums = (uint64_t *) workspace;
     const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
     if (n == 0) {
         cudaMemsetAsync(out, 0, sizeof(OutT), s);
         return;
     }
-    scan_tile_sums_kernel<<<(unsigned) tiles, kScanThreads, 0, s>>>(in, n, tile_sums);
-    scan_spine_kernel<<<1, kScanThreads, 0, s>>>(tile_sums, tiles);
-    scan_apply_kernel<OutT><<<(unsigned) tiles, kScanThreads, 0, s>>>(in, out, n, tile_sums, tiles);
+    scan_tile_sums_kernel<<<(unsigned) tiles, kScanThreads, 0, s>>>(in, n, tile_sums, run_if);
+    scan_spine_kernel<<<1, kScanThreads, 0, s>>>(tile_sums, tiles, run_if);
+    scan_apply_kernel<OutT><<<(unsigned) tiles, kScanThreads, 0, s>>>(in, out, n, tile_sums, tiles, run_if);
     bump(cfg);
     bump(cfg);
     bump(cfg);
 }
 
 void launch_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, void *workspace, cudaStream_t s,
-                     const LaunchCfg &cfg) {
-    launch_scan_impl<uint32_t>(in, out, n, workspace, s, cfg);
+                     const LaunchCfg &cfg, const uint32_t *run_if) {
+    launch_scan_impl<uint32_t>(in, out, n, workspace, s, cfg, run_if);
 }
 void launch_scan_u64(const uint32_t *in, uint64_t *out, uint64_t n, void *workspace, cudaStream_t s,
                      const LaunchCfg &cfg) {

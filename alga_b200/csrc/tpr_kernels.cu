@@ -1,29 +1,44 @@
 // Thread-per-read overlap search kernels (sm_100a): the fast path of GraphCreatorPrefSuf phase 1 and phase 2.
 //
-// One THREAD owns one read and walks its overlap lengths one per iteration; the 32 reads of a warp advance in
-// lock step.  Per iteration a thread extracts its K-nucleotide seed window from shared memory, hashes it and
-// loads one 32-byte bucket (the bucket of the next iteration is already in flight).  Tag hits are rare and
-// expensive (a 2-bit compare of the whole overlap), so the compares are handed to the warp: the lanes are cut
-// into groups of 8/10/16/32, each group verifies one requesting thread's candidate, one 32-bit word per lane,
-// straight from the requester's staged read in shared memory.  All bookkeeping (the 3 best phase-1 edges, the
-// surviving phase-2 arrivals) lives in the owning thread's registers, so the per-read overhead is thread
-// instructions, not warp instructions -- the warp-per-read version of these kernels was issue-bound at 560-670
-// warp instructions per read (profiles/ncu_full_r01c_summary.txt).
+// One THREAD owns one read, one WARP owns a tile of 32 consecutive reads (no block-level barriers).  The work of a
+// read is split into two loops with very different instruction mixes:
 //
-// Reads the fast path cannot take (longer than 512 nt, a window with more than two tag matches, offsets above
-// 32, more than 4 surviving arrivals, a source id that occurs twice for one target, ...) are queued for the
-// generic kernels of prefsuf_kernels.cu, which replay GraphCreatorPrefSuf.cpp:356-488 literally.
+//   probe    walk the overlap lengths, one 32-byte bucket of the seed index per length.  The K-nucleotide seed
+//            window slides through a 96-bit register window over the read staged in shared memory (two funnel
+//            shifts per length), the hash is four IMADs.  Buckets are fetched by cp.async (2 x 16 bytes, L2-only,
+//            evict_last: the index is the one structure worth keeping in the 126 MB L2) into a per-thread ring in
+//            shared memory kRing lengths ahead of their use, so kRing random sectors per thread are in flight
+//            without costing registers.  A bucket is tested with eight XOR + a min tree (an entry with the right tag
+//            XORs to its bare read id, everything else to something larger).  Tag hits (0.3 per length) are only
+//            QUEUED in shared memory; in phase 2 the first 64 bits of the hit read (all its overhang tail needs)
+//            follow by cp.async as well.
+//   resolve  take the queued hits in order.  Exact 2-bit compares of whole overlaps are thread-local: every lane
+//            verifies its own candidate, words of the candidate straight from L1/L2, words of the own read from
+//            shared memory -- at 3 candidates per read in phase 1 nearly all lanes are busy.
+//
+// History (profiles/): the first thread-per-read version interleaved probe and resolve per length and verified with
+// warp-cooperative groups; ncu showed it issue-bound at 300-440 warp instructions per (warp, length) with 9 of 32
+// lanes inside the hit branch (r01d).  Splitting the loops (r01h) halved the instructions and left the kernels
+// latency-bound on the bucket loads (27 % of the stall samples at 20 warps per SM, one bucket in flight per thread).
+//
+// Reads the fast path cannot take (longer than 512 nt, a window with more than two tag matches, offsets above 32,
+// more queued arrivals than fit, a source id that occurs twice for one target, ...) are queued for the generic
+// kernels of prefsuf_kernels.cu, which replay GraphCreatorPrefSuf.cpp:356-488 literally.
 #include "launch.h"
 
 namespace alga {
 
 namespace {
 
-constexpr int kTpr = 256;    // threads = reads per tile
-constexpr int kIdCap = 32;   // candidate + in-neighbour ids remembered per target (duplicate detection)
-constexpr int kSurv = 4;     // surviving arrivals kept in registers per target
+constexpr int kTpr = 128;     // threads per block = 4 independent warps
+constexpr int kWarps = kTpr / 32;
+constexpr int kQ2 = 20;       // arrivals queued per target in phase 2
+constexpr int kSurv = 4;      // surviving arrivals kept in registers per target
+constexpr int kRowFast = 32;  // longest transposed row the fast phase-2 kernel takes
+constexpr int kRing1 = 4;     // buckets in flight per thread, phase 1 (ring index is dynamic: power of two)
+constexpr int kRing2 = 3;     // buckets in flight per thread, phase 2 (ring index is static: the loop is unrolled)
 
-inline int tile_grid(uint64_t n_items, const LaunchCfg &cfg, int blocks_per_sm) {
+inline int warp_tile_grid(uint64_t n_items, const LaunchCfg &cfg, int blocks_per_sm) {
     uint64_t need = (n_items + kTpr - 1) / kTpr;
     uint64_t cap = (uint64_t) cfg.sm_count * blocks_per_sm;
     if (need < 1) need = 1;
@@ -38,139 +53,194 @@ __device__ __forceinline__ int warp_max(int v) {
     return v;
 }
 
+// ---- asynchronous copies ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gmem_src) {
+    const uint32_t d = (uint32_t) __cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+// one 32-byte bucket -> two 16-byte chunks of the ring (L2 only, kept in L2 with priority)
+__device__ __forceinline__ void cp_async_bucket(uint32_t *dst_lo, uint32_t *dst_hi, const uint32_t *bucket, uint64_t pol) {
+    const uint32_t d0 = (uint32_t) __cvta_generic_to_shared(dst_lo), d1 = (uint32_t) __cvta_generic_to_shared(dst_hi);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d0), "l"(bucket), "l"(pol) : "memory");
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d1), "l"(bucket + 4), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// ---- bucket evaluation ----------------------------------------------------------------------------------------
+// An entry with the probed tag XORs to its bare read id (<= id_mask), any other entry to something larger: the
+// minimum over the bucket is the smallest matching id, if there is one.
+__device__ __forceinline__ uint32_t bucket_min(const uint32_t (&e)[8], uint32_t tag) {
+    uint32_t m = e[0] ^ tag;
+#pragma unroll
+    for (int s = 1; s < kSlotsPerBucket; s++) m = min(m, e[s] ^ tag);
+    return m;
+}
+
 // ids of the entries of one bucket whose tag matches (first two) and how many there are; true if the bucket is full
 __device__ __forceinline__ bool eval_bucket(const SeedTable &t, const uint32_t (&e)[8], uint32_t tag, uint32_t &c0,
                                             uint32_t &c1, int &n) {
-    uint32_t hm = 0;
 #pragma unroll
-    for (int s = 0; s < kSlotsPerBucket; s++) hm |= ((e[s] ^ tag) <= t.id_mask ? 1u : 0u) << s;
-    if (hm) {
-#pragma unroll
-        for (int s = 0; s < kSlotsPerBucket; s++) {
-            if (hm & (1u << s)) {
-                if (n == 0) c0 = e[s] & t.id_mask;
-                else if (n == 1) c1 = e[s] & t.id_mask;
-                n++;
-            }
+    for (int s = 0; s < kSlotsPerBucket; s++) {
+        if ((e[s] ^ tag) <= t.id_mask) {
+            if (n == 0) c0 = e[s] & t.id_mask;
+            else if (n == 1) c1 = e[s] & t.id_mask;
+            n++;
         }
     }
     return e[kSlotsPerBucket - 1] != kEmptySlot;  // buckets fill front to back: a full one chains on
 }
 
-// Finish the probe whose first bucket is in e[]: chained buckets are walked on demand (p ~ 1e-3 per probe).
-__device__ __forceinline__ void finish_probe(const SeedTable &t, uint32_t (&e)[8], uint32_t tag, uint32_t bk, uint32_t &c0,
-                                             uint32_t &c1, int &n) {
-    n = 0;
+// Matches of a probe whose first bucket is in e[] and holds at least one match or is full.  The common case -- one
+// match, bucket not full -- is answered by the minimum alone; otherwise collect the matches and walk the chain.
+__device__ __forceinline__ void probe_matches(const SeedTable &t, uint32_t (&e)[8], uint32_t tag, uint32_t bk, uint32_t m,
+                                              uint32_t &c0, uint32_t &c1, int &n) {
+    int cnt = 0;
+#pragma unroll
+    for (int s = 0; s < kSlotsPerBucket; s++) cnt += ((e[s] ^ tag) <= t.id_mask) ? 1 : 0;
+    const bool full = e[kSlotsPerBucket - 1] != kEmptySlot;
     c0 = c1 = kNone;
-    bool full = eval_bucket(t, e, tag, c0, c1, n);
-    while (full) {
+    if (cnt == 1 && !full) {
+        n = 1;
+        c0 = m;
+        return;
+    }
+    n = 0;
+    bool more = eval_bucket(t, e, tag, c0, c1, n);
+    while (more) {
         bk = (bk + 1 == t.n_buckets) ? 0u : bk + 1;
         load_bucket(t.slots + (uint64_t) bk * kSlotsPerBucket, e);
-        full = eval_bucket(t, e, tag, c0, c1, n);
+        more = eval_bucket(t, e, tag, c0, c1, n);
     }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// Warp-cooperative verification of phase-1 candidates: requester r asks "prefix(cand, L) == suffix(own_r, L)?".
-// wown = staged reads of the warp (read of lane r at wown + r * wp).
-template <bool UNIFORM>
-__device__ __forceinline__ bool coop_verify_suffix(const ReadsDev &R, const uint32_t *wown, int wp, const GroupGeom &q,
-                                                   bool want, uint32_t cand, uint32_t self, uint32_t o, int32_t L,
-                                                   int lane) {
-    unsigned req = __ballot_sync(kFull, want);
-    bool result = false;
-    const unsigned lt = (1u << lane) - 1u;
-    while (req) {
-        unsigned chunk = 0;
-        int src = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (i < q.V && req) {
-                const int l = __ffs(req) - 1;
-                if (i == q.g) src = l;
-                chunk |= 1u << l;
-                req &= req - 1;
-            }
-        }
-        const int ng = __popc(chunk);
-        const uint32_t c_s = __shfl_sync(kFull, cand, src), b_s = __shfl_sync(kFull, self, src);
-        const uint32_t o_s = __shfl_sync(kFull, o, src);
-        const int32_t L_s = __shfl_sync(kFull, L, src);
-        const bool act = q.g < ng && q.g < q.V;
-        bool bad = false;
-        if (act) {
-            const uint32_t nbits = 2u * (uint32_t) L_s, nw = (nbits + 31u) >> 5;
-            if (q.k == 0 && (c_s == b_s || (!UNIFORM && (int64_t) R.len[c_s] < L_s))) bad = true;
-            if ((uint32_t) q.k < nw) {
-                const uint32_t *ow = wown + src * wp + ((2u * o_s) >> 5) + q.k;
-                uint32_t x = __funnelshift_r(ow[0], ow[1], (2u * o_s) & 31u) ^ __ldg(read_ptr(R, c_s) + q.k);
-                if ((uint32_t) q.k == nw - 1 && (nbits & 31u)) x &= (1u << (nbits & 31u)) - 1u;
-                bad |= x != 0;
-            }
-        }
-        const unsigned okbits = group_ok(q, act, bad);
-        if ((chunk >> lane) & 1u) result = (okbits >> __popc(chunk & lt)) & 1u;
-    }
-    return result;
+// 64 bits of the staged read starting `s` bits into the register window (w0, w1, w2)
+__device__ __forceinline__ uint64_t window_key(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t s) {
+    return (uint64_t) __funnelshift_r(w0, w1, s) | ((uint64_t) __funnelshift_r(w1, w2, s) << 32);
 }
 
-// Phase-2 flavour: requester r asks "suffix(cand, L) == prefix(own_r, L)?", o = len(cand) - L.
-__device__ __forceinline__ bool coop_verify_prefix(const ReadsDev &R, const uint32_t *wown, int wp, const GroupGeom &q,
-                                                   bool want, uint32_t cand, uint32_t o, int32_t L, int lane) {
-    unsigned req = __ballot_sync(kFull, want);
-    bool result = false;
-    const unsigned lt = (1u << lane) - 1u;
-    while (req) {
-        unsigned chunk = 0;
-        int src = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (i < q.V && req) {
-                const int l = __ffs(req) - 1;
-                if (i == q.g) src = l;
-                chunk |= 1u << l;
-                req &= req - 1;
+// Stage the (up to 32) reads of a warp's tile: `sw` words each at stride `wp`, the rest of the stride zeroed.
+// FAST (fixed stride in HBM): the tile is one contiguous range, copied with fully coalesced loads.
+template <bool FAST>
+__device__ __forceinline__ void stage_warp(const ReadsDev &R, uint32_t *wown, int wp, int sw, uint64_t first,
+                                           uint32_t n_valid, uint32_t my_words, int lane) {
+    uint32_t *own = wown + lane * wp;
+    __syncwarp();
+    if (FAST) {
+        for (int w = sw; w < wp; w++) own[w] = 0u;
+        const uint32_t *base = R.words + first * R.stride;
+        if ((uint32_t) sw == R.stride) {
+            const uint32_t total = n_valid * (uint32_t) sw;
+            uint32_t r = (uint32_t) lane / (uint32_t) sw, w = (uint32_t) lane - r * (uint32_t) sw;
+            const uint32_t dr = 32u / (uint32_t) sw, dw = 32u - dr * (uint32_t) sw;
+            for (uint32_t j = lane; j < total; j += 32) {
+                wown[r * wp + w] = __ldg(base + j);
+                r += dr;
+                w += dw;
+                if (w >= (uint32_t) sw) {
+                    w -= sw;
+                    r++;
+                }
             }
+        } else {
+            if ((uint32_t) lane < n_valid)
+                for (int w = 0; w < sw; w++) own[w] = __ldg(base + (uint64_t) lane * R.stride + w);
         }
-        const int ng = __popc(chunk);
-        const uint32_t b_s = __shfl_sync(kFull, cand, src), o_s = __shfl_sync(kFull, o, src);
-        const int32_t L_s = __shfl_sync(kFull, L, src);
-        const bool act = q.g < ng && q.g < q.V;
-        bool bad = false;
-        if (act) {
-            const uint32_t nbits = 2u * (uint32_t) L_s, nw = (nbits + 31u) >> 5;
-            if ((uint32_t) q.k < nw) {
-                const uint32_t *qb = read_ptr(R, b_s) + ((2u * o_s) >> 5) + q.k;
-                uint32_t x = __funnelshift_r(__ldg(qb), __ldg(qb + 1), (2u * o_s) & 31u) ^ wown[src * wp + q.k];
-                if ((uint32_t) q.k == nw - 1 && (nbits & 31u)) x &= (1u << (nbits & 31u)) - 1u;
-                bad = x != 0;
-            }
-        }
-        const unsigned okbits = group_ok(q, act, bad);
-        if ((chunk >> lane) & 1u) result = (okbits >> __popc(chunk & lt)) & 1u;
+    } else {
+        const uint32_t *p = (uint32_t) lane < n_valid ? read_ptr(R, (uint32_t) (first + lane)) : R.words;
+        for (int w = 0; w < wp; w++) own[w] = (uint32_t) w < my_words ? __ldg(p + w) : 0u;
     }
-    return result;
+    __syncwarp();
+}
+
+// prefix(cand, L) == own[o .. o + L) ?   (phase 1: suffix of the own read against the prefix of the candidate)
+__device__ __forceinline__ bool verify_own_suffix(const ReadsDev &R, const uint32_t *own, uint32_t cand, uint32_t o,
+                                                  int32_t L) {
+    const uint32_t *pc = read_ptr(R, cand);
+    const uint32_t nbits = 2u * (uint32_t) L, nw = (nbits + 31u) >> 5, sh = (2u * o) & 31u;
+    const uint32_t *ow = own + ((2u * o) >> 5);
+    for (uint32_t k0 = 0; k0 < nw; k0 += 4) {
+        uint32_t g[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) g[j] = k0 + j < nw ? __ldg(pc + k0 + j) : 0u;
+        uint32_t diff = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t k = k0 + j;
+            if (k < nw) {
+                uint32_t x = __funnelshift_r(ow[k], ow[k + 1], sh) ^ g[j];
+                if (k == nw - 1 && (nbits & 31u)) x &= (1u << (nbits & 31u)) - 1u;
+                diff |= x;
+            }
+        }
+        if (diff) return false;
+    }
+    return true;
+}
+
+// cand[o .. o + L) == own[0 .. L) ?   (phase 2: suffix of the candidate against the prefix of the own read)
+__device__ __forceinline__ bool verify_own_prefix(const ReadsDev &R, const uint32_t *own, uint32_t cand, uint32_t o,
+                                                  int32_t L) {
+    const uint32_t *pb = read_ptr(R, cand) + ((2u * o) >> 5);
+    const uint32_t nbits = 2u * (uint32_t) L, nw = (nbits + 31u) >> 5, sh = (2u * o) & 31u;
+    for (uint32_t k0 = 0; k0 < nw; k0 += 4) {
+        uint32_t g[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++) g[j] = k0 + j <= nw ? __ldg(pb + k0 + j) : 0u;
+        uint32_t diff = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t k = k0 + j;
+            if (k < nw) {
+                uint32_t x = __funnelshift_r(g[j], g[j + 1], sh) ^ own[k];
+                if (k == nw - 1 && (nbits & 31u)) x &= (1u << (nbits & 31u)) - 1u;
+                diff |= x;
+            }
+        }
+        if (diff) return false;
+    }
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // Phase 1 (GraphCreatorPrefSuf.cpp:397-402 in closed form): source read b walks L from min(rs-1, len) downwards
 // and keeps the first 3 confirmed (L, c) -- within one L the larger c first -- = "the last 3 pushes".
-template <bool UNIFORM>
-__global__ void __launch_bounds__(kTpr, 4)
-phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, int wp, int nw_max, int2 *__restrict__ fwd,
-                  uint64_t *__restrict__ fwd_t, uint32_t *__restrict__ fwd_pos, uint32_t *__restrict__ indeg,
+//
+// Shared memory per warp: own reads [32][wp] | bucket ring [kRing1][2][32] x 16 B | tag ring, bucket-id ring
+// [kRing1][32].  Lanes pause once they hold 3 candidates, so their positions in the walk differ: ring index, window
+// and prefetch state are per lane.
+template <bool FAST>
+__global__ void __launch_bounds__(kTpr, 8)
+phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, int wp, Phase1Out out,
                   uint32_t *__restrict__ hard_queue, uint32_t *n_hard, int force_hard) {
-    extern __shared__ uint32_t smem[];
-    const int tid = threadIdx.x, lane = tid & 31;
-    uint32_t *own = smem + tid * wp;
-    const uint32_t *wown = smem + (tid & ~31) * wp;
-    const GroupGeom q = group_geom(nw_max, lane);
-    const uint64_t n_tiles = ((uint64_t) (hi - lo) + kTpr - 1) / kTpr;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t bb = (uint64_t) lo + tile * kTpr + tid;
-        const bool inr = bb < hi;
-        const uint32_t b = inr ? (uint32_t) bb : lo;
-        const uint32_t lenb = inr ? (UNIFORM ? P.uniform_len : R.len[b]) : 0u;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int per_warp = 32 * wp + kRing1 * 32 * 10;
+    const int own_words = ((kWarps * 32 * wp + 3) & ~3);  // ring chunks stay 16-byte aligned
+    uint32_t *wown = smem + wib * 32 * wp;
+    const uint32_t *own = wown + lane * wp;
+    uint32_t *ring = smem + own_words + wib * (kRing1 * 32 * 10);  // [slot][half][lane] x 4 words
+    uint32_t *ring_tag = ring + kRing1 * 2 * 32 * 4;                // [slot][lane]
+    uint32_t *ring_bk = ring_tag + kRing1 * 32;
+    (void) per_warp;
+    const uint64_t pol = l2_evict_last_policy();
+    const uint64_t n_tiles = ((uint64_t) (hi - lo) + 31) / 32;
+    const uint64_t warp_id = (uint64_t) blockIdx.x * kWarps + wib, n_warps = (uint64_t) gridDim.x * kWarps;
+    for (uint64_t tile = warp_id; tile < n_tiles; tile += n_warps) {
+        const uint64_t first = (uint64_t) lo + tile * 32;
+        const uint32_t n_valid = (uint32_t) min((uint64_t) 32, (uint64_t) hi - first);
+        const bool inr = (uint32_t) lane < n_valid;
+        const uint32_t b = inr ? (uint32_t) (first + lane) : lo;
+        const uint32_t lenb = inr ? (FAST ? P.uniform_len : R.len[b]) : 0u;
         int64_t l_hi64 = (int64_t) lenb - P.min_offset;
         if (l_hi64 > P.rs - 1) l_hi64 = P.rs - 1;
         if (l_hi64 > P.max_l) l_hi64 = P.max_l;
@@ -181,77 +251,174 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
             hard = true;
             active = false;
         }
-        __syncwarp();
-        {
-            const uint32_t nw = active ? (lenb + 15u) >> 4 : 0u;
-            const uint32_t *p = read_ptr(R, b);
-            for (int w = 0; w < wp; w++) own[w] = (uint32_t) w < nw ? __ldg(p + w) : 0u;
-        }
-        __syncwarp();
-        int found = 0;
-        uint32_t sc0 = kNone, sc1 = kNone, sc2 = kNone, so0 = 0, so1 = 0, so2 = 0;
-        const int n_iter = warp_max(active ? l_hi - P.lmin + 1 : 0);
-        uint32_t e[8];
-        uint32_t tag = 0, bk = 0;
+        stage_warp<FAST>(R, wown, wp, wp - 2, first, n_valid, active ? (lenb + 15u) >> 4 : 0u, lane);
+
+        int conf = 0, np = 0;
+        uint32_t sc[kSmallEdgesKept], so[kSmallEdgesKept], pc[4];
+        int32_t pl[4];
+#pragma unroll
+        for (int k = 0; k < kSmallEdgesKept; k++) sc[k] = kNone, so[k] = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) pc[k] = kNone, pl[k] = 0;
+
+        // walk state: Lc = next length to test (its bucket is, or will be, in ring slot it % kRing1),
+        // Lp = next length to prefetch, (w0, w1, w2, sh, wb) = register window at Lp
+        int32_t Lc = l_hi, Lp = l_hi;
+        int it = 0;
+        bool more = active;
+        uint32_t w0 = 0, w1 = 0, w2 = 0, sh = 0;
+        int wb = 0;
         if (active) {
-            const uint64_t h = mix64(sbits64(own, 2u * (lenb - (uint32_t) l_hi)) & P.seed_mask);
-            tag = tag_of(T, h);
-            bk = bucket_of(h, T.n_buckets);
-            load_bucket(T.slots + (uint64_t) bk * kSlotsPerBucket, e);
+            const uint32_t p = 2u * (lenb - (uint32_t) Lp);
+            wb = (int) (p >> 5);
+            sh = p & 31u;
+            w0 = own[wb], w1 = own[wb + 1], w2 = own[wb + 2];
         }
-        for (int it = 0; it < n_iter; it++) {
-            const int32_t L = l_hi - it;
-            const bool live = active && !hard && found < kSmallEdgesKept && L >= P.lmin;
-            if (!__any_sync(kFull, live)) break;
-            uint32_t c0 = kNone, c1 = kNone;
-            int n = 0;
-            if (live) finish_probe(T, e, tag, bk, c0, c1, n);
-            if (live && L - 1 >= P.lmin) {  // bucket of the next length goes in flight before the compares
-                const uint64_t h = mix64(sbits64(own, 2u * (lenb - (uint32_t) (L - 1))) & P.seed_mask);
-                tag = tag_of(T, h);
-                bk = bucket_of(h, T.n_buckets);
-                load_bucket(T.slots + (uint64_t) bk * kSlotsPerBucket, e);
+        auto prefetch = [&](int slot) {  // bucket of length Lp -> ring slot, then slide the window one nucleotide
+            if (active && Lp >= P.lmin) {
+                const uint64_t h = mix64(window_key(w0, w1, w2, sh) & P.seed_mask);
+                const uint32_t bk = bucket_of(h, T.n_buckets);
+                ring_tag[slot * 32 + lane] = tag_of(T, h);
+                ring_bk[slot * 32 + lane] = bk;
+                cp_async_bucket(ring + ((slot * 2) * 32 + lane) * 4, ring + ((slot * 2 + 1) * 32 + lane) * 4,
+                                T.slots + (uint64_t) bk * kSlotsPerBucket, pol);
+                Lp--;
+                sh += 2u;
+                if (sh == 32u) {
+                    sh = 0u;
+                    wb++;
+                    w0 = w1, w1 = w2, w2 = own[wb + 2];
+                }
             }
-            if (n > 2) hard = true;
-            if (n == 2 && c1 > c0) {  // within one length the larger target id is the later push
-                const uint32_t x = c0;
-                c0 = c1;
-                c1 = x;
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int j = 0; j < kRing1; j++) prefetch(j);
+
+        while (true) {
+            // ---- probe until every lane has 3 candidates (confirmed + pending) or ran out of lengths
+            while (true) {
+                const bool need = more && !hard && conf + np < kSmallEdgesKept;
+                if (!__any_sync(kFull, need)) break;
+                if (need) {
+                    const int slot = it & (kRing1 - 1);
+                    cp_async_wait_group<kRing1 - 1>();
+                    uint32_t e[8];
+                    {
+                        const uint4 a = *reinterpret_cast<const uint4 *>(ring + ((slot * 2) * 32 + lane) * 4);
+                        const uint4 c = *reinterpret_cast<const uint4 *>(ring + ((slot * 2 + 1) * 32 + lane) * 4);
+                        e[0] = a.x, e[1] = a.y, e[2] = a.z, e[3] = a.w, e[4] = c.x, e[5] = c.y, e[6] = c.z, e[7] = c.w;
+                    }
+                    const uint32_t tag = ring_tag[slot * 32 + lane];
+                    const uint32_t m = bucket_min(e, tag);
+                    uint32_t c0 = kNone, c1 = kNone;
+                    int n = 0;
+                    if (m <= T.id_mask || e[7] != kEmptySlot) probe_matches(T, e, tag, ring_bk[slot * 32 + lane], m, c0, c1, n);
+                    prefetch(slot);
+                    const int32_t L = Lc;
+                    it++;
+                    Lc--;
+                    more = Lc >= P.lmin;
+                    if (n > 2) {
+                        hard = true;
+                    } else if (n) {
+                        if (n == 2 && c1 > c0) {  // within one length the larger target id is the later push
+                            const uint32_t x = c0;
+                            c0 = c1;
+                            c1 = x;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if (k == np) pc[k] = c0, pl[k] = L;
+                        np++;
+                        if (n == 2) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                if (k == np) pc[k] = c1, pl[k] = L;
+                            np++;
+                        }
+                    }
+                }
             }
-            const uint32_t o = lenb - (uint32_t) L;
-            const bool ok0 = coop_verify_suffix<UNIFORM>(R, wown, wp, q, live && !hard && n > 0, c0, b, o, L, lane);
-            bool ok1 = false;
-            if (__any_sync(kFull, live && !hard && n > 1))
-                ok1 = coop_verify_suffix<UNIFORM>(R, wown, wp, q, live && !hard && n > 1, c1, b, o, L, lane);
-            if (ok0) {
-                if (found == 0) sc0 = c0, so0 = o;
-                else if (found == 1) sc1 = c0, so1 = o;
-                else if (found == 2) sc2 = c0, so2 = o;
-                found++;
+            // ---- confirm the pending candidates, every lane its own
+            const int np_max = warp_max(hard ? 0 : np);
+            if (np_max == 0) break;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (k < np_max) {
+                    const bool want = k < np && !hard && conf < kSmallEdgesKept;
+                    if (want) {
+                        const uint32_t cand = pc[k];
+                        const int32_t L = pl[k];
+                        const uint32_t o = lenb - (uint32_t) L;
+                        if (cand != b && (FAST || (int64_t) R.len[cand] >= L) && verify_own_suffix(R, own, cand, o, L)) {
+#pragma unroll
+                            for (int q = 0; q < kSmallEdgesKept; q++)
+                                if (q == conf) sc[q] = cand, so[q] = o;
+                            conf++;
+                        }
+                    }
+                }
             }
-            if (ok1) {
-                if (found == 0) sc0 = c1, so0 = o;
-                else if (found == 1) sc1 = c1, so1 = o;
-                else if (found == 2) sc2 = c1, so2 = o;
-                found++;
-            }
+            np = 0;
         }
-        if (hard) {
-            hard_queue[atomicAdd(n_hard, 1u)] = b;
-        } else if (inr) {
-            const uint64_t s0 = (uint64_t) (b - lo) * kSmallEdgesKept;
+        cp_async_wait_all();  // prefetches beyond the last tested length: land before the ring is reused
+
+        // ---- emit
+        if (out.mode == 0) {
+            if (!hard) {
+                uint32_t pos[kSmallEdgesKept];
+#pragma unroll
+                for (int k = 0; k < kSmallEdgesKept; k++) pos[k] = k < conf ? atomicAdd(out.indeg + sc[k], 1u) : 0u;
+#pragma unroll
+                for (int k = 0; k < kSmallEdgesKept; k++) {
+                    if (k < conf) {
+                        const uint32_t c = sc[k];
+                        RevEntry r;
+                        r.b = (int32_t) b;
+                        r.o = (int32_t) so[k];
+                        r.t = overhang_tail_own(own, so[k]);
+                        if (pos[k] < out.row_cap) {
+                            out.rows[(uint64_t) c * out.row_cap + pos[k]] = r;
+                        } else {
+                            const uint32_t i = atomicAdd(out.n_list, 1u);
+                            if (i < out.list_cap) {
+                                Edge1 x;
+                                x.c = (int32_t) c, x.b = r.b, x.o = r.o, x.pad = 0, x.t = r.t;
+                                out.list[i] = x;
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
+            const uint32_t n_out = hard ? 0u : (uint32_t) conf;
+            uint32_t incl = n_out;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(kFull, incl, d);
+                if (lane >= d) incl += y;
+            }
+            const uint32_t total = __shfl_sync(kFull, incl, 31);
+            uint32_t base = 0;
+            if (total) {
+                if (lane == 31) base = atomicAdd(out.n_list, total);
+                base = __shfl_sync(kFull, base, 31);
+            }
+            uint32_t pos = base + incl - n_out;
 #pragma unroll
             for (int k = 0; k < kSmallEdgesKept; k++) {
-                const uint32_t c = k == 0 ? sc0 : (k == 1 ? sc1 : sc2), o = k == 0 ? so0 : (k == 1 ? so1 : so2);
-                if (k < found) {
-                    fwd[s0 + k] = make_int2((int32_t) c, (int32_t) o);
-                    fwd_t[s0 + k] = overhang_tail_own(own, o);
-                    if (indeg) fwd_pos[s0 + k] = atomicAdd(indeg + c, 1u);
-                } else {
-                    fwd[s0 + k] = make_int2(-1, 0);
+                if ((uint32_t) k < n_out) {
+                    if (pos < out.list_cap) {
+                        Edge1 x;
+                        x.c = (int32_t) sc[k], x.b = (int32_t) b, x.o = (int32_t) so[k], x.pad = 0;
+                        x.t = overhang_tail_own(own, so[k]);
+                        out.list[pos] = x;
+                    }
+                    pos++;
                 }
             }
         }
+        if (hard) hard_queue[atomicAdd(n_hard, 1u)] = b;
     }
 }
 
@@ -260,159 +427,239 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
 // LAST arrival to its first.  An arrival (b, o) stays in c's list unless a later arrival j with o_j > 0 has an
 // overhang that is a suffix of b's overhang (a[oa-oj .. oa) == b_j[0 .. oj), right offset >= 0); the relation is
 // transitive, so it is enough to test against the arrivals that survived so far, and a candidate that fails this
-// test is dropped without ever comparing its overlap.  Survivors are confirmed by the warp.  Entries of the
-// transposed phase-1 graph (rows) are tested against the survivors at the end.
-template <bool UNIFORM>
-__global__ void __launch_bounds__(kTpr, 3)
-phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, int wp, int nw_max,
-                  const uint32_t *__restrict__ rev_off, const RevEntry *__restrict__ rev, Phase2Out out, int force_hard) {
-    extern __shared__ uint32_t smem[];
-    const int tid = threadIdx.x, lane = tid & 31;
-    uint32_t *own = smem + tid * wp;
-    const uint32_t *wown = smem + (tid & ~31) * wp;
-    uint32_t *ids = smem + kTpr * wp + tid;  // ids[k * kTpr]: k-th remembered id of this thread
-    const GroupGeom q = group_geom(nw_max, lane);
+// test is dropped without ever comparing its overlap.  Entries of the transposed phase-1 graph (rows) are tested
+// against the survivors at the end.
+//
+// Shared memory per warp: own reads [32][wp] | bucket ring [kRing2][2][32] x 16 B | queue: ids [kQ2][32],
+// heads [kQ2][2][32], lengths [kQ2][32] (u16).
+template <bool FAST>
+__global__ void __launch_bounds__(kTpr, 4)
+phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, int wp, RowsView rows, Phase2Out out,
+                  int force_hard) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int own_words = ((kWarps * 32 * wp + 3) & ~3);
+    constexpr int kRingWords = kRing2 * 2 * 32 * 4, kQueueWords = kQ2 * 32 * 3 + kQ2 * 32 / 2;
+    uint32_t *wown = smem + wib * 32 * wp;
+    const uint32_t *own = wown + lane * wp;
+    uint32_t *ring = smem + own_words + wib * kRingWords;  // [slot][half][lane] x 4 words
+    uint32_t *q_id = smem + own_words + kWarps * kRingWords + wib * kQueueWords + lane;  // q_id[k * 32]
+    uint32_t *q_t = q_id + kQ2 * 32;                                                     // q_t[(2k | 2k+1) * 32]
+    uint16_t *q_l = reinterpret_cast<uint16_t *>(q_id - lane + kQ2 * 32 * 3) + lane;      // q_l[k * 32]
+    const uint64_t pol = l2_evict_last_policy();
     const int32_t l_lo = P.rs > P.lmin ? P.rs : P.lmin;
-    const uint64_t n_tiles = ((uint64_t) (hi - lo) + kTpr - 1) / kTpr;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t cc = (uint64_t) lo + tile * kTpr + tid;
-        const bool inr = cc < hi;
-        const uint32_t c = inr ? (uint32_t) cc : lo;
-        uint32_t r0 = 0, deg = 0;
-        if (inr) {
-            r0 = rev_off[c - lo];
-            deg = rev_off[c - lo + 1] - r0;
-        }
-        const uint32_t lenc = inr ? (UNIFORM ? P.uniform_len : R.len[c]) : 0u;
-        int32_t l_hi = (int32_t) (lenc < (uint32_t) P.max_l ? lenc : (uint32_t) P.max_l);
+    const bool csr = rows_are_csr(rows);
+    const uint64_t n_tiles = ((uint64_t) (hi - lo) + 31) / 32;
+    const uint64_t warp_id = (uint64_t) blockIdx.x * kWarps + wib, n_warps = (uint64_t) gridDim.x * kWarps;
+    for (uint64_t tile = warp_id; tile < n_tiles; tile += n_warps) {
+        const uint64_t first = (uint64_t) lo + tile * 32;
+        const uint32_t n_valid = (uint32_t) min((uint64_t) 32, (uint64_t) hi - first);
+        const bool inr = (uint32_t) lane < n_valid;
+        const uint32_t c = inr ? (uint32_t) (first + lane) : lo;
+        uint32_t deg = 0;
+        const RevEntry *row = rows.rev;
+        if (inr) row = get_row(rows, csr, c - lo, deg);
+        const uint32_t lenc = inr ? (FAST ? P.uniform_len : R.len[c]) : 0u;
+        const int32_t l_hi = (int32_t) (lenc < (uint32_t) P.max_l ? lenc : (uint32_t) P.max_l);
         const bool active = inr && lenc != 0 && flag_to(R, c) && l_hi >= l_lo;
         const bool part = active || deg > 0;  // has something to emit
-        bool hard = part && (force_hard || deg > (uint32_t) kIdCap);
-        __syncwarp();
+        bool hard = part && (force_hard || deg > (uint32_t) kRowFast || (!csr && deg > rows.cap));
         {
             uint32_t nw = 0;
             if (active && !hard) {
                 const uint32_t need = (uint32_t) ((2 * l_hi + 31) >> 5), have = (lenc + 15u) >> 4;
                 nw = need < have ? need : have;
             }
-            const uint32_t *p = read_ptr(R, c);
-            for (int w = 0; w < wp; w++) own[w] = (uint32_t) w < nw ? __ldg(p + w) : 0u;
+            stage_warp<FAST>(R, wown, wp, wp - 2, first, n_valid, nw, lane);
         }
-        __syncwarp();
-        int n_ids = 0, ns = 0;
+
+        // ---- probe: queue every tag hit (b, L); FAST: the first 64 bits of b follow by cp.async
+        int qn = 0;
+        const bool walk = active && !hard;
+        const int n_iter = warp_max(walk ? l_hi - l_lo + 1 : 0);
+        uint32_t tagr[kRing2], bkr[kRing2], w0 = 0, w1 = 0, w2 = 0, sh = 0;
+        int wb = 0;
+        int32_t Lp = l_hi;  // next length to prefetch; (w0, w1, w2, sh, wb) = register window at Lp
+        if (walk) {
+            const uint32_t p = 2u * (uint32_t) (l_hi - P.seed_nt);
+            wb = (int) (p >> 5);
+            sh = p & 31u;
+            w0 = own[wb], w1 = own[wb + 1], w2 = own[wb + 2];
+        }
+#pragma unroll
+        for (int j = 0; j < kRing2; j++) tagr[j] = 0, bkr[j] = 0;
+        auto prefetch = [&](int slot, uint32_t &tag_out, uint32_t &bk_out) {
+            if (walk && Lp >= l_lo) {
+                const uint64_t h = mix64(window_key(w0, w1, w2, sh) & P.seed_mask);
+                tag_out = tag_of(T, h);
+                bk_out = bucket_of(h, T.n_buckets);
+                cp_async_bucket(ring + ((slot * 2) * 32 + lane) * 4, ring + ((slot * 2 + 1) * 32 + lane) * 4,
+                                T.slots + (uint64_t) bk_out * kSlotsPerBucket, pol);
+                Lp--;
+                if (sh == 0u) {  // slide the window down by one nucleotide
+                    sh = 32u;
+                    wb--;
+                    w2 = w1, w1 = w0, w0 = wb >= 0 ? own[wb] : 0u;
+                }
+                sh -= 2u;
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int j = 0; j < kRing2; j++) prefetch(j, tagr[j], bkr[j]);
+
+        for (int it0 = 0; it0 < n_iter; it0 += kRing2) {
+#pragma unroll
+            for (int j = 0; j < kRing2; j++) {
+                const int32_t L = l_hi - (it0 + j);
+                if (walk && L >= l_lo) {
+                    cp_async_wait_group<kRing2 - 1>();
+                    uint32_t e[8];
+                    {
+                        const uint4 a = *reinterpret_cast<const uint4 *>(ring + ((j * 2) * 32 + lane) * 4);
+                        const uint4 d = *reinterpret_cast<const uint4 *>(ring + ((j * 2 + 1) * 32 + lane) * 4);
+                        e[0] = a.x, e[1] = a.y, e[2] = a.z, e[3] = a.w, e[4] = d.x, e[5] = d.y, e[6] = d.z, e[7] = d.w;
+                    }
+                    const uint32_t tag = tagr[j], bk = bkr[j];
+                    const uint32_t m = bucket_min(e, tag);
+                    uint32_t b0 = kNone, b1 = kNone;
+                    int n = 0;
+                    if (!hard && (m <= T.id_mask || e[7] != kEmptySlot)) probe_matches(T, e, tag, bk, m, b0, b1, n);
+                    prefetch(j, tagr[j], bkr[j]);
+                    if (n > 2) {
+                        hard = true;
+                    } else if (n) {
+                        if (n == 2 && b1 > b0) {  // walking backwards: within one length the larger source id arrived later
+                            const uint32_t x = b0;
+                            b0 = b1;
+                            b1 = x;
+                        }
+                        for (int k = 0; k < n; k++) {
+                            const uint32_t cand = k ? b1 : b0;
+                            if (cand == c) continue;
+                            if (qn >= kQ2) {
+                                hard = true;
+                                break;
+                            }
+                            q_id[qn * 32] = cand;
+                            q_l[qn * 32] = (uint16_t) L;
+                            if (FAST) {
+                                const uint32_t *pb = R.words + (uint64_t) cand * R.stride;
+                                cp_async4(q_t + (2 * qn) * 32, pb);
+                                cp_async4(q_t + (2 * qn + 1) * 32, pb + 1);
+                            }
+                            qn++;
+                        }
+                    }
+                }
+            }
+        }
+        cp_async_wait_all();
+
+        // ---- resolve the queued arrivals, last arrival first
+        int ns = 0;
         uint32_t s_id[kSurv], s_o[kSurv], s_len[kSurv];
         uint64_t s_t[kSurv];
 #pragma unroll
         for (int s = 0; s < kSurv; s++) s_id[s] = kNone, s_o[s] = 0, s_len[s] = 0, s_t[s] = 0;
-        const int n_iter = warp_max(active && !hard ? l_hi - l_lo + 1 : 0);
-        uint32_t e[8];
-        uint32_t tag = 0, bk = 0;
-        if (active && !hard) {
-            const uint64_t h = mix64(sbits64(own, 2u * (uint32_t) (l_hi - P.seed_nt)) & P.seed_mask);
-            tag = tag_of(T, h);
-            bk = bucket_of(h, T.n_buckets);
-            load_bucket(T.slots + (uint64_t) bk * kSlotsPerBucket, e);
-        }
-        for (int it = 0; it < n_iter; it++) {
-            const int32_t L = l_hi - it;
-            const bool live = active && !hard && L >= l_lo;
-            if (!__any_sync(kFull, live)) break;
-            uint32_t b0 = kNone, b1 = kNone;
-            int n = 0;
-            if (live) finish_probe(T, e, tag, bk, b0, b1, n);
-            if (live && L - 1 >= l_lo) {
-                const uint64_t h = mix64(sbits64(own, 2u * (uint32_t) (L - 1 - P.seed_nt)) & P.seed_mask);
-                tag = tag_of(T, h);
-                bk = bucket_of(h, T.n_buckets);
-                load_bucket(T.slots + (uint64_t) bk * kSlotsPerBucket, e);
-            }
-            if (n > 2) hard = true;
-            if (n == 2 && b1 > b0) {  // walking backwards: within one length the larger source id arrived later
-                const uint32_t x = b0;
-                b0 = b1;
-                b1 = x;
-            }
-            const int n_pass = __any_sync(kFull, live && !hard && n > 1) ? 2 : 1;
-            for (int k = 0; k < n_pass; k++) {
-                const uint32_t cand = k ? b1 : b0;
-                bool want = false;
-                uint32_t o = 0, lenb = lenc;
-                uint64_t t = 0;
-                if (live && !hard && n > k && cand != c) {
-                    if (!UNIFORM) lenb = R.len[cand];
-                    if ((int64_t) lenb - P.min_offset >= L) {
-                        o = lenb - (uint32_t) L;
-                        if (o > 32u || n_ids >= kIdCap) {
-                            hard = true;
-                        } else {
-                            ids[n_ids * kTpr] = cand;
-                            n_ids++;
-                            t = overhang_tail(read_ptr(R, cand), o);
-                            bool removed = false;
-#pragma unroll
-                            for (int s = 0; s < kSurv; s++) {
-                                if (s < ns && s_o[s] > 0 && o >= s_o[s] &&
-                                    (UNIFORM || (int64_t) s_len[s] + (int64_t) (o - s_o[s]) - (int64_t) lenb >= 0) &&
-                                    ((t ^ s_t[s]) >> (64u - 2u * s_o[s])) == 0)
-                                    removed = true;
-                            }
-                            want = !removed;
-                        }
-                    }
-                }
-                const bool ok = coop_verify_prefix(R, wown, wp, q, want, cand, o, L, lane);
-                if (ok) {
-                    if (ns >= kSurv) {
+        const int q_max = warp_max(hard ? 0 : qn);
+        for (int k = 0; k < q_max; k++) {
+            bool want = false;
+            uint32_t cand = kNone, o = 0, lenb = lenc;
+            int32_t L = 0;
+            uint64_t t = 0;
+            if (k < qn && !hard) {
+                cand = q_id[k * 32];
+                L = (int32_t) q_l[k * 32];
+                if (!FAST) lenb = R.len[cand];
+                if ((int64_t) lenb - P.min_offset >= L) {
+                    o = lenb - (uint32_t) L;
+                    if (o > 32u) {
                         hard = true;
                     } else {
+                        if (FAST) {
+                            const uint64_t head = (uint64_t) q_t[(2 * k) * 32] | ((uint64_t) q_t[(2 * k + 1) * 32] << 32);
+                            t = o ? head << (64u - 2u * o) : 0ull;
+                        } else {
+                            t = overhang_tail(read_ptr(R, cand), o);
+                        }
+                        bool removed = false;
 #pragma unroll
-                        for (int s = 0; s < kSurv; s++)
-                            if (s == ns) s_id[s] = cand, s_o[s] = o, s_len[s] = lenb, s_t[s] = t;
-                        ns++;
+                        for (int s = 0; s < kSurv; s++) {
+                            if (s < ns && s_o[s] > 0 && o >= s_o[s] &&
+                                (FAST || (int64_t) s_len[s] + (int64_t) (o - s_o[s]) - (int64_t) lenb >= 0) &&
+                                ((t ^ s_t[s]) >> (64u - 2u * s_o[s])) == 0)
+                                removed = true;
+                        }
+                        want = !removed;
+                    }
+                } else {
+                    q_id[k * 32] = kNone;  // too short for this length: not an arrival
+                }
+            }
+            if (__any_sync(kFull, want)) {
+                if (want) {
+                    if (verify_own_prefix(R, own, cand, o, L)) {
+                        if (ns >= kSurv) {
+                            hard = true;
+                        } else {
+#pragma unroll
+                            for (int s = 0; s < kSurv; s++)
+                                if (s == ns) s_id[s] = cand, s_o[s] = o, s_len[s] = lenb, s_t[s] = t;
+                            ns++;
+                        }
+                    } else {
+                        q_id[k * 32] = kNone;  // seed matched, overlap did not: not an arrival
                     }
                 }
             }
         }
-        // in-neighbours from phase 1 (row of the transposed graph): kept unless a surviving arrival removes them
+
+        // ---- in-neighbours from phase 1 (row of the transposed graph): kept unless a surviving arrival removes them
         uint32_t rowmask = 0;
         if (part && !hard) {
             for (uint32_t r = 0; r < deg; r++) {
-                const RevEntry en = rev[r0 + r];
-                const uint32_t a = (uint32_t) en.b, oa = (uint32_t) en.o;
-                for (int k = 0; k < n_ids; k++)
-                    if (ids[k * kTpr] == a) hard = true;  // the same read twice for one target: generic path
-                if (n_ids >= kIdCap) {
-                    hard = true;
-                    break;
-                }
-                ids[n_ids * kTpr] = a;
-                n_ids++;
-                const uint64_t ta = en.t;
-                const uint32_t lena = UNIFORM ? lenc : R.len[a];
+                const RevEntry en = row[r];
+                const uint32_t oa = (uint32_t) en.o;
+                const uint32_t lena = FAST ? lenc : R.len[(uint32_t) en.b];
                 bool removed = false;
 #pragma unroll
                 for (int s = 0; s < kSurv; s++) {
                     if (s < ns && s_o[s] > 0 && oa >= s_o[s] &&
-                        (UNIFORM || (int64_t) s_len[s] + (int64_t) (oa - s_o[s]) - (int64_t) lena >= 0) &&
-                        ((ta ^ s_t[s]) >> (64u - 2u * s_o[s])) == 0)
+                        (FAST || (int64_t) s_len[s] + (int64_t) (oa - s_o[s]) - (int64_t) lena >= 0) &&
+                        ((en.t ^ s_t[s]) >> (64u - 2u * s_o[s])) == 0)
                         removed = true;
                 }
                 if (!removed) rowmask |= 1u << r;
             }
-            // a surviving arrival whose read occurs a second time among the candidates (same-id replacement rule)
-            for (int k = 0; k < n_ids; k++) {
-                const uint32_t v = ids[k * kTpr];
-                int cnt = 0;
+            // Same-id replacement rule (an arrival of read x also removes any older entry of x): whatever is about
+            // to be emitted must be the only occurrence of its read among the arrivals and the row, else the
+            // generic kernel decides.  Entries that are dropped anyway need no such check.
+            for (uint32_t m = rowmask; m; m &= m - 1) {
+                const uint32_t r = (uint32_t) __ffs(m) - 1u;
+                const uint32_t a = (uint32_t) row[r].b;
+                for (int k = 0; k < qn; k++)
+                    if (q_id[k * 32] == a) hard = true;
+                for (uint32_t r2 = 0; r2 < deg; r2++)
+                    if (r2 != r && (uint32_t) row[r2].b == a) hard = true;
+            }
+            if (ns) {
+                int cnt[kSurv];
 #pragma unroll
-                for (int s = 0; s < kSurv; s++) cnt += (s < ns && s_id[s] == v) ? 1 : 0;
-                if (cnt) {
-                    for (int k2 = k + 1; k2 < n_ids; k2++)
-                        if (ids[k2 * kTpr] == v) hard = true;
+                for (int s = 0; s < kSurv; s++) cnt[s] = 0;
+                for (int k = 0; k < qn; k++) {
+                    const uint32_t v = q_id[k * 32];
+#pragma unroll
+                    for (int s = 0; s < kSurv; s++) cnt[s] += (s < ns && s_id[s] == v) ? 1 : 0;
                 }
+#pragma unroll
+                for (int s = 0; s < kSurv; s++)
+                    if (cnt[s] > 1) hard = true;
             }
         }
-        // emit: one atomicAdd on the edge counter per warp
-        uint32_t n_out = (part && !hard) ? (uint32_t) ns + __popc(rowmask) : 0u;
+
+        // ---- emit: one atomicAdd on the edge counter per warp
+        const uint32_t n_out = (part && !hard) ? (uint32_t) ns + __popc(rowmask) : 0u;
         uint32_t incl = n_out;
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t y = __shfl_up_sync(kFull, incl, d);
@@ -439,7 +686,7 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
                 }
             }
             for (uint32_t m = rowmask; m; m &= m - 1) {
-                const RevEntry en = rev[r0 + (__ffs(m) - 1)];
+                const RevEntry en = row[__ffs(m) - 1];
                 if (pos < out.edge_cap) {
                     out.triples[3 * pos] = en.b;
                     out.triples[3 * pos + 1] = (int32_t) c;
@@ -453,59 +700,51 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
     }
 }
 
-inline int smem_words_per_read(uint32_t max_len_nt, int need_words) {
-    int w = (int) ((max_len_nt + 15u) >> 4);
-    if (w > kOwnWords) w = kOwnWords;
-    if (need_words > 0 && w > need_words) w = need_words;
-    return (w + 2) | 1;  // two pad words; odd stride: lanes of a warp fall into distinct banks
+inline int stride_words(int words) {
+    return (words + 2) | 1;  // two pad words; odd stride: lanes of a warp fall into distinct banks
 }
 
 }  // namespace
 
 void launch_phase1_tpr(const ReadsDev &R, const SeedTable &prefix, const PsDev &P, uint32_t max_len_nt, uint32_t lo,
-                       uint32_t hi, int2 *fwd, uint64_t *fwd_t, uint32_t *fwd_pos, uint32_t *indeg, uint32_t *hard_queue,
-                       uint32_t *n_hard, int force_hard, cudaStream_t s, const LaunchCfg &cfg) {
+                       uint32_t hi, const Phase1Out &out, uint32_t *hard_queue, uint32_t *n_hard, int force_hard,
+                       cudaStream_t s, const LaunchCfg &cfg) {
     if (hi <= lo) return;
-    const int wp = smem_words_per_read(max_len_nt, 0);
-    int64_t lmax = (int64_t) P.rs - 1;
-    if (lmax > P.max_l) lmax = P.max_l;
-    if (lmax > (int64_t) max_len_nt) lmax = max_len_nt;
-    if (lmax < 1) lmax = 1;
-    if (lmax > kOwnWords * 16) lmax = kOwnWords * 16;
-    const int nw_max = (int) ((2 * lmax + 31) >> 5);
-    const size_t smem = (size_t) kTpr * wp * sizeof(uint32_t);
-    const int grid = tile_grid(hi - lo, cfg, 6);
-    if (P.uniform_len) {
+    int w = (int) ((max_len_nt + 15u) >> 4);
+    if (w > kOwnWords) w = kOwnWords;
+    const int wp = stride_words(w);
+    const size_t smem = (size_t) (((kWarps * 32 * wp + 3) & ~3) + kWarps * kRing1 * 32 * 10) * sizeof(uint32_t);
+    const int grid = warp_tile_grid(hi - lo, cfg, 8);
+    if (P.uniform_len && !R.word_off) {
         cudaFuncSetAttribute(phase1_tpr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        phase1_tpr_kernel<true><<<grid, kTpr, smem, s>>>(R, prefix, P, lo, hi, wp, nw_max, fwd, fwd_t, fwd_pos, indeg,
-                                                         hard_queue, n_hard, force_hard);
+        phase1_tpr_kernel<true><<<grid, kTpr, smem, s>>>(R, prefix, P, lo, hi, wp, out, hard_queue, n_hard, force_hard);
     } else {
         cudaFuncSetAttribute(phase1_tpr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        phase1_tpr_kernel<false><<<grid, kTpr, smem, s>>>(R, prefix, P, lo, hi, wp, nw_max, fwd, fwd_t, fwd_pos, indeg,
-                                                          hard_queue, n_hard, force_hard);
+        phase1_tpr_kernel<false><<<grid, kTpr, smem, s>>>(R, prefix, P, lo, hi, wp, out, hard_queue, n_hard, force_hard);
     }
     bump(cfg);
 }
 
 void launch_phase2_tpr(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t max_len_nt, uint32_t lo,
-                       uint32_t hi, const uint32_t *rev_off, const RevEntry *rev, const Phase2Out &out, int force_hard,
-                       cudaStream_t s, const LaunchCfg &cfg) {
+                       uint32_t hi, const RowsView &rows, const Phase2Out &out, int force_hard, cudaStream_t s,
+                       const LaunchCfg &cfg) {
     if (hi <= lo) return;
     int64_t lmax = P.max_l;
     if (lmax > (int64_t) max_len_nt) lmax = max_len_nt;
     if (lmax < 1) lmax = 1;
-    const int nw_max = (int) ((2 * lmax + 31) >> 5);
-    const int wp = smem_words_per_read(max_len_nt, nw_max);
-    const size_t smem = (size_t) kTpr * (wp + kIdCap) * sizeof(uint32_t);
-    const int grid = tile_grid(hi - lo, cfg, 5);
-    if (P.uniform_len) {
+    int w = (int) ((2 * lmax + 31) >> 5);  // words of the longest prefix that takes part
+    const int have = (int) ((max_len_nt + 15u) >> 4);
+    if (w > have) w = have;
+    const int wp = stride_words(w);
+    const size_t smem = (size_t) (((kWarps * 32 * wp + 3) & ~3) + kWarps * (kRing2 * 2 * 32 * 4) +
+                                  kWarps * (kQ2 * 32 * 3 + kQ2 * 32 / 2)) * sizeof(uint32_t);
+    const int grid = warp_tile_grid(hi - lo, cfg, 4);
+    if (P.uniform_len && !R.word_off) {
         cudaFuncSetAttribute(phase2_tpr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        phase2_tpr_kernel<true><<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, wp, nw_max, rev_off, rev, out,
-                                                         force_hard);
+        phase2_tpr_kernel<true><<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, wp, rows, out, force_hard);
     } else {
         cudaFuncSetAttribute(phase2_tpr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        phase2_tpr_kernel<false><<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, wp, nw_max, rev_off, rev, out,
-                                                          force_hard);
+        phase2_tpr_kernel<false><<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, wp, rows, out, force_hard);
     }
     bump(cfg);
 }

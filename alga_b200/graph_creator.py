@@ -147,6 +147,8 @@ class GraphCreatorPrefSuf:
             lib.alga_gpu_free_csr(C.byref(csr))
         self.timing = {k: getattr(tm, k) for k, _ in _lib.Timing._fields_ if k != "stage_ms"}
         self.timing["stage_ms"] = dict(zip(("index", "phase1", "transpose", "phase2", "csr"), list(tm.stage_ms)[:5]))
+        self.timing["n_row_overflow"] = int(tm.stage_ms[5])
+        self.timing["n_hard_sources"] = int(tm.stage_ms[6])
         return self.graph
 
     def clear(self):

@@ -114,6 +114,8 @@ class PrefSufPlan:
         _lib.check(self.lib.alga_ps_plan_stats(self._h, C.byref(tm)))
         d = {k: getattr(tm, k) for k, _ in _lib.Timing._fields_ if k != "stage_ms"}
         d["stage_ms"] = dict(zip(("index", "phase1", "transpose", "phase2", "csr"), list(tm.stage_ms)[:5]))
+        d["n_row_overflow"] = int(tm.stage_ms[5])
+        d["n_hard_sources"] = int(tm.stage_ms[6])
         return d
 
     # ---- stages (sharded runs) ------------------------------------------------------------------

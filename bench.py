@@ -254,7 +254,7 @@ def run_ours(args):
         step()
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    stage_acc, launches = {}, 0
+    stage_acc, launches, diag = {}, 0, {}
     clocks.start()
     barrier()
     wall0 = time.perf_counter()
@@ -267,6 +267,7 @@ def run_ours(args):
         b.record()
         st = step_stats()
         launches += int(st["kernel_launches"])
+        diag = {k: st[k] for k in ("n_spilled_targets", "n_row_overflow", "n_hard_sources") if k in st}
         for k, v in st["stage_ms"].items():
             stage_acc[k] = stage_acc.get(k, 0.0) + float(v)
     barrier()
@@ -330,7 +331,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (traffic or {}).get("pipeline_dram_bytes_per_step"), "peak_source": peak_src,
                 "kernel": "whole device pipeline of one step (index + phase1 + transpose + phase2 + csr), per GPU",
-                "alg_bytes_per_node": b_alg, "nodes_per_gpu": nodes_per_gpu, "stage_ms": stages,
+                "alg_bytes_per_node": b_alg, "nodes_per_gpu": nodes_per_gpu, "stage_ms": stages, "diag": diag,
                 "traffic_detail": traffic}
 
     cpu = None

@@ -80,7 +80,9 @@ typedef struct {
     uint64_t n_spilled_targets; /* targets that took the global-memory list path */
     /* CUDA-event time of each stage of alga_ps_plan_run on its stream (sums to ~device_ms):
      * [0] seed index build, [1] phase 1 (L < rs), [2] transpose of the phase-1 graph,
-     * [3] phase 2 (L >= rs, transitive reduction), [4] CSR assembly, [5..7] reserved (0). */
+     * [3] phase 2 (L >= rs, transitive reduction), [4] CSR assembly; diagnostics (counts, not times): [5] phase-1
+     * edges that overflowed their fixed-capacity row, [6] source reads that took the generic phase-1 kernel;
+     * [7] reserved (0). */
     double stage_ms[8];
 } alga_timing;
 #define ALGA_STAGE_INDEX 0
