@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libalga_gpu.so")
+LIB_PATH = os.environ.get("ALGA_GPU_LIB") or os.path.join(HERE, "libalga_gpu.so")  # override: A/B builds only
 
 ALGA_OK = 0
 ERRORS = {-1: "ALGA_E_INVALID", -2: "ALGA_E_CUDA", -3: "ALGA_E_NOMEM", -4: "ALGA_E_CAPACITY"}

@@ -32,11 +32,23 @@ namespace {
 
 constexpr int kTpr = 128;     // threads per block = 4 independent warps
 constexpr int kWarps = kTpr / 32;
-constexpr int kQ2 = 20;       // arrivals queued per target in phase 2
+// tuning knobs (scripts/build_variant.sh builds A/B variants with -D...)
+#ifndef ALGA_P1_BLOCKS
+#define ALGA_P1_BLOCKS 6
+#endif
+#ifndef ALGA_P2_BLOCKS
+#define ALGA_P2_BLOCKS 4
+#endif
+#ifndef ALGA_Q2
+#define ALGA_Q2 20
+#endif
+#ifndef ALGA_RING2
+#define ALGA_RING2 3
+#endif
+constexpr int kQ2 = ALGA_Q2;  // arrivals queued per target in phase 2
 constexpr int kSurv = 4;      // surviving arrivals kept in registers per target
 constexpr int kRowFast = 32;  // longest transposed row the fast phase-2 kernel takes
-constexpr int kRing1 = 4;     // buckets in flight per thread, phase 1 (ring index is dynamic: power of two)
-constexpr int kRing2 = 3;     // buckets in flight per thread, phase 2 (ring index is static: the loop is unrolled)
+constexpr int kRing2 = ALGA_RING2;     // buckets in flight per thread in phase 2 (static ring index: the loop is unrolled)
 
 inline int warp_tile_grid(uint64_t n_items, const LaunchCfg &cfg, int blocks_per_sm) {
     uint64_t need = (n_items + kTpr - 1) / kTpr;
@@ -215,24 +227,17 @@ __device__ __forceinline__ bool verify_own_prefix(const ReadsDev &R, const uint3
 // Phase 1 (GraphCreatorPrefSuf.cpp:397-402 in closed form): source read b walks L from min(rs-1, len) downwards
 // and keeps the first 3 confirmed (L, c) -- within one L the larger c first -- = "the last 3 pushes".
 //
-// Shared memory per warp: own reads [32][wp] | bucket ring [kRing1][2][32] x 16 B | tag ring, bucket-id ring
-// [kRing1][32].  Lanes pause once they hold 3 candidates, so their positions in the walk differ: ring index, window
-// and prefetch state are per lane.
+// Lanes pause once they hold 3 candidates, so their positions in the walk differ; with so few lengths per read
+// (about 11 of the 34 possible) a deep prefetch ring mostly fetches buckets nobody tests, so this kernel keeps ONE
+// bucket in flight per lane, in registers.  Shared memory per warp: own reads [32][wp].
 template <bool FAST>
-__global__ void __launch_bounds__(kTpr, 8)
+__global__ void __launch_bounds__(kTpr, ALGA_P1_BLOCKS)
 phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, int wp, Phase1Out out,
                   uint32_t *__restrict__ hard_queue, uint32_t *n_hard, int force_hard) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int per_warp = 32 * wp + kRing1 * 32 * 10;
-    const int own_words = ((kWarps * 32 * wp + 3) & ~3);  // ring chunks stay 16-byte aligned
     uint32_t *wown = smem + wib * 32 * wp;
     const uint32_t *own = wown + lane * wp;
-    uint32_t *ring = smem + own_words + wib * (kRing1 * 32 * 10);  // [slot][half][lane] x 4 words
-    uint32_t *ring_tag = ring + kRing1 * 2 * 32 * 4;                // [slot][lane]
-    uint32_t *ring_bk = ring_tag + kRing1 * 32;
-    (void) per_warp;
-    const uint64_t pol = l2_evict_last_policy();
     const uint64_t n_tiles = ((uint64_t) (hi - lo) + 31) / 32;
     const uint64_t warp_id = (uint64_t) blockIdx.x * kWarps + wib, n_warps = (uint64_t) gridDim.x * kWarps;
     for (uint64_t tile = warp_id; tile < n_tiles; tile += n_warps) {
@@ -259,66 +264,49 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
 #pragma unroll
         for (int k = 0; k < kSmallEdgesKept; k++) sc[k] = kNone, so[k] = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) pc[k] = kNone, pl[k] = 0;
+        for (int k = 0; k < 4; k++) pc[k] = 0, pl[k] = 0;
 
-        // walk state: Lc = next length to test (its bucket is, or will be, in ring slot it % kRing1),
-        // Lp = next length to prefetch, (w0, w1, w2, sh, wb) = register window at Lp
-        int32_t Lc = l_hi, Lp = l_hi;
-        int it = 0;
+        // probe state: the bucket of length `Lc` is in flight in e[]
+        int32_t Lc = l_hi;
         bool more = active;
-        uint32_t w0 = 0, w1 = 0, w2 = 0, sh = 0;
+        uint32_t e[8], tag = 0, bk = 0, w0 = 0, w1 = 0, w2 = 0, sh = 0;
         int wb = 0;
-        if (active) {
-            const uint32_t p = 2u * (lenb - (uint32_t) Lp);
+        if (more) {
+            const uint32_t p = 2u * (lenb - (uint32_t) Lc);
             wb = (int) (p >> 5);
             sh = p & 31u;
             w0 = own[wb], w1 = own[wb + 1], w2 = own[wb + 2];
+            const uint64_t h = mix64(window_key(w0, w1, w2, sh) & P.seed_mask);
+            tag = tag_of(T, h);
+            bk = bucket_of(h, T.n_buckets);
+            load_bucket(T.slots + (uint64_t) bk * kSlotsPerBucket, e);
         }
-        auto prefetch = [&](int slot) {  // bucket of length Lp -> ring slot, then slide the window one nucleotide
-            if (active && Lp >= P.lmin) {
-                const uint64_t h = mix64(window_key(w0, w1, w2, sh) & P.seed_mask);
-                const uint32_t bk = bucket_of(h, T.n_buckets);
-                ring_tag[slot * 32 + lane] = tag_of(T, h);
-                ring_bk[slot * 32 + lane] = bk;
-                cp_async_bucket(ring + ((slot * 2) * 32 + lane) * 4, ring + ((slot * 2 + 1) * 32 + lane) * 4,
-                                T.slots + (uint64_t) bk * kSlotsPerBucket, pol);
-                Lp--;
-                sh += 2u;
-                if (sh == 32u) {
-                    sh = 0u;
-                    wb++;
-                    w0 = w1, w1 = w2, w2 = own[wb + 2];
-                }
-            }
-            cp_async_commit();
-        };
-#pragma unroll
-        for (int j = 0; j < kRing1; j++) prefetch(j);
-
         while (true) {
             // ---- probe until every lane has 3 candidates (confirmed + pending) or ran out of lengths
             while (true) {
                 const bool need = more && !hard && conf + np < kSmallEdgesKept;
                 if (!__any_sync(kFull, need)) break;
                 if (need) {
-                    const int slot = it & (kRing1 - 1);
-                    cp_async_wait_group<kRing1 - 1>();
-                    uint32_t e[8];
-                    {
-                        const uint4 a = *reinterpret_cast<const uint4 *>(ring + ((slot * 2) * 32 + lane) * 4);
-                        const uint4 c = *reinterpret_cast<const uint4 *>(ring + ((slot * 2 + 1) * 32 + lane) * 4);
-                        e[0] = a.x, e[1] = a.y, e[2] = a.z, e[3] = a.w, e[4] = c.x, e[5] = c.y, e[6] = c.z, e[7] = c.w;
-                    }
-                    const uint32_t tag = ring_tag[slot * 32 + lane];
                     const uint32_t m = bucket_min(e, tag);
                     uint32_t c0 = kNone, c1 = kNone;
                     int n = 0;
-                    if (m <= T.id_mask || e[7] != kEmptySlot) probe_matches(T, e, tag, ring_bk[slot * 32 + lane], m, c0, c1, n);
-                    prefetch(slot);
+                    if (m <= T.id_mask || e[7] != kEmptySlot) probe_matches(T, e, tag, bk, m, c0, c1, n);
                     const int32_t L = Lc;
-                    it++;
                     Lc--;
-                    more = Lc >= P.lmin;
+                    if (Lc >= P.lmin) {  // slide the window by one nucleotide, next bucket goes in flight
+                        sh += 2u;
+                        if (sh == 32u) {
+                            sh = 0u;
+                            wb++;
+                            w0 = w1, w1 = w2, w2 = own[wb + 2];
+                        }
+                        const uint64_t h = mix64(window_key(w0, w1, w2, sh) & P.seed_mask);
+                        tag = tag_of(T, h);
+                        bk = bucket_of(h, T.n_buckets);
+                        load_bucket(T.slots + (uint64_t) bk * kSlotsPerBucket, e);
+                    } else {
+                        more = false;
+                    }
                     if (n > 2) {
                         hard = true;
                     } else if (n) {
@@ -340,29 +328,57 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
                     }
                 }
             }
-            // ---- confirm the pending candidates, every lane its own
+            // ---- confirm the pending candidates, every lane its own: the words of all of them are requested before
+            // the first compare, so their (random, mostly DRAM) latencies overlap
             const int np_max = warp_max(hard ? 0 : np);
             if (np_max == 0) break;
+            const int nw_max = warp_max(np && !hard ? (2 * pl[0] + 31) >> 5 : 0);
+            uint32_t diff[4] = {0u, 0u, 0u, 0u};
+            for (int k0 = 0; k0 < nw_max; k0 += 4) {
+                uint32_t g[4][4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (k < np_max) {
+                        const bool on = k < np && !hard;
+                        const uint32_t *pcand = read_ptr(R, on ? pc[k] : b);
+                        const int nw = on ? (2 * pl[k] + 31) >> 5 : 0;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) g[k][j] = k0 + j < nw ? __ldg(pcand + k0 + j) : 0u;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (k < np_max && k < np && !hard) {
+                        const uint32_t nbits = 2u * (uint32_t) pl[k], nw = (nbits + 31u) >> 5;
+                        const uint32_t o2 = 2u * (lenb - (uint32_t) pl[k]), shv = o2 & 31u;
+                        const uint32_t *ow = own + (o2 >> 5);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint32_t w = (uint32_t) (k0 + j);
+                            if (w < nw) {
+                                uint32_t x = __funnelshift_r(ow[w], ow[w + 1], shv) ^ g[k][j];
+                                if (w == nw - 1 && (nbits & 31u)) x &= (1u << (nbits & 31u)) - 1u;
+                                diff[k] |= x;
+                            }
+                        }
+                    }
+                }
+            }
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                if (k < np_max) {
-                    const bool want = k < np && !hard && conf < kSmallEdgesKept;
-                    if (want) {
-                        const uint32_t cand = pc[k];
-                        const int32_t L = pl[k];
-                        const uint32_t o = lenb - (uint32_t) L;
-                        if (cand != b && (FAST || (int64_t) R.len[cand] >= L) && verify_own_suffix(R, own, cand, o, L)) {
+                if (k < np && !hard && conf < kSmallEdgesKept) {
+                    const uint32_t cand = pc[k];
+                    const int32_t L = pl[k];
+                    if (diff[k] == 0 && cand != b && (FAST || (int64_t) R.len[cand] >= L)) {
 #pragma unroll
-                            for (int q = 0; q < kSmallEdgesKept; q++)
-                                if (q == conf) sc[q] = cand, so[q] = o;
-                            conf++;
-                        }
+                        for (int q = 0; q < kSmallEdgesKept; q++)
+                            if (q == conf) sc[q] = cand, so[q] = lenb - (uint32_t) L;
+                        conf++;
                     }
                 }
             }
             np = 0;
         }
-        cp_async_wait_all();  // prefetches beyond the last tested length: land before the ring is reused
 
         // ---- emit
         if (out.mode == 0) {
@@ -433,7 +449,7 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
 // Shared memory per warp: own reads [32][wp] | bucket ring [kRing2][2][32] x 16 B | queue: ids [kQ2][32],
 // heads [kQ2][2][32], lengths [kQ2][32] (u16).
 template <bool FAST>
-__global__ void __launch_bounds__(kTpr, 4)
+__global__ void __launch_bounds__(kTpr, ALGA_P2_BLOCKS)
 phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, int wp, RowsView rows, Phase2Out out,
                   int force_hard) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -713,8 +729,8 @@ void launch_phase1_tpr(const ReadsDev &R, const SeedTable &prefix, const PsDev &
     int w = (int) ((max_len_nt + 15u) >> 4);
     if (w > kOwnWords) w = kOwnWords;
     const int wp = stride_words(w);
-    const size_t smem = (size_t) (((kWarps * 32 * wp + 3) & ~3) + kWarps * kRing1 * 32 * 10) * sizeof(uint32_t);
-    const int grid = warp_tile_grid(hi - lo, cfg, 8);
+    const size_t smem = (size_t) kWarps * 32 * wp * sizeof(uint32_t);
+    const int grid = warp_tile_grid(hi - lo, cfg, ALGA_P1_BLOCKS);
     if (P.uniform_len && !R.word_off) {
         cudaFuncSetAttribute(phase1_tpr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         phase1_tpr_kernel<true><<<grid, kTpr, smem, s>>>(R, prefix, P, lo, hi, wp, out, hard_queue, n_hard, force_hard);
@@ -738,7 +754,7 @@ void launch_phase2_tpr(const ReadsDev &R, const SeedTable &suffix, const PsDev &
     const int wp = stride_words(w);
     const size_t smem = (size_t) (((kWarps * 32 * wp + 3) & ~3) + kWarps * (kRing2 * 2 * 32 * 4) +
                                   kWarps * (kQ2 * 32 * 3 + kQ2 * 32 / 2)) * sizeof(uint32_t);
-    const int grid = warp_tile_grid(hi - lo, cfg, 4);
+    const int grid = warp_tile_grid(hi - lo, cfg, ALGA_P2_BLOCKS);
     if (P.uniform_len && !R.word_off) {
         cudaFuncSetAttribute(phase2_tpr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         phase2_tpr_kernel<true><<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, wp, rows, out, force_hard);
