@@ -43,16 +43,22 @@ class Graph:
         return list(zip(self.nbr[s:e].tolist(), self.off[s:e].tolist()))
 
 
-def _reads_struct(reads: ReadSet, stride_hint: bool = True) -> _lib.Reads:
+def fixed_stride(reads: ReadSet) -> int:
+    """Words per read if every read starts at a multiple of the same word count (else 0)."""
     n = reads.n
-    stride = 0
-    word_off = reads.word_off.ctypes.data
-    if stride_hint and n:
-        # fixed-stride layout lets the library skip the offset array (alga_gpu.h: word_off == NULL)
-        w = int(reads.word_off[1] - reads.word_off[0]) if n else 0
-        if w > 0 and np.array_equal(reads.word_off, np.arange(n + 1, dtype=np.uint64) * np.uint64(w)):
-            stride, word_off = w, None
-    return _lib.Reads(n, reads.words.ctypes.data, word_off, stride, reads.len_nt.ctypes.data,
+    w = int(reads.word_off[1] - reads.word_off[0]) if n else 0
+    if w > 0 and np.array_equal(reads.word_off, np.arange(n + 1, dtype=np.uint64) * np.uint64(w)):
+        return w
+    return 0
+
+
+def _reads_struct(reads: ReadSet, stride: int | None = None) -> _lib.Reads:
+    """``stride``: result of ``fixed_stride`` if the caller already knows it (it costs a pass over word_off)."""
+    if stride is None:
+        stride = fixed_stride(reads)
+    # fixed-stride layout lets the library skip the offset array (alga_gpu.h: word_off == NULL)
+    word_off = None if stride else reads.word_off.ctypes.data
+    return _lib.Reads(reads.n, reads.words.ctypes.data, word_off, stride, reads.len_nt.ctypes.data,
                       reads.align_from.ctypes.data, reads.align_to.ctypes.data)
 
 
@@ -117,6 +123,7 @@ class GraphCreatorPrefSuf:
             self.alignFrom = reads.align_from.copy()
             self.alignTo = reads.align_to.copy()
         self.reads = reads
+        self._stride = fixed_stride(reads)
         self.graph: Graph | None = None
         self.timing: dict | None = None
 
@@ -136,8 +143,9 @@ class GraphCreatorPrefSuf:
     def startAlignmentGraphCreation(self) -> Graph:
         """GraphCreatorPrefSuf.cpp:73-126 + Graph::retainOnlySmallestOffset (main.cpp:291)."""
         lib = _lib.load()
-        rs = ReadSet(self.reads.words, self.reads.word_off, self.reads.len_nt, self.alignFrom, self.alignTo)
-        st = _reads_struct(rs)
+        r = self.reads
+        st = _lib.Reads(r.n, r.words.ctypes.data, None if self._stride else r.word_off.ctypes.data, self._stride,
+                        r.len_nt.ctypes.data, self.alignFrom.ctypes.data, self.alignTo.ctypes.data)
         csr = _lib.Csr()
         tm = _lib.Timing()
         _lib.check(lib.alga_gpu_prefsuf_build(C.byref(st), C.byref(self.params), C.byref(csr), C.byref(tm)))

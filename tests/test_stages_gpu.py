@@ -139,3 +139,40 @@ def test_full_config2_properties(gpu):
 def _codes(words, ln):
     j = np.arange(ln)
     return (words[j >> 4] >> ((j & 15) * 2).astype(np.uint32)) & 3
+
+
+@pytest.mark.parametrize("name", ["cfg2_small", "cfg5_small", "varlen_dups", "periodic_dups", "rs_above_maxl", "flags"])
+@pytest.mark.parametrize("row_cap", [1, 3])
+def test_row_overflow_paths_match_oracle(gpu, monkeypatch, name, row_cap):
+    """Phase 1 writes into fixed-capacity rows of the transposed graph.  A tiny capacity (ALGA_PS_ROW_CAP, read when
+    the plan is created) pushes edges into the overflow list: short lists are scanned by the generic phase-2 kernel,
+    long ones (> 2048 entries) trigger the CSR rebuild on the device."""
+    import torch
+
+    from alga_b200.plan import DeviceReads, PrefSufPlan
+
+    monkeypatch.setenv("ALGA_PS_ROW_CAP", str(row_cap))
+    rs, lmin, rsmin, mo = build_case(name)
+    plan = PrefSufPlan(lmin, rsmin, mo, device=0)
+    plan.bind(DeviceReads(rs, torch.device("cuda", 0)))
+    plan.run()
+    st = plan.stats()
+    assert st["n_row_overflow"] > 0
+    assert np.array_equal(plan.result_host().edges(), oracle.prefsuf(rs, lmin, rsmin, mo))
+    plan.close()
+
+
+def test_row_overflow_list_regrows(gpu, monkeypatch):
+    """More overflow entries than the overflow list holds: the build reruns with a worst-case list."""
+    import torch
+
+    from alga_b200.plan import DeviceReads, PrefSufPlan
+
+    monkeypatch.setenv("ALGA_PS_ROW_CAP", "1")
+    w = synth.make_config("cfg2", scale=0.05)  # ~130 k nodes, ~250 k overflow entries > n / 8 + 65536
+    plan = PrefSufPlan(w.params.min_overlap, w.params.rs_min_overlap, 0, device=0)
+    plan.bind(DeviceReads(w.reads, torch.device("cuda", 0)))
+    plan.run()
+    assert plan.stats()["n_row_overflow"] > w.reads.n // 8 + 65536
+    assert np.array_equal(plan.result_host().edges(), oracle.prefsuf(w.reads, w.params.min_overlap, w.params.rs_min_overlap))
+    plan.close()
