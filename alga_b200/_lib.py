@@ -45,6 +45,11 @@ class Timing(C.Structure):
                 ("kernel_launches", C.c_uint64), ("n_spilled_targets", C.c_uint64), ("stage_ms", C.c_double * 8)]
 
 
+class Shard(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("n_shard", C.c_uint32), ("n_total", C.c_uint32),
+                ("peer_ws", C.c_void_p * 8)]
+
+
 class VerifyParams(C.Structure):
     _fields_ = [("max_offset_pct", C.c_int32), ("min_offset", C.c_int32), ("min_overlap_area", C.c_int32),
                 ("threshold_pct", C.c_int32), ("same_ends", C.c_int32), ("device", C.c_int32)]
@@ -65,6 +70,12 @@ SYMBOLS = {
     "alga_ps_stage_phase2": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint64, _P, C.POINTER(_P),
                                        C.POINTER(C.c_uint64)]),
     "alga_ps_stage_csr": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint64, C.c_int, _P]),
+    "alga_ps_plan_bind_reads_uniform": (C.c_int, [_P, C.POINTER(Reads), C.c_uint32]),
+    "alga_ps_stage_index_range": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_int, _P]),
+    "alga_ps_shard_ws_bytes": (C.c_uint64, [C.c_uint32, C.c_int32]),
+    "alga_ps_shard_phase1": (C.c_int, [_P, C.POINTER(Shard), _P]),
+    "alga_ps_shard_phase2": (C.c_int, [_P, C.POINTER(Shard), _P]),
+    "alga_ps_shard_csr": (C.c_int, [_P, C.POINTER(Shard), _P]),
     "alga_ps_plan_result_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64)]),
     "alga_ps_plan_result_rows": (C.c_uint32, [_P]),
     "alga_ps_plan_result_host": (C.c_int, [_P, C.POINTER(Csr)]),

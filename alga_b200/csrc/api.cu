@@ -104,7 +104,7 @@ struct Counters {
     uint32_t n_spill;
     uint32_t n_big;
     uint32_t n_hard1;  // source reads phase 1's fast kernel handed to the generic kernel
-    uint32_t pad;
+    uint32_t rev_overflow;  // the CSR rebuild of the transposed graph did not fit (sharded runs only)
 };
 
 constexpr uint32_t kRowCapDefault = 16;  // entries per target in the fixed-capacity rows of the transposed phase-1 graph
@@ -239,7 +239,7 @@ void size_table(SeedTable &t, uint32_t entries, uint32_t n_reads) {
     t.tag_mask = (uint32_t) ((1ull << (32 - bits)) - 1ull);
 }
 
-int stage_index(alga_ps_plan *plan, cudaStream_t s) {
+int stage_index_begin(alga_ps_plan *plan, cudaStream_t s) {
     if (!plan->bound) return fail(ALGA_E_INVALID, "no read set bound to the plan");
     size_table(plan->Tp, plan->stats.n_prefix, plan->R.n);
     size_table(plan->Ts, plan->stats.n_suffix, plan->R.n);
@@ -250,14 +250,20 @@ int stage_index(alga_ps_plan *plan, cudaStream_t s) {
     plan->Ts.slots = plan->ts.as<uint32_t>();
     CK(cudaMemsetAsync(plan->tp.p, 0xFF, bp, s));
     CK(cudaMemsetAsync(plan->ts.p, 0xFF, bs, s));
-    launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, s, plan->cfg);
+    return ALGA_OK;
+}
+
+int stage_index(alga_ps_plan *plan, cudaStream_t s) {
+    CKR(stage_index_begin(plan, s));
+    launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, 0, plan->R.n, s, plan->cfg);
     CK(cudaGetLastError());
     plan->index_valid = true;
     return ALGA_OK;
 }
 
 // phase 2 (+ spill path) for targets [lo,hi) given rev rows; leaves triples in plan->triples, count in h_counters
-int run_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const RowsView &rows, uint32_t *outdeg, cudaStream_t s) {
+int run_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const RowsView &rows, uint32_t *outdeg, cudaStream_t s,
+               const ShardOut &sh = ShardOut{}) {
     const uint32_t n = hi - lo;
     int list_cap = plan->params.list_cap > 0 ? plan->params.list_cap : 64;
     if (list_cap > 2048) list_cap = 2048;
@@ -270,7 +276,7 @@ int run_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const RowsView &row
         CK(cudaMemsetAsync(&dc->n_spill, 0, 4, s));
         if (outdeg) CK(cudaMemsetAsync(outdeg, 0, (size_t) plan->R.n * 4, s));
         Phase2Out out{plan->triples.as<int32_t>(), &dc->n_edges, edge_cap, outdeg, plan->spill_queue.as<uint32_t>(),
-                      &dc->n_spill};
+                      &dc->n_spill, sh};
         if (plan->params.list_cap > 0)  // testing: generic kernel with a tiny on-chip list
             launch_phase2(plan->R, plan->Ts, plan->P, lo, hi, rows, list_cap, out, s, plan->cfg);
         else
@@ -313,6 +319,7 @@ int build_rev_from_counts(alga_ps_plan *plan, uint32_t n_targets, cudaStream_t s
     return ALGA_OK;
 }
 
+// outdeg_ready: plan->outdeg already holds the row sizes, indexed by global read id
 int stage_csr(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int32_t *triples, uint64_t n_tr, int swap,
               bool outdeg_ready, cudaStream_t s) {
     const uint32_t n = hi - lo;
@@ -492,7 +499,7 @@ int alga_ps_stage_phase1(alga_ps_plan *plan, uint32_t lo, uint32_t hi, void *str
     CK(cudaMemsetAsync(&dc->n_hard1, 0, 4, s));
     CK(cudaMemsetAsync(&dc->n_list, 0, 4, s));
     const int force = plan->params.flags & ALGA_PS_FORCE_GENERIC;
-    Phase1Out p1{1, nullptr, nullptr, 0, plan->list1.as<Edge1>(), &dc->n_list, (uint32_t) max_edges};
+    Phase1Out p1{1, nullptr, nullptr, 0, plan->list1.as<Edge1>(), &dc->n_list, (uint32_t) max_edges, 0u, ShardOut{}};
     launch_phase1_tpr(plan->R, plan->Tp, plan->P, plan->stats.max_len, lo, hi, p1, plan->hard1.as<uint32_t>(),
                       &dc->n_hard1, force, s, plan->cfg);
     launch_phase1_queue(plan->R, plan->Tp, plan->P, force ? n : (n < 4096 ? n : 4096), plan->hard1.as<uint32_t>(),
@@ -539,6 +546,191 @@ int alga_ps_stage_csr(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int32_
     return stage_csr(plan, lo, hi, triples, n, swap, false, (cudaStream_t) stream);
 }
 
+
+int alga_ps_plan_bind_reads_uniform(alga_ps_plan *plan, const alga_reads *r, uint32_t len_nt) {
+    if (!plan || !r) return fail(ALGA_E_INVALID, "null argument");
+    if (!r->words || !r->len_nt || r->word_off || r->stride_words == 0 || len_nt == 0 || r->n_reads == 0)
+        return fail(ALGA_E_INVALID, "uniform binding needs words, len_nt, a fixed stride and a length");
+    if (r->align_from || r->align_to) return fail(ALGA_E_INVALID, "uniform binding takes no flag arrays");
+    if (r->n_reads > 0x7FFFFFFFu) return fail(ALGA_E_INVALID, "too many reads (ids are int32 in the edge arrays)");
+    CKR(use_device(plan));
+    plan->R.words = r->words;
+    plan->R.word_off = nullptr;
+    plan->R.len = r->len_nt;
+    plan->R.from = plan->R.to = nullptr;
+    plan->R.n = r->n_reads;
+    plan->R.stride = r->stride_words;
+    plan->bound = true;
+    plan->index_valid = false;
+    // no pass over the reads (they may not be resident yet): every read has this length and takes part
+    plan->stats.max_len = plan->stats.min_len = len_nt;
+    plan->stats.n_prefix = plan->stats.n_suffix = r->n_reads;
+    return resolve_params(plan);
+}
+
+int alga_ps_stage_index_range(alga_ps_plan *plan, uint32_t lo, uint32_t hi, int first, void *stream) {
+    if (!plan) return fail(ALGA_E_INVALID, "null plan");
+    if (lo > hi || hi > plan->R.n) return fail(ALGA_E_INVALID, "bad range [%u,%u)", lo, hi);
+    CKR(use_device(plan));
+    cudaStream_t s = (cudaStream_t) stream;
+    if (first) {
+        CKR(stage_index_begin(plan, s));
+        plan->launches = 0;
+    } else if (!plan->Tp.slots) {
+        return fail(ALGA_E_INVALID, "the first range of a build must be inserted with first != 0");
+    }
+    launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, lo, hi, s, plan->cfg);
+    CK(cudaGetLastError());
+    plan->index_valid = true;
+    return ALGA_OK;
+}
+
+// ---- sharded build: exchange through the ranks' workspaces (peer memory over NVLink) -----------------------
+namespace {
+struct ShardLayout {
+    uint64_t cnt1_off, cnt2_off, seg1_off, seg2_off, total;
+    uint32_t cap1, cap2;
+};
+ShardLayout shard_layout(uint32_t n_shard, int world) {
+    ShardLayout L;
+    L.cnt1_off = 0;
+    L.cnt2_off = 64;
+    L.seg1_off = 256;
+    L.cap1 = n_shard * (uint32_t) kSmallEdgesKept;           // worst case: every edge of the rank to one owner
+    L.cap2 = n_shard * (uint32_t) kSmallEdgesKept + 65536u;  // survivors per owner (checked; ALGA_E_CAPACITY beyond)
+    L.seg2_off = (L.seg1_off + (uint64_t) world * L.cap1 * sizeof(Edge1) + 255) & ~255ull;
+    L.total = (L.seg2_off + (uint64_t) world * L.cap2 * 12 + 255) & ~255ull;
+    return L;
+}
+int check_shard(alga_ps_plan *plan, const alga_ps_shard *sh, uint32_t *lo, uint32_t *hi) {
+    if (!plan || !sh) return fail(ALGA_E_INVALID, "null argument");
+    if (sh->world < 1 || sh->world > 8 || sh->rank < 0 || sh->rank >= sh->world)
+        return fail(ALGA_E_INVALID, "bad rank %d / world %d (1..8 GPUs of one box)", sh->rank, sh->world);
+    if (!plan->bound || sh->n_total != plan->R.n) return fail(ALGA_E_INVALID, "n_total does not match the bound read set");
+    if (sh->n_shard == 0 || (uint64_t) sh->n_shard * sh->world < sh->n_total) return fail(ALGA_E_INVALID, "n_shard too small");
+    if ((uint64_t) sh->n_shard * kSmallEdgesKept + 65536u > 0xFFFFFFFFull) return fail(ALGA_E_INVALID, "shard too large");
+    for (int p = 0; p < sh->world; p++)
+        if (!sh->peer_ws[p]) return fail(ALGA_E_INVALID, "null workspace pointer for rank %d", p);
+    if (plan->swap_direction) return fail(ALGA_E_INVALID, "rs_min_overlap beyond the longest read is not supported in sharded runs");
+    const uint64_t l = (uint64_t) sh->rank * sh->n_shard, h = l + sh->n_shard;
+    *lo = (uint32_t) (l < sh->n_total ? l : sh->n_total);
+    *hi = (uint32_t) (h < sh->n_total ? h : sh->n_total);
+    return ALGA_OK;
+}
+}  // namespace
+
+uint64_t alga_ps_shard_ws_bytes(uint32_t n_shard, int32_t world) { return shard_layout(n_shard, world).total; }
+
+int alga_ps_shard_phase1(alga_ps_plan *plan, const alga_ps_shard *sh, void *stream) {
+    uint32_t lo, hi;
+    CKR(check_shard(plan, sh, &lo, &hi));
+    if (!plan->index_valid) return fail(ALGA_E_INVALID, "seed index not built");
+    CKR(use_device(plan));
+    cudaStream_t s = (cudaStream_t) stream;
+    const ShardLayout L = shard_layout(sh->n_shard, sh->world);
+    char *ws = (char *) sh->peer_ws[sh->rank];
+    const uint32_t n = hi - lo;
+    Counters *dc = plan->counters_d.as<Counters>();
+    CKR(plan->hard1.ensure((size_t) (n ? n : 1) * 4));
+    CK(cudaMemsetAsync(ws + L.cnt1_off, 0, 32, s));
+    CK(cudaMemsetAsync(&dc->n_hard1, 0, 4, s));
+    const int force = plan->params.flags & ALGA_PS_FORCE_GENERIC;
+    Phase1Out p1{2, nullptr, nullptr, 0, nullptr, nullptr, 0, 0u,
+                 ShardOut{sh->world, sh->n_shard, (uint32_t *) (ws + L.cnt1_off), ws + L.seg1_off, L.cap1}};
+    launch_phase1_tpr(plan->R, plan->Tp, plan->P, plan->stats.max_len, lo, hi, p1, plan->hard1.as<uint32_t>(), &dc->n_hard1,
+                      force, s, plan->cfg);
+    launch_phase1_queue(plan->R, plan->Tp, plan->P, force ? n : (n < 4096 ? n : 4096), plan->hard1.as<uint32_t>(),
+                        &dc->n_hard1, p1, s, plan->cfg);
+    CK(cudaGetLastError());
+    return ALGA_OK;
+}
+
+int alga_ps_shard_phase2(alga_ps_plan *plan, const alga_ps_shard *sh, void *stream) {
+    uint32_t lo, hi;
+    CKR(check_shard(plan, sh, &lo, &hi));
+    if (!plan->index_valid) return fail(ALGA_E_INVALID, "seed index not built");
+    CKR(use_device(plan));
+    cudaStream_t s = (cudaStream_t) stream;
+    const ShardLayout L = shard_layout(sh->n_shard, sh->world);
+    char *ws = (char *) sh->peer_ws[sh->rank];
+    const uint32_t n = hi - lo;
+    Counters *dc = plan->counters_d.as<Counters>();
+    if (plan->over_cap < kOverScanMax) plan->over_cap = sh->n_shard / 8 + 65536;
+    const uint64_t rev_cap = (uint64_t) (n ? n : 1) * kSmallEdgesKept * 2 + 65536;
+    CKR(plan->rows.ensure((size_t) (n ? n : 1) * plan->row_cap * sizeof(RevEntry)));
+    CKR(plan->over.ensure((size_t) plan->over_cap * sizeof(Edge1)));
+    CKR(plan->indeg.ensure((size_t) (n ? n : 1) * 4));
+    CKR(plan->rev_off.ensure(((size_t) n + 1) * 4));
+    CKR(plan->rev.ensure((size_t) rev_cap * sizeof(RevEntry)));
+    CKR(plan->scan_ws.ensure(scan_workspace_bytes(n)));
+    CK(cudaMemsetAsync(plan->indeg.p, 0, (size_t) (n ? n : 1) * 4, s));
+    CK(cudaMemsetAsync(&dc->n_list, 0, 12, s));  // n_list, n_over, n_spill
+    CK(cudaMemsetAsync(&dc->rev_overflow, 0, 4, s));
+    CK(cudaMemsetAsync(ws + L.cnt2_off, 0, 32, s));
+    // rows of the transposed phase-1 graph for the targets this rank owns, pulled out of every rank's workspace
+    const void *seg[8];
+    const uint32_t *cnt[8];
+    for (int p = 0; p < sh->world; p++) {
+        const char *pw = (const char *) sh->peer_ws[p];
+        seg[p] = pw + L.seg1_off + (uint64_t) sh->rank * L.cap1 * sizeof(Edge1);
+        cnt[p] = (const uint32_t *) (pw + L.cnt1_off) + sh->rank;
+    }
+    Phase1Out rows_out{0, plan->indeg.as<uint32_t>(), plan->rows.as<RevEntry>(), plan->row_cap, plan->over.as<Edge1>(),
+                       &dc->n_over, plan->over_cap, lo, ShardOut{}};
+    launch_pull_rows(seg, cnt, sh->world, L.cap1, n * (uint32_t) kSmallEdgesKept / (uint32_t) sh->world + 1, rows_out, s,
+                     plan->cfg);
+    launch_rebuild_rows_csr(&dc->n_over, plan->over_cap, plan->over.as<Edge1>(), plan->indeg.as<uint32_t>(),
+                            plan->rows.as<RevEntry>(), plan->row_cap, n, plan->rev_off.as<uint32_t>(), plan->rev.as<RevEntry>(),
+                            rev_cap, &dc->rev_overflow, plan->scan_ws.p, s, plan->cfg);
+    CK(cudaGetLastError());
+    const RowsView view{plan->indeg.as<uint32_t>(), plan->rows.as<RevEntry>(), plan->row_cap, &dc->n_over,
+                        plan->over.as<Edge1>(), plan->rev_off.as<uint32_t>(), plan->rev.as<RevEntry>()};
+    const ShardOut so{sh->world > 1 ? sh->world : 2, sh->n_shard, (uint32_t *) (ws + L.cnt2_off), ws + L.seg2_off, L.cap2};
+    CKR(run_phase2(plan, lo, hi, view, nullptr, s, so));
+    if (plan->h_counters->n_over > plan->over_cap) {
+        plan->over_cap = sh->n_shard * (uint32_t) kSmallEdgesKept * 2;
+        return fail(ALGA_E_CAPACITY, "phase-1 overflow list too small; the plan has grown it, run the build again");
+    }
+    if (plan->h_counters->rev_overflow) return fail(ALGA_E_CAPACITY, "transposed phase-1 graph of this shard exceeds its buffer");
+    uint32_t h_cnt2[8];
+    CK(cudaMemcpyAsync(h_cnt2, ws + L.cnt2_off, 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int p = 0; p < sh->world; p++)
+        if (h_cnt2[p] > L.cap2) return fail(ALGA_E_CAPACITY, "%u surviving edges for rank %d exceed the exchange segment (%u)", h_cnt2[p], p, L.cap2);
+    return ALGA_OK;
+}
+
+int alga_ps_shard_csr(alga_ps_plan *plan, const alga_ps_shard *sh, void *stream) {
+    uint32_t lo, hi;
+    CKR(check_shard(plan, sh, &lo, &hi));
+    CKR(use_device(plan));
+    cudaStream_t s = (cudaStream_t) stream;
+    const ShardLayout L = shard_layout(sh->n_shard, sh->world);
+    const uint32_t n = hi - lo;
+    Counters *dc = plan->counters_d.as<Counters>();
+    const void *seg[8];
+    const uint32_t *cnt[8];
+    for (int p = 0; p < sh->world; p++) {
+        const char *pw = (const char *) sh->peer_ws[p];
+        seg[p] = pw + L.seg2_off + (uint64_t) sh->rank * L.cap2 * 12;
+        cnt[p] = (const uint32_t *) (pw + L.cnt2_off) + sh->rank;
+    }
+    CKR(plan->outdeg.ensure((size_t) (plan->R.n ? plan->R.n : 1) * 4));
+    uint64_t cap_local = (uint64_t) n * 2 + 65536;
+    for (int attempt = 0;; attempt++) {
+        CKR(plan->triples.ensure((size_t) cap_local * 12));
+        CK(cudaMemsetAsync(plan->outdeg.as<uint32_t>() + lo, 0, (size_t) (n ? n : 1) * 4, s));
+        launch_pull_triples(seg, cnt, sh->world, L.cap2, n / (uint32_t) sh->world + 1, cap_local, plan->triples.as<int32_t>(),
+                            &dc->n_edges, plan->outdeg.as<uint32_t>(), s, plan->cfg);
+        CK(cudaGetLastError());
+        CKR(read_counters(plan, s));
+        if (plan->h_counters->n_edges <= cap_local) break;
+        if (attempt) return fail(ALGA_E_CAPACITY, "edge buffer overflow persisted");
+        cap_local = plan->h_counters->n_edges + 1024;
+    }
+    return stage_csr(plan, lo, hi, plan->triples.as<int32_t>(), plan->h_counters->n_edges, 0, true, s);
+}
+
 int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
     if (!plan) return fail(ALGA_E_INVALID, "null plan");
     if (!plan->bound) return fail(ALGA_E_INVALID, "no read set bound to the plan");
@@ -567,7 +759,7 @@ int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
         CK(cudaMemsetAsync(&dc->n_list, 0, 12, s));  // n_list, n_over, n_spill
         CK(cudaMemsetAsync(&dc->n_hard1, 0, 4, s));
         Phase1Out p1{0, plan->indeg.as<uint32_t>(), plan->rows.as<RevEntry>(), plan->row_cap, plan->over.as<Edge1>(), &dc->n_over,
-                     plan->over_cap};
+                     plan->over_cap, 0u, ShardOut{}};
         launch_phase1_tpr(plan->R, plan->Tp, plan->P, plan->stats.max_len, 0, n, p1, plan->hard1.as<uint32_t>(), &dc->n_hard1,
                           force, s, plan->cfg);
         launch_phase1_queue(plan->R, plan->Tp, plan->P, force ? n : (n < 4096 ? n : 4096), plan->hard1.as<uint32_t>(),
@@ -576,7 +768,7 @@ int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
         // only when a row overflowed (decided on the device): CSR form of the transposed graph
         launch_rebuild_rows_csr(&dc->n_over, plan->over_cap, plan->over.as<Edge1>(), plan->indeg.as<uint32_t>(),
                                 plan->rows.as<RevEntry>(), plan->row_cap, n, plan->rev_off.as<uint32_t>(), plan->rev.as<RevEntry>(),
-                                plan->scan_ws.p, s, plan->cfg);
+                                (uint64_t) (n ? n : 1) * kSmallEdgesKept, &dc->rev_overflow, plan->scan_ws.p, s, plan->cfg);
         CK(cudaGetLastError());
         CK(cudaEventRecord(plan->ev_stage[2], s));
         // phase 2 with fused out-degree counting (not in the reversed-result corner)

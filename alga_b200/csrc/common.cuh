@@ -55,11 +55,37 @@ struct __align__(8) Edge1 {
     uint64_t t;
 };
 
+// Sharded runs (one process per GPU): what a rank produces for reads owned by another rank is appended to the
+// per-destination segment of the rank's own exchange workspace, which the owner later reads over NVLink.
+struct ShardOut {
+    int world;         // <= 1: not sharded
+    uint32_t n_shard;  // reads owned per rank; owner(id) = min(id / n_shard, world - 1)
+    uint32_t *cnt;     // [world] entries appended per destination (keeps counting past cap: the host checks)
+    void *seg;         // world segments of `cap` entries each
+    uint32_t cap;
+};
+__device__ __forceinline__ uint32_t shard_of(const ShardOut &sh, uint32_t id) {
+    const uint32_t d = id / sh.n_shard;
+    return d < (uint32_t) sh.world ? d : (uint32_t) sh.world - 1u;
+}
+// Warp-aggregated reservation of one slot per valid lane in the segment of its destination (one atomicAdd per
+// distinct destination in the warp).  Every lane of the warp must call it.
+__device__ __forceinline__ uint32_t shard_reserve(const ShardOut &sh, bool valid, uint32_t dest, int lane) {
+    const unsigned grp = __match_any_sync(0xFFFFFFFFu, valid ? dest : (0x80000000u | (uint32_t) lane));
+    const int leader = __ffs(grp) - 1;
+    uint32_t base = 0;
+    if (valid && lane == leader) base = atomicAdd(sh.cnt + dest, (uint32_t) __popc(grp));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    return base + (uint32_t) __popc(grp & ((1u << lane) - 1u));
+}
+
 // Where phase 1 puts its edges (GraphCreatorPrefSuf.cpp:397-402 pushes to G[b]; phase 2 needs them by target c):
 //   mode 0: straight into the row of the target read in the transposed graph -- `row_cap` entries per target,
 //           position = atomicAdd(indeg[c]); entries beyond the capacity go to `list` (then *n_list != 0 and the
 //           rows are rebuilt in CSR form before phase 2);
-//   mode 1: appended to `list` (one warp-aggregated atomicAdd per warp).
+//   mode 1: appended to `list` (one warp-aggregated atomicAdd per warp);
+//   mode 2: appended to the segment of the rank that owns the target read (`sh`, Edge1 entries).
+// `c_base` is subtracted from the target id wherever it indexes rows (sharded: rows cover the rank's own reads).
 struct Phase1Out {
     int mode;
     uint32_t *indeg;
@@ -68,23 +94,36 @@ struct Phase1Out {
     Edge1 *list;
     uint32_t *n_list;
     uint32_t list_cap;
+    uint32_t c_base;
+    ShardOut sh;
 };
 
 // one edge, one thread (generic kernels; the fast kernel aggregates its list appends per warp)
 __device__ __forceinline__ void emit_edge1(const Phase1Out &out, uint32_t b, uint32_t c, uint32_t o, uint64_t t) {
+    if (out.mode == 2) {
+        const uint32_t d = shard_of(out.sh, c);
+        const uint32_t i = atomicAdd(out.sh.cnt + d, 1u);
+        if (i < out.sh.cap) {
+            Edge1 x;
+            x.c = (int32_t) c, x.b = (int32_t) b, x.o = (int32_t) o, x.pad = 0, x.t = t;
+            reinterpret_cast<Edge1 *>(out.sh.seg)[(uint64_t) d * out.sh.cap + i] = x;
+        }
+        return;
+    }
     if (out.mode == 0) {
-        const uint32_t pos = atomicAdd(out.indeg + c, 1u);
+        const uint32_t ci = c - out.c_base;
+        const uint32_t pos = atomicAdd(out.indeg + ci, 1u);
         if (pos < out.row_cap) {
             RevEntry r;
             r.b = (int32_t) b, r.o = (int32_t) o, r.t = t;
-            out.rows[(uint64_t) c * out.row_cap + pos] = r;
+            out.rows[(uint64_t) ci * out.row_cap + pos] = r;
             return;
         }
     }
     const uint32_t i = atomicAdd(out.n_list, 1u);
     if (i < out.list_cap) {
         Edge1 x;
-        x.c = (int32_t) c, x.b = (int32_t) b, x.o = (int32_t) o, x.pad = 0, x.t = t;
+        x.c = (int32_t) (c - out.c_base), x.b = (int32_t) b, x.o = (int32_t) o, x.pad = 0, x.t = t;
         out.list[i] = x;
     }
 }
@@ -233,11 +272,19 @@ __device__ __forceinline__ void insert_seed(const SeedTable &t, uint64_t h, uint
     uint32_t bk = bucket_of(h, t.n_buckets);
     while (true) {
         uint32_t *base = t.slots + (uint64_t) bk * kSlotsPerBucket;
-#pragma unroll
-        for (int s = 0; s < kSlotsPerBucket; s++) {
-            if (base[s] != kEmptySlot) continue;
+        // one look at the whole bucket (L2), then CAS from its first empty slot on: buckets fill front to back
+        const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(base)), b = __ldcg(reinterpret_cast<const uint4 *>(base) + 1);
+        int s = 8;
+        if (a.x == kEmptySlot) s = 0;
+        else if (a.y == kEmptySlot) s = 1;
+        else if (a.z == kEmptySlot) s = 2;
+        else if (a.w == kEmptySlot) s = 3;
+        else if (b.x == kEmptySlot) s = 4;
+        else if (b.y == kEmptySlot) s = 5;
+        else if (b.z == kEmptySlot) s = 6;
+        else if (b.w == kEmptySlot) s = 7;
+        for (; s < kSlotsPerBucket; s++)
             if (atomicCAS(base + s, kEmptySlot, entry) == kEmptySlot) return;
-        }
         bk = (bk + 1 == t.n_buckets) ? 0u : bk + 1;
     }
 }

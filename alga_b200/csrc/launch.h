@@ -23,8 +23,17 @@ void launch_read_stats(const ReadsDev &R, int lmin, int min_offset, ReadStats *d
                        const LaunchCfg &cfg);
 
 // --- seed index -------------------------------------------------------------------------------
-void launch_build_index(const ReadsDev &R, const PsDev &P, SeedTable prefix, SeedTable suffix, cudaStream_t s,
-                        const LaunchCfg &cfg);
+// inserts the reads [lo, hi) (the tables must have been cleared before the first range)
+void launch_build_index(const ReadsDev &R, const PsDev &P, SeedTable prefix, SeedTable suffix, uint32_t lo, uint32_t hi,
+                        cudaStream_t s, const LaunchCfg &cfg);
+
+// --- sharded runs: read what the peers produced for this rank out of their exchange workspaces (NVLink) ----
+// seg[p] / cnt[p]: peer p's segment for this rank and its entry count (device pointers valid in this process)
+void launch_pull_rows(const void *const *seg, const uint32_t *const *cnt, int world, uint32_t cap, uint32_t n_expected,
+                      const Phase1Out &out, cudaStream_t s, const LaunchCfg &cfg);
+void launch_pull_triples(const void *const *seg, const uint32_t *const *cnt, int world, uint32_t cap, uint32_t n_expected,
+                         uint64_t cap_local, int32_t *triples, unsigned long long *n_total, uint32_t *outdeg,
+                         cudaStream_t s, const LaunchCfg &cfg);
 
 // --- phase 1: L in [lmin, min(rs-1, max_l)], keeps the 3 largest (L, c) per source read ----------
 // Edges go where `out` says (common.cuh: rows of the transposed graph, or an edge list), each with its overhang tail
@@ -43,7 +52,8 @@ void launch_edges_to_triples(const Edge1 *list, const uint32_t *n_list, uint64_t
 // only if *n_over > kOverScanMax (tested on the device): CSR form of the transposed graph from fixed rows + overflow list
 void launch_rebuild_rows_csr(const uint32_t *n_over, uint32_t over_cap, const Edge1 *over, uint32_t *indeg,
                              const RevEntry *rows, uint32_t cap, uint32_t n_targets, uint32_t *rev_off, RevEntry *rev,
-                             void *scan_ws, cudaStream_t s, const LaunchCfg &cfg);
+                             uint64_t rev_cap, uint32_t *rev_overflow, void *scan_ws, cudaStream_t s,
+                             const LaunchCfg &cfg);
 
 // --- reversed phase-1 adjacency from exchanged triples (rows by target c in [lo,hi)) ---------------
 // counts -> offsets is done with launch_scan; scatter consumes `cursor` (a copy of the counts).
@@ -61,7 +71,17 @@ struct Phase2Out {
     uint32_t *outdeg;             // nullable, indexed by b (global id)
     uint32_t *spill_queue;        // targets whose list outgrew the on-chip capacity
     uint32_t *n_spill;
+    ShardOut sh;                  // sharded runs (sh.world > 1): triples go to the segment of the owner of b instead
 };
+// one surviving edge, one thread (generic kernels)
+__device__ __forceinline__ void emit_triple_sharded(const ShardOut &sh, int32_t a, int32_t c, int32_t o) {
+    const uint32_t d = shard_of(sh, (uint32_t) a);
+    const uint32_t i = atomicAdd(sh.cnt + d, 1u);
+    if (i < sh.cap) {
+        int32_t *t = reinterpret_cast<int32_t *>(sh.seg) + ((uint64_t) d * sh.cap + i) * 3;
+        t[0] = a, t[1] = c, t[2] = o;
+    }
+}
 // thread-per-target fast kernel (tpr_kernels.cu); everything it cannot take goes to out.spill_queue
 void launch_phase2_tpr(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t max_len_nt, uint32_t lo,
                        uint32_t hi, const RowsView &rows, const Phase2Out &out, int force_hard, cudaStream_t s,

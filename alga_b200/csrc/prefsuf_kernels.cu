@@ -59,9 +59,9 @@ __global__ void read_stats_kernel(ReadsDev R, int lmin, int min_offset, ReadStat
 
 // ------------------------------------------------------------------------------------------------
 // Seed index build: one thread per read, two inserts (prefix side, suffix side).
-__global__ void build_index_kernel(ReadsDev R, PsDev P, SeedTable tp, SeedTable ts) {
-    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < R.n; i += (uint64_t) gridDim.x * blockDim.x) {
-        const uint32_t len = R.len[i];
+__global__ void build_index_kernel(ReadsDev R, PsDev P, SeedTable tp, SeedTable ts, uint32_t lo, uint32_t hi) {
+    for (uint64_t i = (uint64_t) lo + blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < hi; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t len = P.uniform_len ? P.uniform_len : R.len[i];
         if (len == 0 || (int64_t) len < P.lmin) continue;
         const uint32_t *p = read_ptr(R, (uint32_t) i);
         if (flag_to(R, (uint32_t) i)) {
@@ -72,6 +72,52 @@ __global__ void build_index_kernel(ReadsDev R, PsDev P, SeedTable tp, SeedTable 
             const uint64_t w = bits64(p, 2u * (len - (uint32_t) P.seed_nt)) & P.seed_mask;
             insert_seed(ts, mix64(w), (uint32_t) i);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sharded runs: what the other ranks produced for this rank's reads is read straight out of their exchange
+// workspaces over NVLink (peer pointers), no staging copy.
+struct PeerSegs {
+    const void *seg[8];      // peer p's segment for this rank
+    const uint32_t *cnt[8];  // peer p's entry count for this rank
+    uint32_t cap;
+    int world;
+};
+
+// phase-1 edges whose target this rank owns -> rows of the transposed graph (blockIdx.y = peer)
+__global__ void pull_rows_kernel(PeerSegs ps, Phase1Out out) {
+    const int p = blockIdx.y;
+    uint32_t n = *ps.cnt[p];
+    if (n > ps.cap) n = ps.cap;
+    const Edge1 *src = reinterpret_cast<const Edge1 *>(ps.seg[p]);
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const Edge1 e = src[i];
+        emit_edge1(out, (uint32_t) e.b, (uint32_t) e.c, (uint32_t) e.o, e.t);
+    }
+}
+
+// surviving edges whose source this rank owns -> local triples + out-degrees (blockIdx.y = peer)
+__global__ void pull_triples_kernel(PeerSegs ps, uint64_t cap_local, int32_t *__restrict__ triples,
+                                    unsigned long long *n_total, uint32_t *outdeg) {
+    const int p = blockIdx.y;
+    uint64_t base = 0, total = 0;
+    uint32_t n = 0;
+    for (int q = 0; q < ps.world; q++) {
+        uint32_t c = *ps.cnt[q];
+        if (c > ps.cap) c = ps.cap;
+        if (q < p) base += c;
+        if (q == p) n = c;
+        total += c;
+    }
+    if (p == 0 && blockIdx.x == 0 && threadIdx.x == 0) *n_total = total;
+    const int32_t *src = reinterpret_cast<const int32_t *>(ps.seg[p]);
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        if (base + i >= cap_local) break;  // the host sees n_total > cap_local and pulls again into a larger buffer
+        const int32_t a = src[3 * i], c = src[3 * i + 1], o = src[3 * i + 2];
+        int32_t *dst = triples + 3 * (base + i);
+        dst[0] = a, dst[1] = c, dst[2] = o;
+        atomicAdd(outdeg + (uint32_t) a, 1u);  // counted by global id
     }
 }
 
@@ -168,8 +214,13 @@ __global__ void edges_to_triples_kernel(const Edge1 *__restrict__ list, const ui
 // positions by counting indeg[c] down from the row's full size.
 __global__ void rows_to_csr_kernel(const uint32_t *__restrict__ n_over, const uint32_t *__restrict__ indeg,
                                    const RevEntry *__restrict__ rows, uint32_t cap, uint32_t n_targets,
-                                   const uint32_t *__restrict__ rev_off, RevEntry *__restrict__ rev) {
+                                   const uint32_t *__restrict__ rev_off, RevEntry *__restrict__ rev, uint64_t rev_cap,
+                                   uint32_t *rev_overflow) {
     if (*n_over <= kOverScanMax) return;
+    if (rev_off[n_targets] > rev_cap) {  // the host reports ALGA_E_CAPACITY
+        if (blockIdx.x == 0 && threadIdx.x == 0) *rev_overflow = 1u;
+        return;
+    }
     const uint64_t total = (uint64_t) n_targets * cap;
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < total; i += (uint64_t) gridDim.x * blockDim.x) {
         const uint32_t c = (uint32_t) (i / cap), j = (uint32_t) (i - (uint64_t) c * cap);
@@ -177,9 +228,10 @@ __global__ void rows_to_csr_kernel(const uint32_t *__restrict__ n_over, const ui
     }
 }
 __global__ void over_to_csr_kernel(const uint32_t *__restrict__ n_over, uint32_t over_cap, const Edge1 *__restrict__ over,
-                                   uint32_t *indeg, const uint32_t *__restrict__ rev_off, RevEntry *__restrict__ rev) {
+                                   uint32_t *indeg, const uint32_t *__restrict__ rev_off, RevEntry *__restrict__ rev,
+                                   uint32_t n_targets, uint64_t rev_cap) {
     uint32_t n = *n_over;
-    if (n <= kOverScanMax) return;
+    if (n <= kOverScanMax || rev_off[n_targets] > rev_cap) return;
     if (n > over_cap) n = over_cap;  // the host notices the overflow of the overflow list and reruns
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
         const Edge1 e = over[i];
@@ -319,7 +371,7 @@ __device__ __forceinline__ bool load_rev_row(const ReadsDev &R, const RowsView &
             Edge1 e;
             e.c = -1;
             if (base + lane < n_over) e = rows.over[base + lane];
-            const bool mine = (uint32_t) e.c == c;
+            const bool mine = (uint32_t) e.c == ci;  // the list holds row indices
             const unsigned m = __ballot_sync(kFull, mine);
             if (mine) {
                 const uint32_t pos = w + __popc(m & ((1u << lane) - 1u));
@@ -411,7 +463,9 @@ __device__ __forceinline__ bool phase2_target(const ReadsDev &R, const SeedTable
         }
     }
     // emit the surviving in-neighbours of c as forward triples (a, c, offset)
-    if (cnt) {
+    if (cnt && out.sh.world > 1) {
+        for (uint32_t j = lane; j < cnt; j += 32) emit_triple_sharded(out.sh, (int32_t) lst.a[j], (int32_t) c, (int32_t) lst.o[j]);
+    } else if (cnt) {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(out.n_edges, (unsigned long long) cnt);
         base = __shfl_sync(kFull, base, 0);
@@ -682,9 +736,33 @@ void launch_read_stats(const ReadsDev &R, int lmin, int min_offset, ReadStats *d
     bump(cfg);
 }
 
-void launch_build_index(const ReadsDev &R, const PsDev &P, SeedTable prefix, SeedTable suffix, cudaStream_t s,
-                        const LaunchCfg &cfg) {
-    build_index_kernel<<<grid_for(R.n, 256, cfg), 256, 0, s>>>(R, P, prefix, suffix);
+void launch_build_index(const ReadsDev &R, const PsDev &P, SeedTable prefix, SeedTable suffix, uint32_t lo, uint32_t hi,
+                        cudaStream_t s, const LaunchCfg &cfg) {
+    if (hi <= lo) return;
+    build_index_kernel<<<grid_for(hi - lo, 256, cfg), 256, 0, s>>>(R, P, prefix, suffix, lo, hi);
+    bump(cfg);
+}
+
+void launch_pull_rows(const void *const *seg, const uint32_t *const *cnt, int world, uint32_t cap, uint32_t n_expected,
+                      const Phase1Out &out, cudaStream_t s, const LaunchCfg &cfg) {
+    PeerSegs ps{};
+    for (int p = 0; p < world; p++) ps.seg[p] = seg[p], ps.cnt[p] = cnt[p];
+    ps.cap = cap;
+    ps.world = world;
+    dim3 grid((unsigned) grid_for(n_expected ? n_expected : 1, 256, cfg, 4), (unsigned) world);
+    pull_rows_kernel<<<grid, 256, 0, s>>>(ps, out);
+    bump(cfg);
+}
+
+void launch_pull_triples(const void *const *seg, const uint32_t *const *cnt, int world, uint32_t cap, uint32_t n_expected,
+                         uint64_t cap_local, int32_t *triples, unsigned long long *n_total, uint32_t *outdeg,
+                         cudaStream_t s, const LaunchCfg &cfg) {
+    PeerSegs ps{};
+    for (int p = 0; p < world; p++) ps.seg[p] = seg[p], ps.cnt[p] = cnt[p];
+    ps.cap = cap;
+    ps.world = world;
+    dim3 grid((unsigned) grid_for(n_expected ? n_expected : 1, 256, cfg, 4), (unsigned) world);
+    pull_triples_kernel<<<grid, 256, 0, s>>>(ps, cap_local, triples, n_total, outdeg);
     bump(cfg);
 }
 
@@ -707,13 +785,14 @@ void launch_edges_to_triples(const Edge1 *list, const uint32_t *n_list, uint64_t
 
 void launch_rebuild_rows_csr(const uint32_t *n_over, uint32_t over_cap, const Edge1 *over, uint32_t *indeg,
                              const RevEntry *rows, uint32_t cap, uint32_t n_targets, uint32_t *rev_off, RevEntry *rev,
-                             void *scan_ws, cudaStream_t s, const LaunchCfg &cfg) {
+                             uint64_t rev_cap, uint32_t *rev_overflow, void *scan_ws, cudaStream_t s,
+                             const LaunchCfg &cfg) {
     if (!n_targets) return;
     launch_scan_u32(indeg, rev_off, n_targets, scan_ws, s, cfg, n_over);
     rows_to_csr_kernel<<<grid_for((uint64_t) n_targets * cap, 256, cfg), 256, 0, s>>>(n_over, indeg, rows, cap, n_targets,
-                                                                                       rev_off, rev);
-    over_to_csr_kernel<<<grid_for(over_cap < 65536 ? over_cap : 65536, 256, cfg), 256, 0, s>>>(n_over, over_cap, over, indeg,
-                                                                                                rev_off, rev);
+                                                                                       rev_off, rev, rev_cap, rev_overflow);
+    over_to_csr_kernel<<<grid_for(over_cap < 65536 ? over_cap : 65536, 256, cfg), 256, 0, s>>>(
+        n_over, over_cap, over, indeg, rev_off, rev, n_targets, rev_cap);
     bump(cfg);
     bump(cfg);
 }

@@ -385,7 +385,8 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
             if (!hard) {
                 uint32_t pos[kSmallEdgesKept];
 #pragma unroll
-                for (int k = 0; k < kSmallEdgesKept; k++) pos[k] = k < conf ? atomicAdd(out.indeg + sc[k], 1u) : 0u;
+                for (int k = 0; k < kSmallEdgesKept; k++)
+                    pos[k] = k < conf ? atomicAdd(out.indeg + (sc[k] - out.c_base), 1u) : 0u;
 #pragma unroll
                 for (int k = 0; k < kSmallEdgesKept; k++) {
                     if (k < conf) {
@@ -395,15 +396,31 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
                         r.o = (int32_t) so[k];
                         r.t = overhang_tail_own(own, so[k]);
                         if (pos[k] < out.row_cap) {
-                            out.rows[(uint64_t) c * out.row_cap + pos[k]] = r;
+                            out.rows[(uint64_t) (c - out.c_base) * out.row_cap + pos[k]] = r;
                         } else {
                             const uint32_t i = atomicAdd(out.n_list, 1u);
                             if (i < out.list_cap) {
                                 Edge1 x;
-                                x.c = (int32_t) c, x.b = r.b, x.o = r.o, x.pad = 0, x.t = r.t;
+                                x.c = (int32_t) (c - out.c_base), x.b = r.b, x.o = r.o, x.pad = 0, x.t = r.t;
                                 out.list[i] = x;
                             }
                         }
+                    }
+                }
+            }
+        } else if (out.mode == 2) {
+            // sharded: every edge goes to the segment of the rank that owns its target read
+#pragma unroll
+            for (int k = 0; k < kSmallEdgesKept; k++) {
+                const bool valid = !hard && k < conf;
+                if (__any_sync(kFull, valid)) {
+                    const uint32_t d = valid ? shard_of(out.sh, sc[k]) : 0u;
+                    const uint32_t pos = shard_reserve(out.sh, valid, d, lane);
+                    if (valid && pos < out.sh.cap) {
+                        Edge1 x;
+                        x.c = (int32_t) sc[k], x.b = (int32_t) b, x.o = (int32_t) so[k], x.pad = 0;
+                        x.t = overhang_tail_own(own, so[k]);
+                        reinterpret_cast<Edge1 *>(out.sh.seg)[(uint64_t) d * out.sh.cap + pos] = x;
                     }
                 }
             }
@@ -674,6 +691,38 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
             }
         }
 
+        if (out.sh.world > 1) {
+            // ---- emit, sharded: every surviving edge goes to the segment of the rank that owns its source read
+            const bool emit = part && !hard;
+#pragma unroll
+            for (int sidx = 0; sidx < kSurv; sidx++) {
+                const bool valid = emit && sidx < ns;
+                if (__any_sync(kFull, valid)) {
+                    const uint32_t d = valid ? shard_of(out.sh, s_id[sidx]) : 0u;
+                    const uint32_t pos = shard_reserve(out.sh, valid, d, lane);
+                    if (valid && pos < out.sh.cap) {
+                        int32_t *t = reinterpret_cast<int32_t *>(out.sh.seg) + ((uint64_t) d * out.sh.cap + pos) * 3;
+                        t[0] = (int32_t) s_id[sidx], t[1] = (int32_t) c, t[2] = (int32_t) s_o[sidx];
+                    }
+                }
+            }
+            uint32_t m = emit ? rowmask : 0u;
+            while (__any_sync(kFull, m != 0u)) {
+                const bool valid = m != 0u;
+                RevEntry en;
+                en.b = 0, en.o = 0, en.t = 0;
+                if (valid) en = row[__ffs(m) - 1];
+                m &= m - 1;
+                const uint32_t d = valid ? shard_of(out.sh, (uint32_t) en.b) : 0u;
+                const uint32_t pos = shard_reserve(out.sh, valid, d, lane);
+                if (valid && pos < out.sh.cap) {
+                    int32_t *t = reinterpret_cast<int32_t *>(out.sh.seg) + ((uint64_t) d * out.sh.cap + pos) * 3;
+                    t[0] = en.b, t[1] = (int32_t) c, t[2] = en.o;
+                }
+            }
+            if (hard) out.spill_queue[atomicAdd(out.n_spill, 1u)] = c;
+            continue;
+        }
         // ---- emit: one atomicAdd on the edge counter per warp
         const uint32_t n_out = (part && !hard) ? (uint32_t) ns + __popc(rowmask) : 0u;
         uint32_t incl = n_out;

@@ -3,18 +3,12 @@
 The reference has no distributed path; the unit that shards naturally is the read:
 phase 1 of GraphCreatorPrefSuf.cpp:397-402 depends only on the source read b, phase 2 (:403-483) only on the
 target read c, and the rows of the final adjacency are disjoint by source read.  Rank r owns the reads
-[r * n_shard, (r + 1) * n_shard).  Per build:
+[r * n_shard, (r + 1) * n_shard).  ``ShardedPrefSuf`` is the product path: the exchanges happen inside the kernels
+over peer memory.  ``route_triples`` is the same routing rule written with torch collectives; it documents the
+semantics and is what the CPU (gloo) tests exercise, together with the triple-based stage calls of the C ABI.
 
-    1. all-gather of the 2-bit packed reads (NCCL over NVLink; 4 W bytes per node)      -> every GPU holds all reads
-    2. seed index over all reads (replicated; libalga_gpu kernel)
-    3. phase 1 for own source reads                                                      -> (b, c, o) edges
-    4. all-to-all of those edges to the owner of c
-    5. phase 2 (transitive reduction) for own target reads                               -> surviving (a, c, o)
-    6. all-to-all of the survivors to the owner of a
-    7. CSR assembly of own rows
-
-PyTorch supplies the device buffers and the process group only; all graph work is libalga_gpu.so.
-``route_triples`` is device-agnostic so that the exchange logic is tested with gloo on CPU tensors.
+PyTorch supplies device buffers, streams, symmetric memory and the process group only; all graph work is
+libalga_gpu.so.
 """
 from __future__ import annotations
 
@@ -66,54 +60,87 @@ def interleave_shards(reads, rank: int, world: int, device) -> tuple[torch.Tenso
 
 
 class ShardedPrefSuf:
-    """One rank of the sharded overlap-graph build for equal-length reads."""
+    """One rank of the sharded overlap-graph build for equal-length reads (one process per GPU, one box).
 
-    def __init__(self, min_overlap, rs_min_overlap, min_offset, max_len_cap, device, rank, world, len_nt, group=None):
-        self.rank, self.world, self.group = rank, world, group
+    Exchange design (alga_gpu.h, ``alga_ps_shard_*``): nothing is routed on the host and no NCCL collective carries
+    graph data.  Each rank owns two peer-mapped buffers (``torch.distributed._symmetric_memory``): its shard of the
+    packed reads and an exchange workspace.  Per build
+
+        1. the other ranks' read shards are pulled over NVLink on a copy stream, one peer at a time, while the main
+           stream inserts the shards that already arrived into the (replicated) seed index;
+        2. phase 1 appends every edge to the segment of the rank owning its target, in the rank's own workspace;
+        3. phase 2 reads the segments addressed to it straight out of all workspaces (NVLink loads in the kernel) and
+           appends the surviving edges to the segment of the rank owning their source;
+        4. the CSR stage reads those segments the same way.
+
+    Three stream-ordered barriers on the symmetric-memory signal pads separate the stages.
+    """
+
+    def __init__(self, min_overlap, rs_min_overlap, min_offset, max_len_cap, device, rank, world, len_nt, n_shard, words_per_read,
+                 group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        self.rank, self.world = rank, world
+        self.group = group if group is not None else dist.group.WORLD
         self.device = device
-        self.len_nt = len_nt
+        self.len_nt, self.n_shard, self.W = len_nt, n_shard, words_per_read
+        self.n_total = n_shard * world
         self.plan = PrefSufPlan(min_overlap, rs_min_overlap, min_offset, max_len_cap, device=device)
-        self._full = None
-        self._len = None
-        self._launch_mark = 0
-        self.stage_ms = {}
+        # peer-mapped buffers
+        self.shard_sym = symm.empty(n_shard * words_per_read, dtype=torch.int32, device=device)
+        self.ws_sym = symm.empty(self.plan.shard_ws_bytes(n_shard, world), dtype=torch.uint8, device=device)
+        self.ws_sym.zero_()
+        self._h_shard = symm.rendezvous(self.shard_sym, self.group)
+        self._h_ws = symm.rendezvous(self.ws_sym, self.group)
+        self._peer_shards = [self._h_shard.get_buffer(p, (n_shard * words_per_read,), torch.int32) for p in range(world)]
+        self._shard = PrefSufPlan.shard_struct(rank, world, n_shard, self.n_total, list(self._h_ws.buffer_ptrs))
+        # replicated read set + its binding (no pass over the reads: they arrive during the build)
+        self._full = torch.zeros(self.n_total * words_per_read + READ_PAD_BYTES // 4, dtype=torch.int32, device=device)
+        self._len = torch.full((self.n_total,), len_nt, dtype=torch.int32, device=device)
+        self._reads = DeviceReads.from_tensors(self._full, self._len, stride=words_per_read, n=self.n_total, max_len=len_nt)
+        self.plan.bind_uniform(self._reads, len_nt)
+        self._copy_stream = torch.cuda.Stream(device=device)
         self._ev = None
+        self._launches = 0
+        torch.cuda.synchronize(device)
+        self._h_ws.barrier()
 
-    def _buffers(self, n_shard: int, W: int):
-        n_total = n_shard * self.world
-        if self._full is None or self._full.numel() != n_total * W + READ_PAD_BYTES // 4:
-            self._full = torch.zeros(n_total * W + READ_PAD_BYTES // 4, dtype=torch.int32, device=self.device)
-            self._len = torch.full((n_total,), self.len_nt, dtype=torch.int32, device=self.device)
-        return n_total
+    def load_shard(self, shard_words: torch.Tensor):
+        """Put this rank's packed reads ([n_shard, W] int32, device or pinned host) into its peer-visible buffer."""
+        self.shard_sym.copy_(shard_words.reshape(-1), non_blocking=True)
 
-    def run(self, shard_words: torch.Tensor):
-        n_shard, W = shard_words.shape
-        n_total = self._buffers(n_shard, W)
-        lo, hi = self.rank * n_shard, (self.rank + 1) * n_shard
-        marks = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
-        before = self.plan.stats()["kernel_launches"]
+    def run(self):
+        """One build over the shards currently in the ranks' peer-visible buffers."""
+        main = torch.cuda.current_stream(self.device)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        n, W = self.n_shard, self.W
         marks[0].record()
-        dist.all_gather_into_tensor(self._full[: n_total * W], shard_words.reshape(-1), group=self.group)
+        self._h_shard.barrier()  # every rank's shard is in place (and nobody still reads the previous one)
+        self._copy_stream.wait_stream(main)
+        for k in range(self.world):
+            p = (self.rank + k) % self.world
+            dst = self._full[p * n * W:(p + 1) * n * W]
+            ev = torch.cuda.Event()
+            with torch.cuda.stream(self._copy_stream):
+                dst.copy_(self._peer_shards[p], non_blocking=True)
+                ev.record()
+            main.wait_event(ev)
+            self.plan.stage_index_range(p * n, (p + 1) * n, first=(k == 0))
         marks[1].record()
-        dr = DeviceReads.from_tensors(self._full, self._len, stride=W, n=n_total, max_len=self.len_nt)
-        self.plan.bind(dr)
-        self.plan.stage_index()
+        self.plan.shard_phase1(self._shard)
         marks[2].record()
-        t1 = self.plan.stage_phase1(lo, hi)
+        self._h_ws.barrier()
+        self.plan.shard_phase2(self._shard)
         marks[3].record()
-        t1r = route_triples(t1, 1, n_shard, self.world, self.group)
+        self._h_ws.barrier()
         marks[4].record()
-        t2 = self.plan.stage_phase2(lo, hi, t1r)
+        self.plan.shard_csr(self._shard)
         marks[5].record()
-        t2r = route_triples(t2, 0, n_shard, self.world, self.group)
-        marks[6].record()
-        self.plan.stage_csr(lo, hi, t2r)
-        marks[7].record()
         self._ev = marks
-        self._launches = self.plan.stats()["kernel_launches"] - before
+        self._launches = self.plan.stats()["kernel_launches"]
 
     def stats(self) -> dict:
-        names = ("allgather", "index", "phase1", "route1", "phase2", "route2", "csr")
+        names = ("gather+index", "phase1", "barrier+pull+phase2", "barrier", "pull+csr")
         self._ev[-1].synchronize()
         ms = {k: self._ev[i].elapsed_time(self._ev[i + 1]) for i, k in enumerate(names)}
         return {"kernel_launches": self._launches, "stage_ms": ms}
@@ -126,11 +153,11 @@ class ShardedPrefSuf:
     def result_device(self):
         return self.plan.result_device()
 
-    def e2e(self, shard_words: torch.Tensor, steps: int, n_nodes_total: int) -> dict:
+    def e2e(self, host_shard: torch.Tensor, steps: int, n_nodes_total: int) -> dict:
         """Same build with HOST buffers: pinned shard in, this rank's CSR rows out (pinned), wall clock, max over ranks."""
-        host_in = shard_words.cpu().pin_memory()
-        dev_in = torch.empty_like(shard_words)
-        self.run(shard_words)
+        host_in = host_shard.cpu().pin_memory()
+        self.load_shard(host_in)
+        self.run()
         ro, nb, of = self.result_device()
         cap = int(nb.numel() * 1.1) + 1024
         h_ro = torch.empty(ro.numel(), dtype=ro.dtype).pin_memory()
@@ -140,8 +167,8 @@ class ShardedPrefSuf:
 
         def one():
             nonlocal d2h
-            dev_in.copy_(host_in, non_blocking=True)
-            self.run(dev_in)
+            self.load_shard(host_in)
+            self.run()
             ro, nb, of = self.result_device()
             e = nb.numel()
             h_ro.copy_(ro, non_blocking=True)
@@ -162,4 +189,4 @@ class ShardedPrefSuf:
         dist.all_reduce(b, group=self.group)
         return {"value": n_nodes_total / (float(ms.item()) / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(b[0].item()),
                 "d2h_bytes_per_step": int(b[1].item()), "ms_per_step": float(ms.item()), "steps": steps,
-                "call": "alga_b200.distributed.ShardedPrefSuf.run with pinned host shard in / pinned host CSR rows out"}
+                "call": "alga_b200.distributed.ShardedPrefSuf.load_shard(pinned host) + run() + pinned host CSR rows out"}

@@ -105,6 +105,12 @@ class PrefSufPlan:
         torch.cuda.current_stream(self.device).synchronize()
         _lib.check(self.lib.alga_ps_plan_bind_reads_device(self._h, C.byref(st), reads.max_len))
 
+    def bind_uniform(self, reads: DeviceReads, len_nt: int):
+        """Equal-length reads at a fixed stride, no flags: bound without a pass over them (they may still be arriving)."""
+        self.reads = reads
+        st = reads.struct()
+        _lib.check(self.lib.alga_ps_plan_bind_reads_uniform(self._h, C.byref(st), len_nt))
+
     # ---- whole pipeline on this GPU -------------------------------------------------------------
     def run(self):
         _lib.check(self.lib.alga_ps_plan_run(self._h, self._stream()))
@@ -140,6 +146,29 @@ class PrefSufPlan:
         triples = triples.contiguous()
         _lib.check(self.lib.alga_ps_stage_csr(self._h, lo, hi, triples.data_ptr() if triples.numel() else None,
                                               triples.shape[0], 1 if swap_direction else 0, self._stream()))
+
+    # ---- sharded build, exchange inside the kernels over peer memory (alga_gpu.h: alga_ps_shard_*) ---
+    def stage_index_range(self, lo: int, hi: int, first: bool):
+        _lib.check(self.lib.alga_ps_stage_index_range(self._h, lo, hi, 1 if first else 0, self._stream()))
+
+    def shard_ws_bytes(self, n_shard: int, world: int) -> int:
+        return int(self.lib.alga_ps_shard_ws_bytes(n_shard, world))
+
+    @staticmethod
+    def shard_struct(rank: int, world: int, n_shard: int, n_total: int, peer_ws_ptrs) -> _lib.Shard:
+        sh = _lib.Shard(rank, world, n_shard, n_total)
+        for p, ptr in enumerate(peer_ws_ptrs):
+            sh.peer_ws[p] = int(ptr)
+        return sh
+
+    def shard_phase1(self, sh: _lib.Shard):
+        _lib.check(self.lib.alga_ps_shard_phase1(self._h, C.byref(sh), self._stream()))
+
+    def shard_phase2(self, sh: _lib.Shard):
+        _lib.check(self.lib.alga_ps_shard_phase2(self._h, C.byref(sh), self._stream()))
+
+    def shard_csr(self, sh: _lib.Shard):
+        _lib.check(self.lib.alga_ps_shard_csr(self._h, C.byref(sh), self._stream()))
 
     # ---- results --------------------------------------------------------------------------------
     def result_device(self):

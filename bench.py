@@ -9,9 +9,9 @@ packed reads resident in HBM -> CSR adjacency resident in HBM.  Metric: graph no
 * N = 1 : BASELINE.json configs[1] (4.6 Mbp genome, 2x150 bp, 50x, error-free; seed 2).
 * N > 1 : weak scaling -- N chromosomes of 4.6 Mbp (seeds 2 + 100 r), read ids interleaved so that every
           rank's id range holds reads of every chromosome; each rank starts with its own shard of the packed
-          reads in HBM.  The timed region contains the NCCL all-gather of the packed reads, the index build,
-          phase 1, the all-to-all of phase-1 edges to the owner of the target read, phase 2, the all-to-all of
-          surviving edges to the owner of the source read and the CSR assembly (alga_b200/distributed.py).
+          reads in HBM.  The timed region contains the NVLink pull of the other ranks' shards overlapped with the
+          (replicated) index build, phase 1, phase 2 and the CSR assembly; the two edge exchanges happen inside
+          those kernels over peer memory (alga_b200/distributed.py), separated by three stream-ordered barriers.
 * --impl reference : the reference's own CPU GraphCreatorPrefSuf (oracle/_ref/alga_ref_harness = the unmodified
           reference sources behind a file-reading main; else the plain-C oracle port), all host threads, on a
           bounded sample of the same workload.
@@ -236,10 +236,12 @@ def run_ours(args):
 
         shard_words, n_nodes_total = interleave_shards(w.reads, rank, world, dev)
         sp = ShardedPrefSuf(params.min_overlap, params.rs_min_overlap, params.min_offset, params.max_len_cap, dev,
-                            rank, world, len_nt=len_nt)
+                            rank, world, len_nt=len_nt, n_shard=int(shard_words.shape[0]),
+                            words_per_read=int(shard_words.shape[1]))
+        sp.load_shard(shard_words)  # the rank's packed reads, resident in its peer-visible HBM buffer
 
         def step():
-            sp.run(shard_words)
+            sp.run()
 
         def step_stats():
             return sp.stats()

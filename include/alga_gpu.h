@@ -133,6 +133,40 @@ int alga_ps_stage_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int
 int alga_ps_stage_csr(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int32_t *dev_triples, uint64_t n,
                       int swap_direction, void *stream);
 
+/* ---- sharded build with the exchange in the kernels (peer memory over NVLink / NVSwitch) ----------------------
+ * One process per GPU, up to 8 GPUs of one box.  Rank r owns the reads [r * n_shard, min((r+1) * n_shard, n_total)).
+ * Every rank holds all packed reads (bound with alga_ps_plan_bind_reads_*) and the whole seed index, and owns one
+ * exchange workspace of alga_ps_shard_ws_bytes() bytes that every other rank can address (peer-mapped memory, e.g.
+ * torch.distributed._symmetric_memory); peer_ws[p] is this process's pointer to rank p's workspace.
+ *
+ *   alga_ps_shard_phase1   phase 1 for the rank's own source reads; every edge (b, c, offset, overhang tail) is
+ *                          appended to the segment of the rank that owns c, in the rank's OWN workspace
+ *   -- barrier across ranks (the caller's, stream-ordered) --
+ *   alga_ps_shard_phase2   reads the segments addressed to this rank out of all workspaces (NVLink loads inside the
+ *                          kernel, no staging copy), builds the rows of the transposed graph, runs phase 2 for the
+ *                          rank's own target reads; survivors (a, c, offset) go to the segment of the owner of a
+ *   -- barrier across ranks --
+ *   alga_ps_shard_csr      reads the survivors addressed to this rank and assembles its CSR rows
+ *                          (alga_ps_plan_result_*: rows of [lo, hi), row_off relative to lo)
+ *
+ * The next build may start right away: its first barrier also orders it after the peers' reads of this one. */
+typedef struct {
+    int32_t rank, world;
+    uint32_t n_shard;  /* reads owned per rank (the last rank may own fewer) */
+    uint32_t n_total;  /* = n_reads of the bound read set */
+    void *peer_ws[8];  /* [world] device pointers, peer_ws[rank] = this rank's own workspace */
+} alga_ps_shard;
+uint64_t alga_ps_shard_ws_bytes(uint32_t n_shard, int32_t world);
+int alga_ps_shard_phase1(alga_ps_plan *plan, const alga_ps_shard *shard, void *stream);
+int alga_ps_shard_phase2(alga_ps_plan *plan, const alga_ps_shard *shard, void *stream);
+int alga_ps_shard_csr(alga_ps_plan *plan, const alga_ps_shard *shard, void *stream);
+/* Bind device-resident equal-length reads (fixed stride, no flags, none removed) WITHOUT a pass over them: they need
+ * not be resident yet, e.g. while the other ranks' shards are still arriving. */
+int alga_ps_plan_bind_reads_uniform(alga_ps_plan *plan, const alga_reads *dev_reads, uint32_t len_nt);
+/* Seed index in pieces: inserts the reads [lo, hi); first != 0 clears the tables before (start of a build).  Lets the
+ * caller overlap the arrival of the other ranks' reads with the insertion of those already there. */
+int alga_ps_stage_index_range(alga_ps_plan *plan, uint32_t lo, uint32_t hi, int first, void *stream);
+
 /* Result of the last run / stage_csr: device pointers (row_off has hi-lo+1 entries, relative to lo). */
 int alga_ps_plan_result_device(alga_ps_plan *plan, const uint64_t **row_off, const int32_t **nbr,
                                const int32_t **off, uint64_t *n_edges);

@@ -176,3 +176,40 @@ def test_row_overflow_list_regrows(gpu, monkeypatch):
     assert plan.stats()["n_row_overflow"] > w.reads.n // 8 + 65536
     assert np.array_equal(plan.result_host().edges(), oracle.prefsuf(w.reads, w.params.min_overlap, w.params.rs_min_overlap))
     plan.close()
+
+
+@pytest.mark.parametrize("name", ["cfg2_small", "cfg1_small", "cfg5_small"])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_sharded_peer_exchange_emulated_ranks(gpu, name, world):
+    """alga_ps_shard_* with the ranks emulated one after another on one GPU: every rank has its own exchange workspace
+    (an ordinary device buffer here, peer-mapped symmetric memory in alga_b200/distributed.py), phase 1 appends to the
+    owner's segment, phase 2 and the CSR stage read the segments addressed to them out of all workspaces."""
+    import torch
+
+    from alga_b200.plan import DeviceReads, PrefSufPlan
+
+    rs, lmin, rsmin, mo = build_case(name)
+    dev = torch.device("cuda", 0)
+    n = rs.n
+    n_shard = (n + world - 1) // world
+    plan = PrefSufPlan(lmin, rsmin, mo, device=0)
+    dr = DeviceReads(rs, dev)
+    dr.align_from = dr.align_to = None
+    plan.bind_uniform(dr, int(rs.len_nt[0]))
+    ws = [torch.zeros(plan.shard_ws_bytes(n_shard, world), dtype=torch.uint8, device=dev) for _ in range(world)]
+    shards = [plan.shard_struct(r, world, n_shard, n, [w.data_ptr() for w in ws]) for r in range(world)]
+    bounds = [min(n, r * n_shard) for r in range(world + 1)]
+    for r in range(world):  # the index arrives in pieces, one per rank
+        plan.stage_index_range(bounds[r], bounds[r + 1], first=(r == 0))
+    for r in range(world):
+        plan.shard_phase1(shards[r])
+    for r in range(world):
+        plan.shard_phase2(shards[r])
+    edges = []
+    for r in range(world):
+        plan.shard_csr(shards[r])
+        e = plan.result_host().edges()
+        e[:, 0] += bounds[r]
+        edges.append(e)
+    assert np.array_equal(np.concatenate(edges), oracle.prefsuf(rs, lmin, rsmin, mo))
+    plan.close()
