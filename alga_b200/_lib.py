@@ -47,7 +47,7 @@ class Timing(C.Structure):
 
 class Shard(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("n_shard", C.c_uint32), ("n_total", C.c_uint32),
-                ("peer_ws", C.c_void_p * 8)]
+                ("peer_ws", C.c_void_p * 8), ("table_prefix", C.c_void_p), ("table_suffix", C.c_void_p)]
 
 
 class VerifyParams(C.Structure):
@@ -73,6 +73,8 @@ SYMBOLS = {
     "alga_ps_plan_bind_reads_uniform": (C.c_int, [_P, C.POINTER(Reads), C.c_uint32]),
     "alga_ps_stage_index_range": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_int, _P]),
     "alga_ps_shard_ws_bytes": (C.c_uint64, [C.c_uint32, C.c_int32]),
+    "alga_ps_shard_table_bytes": (C.c_uint64, [C.c_uint32, C.c_int32]),
+    "alga_ps_shard_index_range": (C.c_int, [_P, C.POINTER(Shard), C.c_uint32, C.c_uint32, C.c_int, _P]),
     "alga_ps_shard_phase1": (C.c_int, [_P, C.POINTER(Shard), _P]),
     "alga_ps_shard_phase2": (C.c_int, [_P, C.POINTER(Shard), _P]),
     "alga_ps_shard_csr": (C.c_int, [_P, C.POINTER(Shard), _P]),

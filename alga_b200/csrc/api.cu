@@ -230,8 +230,10 @@ uint32_t buckets_for(uint32_t entries) {
     return (uint32_t) nb;
 }
 
-void size_table(SeedTable &t, uint32_t entries, uint32_t n_reads) {
+void size_table(SeedTable &t, uint32_t entries, uint32_t n_reads, int world = 1) {
     t.n_buckets = buckets_for(entries);
+    if (world > 1) t.n_buckets = (t.n_buckets + world - 1) / world * world;
+    t.slice = t.n_buckets / (world > 1 ? world : 1);
     uint32_t bits = 1;
     while (bits < 31 && (1ull << bits) < (uint64_t) n_reads) bits++;
     t.id_bits = bits;
@@ -255,7 +257,7 @@ int stage_index_begin(alga_ps_plan *plan, cudaStream_t s) {
 
 int stage_index(alga_ps_plan *plan, cudaStream_t s) {
     CKR(stage_index_begin(plan, s));
-    launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, 0, plan->R.n, s, plan->cfg);
+    launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, 0, plan->R.n, 0u, 0xFFFFFFFFu, s, plan->cfg);
     CK(cudaGetLastError());
     plan->index_valid = true;
     return ALGA_OK;
@@ -579,7 +581,7 @@ int alga_ps_stage_index_range(alga_ps_plan *plan, uint32_t lo, uint32_t hi, int 
     } else if (!plan->Tp.slots) {
         return fail(ALGA_E_INVALID, "the first range of a build must be inserted with first != 0");
     }
-    launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, lo, hi, s, plan->cfg);
+    launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, lo, hi, 0u, 0xFFFFFFFFu, s, plan->cfg);
     CK(cudaGetLastError());
     plan->index_valid = true;
     return ALGA_OK;
@@ -612,6 +614,13 @@ int check_shard(alga_ps_plan *plan, const alga_ps_shard *sh, uint32_t *lo, uint3
     for (int p = 0; p < sh->world; p++)
         if (!sh->peer_ws[p]) return fail(ALGA_E_INVALID, "null workspace pointer for rank %d", p);
     if (plan->swap_direction) return fail(ALGA_E_INVALID, "rs_min_overlap beyond the longest read is not supported in sharded runs");
+    if (sh->table_prefix && sh->table_suffix) {  // the caller's (sliced, exchanged) seed tables are the plan's tables
+        size_table(plan->Tp, sh->n_total, sh->n_total, sh->world);
+        size_table(plan->Ts, sh->n_total, sh->n_total, sh->world);
+        plan->Tp.slots = (uint32_t *) sh->table_prefix;
+        plan->Ts.slots = (uint32_t *) sh->table_suffix;
+        plan->index_valid = true;
+    }
     const uint64_t l = (uint64_t) sh->rank * sh->n_shard, h = l + sh->n_shard;
     *lo = (uint32_t) (l < sh->n_total ? l : sh->n_total);
     *hi = (uint32_t) (h < sh->n_total ? h : sh->n_total);
@@ -620,6 +629,36 @@ int check_shard(alga_ps_plan *plan, const alga_ps_shard *sh, uint32_t *lo, uint3
 }  // namespace
 
 uint64_t alga_ps_shard_ws_bytes(uint32_t n_shard, int32_t world) { return shard_layout(n_shard, world).total; }
+
+uint64_t alga_ps_shard_table_bytes(uint32_t n_total, int32_t world) {
+    SeedTable t{};
+    size_table(t, n_total, n_total, world);
+    return (uint64_t) t.n_buckets * kSlotsPerBucket * 4;
+}
+
+int alga_ps_shard_index_range(alga_ps_plan *plan, const alga_ps_shard *sh, uint32_t lo, uint32_t hi, int first, void *stream) {
+    uint32_t my_lo, my_hi;
+    CKR(check_shard(plan, sh, &my_lo, &my_hi));
+    if (!sh->table_prefix || !sh->table_suffix) return fail(ALGA_E_INVALID, "null seed table pointer");
+    if (lo > hi || hi > plan->R.n) return fail(ALGA_E_INVALID, "bad range [%u,%u)", lo, hi);
+    CKR(use_device(plan));
+    cudaStream_t s = (cudaStream_t) stream;
+    size_table(plan->Tp, sh->n_total, sh->n_total, sh->world);
+    size_table(plan->Ts, sh->n_total, sh->n_total, sh->world);
+    plan->Tp.slots = (uint32_t *) sh->table_prefix;
+    plan->Ts.slots = (uint32_t *) sh->table_suffix;
+    const uint32_t slice = plan->Tp.slice, b_lo = (uint32_t) sh->rank * slice, b_hi = b_lo + slice;
+    if (first) {
+        plan->launches = 0;
+        const size_t off = (size_t) b_lo * kSlotsPerBucket * 4, bytes = (size_t) slice * kSlotsPerBucket * 4;
+        CK(cudaMemsetAsync((char *) sh->table_prefix + off, 0xFF, bytes, s));
+        CK(cudaMemsetAsync((char *) sh->table_suffix + off, 0xFF, bytes, s));
+    }
+    launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, lo, hi, b_lo, b_hi, s, plan->cfg);
+    CK(cudaGetLastError());
+    plan->index_valid = true;
+    return ALGA_OK;
+}
 
 int alga_ps_shard_phase1(alga_ps_plan *plan, const alga_ps_shard *sh, void *stream) {
     uint32_t lo, hi;
@@ -677,16 +716,29 @@ int alga_ps_shard_phase2(alga_ps_plan *plan, const alga_ps_shard *sh, void *stre
     }
     Phase1Out rows_out{0, plan->indeg.as<uint32_t>(), plan->rows.as<RevEntry>(), plan->row_cap, plan->over.as<Edge1>(),
                        &dc->n_over, plan->over_cap, lo, ShardOut{}};
+    CK(cudaEventRecord(plan->ev_stage[0], s));
     launch_pull_rows(seg, cnt, sh->world, L.cap1, n * (uint32_t) kSmallEdgesKept / (uint32_t) sh->world + 1, rows_out, s,
                      plan->cfg);
     launch_rebuild_rows_csr(&dc->n_over, plan->over_cap, plan->over.as<Edge1>(), plan->indeg.as<uint32_t>(),
                             plan->rows.as<RevEntry>(), plan->row_cap, n, plan->rev_off.as<uint32_t>(), plan->rev.as<RevEntry>(),
                             rev_cap, &dc->rev_overflow, plan->scan_ws.p, s, plan->cfg);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(plan->ev_stage[1], s));
     const RowsView view{plan->indeg.as<uint32_t>(), plan->rows.as<RevEntry>(), plan->row_cap, &dc->n_over,
                         plan->over.as<Edge1>(), plan->rev_off.as<uint32_t>(), plan->rev.as<RevEntry>()};
     const ShardOut so{sh->world > 1 ? sh->world : 2, sh->n_shard, (uint32_t *) (ws + L.cnt2_off), ws + L.seg2_off, L.cap2};
     CKR(run_phase2(plan, lo, hi, view, nullptr, s, so));
+    CK(cudaEventRecord(plan->ev_stage[2], s));
+    CK(cudaEventSynchronize(plan->ev_stage[2]));
+    {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, plan->ev_stage[0], plan->ev_stage[1]));
+        plan->stage_ms[2] = ms;  // rows of the transposed graph (pull over NVLink)
+        CK(cudaEventElapsedTime(&ms, plan->ev_stage[1], plan->ev_stage[2]));
+        plan->stage_ms[3] = ms;  // phase 2
+        plan->stage_ms[5] = plan->h_counters->n_over;
+        plan->stage_ms[6] = plan->h_counters->n_hard1;
+    }
     if (plan->h_counters->n_over > plan->over_cap) {
         plan->over_cap = sh->n_shard * (uint32_t) kSmallEdgesKept * 2;
         return fail(ALGA_E_CAPACITY, "phase-1 overflow list too small; the plan has grown it, run the build again");

@@ -159,6 +159,8 @@ __device__ __forceinline__ const RevEntry *get_row(const RowsView &v, bool csr, 
 struct SeedTable {
     uint32_t *slots;
     uint32_t n_buckets;
+    uint32_t slice;     // chains wrap inside slices of this many buckets (= n_buckets unless the build is sharded: rank
+                        // r fills the buckets [r * slice, (r + 1) * slice) and the ranks then exchange slices)
     uint32_t id_bits;   // bits of a read id, <= 31 (edge arrays carry int32 ids)
     uint32_t id_mask;   // (1 << id_bits) - 1
     uint32_t tag_mask;  // (1 << (32 - id_bits)) - 1; the all-ones tag is never used, so no entry equals kEmptySlot
@@ -236,6 +238,11 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 __device__ __forceinline__ uint32_t bucket_of(uint64_t h, uint32_t n_buckets) {
     return __umulhi((uint32_t) (h >> 32), n_buckets);
 }
+// next bucket of a chain (rare path)
+__device__ __forceinline__ uint32_t next_bucket(const SeedTable &t, uint32_t bk) {
+    const uint32_t nb = bk + 1;
+    return nb % t.slice == 0 ? nb - t.slice : nb;
+}
 // tag already shifted into entry position (the bits of an entry above the read id)
 __device__ __forceinline__ uint32_t tag_of(const SeedTable &t, uint64_t h) {
     uint32_t tag = (uint32_t) h >> t.id_bits;
@@ -263,7 +270,7 @@ __device__ __forceinline__ void probe_seed(const SeedTable &t, uint64_t h, F &&f
             if (e[s] == kEmptySlot) return;
             if ((e[s] ^ tag) <= t.id_mask) f(e[s] & t.id_mask);
         }
-        bk = (bk + 1 == t.n_buckets) ? 0u : bk + 1;
+        bk = next_bucket(t, bk);
     }
 }
 
@@ -285,7 +292,7 @@ __device__ __forceinline__ void insert_seed(const SeedTable &t, uint64_t h, uint
         else if (b.w == kEmptySlot) s = 7;
         for (; s < kSlotsPerBucket; s++)
             if (atomicCAS(base + s, kEmptySlot, entry) == kEmptySlot) return;
-        bk = (bk + 1 == t.n_buckets) ? 0u : bk + 1;
+        bk = next_bucket(t, bk);
     }
 }
 

@@ -59,18 +59,22 @@ __global__ void read_stats_kernel(ReadsDev R, int lmin, int min_offset, ReadStat
 
 // ------------------------------------------------------------------------------------------------
 // Seed index build: one thread per read, two inserts (prefix side, suffix side).
-__global__ void build_index_kernel(ReadsDev R, PsDev P, SeedTable tp, SeedTable ts, uint32_t lo, uint32_t hi) {
+// [b_lo, b_hi): only seeds whose bucket falls in this range are inserted (sharded build: the rank's own slice)
+__global__ void build_index_kernel(ReadsDev R, PsDev P, SeedTable tp, SeedTable ts, uint32_t lo, uint32_t hi, uint32_t b_lo,
+                                   uint32_t b_hi) {
     for (uint64_t i = (uint64_t) lo + blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < hi; i += (uint64_t) gridDim.x * blockDim.x) {
         const uint32_t len = P.uniform_len ? P.uniform_len : R.len[i];
         if (len == 0 || (int64_t) len < P.lmin) continue;
         const uint32_t *p = read_ptr(R, (uint32_t) i);
         if (flag_to(R, (uint32_t) i)) {
-            const uint64_t w = bits64(p, 0) & P.seed_mask;
-            insert_seed(tp, mix64(w), (uint32_t) i);
+            const uint64_t h = mix64(bits64(p, 0) & P.seed_mask);
+            const uint32_t bk = bucket_of(h, tp.n_buckets);
+            if (bk >= b_lo && bk < b_hi) insert_seed(tp, h, (uint32_t) i);
         }
         if (flag_from(R, (uint32_t) i) && (int64_t) len - P.min_offset >= P.lmin) {
-            const uint64_t w = bits64(p, 2u * (len - (uint32_t) P.seed_nt)) & P.seed_mask;
-            insert_seed(ts, mix64(w), (uint32_t) i);
+            const uint64_t h = mix64(bits64(p, 2u * (len - (uint32_t) P.seed_nt)) & P.seed_mask);
+            const uint32_t bk = bucket_of(h, ts.n_buckets);
+            if (bk >= b_lo && bk < b_hi) insert_seed(ts, h, (uint32_t) i);
         }
     }
 }
@@ -85,15 +89,41 @@ struct PeerSegs {
     int world;
 };
 
-// phase-1 edges whose target this rank owns -> rows of the transposed graph (blockIdx.y = peer)
+// phase-1 edges whose target this rank owns -> rows of the transposed graph (blockIdx.y = peer).  Four entries per
+// thread and round: their loads over NVLink, then their four atomics, are in flight together.
 __global__ void pull_rows_kernel(PeerSegs ps, Phase1Out out) {
     const int p = blockIdx.y;
     uint32_t n = *ps.cnt[p];
     if (n > ps.cap) n = ps.cap;
     const Edge1 *src = reinterpret_cast<const Edge1 *>(ps.seg[p]);
-    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
-        const Edge1 e = src[i];
-        emit_edge1(out, (uint32_t) e.b, (uint32_t) e.c, (uint32_t) e.o, e.t);
+    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
+    for (uint64_t i0 = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        Edge1 e[4];
+        uint32_t pos[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (i0 + j * stride < n) e[j] = src[i0 + j * stride];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (i0 + j * stride < n) pos[j] = atomicAdd(out.indeg + ((uint32_t) e[j].c - out.c_base), 1u);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (i0 + j * stride < n) {
+                const uint32_t ci = (uint32_t) e[j].c - out.c_base;
+                if (pos[j] < out.row_cap) {
+                    RevEntry r;
+                    r.b = e[j].b, r.o = e[j].o, r.t = e[j].t;
+                    out.rows[(uint64_t) ci * out.row_cap + pos[j]] = r;
+                } else {
+                    const uint32_t k = atomicAdd(out.n_list, 1u);
+                    if (k < out.list_cap) {
+                        Edge1 x = e[j];
+                        x.c = (int32_t) ci;
+                        out.list[k] = x;
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -737,9 +767,9 @@ void launch_read_stats(const ReadsDev &R, int lmin, int min_offset, ReadStats *d
 }
 
 void launch_build_index(const ReadsDev &R, const PsDev &P, SeedTable prefix, SeedTable suffix, uint32_t lo, uint32_t hi,
-                        cudaStream_t s, const LaunchCfg &cfg) {
+                        uint32_t b_lo, uint32_t b_hi, cudaStream_t s, const LaunchCfg &cfg) {
     if (hi <= lo) return;
-    build_index_kernel<<<grid_for(hi - lo, 256, cfg), 256, 0, s>>>(R, P, prefix, suffix, lo, hi);
+    build_index_kernel<<<grid_for(hi - lo, 256, cfg), 256, 0, s>>>(R, P, prefix, suffix, lo, hi, b_lo, b_hi);
     bump(cfg);
 }
 
@@ -749,7 +779,8 @@ void launch_pull_rows(const void *const *seg, const uint32_t *const *cnt, int wo
     for (int p = 0; p < world; p++) ps.seg[p] = seg[p], ps.cnt[p] = cnt[p];
     ps.cap = cap;
     ps.world = world;
-    dim3 grid((unsigned) grid_for(n_expected ? n_expected : 1, 256, cfg, 4), (unsigned) world);
+    dim3 grid((unsigned) grid_for((n_expected ? n_expected : 1) / 4 + 1, 256, cfg, world >= 8 ? 2 : (world >= 4 ? 4 : 8)),
+              (unsigned) world);
     pull_rows_kernel<<<grid, 256, 0, s>>>(ps, out);
     bump(cfg);
 }

@@ -129,7 +129,7 @@ __device__ __forceinline__ void probe_matches(const SeedTable &t, uint32_t (&e)[
     n = 0;
     bool more = eval_bucket(t, e, tag, c0, c1, n);
     while (more) {
-        bk = (bk + 1 == t.n_buckets) ? 0u : bk + 1;
+        bk = next_bucket(t, bk);
         load_bucket(t.slots + (uint64_t) bk * kSlotsPerBucket, e);
         more = eval_bucket(t, e, tag, c0, c1, n);
     }

@@ -93,7 +93,17 @@ class ShardedPrefSuf:
         self._h_shard = symm.rendezvous(self.shard_sym, self.group)
         self._h_ws = symm.rendezvous(self.ws_sym, self.group)
         self._peer_shards = [self._h_shard.get_buffer(p, (n_shard * words_per_read,), torch.int32) for p in range(world)]
-        self._shard = PrefSufPlan.shard_struct(rank, world, n_shard, self.n_total, list(self._h_ws.buffer_ptrs))
+        # seed tables: every rank fills its slice of the bucket space, the slices are then copied from each other
+        tb = self.plan.shard_table_bytes(self.n_total, world)
+        self._slice_bytes = tb // world
+        self.tp_sym = symm.empty(tb, dtype=torch.uint8, device=device)
+        self.ts_sym = symm.empty(tb, dtype=torch.uint8, device=device)
+        self._h_tp = symm.rendezvous(self.tp_sym, self.group)
+        self._h_ts = symm.rendezvous(self.ts_sym, self.group)
+        self._peer_tp = [self._h_tp.get_buffer(p, (tb,), torch.uint8) for p in range(world)]
+        self._peer_ts = [self._h_ts.get_buffer(p, (tb,), torch.uint8) for p in range(world)]
+        self._shard = PrefSufPlan.shard_struct(rank, world, n_shard, self.n_total, list(self._h_ws.buffer_ptrs),
+                                               self.tp_sym.data_ptr(), self.ts_sym.data_ptr())
         # replicated read set + its binding (no pass over the reads: they arrive during the build)
         self._full = torch.zeros(self.n_total * words_per_read + READ_PAD_BYTES // 4, dtype=torch.int32, device=device)
         self._len = torch.full((self.n_total,), len_nt, dtype=torch.int32, device=device)
@@ -125,11 +135,26 @@ class ShardedPrefSuf:
                 dst.copy_(self._peer_shards[p], non_blocking=True)
                 ev.record()
             main.wait_event(ev)
-            self.plan.stage_index_range(p * n, (p + 1) * n, first=(k == 0))
+            # seeds of the arrived shard that fall into this rank's slice of the bucket space
+            self.plan.shard_index_range(self._shard, p * n, (p + 1) * n, first=(k == 0))
+        self._h_ws.barrier()  # every rank's slice is complete
         marks[1].record()
+        ev_slices = torch.cuda.Event()
+        ev_slices.record(main)
+        ev_tp, ev_ts = torch.cuda.Event(), torch.cuda.Event()
+        sb = self._slice_bytes
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ev_slices)
+            for tabs, mine, ev in ((self._peer_tp, self.tp_sym, ev_tp), (self._peer_ts, self.ts_sym, ev_ts)):
+                for k in range(1, self.world):
+                    p = (self.rank + k) % self.world
+                    mine[p * sb:(p + 1) * sb].copy_(tabs[p][p * sb:(p + 1) * sb], non_blocking=True)
+                ev.record()
+        main.wait_event(ev_tp)  # the suffix table keeps arriving while phase 1 runs
         self.plan.shard_phase1(self._shard)
         marks[2].record()
         self._h_ws.barrier()
+        main.wait_event(ev_ts)
         self.plan.shard_phase2(self._shard)
         marks[3].record()
         self._h_ws.barrier()
@@ -140,10 +165,14 @@ class ShardedPrefSuf:
         self._launches = self.plan.stats()["kernel_launches"]
 
     def stats(self) -> dict:
-        names = ("gather+index", "phase1", "barrier+pull+phase2", "barrier", "pull+csr")
+        names = ("gather+index", "slices+phase1", "barrier+pull+phase2", "barrier", "pull+csr")
         self._ev[-1].synchronize()
         ms = {k: self._ev[i].elapsed_time(self._ev[i + 1]) for i, k in enumerate(names)}
-        return {"kernel_launches": self._launches, "stage_ms": ms}
+        st = self.plan.stats()
+        ms["pull_rows_kernel"] = st["stage_ms"]["transpose"]
+        ms["phase2_kernels"] = st["stage_ms"]["phase2"]
+        return {"kernel_launches": self._launches, "stage_ms": ms, "n_spilled_targets": st["n_spilled_targets"],
+                "n_row_overflow": st["n_row_overflow"], "n_hard_sources": st["n_hard_sources"]}
 
     def total_edges(self) -> int:
         t = torch.tensor([self.plan.n_edges()], dtype=torch.int64, device=self.device)

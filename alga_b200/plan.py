@@ -155,11 +155,20 @@ class PrefSufPlan:
         return int(self.lib.alga_ps_shard_ws_bytes(n_shard, world))
 
     @staticmethod
-    def shard_struct(rank: int, world: int, n_shard: int, n_total: int, peer_ws_ptrs) -> _lib.Shard:
+    def shard_struct(rank: int, world: int, n_shard: int, n_total: int, peer_ws_ptrs, table_prefix: int = 0,
+                     table_suffix: int = 0) -> _lib.Shard:
         sh = _lib.Shard(rank, world, n_shard, n_total)
         for p, ptr in enumerate(peer_ws_ptrs):
             sh.peer_ws[p] = int(ptr)
+        sh.table_prefix = table_prefix or None
+        sh.table_suffix = table_suffix or None
         return sh
+
+    def shard_table_bytes(self, n_total: int, world: int) -> int:
+        return int(self.lib.alga_ps_shard_table_bytes(n_total, world))
+
+    def shard_index_range(self, sh: _lib.Shard, lo: int, hi: int, first: bool):
+        _lib.check(self.lib.alga_ps_shard_index_range(self._h, C.byref(sh), lo, hi, 1 if first else 0, self._stream()))
 
     def shard_phase1(self, sh: _lib.Shard):
         _lib.check(self.lib.alga_ps_shard_phase1(self._h, C.byref(sh), self._stream()))

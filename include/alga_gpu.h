@@ -155,8 +155,19 @@ typedef struct {
     uint32_t n_shard;  /* reads owned per rank (the last rank may own fewer) */
     uint32_t n_total;  /* = n_reads of the bound read set */
     void *peer_ws[8];  /* [world] device pointers, peer_ws[rank] = this rank's own workspace */
+    /* this rank's copies of the two seed tables (alga_ps_shard_table_bytes() each, caller-owned and readable by the
+     * peers) -- only for alga_ps_shard_index_range, NULL otherwise */
+    void *table_prefix, *table_suffix;
 } alga_ps_shard;
 uint64_t alga_ps_shard_ws_bytes(uint32_t n_shard, int32_t world);
+/* Sharded index build: the bucket space of each table is cut into `world` slices; rank r inserts -- out of the reads
+ * [lo, hi) of the (replicated) read set -- the seeds that fall into slice r of ITS copy of the tables (first != 0
+ * clears that slice first).  When every rank has inserted all reads, slice r of rank r's tables is final and the
+ * ranks copy each other's slices (bytes [r, r+1) * table_bytes / world of the table buffers); the plan then probes
+ * the caller's tables.  Replaces alga_ps_stage_index_range for sharded runs: no rank inserts more than its share. */
+uint64_t alga_ps_shard_table_bytes(uint32_t n_total, int32_t world);
+int alga_ps_shard_index_range(alga_ps_plan *plan, const alga_ps_shard *shard, uint32_t lo, uint32_t hi, int first,
+                              void *stream);
 int alga_ps_shard_phase1(alga_ps_plan *plan, const alga_ps_shard *shard, void *stream);
 int alga_ps_shard_phase2(alga_ps_plan *plan, const alga_ps_shard *shard, void *stream);
 int alga_ps_shard_csr(alga_ps_plan *plan, const alga_ps_shard *shard, void *stream);

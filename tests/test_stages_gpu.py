@@ -197,10 +197,21 @@ def test_sharded_peer_exchange_emulated_ranks(gpu, name, world):
     dr.align_from = dr.align_to = None
     plan.bind_uniform(dr, int(rs.len_nt[0]))
     ws = [torch.zeros(plan.shard_ws_bytes(n_shard, world), dtype=torch.uint8, device=dev) for _ in range(world)]
-    shards = [plan.shard_struct(r, world, n_shard, n, [w.data_ptr() for w in ws]) for r in range(world)]
+    tb = plan.shard_table_bytes(n, world)
+    tp = [torch.zeros(tb, dtype=torch.uint8, device=dev) for _ in range(world)]
+    ts = [torch.zeros(tb, dtype=torch.uint8, device=dev) for _ in range(world)]
+    shards = [plan.shard_struct(r, world, n_shard, n, [w.data_ptr() for w in ws], tp[r].data_ptr(), ts[r].data_ptr())
+              for r in range(world)]
     bounds = [min(n, r * n_shard) for r in range(world + 1)]
-    for r in range(world):  # the index arrives in pieces, one per rank
-        plan.stage_index_range(bounds[r], bounds[r + 1], first=(r == 0))
+    for r in range(world):  # every rank fills its slice of the bucket space, the reads arriving in pieces
+        for q in range(world):
+            plan.shard_index_range(shards[r], bounds[q], bounds[q + 1], first=(q == 0))
+    sb = tb // world
+    for r in range(world):  # ... and copies the other ranks' slices
+        for q in range(world):
+            if q != r:
+                tp[r][q * sb:(q + 1) * sb] = tp[q][q * sb:(q + 1) * sb]
+                ts[r][q * sb:(q + 1) * sb] = ts[q][q * sb:(q + 1) * sb]
     for r in range(world):
         plan.shard_phase1(shards[r])
     for r in range(world):
