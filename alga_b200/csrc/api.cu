@@ -598,8 +598,9 @@ ShardLayout shard_layout(uint32_t n_shard, int world) {
     L.cnt1_off = 0;
     L.cnt2_off = 64;
     L.seg1_off = 256;
-    L.cap1 = n_shard * (uint32_t) kSmallEdgesKept;           // worst case: every edge of the rank to one owner
-    L.cap2 = n_shard * (uint32_t) kSmallEdgesKept + 65536u;  // survivors per owner (checked; ALGA_E_CAPACITY beyond)
+    // segment sizes are multiples of 4 entries: every segment starts 16-byte aligned (the pull kernels load uint4)
+    L.cap1 = (n_shard * (uint32_t) kSmallEdgesKept + 3u) & ~3u;           // worst case: every edge of the rank to one owner
+    L.cap2 = (n_shard * (uint32_t) kSmallEdgesKept + 65536u + 3u) & ~3u;  // survivors per owner (checked; ALGA_E_CAPACITY beyond)
     L.seg2_off = (L.seg1_off + (uint64_t) world * L.cap1 * sizeof(Edge1) + 255) & ~255ull;
     L.total = (L.seg2_off + (uint64_t) world * L.cap2 * 12 + 255) & ~255ull;
     return L;

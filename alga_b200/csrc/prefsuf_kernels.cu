@@ -89,26 +89,45 @@ struct PeerSegs {
     int world;
 };
 
+// Peer memory is not cached on this side of the link, so every load instruction costs its own NVLink sectors: the
+// pull kernels move tiles of the peer's segment into shared memory with fully coalesced 16-byte loads and work from
+// there.
+constexpr int kPullTile = 1024;  // entries per block and round
+
+__device__ __forceinline__ void pull_tile(const void *src, uint64_t first, uint32_t count, uint32_t entry_bytes, uint4 *sh) {
+    // segments start 16-byte aligned and entry_bytes * kPullTile is a multiple of 16
+    const uint4 *g = reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(src) + first * entry_bytes);
+    const uint32_t n16 = (count * entry_bytes + 15u) >> 4;
+    for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) sh[i] = g[i];
+    __syncthreads();
+}
+
 // phase-1 edges whose target this rank owns -> rows of the transposed graph (blockIdx.y = peer).  Four entries per
-// thread and round: their loads over NVLink, then their four atomics, are in flight together.
-__global__ void pull_rows_kernel(PeerSegs ps, Phase1Out out) {
+// thread and round: their four atomics are in flight together.
+__global__ void __launch_bounds__(256) pull_rows_kernel(PeerSegs ps, Phase1Out out) {
+    __shared__ uint4 sh[kPullTile * sizeof(Edge1) / 16];
     const int p = blockIdx.y;
     uint32_t n = *ps.cnt[p];
     if (n > ps.cap) n = ps.cap;
-    const Edge1 *src = reinterpret_cast<const Edge1 *>(ps.seg[p]);
-    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
-    for (uint64_t i0 = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+    const Edge1 *tile = reinterpret_cast<const Edge1 *>(sh);
+    for (uint64_t first = (uint64_t) blockIdx.x * kPullTile; first < n; first += (uint64_t) gridDim.x * kPullTile) {
+        const uint32_t count = (uint32_t) min((uint64_t) kPullTile, (uint64_t) n - first);
+        __syncthreads();
+        pull_tile(ps.seg[p], first, count, sizeof(Edge1), sh);
         Edge1 e[4];
         uint32_t pos[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (i0 + j * stride < n) e[j] = src[i0 + j * stride];
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (i0 + j * stride < n) pos[j] = atomicAdd(out.indeg + ((uint32_t) e[j].c - out.c_base), 1u);
+        for (int j = 0; j < 4; j++) {
+            const uint32_t i = threadIdx.x + j * 256;
+            if (i < count) {
+                e[j] = tile[i];
+                pos[j] = atomicAdd(out.indeg + ((uint32_t) e[j].c - out.c_base), 1u);
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            if (i0 + j * stride < n) {
+            const uint32_t i = threadIdx.x + j * 256;
+            if (i < count) {
                 const uint32_t ci = (uint32_t) e[j].c - out.c_base;
                 if (pos[j] < out.row_cap) {
                     RevEntry r;
@@ -128,8 +147,9 @@ __global__ void pull_rows_kernel(PeerSegs ps, Phase1Out out) {
 }
 
 // surviving edges whose source this rank owns -> local triples + out-degrees (blockIdx.y = peer)
-__global__ void pull_triples_kernel(PeerSegs ps, uint64_t cap_local, int32_t *__restrict__ triples,
-                                    unsigned long long *n_total, uint32_t *outdeg) {
+__global__ void __launch_bounds__(256) pull_triples_kernel(PeerSegs ps, uint64_t cap_local, int32_t *__restrict__ triples,
+                                                           unsigned long long *n_total, uint32_t *outdeg) {
+    __shared__ uint4 sh[kPullTile * 12 / 16];
     const int p = blockIdx.y;
     uint64_t base = 0, total = 0;
     uint32_t n = 0;
@@ -141,13 +161,18 @@ __global__ void pull_triples_kernel(PeerSegs ps, uint64_t cap_local, int32_t *__
         total += c;
     }
     if (p == 0 && blockIdx.x == 0 && threadIdx.x == 0) *n_total = total;
-    const int32_t *src = reinterpret_cast<const int32_t *>(ps.seg[p]);
-    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
-        if (base + i >= cap_local) break;  // the host sees n_total > cap_local and pulls again into a larger buffer
-        const int32_t a = src[3 * i], c = src[3 * i + 1], o = src[3 * i + 2];
-        int32_t *dst = triples + 3 * (base + i);
-        dst[0] = a, dst[1] = c, dst[2] = o;
-        atomicAdd(outdeg + (uint32_t) a, 1u);  // counted by global id
+    const int32_t *tile = reinterpret_cast<const int32_t *>(sh);
+    for (uint64_t first = (uint64_t) blockIdx.x * kPullTile; first < n; first += (uint64_t) gridDim.x * kPullTile) {
+        const uint32_t count = (uint32_t) min((uint64_t) kPullTile, (uint64_t) n - first);
+        __syncthreads();
+        pull_tile(ps.seg[p], first, count, 12, sh);
+        // the local copy is contiguous: written as plain words, coalesced; the host pulls again if it did not fit
+        for (uint32_t w = threadIdx.x; w < 3 * count; w += blockDim.x) {
+            const uint64_t dst = 3 * (base + first) + w;
+            if (dst < 3 * cap_local) triples[dst] = tile[w];
+        }
+        if (base + first + count <= cap_local)
+            for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) atomicAdd(outdeg + (uint32_t) tile[3 * i], 1u);  // global id
     }
 }
 
@@ -779,7 +804,7 @@ void launch_pull_rows(const void *const *seg, const uint32_t *const *cnt, int wo
     for (int p = 0; p < world; p++) ps.seg[p] = seg[p], ps.cnt[p] = cnt[p];
     ps.cap = cap;
     ps.world = world;
-    dim3 grid((unsigned) grid_for((n_expected ? n_expected : 1) / 4 + 1, 256, cfg, world >= 8 ? 2 : (world >= 4 ? 4 : 8)),
+    dim3 grid((unsigned) grid_for(n_expected ? n_expected : 1, kPullTile, cfg, world >= 8 ? 1 : (world >= 4 ? 2 : 4)),
               (unsigned) world);
     pull_rows_kernel<<<grid, 256, 0, s>>>(ps, out);
     bump(cfg);
@@ -792,7 +817,8 @@ void launch_pull_triples(const void *const *seg, const uint32_t *const *cnt, int
     for (int p = 0; p < world; p++) ps.seg[p] = seg[p], ps.cnt[p] = cnt[p];
     ps.cap = cap;
     ps.world = world;
-    dim3 grid((unsigned) grid_for(n_expected ? n_expected : 1, 256, cfg, 4), (unsigned) world);
+    dim3 grid((unsigned) grid_for(n_expected ? n_expected : 1, kPullTile, cfg, world >= 8 ? 1 : (world >= 4 ? 2 : 4)),
+              (unsigned) world);
     pull_triples_kernel<<<grid, 256, 0, s>>>(ps, cap_local, triples, n_total, outdeg);
     bump(cfg);
 }
