@@ -55,6 +55,11 @@ class VerifyParams(C.Structure):
                 ("threshold_pct", C.c_int32), ("same_ends", C.c_int32), ("device", C.c_int32)]
 
 
+class SupParams(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("max_offset_pct", "min_offset", "min_overlap_area", "threshold_pct", "same_ends",
+                                          "kmer_length", "intervals", "kmer_length_bucket", "device")]
+
+
 # every symbol include/alga_gpu.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -88,6 +93,9 @@ SYMBOLS = {
     "alga_gpu_fingerprints": (C.c_int, [C.POINTER(Reads), C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "alga_gpu_pack_reads": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_int32, _P]),
     "alga_gpu_verify_pairs": (C.c_int, [C.POINTER(Reads), _P, C.c_uint64, C.POINTER(VerifyParams), _P]),
+    "alga_gpu_supplement": (C.c_int, [C.POINTER(Reads), C.POINTER(Csr), C.POINTER(SupParams), C.POINTER(Csr),
+                                      C.POINTER(Timing)]),
+    "alga_gpu_li_kmers": (C.c_int, [C.POINTER(Reads), _P, C.c_uint32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "alga_gpu_device_count": (C.c_int, []),
     "alga_gpu_last_error": (C.c_char_p, []),
     "alga_gpu_version": (C.c_char_p, []),

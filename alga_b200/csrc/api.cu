@@ -14,6 +14,10 @@
 
 using namespace alga;
 
+namespace alga {
+int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_params *sp, alga_csr *gout, alga_timing *tm);
+}
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -1105,6 +1109,49 @@ int alga_gpu_verify_pairs(const alga_reads *reads, const int32_t *pairs, uint64_
     }();
     dp.release();
     dv.release();
+    return r;
+}
+
+int alga_gpu_supplement(const alga_reads *reads, const alga_csr *graph_in, const alga_sup_params *params,
+                        alga_csr *graph_out, alga_timing *timing) {
+    if (!reads || !graph_in || !params || !graph_out) return fail(ALGA_E_INVALID, "null argument");
+    if (reads->n_reads && (!reads->words || !reads->len_nt)) return fail(ALGA_E_INVALID, "words / len_nt must not be null");
+    if (!reads->word_off && reads->stride_words == 0 && reads->n_reads) return fail(ALGA_E_INVALID, "word_off is null and stride_words is 0");
+    if (reads->n_reads && (!graph_in->row_off || (graph_in->n_edges && (!graph_in->nbr || !graph_in->off))))
+        return fail(ALGA_E_INVALID, "graph_in arrays must not be null");
+    const int rc = supplement_impl(reads, graph_in, params, graph_out, timing);
+    if (rc != ALGA_OK) return fail(rc, "%s", supplement_last_error());
+    return ALGA_OK;
+}
+
+int alga_gpu_li_kmers(const alga_reads *reads, const uint32_t *ids, uint32_t n_ids, const int32_t priorities[4],
+                      int32_t kmer_length, int32_t intervals, int32_t device, uint64_t *hash_out, int32_t *ind_out) {
+    if (!reads || !priorities || (n_ids && (!ids || !hash_out || !ind_out))) return fail(ALGA_E_INVALID, "null argument");
+    if (kmer_length < 1 || kmer_length > 63 || intervals < 1 || intervals > 64)
+        return fail(ALGA_E_INVALID, "kmer_length must be 1..63 and intervals 1..64");
+    for (uint32_t i = 0; i < n_ids; i++)
+        if (ids[i] >= reads->n_reads || (int64_t) reads->len_nt[ids[i]] < kmer_length)
+            return fail(ALGA_E_INVALID, "read %u is missing or shorter than the k-mer", ids[i]);
+    LaunchCfg cfg;
+    CKR(pick_device(device, &cfg));
+    TmpReads t;
+    CKR(t.upload(reads));
+    DevBuf di, dh, dn;
+    int r = [&]() -> int {
+        CKR(di.ensure((size_t) (n_ids ? n_ids : 1) * 4));
+        CKR(dh.ensure((size_t) (n_ids ? n_ids : 1) * intervals * 8));
+        CKR(dn.ensure((size_t) (n_ids ? n_ids : 1) * intervals * 4));
+        CK(cudaMemcpy(di.p, ids, (size_t) n_ids * 4, cudaMemcpyHostToDevice));
+        const int rc = run_li_kmers(t.R, di.as<uint32_t>(), n_ids, priorities, kmer_length, intervals, dh.as<uint64_t>(),
+                                    dn.as<int32_t>(), 0, cfg);
+        if (rc != ALGA_OK) return fail(rc, "%s", supplement_last_error());
+        CK(cudaMemcpy(hash_out, dh.p, (size_t) n_ids * intervals * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(ind_out, dn.p, (size_t) n_ids * intervals * 4, cudaMemcpyDeviceToHost));
+        return ALGA_OK;
+    }();
+    di.release();
+    dh.release();
+    dn.release();
     return r;
 }
 

@@ -129,4 +129,10 @@ struct VerifyDev {
 void launch_verify_pairs(const ReadsDev &R, const int32_t *pairs, uint64_t n_pairs, const VerifyDev &V,
                          uint8_t *verdict, cudaStream_t s, const LaunchCfg &cfg);
 
+// --- error-rate supplement (supplement.cu) -------------------------------------------------------
+// LI k-mers (Read.cpp:145-226) of the reads d_ids[0 .. n_ids): `intervals` slots per read, ind = -1 where absent
+int run_li_kmers(const ReadsDev &R, const uint32_t *d_ids, uint32_t n_ids, const int32_t prio[4], int K, int intervals,
+                 uint64_t *d_hash, int32_t *d_ind, cudaStream_t s, const LaunchCfg &cfg);
+const char *supplement_last_error();
+
 }  // namespace alga

@@ -1,0 +1,409 @@
+// Error-rate supplement of the overlap graph (reference: main.cpp:300-355, GraphCreatorLI / GraphCreatorKmerBased /
+// GraphCreatorPairwiseKmerBranch, AlignmentControllerHybrid) -- alga_gpu_supplement of include/alga_gpu.h.
+//
+// The reference walks, per pass, every group of LI k-mers with equal hash and calls canAlign one pair at a time inside
+// an order-dependent loop (branch markers + the current neighbours of the source read).  canAlign is a pure function of
+// (read a, read b, offset), and so are the filters in front of it, so the work is restructured as
+//
+//     GPU   LI k-mers of every dead-end read            (Read.cpp:145-226; 70-bit rolling minimum per interval)
+//     host  scatter into the 2^20 hash-range buckets, std::sort per bucket (GraphCreatorKmerBased.cpp:94-106,
+//           202-259: the tie order inside a bucket is libstdc++'s, exactly as in the reference), and enumeration of
+//           every pair that passes the static filters of GraphCreatorPairwiseKmerBranch.cpp:43-62
+//     GPU   canAlign of all those pairs in one batch    (AlignmentControllerLowErrorRate.cpp:15-49, one pair per warp)
+//     host  replay of the ordered loop with the verdicts at hand (:64-84), Graph::addDirectedEdge,
+//           retainOnlySmallestOffset
+//
+// four times, with Read::priorities rotated after each pass (GraphCreatorLI.cpp:18-28).  No CPU fallback: the two
+// kernels are the only implementation of the k-mer minimum and of canAlign in this library.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <utility>
+#include <vector>
+
+#include "../../include/alga_gpu.h"
+#include "launch.h"
+
+namespace alga {
+
+namespace {
+
+inline int grid_for(uint64_t n_items, int per_block, const LaunchCfg &cfg, int max_blocks_per_sm = 16) {
+    uint64_t need = (n_items + per_block - 1) / per_block;
+    uint64_t cap = (uint64_t) cfg.sm_count * max_blocks_per_sm;
+    if (need < 1) need = 1;
+    return (int) (need < cap ? need : cap);
+}
+
+typedef unsigned __int128 u128;
+constexpr uint64_t kMaxHash = 1000000000000000003ull;  // Params::MAX_HASH_CONSIDERED (Params.cpp:721)
+
+// Read::getLIKmers (Read.cpp:145-226), one warp per read of `ids`.  Window p (0 <= p <= len - K) has the value
+// sum_k prio[nt(p + k)] * 4^(K-1-k) (K <= 63: fits 126 bits); interval iv = p / ceil((len - K + 1) / intervals) keeps
+// its leftmost minimal window.  Output per read: `intervals` slots of (hash mod 10^18+3, p), p = -1 for intervals
+// beyond the last window.
+__global__ void __launch_bounds__(256)
+li_kmers_kernel(ReadsDev R, const uint32_t *__restrict__ ids, uint32_t n_ids, uint32_t prio_tbl, int K, int intervals,
+                uint64_t *__restrict__ hash_out, int32_t *__restrict__ ind_out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t) blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t) gridDim.x * blockDim.x) >> 5;
+    for (uint64_t q = warp; q < n_ids; q += n_warps) {
+        const uint32_t id = ids[q];
+        const int len = (int) R.len[id];
+        const uint32_t *p = read_ptr(R, id);
+        const int n_win = len - K + 1;
+        const int ilen = (n_win + intervals - 1) / intervals;
+        for (int iv = 0; iv < intervals; iv++) {
+            const int w_lo = iv * ilen, w_hi = min(n_win, (iv + 1) * ilen);
+            u128 best = ~(u128) 0;
+            int best_p = 0x7FFFFFFF;
+            for (int w = w_lo + lane; w < w_hi; w += 32) {
+                u128 h = 0;
+                for (int k = 0; k < K; k++) {
+                    const uint32_t j = (uint32_t) (w + k);
+                    const uint32_t code = (__ldg(p + (j >> 4)) >> ((j & 15u) * 2u)) & 3u;
+                    h = (h << 2) + (u128) ((prio_tbl >> (2u * code)) & 3u);
+                }
+                if (h < best) {  // strict: within one lane the windows come in ascending order
+                    best = h;
+                    best_p = w;
+                }
+            }
+            for (int d = 16; d; d >>= 1) {
+                const uint64_t oh = __shfl_xor_sync(kFull, (uint64_t) (best >> 64), d);
+                const uint64_t ol = __shfl_xor_sync(kFull, (uint64_t) best, d);
+                const int op = __shfl_xor_sync(kFull, best_p, d);
+                const u128 o = ((u128) oh << 64) | (u128) ol;
+                if (o < best || (o == best && op < best_p)) {
+                    best = o;
+                    best_p = op;
+                }
+            }
+            if (lane == 0) {
+                const uint64_t slot = q * (uint64_t) intervals + (uint64_t) iv;
+                if (w_lo < w_hi) {
+                    hash_out[slot] = (uint64_t) (best % (u128) kMaxHash);
+                    ind_out[slot] = best_p;
+                } else {
+                    hash_out[slot] = 0;
+                    ind_out[slot] = -1;
+                }
+            }
+        }
+    }
+}
+
+thread_local char g_sup_err[512] = "";
+int sup_fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_sup_err, sizeof(g_sup_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define SCK(call)                                                                                              \
+    do {                                                                                                       \
+        cudaError_t e_ = (call);                                                                               \
+        if (e_ != cudaSuccess)                                                                                 \
+            return sup_fail(e_ == cudaErrorMemoryAllocation ? ALGA_E_NOMEM : ALGA_E_CUDA, "%s failed: %s (%s:%d)", \
+                            #call, cudaGetErrorString(e_), __FILE__, __LINE__);                                \
+    } while (0)
+
+struct Buf {  // device buffer freed on scope exit
+    void *p = nullptr;
+    ~Buf() {
+        if (p) cudaFree(p);
+    }
+    int alloc(size_t bytes) {
+        if (p) cudaFree(p);
+        p = nullptr;
+        SCK(cudaMalloc(&p, bytes ? bytes : 16));
+        return ALGA_OK;
+    }
+    template <class T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+struct Kmer {
+    uint32_t read;
+    uint64_t hash;
+    int ind;
+    uint32_t read_len;
+    bool operator<(const Kmer &o) const {  // Kmer.cpp:58-64
+        if (hash != o.hash) return hash < o.hash;
+        if (ind != o.ind) return ind > o.ind;
+        if (read_len != o.read_len) return read_len < o.read_len;
+        return false;
+    }
+};
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+const char *supplement_last_error() { return g_sup_err; }
+
+// Device-side pieces exposed to api.cu (alga_gpu_li_kmers) and used below.
+int run_li_kmers(const ReadsDev &R, const uint32_t *d_ids, uint32_t n_ids, const int32_t prio[4], int K, int intervals,
+                 uint64_t *d_hash, int32_t *d_ind, cudaStream_t s, const LaunchCfg &cfg) {
+    if (!n_ids) return ALGA_OK;
+    uint32_t tbl = 0;
+    for (int c = 0; c < 4; c++) tbl |= ((uint32_t) prio[c] & 3u) << (2 * c);
+    li_kmers_kernel<<<grid_for(n_ids, 8, cfg, 8), 256, 0, s>>>(R, d_ids, n_ids, tbl, K, intervals, d_hash, d_ind);
+    if (cfg.launches) (*cfg.launches)++;
+    SCK(cudaGetLastError());
+    return ALGA_OK;
+}
+
+int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_params *sp, alga_csr *gout, alga_timing *tm) {
+    const uint32_t n = h->n_reads;
+    if (gin->n_reads != n) return sup_fail(ALGA_E_INVALID, "graph has %u rows, read set %u reads", gin->n_reads, n);
+    if (sp->kmer_length < 1 || sp->kmer_length > 63 || sp->intervals < 1 || sp->intervals > 64)
+        return sup_fail(ALGA_E_INVALID, "kmer_length must be 1..63 and intervals 1..64");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return sup_fail(ALGA_E_CUDA, "no CUDA device available; libalga_gpu has no CPU fallback");
+    }
+    if (sp->device < 0 || sp->device >= ndev) return sup_fail(ALGA_E_INVALID, "device %d out of range", sp->device);
+    SCK(cudaSetDevice(sp->device));
+    LaunchCfg cfg;
+    uint64_t launches = 0;
+    cfg.launches = &launches;
+    SCK(cudaDeviceGetAttribute(&cfg.sm_count, cudaDevAttrMultiProcessorCount, sp->device));
+    const double t0 = now_ms();
+
+    // ---- reads to the device (once for all passes)
+    const uint64_t n_words = h->word_off ? h->word_off[n] : (uint64_t) n * h->stride_words;
+    Buf d_words, d_off, d_len;
+    if (d_words.alloc((size_t) n_words * 4 + kReadPadBytes) || d_len.alloc((size_t) (n ? n : 1) * 4)) return ALGA_E_NOMEM;
+    SCK(cudaMemcpy(d_words.p, h->words, (size_t) n_words * 4, cudaMemcpyHostToDevice));
+    SCK(cudaMemset((char *) d_words.p + (size_t) n_words * 4, 0, kReadPadBytes));
+    SCK(cudaMemcpy(d_len.p, h->len_nt, (size_t) n * 4, cudaMemcpyHostToDevice));
+    ReadsDev R{};
+    R.words = d_words.as<uint32_t>();
+    R.len = d_len.as<uint32_t>();
+    R.n = n;
+    R.stride = h->word_off ? 0 : h->stride_words;
+    if (h->word_off) {
+        if (d_off.alloc(((size_t) n + 1) * 8)) return ALGA_E_NOMEM;
+        SCK(cudaMemcpy(d_off.p, h->word_off, ((size_t) n + 1) * 8, cudaMemcpyHostToDevice));
+        R.word_off = d_off.as<uint64_t>();
+    }
+    const double t1 = now_ms();
+
+    // ---- graph rows + the reads that take part: dead ends only, fixed before the first pass (main.cpp:308-323)
+    std::vector<std::vector<std::pair<int, int>>> V(n);
+    std::vector<int> indeg(n, 0);
+    for (uint32_t i = 0; i < n; i++) {
+        V[i].reserve((size_t) (gin->row_off[i + 1] - gin->row_off[i]) + 2);
+        for (uint64_t k = gin->row_off[i]; k < gin->row_off[i + 1]; k++) {
+            V[i].push_back({gin->nbr[k], gin->off[k]});
+            indeg[(size_t) gin->nbr[k]]++;
+        }
+    }
+    std::vector<uint32_t> ids;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t len = h->len_nt[i];
+        const bool dead_end = (indeg[i] == 0 && !V[i].empty()) || (indeg[i] > 0 && V[i].empty());
+        // Read::getKmers (Read.cpp:70-72) returns nothing for reads shorter than KMER_LENGTH_BUCKET; getLIKmers needs
+        // len >= K (the reference exits otherwise; main.cpp:253-266 removed such reads before)
+        if (len == 0 || !dead_end || (int64_t) len < sp->kmer_length_bucket || (int64_t) len < sp->kmer_length) continue;
+        ids.push_back(i);
+    }
+    const uint32_t n_ids = (uint32_t) ids.size();
+    const int IV = sp->intervals;
+    Buf d_ids, d_hash, d_ind, d_pairs, d_verdict;
+    size_t pairs_cap = 0;
+    if (d_ids.alloc((size_t) n_ids * 4) || d_hash.alloc((size_t) n_ids * IV * 8) || d_ind.alloc((size_t) n_ids * IV * 4))
+        return ALGA_E_NOMEM;
+    if (n_ids) SCK(cudaMemcpy(d_ids.p, ids.data(), (size_t) n_ids * 4, cudaMemcpyHostToDevice));
+    std::vector<uint64_t> hh((size_t) n_ids * IV);
+    std::vector<int32_t> hi((size_t) n_ids * IV);
+    VerifyDev vd{sp->max_offset_pct, sp->min_offset, sp->min_overlap_area, sp->threshold_pct, sp->same_ends};
+
+    const long long kBucketsSort = 1048576ll;  // GraphCreatorKmerBased.cpp:140
+    std::vector<std::vector<Kmer>> buckets((size_t) kBucketsSort);
+    std::vector<int> neighbors(n, 1000000001);  // Params::INF
+    const int INF = 1000000001;
+    std::vector<int32_t> pairs;
+    std::vector<uint8_t> verdict;
+    std::vector<std::vector<uint8_t>> bm;
+    double gpu_ms = 0;
+    uint64_t pairs_total = 0;
+    int32_t prio[4] = {0, 1, 2, 3};
+
+    for (int pass = 0; pass < 4; pass++) {  // GraphCreatorLI.cpp:20-26
+        // ---- LI k-mers on the GPU
+        const double ta = now_ms();
+        if (int rc = run_li_kmers(R, d_ids.as<uint32_t>(), n_ids, prio, sp->kmer_length, IV, d_hash.as<uint64_t>(),
+                                  d_ind.as<int32_t>(), 0, cfg))
+            return rc;
+        if (n_ids) {
+            SCK(cudaMemcpy(hh.data(), d_hash.p, hh.size() * 8, cudaMemcpyDeviceToHost));
+            SCK(cudaMemcpy(hi.data(), d_ind.p, hi.size() * 4, cudaMemcpyDeviceToHost));
+        }
+        gpu_ms += now_ms() - ta;
+        // ---- buckets in the reference's fill order (reads by id, k-mers by interval), std::sort per bucket
+        for (auto &b : buckets) b.clear();
+        const double B = (double) kMaxHash;
+        for (uint32_t q = 0; q < n_ids; q++) {
+            for (int iv = 0; iv < IV; iv++) {
+                const size_t slot = (size_t) q * IV + (size_t) iv;
+                if (hi[slot] < 0) continue;
+                const Kmer k{ids[q], hh[slot], hi[slot], h->len_nt[ids[q]]};
+                const int ind = (int) ((kBucketsSort - 1) * ((double) k.hash / B));  // GraphCreatorKmerBased.cpp:233
+                buckets[(size_t) ind].push_back(k);
+            }
+        }
+        for (auto &b : buckets)
+            if (b.size() > 1) std::sort(b.begin(), b.end());
+        // ---- every pair that passes the static filters (GraphCreatorPairwiseKmerBranch.cpp:43-62), in loop order
+        pairs.clear();
+        for (auto &km : buckets) {
+            size_t p = 0, q = 0;
+            while (p < km.size()) {
+                while (q < km.size() && km[q].hash == km[p].hash) q++;
+                const int D = (int) (q - p);
+                for (int i = D - 2; i >= 0; i--) {
+                    const Kmer &ki = km[p + (size_t) i];
+                    for (int j = i + 1; j < D; j++) {
+                        const Kmer &kj = km[p + (size_t) j];
+                        if (ki.read == kj.read) continue;
+                        const int offset = ki.ind - kj.ind;
+                        if (offset < sp->min_offset) continue;
+                        if (100ll * offset > (long long) sp->max_offset_pct * (long long) ki.read_len) break;
+                        const int overlap = std::min((int) ki.read_len, (int) kj.read_len + offset) - offset;
+                        if (overlap < sp->min_overlap_area) continue;
+                        if ((int) kj.read_len + offset - (int) ki.read_len < 0) continue;
+                        pairs.push_back((int32_t) ki.read);
+                        pairs.push_back((int32_t) kj.read);
+                        pairs.push_back(offset);
+                    }
+                }
+                p = q;
+            }
+        }
+        const uint64_t n_pairs = pairs.size() / 3;
+        pairs_total += n_pairs;
+        // ---- canAlign of all of them in one batch on the GPU
+        const double tb = now_ms();
+        verdict.assign((size_t) n_pairs, 0);
+        if (n_pairs) {
+            if (n_pairs > pairs_cap) {
+                pairs_cap = (size_t) n_pairs + n_pairs / 4;
+                if (d_pairs.alloc(pairs_cap * 12) || d_verdict.alloc(pairs_cap)) return ALGA_E_NOMEM;
+            }
+            SCK(cudaMemcpy(d_pairs.p, pairs.data(), (size_t) n_pairs * 12, cudaMemcpyHostToDevice));
+            launch_verify_pairs(R, d_pairs.as<int32_t>(), n_pairs, vd, d_verdict.as<uint8_t>(), 0, cfg);
+            SCK(cudaGetLastError());
+            SCK(cudaMemcpy(verdict.data(), d_verdict.p, (size_t) n_pairs, cudaMemcpyDeviceToHost));
+        }
+        gpu_ms += now_ms() - tb;
+        // ---- replay of the ordered loop (:64-84) with the verdicts at hand
+        uint64_t next = 0;
+        for (auto &km : buckets) {
+            size_t p = 0, q = 0;
+            while (p < km.size()) {
+                while (q < km.size() && km[q].hash == km[p].hash) q++;
+                const int D = (int) (q - p);
+                if (D > 1) bm.assign((size_t) D, std::vector<uint8_t>((size_t) D, 0));
+                for (int i = D - 2; i >= 0; i--) {
+                    const Kmer &ki = km[p + (size_t) i];
+                    const int id1 = (int) ki.read;
+                    for (auto &x : V[(size_t) id1]) neighbors[(size_t) x.first] = x.second;
+                    for (int j = i + 1; j < D; j++) {
+                        const Kmer &kj = km[p + (size_t) j];
+                        const int id2 = (int) kj.read;
+                        if (id1 == id2) continue;
+                        const int offset = ki.ind - kj.ind;
+                        if (offset < sp->min_offset) continue;
+                        if (100ll * offset > (long long) sp->max_offset_pct * (long long) ki.read_len) break;
+                        const int overlap = std::min((int) ki.read_len, (int) kj.read_len + offset) - offset;
+                        if (overlap < sp->min_overlap_area) continue;
+                        if ((int) kj.read_len + offset - (int) ki.read_len < 0) continue;
+                        const uint8_t can = verdict[(size_t) next++];
+                        if (!bm[(size_t) i][(size_t) j]) {
+                            if (neighbors[(size_t) id2] > offset && can) {
+                                // Graph::addDirectedEdge (Graph.cpp:53-71): one entry per target, smallest offset
+                                bool found = false;
+                                for (auto &e : V[(size_t) id1]) {
+                                    if (e.first == id2) {
+                                        if (offset < e.second) e.second = offset;
+                                        found = true;
+                                        break;
+                                    }
+                                }
+                                if (!found) V[(size_t) id1].push_back({id2, offset});
+                                neighbors[(size_t) id2] = offset;
+                            }
+                            if (neighbors[(size_t) id2] != INF) {
+                                bm[(size_t) i][(size_t) j] = 1;
+                                for (int t = 0; t < D; t++) bm[(size_t) i][(size_t) t] |= bm[(size_t) j][(size_t) t];
+                            }
+                        }
+                    }
+                    for (auto &x : V[(size_t) id1]) neighbors[(size_t) x.first] = INF;
+                }
+                p = q;
+            }
+        }
+        // ---- retainOnlySmallestOffset (GraphCreatorKmerBased.cpp:87; main.cpp:346 after the last pass)
+        for (auto &row : V) {
+            if (row.size() < 2) continue;
+            std::sort(row.begin(), row.end());
+            size_t w = 0;
+            for (size_t k = 0; k < row.size(); k++)
+                if (w == 0 || row[w - 1].first != row[k].first) row[w++] = row[k];
+            row.resize(w);
+        }
+        std::rotate(prio, prio + 1, prio + 4);
+    }
+
+    // ---- result
+    uint64_t E = 0;
+    for (auto &row : V) E += row.size();
+    memset(gout, 0, sizeof(*gout));
+    gout->n_reads = n;
+    gout->n_edges = E;
+    gout->row_off = (uint64_t *) malloc(((size_t) n + 1) * 8);
+    gout->nbr = (int32_t *) malloc((size_t) (E ? E : 1) * 4);
+    gout->off = (int32_t *) malloc((size_t) (E ? E : 1) * 4);
+    if (!gout->row_off || !gout->nbr || !gout->off) {
+        free(gout->row_off);
+        free(gout->nbr);
+        free(gout->off);
+        memset(gout, 0, sizeof(*gout));
+        return sup_fail(ALGA_E_NOMEM, "out of host memory for %llu edges", (unsigned long long) E);
+    }
+    uint64_t w = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        gout->row_off[i] = w;
+        for (auto &e : V[i]) {
+            gout->nbr[w] = e.first;
+            gout->off[w] = e.second;
+            w++;
+        }
+    }
+    gout->row_off[n] = w;
+    if (tm) {
+        memset(tm, 0, sizeof(*tm));
+        tm->h2d_ms = t1 - t0;
+        tm->device_ms = gpu_ms;  // k-mer + canAlign kernels incl. their transfers
+        tm->total_ms = now_ms() - t0;
+        tm->kernel_launches = launches;
+        tm->stage_ms[5] = (double) n_ids;        // diagnostics: dead-end reads that took part,
+        tm->stage_ms[6] = (double) pairs_total;  // pairs verified on the GPU over the four passes
+    }
+    return ALGA_OK;
+}
+
+}  // namespace alga

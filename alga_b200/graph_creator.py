@@ -196,3 +196,58 @@ def verify_pairs(reads: ReadSet, pairs: np.ndarray, threshold_pct: int, max_offs
     vp = _lib.VerifyParams(max_offset_pct, min_offset, min_overlap_area, threshold_pct, same_ends, device)
     _lib.check(lib.alga_gpu_verify_pairs(C.byref(st), pairs.ctypes.data, pairs.shape[0], C.byref(vp), out.ctypes.data))
     return out
+
+
+def li_kmers(reads: ReadSet, ids: np.ndarray, priorities=(0, 1, 2, 3), kmer_length: int = 35, intervals: int = 6,
+             device: int = 0):
+    """``Read::getLIKmers`` (Read.cpp:145-226) of the reads ``ids``: (hash [n, intervals] uint64, ind [n, intervals] int32,
+    ind = -1 for intervals beyond the last window)."""
+    lib = _lib.load()
+    ids = np.ascontiguousarray(ids, dtype=np.uint32)
+    h = np.zeros((ids.shape[0], intervals), np.uint64)
+    ind = np.zeros((ids.shape[0], intervals), np.int32)
+    pr = np.ascontiguousarray(priorities, dtype=np.int32)
+    st = _reads_struct(reads)
+    _lib.check(lib.alga_gpu_li_kmers(C.byref(st), ids.ctypes.data, ids.shape[0], pr.ctypes.data, kmer_length, intervals,
+                                     device, h.ctypes.data, ind.ctypes.data))
+    return h, ind
+
+
+class GraphCreatorLI:
+    """Drop-in for the error-rate supplement of the reference driver (main.cpp:300-355): ``new GraphCreatorLI(READS, G)``,
+    the dead-end flags of main.cpp:308-323, the Params of main.cpp:332-340 and ``startAlignmentGraphCreation()`` followed
+    by ``G->retainOnlySmallestOffset()`` (main.cpp:343-346).
+
+    ``threshold_pct`` = MINIMAL_OVERLAP_FOR_LCS_LOW_ERROR (99 - ERROR_RATE), ``max_offset_pct`` =
+    MAX_OFFSET_CONSIDERED_FOR_ALIGNMENT ((1 - SCALE) * avg_len / 2), ``min_overlap_area`` = MIN_OVERLAP_AREA
+    ((1 + SCALE) * avg_len / 2), ``kmer_length_bucket`` = KMER_LENGTH_BUCKET (main.cpp:104)."""
+
+    def __init__(self, reads: ReadSet, graph: Graph, threshold_pct: int, max_offset_pct: int, min_overlap_area: int,
+                 kmer_length_bucket: int, min_offset: int = 0, same_ends: int = 3, kmer_length: int = 35,
+                 intervals: int = 6, device: int = 0):
+        self.reads, self.graph_in = reads, graph
+        self.params = _lib.SupParams(max_offset_pct, min_offset, min_overlap_area, threshold_pct, same_ends, kmer_length,
+                                     intervals, kmer_length_bucket, device)
+        self.graph: Graph | None = None
+        self.timing: dict | None = None
+
+    def startAlignmentGraphCreation(self) -> Graph:
+        lib = _lib.load()
+        g = self.graph_in
+        row_off = np.ascontiguousarray(g.row_off, dtype=np.uint64)
+        nbr = np.ascontiguousarray(g.nbr, dtype=np.int32)
+        off = np.ascontiguousarray(g.off, dtype=np.int32)
+        cin = _lib.Csr(g.n, g.n_edges, row_off.ctypes.data_as(C.POINTER(C.c_uint64)), nbr.ctypes.data_as(C.POINTER(C.c_int32)),
+                       off.ctypes.data_as(C.POINTER(C.c_int32)), 1)
+        cout = _lib.Csr()
+        tm = _lib.Timing()
+        st = _reads_struct(self.reads)
+        _lib.check(lib.alga_gpu_supplement(C.byref(st), C.byref(cin), C.byref(self.params), C.byref(cout), C.byref(tm)))
+        try:
+            self.graph = _csr_to_graph(cout)
+        finally:
+            lib.alga_gpu_free_csr(C.byref(cout))
+        self.timing = {"h2d_ms": tm.h2d_ms, "device_ms": tm.device_ms, "total_ms": tm.total_ms,
+                       "kernel_launches": tm.kernel_launches, "n_dead_end_reads": int(tm.stage_ms[5]),
+                       "n_pairs_verified": int(tm.stage_ms[6])}
+        return self.graph

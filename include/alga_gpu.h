@@ -219,6 +219,34 @@ typedef struct {
 int alga_gpu_verify_pairs(const alga_reads *reads, const int32_t *pairs, uint64_t n_pairs,
                           const alga_verify_params *params, uint8_t *verdict);
 
+/* ---- error-rate supplement -------------------------------------------------------------------
+ * Drop-in for main.cpp:300-355 (runs when --error_rate > 0.01): GraphCreatorLI / GraphCreatorPairwiseKmerBranch over the
+ * dead-end reads of the graph produced by alga_gpu_prefsuf_build, four passes with rotated nucleotide priorities,
+ * followed by Graph::retainOnlySmallestOffset (main.cpp:346).  LI k-mer extraction (Read.cpp:145-226) and all canAlign
+ * calls (AlignmentControllerHybrid.cpp:46-83) run on the GPU; the bucket sort and the order-dependent edge replay
+ * (GraphCreatorKmerBased.cpp:94-136, GraphCreatorPairwiseKmerBranch.cpp:16-97) run on the host with libstdc++'s
+ * std::sort, so ties inside a bucket fall exactly as in a reference built with the same toolchain. */
+typedef struct {
+    int32_t max_offset_pct;     /* Params::MAX_OFFSET_CONSIDERED_FOR_ALIGNMENT = (1 - SCALE) * avg_len / 2 (main.cpp:335) */
+    int32_t min_offset;         /* Params::MIN_OFFSET_FOR_ALIGNMENT */
+    int32_t min_overlap_area;   /* Params::MIN_OVERLAP_AREA = (1 + SCALE) * avg_len / 2 (main.cpp:333) */
+    int32_t threshold_pct;      /* Params::MINIMAL_OVERLAP_FOR_LCS_LOW_ERROR = 99 - ERROR_RATE (main.cpp:336) */
+    int32_t same_ends;          /* Params::ALIGNMENT_CONTROLLER_SAME_ENDS_LENGTH (3) */
+    int32_t kmer_length;        /* Params::LI_KMER_LENGTH = 35 (main.cpp:340) */
+    int32_t intervals;          /* Params::LI_KMER_INTERVALS = 6 (main.cpp:339) */
+    int32_t kmer_length_bucket; /* Params::KMER_LENGTH_BUCKET (main.cpp:104): shorter reads contribute no k-mers */
+    int32_t device;
+} alga_sup_params;
+/* graph_in: Graph::V after main.cpp:291 (host CSR); graph_out: Graph::V after main.cpp:346 (malloc'ed host CSR, release
+ * with alga_gpu_free_csr).  timing (may be NULL): h2d_ms, device_ms (kernels + their transfers), total_ms,
+ * kernel_launches; stage_ms[5] = dead-end reads that took part, stage_ms[6] = pairs verified. */
+int alga_gpu_supplement(const alga_reads *reads, const alga_csr *graph_in, const alga_sup_params *params,
+                        alga_csr *graph_out, alga_timing *timing);
+/* Read::getLIKmers for the reads ids[0 .. n_ids) (host buffers): hash_out / ind_out have n_ids * intervals entries,
+ * ind = -1 for intervals beyond the last window; priorities[c] = rank of nucleotide code c (Read::priorities). */
+int alga_gpu_li_kmers(const alga_reads *reads, const uint32_t *ids, uint32_t n_ids, const int32_t priorities[4],
+                      int32_t kmer_length, int32_t intervals, int32_t device, uint64_t *hash_out, int32_t *ind_out);
+
 /* ---- misc ---------------------------------------------------------------------------------- */
 /* Page-locked host memory for callers that stage the packed reads themselves (the shim gathers the blocks of
  * vector<Read*> straight into such a buffer, so the upload runs at full host->device rate).  NULL on failure. */

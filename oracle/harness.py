@@ -82,3 +82,27 @@ def run_verify(reads, pairs, thr, max_offset_pct, min_overlap_area, min_offset=0
         subprocess.run([HARNESS, "verify", rp, pp, vp], check=True, stdout=subprocess.DEVNULL,
                        stderr=subprocess.DEVNULL, cwd=d)
         return np.fromfile(vp, dtype=np.uint8)
+
+
+def write_edges(path, n, edges):
+    e = np.ascontiguousarray(edges, dtype="<i4").reshape(-1, 3)
+    with open(path, "wb") as f:
+        f.write(b"ALGE")
+        f.write(struct.pack("<IQ", n, e.shape[0]))
+        f.write(e.tobytes())
+
+
+def run_supplement(reads, edges_in, threshold_pct, max_offset_pct, min_overlap_area, kmer_length_bucket, min_offset=0,
+                   threads=1):
+    """Run the reference's error-rate supplement (main.cpp:300-355) on a given graph; returns (edges, info)."""
+    if not available():
+        raise RuntimeError("oracle/_ref/alga_ref_harness is not built (make -C oracle ref)")
+    with tempfile.TemporaryDirectory() as d:
+        rp, ip, op = (os.path.join(d, x) for x in ("in.algr", "in.alge", "out.alge"))
+        write_reads(rp, reads, 0, 0, min_offset)
+        write_edges(ip, reads.n, edges_in)
+        out = subprocess.run([HARNESS, "supplement", rp, ip, op, str(min_overlap_area), str(max_offset_pct),
+                              str(threshold_pct), str(kmer_length_bucket), str(threads)], check=True,
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, cwd=d)
+        info = json.loads(out.stdout.decode().strip().splitlines()[-1])
+        return read_edges(op), info

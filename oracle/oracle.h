@@ -47,6 +47,25 @@ typedef struct {
 void oracle_verify_pairs(const oracle_reads *r, const int32_t *pairs, uint64_t n_pairs,
                          const oracle_verify_params *p, uint8_t *verdict);
 
+/* Error-rate supplement (main.cpp:300-355: GraphCreatorLI over the dead-end reads of the graph after main.cpp:291,
+ * followed by retainOnlySmallestOffset).  edges_in / result: (src, dst, offset) triples, rows in id order.
+ * Implemented in supplement_oracle.cpp (C++: bucket tie order = libstdc++ std::sort, as in the reference). */
+typedef struct {
+    int32_t max_offset_pct;     /* Params::MAX_OFFSET_CONSIDERED_FOR_ALIGNMENT = (1 - SCALE) * avg_len / 2 (main.cpp:335) */
+    int32_t min_offset;         /* Params::MIN_OFFSET_FOR_ALIGNMENT */
+    int32_t min_overlap_area;   /* Params::MIN_OVERLAP_AREA = (1 + SCALE) * avg_len / 2 (main.cpp:333) */
+    int32_t threshold_pct;      /* Params::MINIMAL_OVERLAP_FOR_LCS_LOW_ERROR = 99 - ERROR_RATE (main.cpp:336) */
+    int32_t same_ends;          /* Params::ALIGNMENT_CONTROLLER_SAME_ENDS_LENGTH (3) */
+    int32_t kmer_length;        /* Params::LI_KMER_LENGTH = 35 (main.cpp:340) */
+    int32_t intervals;          /* Params::LI_KMER_INTERVALS = 6 (main.cpp:339) */
+    int32_t kmer_length_bucket; /* Params::KMER_LENGTH_BUCKET (main.cpp:104): shorter reads contribute no k-mers */
+} oracle_sup_params;
+/* Read::getLIKmers (Read.cpp:145-226) of the reads ids[0 .. n_ids): `intervals` slots each, ind = -1 where absent. */
+void oracle_li_kmers(const oracle_reads *r, const uint32_t *ids, uint32_t n_ids, const int32_t *prio, int32_t K,
+                     int32_t intervals, uint64_t *hash_out, int32_t *ind_out);
+int32_t *oracle_supplement(const oracle_reads *r, const int32_t *edges_in, uint64_t n_in, const oracle_sup_params *p,
+                           uint64_t *n_out);
+
 void oracle_free(void *p);
 
 #ifdef __cplusplus

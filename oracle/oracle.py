@@ -21,8 +21,14 @@ class _VerifyParams(C.Structure):
                 ("threshold_pct", C.c_int32), ("same_ends", C.c_int32)]
 
 
+class _SupParams(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("max_offset_pct", "min_offset", "min_overlap_area", "threshold_pct", "same_ends",
+                                          "kmer_length", "intervals", "kmer_length_bucket")]
+
+
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(HERE, f) for f in ("prefsuf_oracle.c", "verify_oracle.c", "oracle.h", "Makefile")]
+    srcs = [os.path.join(HERE, f) for f in ("prefsuf_oracle.c", "verify_oracle.c", "supplement_oracle.cpp", "oracle.h",
+                                            "Makefile")]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         subprocess.run(["make", "-C", HERE, "liboracle.so"], check=True, stdout=subprocess.DEVNULL)
     return LIB
@@ -44,6 +50,12 @@ def _load():
         _lib.oracle_verify_pairs.restype = None
         _lib.oracle_verify_pairs.argtypes = [C.POINTER(_Reads), C.c_void_p, C.c_uint64, C.POINTER(_VerifyParams),
                                              C.c_void_p]
+        _lib.oracle_supplement.restype = C.POINTER(C.c_int32)
+        _lib.oracle_supplement.argtypes = [C.POINTER(_Reads), C.c_void_p, C.c_uint64, C.POINTER(_SupParams),
+                                           C.POINTER(C.c_uint64)]
+        _lib.oracle_li_kmers.restype = None
+        _lib.oracle_li_kmers.argtypes = [C.POINTER(_Reads), C.c_void_p, C.c_uint32, C.c_void_p, C.c_int32, C.c_int32,
+                                         C.c_void_p, C.c_void_p]
         _lib.oracle_free.argtypes = [C.c_void_p]
     return _lib
 
@@ -84,3 +96,31 @@ def verify_pairs(reads, pairs, threshold_pct, max_offset_pct, min_overlap_area, 
     out = np.zeros(pairs.shape[0], np.uint8)
     lib.oracle_verify_pairs(C.byref(rs), pairs.ctypes.data, pairs.shape[0], C.byref(vp), out.ctypes.data)
     return out
+
+
+def supplement(reads, edges_in, threshold_pct, max_offset_pct, min_overlap_area, kmer_length_bucket, min_offset=0,
+               same_ends=3, kmer_length=35, intervals=6) -> np.ndarray:
+    """Graph after the error-rate supplement (main.cpp:300-355): (E, 3) int32 edges sorted by (src, dst)."""
+    lib = _load()
+    rs = _reads_struct(reads)
+    e = np.ascontiguousarray(edges_in, dtype=np.int32).reshape(-1, 3)
+    sp = _SupParams(max_offset_pct, min_offset, min_overlap_area, threshold_pct, same_ends, kmer_length, intervals,
+                    kmer_length_bucket)
+    ne = C.c_uint64(0)
+    p = lib.oracle_supplement(C.byref(rs), e.ctypes.data, e.shape[0], C.byref(sp), C.byref(ne))
+    out = np.ctypeslib.as_array(p, shape=(max(ne.value, 1) * 3,))[: ne.value * 3].reshape(-1, 3).copy()
+    lib.oracle_free(p)
+    return out
+
+
+def li_kmers(reads, ids, priorities=(0, 1, 2, 3), kmer_length=35, intervals=6):
+    """Read::getLIKmers of the reads ``ids``: (hash [n, intervals] uint64, ind [n, intervals] int32, -1 = absent)."""
+    lib = _load()
+    rs = _reads_struct(reads)
+    ids = np.ascontiguousarray(ids, dtype=np.uint32)
+    pr = np.ascontiguousarray(priorities, dtype=np.int32)
+    h = np.zeros((ids.shape[0], intervals), np.uint64)
+    ind = np.zeros((ids.shape[0], intervals), np.int32)
+    lib.oracle_li_kmers(C.byref(rs), ids.ctypes.data, ids.shape[0], pr.ctypes.data, kmer_length, intervals, h.ctypes.data,
+                        ind.ctypes.data)
+    return h, ind

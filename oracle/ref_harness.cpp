@@ -12,7 +12,8 @@
 //   main.cpp:282      startAlignmentGraphCreation()
 //   main.cpp:286-291  clear(); delete; G->retainOnlySmallestOffset()
 // and, with --verify, AlignmentControllerLowErrorRate::canAlign on a pair list
-// (AlignmentControllerHybrid.cpp:46-83 -> AlignmentControllerLowErrorRate.cpp:15-49).
+// (AlignmentControllerHybrid.cpp:46-83 -> AlignmentControllerLowErrorRate.cpp:15-49), and, with
+// `supplement`, the error-rate supplement GraphCreatorLI (main.cpp:300-355) on a given graph.
 //
 // File formats are documented in oracle/README.md (ALGR = reads, ALGE = edges).
 #include <Global.h>
@@ -21,6 +22,7 @@
 #include <DataStructures/Read.h>
 #include <DataStructures/Graph.h>
 #include <GraphCreators/GraphCreatorPrefSuf.h>
+#include <GraphCreators/GraphCreatorLI.h>
 #include <AlignmentControllers/AlignmentControllerHybrid.h>
 #include <AlignmentControllers/AlignmentControllerLowErrorRate.h>
 
@@ -176,6 +178,72 @@ int run_verify(const char *in_path, const char *pairs_path, const char *out_path
     return 0;
 }
 
+// Error-rate supplement (main.cpp:300-355) on a given read set and graph:
+//   main.cpp:306      new GraphCreatorLI(READS, G)
+//   main.cpp:308-323  flags from in-/out-degrees (dead ends only)
+//   main.cpp:332-340  Params of the supplement (passed in: they derive from the average read length / error rate)
+//   main.cpp:343-346  startAlignmentGraphCreation(); G->retainOnlySmallestOffset()
+// edges_in: ALGE file (the graph after main.cpp:291); out: ALGE file of the graph after main.cpp:346.
+int run_supplement(const char *reads_path, const char *edges_path, const char *out_path, int moa, int max_off, int thr,
+                   int kmer_bucket_len, int threads) {
+    ReadsFile r = load_reads(reads_path);
+    Params::THREADS = threads;
+    Params::MIN_OFFSET_FOR_ALIGNMENT = r.min_offset;
+    build_reads(r);
+    Global::GRAPH = Graph((int) r.n);
+    Graph *G = &Global::GRAPH;
+    {
+        FILE *f = fopen(edges_path, "rb");
+        if (!f) die("cannot open edges file");
+        char magic[4];
+        uint32_t n;
+        uint64_t E;
+        if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "ALGE", 4) != 0) die("bad edges magic");
+        if (fread(&n, 4, 1, f) != 1 || fread(&E, 8, 1, f) != 1 || n != r.n) die("bad edges header");
+        std::vector<int32_t> t(3 * E);
+        if (E && fread(t.data(), 4, 3 * E, f) != 3 * E) die("short edges");
+        fclose(f);
+        for (uint64_t i = 0; i < E; i++) G->pushDirectedEdge(t[3 * i], t[3 * i + 1], t[3 * i + 2]);
+    }
+    double t0 = now_s();
+    GraphCreator *graphCreator = new GraphCreatorLI(&Global::READS, G);
+    VI *inDeg = G->getInDegrees();
+    for (int i = 0; i < G->size(); i++) {
+        graphCreator->setAlignFrom(i, false);
+        graphCreator->setAlignTo(i, false);
+        if ((*inDeg)[i] == 0 && (*G)[i].size() > 0) graphCreator->setAlignTo(i, true);
+        if ((*inDeg)[i] > 0 && (*G)[i].size() == 0) graphCreator->setAlignFrom(i, true);
+    }
+    delete inDeg;
+    Params::MIN_OVERLAP_AREA = moa;
+    Params::MAX_OFFSET_CONSIDERED_FOR_ALIGNMENT = max_off;
+    Params::MINIMAL_OVERLAP_FOR_LCS_LOW_ERROR = thr;
+    Params::LI_KMER_INTERVALS = 6;
+    Params::LI_KMER_LENGTH = 35;
+    Params::KMER_LENGTH_BUCKET = kmer_bucket_len;
+    graphCreator->startAlignmentGraphCreation();
+    G->retainOnlySmallestOffset();
+    delete graphCreator;
+    double t1 = now_s();
+    uint64_t E = 0;
+    for (int i = 0; i < G->size(); i++) E += (*G)[i].size();
+    FILE *f = fopen(out_path, "wb");
+    if (!f) die("cannot open output");
+    fwrite("ALGE", 1, 4, f);
+    uint32_t n = r.n;
+    fwrite(&n, 4, 1, f);
+    fwrite(&E, 8, 1, f);
+    for (int i = 0; i < G->size(); i++)
+        for (auto &e : (*G)[i]) {
+            int32_t t[3] = {i, e.first, e.second};
+            fwrite(t, 4, 3, f);
+        }
+    fclose(f);
+    printf("{\"n\": %u, \"edges\": %llu, \"threads\": %d, \"supplement_s\": %.6f}\n", r.n, (unsigned long long) E, threads,
+           t1 - t0);
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -186,9 +254,14 @@ int main(int argc, char **argv) {
         return run_prefsuf(argv[2], argv[3], threads);
     }
     if (argc >= 5 && strcmp(argv[1], "verify") == 0) return run_verify(argv[2], argv[3], argv[4]);
+    if (argc >= 9 && strcmp(argv[1], "supplement") == 0)
+        return run_supplement(argv[2], argv[3], argv[4], atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]),
+                              argc >= 10 ? atoi(argv[9]) : 1);
     fprintf(stderr,
             "usage: %s prefsuf <reads.algr> <edges.alge|-> [threads]\n"
-            "       %s verify  <reads.algr> <pairs.algp> <verdict.bin>\n",
-            argv[0], argv[0]);
+            "       %s verify  <reads.algr> <pairs.algp> <verdict.bin>\n"
+            "       %s supplement <reads.algr> <edges_in.alge> <edges_out.alge> <min_overlap_area> <max_offset_pct> "
+            "<threshold_pct> <kmer_length_bucket> [threads]\n",
+            argv[0], argv[0], argv[0]);
     return 2;
 }

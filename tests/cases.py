@@ -129,3 +129,28 @@ def verify_case(seed=31, n_reads=4000, genome=20000, read_len=144, error=0.01):
     pairs = np.array([p for p in pairs if p[2] >= 0], dtype=np.int32)
     vp = dict(threshold_pct=97, max_offset_pct=32, min_overlap_area=111, min_offset=0)
     return rs, pairs, vp
+
+
+def supplement_params(avg_len: float, error_rate_pct: int = 2, scale: float = 0.55):
+    """Params of the supplement as the reference driver derives them (main.cpp:93-115, 332-340), float arithmetic as there."""
+    LEN = int(avg_len) + 6
+    L = int(np.float32(LEN) * np.float32(scale))
+    return dict(threshold_pct=99 - error_rate_pct,
+                max_offset_pct=int((np.float32(1.0) - np.float32(scale)) * np.float32(avg_len) / 2),
+                min_overlap_area=int((np.float32(1.0) + np.float32(scale)) * np.float32(avg_len) / 2),
+                kmer_length_bucket=min(2 * L // 3, 60))
+
+
+SUPPLEMENT_CASES = ["sup_cfg3", "sup_varlen"]
+
+
+def supplement_case(name):
+    """-> (ReadSet, min_overlap, rs_min_overlap, supplement params): the graph to supplement is the GraphCreatorPrefSuf
+    result on the same reads (main.cpp:282-291)."""
+    if name == "sup_cfg3":      # BASELINE config 3 shape: 2x150 bp, 1 % substitutions, --error_rate=0.02
+        w = synth.make_config("cfg3", scale=0.01)
+        return w.reads, w.params.min_overlap, w.params.rs_min_overlap, supplement_params(float(w.reads.len_nt.mean()))
+    if name == "sup_varlen":    # ragged lengths 90..150 (some shorter than KMER_LENGTH_BUCKET never occur here), errors, repeats
+        rs = synth.make_variable_length(30000, 3000, 90, 150, seed=17, error=0.01, repeats=3)
+        return rs, 66, 94, supplement_params(float(rs.len_nt[rs.len_nt > 0].mean()))
+    raise KeyError(name)

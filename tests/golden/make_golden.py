@@ -10,7 +10,8 @@ set and the edge set is stored as `<case>.npz`:
     input_sha  sha256 over len_nt | align_from | align_to | word_off | words  -- guards generator drift
     params     (min_overlap, rs_min_overlap, min_offset)
 `verify_pairs.npz` holds (pairs, verdicts) of AlignmentControllerHybrid::canAlign evaluated by the
-reference on candidate pairs of the cfg3_small read set.
+reference on candidate pairs of the cfg3_small read set; `sup_*.npz` hold the graph before and after the reference's
+error-rate supplement (GraphCreatorLI, main.cpp:300-355) on the supplement cases of tests/cases.py.
 """
 import hashlib
 import os
@@ -22,7 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from oracle import harness  # noqa: E402
-from tests.cases import CASES, build_case, verify_case  # noqa: E402
+from tests.cases import CASES, SUPPLEMENT_CASES, build_case, supplement_case, verify_case  # noqa: E402
 
 
 def input_sha(rs) -> str:
@@ -49,6 +50,16 @@ def main():
     np.savez_compressed(os.path.join(HERE, "verify_pairs.npz"), pairs=pairs, verdict=verdict,
                         input_sha=np.array(input_sha(rs)))
     print(f"verify_pairs: {pairs.shape[0]} pairs, {int(verdict.sum())} accepted")
+    # error-rate supplement (main.cpp:300-355, --threads=1) on top of the reference's own pre-supplement graph
+    for name in SUPPLEMENT_CASES:
+        rs, lmin, rsmin, sp = supplement_case(name)
+        before, _ = harness.run_prefsuf(rs, lmin, rsmin, 0, threads=1)
+        after, _ = harness.run_supplement(rs, before, sp["threshold_pct"], sp["max_offset_pct"], sp["min_overlap_area"],
+                                          sp["kmer_length_bucket"], threads=1)
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), before=before, after=after, input_sha=np.array(input_sha(rs)),
+                            params=np.array([lmin, rsmin, sp["threshold_pct"], sp["max_offset_pct"], sp["min_overlap_area"],
+                                             sp["kmer_length_bucket"]], np.int32))
+        print(f"{name}: n={rs.n} E {before.shape[0]} -> {after.shape[0]}")
 
 
 if __name__ == "__main__":

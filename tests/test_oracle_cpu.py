@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import harness, oracle
-from tests.cases import CASES, build_case, verify_case
+from tests.cases import CASES, SUPPLEMENT_CASES, build_case, supplement_case, verify_case
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -77,3 +77,48 @@ def test_edges_are_exact_overlaps():
         sb, sc = rs.sequence(int(b)), rs.sequence(int(c))
         L = len(sb) - int(o)
         assert L >= lmin and sb[int(o):] == sc[:L]
+
+
+@pytest.mark.parametrize("name", SUPPLEMENT_CASES)
+def test_oracle_supplement_matches_reference_golden(name):
+    """Error-rate supplement (main.cpp:300-355): the C++ restatement against the graph the unmodified reference produced."""
+    rs, lmin, rsmin, sp = supplement_case(name)
+    z = load_golden(name)
+    assert str(z["input_sha"]) == input_sha(rs), "seeded generator drifted: regenerate tests/golden"
+    assert z["params"].tolist() == [lmin, rsmin, sp["threshold_pct"], sp["max_offset_pct"], sp["min_overlap_area"],
+                                    sp["kmer_length_bucket"]]
+    before = oracle.prefsuf(rs, lmin, rsmin, 0)
+    assert np.array_equal(before, z["before"])
+    after = oracle.supplement(rs, before, **sp)
+    assert after.shape[0] > before.shape[0]
+    assert np.array_equal(after, z["after"])
+
+
+@pytest.mark.skipif(not harness.available(), reason="oracle/_ref/alga_ref_harness not present")
+def test_oracle_supplement_matches_reference_live():
+    rs, lmin, rsmin, sp = supplement_case("sup_cfg3")
+    before = oracle.prefsuf(rs, lmin, rsmin, 0)
+    want, _ = harness.run_supplement(rs, before, sp["threshold_pct"], sp["max_offset_pct"], sp["min_overlap_area"],
+                                     sp["kmer_length_bucket"], threads=1)
+    assert np.array_equal(oracle.supplement(rs, before, **sp), want)
+
+
+def test_li_kmer_definition():
+    """oracle li_kmers follows Read.cpp:145-226: per interval the leftmost minimal K-mer under the priorities."""
+    rs, *_ = supplement_case("sup_varlen")
+    ids = np.flatnonzero(rs.len_nt >= 60)[:40].astype(np.uint32)
+    K, IV = 35, 6
+    for prio in ((0, 1, 2, 3), (1, 2, 3, 0), (3, 0, 1, 2)):
+        h, ind = oracle.li_kmers(rs, ids, prio, K, IV)
+        for q, i in enumerate(ids):
+            c = [prio[int(x)] for x in rs.codes(int(i))]
+            n_win = len(c) - K + 1
+            ilen = -(-n_win // IV)
+            vals = [sum(c[p + k] << (2 * (K - 1 - k)) for k in range(K)) for p in range(n_win)]
+            for iv in range(IV):
+                lo, hi = iv * ilen, min(n_win, (iv + 1) * ilen)
+                if lo >= hi:
+                    assert ind[q, iv] == -1
+                    continue
+                best = min(range(lo, hi), key=lambda p: (vals[p], p))
+                assert ind[q, iv] == best and int(h[q, iv]) == vals[best] % (10 ** 18 + 3)
