@@ -332,9 +332,27 @@ def run_ours(args):
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (traffic or {}).get("pipeline_dram_bytes_per_step"), "peak_source": peak_src,
-                "kernel": "whole device pipeline of one step (index + phase1 + transpose + phase2 + csr), per GPU",
+                "kernel": "whole device pipeline of one step (index + phase1 + phase2 + csr), per GPU",
                 "alg_bytes_per_node": b_alg, "nodes_per_gpu": nodes_per_gpu, "stage_ms": stages, "diag": diag,
                 "traffic_detail": traffic}
+    if world == 1 and stages.get("phase2"):
+        # the dominant kernels on their own: algorithmic bytes of their share of the overlap lengths (SURVEY.md 8-d:
+        # 64 B per node and length, + the CSR output for phase 2) over their CUDA-event time inside this run
+        rs_, lmin_ = params.rs_min_overlap, params.min_overlap
+        n_l2 = max(0, len_nt - max(rs_, lmin_) + 1)
+        n_l1 = max(0, min(rs_, len_nt + 1) - lmin_)
+        b2 = 64 * n_l2 + 8 * n_edges / max(n_nodes_total, 1) + 8
+        b1 = 64 * n_l1
+        k2 = nodes_per_gpu * b2 / (stages["phase2"] / 1e3) / 1e9
+        k1 = nodes_per_gpu * b1 / (stages["phase1"] / 1e3) / 1e9
+        roofline["dominant_kernel"] = {"kernel": "phase2_tpr_kernel (+ its spill kernels; 51 % of the step)", "bound": "hbm",
+                                       "achieved": k2, "peak": peak, "unit": "GB/s", "frac": k2 / peak,
+                                       "alg_bytes_per_node": b2, "ms": stages["phase2"],
+                                       "traffic": (traffic or {}).get("phase2_tpr_kernel")}
+        roofline["second_kernel"] = {"kernel": "phase1_tpr_kernel (+ its queue kernel; 37 % of the step)", "bound": "hbm",
+                                     "achieved": k1, "peak": peak, "unit": "GB/s", "frac": k1 / peak,
+                                     "alg_bytes_per_node": b1, "ms": stages["phase1"],
+                                     "traffic": (traffic or {}).get("phase1_tpr_kernel")}
 
     cpu = None
     if world == 1 and not args.no_cpu:

@@ -1,6 +1,6 @@
 #!/bin/bash
 # ncu only: launch list + full capture of kernels matching $2 (regex), using the short bench command
-tag=${1:-n}; pat=${2:-phase1_fast|phase2_fast}
+tag=${1:-n}; pat=${2:-phase1_tpr|phase2_tpr}
 mkdir -p gpurun_out
 timeout 300 python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/plain_${tag}.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${tag}.csv \
