@@ -173,14 +173,16 @@ def run_reference(args):
     return 0
 
 
-def workload_config(workload: str, n_gpus: int) -> dict:
+def workload_config(workload: str, n_gpus: int, scale: float = 1.0, strong: bool = False) -> dict:
     from alga_b200 import synth
 
     kw = synth.CONFIGS[workload]
-    desc = (f"{workload}: synthetic {kw['genome_size'] / 1e6:g} Mbp random genome, "
+    desc = (f"{workload}{'' if scale == 1.0 else f' at genome scale {scale:g}'}: synthetic {kw['genome_size'] * scale / 1e6:g} Mbp random genome, "
             f"{'2x' if kw['paired'] else ''}{kw['read_len']} bp {'paired' if kw['paired'] else 'single-end'} reads at "
             f"{kw['coverage']}x, error {kw.get('error', 0.0):g}, --error_rate=0 (GraphCreatorPrefSuf only)")
-    if n_gpus > 1:
+    if n_gpus > 1 and strong:
+        desc += f"; strong scaling: the same read set, contiguous read-id ranges over {n_gpus} ranks"
+    elif n_gpus > 1:
         desc += f"; weak scaling: {n_gpus} such chromosomes (seeds {kw['seed']}+100r), reads interleaved over ranks"
     return {"workload": desc, "l2": "explicit flush (256 MiB write) between timed steps; step inputs+index also exceed L2",
             "sharding": "1 GPU" if n_gpus == 1 else f"read-id ranges over {n_gpus} GPUs, replicated packed reads + seed index"}
@@ -210,12 +212,31 @@ def run_ours(args):
 
     kw = dict(synth.CONFIGS[args.workload])
     kw["genome_size"] = max(20_000, int(kw["genome_size"] * args.scale))
-    kw["seed"] = kw["seed"] + 100 * rank
+    strong = args.scaling == "strong"
+    if not strong:
+        kw["seed"] = kw["seed"] + 100 * rank  # weak scaling: every rank brings its own chromosome
     t0 = time.time()
-    w = synth.make_workload(args.workload, **kw)
+    strong_words = None
+    if strong and world > 1:
+        # one read set for all ranks: rank 0 generates it (host memory!), the packed words travel over NCCL
+        meta = [None]
+        if rank == 0:
+            w = synth.make_workload(args.workload, **kw)
+            W_ = int(w.reads.word_off[1] - w.reads.word_off[0])
+            meta = [dict(n=w.reads.n, W=W_, len_nt=int(w.reads.len_nt[0]), params=w.params, records=w.records)]
+        dist.broadcast_object_list(meta, src=0)
+        m = meta[0]
+        strong_words = torch.empty((m["n"], m["W"]), dtype=torch.int32, device=dev)
+        if rank == 0:
+            strong_words.copy_(torch.from_numpy(w.reads.words.view(np.int32).reshape(m["n"], m["W"])))
+        dist.broadcast(strong_words, src=0)
+        params, len_nt, n_records = m["params"], m["len_nt"], m["records"]
+    else:
+        w = synth.make_workload(args.workload, **kw)
+        params = w.params
+        len_nt = int(w.reads.len_nt[0])
+        n_records = w.records
     gen_s = time.time() - t0
-    params = w.params
-    len_nt = int(w.reads.len_nt[0])
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     clocks = ClockSampler(local)
@@ -234,7 +255,13 @@ def run_ours(args):
     else:
         from alga_b200.distributed import ShardedPrefSuf, interleave_shards
 
-        shard_words, n_nodes_total = interleave_shards(w.reads, rank, world, dev)
+        if strong:  # rank r takes the r-th contiguous id range
+            n_nodes_total = (strong_words.shape[0] // (2 * world)) * 2 * world
+            per = n_nodes_total // world
+            shard_words = strong_words[rank * per:(rank + 1) * per].clone()
+            del strong_words
+        else:
+            shard_words, n_nodes_total = interleave_shards(w.reads, rank, world, dev)
         sp = ShardedPrefSuf(params.min_overlap, params.rs_min_overlap, params.min_offset, params.max_len_cap, dev,
                             rank, world, len_nt=len_nt, n_shard=int(shard_words.shape[0]),
                             words_per_read=int(shard_words.shape[1]))
@@ -363,10 +390,10 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "u64 (2-bit packed words, exact compare)", "data": "synthetic",
-        "config": workload_config(args.workload, world),
-        "nodes": n_nodes_total, "records": w.records * world, "edges": n_edges, "gen_s": gen_s, "wall_s_timed_region": wall_s,
+        "config": workload_config(args.workload, world, args.scale, strong),
+        "nodes": n_nodes_total, "records": n_records * (1 if strong else world), "edges": n_edges, "gen_s": gen_s, "wall_s_timed_region": wall_s,
         "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
@@ -385,6 +412,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4", "cfg5"])
     ap.add_argument("--scale", type=float, default=1.0, help="genome scale of the GPU workload (1.0 = the named config)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = N chromosomes of the workload (default), strong = the one workload split N ways")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)
