@@ -109,6 +109,8 @@ struct Counters {
     uint32_t n_big;
     uint32_t n_hard1;  // source reads phase 1's fast kernel handed to the generic kernel
     uint32_t rev_overflow;  // the CSR rebuild of the transposed graph did not fit (sharded runs only)
+    uint32_t n_hard1b;      // ... of those, the source reads the second fast pass handed to the generic kernel
+    uint32_t n_spill2;      // targets the second fast phase-2 pass handed to the generic kernels
 };
 
 constexpr uint32_t kRowCapDefault = 16;  // entries per target in the fixed-capacity rows of the transposed phase-1 graph
@@ -137,7 +139,7 @@ struct alga_ps_plan {
     // owned copies (upload path)
     DevBuf words, word_off, len, from, to;
     // workspace
-    DevBuf stats_d, counters_d, tp, ts, rows, over, list1, hard1, indeg, rev_off, rev, triples, triples1, outdeg, scan_ws,
+    DevBuf stats_d, counters_d, tp, ts, rows, over, list1, hard1, hard1b, spill_queue2, indeg, rev_off, rev, triples, triples1, outdeg, scan_ws,
         spill_queue, caps, spill_off, spill_store, row_off, nbr, off, big_rows, tmp_nbr, tmp_off;
     uint32_t over_cap = 0;
     uint32_t row_cap = kRowCapDefault;  // ALGA_PS_ROW_CAP (testing: small rows force the overflow paths)
@@ -156,7 +158,7 @@ struct alga_ps_plan {
     cudaEvent_t ev_stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     ~alga_ps_plan() {
-        DevBuf *all[] = {&words, &word_off, &len, &from, &to, &stats_d, &counters_d, &tp, &ts, &rows, &over, &list1, &hard1, &indeg, &rev_off, &rev,
+        DevBuf *all[] = {&words, &word_off, &len, &from, &to, &stats_d, &counters_d, &tp, &ts, &rows, &over, &list1, &hard1, &hard1b, &spill_queue2, &indeg, &rev_off, &rev,
                          &triples, &triples1, &outdeg, &scan_ws, &spill_queue, &caps, &spill_off, &spill_store, &row_off,
                          &nbr, &off, &big_rows, &tmp_nbr, &tmp_off};
         for (DevBuf *b : all) b->release();
@@ -267,6 +269,31 @@ int stage_index(alga_ps_plan *plan, cudaStream_t s) {
     return ALGA_OK;
 }
 
+// phase 1 for the source reads [lo, hi): first fast pass, second fast pass over what it gave up on, generic kernel
+// over what is left.  All queue lengths stay on the device.
+int run_phase1(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const Phase1Out &p1, cudaStream_t s) {
+    const uint32_t n = hi - lo;
+    Counters *dc = plan->counters_d.as<Counters>();
+    CKR(plan->hard1.ensure((size_t) (n ? n : 1) * 4));
+    CKR(plan->hard1b.ensure((size_t) (n ? n : 1) * 4));
+    CK(cudaMemsetAsync(&dc->n_hard1, 0, 4, s));
+    CK(cudaMemsetAsync(&dc->n_hard1b, 0, 4, s));
+    const int force = plan->params.flags & ALGA_PS_FORCE_GENERIC;
+    launch_phase1_tpr(plan->R, plan->Tp, plan->P, plan->stats.max_len, lo, hi, nullptr, nullptr, p1,
+                      plan->hard1.as<uint32_t>(), &dc->n_hard1, force, s, plan->cfg);
+    const uint32_t *q2 = nullptr, *nq2 = nullptr;
+    if (!force) {  // runs only if the queue is long (kSecondPassMin, decided on the device)
+        launch_phase1_tpr(plan->R, plan->Tp, plan->P, plan->stats.max_len, lo, hi, plan->hard1.as<uint32_t>(), &dc->n_hard1,
+                          p1, plan->hard1b.as<uint32_t>(), &dc->n_hard1b, 0, s, plan->cfg);
+        q2 = plan->hard1b.as<uint32_t>();
+        nq2 = &dc->n_hard1b;
+    }
+    launch_phase1_queue(plan->R, plan->Tp, plan->P, force ? n : (n < 4096 ? n : 4096), plan->hard1.as<uint32_t>(),
+                        &dc->n_hard1, q2, nq2, p1, s, plan->cfg);
+    CK(cudaGetLastError());
+    return ALGA_OK;
+}
+
 // phase 2 (+ spill path) for targets [lo,hi) given rev rows; leaves triples in plan->triples, count in h_counters
 int run_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const RowsView &rows, uint32_t *outdeg, cudaStream_t s,
                const ShardOut &sh = ShardOut{}) {
@@ -275,29 +302,43 @@ int run_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const RowsView &row
     if (list_cap > 2048) list_cap = 2048;
     uint64_t edge_cap = (uint64_t) n * 3 + (1u << 16);
     CKR(plan->spill_queue.ensure((size_t) (n ? n : 1) * 4));
+    CKR(plan->spill_queue2.ensure((size_t) (n ? n : 1) * 4));
     for (int attempt = 0; attempt < 3; attempt++) {
         CKR(plan->triples.ensure((size_t) edge_cap * 12));
         Counters *dc = plan->counters_d.as<Counters>();
         CK(cudaMemsetAsync(&dc->n_edges, 0, 8, s));
         CK(cudaMemsetAsync(&dc->n_spill, 0, 4, s));
+        CK(cudaMemsetAsync(&dc->n_spill2, 0, 4, s));
         if (outdeg) CK(cudaMemsetAsync(outdeg, 0, (size_t) plan->R.n * 4, s));
         Phase2Out out{plan->triples.as<int32_t>(), &dc->n_edges, edge_cap, outdeg, plan->spill_queue.as<uint32_t>(),
                       &dc->n_spill, sh};
         if (plan->params.list_cap > 0)  // testing: generic kernel with a tiny on-chip list
             launch_phase2(plan->R, plan->Ts, plan->P, lo, hi, rows, list_cap, out, s, plan->cfg);
         else
-            launch_phase2_tpr(plan->R, plan->Ts, plan->P, plan->stats.max_len, lo, hi, rows, out,
+            launch_phase2_tpr(plan->R, plan->Ts, plan->P, plan->stats.max_len, lo, hi, nullptr, nullptr, rows, out,
                               plan->params.flags & ALGA_PS_FORCE_GENERIC, s, plan->cfg);
+        const uint32_t *spill_q = plan->spill_queue.as<uint32_t>();
+        const bool second_pass = plan->params.list_cap <= 0 && !(plan->params.flags & ALGA_PS_FORCE_GENERIC);
+        if (second_pass) {  // what the first pass gave up on, once more with four matches per window
+            Phase2Out out2 = out;
+            out2.spill_queue = plan->spill_queue2.as<uint32_t>();
+            out2.n_spill = &dc->n_spill2;
+            launch_phase2_tpr(plan->R, plan->Ts, plan->P, plan->stats.max_len, lo, hi, plan->spill_queue.as<uint32_t>(),
+                              &dc->n_spill, rows, out2, 0, s, plan->cfg);
+            spill_q = plan->spill_queue2.as<uint32_t>();
+        }
         CK(cudaGetLastError());
         CKR(read_counters(plan, s));
-        const uint32_t n_spill = plan->h_counters->n_spill;
+        const bool second_ran = second_pass && plan->h_counters->n_spill >= kSecondPassMin;
+        if (!second_ran) spill_q = plan->spill_queue.as<uint32_t>();
+        const uint32_t n_spill = second_ran ? plan->h_counters->n_spill2 : plan->h_counters->n_spill;
         plan->spilled = n_spill;
         if (n_spill) {
             // targets whose in-neighbour list outgrew shared memory: exact capacity, lists in HBM
             CKR(plan->caps.ensure((size_t) n_spill * 4));
             CKR(plan->spill_off.ensure(((size_t) n_spill + 1) * 8));
             CKR(plan->scan_ws.ensure(scan_workspace_bytes(n_spill)));
-            launch_phase2_count(plan->R, plan->Ts, plan->P, lo, rows, plan->spill_queue.as<uint32_t>(), n_spill,
+            launch_phase2_count(plan->R, plan->Ts, plan->P, lo, rows, spill_q, n_spill,
                                 plan->caps.as<uint32_t>(), s, plan->cfg);
             launch_scan_u64(plan->caps.as<uint32_t>(), plan->spill_off.as<uint64_t>(), n_spill, plan->scan_ws.p, s,
                             plan->cfg);
@@ -306,7 +347,7 @@ int run_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const RowsView &row
             CK(cudaStreamSynchronize(s));
             const uint64_t total = *plan->h_u64;
             CKR(plan->spill_store.ensure((size_t) total * 12 + 16));
-            launch_phase2_spill(plan->R, plan->Ts, plan->P, lo, rows, plan->spill_queue.as<uint32_t>(), n_spill,
+            launch_phase2_spill(plan->R, plan->Ts, plan->P, lo, rows, spill_q, n_spill,
                                 plan->spill_off.as<uint64_t>(), plan->spill_store.as<uint32_t>(), out, s, plan->cfg);
             CK(cudaGetLastError());
             CKR(read_counters(plan, s));
@@ -499,17 +540,11 @@ int alga_ps_stage_phase1(alga_ps_plan *plan, uint32_t lo, uint32_t hi, void *str
     const uint32_t n = hi - lo;
     const size_t max_edges = (size_t) (n ? n : 1) * kSmallEdgesKept;
     CKR(plan->list1.ensure(max_edges * sizeof(Edge1)));
-    CKR(plan->hard1.ensure((size_t) (n ? n : 1) * 4));
     CKR(plan->triples1.ensure(max_edges * 12));
     Counters *dc = plan->counters_d.as<Counters>();
-    CK(cudaMemsetAsync(&dc->n_hard1, 0, 4, s));
     CK(cudaMemsetAsync(&dc->n_list, 0, 4, s));
-    const int force = plan->params.flags & ALGA_PS_FORCE_GENERIC;
     Phase1Out p1{1, nullptr, nullptr, 0, plan->list1.as<Edge1>(), &dc->n_list, (uint32_t) max_edges, 0u, ShardOut{}};
-    launch_phase1_tpr(plan->R, plan->Tp, plan->P, plan->stats.max_len, lo, hi, p1, plan->hard1.as<uint32_t>(),
-                      &dc->n_hard1, force, s, plan->cfg);
-    launch_phase1_queue(plan->R, plan->Tp, plan->P, force ? n : (n < 4096 ? n : 4096), plan->hard1.as<uint32_t>(),
-                        &dc->n_hard1, p1, s, plan->cfg);
+    CKR(run_phase1(plan, lo, hi, p1, s));
     launch_edges_to_triples(plan->list1.as<Edge1>(), &dc->n_list, max_edges, plan->triples1.as<int32_t>(), s, plan->cfg);
     CK(cudaGetLastError());
     CKR(read_counters(plan, s));
@@ -675,18 +710,10 @@ int alga_ps_shard_phase1(alga_ps_plan *plan, const alga_ps_shard *sh, void *stre
     char *ws = (char *) sh->peer_ws[sh->rank];
     const uint32_t n = hi - lo;
     Counters *dc = plan->counters_d.as<Counters>();
-    CKR(plan->hard1.ensure((size_t) (n ? n : 1) * 4));
     CK(cudaMemsetAsync(ws + L.cnt1_off, 0, 32, s));
-    CK(cudaMemsetAsync(&dc->n_hard1, 0, 4, s));
-    const int force = plan->params.flags & ALGA_PS_FORCE_GENERIC;
     Phase1Out p1{2, nullptr, nullptr, 0, nullptr, nullptr, 0, 0u,
                  ShardOut{sh->world, sh->n_shard, (uint32_t *) (ws + L.cnt1_off), ws + L.seg1_off, L.cap1}};
-    launch_phase1_tpr(plan->R, plan->Tp, plan->P, plan->stats.max_len, lo, hi, p1, plan->hard1.as<uint32_t>(), &dc->n_hard1,
-                      force, s, plan->cfg);
-    launch_phase1_queue(plan->R, plan->Tp, plan->P, force ? n : (n < 4096 ? n : 4096), plan->hard1.as<uint32_t>(),
-                        &dc->n_hard1, p1, s, plan->cfg);
-    CK(cudaGetLastError());
-    return ALGA_OK;
+    return run_phase1(plan, lo, hi, p1, s);
 }
 
 int alga_ps_shard_phase2(alga_ps_plan *plan, const alga_ps_shard *sh, void *stream) {
@@ -742,7 +769,7 @@ int alga_ps_shard_phase2(alga_ps_plan *plan, const alga_ps_shard *sh, void *stre
         CK(cudaEventElapsedTime(&ms, plan->ev_stage[1], plan->ev_stage[2]));
         plan->stage_ms[3] = ms;  // phase 2
         plan->stage_ms[5] = plan->h_counters->n_over;
-        plan->stage_ms[6] = plan->h_counters->n_hard1;
+        plan->stage_ms[6] = plan->h_counters->n_hard1 >= kSecondPassMin ? plan->h_counters->n_hard1b : plan->h_counters->n_hard1;
     }
     if (plan->h_counters->n_over > plan->over_cap) {
         plan->over_cap = sh->n_shard * (uint32_t) kSmallEdgesKept * 2;
@@ -807,20 +834,15 @@ int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
         // phase 1 writes every edge straight into the row of its target read (transposed graph, plan->row_cap per target)
         CKR(plan->rows.ensure((size_t) (n ? n : 1) * plan->row_cap * sizeof(RevEntry)));
         CKR(plan->over.ensure((size_t) plan->over_cap * sizeof(Edge1)));
-        CKR(plan->hard1.ensure((size_t) (n ? n : 1) * 4));
         CKR(plan->indeg.ensure((size_t) (n ? n : 1) * 4));
         CKR(plan->rev_off.ensure(((size_t) n + 1) * 4));
         CKR(plan->rev.ensure((size_t) (n ? n : 1) * kSmallEdgesKept * sizeof(RevEntry)));
         CKR(plan->scan_ws.ensure(scan_workspace_bytes(n)));
         CK(cudaMemsetAsync(plan->indeg.p, 0, (size_t) (n ? n : 1) * 4, s));
         CK(cudaMemsetAsync(&dc->n_list, 0, 12, s));  // n_list, n_over, n_spill
-        CK(cudaMemsetAsync(&dc->n_hard1, 0, 4, s));
         Phase1Out p1{0, plan->indeg.as<uint32_t>(), plan->rows.as<RevEntry>(), plan->row_cap, plan->over.as<Edge1>(), &dc->n_over,
                      plan->over_cap, 0u, ShardOut{}};
-        launch_phase1_tpr(plan->R, plan->Tp, plan->P, plan->stats.max_len, 0, n, p1, plan->hard1.as<uint32_t>(), &dc->n_hard1,
-                          force, s, plan->cfg);
-        launch_phase1_queue(plan->R, plan->Tp, plan->P, force ? n : (n < 4096 ? n : 4096), plan->hard1.as<uint32_t>(),
-                            &dc->n_hard1, p1, s, plan->cfg);
+        CKR(run_phase1(plan, 0, n, p1, s));
         CK(cudaEventRecord(plan->ev_stage[1], s));
         // only when a row overflowed (decided on the device): CSR form of the transposed graph
         launch_rebuild_rows_csr(&dc->n_over, plan->over_cap, plan->over.as<Edge1>(), plan->indeg.as<uint32_t>(),
@@ -855,7 +877,7 @@ int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
         plan->stage_ms[k] = ms;
     }
     plan->stage_ms[5] = plan->h_counters->n_over;   // diagnostics: phase-1 edges beyond their row's capacity,
-    plan->stage_ms[6] = plan->h_counters->n_hard1;  // source reads that took the generic phase-1 kernel
+    plan->stage_ms[6] = plan->h_counters->n_hard1 >= kSecondPassMin ? plan->h_counters->n_hard1b : plan->h_counters->n_hard1;  // ... that took the generic phase-1 kernel
     return ALGA_OK;
 }
 

@@ -133,6 +133,8 @@ __device__ __forceinline__ void emit_edge1(const Phase1Out &out, uint32_t b, uin
 // with indeg > cap take the generic kernels, which pick their entries out of that list).  When cap == 0 or the
 // overflow list is longer than kOverScanMax the CSR form (rev_off, rev) is authoritative.  Indexed by c - lo.
 constexpr uint32_t kOverScanMax = 2048;
+// queues shorter than this skip the second fast pass (tpr_kernels.cu) and go straight to the generic kernels
+constexpr uint32_t kSecondPassMin = 4096;
 struct RowsView {
     const uint32_t *indeg;
     const RevEntry *rows;

@@ -40,13 +40,17 @@ void launch_pull_triples(const void *const *seg, const uint32_t *const *cnt, int
 // Edges go where `out` says (common.cuh: rows of the transposed graph, or an edge list), each with its overhang tail
 // (the last min(offset, 32) nucleotides of b[0 .. offset), top-aligned).
 // Thread-per-read fast kernel (tpr_kernels.cu); reads it cannot take are appended to hard_queue (*n_hard must be 0).
+// id_list == nullptr: first pass over the reads [lo, hi) (up to two tag matches per window).  Otherwise second pass
+// over id_list[0 .. *n_list) -- the queue the first pass left -- with up to four matches per window (reads that start
+// at the same position and differ by sequencing errors share their seed); what it gives up on goes to its own queue.
 void launch_phase1_tpr(const ReadsDev &R, const SeedTable &prefix, const PsDev &P, uint32_t max_len_nt, uint32_t lo,
-                       uint32_t hi, const Phase1Out &out, uint32_t *hard_queue, uint32_t *n_hard, int force_hard,
-                       cudaStream_t s, const LaunchCfg &cfg);
-// generic kernel over the queue (n_max = upper bound of the queue length, used for the grid only)
+                       uint32_t hi, const uint32_t *id_list, const uint32_t *n_list, const Phase1Out &out,
+                       uint32_t *hard_queue, uint32_t *n_hard, int force_hard, cudaStream_t s, const LaunchCfg &cfg);
+// generic kernel over the queue (n_max = upper bound of the queue length, used for the grid only).  hard_queue2
+// (nullable): if the first queue was long enough for the second fast pass (kSecondPassMin), the queue IT left.
 void launch_phase1_queue(const ReadsDev &R, const SeedTable &prefix, const PsDev &P, uint32_t n_max,
-                         const uint32_t *hard_queue, const uint32_t *n_hard, const Phase1Out &out, cudaStream_t s,
-                         const LaunchCfg &cfg);
+                         const uint32_t *hard_queue, const uint32_t *n_hard, const uint32_t *hard_queue2,
+                         const uint32_t *n_hard2, const Phase1Out &out, cudaStream_t s, const LaunchCfg &cfg);
 // edge list -> (b, c, o) triples; the list length is read on the device, n_max bounds the grid
 void launch_edges_to_triples(const Edge1 *list, const uint32_t *n_list, uint64_t n_max, int32_t *triples, cudaStream_t s,
                              const LaunchCfg &cfg);
@@ -85,8 +89,8 @@ __device__ __forceinline__ void emit_triple_sharded(const ShardOut &sh, int32_t 
 }
 // thread-per-target fast kernel (tpr_kernels.cu); everything it cannot take goes to out.spill_queue
 void launch_phase2_tpr(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t max_len_nt, uint32_t lo,
-                       uint32_t hi, const RowsView &rows, const Phase2Out &out, int force_hard, cudaStream_t s,
-                       const LaunchCfg &cfg);
+                       uint32_t hi, const uint32_t *id_list, const uint32_t *n_list, const RowsView &rows,
+                       const Phase2Out &out, int force_hard, cudaStream_t s, const LaunchCfg &cfg);
 // generic path: sequential replay on a shared-memory list of list_cap entries per target (spills beyond it)
 void launch_phase2(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t lo, uint32_t hi,
                    const RowsView &rows, int list_cap, const Phase2Out &out, cudaStream_t s, const LaunchCfg &cfg);

@@ -242,10 +242,17 @@ __device__ __forceinline__ void phase1_generic_read(const ReadsDev &R, const See
 // generic phase 1 over a queue of source reads (the reads the fast kernel handed back)
 __global__ void __launch_bounds__(kThreads)
 phase1_queue_kernel(ReadsDev R, SeedTable T, PsDev P, const uint32_t *__restrict__ queue,
-                    const uint32_t *__restrict__ n_queue, Phase1Out out) {
+                    const uint32_t *__restrict__ n_queue, const uint32_t *__restrict__ queue2,
+                    const uint32_t *__restrict__ n_queue2, Phase1Out out) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const uint32_t n_warps = gridDim.x * kWarpsPerBlock;
+    // queue = what the first fast pass gave up on; if it was long enough for the second fast pass to run
+    // (kSecondPassMin), queue2 = what that one gave up on is what is left to do
+    if (queue2 && *n_queue >= kSecondPassMin) {
+        queue = queue2;
+        n_queue = n_queue2;
+    }
     const uint32_t n = *n_queue;
     for (uint32_t q = warp; q < n; q += n_warps) {
         phase1_generic_read(R, T, P, queue[q], out, lane);
@@ -824,12 +831,13 @@ void launch_pull_triples(const void *const *seg, const uint32_t *const *cnt, int
 }
 
 void launch_phase1_queue(const ReadsDev &R, const SeedTable &prefix, const PsDev &P, uint32_t n_max,
-                         const uint32_t *hard_queue, const uint32_t *n_hard, const Phase1Out &out, cudaStream_t s,
-                         const LaunchCfg &cfg) {
+                         const uint32_t *hard_queue, const uint32_t *n_hard, const uint32_t *hard_queue2,
+                         const uint32_t *n_hard2, const Phase1Out &out, cudaStream_t s, const LaunchCfg &cfg) {
     if (!n_max) return;
     // the queue length lives on the device (no host round trip; usually zero): size the grid for a short queue
     // unless the caller knows that every read is in it
-    phase1_queue_kernel<<<grid_for(n_max, kWarpsPerBlock, cfg, 8), kThreads, 0, s>>>(R, prefix, P, hard_queue, n_hard, out);
+    phase1_queue_kernel<<<grid_for(n_max, kWarpsPerBlock, cfg, 8), kThreads, 0, s>>>(R, prefix, P, hard_queue, n_hard,
+                                                                                       hard_queue2, n_hard2, out);
     bump(cfg);
 }
 

@@ -21,9 +21,11 @@
 // lanes inside the hit branch (r01d).  Splitting the loops (r01h) halved the instructions and left the kernels
 // latency-bound on the bucket loads (27 % of the stall samples at 20 warps per SM, one bucket in flight per thread).
 //
-// Reads the fast path cannot take (longer than 512 nt, a window with more than two tag matches, offsets above 32,
+// Reads the fast path cannot take (longer than 512 nt, a window with more than four tag matches, offsets above 32,
 // more queued arrivals than fit, a source id that occurs twice for one target, ...) are queued for the generic
 // kernels of prefsuf_kernels.cu, which replay GraphCreatorPrefSuf.cpp:356-488 literally.
+#include <algorithm>
+
 #include "launch.h"
 
 namespace alga {
@@ -98,40 +100,65 @@ __device__ __forceinline__ uint32_t bucket_min(const uint32_t (&e)[8], uint32_t 
     return m;
 }
 
-// ids of the entries of one bucket whose tag matches (first two) and how many there are; true if the bucket is full
-__device__ __forceinline__ bool eval_bucket(const SeedTable &t, const uint32_t (&e)[8], uint32_t tag, uint32_t &c0,
-                                            uint32_t &c1, int &n) {
+// ids of the entries of one bucket whose tag matches (the first kMaxMatch) and how many there are; true if the bucket
+// is full
+// (MAXM = reads that share a K-nucleotide seed and overlap at one length, i.e. start at the same position: 2 in the
+// first pass over all reads, 4 in the second pass over the reads the first one gave up on)
+template <int MAXM>
+__device__ __forceinline__ bool eval_bucket(const SeedTable &t, const uint32_t (&e)[8], uint32_t tag, uint32_t (&c)[MAXM],
+                                            int &n) {
 #pragma unroll
     for (int s = 0; s < kSlotsPerBucket; s++) {
         if ((e[s] ^ tag) <= t.id_mask) {
-            if (n == 0) c0 = e[s] & t.id_mask;
-            else if (n == 1) c1 = e[s] & t.id_mask;
+#pragma unroll
+            for (int k = 0; k < MAXM; k++)
+                if (k == n) c[k] = e[s] & t.id_mask;
             n++;
         }
     }
     return e[kSlotsPerBucket - 1] != kEmptySlot;  // buckets fill front to back: a full one chains on
 }
 
-// Matches of a probe whose first bucket is in e[] and holds at least one match or is full.  The common case -- one
-// match, bucket not full -- is answered by the minimum alone; otherwise collect the matches and walk the chain.
+__device__ __forceinline__ void order_desc(uint32_t &a, uint32_t &b) {
+    const uint32_t hi = max(a, b), lo = min(a, b);
+    a = hi, b = lo;
+}
+
+// Matches of a probe whose first bucket is in e[] and holds at least one match or is full, largest id first (the order
+// of arrival inside one overlap length, seen backwards).  The common case -- one match, bucket not full -- is answered
+// by the minimum alone; otherwise collect the matches and walk the chain.  n > MAXM: the caller gives up.
+template <int MAXM>
 __device__ __forceinline__ void probe_matches(const SeedTable &t, uint32_t (&e)[8], uint32_t tag, uint32_t bk, uint32_t m,
-                                              uint32_t &c0, uint32_t &c1, int &n) {
+                                              uint32_t (&c)[MAXM], int &n) {
     int cnt = 0;
 #pragma unroll
     for (int s = 0; s < kSlotsPerBucket; s++) cnt += ((e[s] ^ tag) <= t.id_mask) ? 1 : 0;
     const bool full = e[kSlotsPerBucket - 1] != kEmptySlot;
-    c0 = c1 = kNone;
+#pragma unroll
+    for (int k = 0; k < MAXM; k++) c[k] = 0u;
     if (cnt == 1 && !full) {
         n = 1;
-        c0 = m;
+        c[0] = m;
         return;
     }
     n = 0;
-    bool more = eval_bucket(t, e, tag, c0, c1, n);
+    bool more = eval_bucket<MAXM>(t, e, tag, c, n);
     while (more) {
         bk = next_bucket(t, bk);
         load_bucket(t.slots + (uint64_t) bk * kSlotsPerBucket, e);
-        more = eval_bucket(t, e, tag, c0, c1, n);
+        more = eval_bucket<MAXM>(t, e, tag, c, n);
+    }
+    if (n > 1 && n <= MAXM) {  // unused slots hold 0 and sink to the end (n says how many are real)
+        if (MAXM == 2) {
+            order_desc(c[0], c[1]);
+        } else {
+            static_assert(MAXM == 2 || MAXM == 4, "sorting network");
+            order_desc(c[0], c[1]);
+            order_desc(c[MAXM - 2], c[MAXM - 1]);
+            order_desc(c[0], c[MAXM - 2]);
+            order_desc(c[1], c[MAXM - 1]);
+            order_desc(c[1], c[MAXM - 2]);
+        }
     }
 }
 
@@ -142,12 +169,18 @@ __device__ __forceinline__ uint64_t window_key(uint32_t w0, uint32_t w1, uint32_
 
 // Stage the (up to 32) reads of a warp's tile: `sw` words each at stride `wp`, the rest of the stride zeroed.
 // FAST (fixed stride in HBM): the tile is one contiguous range, copied with fully coalesced loads.
+// `listed`: the tile is not a contiguous id range (second pass over a queue): every lane copies its own read `my_id`.
 template <bool FAST>
 __device__ __forceinline__ void stage_warp(const ReadsDev &R, uint32_t *wown, int wp, int sw, uint64_t first,
-                                           uint32_t n_valid, uint32_t my_words, int lane) {
+                                           uint32_t n_valid, uint32_t my_words, int lane, bool listed = false,
+                                           uint32_t my_id = 0) {
     uint32_t *own = wown + lane * wp;
     __syncwarp();
-    if (FAST) {
+    if (listed) {
+        const uint32_t *p = (uint32_t) lane < n_valid ? read_ptr(R, my_id) : R.words;
+        const uint32_t nw = FAST ? ((uint32_t) lane < n_valid ? (uint32_t) sw : 0u) : my_words;
+        for (int w = 0; w < wp; w++) own[w] = (uint32_t) w < nw ? __ldg(p + w) : 0u;
+    } else if (FAST) {
         for (int w = sw; w < wp; w++) own[w] = 0u;
         const uint32_t *base = R.words + first * R.stride;
         if ((uint32_t) sw == R.stride) {
@@ -230,21 +263,26 @@ __device__ __forceinline__ bool verify_own_prefix(const ReadsDev &R, const uint3
 // Lanes pause once they hold 3 candidates, so their positions in the walk differ; with so few lengths per read
 // (about 11 of the 34 possible) a deep prefetch ring mostly fetches buckets nobody tests, so this kernel keeps ONE
 // bucket in flight per lane, in registers.  Shared memory per warp: own reads [32][wp].
-template <bool FAST>
+// id_list != nullptr: second pass -- the reads are id_list[0 .. *n_list) instead of [lo, hi)
+template <bool FAST, int MAXM>
 __global__ void __launch_bounds__(kTpr, ALGA_P1_BLOCKS)
-phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, int wp, Phase1Out out,
-                  uint32_t *__restrict__ hard_queue, uint32_t *n_hard, int force_hard) {
+phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, const uint32_t *__restrict__ id_list,
+                  const uint32_t *__restrict__ n_list, int wp, Phase1Out out, uint32_t *__restrict__ hard_queue,
+                  uint32_t *n_hard, int force_hard) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint32_t *wown = smem + wib * 32 * wp;
     const uint32_t *own = wown + lane * wp;
-    const uint64_t n_tiles = ((uint64_t) (hi - lo) + 31) / 32;
+    const bool listed = id_list != nullptr;
+    const uint64_t n_items = listed ? (uint64_t) *n_list : (uint64_t) (hi - lo);
+    if (listed && n_items < kSecondPassMin) return;  // a short queue is cheaper in the generic kernel (one tile = 40 us)
+    const uint64_t n_tiles = (n_items + 31) / 32;
     const uint64_t warp_id = (uint64_t) blockIdx.x * kWarps + wib, n_warps = (uint64_t) gridDim.x * kWarps;
     for (uint64_t tile = warp_id; tile < n_tiles; tile += n_warps) {
         const uint64_t first = (uint64_t) lo + tile * 32;
-        const uint32_t n_valid = (uint32_t) min((uint64_t) 32, (uint64_t) hi - first);
+        const uint32_t n_valid = (uint32_t) min((uint64_t) 32, n_items - tile * 32);
         const bool inr = (uint32_t) lane < n_valid;
-        const uint32_t b = inr ? (uint32_t) (first + lane) : lo;
+        const uint32_t b = inr ? (listed ? id_list[tile * 32 + lane] : (uint32_t) (first + lane)) : lo;
         const uint32_t lenb = inr ? (FAST ? P.uniform_len : R.len[b]) : 0u;
         int64_t l_hi64 = (int64_t) lenb - P.min_offset;
         if (l_hi64 > P.rs - 1) l_hi64 = P.rs - 1;
@@ -256,15 +294,17 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
             hard = true;
             active = false;
         }
-        stage_warp<FAST>(R, wown, wp, wp - 2, first, n_valid, active ? (lenb + 15u) >> 4 : 0u, lane);
+        stage_warp<FAST>(R, wown, wp, wp - 2, first, n_valid, active ? (lenb + 15u) >> 4 : 0u, lane, listed, b);
 
         int conf = 0, np = 0;
-        uint32_t sc[kSmallEdgesKept], so[kSmallEdgesKept], pc[4];
-        int32_t pl[4];
+        constexpr int kPend = 2 + MAXM;  // fewer than 3 held when a window is probed, up to MAXM more from it
+        constexpr int kBatch = MAXM == 2 ? 4 : 3;  // candidates verified together (their loads overlap)
+        uint32_t sc[kSmallEdgesKept], so[kSmallEdgesKept], pc[kPend];
+        int32_t pl[kPend];
 #pragma unroll
         for (int k = 0; k < kSmallEdgesKept; k++) sc[k] = kNone, so[k] = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) pc[k] = 0, pl[k] = 0;
+        for (int k = 0; k < kPend; k++) pc[k] = 0, pl[k] = 0;
 
         // probe state: the bucket of length `Lc` is in flight in e[]
         int32_t Lc = l_hi;
@@ -288,9 +328,9 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
                 if (!__any_sync(kFull, need)) break;
                 if (need) {
                     const uint32_t m = bucket_min(e, tag);
-                    uint32_t c0 = kNone, c1 = kNone;
+                    uint32_t cm[MAXM];
                     int n = 0;
-                    if (m <= T.id_mask || e[7] != kEmptySlot) probe_matches(T, e, tag, bk, m, c0, c1, n);
+                    if (m <= T.id_mask || e[7] != kEmptySlot) probe_matches<MAXM>(T, e, tag, bk, m, cm, n);
                     const int32_t L = Lc;
                     Lc--;
                     if (Lc >= P.lmin) {  // slide the window by one nucleotide, next bucket goes in flight
@@ -307,73 +347,80 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
                     } else {
                         more = false;
                     }
-                    if (n > 2) {
+                    if (n > MAXM) {
                         hard = true;
-                    } else if (n) {
-                        if (n == 2 && c1 > c0) {  // within one length the larger target id is the later push
-                            const uint32_t x = c0;
-                            c0 = c1;
-                            c1 = x;
-                        }
+                    } else if (n) {  // within one length the larger target id is the later push: cm[] is descending
 #pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            if (k == np) pc[k] = c0, pl[k] = L;
+                        for (int k = 0; k < kPend; k++)
+                            if (k == np) pc[k] = cm[0], pl[k] = L;
                         np++;
-                        if (n == 2) {
+                        if (n > 1) {  // several reads start with this seed (rare without sequencing errors)
 #pragma unroll
-                            for (int k = 0; k < 4; k++)
-                                if (k == np) pc[k] = c1, pl[k] = L;
-                            np++;
-                        }
-                    }
-                }
-            }
-            // ---- confirm the pending candidates, every lane its own: the words of all of them are requested before
-            // the first compare, so their (random, mostly DRAM) latencies overlap
-            const int np_max = warp_max(hard ? 0 : np);
-            if (np_max == 0) break;
-            const int nw_max = warp_max(np && !hard ? (2 * pl[0] + 31) >> 5 : 0);
-            uint32_t diff[4] = {0u, 0u, 0u, 0u};
-            for (int k0 = 0; k0 < nw_max; k0 += 4) {
-                uint32_t g[4][4];
+                            for (int j = 1; j < MAXM; j++) {
+                                if (j < n) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (k < np_max) {
-                        const bool on = k < np && !hard;
-                        const uint32_t *pcand = read_ptr(R, on ? pc[k] : b);
-                        const int nw = on ? (2 * pl[k] + 31) >> 5 : 0;
-#pragma unroll
-                        for (int j = 0; j < 4; j++) g[k][j] = k0 + j < nw ? __ldg(pcand + k0 + j) : 0u;
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (k < np_max && k < np && !hard) {
-                        const uint32_t nbits = 2u * (uint32_t) pl[k], nw = (nbits + 31u) >> 5;
-                        const uint32_t o2 = 2u * (lenb - (uint32_t) pl[k]), shv = o2 & 31u;
-                        const uint32_t *ow = own + (o2 >> 5);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const uint32_t w = (uint32_t) (k0 + j);
-                            if (w < nw) {
-                                uint32_t x = __funnelshift_r(ow[w], ow[w + 1], shv) ^ g[k][j];
-                                if (w == nw - 1 && (nbits & 31u)) x &= (1u << (nbits & 31u)) - 1u;
-                                diff[k] |= x;
+                                    for (int k = 0; k < kPend; k++)
+                                        if (k == np) pc[k] = cm[j], pl[k] = L;
+                                    np++;
+                                }
                             }
                         }
                     }
                 }
             }
+            // ---- confirm the pending candidates, every lane its own, kBatch at a time: the words of a whole batch are
+            // requested before the first compare, so their (random, mostly DRAM) latencies overlap
+            const int np_max = warp_max(hard ? 0 : np);
+            if (np_max == 0) break;
+            const int nw_max = warp_max(np && !hard ? (2 * pl[0] + 31) >> 5 : 0);
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (k < np && !hard && conf < kSmallEdgesKept) {
-                    const uint32_t cand = pc[k];
-                    const int32_t L = pl[k];
-                    if (diff[k] == 0 && cand != b && (FAST || (int64_t) R.len[cand] >= L)) {
+            for (int base = 0; base < kPend; base += kBatch) {
+                if (base < np_max) {
+                    uint32_t diff[kBatch];
 #pragma unroll
-                        for (int q = 0; q < kSmallEdgesKept; q++)
-                            if (q == conf) sc[q] = cand, so[q] = lenb - (uint32_t) L;
-                        conf++;
+                    for (int k = 0; k < kBatch; k++) diff[k] = 0u;
+                    for (int k0 = 0; k0 < nw_max; k0 += 4) {
+                        uint32_t g[kBatch][4];
+#pragma unroll
+                        for (int k = 0; k < kBatch; k++) {
+                            if (base + k < np_max) {
+                                const bool on = base + k < np && !hard;
+                                const uint32_t *pcand = read_ptr(R, on ? pc[base + k] : b);
+                                const int nw = on ? (2 * pl[base + k] + 31) >> 5 : 0;
+#pragma unroll
+                                for (int j = 0; j < 4; j++) g[k][j] = k0 + j < nw ? __ldg(pcand + k0 + j) : 0u;
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < kBatch; k++) {
+                            if (base + k < np_max && base + k < np && !hard) {
+                                const uint32_t nbits = 2u * (uint32_t) pl[base + k], nw = (nbits + 31u) >> 5;
+                                const uint32_t o2 = 2u * (lenb - (uint32_t) pl[base + k]), shv = o2 & 31u;
+                                const uint32_t *ow = own + (o2 >> 5);
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    const uint32_t w = (uint32_t) (k0 + j);
+                                    if (w < nw) {
+                                        uint32_t x = __funnelshift_r(ow[w], ow[w + 1], shv) ^ g[k][j];
+                                        if (w == nw - 1 && (nbits & 31u)) x &= (1u << (nbits & 31u)) - 1u;
+                                        diff[k] |= x;
+                                    }
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < kBatch; k++) {
+                        if (base + k < np && !hard && conf < kSmallEdgesKept) {
+                            const uint32_t cand = pc[base + k];
+                            const int32_t L = pl[base + k];
+                            if (diff[k] == 0 && cand != b && (FAST || (int64_t) R.len[cand] >= L)) {
+#pragma unroll
+                                for (int q = 0; q < kSmallEdgesKept; q++)
+                                    if (q == conf) sc[q] = cand, so[q] = lenb - (uint32_t) L;
+                                conf++;
+                            }
+                        }
                     }
                 }
             }
@@ -465,10 +512,11 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
 //
 // Shared memory per warp: own reads [32][wp] | bucket ring [kRing2][2][32] x 16 B | queue: ids [kQ2][32],
 // heads [kQ2][2][32], lengths [kQ2][32] (u16).
-template <bool FAST>
+// id_list != nullptr: second pass -- the targets are id_list[0 .. *n_list) instead of [lo, hi)
+template <bool FAST, int MAXM>
 __global__ void __launch_bounds__(kTpr, ALGA_P2_BLOCKS)
-phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, int wp, RowsView rows, Phase2Out out,
-                  int force_hard) {
+phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, const uint32_t *__restrict__ id_list,
+                  const uint32_t *__restrict__ n_list, int wp, RowsView rows, Phase2Out out, int force_hard) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int own_words = ((kWarps * 32 * wp + 3) & ~3);
@@ -482,13 +530,16 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
     const uint64_t pol = l2_evict_last_policy();
     const int32_t l_lo = P.rs > P.lmin ? P.rs : P.lmin;
     const bool csr = rows_are_csr(rows);
-    const uint64_t n_tiles = ((uint64_t) (hi - lo) + 31) / 32;
+    const bool listed = id_list != nullptr;
+    const uint64_t n_items = listed ? (uint64_t) *n_list : (uint64_t) (hi - lo);
+    if (listed && n_items < kSecondPassMin) return;  // a short queue is cheaper in the generic kernel (one tile = 40 us)
+    const uint64_t n_tiles = (n_items + 31) / 32;
     const uint64_t warp_id = (uint64_t) blockIdx.x * kWarps + wib, n_warps = (uint64_t) gridDim.x * kWarps;
     for (uint64_t tile = warp_id; tile < n_tiles; tile += n_warps) {
         const uint64_t first = (uint64_t) lo + tile * 32;
-        const uint32_t n_valid = (uint32_t) min((uint64_t) 32, (uint64_t) hi - first);
+        const uint32_t n_valid = (uint32_t) min((uint64_t) 32, n_items - tile * 32);
         const bool inr = (uint32_t) lane < n_valid;
-        const uint32_t c = inr ? (uint32_t) (first + lane) : lo;
+        const uint32_t c = inr ? (listed ? id_list[tile * 32 + lane] : (uint32_t) (first + lane)) : lo;
         uint32_t deg = 0;
         const RevEntry *row = rows.rev;
         if (inr) row = get_row(rows, csr, c - lo, deg);
@@ -503,7 +554,7 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
                 const uint32_t need = (uint32_t) ((2 * l_hi + 31) >> 5), have = (lenc + 15u) >> 4;
                 nw = need < have ? need : have;
             }
-            stage_warp<FAST>(R, wown, wp, wp - 2, first, n_valid, nw, lane);
+            stage_warp<FAST>(R, wown, wp, wp - 2, first, n_valid, nw, lane, listed, c);
         }
 
         // ---- probe: queue every tag hit (b, L); FAST: the first 64 bits of b follow by cp.async
@@ -555,20 +606,18 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, in
                     }
                     const uint32_t tag = tagr[j], bk = bkr[j];
                     const uint32_t m = bucket_min(e, tag);
-                    uint32_t b0 = kNone, b1 = kNone;
+                    uint32_t bm[MAXM];
                     int n = 0;
-                    if (!hard && (m <= T.id_mask || e[7] != kEmptySlot)) probe_matches(T, e, tag, bk, m, b0, b1, n);
+                    if (!hard && (m <= T.id_mask || e[7] != kEmptySlot)) probe_matches<MAXM>(T, e, tag, bk, m, bm, n);
                     prefetch(j, tagr[j], bkr[j]);
-                    if (n > 2) {
+                    if (n > MAXM) {
                         hard = true;
-                    } else if (n) {
-                        if (n == 2 && b1 > b0) {  // walking backwards: within one length the larger source id arrived later
-                            const uint32_t x = b0;
-                            b0 = b1;
-                            b1 = x;
-                        }
-                        for (int k = 0; k < n; k++) {
-                            const uint32_t cand = k ? b1 : b0;
+                    } else if (n) {  // walking backwards: within one length the larger source id arrived later: bm[] is descending
+                        for (int k = 0; k < n; k++) {  // n == 1 unless several reads end with this seed
+                            uint32_t cand = bm[0];
+#pragma unroll
+                            for (int t = 1; t < MAXM; t++)
+                                if (t == k) cand = bm[t];
                             if (cand == c) continue;
                             if (qn >= kQ2) {
                                 hard = true;
@@ -771,28 +820,34 @@ inline int stride_words(int words) {
 
 }  // namespace
 
+// id_list / n_list: nullptr = first pass over [lo, hi) (two matches per window); else second pass over the queue of the
+// first one (four matches per window; the queue length is read on the device, the grid is sized for a short queue)
 void launch_phase1_tpr(const ReadsDev &R, const SeedTable &prefix, const PsDev &P, uint32_t max_len_nt, uint32_t lo,
-                       uint32_t hi, const Phase1Out &out, uint32_t *hard_queue, uint32_t *n_hard, int force_hard,
-                       cudaStream_t s, const LaunchCfg &cfg) {
+                       uint32_t hi, const uint32_t *id_list, const uint32_t *n_list, const Phase1Out &out,
+                       uint32_t *hard_queue, uint32_t *n_hard, int force_hard, cudaStream_t s, const LaunchCfg &cfg) {
     if (hi <= lo) return;
     int w = (int) ((max_len_nt + 15u) >> 4);
     if (w > kOwnWords) w = kOwnWords;
     const int wp = stride_words(w);
     const size_t smem = (size_t) kWarps * 32 * wp * sizeof(uint32_t);
-    const int grid = warp_tile_grid(hi - lo, cfg, ALGA_P1_BLOCKS);
-    if (P.uniform_len && !R.word_off) {
-        cudaFuncSetAttribute(phase1_tpr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        phase1_tpr_kernel<true><<<grid, kTpr, smem, s>>>(R, prefix, P, lo, hi, wp, out, hard_queue, n_hard, force_hard);
+    const bool fast = P.uniform_len && !R.word_off;
+    if (!id_list) {
+        const int grid = warp_tile_grid(hi - lo, cfg, ALGA_P1_BLOCKS);
+        auto k = fast ? phase1_tpr_kernel<true, 2> : phase1_tpr_kernel<false, 2>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        k<<<grid, kTpr, smem, s>>>(R, prefix, P, lo, hi, nullptr, nullptr, wp, out, hard_queue, n_hard, force_hard);
     } else {
-        cudaFuncSetAttribute(phase1_tpr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        phase1_tpr_kernel<false><<<grid, kTpr, smem, s>>>(R, prefix, P, lo, hi, wp, out, hard_queue, n_hard, force_hard);
+        const int grid = warp_tile_grid(std::min<uint64_t>(hi - lo, (uint64_t) cfg.sm_count * kTpr * 2), cfg, 2);
+        auto k = fast ? phase1_tpr_kernel<true, 4> : phase1_tpr_kernel<false, 4>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        k<<<grid, kTpr, smem, s>>>(R, prefix, P, lo, hi, id_list, n_list, wp, out, hard_queue, n_hard, force_hard);
     }
     bump(cfg);
 }
 
 void launch_phase2_tpr(const ReadsDev &R, const SeedTable &suffix, const PsDev &P, uint32_t max_len_nt, uint32_t lo,
-                       uint32_t hi, const RowsView &rows, const Phase2Out &out, int force_hard, cudaStream_t s,
-                       const LaunchCfg &cfg) {
+                       uint32_t hi, const uint32_t *id_list, const uint32_t *n_list, const RowsView &rows,
+                       const Phase2Out &out, int force_hard, cudaStream_t s, const LaunchCfg &cfg) {
     if (hi <= lo) return;
     int64_t lmax = P.max_l;
     if (lmax > (int64_t) max_len_nt) lmax = max_len_nt;
@@ -803,13 +858,17 @@ void launch_phase2_tpr(const ReadsDev &R, const SeedTable &suffix, const PsDev &
     const int wp = stride_words(w);
     const size_t smem = (size_t) (((kWarps * 32 * wp + 3) & ~3) + kWarps * (kRing2 * 2 * 32 * 4) +
                                   kWarps * (kQ2 * 32 * 3 + kQ2 * 32 / 2)) * sizeof(uint32_t);
-    const int grid = warp_tile_grid(hi - lo, cfg, ALGA_P2_BLOCKS);
-    if (P.uniform_len && !R.word_off) {
-        cudaFuncSetAttribute(phase2_tpr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        phase2_tpr_kernel<true><<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, wp, rows, out, force_hard);
+    const bool fast = P.uniform_len && !R.word_off;
+    if (!id_list) {
+        const int grid = warp_tile_grid(hi - lo, cfg, ALGA_P2_BLOCKS);
+        auto k = fast ? phase2_tpr_kernel<true, 2> : phase2_tpr_kernel<false, 2>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        k<<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, nullptr, nullptr, wp, rows, out, force_hard);
     } else {
-        cudaFuncSetAttribute(phase2_tpr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        phase2_tpr_kernel<false><<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, wp, rows, out, force_hard);
+        const int grid = warp_tile_grid(std::min<uint64_t>(hi - lo, (uint64_t) cfg.sm_count * kTpr * 2), cfg, 2);
+        auto k = fast ? phase2_tpr_kernel<true, 4> : phase2_tpr_kernel<false, 4>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        k<<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, id_list, n_list, wp, rows, out, force_hard);
     }
     bump(cfg);
 }

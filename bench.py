@@ -388,6 +388,20 @@ def run_ours(args):
         cpu = {"value": sample.reads.n / s, "unit": UNIT, "cores": used, "kind": kind, "seconds": s,
                "sample": f"{sample.name}: {sample.reads.n} nodes, one build, region main.cpp:282-291 (steady_clock)"}
 
+    supplement = None
+    if world == 1 and args.workload == "cfg3":
+        # BASELINE configs[2]: the error-rate supplement (main.cpp:300-355) on top of the graph just built, host to host
+        from alga_b200.graph_creator import GraphCreatorLI
+        from tests.cases import supplement_params
+
+        sp = supplement_params(float(w.reads.len_nt.mean()))
+        li = GraphCreatorLI(w.reads, g, **sp, device=local)
+        ts = time.perf_counter()
+        g2 = li.startAlignmentGraphCreation()
+        supplement = {"ms": 1e3 * (time.perf_counter() - ts), "edges_before": int(g.n_edges), "edges_after": int(g2.n_edges),
+                      "params": sp, **li.timing,
+                      "note": "alga_gpu_supplement: LI k-mers + canAlign on the GPU, bucket sort + ordered replay on the host"}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
@@ -396,6 +410,8 @@ def run_ours(args):
         "nodes": n_nodes_total, "records": n_records * (1 if strong else world), "edges": n_edges, "gen_s": gen_s, "wall_s_timed_region": wall_s,
         "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }
+    if supplement:
+        line["supplement"] = supplement
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -409,7 +425,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4", "cfg5"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--scale", type=float, default=1.0, help="genome scale of the GPU workload (1.0 = the named config)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],

@@ -43,3 +43,17 @@ def test_spill_path_matches_oracle(gpu, name, cap):
     g, gc = _run(rs, lmin, rsmin, mo, list_cap=cap)
     assert gc.timing["n_spilled_targets"] > 0
     assert np.array_equal(g.edges(), want)
+
+
+def test_second_fast_pass_matches_oracle(gpu):
+    """Reads with sequencing errors (BASELINE config 3): reads that start at the same position are not duplicates any
+    more but share their seed, so ~3 % of the reads see more than two tag matches in one window.  A queue that long
+    (>= 4096) takes the second fast pass (four matches per window) before the generic kernels."""
+    from alga_b200 import synth
+
+    w = synth.make_config("cfg3", scale=0.1)
+    want = oracle.prefsuf(w.reads, w.params.min_overlap, w.params.rs_min_overlap)
+    g, gc = _run(w.reads, w.params.min_overlap, w.params.rs_min_overlap, 0)
+    assert np.array_equal(g.edges(), want)
+    # what is left for the generic kernels after two fast passes is a small fraction of what the first pass queued
+    assert gc.timing["n_hard_sources"] < 0.005 * w.reads.n and gc.timing["n_spilled_targets"] < 0.005 * w.reads.n
