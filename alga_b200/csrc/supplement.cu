@@ -21,6 +21,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -231,15 +232,41 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
     VerifyDev vd{sp->max_offset_pct, sp->min_offset, sp->min_overlap_area, sp->threshold_pct, sp->same_ends};
 
     const long long kBucketsSort = 1048576ll;  // GraphCreatorKmerBased.cpp:140
-    std::vector<std::vector<Kmer>> buckets((size_t) kBucketsSort);
-    std::vector<int> neighbors(n, 1000000001);  // Params::INF
+    // Host side, flat: all k-mers of a pass in ONE array ordered by bucket (counting sort that keeps the reference's fill
+    // order inside a bucket: reads by id, k-mers by interval), std::sort on each bucket's range -- the same sequence,
+    // comparator and algorithm as std::sort on the reference's per-bucket vectors, hence the same tie order.
+    std::vector<Kmer> km;                                     // k-mers of the pass, bucket-major
+    std::vector<uint32_t> bstart((size_t) kBucketsSort + 1);  // bucket -> first k-mer
+    std::vector<uint32_t> kbucket;                            // scratch: bucket of every k-mer in input order
+    std::vector<int> neighbors(n, 1000000001);                // Params::INF
     const int INF = 1000000001;
+    const unsigned n_thr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::vector<int32_t>> tpairs(n_thr);          // pairs found by each thread's share of the buckets
     std::vector<int32_t> pairs;
     std::vector<uint8_t> verdict;
-    std::vector<std::vector<uint8_t>> bm;
-    double gpu_ms = 0;
+    std::vector<uint64_t> bm;                                  // branch markers of one group: D rows of ceil(D/64) words
+    double gpu_ms = 0, t_kmers = 0, t_sort = 0, t_enum = 0, t_verify = 0, t_replay = 0;
     uint64_t pairs_total = 0;
     int32_t prio[4] = {0, 1, 2, 3};
+
+    // the static filters of GraphCreatorPairwiseKmerBranch.cpp:43-62 for the ordered pair (i, j) of one group:
+    // 0 = candidate, 1 = skip j, 2 = stop this i
+    auto pair_filter = [&](const Kmer &ki, const Kmer &kj, int &offset) -> int {
+        if (ki.read == kj.read) return 1;
+        offset = ki.ind - kj.ind;
+        if (offset < sp->min_offset) return 1;
+        if (100ll * offset > (long long) sp->max_offset_pct * (long long) ki.read_len) return 2;
+        const int overlap = std::min((int) ki.read_len, (int) kj.read_len + offset) - offset;
+        if (overlap < sp->min_overlap_area) return 1;
+        if ((int) kj.read_len + offset - (int) ki.read_len < 0) return 1;  // Read::getRightOffset
+        return 0;
+    };
+    auto run_threads = [&](auto &&fn) {  // fn(t): bucket range [t, t+1) * kBucketsSort / n_thr
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < n_thr; t++) th.emplace_back([&fn, t] { fn(t); });
+        fn(0u);
+        for (auto &x : th) x.join();
+    };
 
     for (int pass = 0; pass < 4; pass++) {  // GraphCreatorLI.cpp:20-26
         // ---- LI k-mers on the GPU
@@ -252,48 +279,82 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
             SCK(cudaMemcpy(hi.data(), d_ind.p, hi.size() * 4, cudaMemcpyDeviceToHost));
         }
         gpu_ms += now_ms() - ta;
-        // ---- buckets in the reference's fill order (reads by id, k-mers by interval), std::sort per bucket
-        for (auto &b : buckets) b.clear();
+        t_kmers += now_ms() - ta;
+        // ---- buckets in the reference's fill order, std::sort per bucket
+        const double tc = now_ms();
         const double B = (double) kMaxHash;
-        for (uint32_t q = 0; q < n_ids; q++) {
-            for (int iv = 0; iv < IV; iv++) {
-                const size_t slot = (size_t) q * IV + (size_t) iv;
-                if (hi[slot] < 0) continue;
-                const Kmer k{ids[q], hh[slot], hi[slot], h->len_nt[ids[q]]};
-                const int ind = (int) ((kBucketsSort - 1) * ((double) k.hash / B));  // GraphCreatorKmerBased.cpp:233
-                buckets[(size_t) ind].push_back(k);
+        const size_t n_slots = (size_t) n_ids * IV;
+        kbucket.resize(n_slots);
+        std::fill(bstart.begin(), bstart.end(), 0u);
+        size_t nk = 0;
+        for (size_t slot = 0; slot < n_slots; slot++) {
+            if (hi[slot] < 0) {
+                kbucket[slot] = 0xFFFFFFFFu;
+                continue;
+            }
+            const uint32_t ind = (uint32_t) (int) ((kBucketsSort - 1) * ((double) hh[slot] / B));  // GraphCreatorKmerBased.cpp:233
+            kbucket[slot] = ind;
+            bstart[(size_t) ind + 1]++;
+            nk++;
+        }
+        for (size_t k = 0; k < (size_t) kBucketsSort; k++) bstart[k + 1] += bstart[k];
+        km.resize(nk);
+        {
+            std::vector<uint32_t> cursor(bstart.begin(), bstart.end() - 1);
+            for (size_t slot = 0; slot < n_slots; slot++) {
+                if (kbucket[slot] == 0xFFFFFFFFu) continue;
+                const uint32_t id = ids[slot / (size_t) IV];
+                km[cursor[kbucket[slot]]++] = Kmer{id, hh[slot], hi[slot], h->len_nt[id]};
             }
         }
-        for (auto &b : buckets)
-            if (b.size() > 1) std::sort(b.begin(), b.end());
-        // ---- every pair that passes the static filters (GraphCreatorPairwiseKmerBranch.cpp:43-62), in loop order
-        pairs.clear();
-        for (auto &km : buckets) {
-            size_t p = 0, q = 0;
-            while (p < km.size()) {
-                while (q < km.size() && km[q].hash == km[p].hash) q++;
-                const int D = (int) (q - p);
-                for (int i = D - 2; i >= 0; i--) {
-                    const Kmer &ki = km[p + (size_t) i];
-                    for (int j = i + 1; j < D; j++) {
-                        const Kmer &kj = km[p + (size_t) j];
-                        if (ki.read == kj.read) continue;
-                        const int offset = ki.ind - kj.ind;
-                        if (offset < sp->min_offset) continue;
-                        if (100ll * offset > (long long) sp->max_offset_pct * (long long) ki.read_len) break;
-                        const int overlap = std::min((int) ki.read_len, (int) kj.read_len + offset) - offset;
-                        if (overlap < sp->min_overlap_area) continue;
-                        if ((int) kj.read_len + offset - (int) ki.read_len < 0) continue;
-                        pairs.push_back((int32_t) ki.read);
-                        pairs.push_back((int32_t) kj.read);
-                        pairs.push_back(offset);
+        run_threads([&](unsigned t) {
+            const size_t b0 = (size_t) kBucketsSort * t / n_thr, b1 = (size_t) kBucketsSort * (t + 1) / n_thr;
+            for (size_t k = b0; k < b1; k++)
+                if (bstart[k + 1] - bstart[k] > 1) std::sort(km.begin() + bstart[k], km.begin() + bstart[k + 1]);
+        });
+        t_sort += now_ms() - tc;
+        // ---- every pair that passes the static filters, in loop order (buckets, groups, i descending, j ascending)
+        const double td = now_ms();
+        run_threads([&](unsigned t) {
+            std::vector<int32_t> &out = tpairs[t];
+            out.clear();
+            const size_t b0 = (size_t) kBucketsSort * t / n_thr, b1 = (size_t) kBucketsSort * (t + 1) / n_thr;
+            for (size_t k = b0; k < b1; k++) {
+                size_t p = bstart[k], q = p;
+                const size_t end = bstart[k + 1];
+                while (p < end) {
+                    while (q < end && km[q].hash == km[p].hash) q++;
+                    const int D = (int) (q - p);
+                    for (int i = D - 2; i >= 0; i--) {
+                        const Kmer &ki = km[p + (size_t) i];
+                        for (int j = i + 1; j < D; j++) {
+                            const Kmer &kj = km[p + (size_t) j];
+                            int offset = 0;
+                            const int f = pair_filter(ki, kj, offset);
+                            if (f == 2) break;
+                            if (f == 1) continue;
+                            out.push_back((int32_t) ki.read);
+                            out.push_back((int32_t) kj.read);
+                            out.push_back(offset);
+                        }
                     }
+                    p = q;
                 }
-                p = q;
+            }
+        });
+        size_t total3 = 0;
+        for (auto &v : tpairs) total3 += v.size();
+        pairs.resize(total3);
+        {
+            size_t w = 0;
+            for (auto &v : tpairs) {
+                if (!v.empty()) memcpy(pairs.data() + w, v.data(), v.size() * sizeof(int32_t));
+                w += v.size();
             }
         }
         const uint64_t n_pairs = pairs.size() / 3;
         pairs_total += n_pairs;
+        t_enum += now_ms() - td;
         // ---- canAlign of all of them in one batch on the GPU
         const double tb = now_ms();
         verdict.assign((size_t) n_pairs, 0);
@@ -308,64 +369,73 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
             SCK(cudaMemcpy(verdict.data(), d_verdict.p, (size_t) n_pairs, cudaMemcpyDeviceToHost));
         }
         gpu_ms += now_ms() - tb;
-        // ---- replay of the ordered loop (:64-84) with the verdicts at hand
+        t_verify += now_ms() - tb;
+        // ---- replay of the ordered loop (:64-84) with the verdicts at hand; sequential: groups share graph rows
+        const double te = now_ms();
         uint64_t next = 0;
-        for (auto &km : buckets) {
-            size_t p = 0, q = 0;
-            while (p < km.size()) {
-                while (q < km.size() && km[q].hash == km[p].hash) q++;
+        for (size_t k = 0; k < (size_t) kBucketsSort; k++) {
+            size_t p = bstart[k], q = p;
+            const size_t end = bstart[k + 1];
+            while (p < end) {
+                while (q < end && km[q].hash == km[p].hash) q++;
                 const int D = (int) (q - p);
-                if (D > 1) bm.assign((size_t) D, std::vector<uint8_t>((size_t) D, 0));
+                const int RW = (D + 63) >> 6;  // words per branch-marker row
+                if (D > 1) bm.assign((size_t) D * RW, 0ull);
                 for (int i = D - 2; i >= 0; i--) {
                     const Kmer &ki = km[p + (size_t) i];
                     const int id1 = (int) ki.read;
-                    for (auto &x : V[(size_t) id1]) neighbors[(size_t) x.first] = x.second;
+                    auto &row = V[(size_t) id1];
+                    for (auto &x : row) neighbors[(size_t) x.first] = x.second;
+                    uint64_t *bi = bm.data() + (size_t) i * RW;
                     for (int j = i + 1; j < D; j++) {
                         const Kmer &kj = km[p + (size_t) j];
+                        int offset = 0;
+                        const int f = pair_filter(ki, kj, offset);
+                        if (f == 2) break;
+                        if (f == 1) continue;
                         const int id2 = (int) kj.read;
-                        if (id1 == id2) continue;
-                        const int offset = ki.ind - kj.ind;
-                        if (offset < sp->min_offset) continue;
-                        if (100ll * offset > (long long) sp->max_offset_pct * (long long) ki.read_len) break;
-                        const int overlap = std::min((int) ki.read_len, (int) kj.read_len + offset) - offset;
-                        if (overlap < sp->min_overlap_area) continue;
-                        if ((int) kj.read_len + offset - (int) ki.read_len < 0) continue;
                         const uint8_t can = verdict[(size_t) next++];
-                        if (!bm[(size_t) i][(size_t) j]) {
+                        if (!((bi[j >> 6] >> (j & 63)) & 1ull)) {
                             if (neighbors[(size_t) id2] > offset && can) {
                                 // Graph::addDirectedEdge (Graph.cpp:53-71): one entry per target, smallest offset
                                 bool found = false;
-                                for (auto &e : V[(size_t) id1]) {
+                                for (auto &e : row) {
                                     if (e.first == id2) {
                                         if (offset < e.second) e.second = offset;
                                         found = true;
                                         break;
                                     }
                                 }
-                                if (!found) V[(size_t) id1].push_back({id2, offset});
+                                if (!found) row.push_back({id2, offset});
                                 neighbors[(size_t) id2] = offset;
                             }
                             if (neighbors[(size_t) id2] != INF) {
-                                bm[(size_t) i][(size_t) j] = 1;
-                                for (int t = 0; t < D; t++) bm[(size_t) i][(size_t) t] |= bm[(size_t) j][(size_t) t];
+                                bi[j >> 6] |= 1ull << (j & 63);
+                                const uint64_t *bj = bm.data() + (size_t) j * RW;
+                                for (int t = 0; t < RW; t++) bi[t] |= bj[t];
                             }
                         }
                     }
-                    for (auto &x : V[(size_t) id1]) neighbors[(size_t) x.first] = INF;
+                    for (auto &x : row) neighbors[(size_t) x.first] = INF;
                 }
                 p = q;
             }
         }
         // ---- retainOnlySmallestOffset (GraphCreatorKmerBased.cpp:87; main.cpp:346 after the last pass)
-        for (auto &row : V) {
-            if (row.size() < 2) continue;
-            std::sort(row.begin(), row.end());
-            size_t w = 0;
-            for (size_t k = 0; k < row.size(); k++)
-                if (w == 0 || row[w - 1].first != row[k].first) row[w++] = row[k];
-            row.resize(w);
-        }
+        run_threads([&](unsigned t) {
+            const size_t r0 = (size_t) n * t / n_thr, r1 = (size_t) n * (t + 1) / n_thr;
+            for (size_t r = r0; r < r1; r++) {
+                auto &row = V[r];
+                if (row.size() < 2) continue;
+                std::sort(row.begin(), row.end());
+                size_t w = 0;
+                for (size_t k = 0; k < row.size(); k++)
+                    if (w == 0 || row[w - 1].first != row[k].first) row[w++] = row[k];
+                row.resize(w);
+            }
+        });
         std::rotate(prio, prio + 1, prio + 4);
+        t_replay += now_ms() - te;
     }
 
     // ---- result
@@ -400,6 +470,11 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
         tm->device_ms = gpu_ms;  // k-mer + canAlign kernels incl. their transfers
         tm->total_ms = now_ms() - t0;
         tm->kernel_launches = launches;
+        tm->stage_ms[0] = t_kmers;   // LI k-mers (GPU + D2H)
+        tm->stage_ms[1] = t_sort;    // bucket scatter + std::sort (host)
+        tm->stage_ms[2] = t_enum;    // pair enumeration (host)
+        tm->stage_ms[3] = t_verify;  // canAlign batch (H2D + GPU + D2H)
+        tm->stage_ms[4] = t_replay;  // ordered replay + row dedupe (host)
         tm->stage_ms[5] = (double) n_ids;        // diagnostics: dead-end reads that took part,
         tm->stage_ms[6] = (double) pairs_total;  // pairs verified on the GPU over the four passes
     }

@@ -248,6 +248,8 @@ class GraphCreatorLI:
         finally:
             lib.alga_gpu_free_csr(C.byref(cout))
         self.timing = {"h2d_ms": tm.h2d_ms, "device_ms": tm.device_ms, "total_ms": tm.total_ms,
-                       "kernel_launches": tm.kernel_launches, "n_dead_end_reads": int(tm.stage_ms[5]),
+                       "kernel_launches": tm.kernel_launches,
+                       "stage_ms": dict(zip(("li_kmers", "bucket_sort", "enumerate", "can_align", "replay"), list(tm.stage_ms)[:5])),
+                       "n_dead_end_reads": int(tm.stage_ms[5]),
                        "n_pairs_verified": int(tm.stage_ms[6])}
         return self.graph
