@@ -259,6 +259,14 @@ __device__ __forceinline__ void load_bucket(const uint32_t *__restrict__ p, uint
                  : "l"(p));
 }
 
+// The same load for the hot probe loops: not allocated in L1 (a random bucket is never reused there, and filling L1
+// lines with them halves the rate -- measured with cp.async.ca against .cg in phase 2), kept in L2 with priority.
+__device__ __forceinline__ void load_bucket_na(const uint32_t *__restrict__ p, uint32_t (&e)[8], uint64_t policy) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(e[0]), "=r"(e[1]), "=r"(e[2]), "=r"(e[3]), "=r"(e[4]), "=r"(e[5]), "=r"(e[6]), "=r"(e[7])
+                 : "l"(p), "l"(policy));
+}
+
 // Walk the bucket chain of hash h and call f(read_id) for every entry whose tag matches.
 template <class F>
 __device__ __forceinline__ void probe_seed(const SeedTable &t, uint64_t h, F &&f) {

@@ -276,6 +276,7 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
     const bool listed = id_list != nullptr;
     const uint64_t n_items = listed ? (uint64_t) *n_list : (uint64_t) (hi - lo);
     if (listed && n_items < kSecondPassMin) return;  // a short queue is cheaper in the generic kernel (one tile = 40 us)
+    const uint64_t pol = l2_evict_last_policy();
     const uint64_t n_tiles = (n_items + 31) / 32;
     const uint64_t warp_id = (uint64_t) blockIdx.x * kWarps + wib, n_warps = (uint64_t) gridDim.x * kWarps;
     for (uint64_t tile = warp_id; tile < n_tiles; tile += n_warps) {
@@ -319,7 +320,7 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
             const uint64_t h = mix64(window_key(w0, w1, w2, sh) & P.seed_mask);
             tag = tag_of(T, h);
             bk = bucket_of(h, T.n_buckets);
-            load_bucket(T.slots + (uint64_t) bk * kSlotsPerBucket, e);
+            load_bucket_na(T.slots + (uint64_t) bk * kSlotsPerBucket, e, pol);
         }
         while (true) {
             // ---- probe until every lane has 3 candidates (confirmed + pending) or ran out of lengths
@@ -343,7 +344,7 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
                         const uint64_t h = mix64(window_key(w0, w1, w2, sh) & P.seed_mask);
                         tag = tag_of(T, h);
                         bk = bucket_of(h, T.n_buckets);
-                        load_bucket(T.slots + (uint64_t) bk * kSlotsPerBucket, e);
+                        load_bucket_na(T.slots + (uint64_t) bk * kSlotsPerBucket, e, pol);
                     } else {
                         more = false;
                     }
