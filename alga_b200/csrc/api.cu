@@ -154,7 +154,8 @@ struct alga_ps_plan {
     uint64_t n_edges = 0;
     double last_device_ms = 0;
     double stage_ms[8] = {0};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t side = nullptr;  // the suffix table is built here while phase 1 (prefix table only) runs
     cudaEvent_t ev_stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     ~alga_ps_plan() {
@@ -170,6 +171,9 @@ struct alga_ps_plan {
         if (h_u64) cudaFreeHost(h_u64);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (side) cudaStreamDestroy(side);
         for (cudaEvent_t e : ev_stage)
             if (e) cudaEventDestroy(e);
     }
@@ -247,7 +251,8 @@ void size_table(SeedTable &t, uint32_t entries, uint32_t n_reads, int world = 1)
     t.tag_mask = (uint32_t) ((1ull << (32 - bits)) - 1ull);
 }
 
-int stage_index_begin(alga_ps_plan *plan, cudaStream_t s) {
+// s2 != nullptr: everything that concerns the suffix table goes to s2
+int stage_index_begin(alga_ps_plan *plan, cudaStream_t s, cudaStream_t s2 = nullptr) {
     if (!plan->bound) return fail(ALGA_E_INVALID, "no read set bound to the plan");
     size_table(plan->Tp, plan->stats.n_prefix, plan->R.n);
     size_table(plan->Ts, plan->stats.n_suffix, plan->R.n);
@@ -257,7 +262,7 @@ int stage_index_begin(alga_ps_plan *plan, cudaStream_t s) {
     plan->Tp.slots = plan->tp.as<uint32_t>();
     plan->Ts.slots = plan->ts.as<uint32_t>();
     CK(cudaMemsetAsync(plan->tp.p, 0xFF, bp, s));
-    CK(cudaMemsetAsync(plan->ts.p, 0xFF, bs, s));
+    CK(cudaMemsetAsync(plan->ts.p, 0xFF, bs, s2 ? s2 : s));
     return ALGA_OK;
 }
 
@@ -381,6 +386,7 @@ int stage_csr(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int32_t *tripl
     CKR(plan->row_off.ensure(((size_t) n + 1) * 8));
     CKR(plan->scan_ws.ensure(scan_workspace_bytes(n)));
     launch_scan_u64(outdeg, plan->row_off.as<uint64_t>(), n, plan->scan_ws.p, s, plan->cfg);
+    CK(cudaMemcpyAsync(plan->h_u64, plan->row_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, s));  // read with the counters
     CKR(plan->nbr.ensure((size_t) (n_tr ? n_tr : 1) * 4));
     CKR(plan->off.ensure((size_t) (n_tr ? n_tr : 1) * 4));
     CKR(plan->big_rows.ensure((size_t) (n ? n : 1) * 4));
@@ -400,8 +406,7 @@ int stage_csr(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int32_t *tripl
                              plan->tmp_off.as<int32_t>(), s, plan->cfg);
         CK(cudaGetLastError());
     }
-    CK(cudaMemcpyAsync(plan->h_u64, plan->row_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    if (plan->h_counters->n_big) CK(cudaStreamSynchronize(s));
     plan->n_edges = *plan->h_u64;
     plan->res_lo = lo;
     plan->res_hi = hi;
@@ -454,6 +459,9 @@ int alga_ps_plan_create(alga_ps_plan **out, const alga_ps_params *params) {
         CK(cudaMallocHost((void **) &plan->h_u64, 8));
         CK(cudaEventCreate(&plan->ev0));
         CK(cudaEventCreate(&plan->ev1));
+        CK(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&plan->side, cudaStreamNonBlocking));
         for (cudaEvent_t &e : plan->ev_stage) CK(cudaEventCreate(&e));
         CKR(plan->counters_d.ensure(sizeof(Counters)));
         return ALGA_OK;
@@ -829,7 +837,16 @@ int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
     if (plan->over_cap < kOverScanMax) plan->over_cap = n / 8 + 65536;
     for (int attempt = 0;; attempt++) {
         CK(cudaEventRecord(plan->ev0, s));
-        CKR(stage_index(plan, s));
+        // seed index: the prefix table on this stream, the suffix table -- first needed by phase 2 -- on a side stream,
+        // so its build overlaps phase 1
+        CK(cudaEventRecord(plan->ev_fork, s));
+        CK(cudaStreamWaitEvent(plan->side, plan->ev_fork, 0));
+        CKR(stage_index_begin(plan, s, plan->side));
+        launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, 0, n, 0u, 0xFFFFFFFFu, s, plan->cfg, 1);
+        launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, 0, n, 0u, 0xFFFFFFFFu, plan->side, plan->cfg, 2);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(plan->ev_join, plan->side));
+        plan->index_valid = true;
         CK(cudaEventRecord(plan->ev_stage[0], s));
         // phase 1 writes every edge straight into the row of its target read (transposed graph, plan->row_cap per target)
         CKR(plan->rows.ensure((size_t) (n ? n : 1) * plan->row_cap * sizeof(RevEntry)));
@@ -849,6 +866,7 @@ int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
                                 plan->rows.as<RevEntry>(), plan->row_cap, n, plan->rev_off.as<uint32_t>(), plan->rev.as<RevEntry>(),
                                 (uint64_t) (n ? n : 1) * kSmallEdgesKept, &dc->rev_overflow, plan->scan_ws.p, s, plan->cfg);
         CK(cudaGetLastError());
+        CK(cudaStreamWaitEvent(s, plan->ev_join, 0));  // the suffix table is complete
         CK(cudaEventRecord(plan->ev_stage[2], s));
         // phase 2 with fused out-degree counting (not in the reversed-result corner)
         CKR(plan->outdeg.ensure((size_t) (n ? n : 1) * 4));

@@ -25,8 +25,9 @@ void launch_read_stats(const ReadsDev &R, int lmin, int min_offset, ReadStats *d
 // --- seed index -------------------------------------------------------------------------------
 // inserts the seeds of the reads [lo, hi) whose bucket lies in [b_lo, b_hi) (the tables must have been cleared before
 // the first range; prefix and suffix table have the same number of buckets when b_lo / b_hi restrict anything)
+// which: 1 = prefix table only, 2 = suffix table only, 3 = both
 void launch_build_index(const ReadsDev &R, const PsDev &P, SeedTable prefix, SeedTable suffix, uint32_t lo, uint32_t hi,
-                        uint32_t b_lo, uint32_t b_hi, cudaStream_t s, const LaunchCfg &cfg);
+                        uint32_t b_lo, uint32_t b_hi, cudaStream_t s, const LaunchCfg &cfg, int which = 3);
 
 // --- sharded runs: read what the peers produced for this rank out of their exchange workspaces (NVLink) ----
 // seg[p] / cnt[p]: peer p's segment for this rank and its entry count (device pointers valid in this process)

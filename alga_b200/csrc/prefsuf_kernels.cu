@@ -60,18 +60,19 @@ __global__ void read_stats_kernel(ReadsDev R, int lmin, int min_offset, ReadStat
 // ------------------------------------------------------------------------------------------------
 // Seed index build: one thread per read, two inserts (prefix side, suffix side).
 // [b_lo, b_hi): only seeds whose bucket falls in this range are inserted (sharded build: the rank's own slice)
+// which: bit 0 = prefix table, bit 1 = suffix table
 __global__ void build_index_kernel(ReadsDev R, PsDev P, SeedTable tp, SeedTable ts, uint32_t lo, uint32_t hi, uint32_t b_lo,
-                                   uint32_t b_hi) {
+                                   uint32_t b_hi, int which) {
     for (uint64_t i = (uint64_t) lo + blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < hi; i += (uint64_t) gridDim.x * blockDim.x) {
         const uint32_t len = P.uniform_len ? P.uniform_len : R.len[i];
         if (len == 0 || (int64_t) len < P.lmin) continue;
         const uint32_t *p = read_ptr(R, (uint32_t) i);
-        if (flag_to(R, (uint32_t) i)) {
+        if ((which & 1) && flag_to(R, (uint32_t) i)) {
             const uint64_t h = mix64(bits64(p, 0) & P.seed_mask);
             const uint32_t bk = bucket_of(h, tp.n_buckets);
             if (bk >= b_lo && bk < b_hi) insert_seed(tp, h, (uint32_t) i);
         }
-        if (flag_from(R, (uint32_t) i) && (int64_t) len - P.min_offset >= P.lmin) {
+        if ((which & 2) && flag_from(R, (uint32_t) i) && (int64_t) len - P.min_offset >= P.lmin) {
             const uint64_t h = mix64(bits64(p, 2u * (len - (uint32_t) P.seed_nt)) & P.seed_mask);
             const uint32_t bk = bucket_of(h, ts.n_buckets);
             if (bk >= b_lo && bk < b_hi) insert_seed(ts, h, (uint32_t) i);
@@ -799,9 +800,9 @@ void launch_read_stats(const ReadsDev &R, int lmin, int min_offset, ReadStats *d
 }
 
 void launch_build_index(const ReadsDev &R, const PsDev &P, SeedTable prefix, SeedTable suffix, uint32_t lo, uint32_t hi,
-                        uint32_t b_lo, uint32_t b_hi, cudaStream_t s, const LaunchCfg &cfg) {
+                        uint32_t b_lo, uint32_t b_hi, cudaStream_t s, const LaunchCfg &cfg, int which) {
     if (hi <= lo) return;
-    build_index_kernel<<<grid_for(hi - lo, 256, cfg), 256, 0, s>>>(R, P, prefix, suffix, lo, hi, b_lo, b_hi);
+    build_index_kernel<<<grid_for(hi - lo, 256, cfg), 256, 0, s>>>(R, P, prefix, suffix, lo, hi, b_lo, b_hi, which);
     bump(cfg);
 }
 
