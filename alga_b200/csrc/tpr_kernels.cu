@@ -5,25 +5,32 @@
 //
 //   probe    walk the overlap lengths, one 32-byte bucket of the seed index per length.  The K-nucleotide seed
 //            window slides through a 96-bit register window over the read staged in shared memory (two funnel
-//            shifts per length), the hash is four IMADs.  Buckets are fetched by cp.async (2 x 16 bytes, L2-only,
-//            evict_last: the index is the one structure worth keeping in the 126 MB L2) into a per-thread ring in
-//            shared memory kRing lengths ahead of their use, so kRing random sectors per thread are in flight
-//            without costing registers.  A bucket is tested with eight XOR + a min tree (an entry with the right tag
-//            XORs to its bare read id, everything else to something larger).  Tag hits (0.3 per length) are only
-//            QUEUED in shared memory; in phase 2 the first 64 bits of the hit read (all its overhang tail needs)
-//            follow by cp.async as well.
+//            shifts per length), the hash is four IMADs.  Random buckets must not pass through L1 (filling its
+//            lines with them halves the rate: 2.5 vs 1.4 ms in phase 2) and are the one structure worth keeping in
+//            L2 (evict_last).  Phase 2 fetches them by cp.async.cg (2 x 16 bytes) into a per-thread ring in shared
+//            memory kRing2 lengths ahead of their use, so kRing2 random sectors per thread are in flight without
+//            costing registers; phase 1, whose lanes stop after about a third of their lengths, keeps one bucket in
+//            flight in registers (LDG.E.NA.256).  A bucket is tested with eight XOR + a min tree (an entry with the
+//            right tag XORs to its bare read id, everything else to something larger).  Tag hits (0.3 per length)
+//            are only QUEUED; in phase 2 the first 64 bits of the hit read (all its overhang tail needs) follow by
+//            cp.async as well.
 //   resolve  take the queued hits in order.  Exact 2-bit compares of whole overlaps are thread-local: every lane
 //            verifies its own candidate, words of the candidate straight from L1/L2, words of the own read from
 //            shared memory -- at 3 candidates per read in phase 1 nearly all lanes are busy.
 //
-// History (profiles/): the first thread-per-read version interleaved probe and resolve per length and verified with
-// warp-cooperative groups; ncu showed it issue-bound at 300-440 warp instructions per (warp, length) with 9 of 32
-// lanes inside the hit branch (r01d).  Splitting the loops (r01h) halved the instructions and left the kernels
-// latency-bound on the bucket loads (27 % of the stall samples at 20 warps per SM, one bucket in flight per thread).
+// Two passes: the first over all reads allows two tag matches per window; reads that see more (same start position,
+// different sequencing errors) are queued, and a queue of at least kSecondPassMin reads is run again with four
+// matches per window (template parameter MAXM) before the rest goes to the generic kernels.
 //
-// Reads the fast path cannot take (longer than 512 nt, a window with more than four tag matches, offsets above 32,
-// more queued arrivals than fit, a source id that occurs twice for one target, ...) are queued for the generic
-// kernels of prefsuf_kernels.cu, which replay GraphCreatorPrefSuf.cpp:356-488 literally.
+// History (profiles/): the first thread-per-read version interleaved probe and resolve per
+// length and verified with warp-cooperative groups; ncu showed it issue-bound at 300-440 warp instructions per
+// (warp, length) with 9 of 32 lanes inside the hit branch (r01d).  Splitting the loops (r01h) halved the
+// instructions and left the kernels latency-bound on the bucket loads (27 % of the stall samples at 20 warps per
+// SM, one bucket in flight per thread); the cp.async ring (r01i) removed that.
+//
+// Reads the fast path cannot take at all (longer than 512 nt, a window with more than four tag matches, offsets above
+// 32, more queued arrivals than fit, a source id that occurs twice for one target, ...) go to the generic kernels of
+// prefsuf_kernels.cu, which replay GraphCreatorPrefSuf.cpp:356-488 literally.
 #include <algorithm>
 
 #include "launch.h"
