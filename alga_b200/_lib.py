@@ -93,6 +93,7 @@ SYMBOLS = {
     "alga_gpu_fingerprints": (C.c_int, [C.POINTER(Reads), C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "alga_gpu_pack_reads": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_int32, _P]),
     "alga_gpu_verify_pairs": (C.c_int, [C.POINTER(Reads), _P, C.c_uint64, C.POINTER(VerifyParams), _P]),
+    "alga_gpu_prefix_reads": (C.c_int, [C.POINTER(Reads), C.c_int32, C.c_int32, _P, C.POINTER(Timing)]),
     "alga_gpu_supplement": (C.c_int, [C.POINTER(Reads), C.POINTER(Csr), C.POINTER(SupParams), C.POINTER(Csr),
                                       C.POINTER(Timing)]),
     "alga_gpu_li_kmers": (C.c_int, [C.POINTER(Reads), _P, C.c_uint32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),

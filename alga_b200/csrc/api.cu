@@ -1152,6 +1152,60 @@ int alga_gpu_verify_pairs(const alga_reads *reads, const int32_t *pairs, uint64_
     return r;
 }
 
+int alga_gpu_prefix_reads(const alga_reads *reads, int32_t remove_type, int32_t device, uint8_t *mask, alga_timing *timing) {
+    if (!reads || (reads->n_reads && !mask)) return fail(ALGA_E_INVALID, "null argument");
+    if (remove_type != 1 && remove_type != 2) return fail(ALGA_E_INVALID, "remove_type must be 1 (duplicates) or 2 (all prefix reads)");
+    const double t0 = now_ms();
+    LaunchCfg cfg;
+    uint64_t launches = 0;
+    cfg.launches = &launches;
+    CKR(pick_device(device, &cfg));
+    TmpReads t;
+    CKR(t.upload(reads));
+    const double t1 = now_ms();
+    const uint32_t n = reads->n_reads;
+    DevBuf table, lenmap, flags, dmask;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    float dev_ms = 0;
+    int r = [&]() -> int {
+        SeedTable T{};
+        size_table(T, n, n);
+        const size_t tb = (size_t) T.n_buckets * kSlotsPerBucket * 4;
+        CKR(table.ensure(tb));
+        CKR(lenmap.ensure(prefix_reads_lenmap_words() * 4));
+        CKR(flags.ensure((size_t) (n ? n : 1) * 4));
+        CKR(dmask.ensure(n ? n : 1));
+        T.slots = table.as<uint32_t>();
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, 0));
+        CK(cudaMemsetAsync(table.p, 0xFF, tb, 0));
+        launch_prefix_reads(t.R, T, remove_type, lenmap.as<uint32_t>(), flags.as<uint32_t>(), dmask.as<uint8_t>(), 0, cfg);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e1, 0));
+        uint32_t too_long = 0;
+        CK(cudaMemcpy(&too_long, lenmap.as<uint32_t>() + prefix_reads_lenmap_words() - 1, 4, cudaMemcpyDeviceToHost));
+        if (too_long) return fail(ALGA_E_INVALID, "a read is longer than 65535 nucleotides");
+        if (n) CK(cudaMemcpy(mask, dmask.p, n, cudaMemcpyDeviceToHost));
+        CK(cudaEventElapsedTime(&dev_ms, e0, e1));
+        return ALGA_OK;
+    }();
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    table.release();
+    lenmap.release();
+    flags.release();
+    dmask.release();
+    if (r == ALGA_OK && timing) {
+        memset(timing, 0, sizeof(*timing));
+        timing->h2d_ms = t1 - t0;
+        timing->device_ms = dev_ms;
+        timing->total_ms = now_ms() - t0;
+        timing->kernel_launches = launches;
+    }
+    return r;
+}
+
 int alga_gpu_supplement(const alga_reads *reads, const alga_csr *graph_in, const alga_sup_params *params,
                         alga_csr *graph_out, alga_timing *timing) {
     if (!reads || !graph_in || !params || !graph_out) return fail(ALGA_E_INVALID, "null argument");

@@ -134,6 +134,13 @@ struct VerifyDev {
 void launch_verify_pairs(const ReadsDev &R, const int32_t *pairs, uint64_t n_pairs, const VerifyDev &V,
                          uint8_t *verdict, cudaStream_t s, const LaunchCfg &cfg);
 
+// --- ReadPreprocess::getPrefixReads (preprocess.cu): mask[i] = 1 for duplicates / prefix reads (+ reverse complements)
+// t: an empty (all 0xFF) table sized for R.n entries; lenmap: prefix_reads_lenmap_words() words; flags: R.n words.
+// lenmap[last] != 0 afterwards: a read is longer than the 65 535 nucleotides the length map covers.
+void launch_prefix_reads(const ReadsDev &R, const SeedTable &t, int remove_type, uint32_t *lenmap, uint32_t *flags,
+                         uint8_t *mask, cudaStream_t s, const LaunchCfg &cfg);
+size_t prefix_reads_lenmap_words();
+
 // --- error-rate supplement (supplement.cu) -------------------------------------------------------
 // LI k-mers (Read.cpp:145-226) of the reads d_ids[0 .. n_ids): `intervals` slots per read, ind = -1 where absent
 int run_li_kmers(const ReadsDev &R, const uint32_t *d_ids, uint32_t n_ids, const int32_t prio[4], int K, int intervals,

@@ -253,3 +253,24 @@ class GraphCreatorLI:
                        "n_dead_end_reads": int(tm.stage_ms[5]),
                        "n_pairs_verified": int(tm.stage_ms[6])}
         return self.graph
+
+
+class ReadPreprocess:
+    """Mirror of the reference's ``ReadPreprocess`` (include/IO/ReadPreprocess.h:11-17) for the one method the driver
+    calls before the graph build (main.cpp:132-134)."""
+
+    def __init__(self, reads: ReadSet, device: int = 0):
+        self.reads, self.device = reads, device
+        self.timing: dict | None = None
+
+    def getPrefixReads(self, remove_type: int = 2) -> np.ndarray:
+        """uint8 mask: 1 = removed (duplicates except the greatest id; with ``remove_type`` 2 also proper prefixes of
+        other reads and their reverse complements ``id ^ 1``).  ReadPreprocess.cpp:13-77."""
+        lib = _lib.load()
+        mask = np.zeros(self.reads.n, np.uint8)
+        st = _reads_struct(self.reads)
+        tm = _lib.Timing()
+        _lib.check(lib.alga_gpu_prefix_reads(C.byref(st), remove_type, self.device, mask.ctypes.data, C.byref(tm)))
+        self.timing = {"h2d_ms": tm.h2d_ms, "device_ms": tm.device_ms, "total_ms": tm.total_ms,
+                       "kernel_launches": tm.kernel_launches}
+        return mask

@@ -248,6 +248,15 @@ int alga_gpu_supplement(const alga_reads *reads, const alga_csr *graph_in, const
 int alga_gpu_li_kmers(const alga_reads *reads, const uint32_t *ids, uint32_t n_ids, const int32_t priorities[4],
                       int32_t kmer_length, int32_t intervals, int32_t device, uint64_t *hash_out, int32_t *ind_out);
 
+/* ---- read preprocessing (the step before the graph build) ----------------------------
+ * ReadPreprocess::getPrefixReads (src/IO/ReadPreprocess.cpp:13-77, called from main.cpp:132-134): mask[i] = 1 for every
+ * read the reference removes -- identical reads except the one with the greatest id and, with remove_type 2
+ * (Params::PREF_READS_ALL_PREFIX_READS, the default), reads that are a proper prefix of another read together with
+ * their reverse complements (id ^ 1); remove_type 1 = Params::PREF_READS_ONLY_DUPLICATES.  Host buffers; align flags
+ * are ignored.  Reads of up to 65535 nucleotides. */
+int alga_gpu_prefix_reads(const alga_reads *reads, int32_t remove_type, int32_t device, uint8_t *mask,
+                          alga_timing *timing /* may be NULL */);
+
 /* ---- misc ---------------------------------------------------------------------------------- */
 /* Page-locked host memory for callers that stage the packed reads themselves (the shim gathers the blocks of
  * vector<Read*> straight into such a buffer, so the upload runs at full host->device rate).  NULL on failure. */

@@ -106,3 +106,15 @@ def run_supplement(reads, edges_in, threshold_pct, max_offset_pct, min_overlap_a
                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, cwd=d)
         info = json.loads(out.stdout.decode().strip().splitlines()[-1])
         return read_edges(op), info
+
+
+def run_prefix_reads(reads, remove_type=2, threads=1) -> np.ndarray:
+    """Run the reference's ReadPreprocess::getPrefixReads; returns the uint8 removal mask."""
+    if not available():
+        raise RuntimeError("oracle/_ref/alga_ref_harness is not built (make -C oracle ref)")
+    with tempfile.TemporaryDirectory() as d:
+        rp, mp = os.path.join(d, "in.algr"), os.path.join(d, "mask.bin")
+        write_reads(rp, reads, 0, 0, 0)
+        subprocess.run([HARNESS, "prefixreads", rp, mp, str(remove_type), str(threads)], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=d)
+        return np.fromfile(mp, dtype=np.uint8)

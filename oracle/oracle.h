@@ -66,6 +66,11 @@ void oracle_li_kmers(const oracle_reads *r, const uint32_t *ids, uint32_t n_ids,
 int32_t *oracle_supplement(const oracle_reads *r, const int32_t *edges_in, uint64_t n_in, const oracle_sup_params *p,
                            uint64_t *n_out);
 
+/* ReadPreprocess::getPrefixReads (ReadPreprocess.cpp:13-77): mask[i] = 1 for reads that are removed -- duplicates except
+ * the one with the greatest id and, with remove_type 2 (the default), reads that are a proper prefix of another read
+ * together with their reverse complements (id ^ 1).  remove_type 1 = duplicates only. */
+void oracle_prefix_reads(const oracle_reads *r, int32_t remove_type, uint8_t *mask);
+
 void oracle_free(void *p);
 
 #ifdef __cplusplus

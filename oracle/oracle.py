@@ -27,7 +27,7 @@ class _SupParams(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(HERE, f) for f in ("prefsuf_oracle.c", "verify_oracle.c", "supplement_oracle.cpp", "oracle.h",
+    srcs = [os.path.join(HERE, f) for f in ("prefsuf_oracle.c", "verify_oracle.c", "supplement_oracle.cpp", "preprocess_oracle.c", "oracle.h",
                                             "Makefile")]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         subprocess.run(["make", "-C", HERE, "liboracle.so"], check=True, stdout=subprocess.DEVNULL)
@@ -56,6 +56,8 @@ def _load():
         _lib.oracle_li_kmers.restype = None
         _lib.oracle_li_kmers.argtypes = [C.POINTER(_Reads), C.c_void_p, C.c_uint32, C.c_void_p, C.c_int32, C.c_int32,
                                          C.c_void_p, C.c_void_p]
+        _lib.oracle_prefix_reads.restype = None
+        _lib.oracle_prefix_reads.argtypes = [C.POINTER(_Reads), C.c_int32, C.c_void_p]
         _lib.oracle_free.argtypes = [C.c_void_p]
     return _lib
 
@@ -124,3 +126,12 @@ def li_kmers(reads, ids, priorities=(0, 1, 2, 3), kmer_length=35, intervals=6):
     lib.oracle_li_kmers(C.byref(rs), ids.ctypes.data, ids.shape[0], pr.ctypes.data, kmer_length, intervals, h.ctypes.data,
                         ind.ctypes.data)
     return h, ind
+
+
+def prefix_reads(reads, remove_type=2) -> np.ndarray:
+    """ReadPreprocess::getPrefixReads: uint8 mask of the reads that are removed (duplicates, prefix reads + revcomps)."""
+    lib = _load()
+    rs = _reads_struct(reads)
+    mask = np.zeros(reads.n, np.uint8)
+    lib.oracle_prefix_reads(C.byref(rs), remove_type, mask.ctypes.data)
+    return mask

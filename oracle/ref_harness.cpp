@@ -23,6 +23,7 @@
 #include <DataStructures/Graph.h>
 #include <GraphCreators/GraphCreatorPrefSuf.h>
 #include <GraphCreators/GraphCreatorLI.h>
+#include <IO/ReadPreprocess.h>
 #include <AlignmentControllers/AlignmentControllerHybrid.h>
 #include <AlignmentControllers/AlignmentControllerLowErrorRate.h>
 
@@ -244,6 +245,28 @@ int run_supplement(const char *reads_path, const char *edges_path, const char *o
     return 0;
 }
 
+// ReadPreprocess::getPrefixReads (main.cpp:132-134) on a given read set: one byte per read, 1 = removed.
+int run_prefix_reads(const char *reads_path, const char *out_path, int remove_type, int threads) {
+    ReadsFile r = load_reads(reads_path);
+    Params::THREADS = threads;
+    Params::REMOVE_PREF_READS_TYPE = remove_type;
+    build_reads(r);
+    ReadPreprocess prepr;
+    VB marked = prepr.getPrefixReads();
+    std::vector<uint8_t> mask(r.n, 0);
+    uint64_t removed = 0;
+    for (uint32_t i = 0; i < r.n; i++) {
+        mask[i] = marked[i] ? 1 : 0;
+        removed += mask[i];
+    }
+    FILE *f = fopen(out_path, "wb");
+    if (!f) die("cannot open mask output");
+    fwrite(mask.data(), 1, r.n, f);
+    fclose(f);
+    printf("{\"n\": %u, \"removed\": %llu}\n", r.n, (unsigned long long) removed);
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -254,6 +277,8 @@ int main(int argc, char **argv) {
         return run_prefsuf(argv[2], argv[3], threads);
     }
     if (argc >= 5 && strcmp(argv[1], "verify") == 0) return run_verify(argv[2], argv[3], argv[4]);
+    if (argc >= 4 && strcmp(argv[1], "prefixreads") == 0)
+        return run_prefix_reads(argv[2], argv[3], argc >= 5 ? atoi(argv[4]) : 2, argc >= 6 ? atoi(argv[5]) : 1);
     if (argc >= 9 && strcmp(argv[1], "supplement") == 0)
         return run_supplement(argv[2], argv[3], argv[4], atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]),
                               argc >= 10 ? atoi(argv[9]) : 1);
@@ -261,7 +286,8 @@ int main(int argc, char **argv) {
             "usage: %s prefsuf <reads.algr> <edges.alge|-> [threads]\n"
             "       %s verify  <reads.algr> <pairs.algp> <verdict.bin>\n"
             "       %s supplement <reads.algr> <edges_in.alge> <edges_out.alge> <min_overlap_area> <max_offset_pct> "
-            "<threshold_pct> <kmer_length_bucket> [threads]\n",
-            argv[0], argv[0], argv[0]);
+            "<threshold_pct> <kmer_length_bucket> [threads]\n"
+            "       %s prefixreads <reads.algr> <mask.bin> [remove_type 1|2] [threads]\n",
+            argv[0], argv[0], argv[0], argv[0]);
     return 2;
 }

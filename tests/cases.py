@@ -154,3 +154,20 @@ def supplement_case(name):
         rs = synth.make_variable_length(30000, 3000, 90, 150, seed=17, error=0.01, repeats=3)
         return rs, 66, 94, supplement_params(float(rs.len_nt[rs.len_nt > 0].mean()))
     raise KeyError(name)
+
+
+PREPROCESS_CASES = ["pre_equal", "pre_varlen", "pre_periodic"]
+
+
+def preprocess_case(name):
+    """Read sets BEFORE ReadPreprocess (main.cpp:132-232): duplicates and contained reads still in."""
+    if name == "pre_equal":     # equal lengths, 2x150 bp at 50x over 30 kbp: many exact duplicates
+        rng = np.random.default_rng(41)
+        g = synth.make_genome(30_000, rng)
+        m1, m2 = synth.sample_paired_end(g, 150, 50, rng, 0.0)
+        return readset.from_code_matrix(synth.strand_nodes(m1, m2))
+    if name == "pre_varlen":    # ragged lengths: proper prefixes, their reverse complements, duplicates
+        return synth.make_variable_length(15000, 4000, 40, 150, seed=42, repeats=2, dedupe=False)
+    if name == "pre_periodic":  # low complexity: long runs of reads that are prefixes of each other
+        return _periodic(43, 1500, dedupe=False)
+    raise KeyError(name)

@@ -11,7 +11,8 @@ set and the edge set is stored as `<case>.npz`:
     params     (min_overlap, rs_min_overlap, min_offset)
 `verify_pairs.npz` holds (pairs, verdicts) of AlignmentControllerHybrid::canAlign evaluated by the
 reference on candidate pairs of the cfg3_small read set; `sup_*.npz` hold the graph before and after the reference's
-error-rate supplement (GraphCreatorLI, main.cpp:300-355) on the supplement cases of tests/cases.py.
+error-rate supplement (GraphCreatorLI, main.cpp:300-355) on the supplement cases of tests/cases.py; `pre_*.npz` hold the
+removal masks of ReadPreprocess::getPrefixReads (both removal types) on the preprocessing cases.
 """
 import hashlib
 import os
@@ -23,7 +24,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from oracle import harness  # noqa: E402
-from tests.cases import CASES, SUPPLEMENT_CASES, build_case, supplement_case, verify_case  # noqa: E402
+from tests.cases import (CASES, PREPROCESS_CASES, SUPPLEMENT_CASES, build_case, preprocess_case, supplement_case,  # noqa: E402
+                         verify_case)
 
 
 def input_sha(rs) -> str:
@@ -60,6 +62,13 @@ def main():
                             params=np.array([lmin, rsmin, sp["threshold_pct"], sp["max_offset_pct"], sp["min_overlap_area"],
                                              sp["kmer_length_bucket"]], np.int32))
         print(f"{name}: n={rs.n} E {before.shape[0]} -> {after.shape[0]}")
+    # ReadPreprocess::getPrefixReads (main.cpp:132-134) on read sets that still hold duplicates and contained reads
+    for name in PREPROCESS_CASES:
+        rs = preprocess_case(name)
+        m2 = harness.run_prefix_reads(rs, 2)
+        m1 = harness.run_prefix_reads(rs, 1)
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), mask_all=m2, mask_dup=m1, input_sha=np.array(input_sha(rs)))
+        print(f"{name}: n={rs.n} removed {int(m2.sum())} (all prefix reads) / {int(m1.sum())} (duplicates only)")
 
 
 if __name__ == "__main__":

@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 
 from oracle import harness, oracle
-from tests.cases import CASES, SUPPLEMENT_CASES, build_case, supplement_case, verify_case
+from tests.cases import (CASES, PREPROCESS_CASES, SUPPLEMENT_CASES, build_case, preprocess_case, supplement_case,
+                         verify_case)
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -122,3 +123,20 @@ def test_li_kmer_definition():
                     continue
                 best = min(range(lo, hi), key=lambda p: (vals[p], p))
                 assert ind[q, iv] == best and int(h[q, iv]) == vals[best] % (10 ** 18 + 3)
+
+
+@pytest.mark.parametrize("name", PREPROCESS_CASES)
+def test_oracle_prefix_reads_matches_reference_golden(name):
+    """ReadPreprocess::getPrefixReads (ReadPreprocess.cpp:13-77), both removal types."""
+    rs = preprocess_case(name)
+    z = load_golden(name)
+    assert str(z["input_sha"]) == input_sha(rs), "seeded generator drifted: regenerate tests/golden"
+    assert np.array_equal(oracle.prefix_reads(rs, 2), z["mask_all"])
+    assert np.array_equal(oracle.prefix_reads(rs, 1), z["mask_dup"])
+    assert 0 < z["mask_dup"].sum() <= z["mask_all"].sum() < rs.n
+
+
+@pytest.mark.skipif(not harness.available(), reason="oracle/_ref/alga_ref_harness not present")
+def test_oracle_prefix_reads_matches_reference_live():
+    rs = preprocess_case("pre_varlen")
+    assert np.array_equal(oracle.prefix_reads(rs, 2), harness.run_prefix_reads(rs, 2))
