@@ -402,6 +402,38 @@ def run_ours(args):
                       "params": sp, **li.timing,
                       "note": "alga_gpu_supplement: LI k-mers + canAlign on the GPU, bucket sort + ordered replay on the host"}
 
+    preprocess = None
+    if world == 1 and args.with_preprocess:
+        # ReadPreprocess::getPrefixReads on the strand-reads BEFORE duplicate removal, host to host
+        from alga_b200 import readset as _rs
+        from alga_b200.graph_creator import ReadPreprocess
+
+        kwp = dict(synth.CONFIGS[args.workload])
+        kwp["genome_size"] = max(20_000, int(kwp["genome_size"] * args.scale))
+        rngp = np.random.default_rng(kwp["seed"])
+        gen = synth.make_genome(kwp["genome_size"], rngp, repeats=kwp.get("repeats", 0))
+        if kwp["paired"]:
+            m1, m2 = synth.sample_paired_end(gen, kwp["read_len"], kwp["coverage"], rngp, kwp.get("error", 0.0))
+            raw = _rs.from_code_matrix(synth.strand_nodes(m1, m2))
+        else:
+            raw = _rs.from_code_matrix(synth.strand_nodes(synth.sample_single_end(gen, kwp["read_len"], kwp["coverage"], rngp,
+                                                                                   kwp.get("error", 0.0))))
+        rp = ReadPreprocess(raw, device=local)
+        rp.getPrefixReads(2)
+        ts = time.perf_counter()
+        mask = rp.getPrefixReads(2)
+        ms = 1e3 * (time.perf_counter() - ts)
+        preprocess = {"ms": ms, "reads": raw.n, "removed": int(mask.sum()), **rp.timing,
+                      "reads_per_s": raw.n / (ms / 1e3), "call": "alga_gpu_prefix_reads (host buffers)"}
+        from oracle import harness as _h
+        if _h.available() and not args.no_cpu:
+            import subprocess as _sp, tempfile as _tf
+            sub = _rs.ReadSet(raw.words[: (raw.n // 8) * int(raw.word_off[1])], raw.word_off[: raw.n // 8 + 1], raw.len_nt[: raw.n // 8])
+            t0c = time.perf_counter()
+            _h.run_prefix_reads(sub, 2, threads=_cpu_threads())
+            preprocess["cpu_reference"] = {"reads": sub.n, "seconds_incl_io": time.perf_counter() - t0c, "cores": _cpu_threads(),
+                                           "note": "oracle/_ref harness: ReadPreprocess::getPrefixReads on 1/8 of the reads, file IO included"}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
@@ -412,6 +444,8 @@ def run_ours(args):
     }
     if supplement:
         line["supplement"] = supplement
+    if preprocess:
+        line["preprocess"] = preprocess
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -428,6 +462,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--scale", type=float, default=1.0, help="genome scale of the GPU workload (1.0 = the named config)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--with-preprocess", action="store_true",
+                    help="also time ReadPreprocess::getPrefixReads (alga_gpu_prefix_reads) on the reads before dedupe")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = N chromosomes of the workload (default), strong = the one workload split N ways")
     args = ap.parse_args()
