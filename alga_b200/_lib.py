@@ -60,6 +60,20 @@ class SupParams(C.Structure):
                                           "kmer_length", "intervals", "kmer_length_bucket", "device")]
 
 
+class InputParams(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("file_type", "trim_left", "trim_right", "rna", "str_threshold", "device")]
+
+
+INPUT_PLAIN, INPUT_FASTA, INPUT_FASTQ = 0, 1, 2
+
+
+class ReadSetOut(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("stride_words", C.c_uint32), ("max_len_nt", C.c_uint32),
+                ("words", C.POINTER(C.c_uint32)), ("len_nt", C.POINTER(C.c_uint32)), ("old_id", C.POINTER(C.c_uint32)),
+                ("paired_offset", C.POINTER(C.c_uint8)), ("n_records", C.c_uint64 * 2), ("n_with_n", C.c_uint64),
+                ("n_str", C.c_uint64)]
+
+
 # every symbol include/alga_gpu.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -94,6 +108,10 @@ SYMBOLS = {
     "alga_gpu_pack_reads": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_int32, _P]),
     "alga_gpu_verify_pairs": (C.c_int, [C.POINTER(Reads), _P, C.c_uint64, C.POINTER(VerifyParams), _P]),
     "alga_gpu_prefix_reads": (C.c_int, [C.POINTER(Reads), C.c_int32, C.c_int32, _P, C.POINTER(Timing)]),
+    "alga_gpu_read_input": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64, C.POINTER(InputParams), C.POINTER(ReadSetOut),
+                                      C.POINTER(Timing)]),
+    "alga_gpu_remap_reads": (C.c_int, [C.POINTER(Reads), _P, C.c_int32, C.POINTER(ReadSetOut), C.POINTER(Timing)]),
+    "alga_gpu_free_read_set": (None, [C.POINTER(ReadSetOut)]),
     "alga_gpu_supplement": (C.c_int, [C.POINTER(Reads), C.POINTER(Csr), C.POINTER(SupParams), C.POINTER(Csr),
                                       C.POINTER(Timing)]),
     "alga_gpu_li_kmers": (C.c_int, [C.POINTER(Reads), _P, C.c_uint32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),

@@ -1250,3 +1250,241 @@ int alga_gpu_li_kmers(const alga_reads *reads, const uint32_t *ids, uint32_t n_i
 }
 
 }  // extern "C"
+
+// ---- InputReader::readInput / renumbering (input.cu) -----------------------------------------------------------------
+namespace {
+
+struct InputScalarsHost {  // layout of input.cu's InputScalars
+    uint32_t first_empty, first_bad, max_len, pad;
+    unsigned long long n_with_n, n_str;
+};
+
+struct InputFile {
+    DevBuf text, block_cnt, block_off, rec_start, info, scalars, scan_ws;
+    uint64_t n = 0;
+    uint32_t n_rec = 0;
+    InputScalarsHost sc{};
+    void release() {
+        text.release(), block_cnt.release(), block_off.release(), rec_start.release(), info.release(), scalars.release(),
+            scan_ws.release();
+    }
+};
+
+// upload + record index + per-record scan of one file; leaves f.n_rec, f.sc and the device buffers text / info
+int input_scan_file(InputFile &f, const uint8_t *text, uint64_t n, const alga_input_params &p, int which, const LaunchCfg &cfg,
+                    double *h2d_ms) {
+    const bool plain = p.file_type == ALGA_INPUT_PLAIN;
+    const uint32_t lpr = p.file_type == ALGA_INPUT_FASTQ ? 4u : 2u;
+    f.n = n;
+    const double t0 = now_ms();
+    const size_t padded = (size_t) ((n + 15) / 16) * 16 + 16;
+    CKR(f.text.ensure(padded));
+    if (n) CK(cudaMemcpy(f.text.p, text, (size_t) n, cudaMemcpyHostToDevice));
+    CK(cudaMemset((char *) f.text.p + n, 0x0A, padded - (size_t) n));  // the kernels never look past n; keep the pad defined
+    CK(cudaDeviceSynchronize());
+    *h2d_ms += now_ms() - t0;
+    const uint64_t nb = input_mark_blocks(n);
+    if (nb > 0x7FFFFFFFull) return fail(ALGA_E_INVALID, "input file %d is too large (%llu bytes)", which, (unsigned long long) n);
+    CKR(f.scalars.ensure(input_scalars_bytes()));
+    InputScalarsHost init{};
+    init.first_empty = init.first_bad = 0xFFFFFFFFu;
+    CK(cudaMemcpy(f.scalars.p, &init, sizeof(init), cudaMemcpyHostToDevice));
+    uint64_t n_marks = 0;
+    if (nb) {
+        CKR(f.block_cnt.ensure((size_t) nb * 4));
+        CKR(f.block_off.ensure(((size_t) nb + 1) * 8));
+        CKR(f.scan_ws.ensure(scan_workspace_bytes(nb)));
+        launch_count_marks(f.text.as<uint8_t>(), n, plain, f.block_cnt.as<uint32_t>(), 0, cfg);
+        launch_scan_u64(f.block_cnt.as<uint32_t>(), f.block_off.as<uint64_t>(), nb, f.scan_ws.p, 0, cfg);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(&n_marks, f.block_off.as<uint64_t>() + nb, 8, cudaMemcpyDeviceToHost));
+    }
+    const uint64_t n_cand = plain ? n_marks : (n_marks + lpr - 1) / lpr;
+    if (n_cand > 0x1FFFFFFFull) return fail(ALGA_E_INVALID, "input file %d holds too many records (%llu)", which, (unsigned long long) n_cand);
+    f.n_rec = 0;
+    f.sc = init;
+    if (!n_cand) return ALGA_OK;
+    CKR(f.rec_start.ensure((size_t) n_cand * 8));
+    CKR(f.info.ensure((size_t) n_cand * input_rec_info_bytes()));
+    launch_write_marks(f.text.as<uint8_t>(), n, plain, f.block_off.as<uint64_t>(), lpr, f.rec_start.as<uint64_t>(), n_cand, 0, cfg);
+    launch_scan_records(f.text.as<uint8_t>(), n, plain, f.rec_start.as<uint64_t>(), (uint32_t) n_cand, p.trim_left, p.trim_right,
+                        p.rna != 0, p.str_threshold > 0 ? p.str_threshold : 20, f.info.p, f.scalars.p, 0, cfg);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(&f.sc, f.scalars.p, sizeof(f.sc), cudaMemcpyDeviceToHost));
+    f.n_rec = f.sc.first_empty < n_cand ? f.sc.first_empty : (uint32_t) n_cand;
+    if (f.sc.first_bad < f.n_rec)
+        return fail(ALGA_E_INVALID, "record %u of input file %d holds a character other than A, C, G, T, N, U", f.sc.first_bad, which);
+    launch_record_totals(f.info.p, f.n_rec, f.scalars.p, 0, cfg);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(&f.sc, f.scalars.p, sizeof(f.sc), cudaMemcpyDeviceToHost));
+    return ALGA_OK;
+}
+
+void clear_read_set(alga_read_set *rs) { memset(rs, 0, sizeof(*rs)); }
+
+}  // namespace
+
+void alga_gpu_free_read_set(alga_read_set *rs) {
+    if (!rs) return;
+    free(rs->words);
+    free(rs->len_nt);
+    free(rs->old_id);
+    free(rs->paired_offset);
+    clear_read_set(rs);
+}
+
+int alga_gpu_read_input(const uint8_t *text1, uint64_t n1, const uint8_t *text2, uint64_t n2, const alga_input_params *params,
+                        alga_read_set *out, alga_timing *timing) {
+    if (!params || !out || (n1 && !text1) || (n2 && !text2)) return fail(ALGA_E_INVALID, "null argument");
+    if (params->file_type < ALGA_INPUT_PLAIN || params->file_type > ALGA_INPUT_FASTQ)
+        return fail(ALGA_E_INVALID, "file_type must be ALGA_INPUT_PLAIN, _FASTA or _FASTQ");
+    if (params->trim_left < 0 || params->trim_right < 0) return fail(ALGA_E_INVALID, "trim_left / trim_right must not be negative");
+    clear_read_set(out);
+    const double t0 = now_ms();
+    LaunchCfg cfg;
+    uint64_t launches = 0;
+    cfg.launches = &launches;
+    CKR(pick_device(params->device, &cfg));
+    const bool paired = text2 != nullptr;
+    InputFile f[2];
+    DevBuf words, len;
+    double h2d_ms = 0, d2h_ms = 0;
+    int r = [&]() -> int {
+        CKR(input_scan_file(f[0], text1, n1, *params, 1, cfg, &h2d_ms));
+        if (paired) {
+            CKR(input_scan_file(f[1], text2, n2, *params, 2, cfg, &h2d_ms));
+            if (f[0].n_rec != f[1].n_rec)
+                return fail(ALGA_E_INVALID, "the mate files hold different numbers of records (%u and %u)", f[0].n_rec, f[1].n_rec);
+        }
+        const uint64_t n_reads = (uint64_t) f[0].n_rec * (paired ? 4 : 2);
+        if (n_reads > 0x7FFFFFFFull) return fail(ALGA_E_INVALID, "too many reads (%llu): ids are 31-bit", (unsigned long long) n_reads);
+        uint32_t max_len = f[0].sc.max_len;
+        if (paired && f[1].sc.max_len > max_len) max_len = f[1].sc.max_len;
+        const uint32_t stride = max_len ? (max_len + 15) / 16 : 1;
+        out->n_reads = (uint32_t) n_reads;
+        out->stride_words = stride;
+        out->max_len_nt = max_len;
+        out->n_records[0] = f[0].n_rec;
+        out->n_records[1] = paired ? f[1].n_rec : 0;
+        out->n_with_n = f[0].sc.n_with_n + (paired ? f[1].sc.n_with_n : 0);
+        out->n_str = f[0].sc.n_str + (paired ? f[1].sc.n_str : 0);
+        const size_t wb = (size_t) n_reads * stride * 4;
+        out->words = (uint32_t *) malloc(wb ? wb : 4);
+        out->len_nt = (uint32_t *) malloc(n_reads ? n_reads * 4 : 4);
+        if (!out->words || !out->len_nt) return fail(ALGA_E_NOMEM, "host allocation of the read set failed");
+        if (!n_reads) return ALGA_OK;
+        CKR(words.ensure(wb));
+        CKR(len.ensure((size_t) n_reads * 4));
+        for (int k = 0; k < (paired ? 2 : 1); k++)
+            launch_pack_records(f[k].text.as<uint8_t>(), f[k].info.p, f[k].n_rec, params->rna != 0, paired ? 4u : 2u, 2u * k, stride,
+                                words.as<uint32_t>(), len.as<uint32_t>(), 0, cfg);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        const double t1 = now_ms();
+        CK(cudaMemcpy(out->words, words.p, wb, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(out->len_nt, len.p, (size_t) n_reads * 4, cudaMemcpyDeviceToHost));
+        d2h_ms = now_ms() - t1;
+        return ALGA_OK;
+    }();
+    f[0].release();
+    f[1].release();
+    words.release();
+    len.release();
+    if (r != ALGA_OK) {
+        alga_gpu_free_read_set(out);
+        return r;
+    }
+    if (timing) {
+        memset(timing, 0, sizeof(*timing));
+        timing->h2d_ms = h2d_ms;
+        timing->d2h_ms = d2h_ms;
+        timing->total_ms = now_ms() - t0;
+        timing->device_ms = timing->total_ms - h2d_ms - d2h_ms;  // kernels + their scalar read-backs and allocations
+        timing->kernel_launches = launches;
+    }
+    return ALGA_OK;
+}
+
+int alga_gpu_remap_reads(const alga_reads *reads, const uint8_t *remove_mask, int32_t device, alga_read_set *out,
+                         alga_timing *timing) {
+    if (!reads || !out) return fail(ALGA_E_INVALID, "null argument");
+    if (reads->n_reads & 1u) return fail(ALGA_E_INVALID, "n_reads must be even (both strands of every record)");
+    clear_read_set(out);
+    const double t0 = now_ms();
+    LaunchCfg cfg;
+    uint64_t launches = 0;
+    cfg.launches = &launches;
+    CKR(pick_device(device, &cfg));
+    TmpReads t;
+    CKR(t.upload(reads));
+    const uint32_t n = reads->n_reads, n_units = n / 2;
+    DevBuf mask, flag, pos, scalars, scan_ws, words, len, old_id, po;
+    double h2d_ms = 0, d2h_ms = 0;
+    int r = [&]() -> int {
+        if (remove_mask && n) {
+            CKR(mask.ensure(n));
+            CK(cudaMemcpy(mask.p, remove_mask, n, cudaMemcpyHostToDevice));
+        }
+        h2d_ms = now_ms() - t0;
+        out->words = (uint32_t *) malloc(4);
+        out->len_nt = (uint32_t *) malloc(4);
+        out->old_id = (uint32_t *) malloc(4);
+        out->paired_offset = (uint8_t *) malloc(4);
+        out->stride_words = 1;
+        if (!out->words || !out->len_nt || !out->old_id || !out->paired_offset) return fail(ALGA_E_NOMEM, "host allocation failed");
+        if (!n_units) return ALGA_OK;
+        CKR(flag.ensure((size_t) n_units * 4));
+        CKR(pos.ensure(((size_t) n_units + 1) * 4));
+        CKR(scalars.ensure(8));
+        CKR(scan_ws.ensure(scan_workspace_bytes(n_units)));
+        CK(cudaMemsetAsync(scalars.p, 0, 8, 0));
+        launch_remap_flags(t.R, remove_mask ? mask.as<uint8_t>() : nullptr, n_units, flag.as<uint32_t>(), scalars.p, 0, cfg);
+        launch_scan_u32(flag.as<uint32_t>(), pos.as<uint32_t>(), n_units, scan_ws.p, 0, cfg);
+        CK(cudaGetLastError());
+        uint32_t sc[2] = {0, 0}, units_out = 0;
+        CK(cudaMemcpy(sc, scalars.p, 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&units_out, pos.as<uint32_t>() + n_units, 4, cudaMemcpyDeviceToHost));
+        if (sc[1]) return fail(ALGA_E_INVALID, "read %u is present without its reverse complement (main.cpp:173 asserts)", sc[1] - 1);
+        const uint32_t n_out = 2 * units_out, stride = sc[0] ? (sc[0] + 15) / 16 : 1;
+        out->n_reads = n_out;
+        out->stride_words = stride;
+        out->max_len_nt = sc[0];
+        if (!n_out) return ALGA_OK;
+        const size_t wb = (size_t) n_out * stride * 4;
+        free(out->words), free(out->len_nt), free(out->old_id), free(out->paired_offset);
+        out->words = (uint32_t *) malloc(wb);
+        out->len_nt = (uint32_t *) malloc((size_t) n_out * 4);
+        out->old_id = (uint32_t *) malloc((size_t) n_out * 4);
+        out->paired_offset = (uint8_t *) malloc(n_out);
+        if (!out->words || !out->len_nt || !out->old_id || !out->paired_offset) return fail(ALGA_E_NOMEM, "host allocation failed");
+        CKR(words.ensure(wb));
+        CKR(len.ensure((size_t) n_out * 4));
+        CKR(old_id.ensure((size_t) n_out * 4));
+        CKR(po.ensure(n_out));
+        launch_remap_scatter(t.R, n_units, flag.as<uint32_t>(), pos.as<uint32_t>(), stride, words.as<uint32_t>(), len.as<uint32_t>(),
+                             old_id.as<uint32_t>(), po.as<uint8_t>(), 0, cfg);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        const double t1 = now_ms();
+        CK(cudaMemcpy(out->words, words.p, wb, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(out->len_nt, len.p, (size_t) n_out * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(out->old_id, old_id.p, (size_t) n_out * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(out->paired_offset, po.p, n_out, cudaMemcpyDeviceToHost));
+        d2h_ms = now_ms() - t1;
+        return ALGA_OK;
+    }();
+    for (DevBuf *b : {&mask, &flag, &pos, &scalars, &scan_ws, &words, &len, &old_id, &po}) b->release();
+    if (r != ALGA_OK) {
+        alga_gpu_free_read_set(out);
+        return r;
+    }
+    if (timing) {
+        memset(timing, 0, sizeof(*timing));
+        timing->h2d_ms = h2d_ms;
+        timing->d2h_ms = d2h_ms;
+        timing->total_ms = now_ms() - t0;
+        timing->device_ms = timing->total_ms - h2d_ms - d2h_ms;
+        timing->kernel_launches = launches;
+    }
+    return ALGA_OK;
+}

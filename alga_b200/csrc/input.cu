@@ -1,0 +1,414 @@
+// InputReader::readInput on the GPU (reference: src/IO/InputReader.cpp:44-139, 142-180, 272-391) and the renumbering of
+// the surviving reads (main.cpp:150-232): the two steps that turn the input files into the read set the graph creators
+// see.  SURVEY.md 8-f rank 2.
+//
+// The file text is copied to HBM as it is.  Records are found without any sequential pass:
+//   marks      every thread looks at 16 bytes and counts line ends ('\n'; plain input: token starts), a scan over the
+//              per-block counts gives every mark its global number k, and mark k with k % lines_per_record == 0 is the
+//              line end in front of the sequence line of record k / lines_per_record (readOneRead1, :142-180);
+//   scan       one warp per record: end of the line, the space stripping and end trimming of readParallelJob (:286-303),
+//              the character check (:316-334), N detection (:341-347) and the minimal-period filter (:343-353) as
+//              "is there a period p <= 20", 32 positions per step;  reading stops at the first record whose sequence line
+//              is empty (:284), so the smallest such record number is kept with atomicMin;
+//   pack       one warp per record, one 16-nucleotide word per lane: forward strand and reverse complement
+//              (Read::createSequence, Read.cpp:40-68; getComplimentaryString, InputReader.cpp:23-33) written straight
+//              to their final ids -- reverse complement at the even id, mates of the two files interleaved (:54-85).
+// All results are defined by the reference's --threads=1 order (with several threads a malformed file is read
+// differently, see oracle/input_oracle.c).
+#include <cstdio>
+
+#include "../../include/alga_gpu.h"
+#include "launch.h"
+
+namespace alga {
+
+namespace {
+
+constexpr int kMarkThreads = 256;
+constexpr int kMarkChunk = kMarkThreads * 16;  // bytes of text per block
+
+__device__ __forceinline__ bool is_space_c(uint32_t c) { return c == 32u || (c - 9u) <= 4u; }  // isspace in the C locale
+
+// marks of the 16 bytes at `base` (bit j = byte base + j): line ends, or (plain input, `str >> s`) token starts
+template <bool PLAIN>
+__device__ __forceinline__ uint32_t marks16(const uint8_t *__restrict__ text, uint64_t n, uint64_t base) {
+    if (base >= n) return 0;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + base));  // the buffer is padded to a multiple of 16
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t m = 0;
+    bool prev_space = true;
+    if (PLAIN && base > 0) prev_space = is_space_c(__ldg(text + base - 1));
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint32_t c = (w[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+        if (base + j < n) {
+            if (PLAIN) {
+                const bool sp = is_space_c(c);
+                if (!sp && prev_space) m |= 1u << j;
+                prev_space = sp;
+            } else if (c == '\n') {
+                m |= 1u << j;
+            }
+        }
+    }
+    return m;
+}
+
+// exclusive prefix of `v` over the block (kMarkThreads threads); *total = block sum
+__device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t *total) {
+    __shared__ uint32_t warp_sum[kMarkThreads / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_sum[wid] = inc;
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (int i = 0; i < kMarkThreads / 32; i++) {
+        const uint32_t s = warp_sum[i];
+        if (i < wid) before += s;
+        all += s;
+    }
+    *total = all;
+    return before + inc - v;
+}
+
+template <bool PLAIN>
+__global__ void __launch_bounds__(kMarkThreads) count_marks_kernel(const uint8_t *__restrict__ text, uint64_t n,
+                                                                   uint32_t *__restrict__ block_cnt) {
+    const uint64_t base = (uint64_t) blockIdx.x * kMarkChunk + (uint64_t) threadIdx.x * 16u;
+    const uint32_t c = (uint32_t) __popc(marks16<PLAIN>(text, n, base));
+    uint32_t total;
+    block_exclusive(c, &total);
+    if (threadIdx.x == 0) block_cnt[blockIdx.x] = total;
+}
+
+// rec_start[r] = first byte of the sequence of record r
+template <bool PLAIN>
+__global__ void __launch_bounds__(kMarkThreads) write_marks_kernel(const uint8_t *__restrict__ text, uint64_t n,
+                                                                   const uint64_t *__restrict__ block_off, uint32_t lpr,
+                                                                   uint64_t *__restrict__ rec_start, uint64_t n_rec) {
+    const uint64_t base = (uint64_t) blockIdx.x * kMarkChunk + (uint64_t) threadIdx.x * 16u;
+    uint32_t m = marks16<PLAIN>(text, n, base);
+    uint32_t total;
+    uint64_t k = block_off[blockIdx.x] + block_exclusive((uint32_t) __popc(m), &total);
+    while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        if (PLAIN) {
+            if (k < n_rec) rec_start[k] = base + j;
+        } else if (k % lpr == 0) {
+            const uint64_t r = k / lpr;
+            if (r < n_rec) rec_start[r] = base + j + 1;
+        }
+        k++;
+    }
+}
+
+struct __align__(16) RecInfo {
+    uint64_t begin;   // first byte of the trimmed sequence
+    uint32_t len;     // its length
+    uint32_t status;  // kRec* bits, 0 = a read
+};
+constexpr uint32_t kRecHasN = 1u, kRecStr = 2u, kRecEmpty = 4u, kRecBad = 8u;
+
+struct InputScalars {
+    uint32_t first_empty;  // smallest record number whose sequence line is empty (reading stops there)
+    uint32_t first_bad;    // smallest record number with a character other than A C G T N U
+    uint32_t max_len;
+    uint32_t pad;
+    unsigned long long n_with_n, n_str;
+};
+
+// first position in [from, to) whose byte satisfies pred, or `to`; all 32 lanes call it with the same arguments
+template <class P>
+__device__ __forceinline__ uint64_t warp_find(const uint8_t *__restrict__ text, uint64_t from, uint64_t to, int lane, P pred) {
+    for (uint64_t p = from; p < to; p += 32) {
+        const uint64_t q = p + lane;
+        const bool hit = q < to && pred((uint32_t) __ldg(text + q));
+        const unsigned m = __ballot_sync(kFull, hit);
+        if (m) return p + (uint64_t) (__ffs(m) - 1);
+    }
+    return to;
+}
+
+__device__ __forceinline__ uint32_t sym_of(uint32_t c, int rna) { return (rna && c == 'U') ? (uint32_t) 'T' : c; }
+
+template <bool PLAIN>
+__global__ void __launch_bounds__(256) scan_records_kernel(const uint8_t *__restrict__ text, uint64_t n,
+                                                           const uint64_t *__restrict__ rec_start, uint32_t n_cand,
+                                                           int trim_left, int trim_right, int rna, int str_threshold,
+                                                           RecInfo *__restrict__ info, InputScalars *__restrict__ sc) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = warp0; r < n_cand; r += n_warps) {
+        const uint64_t start = rec_start[r];
+        RecInfo out;
+        out.begin = start, out.len = 0, out.status = kRecEmpty;
+        // the sequence line / token (readOneRead1)
+        uint64_t end = PLAIN ? warp_find(text, start, n, lane, [](uint32_t c) { return is_space_c(c); })
+                             : warp_find(text, start, n, lane, [](uint32_t c) { return c == '\n'; });
+        if (end == start) {  // s == "": the reader stops here (InputReader.cpp:284)
+            if (lane == 0) {
+                atomicMin(&sc->first_empty, r);
+                info[r] = out;
+            }
+            continue;
+        }
+        // :286-291 -- leading spaces off, cut at the next space
+        uint64_t b = start, e = end;
+        if (!PLAIN) {
+            b = warp_find(text, start, end, lane, [](uint32_t c) { return c != ' '; });
+            e = warp_find(text, b, end, lane, [](uint32_t c) { return c == ' '; });
+        }
+        // :298-303 -- end trimming unless the read is short
+        if (e - b >= (uint64_t) (trim_left + trim_right + 10)) {
+            b += (uint64_t) trim_left;
+            e -= (uint64_t) trim_right;
+        }
+        const uint64_t len64 = e - b;
+        // :316-334 -- characters
+        bool bad = false, has_n = false;
+        for (uint64_t i = lane; i < len64; i += 32) {
+            const uint32_t c = __ldg(text + b + i);
+            if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'N' && c != 'U') bad = true;
+            if (c == 'N') has_n = true;
+        }
+        bad = __any_sync(kFull, bad) || len64 > 0x7FFFFFFFull;
+        has_n = __any_sync(kFull, has_n);
+        uint32_t status = 0;
+        if (bad) {
+            status = kRecBad;
+            if (lane == 0) atomicMin(&sc->first_bad, r);
+        } else if (has_n) {
+            status = kRecHasN;
+        } else if (len64 == 0) {
+            status = kRecStr;  // an all-space line: MinPeriod("") is undefined in the reference; dropped
+        } else {
+            // :343-353 -- MinPeriod(s) <= threshold  <=>  some p <= min(threshold, len) has s[i] == s[i + p] for all i
+            const uint32_t len = (uint32_t) len64;
+            const uint32_t pmax = (uint32_t) str_threshold < len ? (uint32_t) str_threshold : len;
+            for (uint32_t p = 1; p <= pmax && !status; p++) {
+                bool periodic = true;
+                for (uint32_t i0 = 0; i0 + p < len; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    bool ok = true;
+                    if (i + p < len) ok = sym_of(__ldg(text + b + i), rna) == sym_of(__ldg(text + b + i + p), rna);
+                    if (!__all_sync(kFull, ok)) {
+                        periodic = false;
+                        break;
+                    }
+                }
+                if (periodic) status = kRecStr;
+            }
+        }
+        if (lane == 0) {
+            out.begin = b, out.len = (uint32_t) len64, out.status = status;
+            info[r] = out;
+        }
+    }
+}
+
+// totals over the records that are actually read (r < n_rec)
+__global__ void record_totals_kernel(const RecInfo *__restrict__ info, uint32_t n_rec, InputScalars *__restrict__ sc) {
+    uint32_t mx = 0, cn = 0, cs = 0;
+    for (uint64_t r = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; r < n_rec; r += (uint64_t) gridDim.x * blockDim.x) {
+        const RecInfo x = info[r];
+        if (x.status == 0) mx = x.len > mx ? x.len : mx;
+        cn += (x.status & kRecHasN) ? 1u : 0u;
+        cs += (x.status & kRecStr) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        const uint32_t o = __shfl_xor_sync(kFull, mx, d);
+        mx = o > mx ? o : mx;
+        cn += __shfl_xor_sync(kFull, cn, d);
+        cs += __shfl_xor_sync(kFull, cs, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (mx) atomicMax(&sc->max_len, mx);
+        if (cn) atomicAdd(&sc->n_with_n, (unsigned long long) cn);
+        if (cs) atomicAdd(&sc->n_str, (unsigned long long) cs);
+    }
+}
+
+// Read::createSequence codes; the reverse strand goes through getComplimentaryString first (a U stays a U there, and
+// packs as 0 like every other non-ACGT character)
+__device__ __forceinline__ uint32_t code_fw(uint32_t c, int rna) {
+    return c == 'C' ? 1u : (c == 'G' ? 2u : ((c == 'T' || (rna && c == 'U')) ? 3u : 0u));
+}
+__device__ __forceinline__ uint32_t code_rc(uint32_t c, int rna) {
+    return c == 'A' ? 3u : (c == 'C' ? 2u : (c == 'G' ? 1u : 0u));
+}
+
+// record r of file `file` -> ids (id0, id0 + 1) = (reverse complement, forward), id0 = r * id_step + 2 * file
+__global__ void __launch_bounds__(256) pack_records_kernel(const uint8_t *__restrict__ text, const RecInfo *__restrict__ info,
+                                                           uint32_t n_rec, int rna, uint32_t id_step, uint32_t id_first,
+                                                           uint32_t stride, uint32_t *__restrict__ words,
+                                                           uint32_t *__restrict__ len_out) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = warp0; r < n_rec; r += n_warps) {
+        const RecInfo x = info[r];
+        const uint64_t id_rc = (uint64_t) r * id_step + id_first, id_fw = id_rc + 1;
+        const uint32_t len = x.status ? 0u : x.len;
+        if (lane == 0) {
+            len_out[id_rc] = len;
+            len_out[id_fw] = len;
+        }
+        const uint8_t *s = text + x.begin;
+        for (uint32_t w = lane; w < stride; w += 32) {
+            uint32_t fw = 0, rc = 0;
+            const uint32_t i0 = w * 16u;
+            if (i0 < len) {
+#pragma unroll
+                for (uint32_t j = 0; j < 16; j++) {
+                    const uint32_t i = i0 + j;
+                    if (i < len) {
+                        fw |= code_fw(__ldg(s + i), rna) << (2u * j);
+                        rc |= code_rc(__ldg(s + (len - 1u - i)), rna) << (2u * j);
+                    }
+                }
+            }
+            words[id_fw * stride + w] = fw;
+            words[id_rc * stride + w] = rc;
+        }
+    }
+}
+
+// ---- renumbering (main.cpp:150-232) ---------------------------------------------------------------------------
+// A unit = the two strands (2u, 2u + 1) of one record.  Unit u survives iff READS[2u] != nullptr (:168); a surviving
+// unit whose second read is gone is the reference's assert (:173) and reported through *err.
+struct RemapScalars {
+    uint32_t max_len;
+    uint32_t err;  // 1 + id of a read that survives without its reverse complement
+};
+
+__device__ __forceinline__ bool alive(const ReadsDev &R, const uint8_t *__restrict__ mask, uint64_t i) {
+    return R.len[i] != 0 && !(mask && mask[i]);
+}
+
+__global__ void remap_flags_kernel(ReadsDev R, const uint8_t *__restrict__ mask, uint32_t n_units, uint32_t *__restrict__ flag,
+                                   RemapScalars *__restrict__ sc) {
+    uint32_t mx = 0;
+    for (uint64_t u = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; u < n_units; u += (uint64_t) gridDim.x * blockDim.x) {
+        const bool a = alive(R, mask, 2 * u);
+        flag[u] = a ? 1u : 0u;
+        if (a) {
+            if (!alive(R, mask, 2 * u + 1)) atomicMax(&sc->err, (uint32_t) (2 * u) + 1u);
+            const uint32_t l0 = R.len[2 * u], l1 = R.len[2 * u + 1];
+            mx = max(mx, max(l0, l1));
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) mx = max(mx, __shfl_xor_sync(kFull, mx, d));
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(&sc->max_len, mx);
+}
+
+__global__ void remap_scatter_kernel(ReadsDev R, uint32_t n_units, const uint32_t *__restrict__ flag,
+                                     const uint32_t *__restrict__ pos, uint32_t stride, uint32_t *__restrict__ words,
+                                     uint32_t *__restrict__ len_out, uint32_t *__restrict__ old_id,
+                                     uint8_t *__restrict__ paired_offset) {
+    const uint64_t per_unit = 2ull * stride, total = (uint64_t) n_units * per_unit;
+    for (uint64_t idx = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; idx < total; idx += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t u = (uint32_t) (idx / per_unit);
+        if (!flag[u]) continue;
+        const uint32_t rem = (uint32_t) (idx - (uint64_t) u * per_unit), k = rem / stride, w = rem - k * stride;
+        const uint32_t src = 2u * u + k;
+        const uint64_t dst = 2ull * pos[u] + k;
+        const uint32_t len = R.len[src];
+        words[dst * stride + w] = w < (len + 15u) / 16u ? read_ptr(R, src)[w] : 0u;
+        if (w == 0) {
+            len_out[dst] = len;
+            old_id[dst] = src;
+            // Global::pairedReadOffset (:176-197): 1 / 2 for the first / second mate when both survive, else 0
+            uint8_t po = 0;
+            if ((u & 1u) == 0) po = (u + 1 < n_units && flag[u + 1]) ? 1 : 0;
+            else po = flag[u - 1] ? 2 : 0;
+            paired_offset[dst] = po;
+        }
+    }
+}
+
+inline int grid_for(uint64_t n_items, int per_block, const LaunchCfg &cfg, int max_blocks_per_sm = 8) {
+    uint64_t need = (n_items + per_block - 1) / per_block;
+    const uint64_t cap = (uint64_t) cfg.sm_count * max_blocks_per_sm;
+    if (need < 1) need = 1;
+    return (int) (need < cap ? need : cap);
+}
+
+}  // namespace
+
+uint64_t input_mark_blocks(uint64_t n_bytes) { return (n_bytes + kMarkChunk - 1) / kMarkChunk; }
+size_t input_rec_info_bytes() { return sizeof(RecInfo); }
+size_t input_scalars_bytes() { return sizeof(InputScalars); }
+
+// block_cnt[input_mark_blocks(n)] = marks per 4 KiB block of text (text padded to a multiple of 16 bytes)
+void launch_count_marks(const uint8_t *text, uint64_t n, bool plain, uint32_t *block_cnt, cudaStream_t s, const LaunchCfg &cfg) {
+    const uint64_t nb = input_mark_blocks(n);
+    if (!nb) return;
+    if (plain) count_marks_kernel<true><<<(unsigned) nb, kMarkThreads, 0, s>>>(text, n, block_cnt);
+    else count_marks_kernel<false><<<(unsigned) nb, kMarkThreads, 0, s>>>(text, n, block_cnt);
+    if (cfg.launches) *cfg.launches += 1;
+}
+
+void launch_write_marks(const uint8_t *text, uint64_t n, bool plain, const uint64_t *block_off, uint32_t lines_per_record,
+                        uint64_t *rec_start, uint64_t n_cand, cudaStream_t s, const LaunchCfg &cfg) {
+    const uint64_t nb = input_mark_blocks(n);
+    if (!nb) return;
+    if (plain) write_marks_kernel<true><<<(unsigned) nb, kMarkThreads, 0, s>>>(text, n, block_off, 1, rec_start, n_cand);
+    else write_marks_kernel<false><<<(unsigned) nb, kMarkThreads, 0, s>>>(text, n, block_off, lines_per_record, rec_start, n_cand);
+    if (cfg.launches) *cfg.launches += 1;
+}
+
+// sc must hold {0xFFFFFFFF, 0xFFFFFFFF, 0, 0, 0, 0} before the call
+void launch_scan_records(const uint8_t *text, uint64_t n, bool plain, const uint64_t *rec_start, uint32_t n_cand, int trim_left,
+                         int trim_right, int rna, int str_threshold, void *info, void *scalars, cudaStream_t s,
+                         const LaunchCfg &cfg) {
+    if (!n_cand) return;
+    const int grid = grid_for((uint64_t) n_cand * 32, 256, cfg);
+    if (plain)
+        scan_records_kernel<true><<<grid, 256, 0, s>>>(text, n, rec_start, n_cand, trim_left, trim_right, rna, str_threshold,
+                                                        (RecInfo *) info, (InputScalars *) scalars);
+    else
+        scan_records_kernel<false><<<grid, 256, 0, s>>>(text, n, rec_start, n_cand, trim_left, trim_right, rna, str_threshold,
+                                                         (RecInfo *) info, (InputScalars *) scalars);
+    if (cfg.launches) *cfg.launches += 1;
+}
+
+void launch_record_totals(const void *info, uint32_t n_rec, void *scalars, cudaStream_t s, const LaunchCfg &cfg) {
+    if (!n_rec) return;
+    record_totals_kernel<<<grid_for(n_rec, 256, cfg), 256, 0, s>>>((const RecInfo *) info, n_rec, (InputScalars *) scalars);
+    if (cfg.launches) *cfg.launches += 1;
+}
+
+void launch_pack_records(const uint8_t *text, const void *info, uint32_t n_rec, int rna, uint32_t id_step, uint32_t id_first,
+                         uint32_t stride, uint32_t *words, uint32_t *len_out, cudaStream_t s, const LaunchCfg &cfg) {
+    if (!n_rec) return;
+    pack_records_kernel<<<grid_for((uint64_t) n_rec * 32, 256, cfg), 256, 0, s>>>(text, (const RecInfo *) info, n_rec, rna, id_step,
+                                                                                 id_first, stride, words, len_out);
+    if (cfg.launches) *cfg.launches += 1;
+}
+
+// scalars: {max_len, err} zeroed before the call
+void launch_remap_flags(const ReadsDev &R, const uint8_t *mask, uint32_t n_units, uint32_t *flag, void *scalars, cudaStream_t s,
+                        const LaunchCfg &cfg) {
+    if (!n_units) return;
+    remap_flags_kernel<<<grid_for(n_units, 256, cfg), 256, 0, s>>>(R, mask, n_units, flag, (RemapScalars *) scalars);
+    if (cfg.launches) *cfg.launches += 1;
+}
+
+void launch_remap_scatter(const ReadsDev &R, uint32_t n_units, const uint32_t *flag, const uint32_t *pos, uint32_t stride,
+                          uint32_t *words, uint32_t *len_out, uint32_t *old_id, uint8_t *paired_offset, cudaStream_t s,
+                          const LaunchCfg &cfg) {
+    if (!n_units) return;
+    remap_scatter_kernel<<<grid_for((uint64_t) n_units * 2 * stride, 256, cfg, 16), 256, 0, s>>>(R, n_units, flag, pos, stride, words,
+                                                                                                len_out, old_id, paired_offset);
+    if (cfg.launches) *cfg.launches += 1;
+}
+
+}  // namespace alga

@@ -141,6 +141,29 @@ void launch_prefix_reads(const ReadsDev &R, const SeedTable &t, int remove_type,
                          uint8_t *mask, cudaStream_t s, const LaunchCfg &cfg);
 size_t prefix_reads_lenmap_words();
 
+// --- InputReader::readInput and the renumbering of main.cpp:150-232 (input.cu) -------------------------------------
+// text: the file as it is, in a buffer padded to a multiple of 16 bytes.  Marks = line ends (plain input: token starts);
+// mark k with k % lines_per_record == 0 precedes the sequence line of record k / lines_per_record.
+uint64_t input_mark_blocks(uint64_t n_bytes);
+size_t input_rec_info_bytes();
+size_t input_scalars_bytes();
+void launch_count_marks(const uint8_t *text, uint64_t n, bool plain, uint32_t *block_cnt, cudaStream_t s, const LaunchCfg &cfg);
+void launch_write_marks(const uint8_t *text, uint64_t n, bool plain, const uint64_t *block_off, uint32_t lines_per_record,
+                        uint64_t *rec_start, uint64_t n_cand, cudaStream_t s, const LaunchCfg &cfg);
+// scalars (input_scalars_bytes()): u32 first_empty = first_bad = 0xFFFFFFFF, u32 max_len = 0, u32 pad, u64 n_with_n = n_str = 0
+void launch_scan_records(const uint8_t *text, uint64_t n, bool plain, const uint64_t *rec_start, uint32_t n_cand, int trim_left,
+                         int trim_right, int rna, int str_threshold, void *info, void *scalars, cudaStream_t s,
+                         const LaunchCfg &cfg);
+void launch_record_totals(const void *info, uint32_t n_rec, void *scalars, cudaStream_t s, const LaunchCfg &cfg);
+void launch_pack_records(const uint8_t *text, const void *info, uint32_t n_rec, int rna, uint32_t id_step, uint32_t id_first,
+                         uint32_t stride, uint32_t *words, uint32_t *len_out, cudaStream_t s, const LaunchCfg &cfg);
+// scalars: u32 max_len = 0, u32 err = 0 (1 + id of a read that survives without its reverse complement)
+void launch_remap_flags(const ReadsDev &R, const uint8_t *mask, uint32_t n_units, uint32_t *flag, void *scalars, cudaStream_t s,
+                        const LaunchCfg &cfg);
+void launch_remap_scatter(const ReadsDev &R, uint32_t n_units, const uint32_t *flag, const uint32_t *pos, uint32_t stride,
+                          uint32_t *words, uint32_t *len_out, uint32_t *old_id, uint8_t *paired_offset, cudaStream_t s,
+                          const LaunchCfg &cfg);
+
 // --- error-rate supplement (supplement.cu) -------------------------------------------------------
 // LI k-mers (Read.cpp:145-226) of the reads d_ids[0 .. n_ids): `intervals` slots per read, ind = -1 where absent
 int run_li_kmers(const ReadsDev &R, const uint32_t *d_ids, uint32_t n_ids, const int32_t prio[4], int K, int intervals,

@@ -87,6 +87,20 @@ def sample_paired_end(genome: np.ndarray, read_len: int, coverage: float, rng, e
     return _substitute(m1s, error, rng), _substitute(m2s, error, rng)
 
 
+def fasta_text(m: np.ndarray) -> bytes:
+    """Two-line FASTA (the only FASTA layout the reference reads, InputReader.cpp:151-154) of an (n, len) code matrix."""
+    n, ln = m.shape
+    rec = np.empty((n, 1 + 8 + 1 + ln + 1), np.uint8)  # ">" + 8-digit id + "\n" + sequence + "\n"
+    rec[:, 0] = ord(">")
+    ids = np.arange(n, dtype=np.int64)
+    for d in range(8):
+        rec[:, 8 - d] = ord("0") + (ids // 10 ** d) % 10
+    rec[:, 9] = ord("\n")
+    rec[:, 10 : 10 + ln] = np.frombuffer(b"ACGT", np.uint8)[m]
+    rec[:, 10 + ln] = ord("\n")
+    return rec.tobytes()
+
+
 def strand_nodes(m1: np.ndarray, m2: np.ndarray | None = None) -> np.ndarray:
     """Trim 3+3 and lay records out as graph nodes in the reference's id order."""
     def trim(m):

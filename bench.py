@@ -434,6 +434,49 @@ def run_ours(args):
             preprocess["cpu_reference"] = {"reads": sub.n, "seconds_incl_io": time.perf_counter() - t0c, "cores": _cpu_threads(),
                                            "note": "oracle/_ref harness: ReadPreprocess::getPrefixReads on 1/8 of the reads, file IO included"}
 
+    input_leg = None
+    if world == 1 and args.with_input:
+        # the files of the workload through InputReader::readInput on the GPU (alga_gpu_read_input), and
+        # the whole driver path main.cpp:82-291 (reader, prefix-read removal, renumbering, GraphCreatorPrefSuf), host to host
+        from alga_b200.input_reader import FASTA, InputReader, build_overlap_graph
+
+        kwi = dict(synth.CONFIGS[args.workload])
+        kwi["genome_size"] = max(20_000, int(kwi["genome_size"] * args.scale))
+        rngi = np.random.default_rng(kwi["seed"])
+        gen = synth.make_genome(kwi["genome_size"], rngi, repeats=kwi.get("repeats", 0))
+        if kwi["paired"]:
+            m1, m2 = synth.sample_paired_end(gen, kwi["read_len"], kwi["coverage"], rngi, kwi.get("error", 0.0))
+            t1, t2 = synth.fasta_text(m1), synth.fasta_text(m2)
+        else:
+            m1 = synth.sample_single_end(gen, kwi["read_len"], kwi["coverage"], rngi, kwi.get("error", 0.0))
+            t1, t2 = synth.fasta_text(m1), None
+        rd = InputReader(FASTA, device=local)
+        rd.readInput(t1, t2)
+        ts = time.perf_counter()
+        rs_in = rd.readInput(t1, t2)
+        ms = 1e3 * (time.perf_counter() - ts)
+        n_rec = m1.shape[0] * (2 if t2 is not None else 1)
+        nbytes = len(t1) + (len(t2) if t2 is not None else 0)
+        input_leg = {"ms": ms, "records": n_rec, "reads": rs_in.n, "file_bytes": nbytes, **rd.timing, **rd.info,
+                     "records_per_s": n_rec / (ms / 1e3), "call": "alga_gpu_read_input (host buffers)"}
+        build_overlap_graph(t1, t2, FASTA, device=local)
+        ts = time.perf_counter()
+        og = build_overlap_graph(t1, t2, FASTA, device=local)
+        msg = 1e3 * (time.perf_counter() - ts)
+        input_leg["files_to_graph"] = {"ms": msg, "nodes": og.reads.n, "edges": og.graph.n_edges, "params": og.params,
+                                       "stages": {k: (v or {}).get("total_ms") for k, v in og.timing.items()},
+                                       "call": "alga_b200.input_reader.build_overlap_graph (main.cpp:82-291 through the C ABI)"}
+        from oracle import harness as _h
+        if _h.available() and not args.no_cpu:
+            k = max(1, m1.shape[0] // 8)
+            s1 = synth.fasta_text(m1[:k])
+            s2 = synth.fasta_text(m2[:k]) if t2 is not None else None
+            t0c = time.perf_counter()
+            _h.run_read_input(s1, s2, 1, threads=_cpu_threads())
+            input_leg["cpu_reference"] = {"records": k * (2 if t2 is not None else 1), "seconds_incl_io": time.perf_counter() - t0c,
+                                          "cores": _cpu_threads(),
+                                          "note": "oracle/_ref harness: InputReader::readInput on 1/8 of the records, file IO included"}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
@@ -446,6 +489,8 @@ def run_ours(args):
         line["supplement"] = supplement
     if preprocess:
         line["preprocess"] = preprocess
+    if input_leg:
+        line["input"] = input_leg
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -464,6 +509,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--with-preprocess", action="store_true",
                     help="also time ReadPreprocess::getPrefixReads (alga_gpu_prefix_reads) on the reads before dedupe")
+    ap.add_argument("--with-input", action="store_true",
+                    help="also time InputReader::readInput (alga_gpu_read_input) and the files-to-graph path on FASTA text of the workload")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = N chromosomes of the workload (default), strong = the one workload split N ways")
     args = ap.parse_args()

@@ -257,6 +257,55 @@ int alga_gpu_li_kmers(const alga_reads *reads, const uint32_t *ids, uint32_t n_i
 int alga_gpu_prefix_reads(const alga_reads *reads, int32_t remove_type, int32_t device, uint8_t *mask,
                           alga_timing *timing /* may be NULL */);
 
+/* ---- reading the input (the producer of the read set) -------------------------------------
+ * InputReader::readInput (src/IO/InputReader.cpp:44-139, called from main.cpp:82) on the contents of the input file(s):
+ * record splitting (readOneRead1, :142-180), space stripping and end trimming (:286-303), the character check (:316-334),
+ * removal of reads with an N (:341-347) and of reads whose minimal period is <= 20 (:343-353, MyUtils::MinPeriod), the
+ * reverse-complement twin (:362-377), 2-bit packing (Read::createSequence, Read.cpp:40-68) and the final order of
+ * Global::READS (:54-85): reverse complement at the even id, forward strand at the odd id, mates of the two files
+ * interleaved (file-1 record i -> ids 4i, 4i+1; file-2 record i -> 4i+2, 4i+3).  Results follow the reference's
+ * --threads=1 order.  Where the reference exits (a character other than A C G T N U) or indexes out of range (mate files
+ * with different record counts) the call fails with ALGA_E_INVALID. */
+#define ALGA_INPUT_PLAIN 0 /* Params::MY_INPUT: whitespace-separated sequences */
+#define ALGA_INPUT_FASTA 1 /* Params::FASTA, and PFASTA with paired reads: header line + sequence line */
+#define ALGA_INPUT_FASTQ 2 /* Params::FASTQ: four lines per record */
+typedef struct {
+    int32_t file_type;     /* ALGA_INPUT_*: Params::INPUT_FILE_TYPE (from the file extension, Params.cpp:332-335) */
+    int32_t trim_left;     /* Params::READ_END_TRIM_LEFT (3) */
+    int32_t trim_right;    /* Params::READ_END_TRIM_RIGHT (3) */
+    int32_t rna;           /* Params::RNA: U is read as T */
+    int32_t str_threshold; /* 20 (InputReader.cpp:343); <= 0 means 20 */
+    int32_t device;
+} alga_input_params;
+
+/* A read set produced by the library: fixed stride, read i = words[i * stride_words ...], len_nt[i] == 0 = nullptr.
+ * Host arrays, malloc'ed by the library; release with alga_gpu_free_read_set. */
+typedef struct {
+    uint32_t n_reads;
+    uint32_t stride_words;  /* ceil(max_len_nt / 16), at least 1 */
+    uint32_t max_len_nt;
+    uint32_t *words;        /* n_reads * stride_words */
+    uint32_t *len_nt;       /* n_reads */
+    uint32_t *old_id;       /* alga_gpu_remap_reads: id of read i before the renumbering; NULL otherwise */
+    uint8_t *paired_offset; /* alga_gpu_remap_reads: Global::pairedReadOffset[i] (main.cpp:176-197); NULL otherwise */
+    uint64_t n_records[2];  /* alga_gpu_read_input: records read from file 1 / file 2 */
+    uint64_t n_with_n;      /* ... records dropped because of an N ("Nreads", InputReader.cpp:346) */
+    uint64_t n_str;         /* ... records dropped as short-period repeats ("STRreads", InputReader.cpp:352) */
+} alga_read_set;
+
+/* text1 / text2: the bytes of --file1 / --file2 (text2 may be NULL: single-end).  timing (may be NULL): h2d_ms, device_ms,
+ * d2h_ms, total_ms, kernel_launches. */
+int alga_gpu_read_input(const uint8_t *text1, uint64_t n1, const uint8_t *text2, uint64_t n2,
+                        const alga_input_params *params, alga_read_set *out, alga_timing *timing);
+
+/* The compaction and renumbering of main.cpp:150-232 after Global::removeRead of the reads ReadPreprocess marked
+ * (main.cpp:133-140): strand pairs (2u, 2u+1) whose first read is present (len_nt != 0 and remove_mask == 0) keep their
+ * order and get consecutive ids; out->old_id and out->paired_offset are filled.  remove_mask may be NULL.  A read that
+ * survives without its reverse complement is the reference's assert (main.cpp:173): ALGA_E_INVALID. */
+int alga_gpu_remap_reads(const alga_reads *reads, const uint8_t *remove_mask, int32_t device, alga_read_set *out,
+                         alga_timing *timing);
+void alga_gpu_free_read_set(alga_read_set *rs);
+
 /* ---- misc ---------------------------------------------------------------------------------- */
 /* Page-locked host memory for callers that stage the packed reads themselves (the shim gathers the blocks of
  * vector<Read*> straight into such a buffer, so the upload runs at full host->device rate).  NULL on failure. */

@@ -118,3 +118,79 @@ def run_prefix_reads(reads, remove_type=2, threads=1) -> np.ndarray:
         subprocess.run([HARNESS, "prefixreads", rp, mp, str(remove_type), str(threads)], check=True,
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=d)
         return np.fromfile(mp, dtype=np.uint8)
+
+
+def read_reads(path):
+    """ALGR file -> ReadSet."""
+    from alga_b200.readset import ReadSet
+    with open(path, "rb") as f:
+        assert f.read(4) == b"ALGR"
+        n, *_ = struct.unpack("<I4i", f.read(20))
+        ln = np.frombuffer(f.read(4 * n), "<u4").copy()
+        af = np.frombuffer(f.read(n), "u1").copy()
+        at = np.frombuffer(f.read(n), "u1").copy()
+        off = np.frombuffer(f.read(8 * (n + 1)), "<u8").copy()
+        w = np.frombuffer(f.read(4 * int(off[n])), "<u4").copy()
+    return ReadSet(w, off, ln, align_from=af, align_to=at)
+
+
+_EXT = {0: "txt", 1: "fasta", 2: "fastq"}
+
+
+def run_read_input(text1: bytes, text2: bytes | None = None, file_type=1, threads=1, extra=()):
+    """Run the reference's InputReader::readInput on the given file contents; returns the ReadSet (nullptr = length 0)."""
+    if not available():
+        raise RuntimeError("oracle/_ref/alga_ref_harness is not built (make -C oracle ref)")
+    with tempfile.TemporaryDirectory() as d:
+        f1 = os.path.join(d, "x_1." + _EXT[file_type])
+        f2 = os.path.join(d, "x_2." + _EXT[file_type])
+        op = os.path.join(d, "out.algr")
+        open(f1, "wb").write(text1)
+        if text2 is not None:
+            open(f2, "wb").write(text2)
+        r = subprocess.run([HARNESS, "readinput", f1, f2 if text2 is not None else "-", op, str(threads), *extra],
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=d)
+        if r.returncode != 0:  # the reference exits on a bad character (InputReader.cpp:324-327) / asserts
+            raise RuntimeError(f"the reference's reader exited with status {r.returncode}")
+        return read_reads(op)
+
+
+STOCK = os.path.join(HERE, "_ref", "ALGA")
+
+
+def read_graph_file(path) -> np.ndarray:
+    """Graph::serializeGraph format (Graph.cpp:269-297) -> (n, (E, 3) int32 sorted edges)."""
+    raw = np.fromfile(path, dtype="<i4")
+    n = int(raw[0])
+    edges = []
+    p = 1
+    for _ in range(n):
+        v, deg = int(raw[p]), int(raw[p + 1])
+        p += 2
+        if deg:
+            e = raw[p : p + 2 * deg].reshape(-1, 2)
+            edges.append(np.column_stack([np.full(deg, v, np.int32), e]))
+            p += 2 * deg
+    e = np.concatenate(edges) if edges else np.zeros((0, 3), np.int32)
+    return n, sort_edges(e)
+
+
+def run_stock_graph(text1: bytes, text2: bytes | None = None, file_type=1, threads=1):
+    """The stock ALGA binary (main.cpp:57-293) with --serialize=1 on the given files: (n_nodes, edges) of the graph it
+    writes after GraphCreatorPrefSuf + retainOnlySmallestOffset, i.e. on the ids left by the reference's own reader,
+    duplicate removal and renumbering."""
+    if not os.path.isfile(STOCK):
+        raise RuntimeError("oracle/_ref/ALGA is not built (make -C oracle ref)")
+    with tempfile.TemporaryDirectory() as d:
+        f1 = "x_1." + _EXT[file_type]
+        args = [STOCK, "--file1=" + f1]
+        open(os.path.join(d, f1), "wb").write(text1)
+        if text2 is not None:
+            f2 = "x_2." + _EXT[file_type]
+            open(os.path.join(d, f2), "wb").write(text2)
+            args.append("--file2=" + f2)
+        args += [f"--threads={threads}", "--output=contigs.fasta", "--serialize=1"]
+        subprocess.run(args, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=d)
+        g = [x for x in os.listdir(d) if x.endswith("_beforeSimplifier.graph")]
+        assert len(g) == 1, g
+        return read_graph_file(os.path.join(d, g[0]))

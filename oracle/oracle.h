@@ -71,6 +71,28 @@ int32_t *oracle_supplement(const oracle_reads *r, const int32_t *edges_in, uint6
  * together with their reverse complements (id ^ 1).  remove_type 1 = duplicates only. */
 void oracle_prefix_reads(const oracle_reads *r, int32_t remove_type, uint8_t *mask);
 
+/* InputReader::readInput (InputReader.cpp:44-139, --threads=1 order) on one or two in-memory files: both strands of every
+ * record in the reference's id order (reverse complement at the even id, mates interleaved), removed reads (N, minimal
+ * period <= str_threshold) as length 0.  Outputs are malloc'ed (oracle_free).  See input_oracle.c. */
+#define ORACLE_INPUT_PLAIN 0 /* Params::MY_INPUT: whitespace-separated sequences */
+#define ORACLE_INPUT_FASTA 1 /* Params::FASTA (and PFASTA with paired reads): header line + sequence line */
+#define ORACLE_INPUT_FASTQ 2 /* Params::FASTQ: four lines per record */
+#define ORACLE_E_BADCHAR (-1) /* a character other than A C G T N U (the reference exits, InputReader.cpp:324-327) */
+#define ORACLE_E_PAIRING (-2) /* mate files with different record counts / a read without its reverse complement */
+typedef struct {
+    int32_t file_type;
+    int32_t trim_left, trim_right; /* Params::READ_END_TRIM_LEFT / RIGHT (3, 3) */
+    int32_t rna;                   /* Params::RNA: U -> T */
+    int32_t str_threshold;         /* 20, InputReader.cpp:343; <= 0 means 20 */
+} oracle_input_params;
+int oracle_read_input(const uint8_t *text1, uint64_t n1, const uint8_t *text2, uint64_t n2, const oracle_input_params *p,
+                      uint32_t *n_reads, uint32_t **len_nt, uint64_t **word_off, uint32_t **words, uint64_t *n_with_n,
+                      uint64_t *n_str);
+/* main.cpp:133-140 + 150-232: compaction of the surviving reads.  old_id[k] = previous id of new read k, paired_offset[k]
+ * = Global::pairedReadOffset[k]; both need room for n entries. */
+int oracle_remap(const uint32_t *len_nt, const uint8_t *mask, uint32_t n, uint32_t *old_id, uint8_t *paired_offset,
+                 uint32_t *n_out);
+
 void oracle_free(void *p);
 
 #ifdef __cplusplus

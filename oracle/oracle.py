@@ -26,8 +26,15 @@ class _SupParams(C.Structure):
                                           "kmer_length", "intervals", "kmer_length_bucket")]
 
 
+class _InputParams(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("file_type", "trim_left", "trim_right", "rna", "str_threshold")]
+
+
+INPUT_PLAIN, INPUT_FASTA, INPUT_FASTQ = 0, 1, 2
+
+
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(HERE, f) for f in ("prefsuf_oracle.c", "verify_oracle.c", "supplement_oracle.cpp", "preprocess_oracle.c", "oracle.h",
+    srcs = [os.path.join(HERE, f) for f in ("prefsuf_oracle.c", "verify_oracle.c", "supplement_oracle.cpp", "preprocess_oracle.c", "input_oracle.c", "oracle.h",
                                             "Makefile")]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         subprocess.run(["make", "-C", HERE, "liboracle.so"], check=True, stdout=subprocess.DEVNULL)
@@ -58,6 +65,12 @@ def _load():
                                          C.c_void_p, C.c_void_p]
         _lib.oracle_prefix_reads.restype = None
         _lib.oracle_prefix_reads.argtypes = [C.POINTER(_Reads), C.c_int32, C.c_void_p]
+        _lib.oracle_read_input.restype = C.c_int
+        _lib.oracle_read_input.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(_InputParams),
+                                           C.POINTER(C.c_uint32), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        _lib.oracle_remap.restype = C.c_int
+        _lib.oracle_remap.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
         _lib.oracle_free.argtypes = [C.c_void_p]
     return _lib
 
@@ -135,3 +148,46 @@ def prefix_reads(reads, remove_type=2) -> np.ndarray:
     mask = np.zeros(reads.n, np.uint8)
     lib.oracle_prefix_reads(C.byref(rs), remove_type, mask.ctypes.data)
     return mask
+
+
+def read_input(text1: bytes, text2: bytes | None = None, file_type=INPUT_FASTA, trim_left=3, trim_right=3, rna=0,
+               str_threshold=20):
+    """InputReader::readInput on in-memory files -> (ReadSet, info dict); raises ValueError where the reference exits."""
+    from alga_b200.readset import ReadSet
+    lib = _load()
+    ip = _InputParams(file_type, trim_left, trim_right, rna, str_threshold)
+    b1 = np.frombuffer(text1, np.uint8)
+    b2 = np.frombuffer(text2, np.uint8) if text2 is not None else None
+    n = C.c_uint32(0)
+    pl, po, pw = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    cn, cs = C.c_uint64(0), C.c_uint64(0)
+    rc = lib.oracle_read_input(b1.ctypes.data if b1.size else None, b1.size,
+                               (b2.ctypes.data if b2.size else C.cast(C.create_string_buffer(1), C.c_void_p)) if b2 is not None else None,
+                               b2.size if b2 is not None else 0, C.byref(ip), C.byref(n), C.byref(pl), C.byref(po),
+                               C.byref(pw), C.byref(cn), C.byref(cs))
+    if rc != 0:
+        raise ValueError({-1: "invalid character in a read", -2: "mate files differ in record count"}.get(rc, str(rc)))
+    nn = n.value
+    ln = np.ctypeslib.as_array(C.cast(pl, C.POINTER(C.c_uint32)), shape=(max(nn, 1),))[:nn].copy()
+    off = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_uint64)), shape=(nn + 1,)).copy()
+    nw = int(off[nn])
+    w = np.ctypeslib.as_array(C.cast(pw, C.POINTER(C.c_uint32)), shape=(max(nw, 1),))[:nw].copy()
+    for q in (pl, po, pw):
+        lib.oracle_free(q)
+    return ReadSet(w, off, ln), dict(n_with_n=cn.value, n_str=cs.value)
+
+
+def remap(len_nt, mask=None):
+    """main.cpp:133-232 -> (old_id uint32 [n_out], paired_offset uint8 [n_out])."""
+    lib = _load()
+    ln = np.ascontiguousarray(len_nt, dtype=np.uint32)
+    n = ln.shape[0]
+    m = np.ascontiguousarray(mask, dtype=np.uint8) if mask is not None else None
+    old = np.zeros(max(n, 1), np.uint32)
+    po = np.zeros(max(n, 1), np.uint8)
+    no = C.c_uint32(0)
+    rc = lib.oracle_remap(ln.ctypes.data, m.ctypes.data if m is not None else None, n, old.ctypes.data, po.ctypes.data,
+                          C.byref(no))
+    if rc != 0:
+        raise ValueError("a read is present without its reverse complement (the reference asserts, main.cpp:173)")
+    return old[: no.value].copy(), po[: no.value].copy()

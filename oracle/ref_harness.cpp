@@ -24,6 +24,7 @@
 #include <GraphCreators/GraphCreatorPrefSuf.h>
 #include <GraphCreators/GraphCreatorLI.h>
 #include <IO/ReadPreprocess.h>
+#include <IO/InputReader.h>
 #include <AlignmentControllers/AlignmentControllerHybrid.h>
 #include <AlignmentControllers/AlignmentControllerLowErrorRate.h>
 
@@ -267,6 +268,50 @@ int run_prefix_reads(const char *reads_path, const char *out_path, int remove_ty
     return 0;
 }
 
+// InputReader::readInput (main.cpp:67-82) on one or two files: the reference's own option parser sets the file type from the
+// extension (Params.cpp:332-335), its reader produces Global::READS; dumped as an ALGR file (nullptr = length 0).
+int run_read_input(const char *file1, const char *file2, const char *out_path, int threads, int n_extra, char **extra) {
+    std::vector<std::string> args = {"ALGA", std::string("--file1=") + file1};
+    if (strcmp(file2, "-") != 0) args.push_back(std::string("--file2=") + file2);
+    args.push_back("--threads=" + std::to_string(threads));
+    args.push_back("--output=harness_out.fasta");
+    for (int i = 0; i < n_extra; i++) args.push_back(extra[i]);  // e.g. --rna=1, --retl=.. (the reference's own option names)
+    std::vector<char *> av;
+    for (auto &a : args) av.push_back(const_cast<char *>(a.c_str()));
+    av.push_back(nullptr);
+    Params::initializeParams((int) args.size(), av.data());
+    InputReader reader;
+    reader.readInput();
+    const uint32_t n = (uint32_t) Global::READS.size();
+    std::vector<uint32_t> len(n, 0), words;
+    std::vector<uint64_t> off(n + 1, 0);
+    for (uint32_t i = 0; i < n; i++) {
+        Read *r = Global::READS[i];
+        if (r != nullptr) {
+            if (r->getId() != (int) i) die("read id differs from its index");
+            len[i] = (uint32_t) r->size();
+            const uint32_t nb = (len[i] + 15) / 16;
+            for (uint32_t b = 0; b < nb; b++) words.push_back(r->getSequence().getBlock((int) b));
+        }
+        off[i + 1] = words.size();
+    }
+    std::vector<uint8_t> ones(n, 1);
+    FILE *f = fopen(out_path, "wb");
+    if (!f) die("cannot open output");
+    fwrite("ALGR", 1, 4, f);
+    fwrite(&n, 4, 1, f);
+    int32_t p[4] = {0, 0, 0, 0};
+    fwrite(p, 4, 4, f);
+    fwrite(len.data(), 4, n, f);
+    fwrite(ones.data(), 1, n, f);
+    fwrite(ones.data(), 1, n, f);
+    fwrite(off.data(), 8, (size_t) n + 1, f);
+    fwrite(words.data(), 4, words.size(), f);
+    fclose(f);
+    printf("{\"n\": %u}\n", n);
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -282,12 +327,15 @@ int main(int argc, char **argv) {
     if (argc >= 9 && strcmp(argv[1], "supplement") == 0)
         return run_supplement(argv[2], argv[3], argv[4], atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]),
                               argc >= 10 ? atoi(argv[9]) : 1);
+    if (argc >= 5 && strcmp(argv[1], "readinput") == 0)
+        return run_read_input(argv[2], argv[3], argv[4], argc >= 6 ? atoi(argv[5]) : 1, argc > 6 ? argc - 6 : 0, argv + 6);
     fprintf(stderr,
             "usage: %s prefsuf <reads.algr> <edges.alge|-> [threads]\n"
             "       %s verify  <reads.algr> <pairs.algp> <verdict.bin>\n"
             "       %s supplement <reads.algr> <edges_in.alge> <edges_out.alge> <min_overlap_area> <max_offset_pct> "
             "<threshold_pct> <kmer_length_bucket> [threads]\n"
-            "       %s prefixreads <reads.algr> <mask.bin> [remove_type 1|2] [threads]\n",
-            argv[0], argv[0], argv[0], argv[0]);
+            "       %s prefixreads <reads.algr> <mask.bin> [remove_type 1|2] [threads]\n"
+            "       %s readinput <file1> <file2|-> <reads_out.algr> [threads [reference options, e.g. --rna=1]]\n",
+            argv[0], argv[0], argv[0], argv[0], argv[0]);
     return 2;
 }

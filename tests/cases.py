@@ -171,3 +171,115 @@ def preprocess_case(name):
     if name == "pre_periodic":  # low complexity: long runs of reads that are prefixes of each other
         return _periodic(43, 1500, dedupe=False)
     raise KeyError(name)
+
+
+# ---- input stage (InputReader::readInput, main.cpp:82; renumbering, main.cpp:150-232) -------------------------------
+_NT = np.frombuffer(b"ACGT", np.uint8)
+
+
+def _seq(codes) -> bytes:
+    return _NT[np.asarray(codes, dtype=np.uint8)].tobytes()
+
+
+def _fasta(seqs, prefix=b"r") -> bytes:
+    return b"".join(b">" + prefix + str(i).encode() + b"\n" + s + b"\n" for i, s in enumerate(seqs))
+
+
+def _fastq(seqs, rng) -> bytes:
+    out = []
+    for i, s in enumerate(seqs):
+        q = bytes(rng.integers(33, 74, size=len(s), dtype=np.uint8).tolist())  # quality lines may hold '>', '@', ' ' ...
+        out.append(b"@q" + str(i).encode() + b" 1:N:0\n" + s + b"\n+\n" + q + b"\n")
+    return b"".join(out)
+
+
+def _spice(seqs, rng, p_n=0.03, p_str=0.03, p_short=0.03, p_space=0.03):
+    """Sprinkle the special cases of InputReader.cpp:286-353 over a list of sequences."""
+    out = []
+    for s in seqs:
+        u = rng.random()
+        if u < p_n:                      # an N somewhere -> both strands dropped
+            k = int(rng.integers(0, len(s)))
+            s = s[:k] + b"N" + s[k + 1:]
+        elif u < p_n + p_str:            # short-period repeat (period 1..20, maybe imperfect at the ends that get trimmed)
+            per = int(rng.integers(1, 24))
+            unit = _seq(rng.integers(0, 4, size=per))
+            s = (unit * (len(s) // per + 2))[: len(s)]
+            if rng.random() < 0.3:
+                s = b"ACG"[: min(3, len(s))] + s[3:]
+        elif u < p_n + p_str + p_short:  # shorter than trim + 10 (not trimmed), down to 1 nt
+            s = s[: int(rng.integers(1, 22))]
+        elif u < p_n + p_str + p_short + p_space:  # leading spaces / trailing junk after a space
+            s = b"  " + s + (b" trailing" if rng.random() < 0.5 else b"")
+        out.append(s)
+    return out
+
+
+INPUT_CASES = ["in_fasta_se", "in_fasta_pe", "in_fastq_pe", "in_plain", "in_rna", "in_u_dna", "in_truncated", "in_no_eol",
+               "in_empty", "in_long"]
+
+
+def input_case(name):
+    """-> (text1, text2 | None, file_type, extra harness args): file contents for InputReader::readInput."""
+    from oracle.oracle import INPUT_FASTA, INPUT_FASTQ, INPUT_PLAIN
+    rng = np.random.default_rng(sum(name.encode()) * 7919)
+    g = synth.make_genome(20_000, rng)
+    if name == "in_fasta_se":
+        m = synth.sample_single_end(g, 100, 12, rng, 0.0)
+        return _fasta(_spice([_seq(r) for r in m], rng)), None, INPUT_FASTA, []
+    if name in ("in_fasta_pe", "in_fastq_pe"):
+        m1, m2 = synth.sample_paired_end(g, 150, 14, rng, 0.005)
+        s1 = _spice([_seq(r[: int(rng.integers(60, 151))]) for r in m1], rng)
+        s2 = _spice([_seq(r[: int(rng.integers(60, 151))]) for r in m2], rng)
+        if name == "in_fasta_pe":
+            return _fasta(s1), _fasta(s2, b"m"), INPUT_FASTA, []
+        return _fastq(s1, rng), _fastq(s2, rng), INPUT_FASTQ, []
+    if name == "in_plain":          # whitespace-separated sequences, mixed separators
+        m = synth.sample_single_end(g, 80, 6, rng, 0.0)
+        seqs = _spice([_seq(r) for r in m], rng, p_space=0.0)
+        seps = [b"\n", b" ", b"\t", b"\n\n", b" \n"]
+        return b"".join(s + seps[int(rng.integers(0, len(seps)))] for s in seqs), None, INPUT_PLAIN, []
+    if name in ("in_rna", "in_u_dna"):  # U characters: T with --rna=1, otherwise kept (packs as 0, complement unchanged)
+        m = synth.sample_single_end(g, 100, 4, rng, 0.0)
+        seqs = [_seq(r).replace(b"T", b"U") if rng.random() < 0.5 else _seq(r) for r in m]
+        return _fasta(_spice(seqs, rng)), None, INPUT_FASTA, (["--rna=1"] if name == "in_rna" else [])
+    if name == "in_truncated":      # an empty sequence line in the middle: reading stops there (InputReader.cpp:284)
+        m = synth.sample_single_end(g, 100, 2, rng, 0.0)
+        seqs = [_seq(r) for r in m]
+        seqs[len(seqs) // 2] = b""
+        return _fasta(seqs), None, INPUT_FASTA, []
+    if name == "in_no_eol":         # last line without a newline; header-only tail in the mate file
+        m1, m2 = synth.sample_paired_end(g, 100, 2, rng, 0.0)
+        return _fasta([_seq(r) for r in m1])[:-1], _fasta([_seq(r) for r in m2]) + b">dangling header", INPUT_FASTA, []
+    if name == "in_empty":
+        return b"", None, INPUT_FASTA, []
+    if name == "in_long":           # reads of several hundred nucleotides to a few thousand (more than one 32-lane step per line)
+        seqs = []
+        for _ in range(300):
+            ln = int(rng.integers(200, 3000))
+            s0 = int(rng.integers(0, len(g) - ln))
+            seqs.append(_seq(g[s0:s0 + ln]))
+        return _fasta(_spice(seqs, rng)), None, INPUT_FASTA, []
+    raise KeyError(name)
+
+
+FRONT_CASES = ["front_se", "front_pe"]
+
+
+def front_case(name):
+    """-> (text1, text2 | None, file_type): inputs for the whole path main.cpp:82-291 (reader, duplicate / prefix-read
+    removal, renumbering, GraphCreatorPrefSuf), pinned by the graph the stock binary serialises."""
+    from oracle.oracle import INPUT_FASTA
+    rng = np.random.default_rng(sum(name.encode()) * 104729)
+    if name == "front_se":          # BASELINE config 1 shape: 100 bp single-end, 30x, error-free
+        g = synth.make_genome(30_000, rng)
+        m = synth.sample_single_end(g, 100, 30, rng, 0.0)
+        return _fasta(_spice([_seq(r) for r in m], rng, p_short=0.0, p_space=0.0)), None, INPUT_FASTA
+    if name == "front_pe":          # 2 x 150 bp, 40x, ragged lengths (contained reads), a repeat, a few errors
+        g = synth.make_genome(25_000, rng, repeats=2, repeat_len=(300, 800))
+        m1, m2 = synth.sample_paired_end(g, 150, 40, rng, 0.002)
+        cut = lambda r: _seq(r[: int(rng.integers(110, 151))] if rng.random() < 0.3 else r)
+        s1 = _spice([cut(r) for r in m1], rng, p_short=0.0, p_space=0.0)
+        s2 = _spice([cut(r) for r in m2], rng, p_short=0.0, p_space=0.0)
+        return _fasta(s1), _fasta(s2, b"m"), INPUT_FASTA
+    raise KeyError(name)

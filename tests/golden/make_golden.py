@@ -12,7 +12,10 @@ set and the edge set is stored as `<case>.npz`:
 `verify_pairs.npz` holds (pairs, verdicts) of AlignmentControllerHybrid::canAlign evaluated by the
 reference on candidate pairs of the cfg3_small read set; `sup_*.npz` hold the graph before and after the reference's
 error-rate supplement (GraphCreatorLI, main.cpp:300-355) on the supplement cases of tests/cases.py; `pre_*.npz` hold the
-removal masks of ReadPreprocess::getPrefixReads (both removal types) on the preprocessing cases.
+removal masks of ReadPreprocess::getPrefixReads (both removal types) on the preprocessing cases; `in_*.npz` hold
+Global::READS as the reference's InputReader::readInput leaves it (lengths, packed blocks) for the input files of the
+input cases; `front_*.npz` hold the graph the STOCK binary serialises (--serialize=1, --threads=1) for the files of the
+front cases, i.e. after its own reader, duplicate / prefix-read removal, renumbering and GraphCreatorPrefSuf.
 """
 import hashlib
 import os
@@ -24,14 +27,22 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from oracle import harness  # noqa: E402
-from tests.cases import (CASES, PREPROCESS_CASES, SUPPLEMENT_CASES, build_case, preprocess_case, supplement_case,  # noqa: E402
-                         verify_case)
+from tests.cases import (CASES, FRONT_CASES, INPUT_CASES, PREPROCESS_CASES, SUPPLEMENT_CASES, build_case,  # noqa: E402
+                         front_case, input_case, preprocess_case, supplement_case, verify_case)
 
 
 def input_sha(rs) -> str:
     h = hashlib.sha256()
     for a in (rs.len_nt, rs.align_from, rs.align_to, rs.word_off, rs.words):
         h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def text_sha(t1, t2) -> str:
+    h = hashlib.sha256(t1)
+    if t2 is not None:
+        h.update(b"|")
+        h.update(t2)
     return h.hexdigest()
 
 
@@ -69,6 +80,19 @@ def main():
         m1 = harness.run_prefix_reads(rs, 1)
         np.savez_compressed(os.path.join(HERE, f"{name}.npz"), mask_all=m2, mask_dup=m1, input_sha=np.array(input_sha(rs)))
         print(f"{name}: n={rs.n} removed {int(m2.sum())} (all prefix reads) / {int(m1.sum())} (duplicates only)")
+    # InputReader::readInput (main.cpp:82) on file contents
+    for name in INPUT_CASES:
+        t1, t2, ft, extra = input_case(name)
+        rs = harness.run_read_input(t1, t2, ft, extra=extra)
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), len_nt=rs.len_nt, word_off=rs.word_off, words=rs.words,
+                            input_sha=np.array(text_sha(t1, t2)))
+        print(f"{name}: {rs.n} reads, {int((rs.len_nt == 0).sum())} nullptr")
+    # the stock binary from the files to the serialised graph (main.cpp:57-293)
+    for name in FRONT_CASES:
+        t1, t2, ft = front_case(name)
+        n, edges = harness.run_stock_graph(t1, t2, ft)
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), n=np.array(n), edges=edges, input_sha=np.array(text_sha(t1, t2)))
+        print(f"{name}: n={n} E={edges.shape[0]}")
 
 
 if __name__ == "__main__":

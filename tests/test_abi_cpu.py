@@ -36,6 +36,8 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Csr) == 48
     assert C.sizeof(_lib.Timing) == 48 + 64
     assert C.sizeof(_lib.VerifyParams) == 24
+    assert C.sizeof(_lib.InputParams) == 24
+    assert C.sizeof(_lib.ReadSetOut) == 80
 
 
 def test_version_and_error_strings():

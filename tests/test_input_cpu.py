@@ -1,0 +1,122 @@
+"""CPU tests of the input stage's oracle (oracle/input_oracle.c): InputReader::readInput against the reads the
+unmodified reference produced (tests/golden/in_*.npz, live against oracle/_ref where it exists), and the whole path
+from the files to the graph -- reader, ReadPreprocess, the renumbering of main.cpp:150-232, GraphCreatorPrefSuf --
+against the graph the STOCK binary serialises (tests/golden/front_*.npz)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from alga_b200.input_reader import driver_params
+from alga_b200.readset import ReadSet
+from oracle import harness, oracle
+from tests.cases import FRONT_CASES, INPUT_CASES, front_case, input_case
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def text_sha(t1, t2):
+    h = hashlib.sha256(t1)
+    if t2 is not None:
+        h.update(b"|")
+        h.update(t2)
+    return h.hexdigest()
+
+
+def same_reads(a: ReadSet, len_nt, word_off, words):
+    return (a.n == len_nt.shape[0] and np.array_equal(a.len_nt, len_nt) and np.array_equal(a.word_off, word_off)
+            and np.array_equal(a.words, words))
+
+
+def gather(rs: ReadSet, ids) -> ReadSet:
+    """Reads `ids` of rs, in that order."""
+    cnt = (rs.word_off[1:] - rs.word_off[:-1])[ids].astype(np.int64)
+    off = np.zeros(len(ids) + 1, np.uint64)
+    np.cumsum(cnt, out=off[1:])
+    src = np.repeat(rs.word_off[:-1][ids].astype(np.int64) - off[:-1].astype(np.int64), cnt) + np.arange(int(off[-1]))
+    return ReadSet(rs.words[src] if len(src) else np.zeros(0, np.uint32), off, rs.len_nt[ids])
+
+
+def oracle_front(t1, t2, ft):
+    """main.cpp:82-291 composed from the oracle's pieces -> (n, edges)."""
+    rs, _ = oracle.read_input(t1, t2, ft)
+    prm = driver_params(rs)
+    mask = oracle.prefix_reads(rs, 2)
+    old, po = oracle.remap(rs.len_nt, mask)
+    rs2 = gather(rs, old)
+    ln = rs2.len_nt.copy()
+    ln[ln < prm["li_kmer_intervals"] + prm["li_kmer_length"]] = 0  # main.cpp:253-266
+    rs3 = ReadSet(rs2.words, rs2.word_off, ln)
+    return rs3, po, harness.sort_edges(oracle.prefsuf(rs3, prm["min_overlap"], prm["rs_min_overlap"]))
+
+
+@pytest.mark.parametrize("name", INPUT_CASES)
+def test_read_input_oracle_matches_reference_fixture(name):
+    t1, t2, ft, extra = input_case(name)
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    assert str(g["input_sha"]) == text_sha(t1, t2), "generator drifted: rerun tests/golden/make_golden.py"
+    rs, info = oracle.read_input(t1, t2, ft, rna=int("--rna=1" in extra))
+    assert same_reads(rs, g["len_nt"], g["word_off"], g["words"])
+    assert rs.n % 2 == 0 and np.array_equal(rs.len_nt[0::2], rs.len_nt[1::2])
+    assert 2 * (info["n_with_n"] + info["n_str"]) == int((rs.len_nt == 0).sum())
+
+
+@pytest.mark.skipif(not harness.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", ["in_fasta_pe", "in_plain", "in_rna", "in_truncated"])
+def test_read_input_oracle_matches_reference_live(name):
+    t1, t2, ft, extra = input_case(name)
+    ref = harness.run_read_input(t1, t2, ft, extra=extra)
+    rs, _ = oracle.read_input(t1, t2, ft, rna=int("--rna=1" in extra))
+    assert same_reads(rs, ref.len_nt, ref.word_off, ref.words)
+
+
+def test_read_input_error_cases():
+    ok = b">a\nACGTACGTACGTACGTACGTAGCATCGATCGACTAGCTAGCTACGACTAGC\n"
+    with pytest.raises(ValueError):
+        oracle.read_input(ok + b">b\nACGTacgtACGTACGTACGTACGTACGT\n", None, oracle.INPUT_FASTA)  # lower case: the reference exits
+    # CR is part of the line: a long read loses it to the end trimming, a short (untrimmed) one keeps it -> bad character
+    rs, _ = oracle.read_input(ok.replace(b"\n", b"\r\n"), None, oracle.INPUT_FASTA)
+    assert rs.len_nt.tolist() == [46, 46]
+    with pytest.raises(ValueError):
+        oracle.read_input(b">s\r\nACGTTGCA\r\n", None, oracle.INPUT_FASTA)
+    with pytest.raises(ValueError):
+        oracle.read_input(ok + ok, ok, oracle.INPUT_FASTA)  # mate files of different length
+    if harness.available():
+        with pytest.raises(RuntimeError):
+            harness.run_read_input(ok + b">b\nACGTacgtACGTACGTACGTACGTACGT\n", None, oracle.INPUT_FASTA)
+    # a bad character behind the point where reading stops is never seen
+    rs, _ = oracle.read_input(ok + b">e\n\n>b\nxxxx\n", None, oracle.INPUT_FASTA)
+    assert rs.n == 2
+
+
+def test_remap_rules():
+    # units: (0,1) mates, (2,3) mates, ... ; unit u = reads 2u, 2u+1
+    ln = np.full(16, 50, np.uint32)
+    mask = np.zeros(16, np.uint8)
+    mask[[2, 3]] = 1      # unit 1 (second mate of pair 0) removed -> unit 0 alone: offset 0
+    mask[[8, 9]] = 1      # unit 4 (first mate of pair 2) removed -> unit 5 alone: offset 0
+    ln[[12, 13]] = 0      # unit 6 nullptr from the reader, unit 7 alone
+    old, po = oracle.remap(ln, mask)
+    assert old.tolist() == [0, 1, 4, 5, 6, 7, 10, 11, 14, 15]
+    assert po.tolist() == [0, 0, 1, 1, 2, 2, 0, 0, 0, 0]
+    with pytest.raises(ValueError):
+        m2 = np.zeros(16, np.uint8)
+        m2[5] = 1         # a read without its reverse complement: main.cpp:173 asserts
+        oracle.remap(ln, m2)
+    old, po = oracle.remap(np.zeros(0, np.uint32), None)
+    assert old.shape == (0,)
+    # odd number of units: the last first-mate has no partner slot
+    old, po = oracle.remap(np.full(6, 9, np.uint32), None)
+    assert po.tolist() == [1, 1, 2, 2, 0, 0]
+
+
+@pytest.mark.parametrize("name", FRONT_CASES)
+def test_files_to_graph_matches_stock_binary(name):
+    t1, t2, ft = front_case(name)
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    assert str(g["input_sha"]) == text_sha(t1, t2), "generator drifted: rerun tests/golden/make_golden.py"
+    rs, po, edges = oracle_front(t1, t2, ft)
+    assert rs.n == int(g["n"])
+    assert np.array_equal(edges, g["edges"])
+    assert po.shape[0] == rs.n

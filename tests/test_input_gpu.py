@@ -1,0 +1,164 @@
+"""GPU parity of the input stage through the C ABI: alga_gpu_read_input (InputReader::readInput), alga_gpu_remap_reads
+(main.cpp:150-232) and the whole path from the files to the overlap graph (main.cpp:82-291) against the oracle, the
+reads the unmodified reference produced (tests/golden/in_*.npz) and the graph the stock binary serialises
+(tests/golden/front_*.npz)."""
+import os
+
+import numpy as np
+import pytest
+
+from alga_b200 import _lib, synth
+from alga_b200.input_reader import FASTA, FASTQ, InputReader, build_overlap_graph, remap_reads
+from alga_b200.readset import ReadSet
+from oracle import oracle
+from tests.cases import FRONT_CASES, INPUT_CASES, PREPROCESS_CASES, _fasta, _seq, front_case, input_case, preprocess_case
+from tests.test_input_cpu import gather
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def words_of(rs: ReadSet, i: int) -> np.ndarray:
+    return rs.words[int(rs.word_off[i]): int(rs.word_off[i]) + (int(rs.len_nt[i]) + 15) // 16]
+
+
+def assert_same_reads(got: ReadSet, len_nt, word_off, words):
+    """`got` has a fixed stride, the reference side ragged offsets: compare read by read, and the padding must be zero."""
+    assert got.n == len_nt.shape[0]
+    assert np.array_equal(got.len_nt, len_nt)
+    if got.n == 0:
+        return
+    stride = int(got.word_off[1] - got.word_off[0])
+    m = got.words.reshape(got.n, stride)
+    cnt = (len_nt.astype(np.int64) + 15) // 16
+    col = np.arange(stride)[None, :]
+    assert not m[col >= cnt[:, None]].any(), "blocks behind the end of a read must be zero"
+    flat = m[col < cnt[:, None]]
+    assert np.array_equal(flat, words)
+
+
+@pytest.mark.parametrize("name", INPUT_CASES)
+def test_read_input_matches_oracle_and_reference(gpu, name):
+    t1, t2, ft, extra = input_case(name)
+    rd = InputReader(ft, rna="--rna=1" in extra)
+    got = rd.readInput(t1, t2)
+    want, info = oracle.read_input(t1, t2, ft, rna=int("--rna=1" in extra))
+    assert_same_reads(got, want.len_nt, want.word_off, want.words)
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    assert_same_reads(got, g["len_nt"], g["word_off"], g["words"])
+    assert rd.info["n_with_n"] == info["n_with_n"] and rd.info["n_str"] == info["n_str"]
+    assert rd.timing["kernel_launches"] > 0 or got.n == 0
+
+
+def test_read_input_trim_and_threshold_options(gpu):
+    t1, _, ft, _ = input_case("in_fasta_se")
+    for tl, tr, thr in [(0, 0, 20), (5, 1, 20), (3, 3, 7), (0, 12, 40)]:
+        got = InputReader(ft, trim_left=tl, trim_right=tr, str_threshold=thr).readInput(t1)
+        want, _ = oracle.read_input(t1, None, ft, trim_left=tl, trim_right=tr, str_threshold=thr)
+        assert_same_reads(got, want.len_nt, want.word_off, want.words)
+
+
+def test_read_input_errors(gpu):
+    ok = b">a\nACGTACGTACGTACGTACGTAGCATCGATCGACTAGCTAGCTACGACTAGC\n"
+    with pytest.raises(_lib.AlgaGpuError) as e:
+        InputReader(FASTA).readInput(ok + b">b\nACGTacgtACGTACGTACGTACGTACGT\n")
+    assert e.value.code == -1 and "record 1" in str(e.value)
+    with pytest.raises(_lib.AlgaGpuError):
+        InputReader(FASTA).readInput(b">s\r\nACGTTGCA\r\n")
+    with pytest.raises(_lib.AlgaGpuError):
+        InputReader(FASTA).readInput(ok + ok, ok)
+    with pytest.raises(_lib.AlgaGpuError):
+        InputReader(7).readInput(ok)
+    # a bad character behind the point where reading stops is never seen (InputReader.cpp:284)
+    assert InputReader(FASTA).readInput(ok + b">e\n\n>b\nxxxx\n").n == 2
+    # CR LF on a long read: the CR falls to the end trimming
+    assert InputReader(FASTA).readInput(ok.replace(b"\n", b"\r\n")).len_nt.tolist() == [46, 46]
+
+
+def test_read_input_block_boundaries(gpu):
+    """Record starts and line ends at every position relative to the 16-byte / 4 KiB granules of the mark kernels."""
+    rng = np.random.default_rng(5)
+    for pad in range(0, 40, 3):
+        seqs = [_seq(rng.integers(0, 4, size=int(rng.integers(30, 130)))) for _ in range(400)]
+        text = b">" + b"x" * pad + b"\n" + seqs[0] + b"\n" + _fasta(seqs[1:])
+        got = InputReader(FASTA).readInput(text)
+        want, _ = oracle.read_input(text, None, oracle.INPUT_FASTA)
+        assert_same_reads(got, want.len_nt, want.word_off, want.words)
+
+
+def test_read_input_full_size_properties(gpu):
+    """BASELINE config 2 sized files (2 x 766 666 records of 150 bp): strands are reverse complements of each other,
+    mates interleave, lengths are 144, and the packed reads equal the host-side packing of the same records."""
+    rng = np.random.default_rng(2)
+    g = synth.make_genome(4_600_000, rng)
+    m1, m2 = synth.sample_paired_end(g, 150, 50, rng, 0.0)
+    rd = InputReader(FASTA)
+    got = rd.readInput(synth.fasta_text(m1), synth.fasta_text(m2))
+    n = m1.shape[0]
+    assert got.n == 4 * n
+    want = synth.strand_nodes(m1, m2)  # host-side trimming / strand layout of the same records
+    from alga_b200.readset import pack_matrix
+    ref_words = pack_matrix(want)
+    alive = got.len_nt > 0
+    assert np.array_equal(got.len_nt[alive], np.full(int(alive.sum()), 144, np.uint32))
+    assert np.array_equal(alive[0::2], alive[1::2])
+    stride = int(got.word_off[1] - got.word_off[0])
+    assert stride == 9
+    assert np.array_equal(got.words.reshape(-1, 9)[alive], ref_words[alive])
+    assert int((~alive).sum()) == 2 * (rd.info["n_with_n"] + rd.info["n_str"])
+    assert (~alive).sum() < 100  # random 144-mers are practically never short-period repeats
+
+
+@pytest.mark.parametrize("name", PREPROCESS_CASES + ["in_fasta_pe", "in_fasta_se"])
+def test_remap_matches_oracle(gpu, name):
+    if name.startswith("in_"):
+        t1, t2, ft, _ = input_case(name)
+        rs, _ = oracle.read_input(t1, t2, ft)
+    else:
+        rs = preprocess_case(name)
+        if rs.n % 2:
+            pytest.skip("odd read count")
+    mask = oracle.prefix_reads(rs, 2)
+    try:
+        old, po = oracle.remap(rs.len_nt, mask)
+    except ValueError:  # a palindromic duplicate leaves one strand without its twin: drop pairs together
+        mask = np.repeat(mask[0::2] | mask[1::2], 2).astype(np.uint8)
+        old, po = oracle.remap(rs.len_nt, mask)
+    rm = remap_reads(rs, mask)
+    assert np.array_equal(rm.old_id, old)
+    assert np.array_equal(rm.paired_offset, po)
+    want = gather(rs, old)
+    assert_same_reads(rm.reads, want.len_nt, want.word_off, want.words)
+    # nothing to remove, no mask: identity
+    if rm.reads.n:
+        again = remap_reads(rm.reads)
+        assert np.array_equal(again.old_id, np.arange(rm.reads.n, dtype=np.uint32))
+
+
+def test_remap_edge_cases(gpu):
+    ln = np.full(16, 50, np.uint32)
+    rs = ReadSet(np.arange(16 * 4, dtype=np.uint32), np.arange(17, dtype=np.uint64) * np.uint64(4), ln.copy())
+    mask = np.zeros(16, np.uint8)
+    mask[[2, 3, 8, 9]] = 1
+    rs.len_nt[[12, 13]] = 0
+    rm = remap_reads(rs, mask)
+    assert rm.old_id.tolist() == [0, 1, 4, 5, 6, 7, 10, 11, 14, 15]
+    assert rm.paired_offset.tolist() == [0, 0, 1, 1, 2, 2, 0, 0, 0, 0]
+    bad = np.zeros(16, np.uint8)
+    bad[5] = 1
+    with pytest.raises(_lib.AlgaGpuError):
+        remap_reads(rs, bad)
+    empty = ReadSet(np.zeros(0, np.uint32), np.zeros(1, np.uint64), np.zeros(0, np.uint32))
+    assert remap_reads(empty).reads.n == 0
+    allgone = remap_reads(rs, np.ones(16, np.uint8))
+    assert allgone.reads.n == 0
+
+
+@pytest.mark.parametrize("name", FRONT_CASES)
+def test_files_to_graph_matches_stock_binary(gpu, name):
+    """main.cpp:82-291 on the GPU end to end: same node count and edge set as the graph the stock binary serialised."""
+    t1, t2, ft = front_case(name)
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    og = build_overlap_graph(t1, t2, ft)
+    assert og.reads.n == int(g["n"])
+    assert np.array_equal(og.graph.edges(), g["edges"])
