@@ -71,7 +71,18 @@ class ReadSetOut(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("stride_words", C.c_uint32), ("max_len_nt", C.c_uint32),
                 ("words", C.POINTER(C.c_uint32)), ("len_nt", C.POINTER(C.c_uint32)), ("old_id", C.POINTER(C.c_uint32)),
                 ("paired_offset", C.POINTER(C.c_uint8)), ("n_records", C.c_uint64 * 2), ("n_with_n", C.c_uint64),
-                ("n_str", C.c_uint64)]
+                ("n_str", C.c_uint64), ("borrowed", C.c_int32)]
+
+
+class DriverParams(C.Structure):
+    _fields_ = [("input", InputParams), ("remove_type", C.c_int32), ("scale", C.c_float), ("min_overlap", C.c_int32),
+                ("rs_min_overlap", C.c_int32)]
+
+
+class OverlapGraphOut(C.Structure):
+    _fields_ = [("reads", ReadSetOut), ("graph", Csr), ("avg_len", C.c_double), ("min_overlap", C.c_int32),
+                ("rs_min_overlap", C.c_int32), ("li_kmer_length", C.c_int32), ("n_reads_in", C.c_uint32),
+                ("n_records", C.c_uint64 * 2), ("n_with_n", C.c_uint64), ("n_str", C.c_uint64)]
 
 
 # every symbol include/alga_gpu.h declares: name -> (restype, argtypes)
@@ -112,6 +123,8 @@ SYMBOLS = {
                                       C.POINTER(Timing)]),
     "alga_gpu_remap_reads": (C.c_int, [C.POINTER(Reads), _P, C.c_int32, C.POINTER(ReadSetOut), C.POINTER(Timing)]),
     "alga_gpu_free_read_set": (None, [C.POINTER(ReadSetOut)]),
+    "alga_gpu_files_to_graph": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64, C.POINTER(DriverParams), C.POINTER(OverlapGraphOut),
+                                          C.POINTER(Timing)]),
     "alga_gpu_supplement": (C.c_int, [C.POINTER(Reads), C.POINTER(Csr), C.POINTER(SupParams), C.POINTER(Csr),
                                       C.POINTER(Timing)]),
     "alga_gpu_li_kmers": (C.c_int, [C.POINTER(Reads), _P, C.c_uint32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),

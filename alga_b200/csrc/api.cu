@@ -1251,51 +1251,118 @@ int alga_gpu_li_kmers(const alga_reads *reads, const uint32_t *ids, uint32_t n_i
 
 }  // extern "C"
 
-// ---- InputReader::readInput / renumbering (input.cu) -----------------------------------------------------------------
+// ---- InputReader::readInput / renumbering / files-to-graph (input.cu) ------------------------------------------------
 namespace {
 
 struct InputScalarsHost {  // layout of input.cu's InputScalars
     uint32_t first_empty, first_bad, max_len, pad;
-    unsigned long long n_with_n, n_str;
+    unsigned long long n_with_n, n_str, sum_len, n_alive;
 };
 
 struct InputFile {
-    DevBuf text, block_cnt, block_off, rec_start, info, scalars, scan_ws;
+    DevBuf text, block_cnt, block_off, rec_start, info, scalars;
     uint64_t n = 0;
     uint32_t n_rec = 0;
     InputScalarsHost sc{};
+    void release() { text.release(), block_cnt.release(), block_off.release(), rec_start.release(), info.release(), scalars.release(); }
+};
+
+// Device-resident working set of the input stage.  One process-wide instance is kept between calls (as the one-call graph
+// build keeps its plan): after the first call nothing is allocated any more.
+struct FrontEnd {
+    int device = -1;
+    InputFile f[2];
+    HostBuf stage[2];  // chunked upload of text that is not page-locked
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    // reader output: Global::READS after InputReader::readInput
+    DevBuf words, len;
+    uint32_t n = 0, stride = 1, max_len = 0;
+    // ReadPreprocess
+    DevBuf table, lenmap, flags, mask;
+    // renumbering
+    DevBuf uflag, upos, rscal, scan_ws;
+    DevBuf words2, len2, old_id, po;
+    uint32_t n2 = 0, stride2 = 1, max_len2 = 0;
+    // page-locked result staging (borrowed outputs)
+    HostBuf h_words, h_len, h_words2, h_len2, h_old, h_po;
+
+    ReadsDev raw() const {
+        ReadsDev R{};
+        R.words = words.as<uint32_t>(), R.len = len.as<uint32_t>(), R.n = n, R.stride = stride;
+        return R;
+    }
+    int init(int dev) {
+        if (device != dev) release();
+        device = dev;
+        for (cudaEvent_t *e : {&stage_ev[0], &stage_ev[1]})
+            if (!*e) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (cudaEvent_t *e : {&ev[0], &ev[1]})
+            if (!*e) CK(cudaEventCreate(e));
+        return ALGA_OK;
+    }
     void release() {
-        text.release(), block_cnt.release(), block_off.release(), rec_start.release(), info.release(), scalars.release(),
-            scan_ws.release();
+        f[0].release(), f[1].release();
+        for (DevBuf *b : {&words, &len, &table, &lenmap, &flags, &mask, &uflag, &upos, &rscal, &scan_ws, &words2, &len2, &old_id, &po})
+            b->release();
+        for (HostBuf *b : {&stage[0], &stage[1], &h_words, &h_len, &h_words2, &h_len2, &h_old, &h_po}) b->release();
+        for (cudaEvent_t *e : {&stage_ev[0], &stage_ev[1], &ev[0], &ev[1]}) {
+            if (*e) cudaEventDestroy(*e);
+            *e = nullptr;
+        }
     }
 };
 
-// upload + record index + per-record scan of one file; leaves f.n_rec, f.sc and the device buffers text / info
-int input_scan_file(InputFile &f, const uint8_t *text, uint64_t n, const alga_input_params &p, int which, const LaunchCfg &cfg,
-                    double *h2d_ms) {
+std::mutex g_front_mutex;
+FrontEnd g_front;
+
+constexpr size_t kStageChunk = 8u << 20;
+
+// host -> device copy of file text: directly if the caller's buffer is page-locked (alga_gpu_host_alloc), otherwise
+// through two page-locked chunks so that the CPU copy of one chunk overlaps the DMA of the previous one
+int fe_upload_text(FrontEnd &fe, DevBuf &dst, const uint8_t *src, uint64_t n) {
+    const size_t padded = (size_t) ((n + 15) / 16) * 16 + 16;
+    CKR(dst.ensure(padded));
+    CK(cudaMemsetAsync((char *) dst.p + n, 0x0A, padded - (size_t) n, 0));  // the kernels never look past n; keep the pad defined
+    if (!n) return ALGA_OK;
+    cudaPointerAttributes attr{};
+    const bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+        CK(cudaMemcpyAsync(dst.p, src, (size_t) n, cudaMemcpyHostToDevice, 0));
+        return ALGA_OK;
+    }
+    CKR(fe.stage[0].ensure(kStageChunk));
+    CKR(fe.stage[1].ensure(kStageChunk));
+    int k = 0;
+    for (uint64_t off = 0; off < n; off += kStageChunk, k ^= 1) {
+        const size_t len = (size_t) (n - off < kStageChunk ? n - off : kStageChunk);
+        if (off >= 2 * kStageChunk) CK(cudaEventSynchronize(fe.stage_ev[k]));
+        memcpy(fe.stage[k].p, src + off, len);
+        CK(cudaMemcpyAsync((char *) dst.p + off, fe.stage[k].p, len, cudaMemcpyHostToDevice, 0));
+        CK(cudaEventRecord(fe.stage_ev[k], 0));
+    }
+    return ALGA_OK;
+}
+
+// record index + per-record scan of one file whose text is on the device; leaves f.n_rec, f.sc and f.info
+int fe_scan_file(FrontEnd &fe, InputFile &f, uint64_t n, const alga_input_params &p, int which, const LaunchCfg &cfg) {
     const bool plain = p.file_type == ALGA_INPUT_PLAIN;
     const uint32_t lpr = p.file_type == ALGA_INPUT_FASTQ ? 4u : 2u;
     f.n = n;
-    const double t0 = now_ms();
-    const size_t padded = (size_t) ((n + 15) / 16) * 16 + 16;
-    CKR(f.text.ensure(padded));
-    if (n) CK(cudaMemcpy(f.text.p, text, (size_t) n, cudaMemcpyHostToDevice));
-    CK(cudaMemset((char *) f.text.p + n, 0x0A, padded - (size_t) n));  // the kernels never look past n; keep the pad defined
-    CK(cudaDeviceSynchronize());
-    *h2d_ms += now_ms() - t0;
     const uint64_t nb = input_mark_blocks(n);
     if (nb > 0x7FFFFFFFull) return fail(ALGA_E_INVALID, "input file %d is too large (%llu bytes)", which, (unsigned long long) n);
     CKR(f.scalars.ensure(input_scalars_bytes()));
     InputScalarsHost init{};
     init.first_empty = init.first_bad = 0xFFFFFFFFu;
-    CK(cudaMemcpy(f.scalars.p, &init, sizeof(init), cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(f.scalars.p, &init, sizeof(init), cudaMemcpyHostToDevice, 0));
     uint64_t n_marks = 0;
     if (nb) {
         CKR(f.block_cnt.ensure((size_t) nb * 4));
         CKR(f.block_off.ensure(((size_t) nb + 1) * 8));
-        CKR(f.scan_ws.ensure(scan_workspace_bytes(nb)));
+        CKR(fe.scan_ws.ensure(scan_workspace_bytes(nb)));
         launch_count_marks(f.text.as<uint8_t>(), n, plain, f.block_cnt.as<uint32_t>(), 0, cfg);
-        launch_scan_u64(f.block_cnt.as<uint32_t>(), f.block_off.as<uint64_t>(), nb, f.scan_ws.p, 0, cfg);
+        launch_scan_u64(f.block_cnt.as<uint32_t>(), f.block_off.as<uint64_t>(), nb, fe.scan_ws.p, 0, cfg);
         CK(cudaGetLastError());
         CK(cudaMemcpy(&n_marks, f.block_off.as<uint64_t>() + nb, 8, cudaMemcpyDeviceToHost));
     }
@@ -1320,86 +1387,184 @@ int input_scan_file(InputFile &f, const uint8_t *text, uint64_t n, const alga_in
     return ALGA_OK;
 }
 
+struct InputTimes {
+    double h2d_ms = 0, kernel_ms = 0;
+};
+
+// InputReader::readInput: file text (host) -> fe.words / fe.len (device); fills the counters of `info`
+int fe_read_input(FrontEnd &fe, const uint8_t *text1, uint64_t n1, const uint8_t *text2, uint64_t n2, const alga_input_params &p,
+                  const LaunchCfg &cfg, alga_read_set *info, InputTimes *tm) {
+    const bool paired = text2 != nullptr;
+    const double t0 = now_ms();
+    CKR(fe_upload_text(fe, fe.f[0].text, text1, n1));
+    if (paired) CKR(fe_upload_text(fe, fe.f[1].text, text2, n2));
+    CK(cudaStreamSynchronize(0));
+    const double t1 = now_ms();
+    tm->h2d_ms = t1 - t0;
+    CKR(fe_scan_file(fe, fe.f[0], n1, p, 1, cfg));
+    if (paired) {
+        CKR(fe_scan_file(fe, fe.f[1], n2, p, 2, cfg));
+        if (fe.f[0].n_rec != fe.f[1].n_rec)
+            return fail(ALGA_E_INVALID, "the mate files hold different numbers of records (%u and %u)", fe.f[0].n_rec, fe.f[1].n_rec);
+    }
+    const uint64_t n_reads = (uint64_t) fe.f[0].n_rec * (paired ? 4 : 2);
+    if (n_reads > 0x7FFFFFFFull) return fail(ALGA_E_INVALID, "too many reads (%llu): ids are 31-bit", (unsigned long long) n_reads);
+    uint32_t max_len = fe.f[0].sc.max_len;
+    if (paired && fe.f[1].sc.max_len > max_len) max_len = fe.f[1].sc.max_len;
+    fe.n = (uint32_t) n_reads;
+    fe.max_len = max_len;
+    fe.stride = max_len ? (max_len + 15) / 16 : 1;
+    info->n_reads = fe.n;
+    info->stride_words = fe.stride;
+    info->max_len_nt = max_len;
+    info->n_records[0] = fe.f[0].n_rec;
+    info->n_records[1] = paired ? fe.f[1].n_rec : 0;
+    info->n_with_n = fe.f[0].sc.n_with_n + (paired ? fe.f[1].sc.n_with_n : 0);
+    info->n_str = fe.f[0].sc.n_str + (paired ? fe.f[1].sc.n_str : 0);
+    CKR(fe.words.ensure((size_t) (n_reads ? n_reads : 1) * fe.stride * 4));
+    CKR(fe.len.ensure((size_t) (n_reads ? n_reads : 1) * 4));
+    for (int k = 0; k < (paired ? 2 : 1); k++)
+        launch_pack_records(fe.f[k].text.as<uint8_t>(), fe.f[k].info.p, fe.f[k].n_rec, p.rna != 0, paired ? 4u : 2u, 2u * k, fe.stride,
+                            fe.words.as<uint32_t>(), fe.len.as<uint32_t>(), 0, cfg);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(0));
+    tm->kernel_ms = now_ms() - t1;
+    return ALGA_OK;
+}
+
+// main.cpp:150-232 on a device-resident read set: R + mask (device, may be null) -> fe.words2 / len2 / old_id / po.
+// stride_out == 0: ceil(longest surviving read / 16).  Reads shorter than min_keep_len become nullptr (length 0).
+int fe_remap(FrontEnd &fe, const ReadsDev &R, const uint8_t *d_mask, uint32_t stride_out, uint32_t min_keep_len, const LaunchCfg &cfg) {
+    const uint32_t n_units = R.n / 2;
+    fe.n2 = 0, fe.stride2 = stride_out ? stride_out : 1, fe.max_len2 = 0;
+    if (!n_units) return ALGA_OK;
+    CKR(fe.uflag.ensure((size_t) n_units * 4));
+    CKR(fe.upos.ensure(((size_t) n_units + 1) * 4));
+    CKR(fe.rscal.ensure(8));
+    CKR(fe.scan_ws.ensure(scan_workspace_bytes(n_units)));
+    CK(cudaMemsetAsync(fe.rscal.p, 0, 8, 0));
+    launch_remap_flags(R, d_mask, n_units, fe.uflag.as<uint32_t>(), fe.rscal.p, 0, cfg);
+    launch_scan_u32(fe.uflag.as<uint32_t>(), fe.upos.as<uint32_t>(), n_units, fe.scan_ws.p, 0, cfg);
+    CK(cudaGetLastError());
+    uint32_t sc[2] = {0, 0}, units_out = 0;
+    CK(cudaMemcpy(sc, fe.rscal.p, 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&units_out, fe.upos.as<uint32_t>() + n_units, 4, cudaMemcpyDeviceToHost));
+    if (sc[1]) return fail(ALGA_E_INVALID, "read %u is present without its reverse complement (main.cpp:173 asserts)", sc[1] - 1);
+    fe.n2 = 2 * units_out;
+    fe.max_len2 = sc[0];
+    if (!stride_out) fe.stride2 = sc[0] ? (sc[0] + 15) / 16 : 1;
+    if (!fe.n2) return ALGA_OK;
+    CKR(fe.words2.ensure((size_t) fe.n2 * fe.stride2 * 4));
+    CKR(fe.len2.ensure((size_t) fe.n2 * 4));
+    CKR(fe.old_id.ensure((size_t) fe.n2 * 4));
+    CKR(fe.po.ensure(fe.n2));
+    launch_remap_scatter(R, n_units, fe.uflag.as<uint32_t>(), fe.upos.as<uint32_t>(), fe.stride2, fe.words2.as<uint32_t>(),
+                         fe.len2.as<uint32_t>(), fe.old_id.as<uint32_t>(), fe.po.as<uint8_t>(), min_keep_len, 0, cfg);
+    CK(cudaGetLastError());
+    return ALGA_OK;
+}
+
+// ReadPreprocess::getPrefixReads on the reader's output -> fe.mask (device)
+int fe_prefix_reads(FrontEnd &fe, int remove_type, const LaunchCfg &cfg) {
+    const uint32_t n = fe.n;
+    SeedTable T{};
+    size_table(T, n, n);
+    const size_t tb = (size_t) T.n_buckets * kSlotsPerBucket * 4;
+    CKR(fe.table.ensure(tb));
+    CKR(fe.lenmap.ensure(prefix_reads_lenmap_words() * 4));
+    CKR(fe.flags.ensure((size_t) (n ? n : 1) * 4));
+    CKR(fe.mask.ensure(n ? n : 1));
+    T.slots = fe.table.as<uint32_t>();
+    CK(cudaMemsetAsync(fe.table.p, 0xFF, tb, 0));
+    launch_prefix_reads(fe.raw(), T, remove_type, fe.lenmap.as<uint32_t>(), fe.flags.as<uint32_t>(), fe.mask.as<uint8_t>(), 0, cfg);
+    CK(cudaGetLastError());
+    uint32_t too_long = 0;
+    CK(cudaMemcpy(&too_long, fe.lenmap.as<uint32_t>() + prefix_reads_lenmap_words() - 1, 4, cudaMemcpyDeviceToHost));
+    if (too_long) return fail(ALGA_E_INVALID, "a read is longer than 65535 nucleotides");
+    return ALGA_OK;
+}
+
 void clear_read_set(alga_read_set *rs) { memset(rs, 0, sizeof(*rs)); }
+
+// device -> page-locked staging of the library; the arrays stay valid until the next call that produces the same kind of
+// read set (out->borrowed = 1)
+int fe_download(FrontEnd &fe, bool remapped, alga_read_set *out) {
+    const uint32_t n = remapped ? fe.n2 : fe.n, stride = remapped ? fe.stride2 : fe.stride;
+    HostBuf &hw = remapped ? fe.h_words2 : fe.h_words, &hl = remapped ? fe.h_len2 : fe.h_len;
+    const size_t wb = (size_t) n * stride * 4;
+    CKR(hw.ensure(wb ? wb : 4));
+    CKR(hl.ensure(n ? (size_t) n * 4 : 4));
+    out->n_reads = n;
+    out->stride_words = stride;
+    out->max_len_nt = remapped ? fe.max_len2 : fe.max_len;
+    out->words = (uint32_t *) hw.p;
+    out->len_nt = (uint32_t *) hl.p;
+    out->borrowed = 1;
+    if (n) {
+        CK(cudaMemcpyAsync(hw.p, remapped ? fe.words2.p : fe.words.p, wb, cudaMemcpyDeviceToHost, 0));
+        CK(cudaMemcpyAsync(hl.p, remapped ? fe.len2.p : fe.len.p, (size_t) n * 4, cudaMemcpyDeviceToHost, 0));
+    }
+    if (remapped) {
+        CKR(fe.h_old.ensure(n ? (size_t) n * 4 : 4));
+        CKR(fe.h_po.ensure(n ? n : 4));
+        out->old_id = (uint32_t *) fe.h_old.p;
+        out->paired_offset = (uint8_t *) fe.h_po.p;
+        if (n) {
+            CK(cudaMemcpyAsync(fe.h_old.p, fe.old_id.p, (size_t) n * 4, cudaMemcpyDeviceToHost, 0));
+            CK(cudaMemcpyAsync(fe.h_po.p, fe.po.p, n, cudaMemcpyDeviceToHost, 0));
+        }
+    }
+    CK(cudaStreamSynchronize(0));
+    return ALGA_OK;
+}
+
+int check_input_params(const alga_input_params *p) {
+    if (p->file_type < ALGA_INPUT_PLAIN || p->file_type > ALGA_INPUT_FASTQ)
+        return fail(ALGA_E_INVALID, "file_type must be ALGA_INPUT_PLAIN, _FASTA or _FASTQ");
+    if (p->trim_left < 0 || p->trim_right < 0) return fail(ALGA_E_INVALID, "trim_left / trim_right must not be negative");
+    return ALGA_OK;
+}
 
 }  // namespace
 
 void alga_gpu_free_read_set(alga_read_set *rs) {
     if (!rs) return;
-    free(rs->words);
-    free(rs->len_nt);
-    free(rs->old_id);
-    free(rs->paired_offset);
+    if (!rs->borrowed) {
+        free(rs->words);
+        free(rs->len_nt);
+        free(rs->old_id);
+        free(rs->paired_offset);
+    }
     clear_read_set(rs);
 }
 
 int alga_gpu_read_input(const uint8_t *text1, uint64_t n1, const uint8_t *text2, uint64_t n2, const alga_input_params *params,
                         alga_read_set *out, alga_timing *timing) {
     if (!params || !out || (n1 && !text1) || (n2 && !text2)) return fail(ALGA_E_INVALID, "null argument");
-    if (params->file_type < ALGA_INPUT_PLAIN || params->file_type > ALGA_INPUT_FASTQ)
-        return fail(ALGA_E_INVALID, "file_type must be ALGA_INPUT_PLAIN, _FASTA or _FASTQ");
-    if (params->trim_left < 0 || params->trim_right < 0) return fail(ALGA_E_INVALID, "trim_left / trim_right must not be negative");
+    CKR(check_input_params(params));
+    std::lock_guard<std::mutex> lock(g_front_mutex);
     clear_read_set(out);
     const double t0 = now_ms();
     LaunchCfg cfg;
     uint64_t launches = 0;
     cfg.launches = &launches;
     CKR(pick_device(params->device, &cfg));
-    const bool paired = text2 != nullptr;
-    InputFile f[2];
-    DevBuf words, len;
-    double h2d_ms = 0, d2h_ms = 0;
-    int r = [&]() -> int {
-        CKR(input_scan_file(f[0], text1, n1, *params, 1, cfg, &h2d_ms));
-        if (paired) {
-            CKR(input_scan_file(f[1], text2, n2, *params, 2, cfg, &h2d_ms));
-            if (f[0].n_rec != f[1].n_rec)
-                return fail(ALGA_E_INVALID, "the mate files hold different numbers of records (%u and %u)", f[0].n_rec, f[1].n_rec);
-        }
-        const uint64_t n_reads = (uint64_t) f[0].n_rec * (paired ? 4 : 2);
-        if (n_reads > 0x7FFFFFFFull) return fail(ALGA_E_INVALID, "too many reads (%llu): ids are 31-bit", (unsigned long long) n_reads);
-        uint32_t max_len = f[0].sc.max_len;
-        if (paired && f[1].sc.max_len > max_len) max_len = f[1].sc.max_len;
-        const uint32_t stride = max_len ? (max_len + 15) / 16 : 1;
-        out->n_reads = (uint32_t) n_reads;
-        out->stride_words = stride;
-        out->max_len_nt = max_len;
-        out->n_records[0] = f[0].n_rec;
-        out->n_records[1] = paired ? f[1].n_rec : 0;
-        out->n_with_n = f[0].sc.n_with_n + (paired ? f[1].sc.n_with_n : 0);
-        out->n_str = f[0].sc.n_str + (paired ? f[1].sc.n_str : 0);
-        const size_t wb = (size_t) n_reads * stride * 4;
-        out->words = (uint32_t *) malloc(wb ? wb : 4);
-        out->len_nt = (uint32_t *) malloc(n_reads ? n_reads * 4 : 4);
-        if (!out->words || !out->len_nt) return fail(ALGA_E_NOMEM, "host allocation of the read set failed");
-        if (!n_reads) return ALGA_OK;
-        CKR(words.ensure(wb));
-        CKR(len.ensure((size_t) n_reads * 4));
-        for (int k = 0; k < (paired ? 2 : 1); k++)
-            launch_pack_records(f[k].text.as<uint8_t>(), f[k].info.p, f[k].n_rec, params->rna != 0, paired ? 4u : 2u, 2u * k, stride,
-                                words.as<uint32_t>(), len.as<uint32_t>(), 0, cfg);
-        CK(cudaGetLastError());
-        CK(cudaDeviceSynchronize());
-        const double t1 = now_ms();
-        CK(cudaMemcpy(out->words, words.p, wb, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(out->len_nt, len.p, (size_t) n_reads * 4, cudaMemcpyDeviceToHost));
-        d2h_ms = now_ms() - t1;
-        return ALGA_OK;
-    }();
-    f[0].release();
-    f[1].release();
-    words.release();
-    len.release();
+    FrontEnd &fe = g_front;
+    CKR(fe.init(params->device));
+    InputTimes tm;
+    int r = fe_read_input(fe, text1, n1, text2, n2, *params, cfg, out, &tm);
+    const double t1 = now_ms();
+    if (r == ALGA_OK) r = fe_download(fe, false, out);
     if (r != ALGA_OK) {
-        alga_gpu_free_read_set(out);
+        clear_read_set(out);
         return r;
     }
     if (timing) {
         memset(timing, 0, sizeof(*timing));
-        timing->h2d_ms = h2d_ms;
-        timing->d2h_ms = d2h_ms;
+        timing->h2d_ms = tm.h2d_ms;
+        timing->device_ms = tm.kernel_ms;  // kernels and their scalar read-backs, text resident -> packed reads resident
+        timing->d2h_ms = now_ms() - t1;
         timing->total_ms = now_ms() - t0;
-        timing->device_ms = timing->total_ms - h2d_ms - d2h_ms;  // kernels + their scalar read-backs and allocations
         timing->kernel_launches = launches;
     }
     return ALGA_OK;
@@ -1409,82 +1574,125 @@ int alga_gpu_remap_reads(const alga_reads *reads, const uint8_t *remove_mask, in
                          alga_timing *timing) {
     if (!reads || !out) return fail(ALGA_E_INVALID, "null argument");
     if (reads->n_reads & 1u) return fail(ALGA_E_INVALID, "n_reads must be even (both strands of every record)");
+    std::lock_guard<std::mutex> lock(g_front_mutex);
     clear_read_set(out);
     const double t0 = now_ms();
     LaunchCfg cfg;
     uint64_t launches = 0;
     cfg.launches = &launches;
     CKR(pick_device(device, &cfg));
+    FrontEnd &fe = g_front;
+    CKR(fe.init(device));
     TmpReads t;
     CKR(t.upload(reads));
-    const uint32_t n = reads->n_reads, n_units = n / 2;
-    DevBuf mask, flag, pos, scalars, scan_ws, words, len, old_id, po;
-    double h2d_ms = 0, d2h_ms = 0;
-    int r = [&]() -> int {
-        if (remove_mask && n) {
-            CKR(mask.ensure(n));
-            CK(cudaMemcpy(mask.p, remove_mask, n, cudaMemcpyHostToDevice));
-        }
-        h2d_ms = now_ms() - t0;
-        out->words = (uint32_t *) malloc(4);
-        out->len_nt = (uint32_t *) malloc(4);
-        out->old_id = (uint32_t *) malloc(4);
-        out->paired_offset = (uint8_t *) malloc(4);
-        out->stride_words = 1;
-        if (!out->words || !out->len_nt || !out->old_id || !out->paired_offset) return fail(ALGA_E_NOMEM, "host allocation failed");
-        if (!n_units) return ALGA_OK;
-        CKR(flag.ensure((size_t) n_units * 4));
-        CKR(pos.ensure(((size_t) n_units + 1) * 4));
-        CKR(scalars.ensure(8));
-        CKR(scan_ws.ensure(scan_workspace_bytes(n_units)));
-        CK(cudaMemsetAsync(scalars.p, 0, 8, 0));
-        launch_remap_flags(t.R, remove_mask ? mask.as<uint8_t>() : nullptr, n_units, flag.as<uint32_t>(), scalars.p, 0, cfg);
-        launch_scan_u32(flag.as<uint32_t>(), pos.as<uint32_t>(), n_units, scan_ws.p, 0, cfg);
-        CK(cudaGetLastError());
-        uint32_t sc[2] = {0, 0}, units_out = 0;
-        CK(cudaMemcpy(sc, scalars.p, 8, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(&units_out, pos.as<uint32_t>() + n_units, 4, cudaMemcpyDeviceToHost));
-        if (sc[1]) return fail(ALGA_E_INVALID, "read %u is present without its reverse complement (main.cpp:173 asserts)", sc[1] - 1);
-        const uint32_t n_out = 2 * units_out, stride = sc[0] ? (sc[0] + 15) / 16 : 1;
-        out->n_reads = n_out;
-        out->stride_words = stride;
-        out->max_len_nt = sc[0];
-        if (!n_out) return ALGA_OK;
-        const size_t wb = (size_t) n_out * stride * 4;
-        free(out->words), free(out->len_nt), free(out->old_id), free(out->paired_offset);
-        out->words = (uint32_t *) malloc(wb);
-        out->len_nt = (uint32_t *) malloc((size_t) n_out * 4);
-        out->old_id = (uint32_t *) malloc((size_t) n_out * 4);
-        out->paired_offset = (uint8_t *) malloc(n_out);
-        if (!out->words || !out->len_nt || !out->old_id || !out->paired_offset) return fail(ALGA_E_NOMEM, "host allocation failed");
-        CKR(words.ensure(wb));
-        CKR(len.ensure((size_t) n_out * 4));
-        CKR(old_id.ensure((size_t) n_out * 4));
-        CKR(po.ensure(n_out));
-        launch_remap_scatter(t.R, n_units, flag.as<uint32_t>(), pos.as<uint32_t>(), stride, words.as<uint32_t>(), len.as<uint32_t>(),
-                             old_id.as<uint32_t>(), po.as<uint8_t>(), 0, cfg);
-        CK(cudaGetLastError());
-        CK(cudaDeviceSynchronize());
-        const double t1 = now_ms();
-        CK(cudaMemcpy(out->words, words.p, wb, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(out->len_nt, len.p, (size_t) n_out * 4, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(out->old_id, old_id.p, (size_t) n_out * 4, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(out->paired_offset, po.p, n_out, cudaMemcpyDeviceToHost));
-        d2h_ms = now_ms() - t1;
-        return ALGA_OK;
-    }();
-    for (DevBuf *b : {&mask, &flag, &pos, &scalars, &scan_ws, &words, &len, &old_id, &po}) b->release();
+    const uint32_t n = reads->n_reads;
+    if (remove_mask && n) {
+        CKR(fe.mask.ensure(n));
+        CK(cudaMemcpy(fe.mask.p, remove_mask, n, cudaMemcpyHostToDevice));
+    }
+    const double t1 = now_ms();
+    int r = fe_remap(fe, t.R, remove_mask && n ? fe.mask.as<uint8_t>() : nullptr, 0, 0, cfg);
+    if (r == ALGA_OK) r = cudaStreamSynchronize(0) == cudaSuccess ? ALGA_OK : fail(ALGA_E_CUDA, "remap kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
+    const double t2 = now_ms();
+    if (r == ALGA_OK) r = fe_download(fe, true, out);
     if (r != ALGA_OK) {
-        alga_gpu_free_read_set(out);
+        clear_read_set(out);
         return r;
     }
     if (timing) {
         memset(timing, 0, sizeof(*timing));
-        timing->h2d_ms = h2d_ms;
-        timing->d2h_ms = d2h_ms;
+        timing->h2d_ms = t1 - t0;
+        timing->device_ms = t2 - t1;
+        timing->d2h_ms = now_ms() - t2;
         timing->total_ms = now_ms() - t0;
-        timing->device_ms = timing->total_ms - h2d_ms - d2h_ms;
         timing->kernel_launches = launches;
+    }
+    return ALGA_OK;
+}
+
+// main.cpp:82-291 in one call, device-resident between the stages
+int alga_gpu_files_to_graph(const uint8_t *text1, uint64_t n1, const uint8_t *text2, uint64_t n2, const alga_driver_params *dp,
+                            alga_overlap_graph *out, alga_timing *timing) {
+    if (!dp || !out || (n1 && !text1) || (n2 && !text2)) return fail(ALGA_E_INVALID, "null argument");
+    CKR(check_input_params(&dp->input));
+    if (dp->remove_type < 0 || dp->remove_type > 2) return fail(ALGA_E_INVALID, "remove_type must be 0 (none), 1 (duplicates) or 2 (all prefix reads)");
+    std::lock_guard<std::mutex> lock(g_front_mutex);
+    std::lock_guard<std::mutex> lock2(g_build_mutex);
+    memset(out, 0, sizeof(*out));
+    const double t0 = now_ms();
+    LaunchCfg cfg;
+    uint64_t launches = 0;
+    cfg.launches = &launches;
+    CKR(pick_device(dp->input.device, &cfg));
+    FrontEnd &fe = g_front;
+    CKR(fe.init(dp->input.device));
+    InputTimes tm;
+    alga_read_set info{};
+    CKR(fe_read_input(fe, text1, n1, text2, n2, dp->input, cfg, &info, &tm));
+    const double t1 = now_ms();
+    // main.cpp:93-110 -- parameters from the average read length (float arithmetic as in the reference)
+    const unsigned long long cnt = fe.f[0].sc.n_alive + (text2 ? fe.f[1].sc.n_alive : 0);
+    const unsigned long long sum = fe.f[0].sc.sum_len + (text2 ? fe.f[1].sc.sum_len : 0);
+    const double avg = cnt ? (double) sum / (double) cnt : 0.0;
+    const float scale = dp->scale > 0 ? dp->scale : 0.55f;
+    const int LEN = (int) (avg + dp->input.trim_left + dp->input.trim_right);
+    const int L = (int) ((float) LEN * scale);
+    const int RS = (int) ((float) LEN * (scale + 1) / 2);
+    out->avg_len = avg;
+    out->min_overlap = dp->min_overlap > 0 ? dp->min_overlap : L;
+    out->rs_min_overlap = dp->rs_min_overlap > 0 ? dp->rs_min_overlap : (dp->min_overlap > 0 ? (dp->min_overlap + LEN) / 2 : RS);
+    out->li_kmer_length = dp->min_overlap > 0 ? dp->min_overlap : (2 * L / 3 < 60 ? 2 * L / 3 : 60);  // Params.cpp:488-497 / main.cpp:103
+    const uint32_t min_keep = (uint32_t) (3 + out->li_kmer_length);  // LI_KMER_INTERVALS (Params.cpp:706) + LI_KMER_LENGTH
+    out->n_records[0] = info.n_records[0], out->n_records[1] = info.n_records[1];
+    out->n_with_n = info.n_with_n, out->n_str = info.n_str;
+    out->n_reads_in = fe.n;
+    // main.cpp:132-140 -- duplicates / prefix reads
+    if (dp->remove_type) CKR(fe_prefix_reads(fe, dp->remove_type, cfg));
+    CK(cudaStreamSynchronize(0));
+    const double t2 = now_ms();
+    // main.cpp:150-232 (+ 253-266: reads too short for the graph creators become nullptr)
+    CKR(fe_remap(fe, fe.raw(), dp->remove_type ? fe.mask.as<uint8_t>() : nullptr, fe.stride, min_keep, cfg));
+    CK(cudaStreamSynchronize(0));
+    const double t3 = now_ms();
+    if (out->min_overlap < 1) {  // no read survived the reader: nothing to build
+        CKR(fe_download(fe, true, &out->reads));
+        out->graph.row_off = (uint64_t *) calloc(1, 8);
+        return out->graph.row_off ? ALGA_OK : fail(ALGA_E_NOMEM, "host allocation failed");
+    }
+    // main.cpp:249-291 -- GraphCreatorPrefSuf + retainOnlySmallestOffset on the device-resident reads
+    alga_ps_params pp{};
+    pp.min_overlap = out->min_overlap, pp.rs_min_overlap = out->rs_min_overlap, pp.min_offset = 0, pp.max_len_cap = 500;
+    pp.device = dp->input.device;
+    if (g_build_plan && g_build_plan->params.device != pp.device) {
+        alga_ps_plan_destroy(g_build_plan);
+        g_build_plan = nullptr;
+    }
+    if (!g_build_plan) CKR(alga_ps_plan_create(&g_build_plan, &pp));
+    g_build_plan->params = pp;
+    CKR(fe.words2.ensure((size_t) (fe.n2 ? fe.n2 : 1) * fe.stride2 * 4));
+    CKR(fe.len2.ensure((size_t) (fe.n2 ? fe.n2 : 1) * 4));
+    alga_reads dr{};
+    dr.n_reads = fe.n2, dr.words = fe.words2.as<uint32_t>(), dr.stride_words = fe.stride2, dr.len_nt = fe.len2.as<uint32_t>();
+    CKR(alga_ps_plan_bind_reads_device(g_build_plan, &dr, 0));
+    CKR(alga_ps_plan_run(g_build_plan, nullptr));
+    const double t4 = now_ms();
+    CKR(alga_ps_plan_result_host_pinned(g_build_plan, &out->graph));
+    CKR(fe_download(fe, true, &out->reads));
+    const double t5 = now_ms();
+    if (timing) {
+        alga_ps_plan_stats(g_build_plan, timing);
+        const double graph_dev_ms = timing->device_ms;
+        timing->kernel_launches += launches;
+        timing->h2d_ms = tm.h2d_ms;
+        timing->d2h_ms = t5 - t4;
+        timing->total_ms = t5 - t0;
+        timing->device_ms = (t4 - t0) - tm.h2d_ms;  // text resident -> CSR resident, all stages
+        timing->stage_ms[0] = tm.kernel_ms;      // reader
+        timing->stage_ms[1] = t2 - t1;           // prefix reads
+        timing->stage_ms[2] = t3 - t2;           // renumbering
+        timing->stage_ms[3] = graph_dev_ms;      // GraphCreatorPrefSuf pipeline (CUDA events)
+        timing->stage_ms[4] = (t4 - t3) - graph_dev_ms;  // bind + host side of the graph build
+        timing->stage_ms[5] = timing->stage_ms[6] = timing->stage_ms[7] = 0;
     }
     return ALGA_OK;
 }

@@ -122,6 +122,7 @@ struct InputScalars {
     uint32_t max_len;
     uint32_t pad;
     unsigned long long n_with_n, n_str;
+    unsigned long long sum_len, n_alive;  // over the records that became reads (Global::calculateAvgReadLength, Global.h:133-145)
 };
 
 // first position in [from, to) whose byte satisfies pred, or `to`; all 32 lanes call it with the same arguments
@@ -215,10 +216,15 @@ __global__ void __launch_bounds__(256) scan_records_kernel(const uint8_t *__rest
 
 // totals over the records that are actually read (r < n_rec)
 __global__ void record_totals_kernel(const RecInfo *__restrict__ info, uint32_t n_rec, InputScalars *__restrict__ sc) {
-    uint32_t mx = 0, cn = 0, cs = 0;
+    uint32_t mx = 0, cn = 0, cs = 0, ca = 0;
+    unsigned long long sum = 0;
     for (uint64_t r = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; r < n_rec; r += (uint64_t) gridDim.x * blockDim.x) {
         const RecInfo x = info[r];
-        if (x.status == 0) mx = x.len > mx ? x.len : mx;
+        if (x.status == 0) {
+            mx = x.len > mx ? x.len : mx;
+            sum += x.len;
+            ca++;
+        }
         cn += (x.status & kRecHasN) ? 1u : 0u;
         cs += (x.status & kRecStr) ? 1u : 0u;
     }
@@ -228,11 +234,17 @@ __global__ void record_totals_kernel(const RecInfo *__restrict__ info, uint32_t 
         mx = o > mx ? o : mx;
         cn += __shfl_xor_sync(kFull, cn, d);
         cs += __shfl_xor_sync(kFull, cs, d);
+        ca += __shfl_xor_sync(kFull, ca, d);
+        sum += __shfl_xor_sync(kFull, sum, d);
     }
     if ((threadIdx.x & 31) == 0) {
         if (mx) atomicMax(&sc->max_len, mx);
         if (cn) atomicAdd(&sc->n_with_n, (unsigned long long) cn);
         if (cs) atomicAdd(&sc->n_str, (unsigned long long) cs);
+        if (ca) {
+            atomicAdd(&sc->n_alive, (unsigned long long) ca);
+            atomicAdd(&sc->sum_len, sum);
+        }
     }
 }
 
@@ -312,7 +324,7 @@ __global__ void remap_flags_kernel(ReadsDev R, const uint8_t *__restrict__ mask,
 __global__ void remap_scatter_kernel(ReadsDev R, uint32_t n_units, const uint32_t *__restrict__ flag,
                                      const uint32_t *__restrict__ pos, uint32_t stride, uint32_t *__restrict__ words,
                                      uint32_t *__restrict__ len_out, uint32_t *__restrict__ old_id,
-                                     uint8_t *__restrict__ paired_offset) {
+                                     uint8_t *__restrict__ paired_offset, uint32_t min_keep_len) {
     const uint64_t per_unit = 2ull * stride, total = (uint64_t) n_units * per_unit;
     for (uint64_t idx = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; idx < total; idx += (uint64_t) gridDim.x * blockDim.x) {
         const uint32_t u = (uint32_t) (idx / per_unit);
@@ -321,9 +333,9 @@ __global__ void remap_scatter_kernel(ReadsDev R, uint32_t n_units, const uint32_
         const uint32_t src = 2u * u + k;
         const uint64_t dst = 2ull * pos[u] + k;
         const uint32_t len = R.len[src];
-        words[dst * stride + w] = w < (len + 15u) / 16u ? read_ptr(R, src)[w] : 0u;
+        words[dst * stride + w] = (w < (len + 15u) / 16u && len >= min_keep_len) ? read_ptr(R, src)[w] : 0u;
         if (w == 0) {
-            len_out[dst] = len;
+            len_out[dst] = len < min_keep_len ? 0u : len;  // main.cpp:253-266: too short for the graph creators -> nullptr
             old_id[dst] = src;
             // Global::pairedReadOffset (:176-197): 1 / 2 for the first / second mate when both survive, else 0
             uint8_t po = 0;
@@ -403,11 +415,11 @@ void launch_remap_flags(const ReadsDev &R, const uint8_t *mask, uint32_t n_units
 }
 
 void launch_remap_scatter(const ReadsDev &R, uint32_t n_units, const uint32_t *flag, const uint32_t *pos, uint32_t stride,
-                          uint32_t *words, uint32_t *len_out, uint32_t *old_id, uint8_t *paired_offset, cudaStream_t s,
-                          const LaunchCfg &cfg) {
+                          uint32_t *words, uint32_t *len_out, uint32_t *old_id, uint8_t *paired_offset, uint32_t min_keep_len,
+                          cudaStream_t s, const LaunchCfg &cfg) {
     if (!n_units) return;
     remap_scatter_kernel<<<grid_for((uint64_t) n_units * 2 * stride, 256, cfg, 16), 256, 0, s>>>(R, n_units, flag, pos, stride, words,
-                                                                                                len_out, old_id, paired_offset);
+                                                                                                len_out, old_id, paired_offset, min_keep_len);
     if (cfg.launches) *cfg.launches += 1;
 }
 

@@ -150,7 +150,7 @@ size_t input_scalars_bytes();
 void launch_count_marks(const uint8_t *text, uint64_t n, bool plain, uint32_t *block_cnt, cudaStream_t s, const LaunchCfg &cfg);
 void launch_write_marks(const uint8_t *text, uint64_t n, bool plain, const uint64_t *block_off, uint32_t lines_per_record,
                         uint64_t *rec_start, uint64_t n_cand, cudaStream_t s, const LaunchCfg &cfg);
-// scalars (input_scalars_bytes()): u32 first_empty = first_bad = 0xFFFFFFFF, u32 max_len = 0, u32 pad, u64 n_with_n = n_str = 0
+// scalars (input_scalars_bytes()): u32 first_empty = first_bad = 0xFFFFFFFF, u32 max_len = 0, u32 pad, u64 n_with_n = n_str = sum_len = n_alive = 0
 void launch_scan_records(const uint8_t *text, uint64_t n, bool plain, const uint64_t *rec_start, uint32_t n_cand, int trim_left,
                          int trim_right, int rna, int str_threshold, void *info, void *scalars, cudaStream_t s,
                          const LaunchCfg &cfg);
@@ -161,8 +161,8 @@ void launch_pack_records(const uint8_t *text, const void *info, uint32_t n_rec, 
 void launch_remap_flags(const ReadsDev &R, const uint8_t *mask, uint32_t n_units, uint32_t *flag, void *scalars, cudaStream_t s,
                         const LaunchCfg &cfg);
 void launch_remap_scatter(const ReadsDev &R, uint32_t n_units, const uint32_t *flag, const uint32_t *pos, uint32_t stride,
-                          uint32_t *words, uint32_t *len_out, uint32_t *old_id, uint8_t *paired_offset, cudaStream_t s,
-                          const LaunchCfg &cfg);
+                          uint32_t *words, uint32_t *len_out, uint32_t *old_id, uint8_t *paired_offset, uint32_t min_keep_len,
+                          cudaStream_t s, const LaunchCfg &cfg);
 
 // --- error-rate supplement (supplement.cu) -------------------------------------------------------
 // LI k-mers (Read.cpp:145-226) of the reads d_ids[0 .. n_ids): `intervals` slots per read, ind = -1 where absent

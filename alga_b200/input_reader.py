@@ -10,7 +10,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from .graph_creator import Graph, GraphCreatorPrefSuf, ReadPreprocess
+from .graph_creator import Graph, GraphCreatorPrefSuf, ReadPreprocess, _csr_to_graph, _PinnedArray
 from .readset import ReadSet
 
 PLAIN, FASTA, FASTQ = _lib.INPUT_PLAIN, _lib.INPUT_FASTA, _lib.INPUT_FASTQ
@@ -109,11 +109,56 @@ class OverlapGraph:
     timing: dict
 
 
-def build_overlap_graph(text1: bytes, text2: bytes | None = None, file_type: int = FASTA, device: int = 0,
-                        remove_type: int = 2) -> OverlapGraph:
-    """The reference driver from the input files to the overlap graph (main.cpp:82-291): InputReader::readInput,
-    parameter derivation, ReadPreprocess::getPrefixReads + removal, renumbering, the short-read rule of main.cpp:253-266
-    and GraphCreatorPrefSuf + retainOnlySmallestOffset -- every step on the GPU."""
+class PinnedText:
+    """The bytes of an input file in page-locked memory (``alga_gpu_host_alloc``) -- where a caller that cares about the
+    upload rate reads its file to."""
+
+    def __init__(self, data: bytes):
+        src = np.frombuffer(data, np.uint8)
+        self.size = int(src.size)
+        self._pin = _PinnedArray(src if src.size else np.zeros(1, np.uint8))
+        self.array = self._pin.array
+
+
+def _text_ptr(t, keep):
+    if t is None:
+        return None, 0
+    if isinstance(t, PinnedText):
+        return t.array.ctypes.data, t.size
+    a = np.frombuffer(t, np.uint8)
+    return (a.ctypes.data if a.size else C.addressof(keep)), int(a.size)
+
+
+def build_overlap_graph(text1, text2=None, file_type: int = FASTA, device: int = 0, remove_type: int = 2,
+                        min_overlap: int = 0, rs_min_overlap: int = 0) -> OverlapGraph:
+    """The reference driver from the input files to the overlap graph (main.cpp:82-291) in ONE call of the C ABI
+    (``alga_gpu_files_to_graph``): reader, parameter derivation, ReadPreprocess::getPrefixReads + removal, renumbering,
+    the short-read rule of main.cpp:253-266, GraphCreatorPrefSuf + retainOnlySmallestOffset -- all on the GPU, the read
+    set device-resident between the stages.  ``text1`` / ``text2``: ``bytes`` or ``PinnedText``."""
+    lib = _lib.load()
+    keep = C.create_string_buffer(1)
+    p1, n1 = _text_ptr(text1, keep)
+    p2, n2 = _text_ptr(text2, keep)
+    dp = _lib.DriverParams(_lib.InputParams(file_type, 3, 3, 0, 20, device), remove_type, 0.55, min_overlap, rs_min_overlap)
+    out, tm = _lib.OverlapGraphOut(), _lib.Timing()
+    _lib.check(lib.alga_gpu_files_to_graph(p1, n1, p2, n2, C.byref(dp), C.byref(out), C.byref(tm)))
+    try:
+        graph = _csr_to_graph(out.graph)
+    finally:
+        lib.alga_gpu_free_csr(C.byref(out.graph))
+    params = {"min_overlap": out.min_overlap, "rs_min_overlap": out.rs_min_overlap, "li_kmer_length": out.li_kmer_length,
+              "li_kmer_intervals": 3, "avg_len": out.avg_len, "n_reads_in": out.n_reads_in,
+              "n_records": (out.n_records[0], out.n_records[1]), "n_with_n": out.n_with_n, "n_str": out.n_str}
+    timing = _timing(tm)
+    timing["stage_ms"] = dict(zip(("read_input", "prefix_reads", "remap", "prefsuf_device", "prefsuf_host"), list(tm.stage_ms)[:5]))
+    rs, old, po, _ = _take(out.reads)
+    return OverlapGraph(rs, graph, po, params, timing, old)
+
+
+def build_overlap_graph_staged(text1: bytes, text2: bytes | None = None, file_type: int = FASTA, device: int = 0,
+                               remove_type: int = 2) -> OverlapGraph:
+    """The same path as ``build_overlap_graph`` composed from the separate entry points (host buffers between the
+    stages) -- the form a driver that keeps its own ``vector<Read*>`` would use; also the cross-check of the fused call."""
     reader = InputReader(file_type, device=device)
     rs = reader.readInput(text1, text2)
     timing = {"read_input": reader.timing}
@@ -130,4 +175,4 @@ def build_overlap_graph(text1: bytes, text2: bytes | None = None, file_type: int
     gc = GraphCreatorPrefSuf(final, params["min_overlap"], params["rs_min_overlap"], device=device)
     graph = gc.startAlignmentGraphCreation()
     timing["prefsuf"] = gc.timing
-    return OverlapGraph(final, graph, rm.paired_offset, params, timing)
+    return OverlapGraph(final, graph, rm.paired_offset, params, timing, rm.old_id)

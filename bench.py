@@ -459,13 +459,26 @@ def run_ours(args):
         nbytes = len(t1) + (len(t2) if t2 is not None else 0)
         input_leg = {"ms": ms, "records": n_rec, "reads": rs_in.n, "file_bytes": nbytes, **rd.timing, **rd.info,
                      "records_per_s": n_rec / (ms / 1e3), "call": "alga_gpu_read_input (host buffers)"}
-        build_overlap_graph(t1, t2, FASTA, device=local)
-        ts = time.perf_counter()
-        og = build_overlap_graph(t1, t2, FASTA, device=local)
-        msg = 1e3 * (time.perf_counter() - ts)
-        input_leg["files_to_graph"] = {"ms": msg, "nodes": og.reads.n, "edges": og.graph.n_edges, "params": og.params,
-                                       "stages": {k: (v or {}).get("total_ms") for k, v in og.timing.items()},
-                                       "call": "alga_b200.input_reader.build_overlap_graph (main.cpp:82-291 through the C ABI)"}
+        from alga_b200.input_reader import PinnedText
+        p1, p2 = PinnedText(t1), (PinnedText(t2) if t2 is not None else None)  # the files read into page-locked memory
+        for _ in range(2):
+            build_overlap_graph(p1, p2, FASTA, device=local)
+        best = None
+        for _ in range(3):
+            ts = time.perf_counter()
+            og = build_overlap_graph(p1, p2, FASTA, device=local)
+            msg = 1e3 * (time.perf_counter() - ts)
+            if best is None or og.timing["total_ms"] < best[1].timing["total_ms"]:
+                best = (msg, og)
+        msg, og = best
+        input_leg["files_to_graph"] = {"ms_python": msg, "nodes": og.reads.n, "edges": og.graph.n_edges, "params": og.params,
+                                       **og.timing, "records_per_s": n_rec / (og.timing["total_ms"] / 1e3),
+                                       "h2d_bytes": nbytes, "d2h_bytes": int(og.reads.words.nbytes + og.reads.len_nt.nbytes * 2 + og.reads.n
+                                                                          + og.graph.n_edges * 8 + (og.reads.n + 1) * 8),
+                                       "call": "alga_gpu_files_to_graph (main.cpp:82-291 in one call, file text in page-locked memory)"}
+        og2 = build_overlap_graph(t1, t2, FASTA, device=local)
+        input_leg["files_to_graph_pageable"] = {"total_ms": og2.timing["total_ms"], "h2d_ms": og2.timing["h2d_ms"],
+                                                "note": "same call, file text in ordinary (pageable) memory: upload through page-locked chunks"}
         from oracle import harness as _h
         if _h.available() and not args.no_cpu:
             k = max(1, m1.shape[0] // 8)

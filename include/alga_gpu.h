@@ -279,7 +279,7 @@ typedef struct {
 } alga_input_params;
 
 /* A read set produced by the library: fixed stride, read i = words[i * stride_words ...], len_nt[i] == 0 = nullptr.
- * Host arrays, malloc'ed by the library; release with alga_gpu_free_read_set. */
+ * Host arrays owned by the library (page-locked staging, see `borrowed`); release with alga_gpu_free_read_set. */
 typedef struct {
     uint32_t n_reads;
     uint32_t stride_words;  /* ceil(max_len_nt / 16), at least 1 */
@@ -291,10 +291,13 @@ typedef struct {
     uint64_t n_records[2];  /* alga_gpu_read_input: records read from file 1 / file 2 */
     uint64_t n_with_n;      /* ... records dropped because of an N ("Nreads", InputReader.cpp:346) */
     uint64_t n_str;         /* ... records dropped as short-period repeats ("STRreads", InputReader.cpp:352) */
+    int32_t borrowed;       /* != 0: the arrays are page-locked staging buffers owned by the library, valid until the next
+                               call of the function that produced them; alga_gpu_free_read_set then only clears them */
 } alga_read_set;
 
-/* text1 / text2: the bytes of --file1 / --file2 (text2 may be NULL: single-end).  timing (may be NULL): h2d_ms, device_ms,
- * d2h_ms, total_ms, kernel_launches. */
+/* text1 / text2: the bytes of --file1 / --file2 (text2 may be NULL: single-end).  Text in a buffer from
+ * alga_gpu_host_alloc is uploaded at the full host->device rate; any other buffer goes through page-locked chunks.
+ * timing (may be NULL): h2d_ms, device_ms, d2h_ms, total_ms, kernel_launches. */
 int alga_gpu_read_input(const uint8_t *text1, uint64_t n1, const uint8_t *text2, uint64_t n2,
                         const alga_input_params *params, alga_read_set *out, alga_timing *timing);
 
@@ -305,6 +308,35 @@ int alga_gpu_read_input(const uint8_t *text1, uint64_t n1, const uint8_t *text2,
 int alga_gpu_remap_reads(const alga_reads *reads, const uint8_t *remove_mask, int32_t device, alga_read_set *out,
                          alga_timing *timing);
 void alga_gpu_free_read_set(alga_read_set *rs);
+
+/* ---- from the input files to the overlap graph in one call ------------------------------------------------------
+ * The reference driver between main.cpp:82 and main.cpp:291 with every stage on the GPU and nothing but scalars coming
+ * back in between: InputReader::readInput (:82), the parameters derived from the average read length (:93-110),
+ * ReadPreprocess::getPrefixReads + Global::removeRead (:132-140), the renumbering (:150-232), the removal of reads too
+ * short for the graph creators (:253-266), GraphCreatorPrefSuf::startAlignmentGraphCreation and
+ * Graph::retainOnlySmallestOffset (:249-291).  What the rest of the driver needs comes back: Global::READS with
+ * Global::pairedReadOffset, and Global::GRAPH. */
+typedef struct {
+    alga_input_params input;
+    int32_t remove_type;    /* Params::REMOVE_PREF_READS_TYPE: 0 none, 1 duplicates only, 2 all prefix reads (the default) */
+    float scale;            /* Params::SCALE (0.55); <= 0 means 0.55 */
+    int32_t min_overlap;    /* Params::MOST_FREQUENTLY_USED_PARAMETER (-l): > 0 overrides the derived minimum overlap */
+    int32_t rs_min_overlap; /* > 0 overrides Params::REMOVE_SMALL_OVERLAP_EDGES_MIN_OVERLAP */
+} alga_driver_params;
+typedef struct {
+    alga_read_set reads;    /* Global::READS at main.cpp:282 (old_id: id after the reader; paired_offset filled) */
+    alga_csr graph;         /* Global::GRAPH after main.cpp:291 */
+    double avg_len;         /* Global::calculateAvgReadLength() at main.cpp:93 */
+    int32_t min_overlap, rs_min_overlap, li_kmer_length; /* the Params the driver derived (main.cpp:99-108) */
+    uint32_t n_reads_in;    /* reads (both strands, nullptr included) the reader produced */
+    uint64_t n_records[2], n_with_n, n_str; /* as in alga_read_set after alga_gpu_read_input */
+} alga_overlap_graph;
+/* timing (may be NULL): h2d_ms (file text), device_ms (text resident -> CSR resident), d2h_ms (graph + reads), total_ms,
+ * stage_ms[0..4] = reader, prefix reads, renumbering, graph build on the device (CUDA events), its host side.
+ * out->reads and out->graph are borrowed page-locked buffers (valid until the next call); release both with
+ * alga_gpu_free_read_set / alga_gpu_free_csr. */
+int alga_gpu_files_to_graph(const uint8_t *text1, uint64_t n1, const uint8_t *text2, uint64_t n2,
+                            const alga_driver_params *params, alga_overlap_graph *out, alga_timing *timing);
 
 /* ---- misc ---------------------------------------------------------------------------------- */
 /* Page-locked host memory for callers that stage the packed reads themselves (the shim gathers the blocks of

@@ -263,7 +263,7 @@ def input_case(name):
     raise KeyError(name)
 
 
-FRONT_CASES = ["front_se", "front_pe"]
+FRONT_CASES = ["front_se", "front_pe", "front_short"]
 
 
 def front_case(name):
@@ -282,4 +282,11 @@ def front_case(name):
         s1 = _spice([cut(r) for r in m1], rng, p_short=0.0, p_space=0.0)
         s2 = _spice([cut(r) for r in m2], rng, p_short=0.0, p_space=0.0)
         return _fasta(s1), _fasta(s2, b"m"), INPUT_FASTA
+    if name == "front_short":       # a few reads shorter than LI_KMER_INTERVALS + LI_KMER_LENGTH: removed at main.cpp:253-266
+        g = synth.make_genome(12_000, rng)
+        m = synth.sample_single_end(g, 100, 25, rng, 0.0)
+        seqs = [_seq(r) for r in m]
+        for k in range(0, len(seqs), 23):
+            seqs[k] = seqs[k][: int(rng.integers(24, 44))]
+        return _fasta(seqs), None, INPUT_FASTA
     raise KeyError(name)

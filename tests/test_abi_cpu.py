@@ -37,7 +37,9 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Timing) == 48 + 64
     assert C.sizeof(_lib.VerifyParams) == 24
     assert C.sizeof(_lib.InputParams) == 24
-    assert C.sizeof(_lib.ReadSetOut) == 80
+    assert C.sizeof(_lib.ReadSetOut) == 88
+    assert C.sizeof(_lib.DriverParams) == 40
+    assert C.sizeof(_lib.OverlapGraphOut) == 192
 
 
 def test_version_and_error_strings():

@@ -8,33 +8,39 @@ import numpy as np
 import pytest
 
 from alga_b200 import _lib, synth
-from alga_b200.input_reader import FASTA, FASTQ, InputReader, build_overlap_graph, remap_reads
+from alga_b200.input_reader import (FASTA, FASTQ, InputReader, PinnedText, build_overlap_graph, build_overlap_graph_staged,
+                                    remap_reads)
 from alga_b200.readset import ReadSet
 from oracle import oracle
 from tests.cases import FRONT_CASES, INPUT_CASES, PREPROCESS_CASES, _fasta, _seq, front_case, input_case, preprocess_case
-from tests.test_input_cpu import gather
+from tests.test_input_cpu import gather, oracle_front
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def words_of(rs: ReadSet, i: int) -> np.ndarray:
-    return rs.words[int(rs.word_off[i]): int(rs.word_off[i]) + (int(rs.len_nt[i]) + 15) // 16]
+def dense(len_nt, word_off, words, width=None):
+    """(n, width) matrix of the blocks of every read, zero behind its last block; removed reads (length 0) are all zero."""
+    n = len_nt.shape[0]
+    cnt = (len_nt.astype(np.int64) + 15) // 16
+    width = int(cnt.max()) if width is None and n else (width or 1)
+    m = np.zeros((n, max(width, 1)), np.uint32)
+    col = np.arange(m.shape[1])[None, :]
+    sel = col < cnt[:, None]
+    src = (word_off[:-1].astype(np.int64)[:, None] + col)[sel]
+    m[sel] = words[src]
+    return m
 
 
 def assert_same_reads(got: ReadSet, len_nt, word_off, words):
-    """`got` has a fixed stride, the reference side ragged offsets: compare read by read, and the padding must be zero."""
+    """`got` has a fixed stride, the reference side ragged offsets: lengths equal, blocks equal, padding zero."""
     assert got.n == len_nt.shape[0]
     assert np.array_equal(got.len_nt, len_nt)
     if got.n == 0:
         return
     stride = int(got.word_off[1] - got.word_off[0])
-    m = got.words.reshape(got.n, stride)
-    cnt = (len_nt.astype(np.int64) + 15) // 16
-    col = np.arange(stride)[None, :]
-    assert not m[col >= cnt[:, None]].any(), "blocks behind the end of a read must be zero"
-    flat = m[col < cnt[:, None]]
-    assert np.array_equal(flat, words)
+    assert stride >= max(1, (int(len_nt.max()) + 15) // 16)
+    assert np.array_equal(got.words.reshape(got.n, stride), dense(len_nt, word_off, words, stride))
 
 
 @pytest.mark.parametrize("name", INPUT_CASES)
@@ -155,10 +161,34 @@ def test_remap_edge_cases(gpu):
 
 
 @pytest.mark.parametrize("name", FRONT_CASES)
-def test_files_to_graph_matches_stock_binary(gpu, name):
+@pytest.mark.parametrize("how", ["fused", "fused_pinned", "staged"])
+def test_files_to_graph_matches_stock_binary(gpu, name, how):
     """main.cpp:82-291 on the GPU end to end: same node count and edge set as the graph the stock binary serialised."""
     t1, t2, ft = front_case(name)
     g = np.load(os.path.join(GOLD, f"{name}.npz"))
-    og = build_overlap_graph(t1, t2, ft)
+    if how == "staged":
+        og = build_overlap_graph_staged(t1, t2, ft)
+    elif how == "fused_pinned":
+        og = build_overlap_graph(PinnedText(t1), PinnedText(t2) if t2 is not None else None, ft)
+    else:
+        og = build_overlap_graph(t1, t2, ft)
     assert og.reads.n == int(g["n"])
     assert np.array_equal(og.graph.edges(), g["edges"])
+
+
+@pytest.mark.parametrize("name", ["in_fasta_se", "in_fasta_pe", "in_fastq_pe", "in_long", "in_no_eol", "in_truncated", "in_empty"])
+def test_files_to_graph_matches_oracle_pipeline(gpu, name):
+    """The fused call against the same path composed from the oracle's pieces: renumbered reads, pairedReadOffset, the
+    removal of short reads, parameters and the edge set (inputs with N reads, repeats, short reads, ragged lengths)."""
+    t1, t2, ft, _ = input_case(name)
+    og = build_overlap_graph(t1, t2, ft)
+    raw, _ = oracle.read_input(t1, t2, ft)
+    if raw.n == 0 or not (raw.len_nt > 0).any():
+        assert og.reads.n == 0 and og.graph.n_edges == 0
+        return
+    rs, po, edges = oracle_front(t1, t2, ft)
+    assert_same_reads(og.reads, rs.len_nt, rs.word_off, rs.words)
+    assert np.array_equal(og.paired_offset, po)
+    assert np.array_equal(og.graph.edges(), edges)
+    old, _ = oracle.remap(raw.len_nt, oracle.prefix_reads(raw, 2))
+    assert np.array_equal(og.old_id, old)
