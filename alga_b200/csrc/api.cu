@@ -1274,6 +1274,7 @@ struct FrontEnd {
     InputFile f[2];
     HostBuf stage[2];  // chunked upload of text that is not page-locked
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    bool stage_used[2] = {false, false};
     cudaEvent_t ev[2] = {nullptr, nullptr};
     // reader output: Global::READS after InputReader::readInput
     DevBuf words, len;
@@ -1310,6 +1311,7 @@ struct FrontEnd {
             if (*e) cudaEventDestroy(*e);
             *e = nullptr;
         }
+        stage_used[0] = stage_used[1] = false;
     }
 };
 
@@ -1337,7 +1339,8 @@ int fe_upload_text(FrontEnd &fe, DevBuf &dst, const uint8_t *src, uint64_t n) {
     int k = 0;
     for (uint64_t off = 0; off < n; off += kStageChunk, k ^= 1) {
         const size_t len = (size_t) (n - off < kStageChunk ? n - off : kStageChunk);
-        if (off >= 2 * kStageChunk) CK(cudaEventSynchronize(fe.stage_ev[k]));
+        if (fe.stage_used[k]) CK(cudaEventSynchronize(fe.stage_ev[k]));  // the DMA out of this chunk must be done
+        fe.stage_used[k] = true;
         memcpy(fe.stage[k].p, src + off, len);
         CK(cudaMemcpyAsync((char *) dst.p + off, fe.stage[k].p, len, cudaMemcpyHostToDevice, 0));
         CK(cudaEventRecord(fe.stage_ev[k], 0));

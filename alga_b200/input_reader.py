@@ -107,6 +107,7 @@ class OverlapGraph:
     paired_offset: np.ndarray
     params: dict
     timing: dict
+    old_id: np.ndarray | None = None  # id of every read before the renumbering (i.e. in the reader's output)
 
 
 class PinnedText:
