@@ -1260,11 +1260,11 @@ struct InputScalarsHost {  // layout of input.cu's InputScalars
 };
 
 struct InputFile {
-    DevBuf text, block_cnt, block_off, rec_start, info, scalars;
+    DevBuf text, block_cnt, block_off, rec_start, rec_end, info, scalars;
     uint64_t n = 0;
     uint32_t n_rec = 0;
     InputScalarsHost sc{};
-    void release() { text.release(), block_cnt.release(), block_off.release(), rec_start.release(), info.release(), scalars.release(); }
+    void release() { text.release(), block_cnt.release(), block_off.release(), rec_start.release(), rec_end.release(), info.release(), scalars.release(); }
 };
 
 // Device-resident working set of the input stage.  One process-wide instance is kept between calls (as the one-call graph
@@ -1375,10 +1375,13 @@ int fe_scan_file(FrontEnd &fe, InputFile &f, uint64_t n, const alga_input_params
     f.sc = init;
     if (!n_cand) return ALGA_OK;
     CKR(f.rec_start.ensure((size_t) n_cand * 8));
+    CKR(f.rec_end.ensure((size_t) n_cand * 8));
     CKR(f.info.ensure((size_t) n_cand * input_rec_info_bytes()));
-    launch_write_marks(f.text.as<uint8_t>(), n, plain, f.block_off.as<uint64_t>(), lpr, f.rec_start.as<uint64_t>(), n_cand, 0, cfg);
-    launch_scan_records(f.text.as<uint8_t>(), n, plain, f.rec_start.as<uint64_t>(), (uint32_t) n_cand, p.trim_left, p.trim_right,
-                        p.rna != 0, p.str_threshold > 0 ? p.str_threshold : 20, f.info.p, f.scalars.p, 0, cfg);
+    launch_write_marks(f.text.as<uint8_t>(), n, plain, f.block_off.as<uint64_t>(), lpr, f.rec_start.as<uint64_t>(),
+                       f.rec_end.as<uint64_t>(), n_cand, 0, cfg);
+    launch_scan_records(f.text.as<uint8_t>(), n, plain, f.rec_start.as<uint64_t>(), f.rec_end.as<uint64_t>(), n_marks, lpr,
+                        (uint32_t) n_cand, p.trim_left, p.trim_right, p.rna != 0, p.str_threshold > 0 ? p.str_threshold : 20, f.info.p,
+                        f.scalars.p, 0, cfg);
     CK(cudaGetLastError());
     CK(cudaMemcpy(&f.sc, f.scalars.p, sizeof(f.sc), cudaMemcpyDeviceToHost));
     f.n_rec = f.sc.first_empty < n_cand ? f.sc.first_empty : (uint32_t) n_cand;

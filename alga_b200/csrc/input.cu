@@ -87,11 +87,13 @@ __global__ void __launch_bounds__(kMarkThreads) count_marks_kernel(const uint8_t
     if (threadIdx.x == 0) block_cnt[blockIdx.x] = total;
 }
 
-// rec_start[r] = first byte of the sequence of record r
+// rec_start[r] = first byte of the sequence of record r; rec_end[r] = the line end behind it (mark lpr * r + 1, if the
+// file has one; not written for plain input)
 template <bool PLAIN>
 __global__ void __launch_bounds__(kMarkThreads) write_marks_kernel(const uint8_t *__restrict__ text, uint64_t n,
                                                                    const uint64_t *__restrict__ block_off, uint32_t lpr,
-                                                                   uint64_t *__restrict__ rec_start, uint64_t n_rec) {
+                                                                   uint64_t *__restrict__ rec_start,
+                                                                   uint64_t *__restrict__ rec_end, uint64_t n_rec) {
     const uint64_t base = (uint64_t) blockIdx.x * kMarkChunk + (uint64_t) threadIdx.x * 16u;
     uint32_t m = marks16<PLAIN>(text, n, base);
     uint32_t total;
@@ -101,9 +103,10 @@ __global__ void __launch_bounds__(kMarkThreads) write_marks_kernel(const uint8_t
         m &= m - 1;
         if (PLAIN) {
             if (k < n_rec) rec_start[k] = base + j;
-        } else if (k % lpr == 0) {
-            const uint64_t r = k / lpr;
-            if (r < n_rec) rec_start[r] = base + j + 1;
+        } else {
+            const uint64_t r = k / lpr, q = k - r * lpr;
+            if (q == 0 && r < n_rec) rec_start[r] = base + j + 1;
+            if (q == 1 && r < n_rec) rec_end[r] = base + j;
         }
         k++;
     }
@@ -115,6 +118,8 @@ struct __align__(16) RecInfo {
     uint32_t status;  // kRec* bits, 0 = a read
 };
 constexpr uint32_t kRecHasN = 1u, kRecStr = 2u, kRecEmpty = 4u, kRecBad = 8u;
+constexpr uint32_t kRecNull = 15u;  // any of the above: no read
+constexpr uint32_t kRecSlow = 16u;  // a read, but not one the word-parallel path handles (U, stripped spaces, > 512 nt)
 
 struct InputScalars {
     uint32_t first_empty;  // smallest record number whose sequence line is empty (reading stops there)
@@ -139,76 +144,183 @@ __device__ __forceinline__ uint64_t warp_find(const uint8_t *__restrict__ text, 
 
 __device__ __forceinline__ uint32_t sym_of(uint32_t c, int rna) { return (rna && c == 'U') ? (uint32_t) 'T' : c; }
 
+// ---- word-parallel helpers: 16 characters per lane ------------------------------------------------------------------
+// 16 bytes at an arbitrary address as four little-endian words (reads up to 7 bytes past them: the text buffer is padded)
+__device__ __forceinline__ void load16(const uint8_t *__restrict__ p, uint32_t (&c)[4]) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t) 3);
+    const uint32_t sh = (uint32_t) (a & 3u) * 8u;
+    uint32_t v[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) v[j] = __ldg(q + j);
+#pragma unroll
+    for (int j = 0; j < 4; j++) c[j] = __funnelshift_r(v[j], v[j + 1], sh);
+}
+// four characters -> four 2-bit codes (A 0, C 1, G 2, T 3) in the low byte; *bad gets a non-zero byte for every
+// character that is not A, C, G or T.  (c >> 1) & 3 maps A C T G to 0 1 2 3, "ACTG"[that] must give the character back.
+__device__ __forceinline__ uint32_t codes4(uint32_t c, uint32_t *bad) {
+    const uint32_t x = (c >> 1) & 0x03030303u;
+    uint32_t t = (x | (x >> 4)) & 0x00FF00FFu;
+    const uint32_t sel = (t | (t >> 8)) & 0xFFFFu;
+    *bad = __byte_perm(0x47544341u, 0u, sel) ^ c;
+    const uint32_t k = x ^ ((x >> 1) & 0x01010101u);
+    return (k | (k >> 6) | (k >> 12) | (k >> 18)) & 0xFFu;
+}
+// 16 characters -> one packed block; bad != 0 iff one of the first `cnt` characters is not A, C, G or T
+__device__ __forceinline__ uint32_t pack16(const uint32_t (&c)[4], uint32_t cnt, uint32_t *bad) {
+    uint32_t w = 0, b = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++) {
+        uint32_t bj;
+        w |= codes4(c[j], &bj) << (8u * j);
+        const uint32_t nv = cnt > 4u * j ? cnt - 4u * j : 0u;
+        b |= nv >= 4u ? bj : (bj & ((1u << (8u * nv)) - 1u));
+    }
+    *bad = b;
+    return cnt >= 16u ? w : (w & ((1u << (2u * cnt)) - 1u));
+}
+// order of the sixteen 2-bit fields reversed
+__device__ __forceinline__ uint32_t reverse_fields(uint32_t p) {
+    const uint32_t r = __brev(p);
+    return ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+}
+constexpr uint32_t kFastMaxLen = 512;  // one block per lane
+
+// The general form of one record (any length, spaces, N, U): sequential warp loops over the bytes.
+template <bool PLAIN>
+__device__ __forceinline__ void scan_record_generic(const uint8_t *__restrict__ text, uint64_t n, uint64_t start, uint32_t r,
+                                                    int trim_left, int trim_right, int rna, int str_threshold, int lane,
+                                                    RecInfo *__restrict__ info, InputScalars *__restrict__ sc) {
+    RecInfo out;
+    out.begin = start, out.len = 0, out.status = kRecEmpty;
+    // the sequence line / token (readOneRead1)
+    uint64_t end = PLAIN ? warp_find(text, start, n, lane, [](uint32_t c) { return is_space_c(c); })
+                         : warp_find(text, start, n, lane, [](uint32_t c) { return c == '\n'; });
+    if (end == start) {  // s == "": the reader stops here (InputReader.cpp:284)
+        if (lane == 0) {
+            atomicMin(&sc->first_empty, r);
+            info[r] = out;
+        }
+        return;
+    }
+    // :286-291 -- leading spaces off, cut at the next space
+    uint64_t b = start, e = end;
+    if (!PLAIN) {
+        b = warp_find(text, start, end, lane, [](uint32_t c) { return c != ' '; });
+        e = warp_find(text, b, end, lane, [](uint32_t c) { return c == ' '; });
+    }
+    // :298-303 -- end trimming unless the read is short
+    if (e - b >= (uint64_t) (trim_left + trim_right + 10)) {
+        b += (uint64_t) trim_left;
+        e -= (uint64_t) trim_right;
+    }
+    const uint64_t len64 = e - b;
+    // :316-334 -- characters
+    bool bad = false, has_n = false;
+    for (uint64_t i = lane; i < len64; i += 32) {
+        const uint32_t c = __ldg(text + b + i);
+        if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'N' && c != 'U') bad = true;
+        if (c == 'N') has_n = true;
+    }
+    bad = __any_sync(kFull, bad) || len64 > 0x7FFFFFFFull;
+    has_n = __any_sync(kFull, has_n);
+    uint32_t status = kRecSlow;
+    if (bad) {
+        status = kRecBad;
+        if (lane == 0) atomicMin(&sc->first_bad, r);
+    } else if (has_n) {
+        status = kRecHasN;
+    } else if (len64 == 0) {
+        status = kRecStr;  // an all-space line: MinPeriod("") is undefined in the reference; dropped
+    } else {
+        // :343-353 -- MinPeriod(s) <= threshold  <=>  some p <= min(threshold, len) has s[i] == s[i + p] for all i
+        const uint32_t len = (uint32_t) len64;
+        const uint32_t pmax = (uint32_t) str_threshold < len ? (uint32_t) str_threshold : len;
+        for (uint32_t p = 1; p <= pmax && status == kRecSlow; p++) {
+            bool periodic = true;
+            for (uint32_t i0 = 0; i0 + p < len; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                bool ok = true;
+                if (i + p < len) ok = sym_of(__ldg(text + b + i), rna) == sym_of(__ldg(text + b + i + p), rna);
+                if (!__all_sync(kFull, ok)) {
+                    periodic = false;
+                    break;
+                }
+            }
+            if (periodic) status = kRecStr;
+        }
+    }
+    if (lane == 0) {
+        out.begin = b, out.len = (uint32_t) len64, out.status = status;
+        info[r] = out;
+    }
+}
+
+// One warp per record.  FASTA / FASTQ records of up to 512 characters made of A, C, G, T only (practically all of
+// them) never loop over bytes: the line end is known from the marks, lane w loads characters 16w .. 16w+15 of the
+// trimmed sequence in one go, checks and packs them with word arithmetic, and the period test "s[i] == s[i+p] for all
+// i" becomes "(X >> 2p) xor X has no bit below 2 (len - p)" on the packed blocks X, one block per lane.
 template <bool PLAIN>
 __global__ void __launch_bounds__(256) scan_records_kernel(const uint8_t *__restrict__ text, uint64_t n,
-                                                           const uint64_t *__restrict__ rec_start, uint32_t n_cand,
-                                                           int trim_left, int trim_right, int rna, int str_threshold,
-                                                           RecInfo *__restrict__ info, InputScalars *__restrict__ sc) {
+                                                           const uint64_t *__restrict__ rec_start,
+                                                           const uint64_t *__restrict__ rec_end, uint64_t n_marks, uint32_t lpr,
+                                                           uint32_t n_cand, int trim_left, int trim_right, int rna,
+                                                           int str_threshold, RecInfo *__restrict__ info,
+                                                           InputScalars *__restrict__ sc) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t r = warp0; r < n_cand; r += n_warps) {
         const uint64_t start = rec_start[r];
-        RecInfo out;
-        out.begin = start, out.len = 0, out.status = kRecEmpty;
-        // the sequence line / token (readOneRead1)
-        uint64_t end = PLAIN ? warp_find(text, start, n, lane, [](uint32_t c) { return is_space_c(c); })
-                             : warp_find(text, start, n, lane, [](uint32_t c) { return c == '\n'; });
-        if (end == start) {  // s == "": the reader stops here (InputReader.cpp:284)
-            if (lane == 0) {
-                atomicMin(&sc->first_empty, r);
-                info[r] = out;
+        bool fast = !PLAIN && trim_left <= 32 && trim_right <= 32 && str_threshold <= 31;  // 2p < 64: two neighbour blocks suffice
+        uint64_t b = start;
+        uint32_t len = 0, x = 0;
+        if (fast) {
+            const uint64_t end = ((uint64_t) lpr * r + 1 < n_marks) ? rec_end[r] : n;
+            const uint64_t raw = end - start;
+            fast = raw > 0 && raw <= kFastMaxLen;
+            if (fast) {
+                const bool trimmed = raw >= (uint64_t) (trim_left + trim_right + 10);
+                b = start + (trimmed ? (uint64_t) trim_left : 0);
+                len = (uint32_t) raw - (trimmed ? (uint32_t) (trim_left + trim_right) : 0u);
+                bool odd = false;  // a space in the trimmed-away ends moves the token (InputReader.cpp:286-291): general form
+                if (trimmed) {
+                    if (lane < trim_left) odd |= __ldg(text + start + lane) == ' ';
+                    if (lane < trim_right) odd |= __ldg(text + end - 1 - lane) == ' ';
+                }
+                const uint32_t cnt = len > 16u * lane ? min(16u, len - 16u * lane) : 0u;
+                if (cnt) {
+                    uint32_t c[4], bad;
+                    load16(text + b + 16u * lane, c);
+                    x = pack16(c, cnt, &bad);
+                    odd |= bad != 0;
+                }
+                fast = !__any_sync(kFull, odd);
             }
+        }
+        if (!fast) {
+            scan_record_generic<PLAIN>(text, n, start, r, trim_left, trim_right, rna, str_threshold, lane, info, sc);
             continue;
         }
-        // :286-291 -- leading spaces off, cut at the next space
-        uint64_t b = start, e = end;
-        if (!PLAIN) {
-            b = warp_find(text, start, end, lane, [](uint32_t c) { return c != ' '; });
-            e = warp_find(text, b, end, lane, [](uint32_t c) { return c == ' '; });
-        }
-        // :298-303 -- end trimming unless the read is short
-        if (e - b >= (uint64_t) (trim_left + trim_right + 10)) {
-            b += (uint64_t) trim_left;
-            e -= (uint64_t) trim_right;
-        }
-        const uint64_t len64 = e - b;
-        // :316-334 -- characters
-        bool bad = false, has_n = false;
-        for (uint64_t i = lane; i < len64; i += 32) {
-            const uint32_t c = __ldg(text + b + i);
-            if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'N' && c != 'U') bad = true;
-            if (c == 'N') has_n = true;
-        }
-        bad = __any_sync(kFull, bad) || len64 > 0x7FFFFFFFull;
-        has_n = __any_sync(kFull, has_n);
+        // MinPeriod(s) <= threshold on the packed blocks: lane w holds X_w = nucleotides 16w .. 16w+15
+        uint32_t x1 = __shfl_down_sync(kFull, x, 1), x2 = __shfl_down_sync(kFull, x, 2);
+        if (lane >= 31) x1 = 0;
+        if (lane >= 30) x2 = 0;
+        const uint32_t pmax = (uint32_t) str_threshold < len ? (uint32_t) str_threshold : len;
         uint32_t status = 0;
-        if (bad) {
-            status = kRecBad;
-            if (lane == 0) atomicMin(&sc->first_bad, r);
-        } else if (has_n) {
-            status = kRecHasN;
-        } else if (len64 == 0) {
-            status = kRecStr;  // an all-space line: MinPeriod("") is undefined in the reference; dropped
-        } else {
-            // :343-353 -- MinPeriod(s) <= threshold  <=>  some p <= min(threshold, len) has s[i] == s[i + p] for all i
-            const uint32_t len = (uint32_t) len64;
-            const uint32_t pmax = (uint32_t) str_threshold < len ? (uint32_t) str_threshold : len;
-            for (uint32_t p = 1; p <= pmax && !status; p++) {
-                bool periodic = true;
-                for (uint32_t i0 = 0; i0 + p < len; i0 += 32) {
-                    const uint32_t i = i0 + lane;
-                    bool ok = true;
-                    if (i + p < len) ok = sym_of(__ldg(text + b + i), rna) == sym_of(__ldg(text + b + i + p), rna);
-                    if (!__all_sync(kFull, ok)) {
-                        periodic = false;
-                        break;
-                    }
-                }
-                if (periodic) status = kRecStr;
+        for (uint32_t p = 1; p <= pmax; p++) {
+            const uint32_t sh = (2u * p) & 31u;
+            const uint32_t lo = 2u * p >= 32u ? x1 : x, hi = 2u * p >= 32u ? x2 : x1;  // p <= 31 here (2p < 64)
+            const uint32_t y = __funnelshift_r(lo, hi, sh);
+            const int nb = (int) (2u * (len - p)) - 32 * lane;  // bits of this block that take part
+            const uint32_t m = nb >= 32 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << nb) - 1u));
+            if (!__any_sync(kFull, ((y ^ x) & m) != 0u)) {
+                status = kRecStr;
+                break;
             }
         }
         if (lane == 0) {
-            out.begin = b, out.len = (uint32_t) len64, out.status = status;
+            RecInfo out;
+            out.begin = b, out.len = len, out.status = status;
             info[r] = out;
         }
     }
@@ -220,7 +332,7 @@ __global__ void record_totals_kernel(const RecInfo *__restrict__ info, uint32_t 
     unsigned long long sum = 0;
     for (uint64_t r = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; r < n_rec; r += (uint64_t) gridDim.x * blockDim.x) {
         const RecInfo x = info[r];
-        if (x.status == 0) {
+        if ((x.status & kRecNull) == 0) {
             mx = x.len > mx ? x.len : mx;
             sum += x.len;
             ca++;
@@ -257,7 +369,10 @@ __device__ __forceinline__ uint32_t code_rc(uint32_t c, int rna) {
     return c == 'A' ? 3u : (c == 'C' ? 2u : (c == 'G' ? 1u : 0u));
 }
 
-// record r of file `file` -> ids (id0, id0 + 1) = (reverse complement, forward), id0 = r * id_step + 2 * file
+// record r of file `file` -> ids (id0, id0 + 1) = (reverse complement, forward), id0 = r * id_step + 2 * file.
+// One warp per record, one block per lane: the forward block from the 16 characters at 16w, the reverse-complement
+// block from the 16 characters that end at len - 16w (fields reversed, codes complemented); records the word-parallel
+// path does not take (kRecSlow, or a stride of more than 32 blocks) loop over their characters.
 __global__ void __launch_bounds__(256) pack_records_kernel(const uint8_t *__restrict__ text, const RecInfo *__restrict__ info,
                                                            uint32_t n_rec, int rna, uint32_t id_step, uint32_t id_first,
                                                            uint32_t stride, uint32_t *__restrict__ words,
@@ -267,12 +382,34 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const uint8_t *__rest
     for (uint32_t r = warp0; r < n_rec; r += n_warps) {
         const RecInfo x = info[r];
         const uint64_t id_rc = (uint64_t) r * id_step + id_first, id_fw = id_rc + 1;
-        const uint32_t len = x.status ? 0u : x.len;
+        const uint32_t len = (x.status & kRecNull) ? 0u : x.len;
         if (lane == 0) {
             len_out[id_rc] = len;
             len_out[id_fw] = len;
         }
         const uint8_t *s = text + x.begin;
+        if (!(x.status & kRecSlow) && stride <= 32u) {
+            if ((uint32_t) lane < stride) {
+                uint32_t fw = 0, rc = 0;
+                const uint32_t i0 = 16u * lane;
+                if (i0 < len) {
+                    const uint32_t cnt = min(16u, len - i0);
+                    uint32_t c[4], bad;
+                    load16(s + i0, c);
+                    fw = pack16(c, cnt, &bad);
+                    // reverse-complement positions i0 .. i0+15 are forward positions len-1-i0 down to len-16-i0
+                    const int f0 = (int) len - (int) i0 - 16;
+                    load16(s + (f0 > 0 ? f0 : 0), c);
+                    uint32_t p = pack16(c, 16u, &bad);
+                    if (f0 < 0) p <<= 2 * (-f0);
+                    rc = ~reverse_fields(p);
+                    if (cnt < 16u) rc &= (1u << (2u * cnt)) - 1u;
+                }
+                words[id_fw * stride + lane] = fw;
+                words[id_rc * stride + lane] = rc;
+            }
+            continue;
+        }
         for (uint32_t w = lane; w < stride; w += 32) {
             uint32_t fw = 0, rc = 0;
             const uint32_t i0 = w * 16u;
@@ -369,26 +506,26 @@ void launch_count_marks(const uint8_t *text, uint64_t n, bool plain, uint32_t *b
 }
 
 void launch_write_marks(const uint8_t *text, uint64_t n, bool plain, const uint64_t *block_off, uint32_t lines_per_record,
-                        uint64_t *rec_start, uint64_t n_cand, cudaStream_t s, const LaunchCfg &cfg) {
+                        uint64_t *rec_start, uint64_t *rec_end, uint64_t n_cand, cudaStream_t s, const LaunchCfg &cfg) {
     const uint64_t nb = input_mark_blocks(n);
     if (!nb) return;
-    if (plain) write_marks_kernel<true><<<(unsigned) nb, kMarkThreads, 0, s>>>(text, n, block_off, 1, rec_start, n_cand);
-    else write_marks_kernel<false><<<(unsigned) nb, kMarkThreads, 0, s>>>(text, n, block_off, lines_per_record, rec_start, n_cand);
+    if (plain) write_marks_kernel<true><<<(unsigned) nb, kMarkThreads, 0, s>>>(text, n, block_off, 1, rec_start, rec_end, n_cand);
+    else write_marks_kernel<false><<<(unsigned) nb, kMarkThreads, 0, s>>>(text, n, block_off, lines_per_record, rec_start, rec_end, n_cand);
     if (cfg.launches) *cfg.launches += 1;
 }
 
-// sc must hold {0xFFFFFFFF, 0xFFFFFFFF, 0, 0, 0, 0} before the call
-void launch_scan_records(const uint8_t *text, uint64_t n, bool plain, const uint64_t *rec_start, uint32_t n_cand, int trim_left,
-                         int trim_right, int rna, int str_threshold, void *info, void *scalars, cudaStream_t s,
-                         const LaunchCfg &cfg) {
+// sc must hold {0xFFFFFFFF, 0xFFFFFFFF, 0, ...} before the call; n_marks = number of marks in the file
+void launch_scan_records(const uint8_t *text, uint64_t n, bool plain, const uint64_t *rec_start, const uint64_t *rec_end,
+                         uint64_t n_marks, uint32_t lines_per_record, uint32_t n_cand, int trim_left, int trim_right, int rna,
+                         int str_threshold, void *info, void *scalars, cudaStream_t s, const LaunchCfg &cfg) {
     if (!n_cand) return;
     const int grid = grid_for((uint64_t) n_cand * 32, 256, cfg);
     if (plain)
-        scan_records_kernel<true><<<grid, 256, 0, s>>>(text, n, rec_start, n_cand, trim_left, trim_right, rna, str_threshold,
-                                                        (RecInfo *) info, (InputScalars *) scalars);
+        scan_records_kernel<true><<<grid, 256, 0, s>>>(text, n, rec_start, rec_end, n_marks, 1, n_cand, trim_left, trim_right, rna,
+                                                        str_threshold, (RecInfo *) info, (InputScalars *) scalars);
     else
-        scan_records_kernel<false><<<grid, 256, 0, s>>>(text, n, rec_start, n_cand, trim_left, trim_right, rna, str_threshold,
-                                                         (RecInfo *) info, (InputScalars *) scalars);
+        scan_records_kernel<false><<<grid, 256, 0, s>>>(text, n, rec_start, rec_end, n_marks, lines_per_record, n_cand, trim_left,
+                                                         trim_right, rna, str_threshold, (RecInfo *) info, (InputScalars *) scalars);
     if (cfg.launches) *cfg.launches += 1;
 }
 

@@ -149,11 +149,11 @@ size_t input_rec_info_bytes();
 size_t input_scalars_bytes();
 void launch_count_marks(const uint8_t *text, uint64_t n, bool plain, uint32_t *block_cnt, cudaStream_t s, const LaunchCfg &cfg);
 void launch_write_marks(const uint8_t *text, uint64_t n, bool plain, const uint64_t *block_off, uint32_t lines_per_record,
-                        uint64_t *rec_start, uint64_t n_cand, cudaStream_t s, const LaunchCfg &cfg);
+                        uint64_t *rec_start, uint64_t *rec_end, uint64_t n_cand, cudaStream_t s, const LaunchCfg &cfg);
 // scalars (input_scalars_bytes()): u32 first_empty = first_bad = 0xFFFFFFFF, u32 max_len = 0, u32 pad, u64 n_with_n = n_str = sum_len = n_alive = 0
-void launch_scan_records(const uint8_t *text, uint64_t n, bool plain, const uint64_t *rec_start, uint32_t n_cand, int trim_left,
-                         int trim_right, int rna, int str_threshold, void *info, void *scalars, cudaStream_t s,
-                         const LaunchCfg &cfg);
+void launch_scan_records(const uint8_t *text, uint64_t n, bool plain, const uint64_t *rec_start, const uint64_t *rec_end,
+                         uint64_t n_marks, uint32_t lines_per_record, uint32_t n_cand, int trim_left, int trim_right, int rna,
+                         int str_threshold, void *info, void *scalars, cudaStream_t s, const LaunchCfg &cfg);
 void launch_record_totals(const void *info, uint32_t n_rec, void *scalars, cudaStream_t s, const LaunchCfg &cfg);
 void launch_pack_records(const uint8_t *text, const void *info, uint32_t n_rec, int rna, uint32_t id_step, uint32_t id_first,
                          uint32_t stride, uint32_t *words, uint32_t *len_out, cudaStream_t s, const LaunchCfg &cfg);
