@@ -1276,6 +1276,10 @@ struct FrontEnd {
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     bool stage_used[2] = {false, false};
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    // copies run on their own (non-blocking) stream: the second file arrives while the first is scanned, and the read
+    // set goes back to the host while the graph is built
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev_up0 = nullptr, ev_up[2] = {nullptr, nullptr}, ev_ready = nullptr;
     // reader output: Global::READS after InputReader::readInput
     DevBuf words, len;
     uint32_t n = 0, stride = 1, max_len = 0;
@@ -1298,8 +1302,10 @@ struct FrontEnd {
         device = dev;
         for (cudaEvent_t *e : {&stage_ev[0], &stage_ev[1]})
             if (!*e) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-        for (cudaEvent_t *e : {&ev[0], &ev[1]})
+        for (cudaEvent_t *e : {&ev[0], &ev[1], &ev_up0, &ev_up[0], &ev_up[1]})
             if (!*e) CK(cudaEventCreate(e));
+        if (!ev_ready) CK(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+        if (!copy) CK(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
         return ALGA_OK;
     }
     void release() {
@@ -1307,10 +1313,12 @@ struct FrontEnd {
         for (DevBuf *b : {&words, &len, &table, &lenmap, &flags, &mask, &uflag, &upos, &rscal, &scan_ws, &words2, &len2, &old_id, &po})
             b->release();
         for (HostBuf *b : {&stage[0], &stage[1], &h_words, &h_len, &h_words2, &h_len2, &h_old, &h_po}) b->release();
-        for (cudaEvent_t *e : {&stage_ev[0], &stage_ev[1], &ev[0], &ev[1]}) {
+        for (cudaEvent_t *e : {&stage_ev[0], &stage_ev[1], &ev[0], &ev[1], &ev_up0, &ev_up[0], &ev_up[1], &ev_ready}) {
             if (*e) cudaEventDestroy(*e);
             *e = nullptr;
         }
+        if (copy) cudaStreamDestroy(copy);
+        copy = nullptr;
         stage_used[0] = stage_used[1] = false;
     }
 };
@@ -1323,15 +1331,16 @@ constexpr size_t kStageChunk = 8u << 20;
 // host -> device copy of file text: directly if the caller's buffer is page-locked (alga_gpu_host_alloc), otherwise
 // through two page-locked chunks so that the CPU copy of one chunk overlaps the DMA of the previous one
 int fe_upload_text(FrontEnd &fe, DevBuf &dst, const uint8_t *src, uint64_t n) {
+    cudaStream_t s = fe.copy;
     const size_t padded = (size_t) ((n + 15) / 16) * 16 + 16;
     CKR(dst.ensure(padded));
-    CK(cudaMemsetAsync((char *) dst.p + n, 0x0A, padded - (size_t) n, 0));  // the kernels never look past n; keep the pad defined
+    CK(cudaMemsetAsync((char *) dst.p + n, 0x0A, padded - (size_t) n, s));  // the kernels never look past n; keep the pad defined
     if (!n) return ALGA_OK;
     cudaPointerAttributes attr{};
     const bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
     if (pinned) {
-        CK(cudaMemcpyAsync(dst.p, src, (size_t) n, cudaMemcpyHostToDevice, 0));
+        CK(cudaMemcpyAsync(dst.p, src, (size_t) n, cudaMemcpyHostToDevice, s));
         return ALGA_OK;
     }
     CKR(fe.stage[0].ensure(kStageChunk));
@@ -1342,8 +1351,8 @@ int fe_upload_text(FrontEnd &fe, DevBuf &dst, const uint8_t *src, uint64_t n) {
         if (fe.stage_used[k]) CK(cudaEventSynchronize(fe.stage_ev[k]));  // the DMA out of this chunk must be done
         fe.stage_used[k] = true;
         memcpy(fe.stage[k].p, src + off, len);
-        CK(cudaMemcpyAsync((char *) dst.p + off, fe.stage[k].p, len, cudaMemcpyHostToDevice, 0));
-        CK(cudaEventRecord(fe.stage_ev[k], 0));
+        CK(cudaMemcpyAsync((char *) dst.p + off, fe.stage[k].p, len, cudaMemcpyHostToDevice, s));
+        CK(cudaEventRecord(fe.stage_ev[k], s));
     }
     return ALGA_OK;
 }
@@ -1398,17 +1407,21 @@ struct InputTimes {
 };
 
 // InputReader::readInput: file text (host) -> fe.words / fe.len (device); fills the counters of `info`
-int fe_read_input(FrontEnd &fe, const uint8_t *text1, uint64_t n1, const uint8_t *text2, uint64_t n2, const alga_input_params &p,
-                  const LaunchCfg &cfg, alga_read_set *info, InputTimes *tm) {
+int fe_read_input_impl(FrontEnd &fe, const uint8_t *text1, uint64_t n1, const uint8_t *text2, uint64_t n2, const alga_input_params &p,
+                       const LaunchCfg &cfg, alga_read_set *info, InputTimes *tm) {
     const bool paired = text2 != nullptr;
     const double t0 = now_ms();
+    CK(cudaEventRecord(fe.ev_up0, fe.copy));
     CKR(fe_upload_text(fe, fe.f[0].text, text1, n1));
-    if (paired) CKR(fe_upload_text(fe, fe.f[1].text, text2, n2));
-    CK(cudaStreamSynchronize(0));
-    const double t1 = now_ms();
-    tm->h2d_ms = t1 - t0;
-    CKR(fe_scan_file(fe, fe.f[0], n1, p, 1, cfg));
+    CK(cudaEventRecord(fe.ev_up[0], fe.copy));
     if (paired) {
+        CKR(fe_upload_text(fe, fe.f[1].text, text2, n2));
+        CK(cudaEventRecord(fe.ev_up[1], fe.copy));
+    }
+    CK(cudaStreamWaitEvent(0, fe.ev_up[0], 0));
+    CKR(fe_scan_file(fe, fe.f[0], n1, p, 1, cfg));  // runs while the second file is still arriving
+    if (paired) {
+        CK(cudaStreamWaitEvent(0, fe.ev_up[1], 0));
         CKR(fe_scan_file(fe, fe.f[1], n2, p, 2, cfg));
         if (fe.f[0].n_rec != fe.f[1].n_rec)
             return fail(ALGA_E_INVALID, "the mate files hold different numbers of records (%u and %u)", fe.f[0].n_rec, fe.f[1].n_rec);
@@ -1434,8 +1447,18 @@ int fe_read_input(FrontEnd &fe, const uint8_t *text1, uint64_t n1, const uint8_t
                             fe.words.as<uint32_t>(), fe.len.as<uint32_t>(), 0, cfg);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(0));
-    tm->kernel_ms = now_ms() - t1;
+    float up_ms = 0;
+    CK(cudaEventElapsedTime(&up_ms, fe.ev_up0, fe.ev_up[paired ? 1 : 0]));
+    tm->h2d_ms = up_ms;                 // the uploads on the copy stream (for page-locked text: pure DMA time)
+    tm->kernel_ms = now_ms() - t0;      // wall: call -> packed reads resident, uploads included (they overlap the scan)
     return ALGA_OK;
+}
+
+int fe_read_input(FrontEnd &fe, const uint8_t *text1, uint64_t n1, const uint8_t *text2, uint64_t n2, const alga_input_params &p,
+                  const LaunchCfg &cfg, alga_read_set *info, InputTimes *tm) {
+    const int r = fe_read_input_impl(fe, text1, n1, text2, n2, p, cfg, info, tm);
+    if (r != ALGA_OK) cudaStreamSynchronize(fe.copy);  // nothing may still be reading the caller's buffers
+    return r;
 }
 
 // main.cpp:150-232 on a device-resident read set: R + mask (device, may be null) -> fe.words2 / len2 / old_id / po.
@@ -1494,7 +1517,8 @@ void clear_read_set(alga_read_set *rs) { memset(rs, 0, sizeof(*rs)); }
 
 // device -> page-locked staging of the library; the arrays stay valid until the next call that produces the same kind of
 // read set (out->borrowed = 1)
-int fe_download(FrontEnd &fe, bool remapped, alga_read_set *out) {
+// s == fe.copy with wait == false: the copies are only queued (behind fe.ev_ready); the caller synchronises fe.copy
+int fe_download(FrontEnd &fe, bool remapped, alga_read_set *out, cudaStream_t s = 0, bool wait = true) {
     const uint32_t n = remapped ? fe.n2 : fe.n, stride = remapped ? fe.stride2 : fe.stride;
     HostBuf &hw = remapped ? fe.h_words2 : fe.h_words, &hl = remapped ? fe.h_len2 : fe.h_len;
     const size_t wb = (size_t) n * stride * 4;
@@ -1507,8 +1531,8 @@ int fe_download(FrontEnd &fe, bool remapped, alga_read_set *out) {
     out->len_nt = (uint32_t *) hl.p;
     out->borrowed = 1;
     if (n) {
-        CK(cudaMemcpyAsync(hw.p, remapped ? fe.words2.p : fe.words.p, wb, cudaMemcpyDeviceToHost, 0));
-        CK(cudaMemcpyAsync(hl.p, remapped ? fe.len2.p : fe.len.p, (size_t) n * 4, cudaMemcpyDeviceToHost, 0));
+        CK(cudaMemcpyAsync(hw.p, remapped ? fe.words2.p : fe.words.p, wb, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(hl.p, remapped ? fe.len2.p : fe.len.p, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
     }
     if (remapped) {
         CKR(fe.h_old.ensure(n ? (size_t) n * 4 : 4));
@@ -1516,11 +1540,11 @@ int fe_download(FrontEnd &fe, bool remapped, alga_read_set *out) {
         out->old_id = (uint32_t *) fe.h_old.p;
         out->paired_offset = (uint8_t *) fe.h_po.p;
         if (n) {
-            CK(cudaMemcpyAsync(fe.h_old.p, fe.old_id.p, (size_t) n * 4, cudaMemcpyDeviceToHost, 0));
-            CK(cudaMemcpyAsync(fe.h_po.p, fe.po.p, n, cudaMemcpyDeviceToHost, 0));
+            CK(cudaMemcpyAsync(fe.h_old.p, fe.old_id.p, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(fe.h_po.p, fe.po.p, n, cudaMemcpyDeviceToHost, s));
         }
     }
-    CK(cudaStreamSynchronize(0));
+    if (wait) CK(cudaStreamSynchronize(s));
     return ALGA_OK;
 }
 
@@ -1567,8 +1591,8 @@ int alga_gpu_read_input(const uint8_t *text1, uint64_t n1, const uint8_t *text2,
     }
     if (timing) {
         memset(timing, 0, sizeof(*timing));
-        timing->h2d_ms = tm.h2d_ms;
-        timing->device_ms = tm.kernel_ms;  // kernels and their scalar read-backs, text resident -> packed reads resident
+        timing->h2d_ms = tm.h2d_ms;        // upload on the copy stream (overlaps the scan of the first file)
+        timing->device_ms = tm.kernel_ms;  // wall: call -> packed reads resident, uploads included
         timing->d2h_ms = now_ms() - t1;
         timing->total_ms = now_ms() - t0;
         timing->kernel_launches = launches;
@@ -1679,21 +1703,25 @@ int alga_gpu_files_to_graph(const uint8_t *text1, uint64_t n1, const uint8_t *te
     CKR(fe.len2.ensure((size_t) (fe.n2 ? fe.n2 : 1) * 4));
     alga_reads dr{};
     dr.n_reads = fe.n2, dr.words = fe.words2.as<uint32_t>(), dr.stride_words = fe.stride2, dr.len_nt = fe.len2.as<uint32_t>();
+    // the renumbered read set goes back to the host on the copy stream while the graph is built from its device copy
+    CK(cudaEventRecord(fe.ev_ready, 0));
+    CK(cudaStreamWaitEvent(fe.copy, fe.ev_ready, 0));
+    CKR(fe_download(fe, true, &out->reads, fe.copy, false));
     CKR(alga_ps_plan_bind_reads_device(g_build_plan, &dr, 0));
     CKR(alga_ps_plan_run(g_build_plan, nullptr));
     const double t4 = now_ms();
     CKR(alga_ps_plan_result_host_pinned(g_build_plan, &out->graph));
-    CKR(fe_download(fe, true, &out->reads));
+    CK(cudaStreamSynchronize(fe.copy));
     const double t5 = now_ms();
     if (timing) {
         alga_ps_plan_stats(g_build_plan, timing);
         const double graph_dev_ms = timing->device_ms;
         timing->kernel_launches += launches;
-        timing->h2d_ms = tm.h2d_ms;
-        timing->d2h_ms = t5 - t4;
+        timing->h2d_ms = tm.h2d_ms;              // upload of the file text (copy stream; overlaps the scan of file 1)
+        timing->d2h_ms = t5 - t4;                // what is left of the downloads once the graph is built (CSR + tail of the reads)
         timing->total_ms = t5 - t0;
-        timing->device_ms = (t4 - t0) - tm.h2d_ms;  // text resident -> CSR resident, all stages
-        timing->stage_ms[0] = tm.kernel_ms;      // reader
+        timing->device_ms = t4 - t0;             // call -> CSR resident on the device, uploads included
+        timing->stage_ms[0] = tm.kernel_ms;      // reader: call -> packed reads resident (wall, uploads included)
         timing->stage_ms[1] = t2 - t1;           // prefix reads
         timing->stage_ms[2] = t3 - t2;           // renumbering
         timing->stage_ms[3] = graph_dev_ms;      // GraphCreatorPrefSuf pipeline (CUDA events)

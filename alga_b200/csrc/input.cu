@@ -269,13 +269,23 @@ __global__ void __launch_bounds__(256) scan_records_kernel(const uint8_t *__rest
                                                            InputScalars *__restrict__ sc) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t r = warp0; r < n_cand; r += n_warps) {
-        const uint64_t start = rec_start[r];
+    // the bounds of the next record are fetched while the current one is worked on
+    uint64_t start = 0, end = n;
+    if (warp0 < n_cand) {
+        start = rec_start[warp0];
+        if (!PLAIN && (uint64_t) lpr * warp0 + 1 < n_marks) end = rec_end[warp0];
+    }
+    for (uint32_t r = warp0; r < n_cand;) {
+        const uint32_t r_next = r + n_warps;
+        uint64_t start_next = 0, end_next = n;
+        if (r_next < n_cand) {
+            start_next = rec_start[r_next];
+            if (!PLAIN && (uint64_t) lpr * r_next + 1 < n_marks) end_next = rec_end[r_next];
+        }
         bool fast = !PLAIN && trim_left <= 32 && trim_right <= 32 && str_threshold <= 31;  // 2p < 64: two neighbour blocks suffice
         uint64_t b = start;
         uint32_t len = 0, x = 0;
         if (fast) {
-            const uint64_t end = ((uint64_t) lpr * r + 1 < n_marks) ? rec_end[r] : n;
             const uint64_t raw = end - start;
             fast = raw > 0 && raw <= kFastMaxLen;
             if (fast) {
@@ -299,30 +309,51 @@ __global__ void __launch_bounds__(256) scan_records_kernel(const uint8_t *__rest
         }
         if (!fast) {
             scan_record_generic<PLAIN>(text, n, start, r, trim_left, trim_right, rna, str_threshold, lane, info, sc);
-            continue;
-        }
-        // MinPeriod(s) <= threshold on the packed blocks: lane w holds X_w = nucleotides 16w .. 16w+15
-        uint32_t x1 = __shfl_down_sync(kFull, x, 1), x2 = __shfl_down_sync(kFull, x, 2);
-        if (lane >= 31) x1 = 0;
-        if (lane >= 30) x2 = 0;
-        const uint32_t pmax = (uint32_t) str_threshold < len ? (uint32_t) str_threshold : len;
-        uint32_t status = 0;
-        for (uint32_t p = 1; p <= pmax; p++) {
-            const uint32_t sh = (2u * p) & 31u;
-            const uint32_t lo = 2u * p >= 32u ? x1 : x, hi = 2u * p >= 32u ? x2 : x1;  // p <= 31 here (2p < 64)
-            const uint32_t y = __funnelshift_r(lo, hi, sh);
-            const int nb = (int) (2u * (len - p)) - 32 * lane;  // bits of this block that take part
-            const uint32_t m = nb >= 32 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << nb) - 1u));
-            if (!__any_sync(kFull, ((y ^ x) & m) != 0u)) {
-                status = kRecStr;
-                break;
+        } else {
+            // MinPeriod(s) <= threshold on the packed blocks (lane w holds X_w = nucleotides 16w .. 16w+15).
+            // Filter: lane p tests period p on the first 64 nucleotides only (blocks 0..3, broadcast); a period of the
+            // read is a period of its prefix, and a random read refutes all of them there.
+            const uint32_t pmax = (uint32_t) str_threshold < len ? (uint32_t) str_threshold : len;
+            const uint32_t blk[6] = {__shfl_sync(kFull, x, 0), __shfl_sync(kFull, x, 1), __shfl_sync(kFull, x, 2),
+                                     __shfl_sync(kFull, x, 3), 0u, 0u};
+            const uint32_t lp = len < 64u ? len : 64u;
+            bool cand = false;
+            if (lane >= 1 && (uint32_t) lane <= pmax) {
+                const uint32_t p = (uint32_t) lane, sh = (2u * p) & 31u;
+                const bool big = 2u * p >= 32u;
+                uint32_t diff = 0;
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const uint32_t y = __funnelshift_r(big ? blk[w + 1] : blk[w], big ? blk[w + 2] : blk[w + 1], sh);
+                    const int nb = (int) (2u * (lp - p)) - 32 * w;
+                    const uint32_t m = nb >= 32 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << nb) - 1u));
+                    diff |= (y ^ blk[w]) & m;
+                }
+                cand = diff == 0;
+            }
+            unsigned cands = __ballot_sync(kFull, cand);  // bit p: period p survives the prefix
+            uint32_t status = 0;
+            if (cands) {  // the whole read, one surviving period at a time
+                uint32_t x1 = __shfl_down_sync(kFull, x, 1), x2 = __shfl_down_sync(kFull, x, 2);
+                if (lane >= 31) x1 = 0;
+                if (lane >= 30) x2 = 0;
+                while (cands && !status) {
+                    const uint32_t p = (uint32_t) __ffs(cands) - 1u;
+                    cands &= cands - 1u;
+                    const uint32_t sh = (2u * p) & 31u;
+                    const uint32_t y = __funnelshift_r(2u * p >= 32u ? x1 : x, 2u * p >= 32u ? x2 : x1, sh);
+                    const int nb = (int) (2u * (len - p)) - 32 * lane;  // bits of this block that take part
+                    const uint32_t m = nb >= 32 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << nb) - 1u));
+                    if (!__any_sync(kFull, ((y ^ x) & m) != 0u)) status = kRecStr;
+                }
+            }
+            if (lane == 0) {
+                RecInfo out;
+                out.begin = b, out.len = len, out.status = status;
+                info[r] = out;
             }
         }
-        if (lane == 0) {
-            RecInfo out;
-            out.begin = b, out.len = len, out.status = status;
-            info[r] = out;
-        }
+        r = r_next, start = start_next, end = end_next;
     }
 }
 

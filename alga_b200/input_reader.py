@@ -151,6 +151,7 @@ def build_overlap_graph(text1, text2=None, file_type: int = FASTA, device: int =
               "li_kmer_intervals": 3, "avg_len": out.avg_len, "n_reads_in": out.n_reads_in,
               "n_records": (out.n_records[0], out.n_records[1]), "n_with_n": out.n_with_n, "n_str": out.n_str}
     timing = _timing(tm)
+    # read_input: wall time from the call to "packed reads resident" (uploads included, they overlap the scan of file 1)
     timing["stage_ms"] = dict(zip(("read_input", "prefix_reads", "remap", "prefsuf_device", "prefsuf_host"), list(tm.stage_ms)[:5]))
     rs, old, po, _ = _take(out.reads)
     return OverlapGraph(rs, graph, po, params, timing, old)
