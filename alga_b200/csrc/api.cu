@@ -133,6 +133,8 @@ struct alga_ps_plan {
     ReadsDev R{};
     ReadStats stats{};
     PsDev P{};
+    bool peek_by_kernel = false;  // control read-backs through launch_peek instead of the DMA engine (set while a bulk
+                                  // download shares the device -> host engine, alga_gpu_files_to_graph)
     bool swap_direction = false;  // rs > max_l + 1 corner of the reference (SURVEY.md A.1 note 2)
     bool index_valid = false;
 
@@ -186,8 +188,19 @@ int use_device(alga_ps_plan *plan) {
     return ALGA_OK;
 }
 
+// small device -> host read-back into one of the plan's page-locked scalars
+int plan_peek(alga_ps_plan *plan, void *dst, const void *src, uint32_t bytes, cudaStream_t s) {
+    if (plan->peek_by_kernel) {
+        launch_peek(dst, src, bytes, s, plan->cfg);
+        CK(cudaGetLastError());
+    } else {
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+    }
+    return ALGA_OK;
+}
+
 int read_counters(alga_ps_plan *plan, cudaStream_t s) {
-    CK(cudaMemcpyAsync(plan->h_counters, plan->counters_d.p, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    CKR(plan_peek(plan, plan->h_counters, plan->counters_d.p, sizeof(Counters), s));
     CK(cudaStreamSynchronize(s));
     return ALGA_OK;
 }
@@ -219,7 +232,7 @@ int compute_stats(alga_ps_plan *plan, cudaStream_t s, uint32_t max_len_hint) {
     launch_read_stats(plan->R, plan->params.min_overlap, plan->params.min_offset, plan->stats_d.as<ReadStats>(), s,
                       plan->cfg);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(plan->h_stats, plan->stats_d.p, sizeof(ReadStats), cudaMemcpyDeviceToHost, s));
+    CKR(plan_peek(plan, plan->h_stats, plan->stats_d.p, sizeof(ReadStats), s));
     CK(cudaStreamSynchronize(s));
     plan->stats = *plan->h_stats;
     if (max_len_hint && max_len_hint != plan->stats.max_len)
@@ -348,7 +361,7 @@ int run_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const RowsView &row
             launch_scan_u64(plan->caps.as<uint32_t>(), plan->spill_off.as<uint64_t>(), n_spill, plan->scan_ws.p, s,
                             plan->cfg);
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(plan->h_u64, plan->spill_off.as<uint64_t>() + n_spill, 8, cudaMemcpyDeviceToHost, s));
+            CKR(plan_peek(plan, plan->h_u64, plan->spill_off.as<uint64_t>() + n_spill, 8, s));
             CK(cudaStreamSynchronize(s));
             const uint64_t total = *plan->h_u64;
             CKR(plan->spill_store.ensure((size_t) total * 12 + 16));
@@ -386,7 +399,7 @@ int stage_csr(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int32_t *tripl
     CKR(plan->row_off.ensure(((size_t) n + 1) * 8));
     CKR(plan->scan_ws.ensure(scan_workspace_bytes(n)));
     launch_scan_u64(outdeg, plan->row_off.as<uint64_t>(), n, plan->scan_ws.p, s, plan->cfg);
-    CK(cudaMemcpyAsync(plan->h_u64, plan->row_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, s));  // read with the counters
+    CKR(plan_peek(plan, plan->h_u64, plan->row_off.as<uint64_t>() + n, 8, s));  // read with the counters
     CKR(plan->nbr.ensure((size_t) (n_tr ? n_tr : 1) * 4));
     CKR(plan->off.ensure((size_t) (n_tr ? n_tr : 1) * 4));
     CKR(plan->big_rows.ensure((size_t) (n ? n : 1) * 4));
@@ -1517,8 +1530,9 @@ void clear_read_set(alga_read_set *rs) { memset(rs, 0, sizeof(*rs)); }
 
 // device -> page-locked staging of the library; the arrays stay valid until the next call that produces the same kind of
 // read set (out->borrowed = 1)
-// s == fe.copy with wait == false: the copies are only queued (behind fe.ev_ready); the caller synchronises fe.copy
-int fe_download(FrontEnd &fe, bool remapped, alga_read_set *out, cudaStream_t s = 0, bool wait = true) {
+// s == fe.copy with wait == false: the copies are only queued (behind fe.ev_ready); the caller synchronises fe.copy.
+// cfg != nullptr: the bulk goes through a copy kernel instead of the DMA engine (see launch_copy_to_host).
+int fe_download(FrontEnd &fe, bool remapped, alga_read_set *out, cudaStream_t s = 0, bool wait = true, const LaunchCfg *cfg = nullptr) {
     const uint32_t n = remapped ? fe.n2 : fe.n, stride = remapped ? fe.stride2 : fe.stride;
     HostBuf &hw = remapped ? fe.h_words2 : fe.h_words, &hl = remapped ? fe.h_len2 : fe.h_len;
     const size_t wb = (size_t) n * stride * 4;
@@ -1530,20 +1544,23 @@ int fe_download(FrontEnd &fe, bool remapped, alga_read_set *out, cudaStream_t s 
     out->words = (uint32_t *) hw.p;
     out->len_nt = (uint32_t *) hl.p;
     out->borrowed = 1;
-    if (n) {
-        CK(cudaMemcpyAsync(hw.p, remapped ? fe.words2.p : fe.words.p, wb, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(hl.p, remapped ? fe.len2.p : fe.len.p, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
-    }
+    auto copy = [&](void *dst, const void *src, size_t bytes) -> int {
+        if (!bytes) return ALGA_OK;
+        if (cfg) launch_copy_to_host(dst, src, bytes, s, *cfg);
+        else CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+        return ALGA_OK;
+    };
+    CKR(copy(hw.p, remapped ? fe.words2.p : fe.words.p, wb));
+    CKR(copy(hl.p, remapped ? fe.len2.p : fe.len.p, (size_t) n * 4));
     if (remapped) {
         CKR(fe.h_old.ensure(n ? (size_t) n * 4 : 4));
         CKR(fe.h_po.ensure(n ? n : 4));
         out->old_id = (uint32_t *) fe.h_old.p;
         out->paired_offset = (uint8_t *) fe.h_po.p;
-        if (n) {
-            CK(cudaMemcpyAsync(fe.h_old.p, fe.old_id.p, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(fe.h_po.p, fe.po.p, n, cudaMemcpyDeviceToHost, s));
-        }
+        CKR(copy(fe.h_old.p, fe.old_id.p, (size_t) n * 4));
+        CKR(copy(fe.h_po.p, fe.po.p, n));
     }
+    CK(cudaGetLastError());
     if (wait) CK(cudaStreamSynchronize(s));
     return ALGA_OK;
 }
@@ -1706,9 +1723,18 @@ int alga_gpu_files_to_graph(const uint8_t *text1, uint64_t n1, const uint8_t *te
     // the renumbered read set goes back to the host on the copy stream while the graph is built from its device copy
     CK(cudaEventRecord(fe.ev_ready, 0));
     CK(cudaStreamWaitEvent(fe.copy, fe.ev_ready, 0));
-    CKR(fe_download(fe, true, &out->reads, fe.copy, false));
-    CKR(alga_ps_plan_bind_reads_device(g_build_plan, &dr, 0));
-    CKR(alga_ps_plan_run(g_build_plan, nullptr));
+    // (bulk through the DMA engine; the build's control read-backs go through a kernel meanwhile, or they would queue
+    // behind it -- measured: 2.1 ms of a 12.4 ms call.  A/B switch ALGA_FE_COPY_KERNEL: bulk through a copy kernel instead.)
+    static const bool copy_kernel = getenv("ALGA_FE_COPY_KERNEL") != nullptr;
+    CKR(fe_download(fe, true, &out->reads, fe.copy, false, copy_kernel ? &cfg : nullptr));
+    g_build_plan->peek_by_kernel = !copy_kernel;
+    int rb = alga_ps_plan_bind_reads_device(g_build_plan, &dr, 0);
+    if (rb == ALGA_OK) rb = alga_ps_plan_run(g_build_plan, nullptr);
+    g_build_plan->peek_by_kernel = false;
+    if (rb != ALGA_OK) {
+        cudaStreamSynchronize(fe.copy);
+        return rb;
+    }
     const double t4 = now_ms();
     CKR(alga_ps_plan_result_host_pinned(g_build_plan, &out->graph));
     CK(cudaStreamSynchronize(fe.copy));

@@ -16,6 +16,7 @@
 // All results are defined by the reference's --threads=1 order (with several threads a malformed file is read
 // differently, see oracle/input_oracle.c).
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/alga_gpu.h"
 #include "launch.h"
@@ -514,6 +515,17 @@ __global__ void remap_scatter_kernel(ReadsDev R, uint32_t n_units, const uint32_
     }
 }
 
+// Device -> page-locked host memory with ordinary stores (the host buffer is mapped into the device's address space).
+// Used instead of the DMA engine for the bulk download that overlaps the graph build: the small control read-backs of
+// the build go through that engine and would otherwise queue behind the bulk transfer.
+__global__ void __launch_bounds__(256) copy_to_host_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint64_t bytes) {
+    const uint64_t n16 = bytes / 16;
+    const uint4 *s16 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d16 = reinterpret_cast<uint4 *>(dst);
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n16; i += (uint64_t) gridDim.x * blockDim.x) d16[i] = __ldg(s16 + i);
+    if (blockIdx.x == 0 && threadIdx.x < (bytes & 15u)) dst[n16 * 16 + threadIdx.x] = src[n16 * 16 + threadIdx.x];
+}
+
 inline int grid_for(uint64_t n_items, int per_block, const LaunchCfg &cfg, int max_blocks_per_sm = 8) {
     uint64_t need = (n_items + per_block - 1) / per_block;
     const uint64_t cap = (uint64_t) cfg.sm_count * max_blocks_per_sm;
@@ -571,6 +583,28 @@ void launch_pack_records(const uint8_t *text, const void *info, uint32_t n_rec, 
     if (!n_rec) return;
     pack_records_kernel<<<grid_for((uint64_t) n_rec * 32, 256, cfg), 256, 0, s>>>(text, (const RecInfo *) info, n_rec, rna, id_step,
                                                                                  id_first, stride, words, len_out);
+    if (cfg.launches) *cfg.launches += 1;
+}
+
+// A few bytes device -> page-locked host memory without the DMA engine (control read-backs while that engine is busy)
+__global__ void peek_kernel(const uint8_t *__restrict__ src, volatile uint8_t *__restrict__ dst, uint32_t bytes) {
+    for (uint32_t i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+void launch_peek(void *dst_host, const void *src_dev, uint32_t bytes, cudaStream_t s, const LaunchCfg &cfg) {
+    if (!bytes) return;
+    peek_kernel<<<1, 64, 0, s>>>((const uint8_t *) src_dev, (volatile uint8_t *) dst_host, bytes);
+    if (cfg.launches) *cfg.launches += 1;
+}
+
+// src: device memory, dst: page-locked host memory (both 16-byte aligned)
+void launch_copy_to_host(void *dst_host, const void *src_dev, uint64_t bytes, cudaStream_t s, const LaunchCfg &cfg) {
+    if (!bytes) return;
+    static const uint64_t max_blocks = getenv("ALGA_FE_COPY_BLOCKS") ? (uint64_t) atoi(getenv("ALGA_FE_COPY_BLOCKS")) : 64;  // tuning knob
+    uint64_t blocks = (bytes / 16 + 255) / 256;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks < 1) blocks = 1;
+    copy_to_host_kernel<<<(unsigned) blocks, 256, 0, s>>>((const uint8_t *) src_dev, (uint8_t *) dst_host, bytes);
     if (cfg.launches) *cfg.launches += 1;
 }
 

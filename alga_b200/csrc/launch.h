@@ -157,6 +157,10 @@ void launch_scan_records(const uint8_t *text, uint64_t n, bool plain, const uint
 void launch_record_totals(const void *info, uint32_t n_rec, void *scalars, cudaStream_t s, const LaunchCfg &cfg);
 void launch_pack_records(const uint8_t *text, const void *info, uint32_t n_rec, int rna, uint32_t id_step, uint32_t id_first,
                          uint32_t stride, uint32_t *words, uint32_t *len_out, cudaStream_t s, const LaunchCfg &cfg);
+// a few bytes device -> page-locked host memory by a kernel (control read-backs that must not queue behind a bulk DMA)
+void launch_peek(void *dst_host, const void *src_dev, uint32_t bytes, cudaStream_t s, const LaunchCfg &cfg);
+// bulk copy device -> page-locked host memory by a kernel (not the DMA engine); 16-byte aligned pointers
+void launch_copy_to_host(void *dst_host, const void *src_dev, uint64_t bytes, cudaStream_t s, const LaunchCfg &cfg);
 // scalars: u32 max_len = 0, u32 err = 0 (1 + id of a read that survives without its reverse complement)
 void launch_remap_flags(const ReadsDev &R, const uint8_t *mask, uint32_t n_units, uint32_t *flag, void *scalars, cudaStream_t s,
                         const LaunchCfg &cfg);
