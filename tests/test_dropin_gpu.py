@@ -1,6 +1,6 @@
 """Drop-in check through the reference's own driver: the stock ALGA binary vs the same sources with
-src/GraphCreators/GraphCreatorPrefSuf.cpp and src/GraphCreators/GraphCreatorLI.cpp swapped for
-shim/GraphCreatorPrefSufGpu.cpp and shim/GraphCreatorLIGpu.cpp (oracle/_ref/ALGA_gpu, built by `make -C oracle ref` in
+src/GraphCreators/GraphCreatorPrefSuf.cpp, src/GraphCreators/GraphCreatorLI.cpp, src/IO/InputReader.cpp and
+src/IO/ReadPreprocess.cpp swapped for the four files of shim/ (oracle/_ref/ALGA_gpu, built by `make -C oracle ref` in
 the dev container).  Same FASTA in, --threads=1: the contigs must be identical."""
 import os
 import subprocess
@@ -67,6 +67,8 @@ def test_contigs_identical_through_reference_driver(gpu, tmp_path, paired, error
         log = _run(binary, d, args + ["--threads=1", "--output=contigs.fasta"] + extra)
         if name == "gpu":
             assert "alga_gpu:" in log, "the GPU shim did not run"
+            assert "alga_gpu reader:" in log, "the GPU reader shim did not run"
+            assert "alga_gpu preprocess:" in log, "the GPU preprocess shim did not run"
             if extra:
                 assert "alga_gpu supplement:" in log, "the GPU supplement shim did not run"
         outs[name] = _contigs(d / "contigs.fasta")
