@@ -238,7 +238,6 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
     std::vector<Kmer> km;                                     // k-mers of the pass, bucket-major
     std::vector<uint32_t> bstart((size_t) kBucketsSort + 1);  // bucket -> first k-mer
     std::vector<uint32_t> kbucket;                            // scratch: bucket of every k-mer in input order
-    std::vector<int> neighbors(n, 1000000001);                // Params::INF
     const int INF = 1000000001;
     const unsigned n_thr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     std::vector<std::vector<int32_t>> tpairs(n_thr);          // pairs found by each thread's share of the buckets
@@ -385,7 +384,8 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
                     const Kmer &ki = km[p + (size_t) i];
                     const int id1 = (int) ki.read;
                     auto &row = V[(size_t) id1];
-                    for (auto &x : row) neighbors[(size_t) x.first] = x.second;
+                    // the reference spreads the row into a dense `neighbors` array (:64-66); rows hold one entry per target
+                    // and stay short, so the entry is looked up in the row itself -- no random access per pair
                     uint64_t *bi = bm.data() + (size_t) i * RW;
                     for (int j = i + 1; j < D; j++) {
                         const Kmer &kj = km[p + (size_t) j];
@@ -396,27 +396,27 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
                         const int id2 = (int) kj.read;
                         const uint8_t can = verdict[(size_t) next++];
                         if (!((bi[j >> 6] >> (j & 63)) & 1ull)) {
-                            if (neighbors[(size_t) id2] > offset && can) {
-                                // Graph::addDirectedEdge (Graph.cpp:53-71): one entry per target, smallest offset
-                                bool found = false;
-                                for (auto &e : row) {
-                                    if (e.first == id2) {
-                                        if (offset < e.second) e.second = offset;
-                                        found = true;
-                                        break;
-                                    }
+                            int *cur = nullptr;  // offset of the edge id1 -> id2, if there is one (= neighbors[id2])
+                            for (auto &e : row) {
+                                if (e.first == id2) {
+                                    cur = &e.second;
+                                    break;
                                 }
-                                if (!found) row.push_back({id2, offset});
-                                neighbors[(size_t) id2] = offset;
                             }
-                            if (neighbors[(size_t) id2] != INF) {
+                            int cur_off = cur ? *cur : INF;
+                            if (cur_off > offset && can) {
+                                // Graph::addDirectedEdge (Graph.cpp:53-71): one entry per target, smallest offset
+                                if (cur) *cur = offset;
+                                else row.push_back({id2, offset});
+                                cur_off = offset;
+                            }
+                            if (cur_off != INF) {
                                 bi[j >> 6] |= 1ull << (j & 63);
                                 const uint64_t *bj = bm.data() + (size_t) j * RW;
                                 for (int t = 0; t < RW; t++) bi[t] |= bj[t];
                             }
                         }
                     }
-                    for (auto &x : row) neighbors[(size_t) x.first] = INF;
                 }
                 p = q;
             }
