@@ -125,6 +125,7 @@ SYMBOLS = {
     "alga_gpu_free_read_set": (None, [C.POINTER(ReadSetOut)]),
     "alga_gpu_files_to_graph": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64, C.POINTER(DriverParams), C.POINTER(OverlapGraphOut),
                                           C.POINTER(Timing)]),
+    "alga_gpu_cut_triangles": (C.c_int, [C.POINTER(Csr), C.c_int32, C.c_int32, C.POINTER(Csr), C.POINTER(Timing)]),
     "alga_gpu_supplement": (C.c_int, [C.POINTER(Reads), C.POINTER(Csr), C.POINTER(SupParams), C.POINTER(Csr),
                                       C.POINTER(Timing)]),
     "alga_gpu_li_kmers": (C.c_int, [C.POINTER(Reads), _P, C.c_uint32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),

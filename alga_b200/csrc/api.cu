@@ -1756,3 +1756,101 @@ int alga_gpu_files_to_graph(const uint8_t *text1, uint64_t n1, const uint8_t *te
     }
     return ALGA_OK;
 }
+
+// ---- first simplifier step (simplify.cu) ------------------------------------------------------------------------------
+int alga_gpu_cut_triangles(const alga_csr *gin, int32_t max_offset, int32_t device, alga_csr *gout, alga_timing *timing) {
+    if (!gin || !gout) return fail(ALGA_E_INVALID, "null argument");
+    const uint32_t n = gin->n_reads;
+    const uint64_t E = gin->n_edges;
+    if (n && !gin->row_off) return fail(ALGA_E_INVALID, "row_off must not be null");
+    if (E && (!gin->nbr || !gin->off)) return fail(ALGA_E_INVALID, "nbr / off must not be null");
+    if (n && gin->row_off[n] != E) return fail(ALGA_E_INVALID, "row_off[n] differs from n_edges");
+    memset(gout, 0, sizeof(*gout));
+    const double t0 = now_ms();
+    LaunchCfg cfg;
+    uint64_t launches = 0;
+    cfg.launches = &launches;
+    CKR(pick_device(device, &cfg));
+    DevBuf d_row, d_nbr, d_off, d_keep, d_kept, d_new_row, d_onbr, d_ooff, d_big, d_nbig, d_tn, d_to, scan_ws;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    float dev_ms = 0;
+    double h2d_ms = 0, d2h_ms = 0;
+    int r = [&]() -> int {
+        gout->n_reads = n;
+        gout->row_off = (uint64_t *) calloc((size_t) n + 1, 8);
+        if (!gout->row_off) return fail(ALGA_E_NOMEM, "host allocation failed");
+        if (!n || !E) return ALGA_OK;
+        CKR(d_row.ensure(((size_t) n + 1) * 8));
+        CKR(d_nbr.ensure((size_t) E * 4));
+        CKR(d_off.ensure((size_t) E * 4));
+        CKR(d_keep.ensure((size_t) E));
+        CKR(d_kept.ensure((size_t) n * 4));
+        CKR(d_new_row.ensure(((size_t) n + 1) * 8));
+        CKR(scan_ws.ensure(scan_workspace_bytes(n)));
+        CK(cudaMemcpy(d_row.p, gin->row_off, ((size_t) n + 1) * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_nbr.p, gin->nbr, (size_t) E * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_off.p, gin->off, (size_t) E * 4, cudaMemcpyHostToDevice));
+        h2d_ms = now_ms() - t0;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, 0));
+        launch_triangle_marks(d_row.as<uint64_t>(), d_nbr.as<int32_t>(), d_off.as<int32_t>(), n, max_offset, d_keep.as<uint8_t>(),
+                              d_kept.as<uint32_t>(), 0, cfg);
+        launch_scan_u64(d_kept.as<uint32_t>(), d_new_row.as<uint64_t>(), n, scan_ws.p, 0, cfg);
+        CK(cudaGetLastError());
+        uint64_t E2 = 0;
+        CK(cudaMemcpy(&E2, d_new_row.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost));
+        CKR(d_onbr.ensure((size_t) (E2 ? E2 : 1) * 4));
+        CKR(d_ooff.ensure((size_t) (E2 ? E2 : 1) * 4));
+        CKR(d_big.ensure((size_t) n * 4));
+        CKR(d_nbig.ensure(4));
+        CK(cudaMemsetAsync(d_nbig.p, 0, 4, 0));
+        launch_triangle_compact(d_row.as<uint64_t>(), d_nbr.as<int32_t>(), d_off.as<int32_t>(), d_keep.as<uint8_t>(), n,
+                                d_new_row.as<uint64_t>(), d_onbr.as<int32_t>(), d_ooff.as<int32_t>(), 0, cfg);
+        // Graph::sortEdgesByIncreasingOffset: rows by (offset, neighbour) -- the (first, second) row sort with the arrays swapped
+        launch_sort_rows(d_new_row.as<uint64_t>(), n, d_ooff.as<int32_t>(), d_onbr.as<int32_t>(), d_big.as<uint32_t>(),
+                         d_nbig.as<uint32_t>(), 0, cfg);
+        CK(cudaGetLastError());
+        uint32_t n_big = 0;
+        CK(cudaMemcpy(&n_big, d_nbig.p, 4, cudaMemcpyDeviceToHost));
+        if (n_big) {
+            CKR(d_tn.ensure((size_t) (E2 ? E2 : 1) * 4));
+            CKR(d_to.ensure((size_t) (E2 ? E2 : 1) * 4));
+            launch_sort_big_rows(d_new_row.as<uint64_t>(), d_big.as<uint32_t>(), n_big, d_ooff.as<int32_t>(), d_onbr.as<int32_t>(),
+                                 d_tn.as<int32_t>(), d_to.as<int32_t>(), 0, cfg);
+            CK(cudaGetLastError());
+        }
+        CK(cudaEventRecord(e1, 0));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&dev_ms, e0, e1));
+        const double t1 = now_ms();
+        gout->n_edges = E2;
+        gout->nbr = (int32_t *) malloc((size_t) (E2 ? E2 : 1) * 4);
+        gout->off = (int32_t *) malloc((size_t) (E2 ? E2 : 1) * 4);
+        if (!gout->nbr || !gout->off) return fail(ALGA_E_NOMEM, "host allocation failed");
+        CK(cudaMemcpy(gout->row_off, d_new_row.p, ((size_t) n + 1) * 8, cudaMemcpyDeviceToHost));
+        if (E2) {
+            CK(cudaMemcpy(gout->nbr, d_onbr.p, (size_t) E2 * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(gout->off, d_ooff.p, (size_t) E2 * 4, cudaMemcpyDeviceToHost));
+        }
+        d2h_ms = now_ms() - t1;
+        return ALGA_OK;
+    }();
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    for (DevBuf *b : {&d_row, &d_nbr, &d_off, &d_keep, &d_kept, &d_new_row, &d_onbr, &d_ooff, &d_big, &d_nbig, &d_tn, &d_to, &scan_ws})
+        b->release();
+    if (r != ALGA_OK) {
+        alga_gpu_free_csr(gout);
+        return r;
+    }
+    if (timing) {
+        memset(timing, 0, sizeof(*timing));
+        timing->h2d_ms = h2d_ms;
+        timing->device_ms = dev_ms;
+        timing->d2h_ms = d2h_ms;
+        timing->total_ms = now_ms() - t0;
+        timing->kernel_launches = launches;
+    }
+    return ALGA_OK;
+}

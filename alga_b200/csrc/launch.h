@@ -168,6 +168,13 @@ void launch_remap_scatter(const ReadsDev &R, uint32_t n_units, const uint32_t *f
                           uint32_t *words, uint32_t *len_out, uint32_t *old_id, uint8_t *paired_offset, uint32_t min_keep_len,
                           cudaStream_t s, const LaunchCfg &cfg);
 
+// --- first simplifier step (simplify.cu): GraphSimplifier::cutNonAndWeaklyMetricTriangles on a CSR with rows sorted by neighbour
+// keep[e] = 0 for removed entries, kept[i] = surviving entries of row i
+void launch_triangle_marks(const uint64_t *row_off, const int32_t *nbr, const int32_t *off, uint32_t n, int32_t max_offset,
+                           uint8_t *keep, uint32_t *kept, cudaStream_t s, const LaunchCfg &cfg);
+void launch_triangle_compact(const uint64_t *row_off, const int32_t *nbr, const int32_t *off, const uint8_t *keep, uint32_t n,
+                             const uint64_t *new_off, int32_t *out_nbr, int32_t *out_off, cudaStream_t s, const LaunchCfg &cfg);
+
 // --- error-rate supplement (supplement.cu) -------------------------------------------------------
 // LI k-mers (Read.cpp:145-226) of the reads d_ids[0 .. n_ids): `intervals` slots per read, ind = -1 where absent
 int run_li_kmers(const ReadsDev &R, const uint32_t *d_ids, uint32_t n_ids, const int32_t prio[4], int K, int intervals,

@@ -274,3 +274,32 @@ class ReadPreprocess:
         self.timing = {"h2d_ms": tm.h2d_ms, "device_ms": tm.device_ms, "total_ms": tm.total_ms,
                        "kernel_launches": tm.kernel_launches}
         return mask
+
+
+class GraphSimplifier:
+    """Mirror of the reference's ``GraphSimplifier`` (include/GraphSimplifiers/GraphSimplifier.h:24-37) for the first step of
+    ``simplifyGraphOld`` (GraphSimplifier.cpp:110-130), the one that works on the graph exactly as the graph creators leave
+    it: ``Graph::sortEdgesByIncreasingOffset`` + ``cutNonAndWeaklyMetricTriangles``."""
+
+    def __init__(self, graph: Graph, max_offset_parallel_paths: int, device: int = 0):
+        self.graph, self.max_offset, self.device = graph, max_offset_parallel_paths, device
+        self.timing: dict | None = None
+
+    def cutNonAndWeaklyMetricTriangles(self) -> Graph:
+        """GraphSimplifier.cpp:228-349; rows of the result are sorted by (offset, neighbour)."""
+        lib = _lib.load()
+        g = self.graph
+        row_off = np.ascontiguousarray(g.row_off, dtype=np.uint64)
+        nbr = np.ascontiguousarray(g.nbr, dtype=np.int32)
+        off = np.ascontiguousarray(g.off, dtype=np.int32)
+        cin = _lib.Csr(g.n, g.n_edges, row_off.ctypes.data_as(C.POINTER(C.c_uint64)), nbr.ctypes.data_as(C.POINTER(C.c_int32)),
+                       off.ctypes.data_as(C.POINTER(C.c_int32)), 1)
+        cout, tm = _lib.Csr(), _lib.Timing()
+        _lib.check(lib.alga_gpu_cut_triangles(C.byref(cin), self.max_offset, self.device, C.byref(cout), C.byref(tm)))
+        try:
+            self.graph = _csr_to_graph(cout)
+        finally:
+            lib.alga_gpu_free_csr(C.byref(cout))
+        self.timing = {"h2d_ms": tm.h2d_ms, "device_ms": tm.device_ms, "d2h_ms": tm.d2h_ms, "total_ms": tm.total_ms,
+                       "kernel_launches": tm.kernel_launches}
+        return self.graph

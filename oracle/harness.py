@@ -194,3 +194,16 @@ def run_stock_graph(text1: bytes, text2: bytes | None = None, file_type=1, threa
         g = [x for x in os.listdir(d) if x.endswith("_beforeSimplifier.graph")]
         assert len(g) == 1, g
         return read_graph_file(os.path.join(d, g[0]))
+
+
+def run_cut_triangles(edges_in, n_nodes: int, max_offset: int, threads=1) -> np.ndarray:
+    """The reference's Graph::sortEdgesByIncreasingOffset + GraphSimplifier::cutNonAndWeaklyMetricTriangles on a graph;
+    returns the surviving edges sorted by (src, dst, offset)."""
+    if not available():
+        raise RuntimeError("oracle/_ref/alga_ref_harness is not built (make -C oracle ref)")
+    with tempfile.TemporaryDirectory() as d:
+        ip, op = os.path.join(d, "in.alge"), os.path.join(d, "out.alge")
+        write_edges(ip, n_nodes, edges_in)
+        subprocess.run([HARNESS, "triangles", ip, op, str(max_offset), str(threads)], check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, cwd=d)
+        return read_edges(op)

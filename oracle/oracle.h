@@ -93,6 +93,10 @@ int oracle_read_input(const uint8_t *text1, uint64_t n1, const uint8_t *text2, u
 int oracle_remap(const uint32_t *len_nt, const uint8_t *mask, uint32_t n, uint32_t *old_id, uint8_t *paired_offset,
                  uint32_t *n_out);
 
+/* Graph::sortEdgesByIncreasingOffset + GraphSimplifier::cutNonAndWeaklyMetricTriangles (GraphSimplifier.cpp:228-349) on
+ * (src, dst, offset) triples grouped by ascending src; result sorted by (src, offset, dst).  See simplify_oracle.c. */
+int32_t *oracle_cut_triangles(const int32_t *edges_in, uint64_t n_in, uint32_t n_nodes, int32_t max_offset, uint64_t *n_out);
+
 void oracle_free(void *p);
 
 #ifdef __cplusplus

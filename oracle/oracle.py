@@ -34,7 +34,7 @@ INPUT_PLAIN, INPUT_FASTA, INPUT_FASTQ = 0, 1, 2
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(HERE, f) for f in ("prefsuf_oracle.c", "verify_oracle.c", "supplement_oracle.cpp", "preprocess_oracle.c", "input_oracle.c", "oracle.h",
+    srcs = [os.path.join(HERE, f) for f in ("prefsuf_oracle.c", "verify_oracle.c", "supplement_oracle.cpp", "preprocess_oracle.c", "input_oracle.c", "simplify_oracle.c", "oracle.h",
                                             "Makefile")]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         subprocess.run(["make", "-C", HERE, "liboracle.so"], check=True, stdout=subprocess.DEVNULL)
@@ -71,6 +71,8 @@ def _load():
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         _lib.oracle_remap.restype = C.c_int
         _lib.oracle_remap.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
+        _lib.oracle_cut_triangles.restype = C.POINTER(C.c_int32)
+        _lib.oracle_cut_triangles.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.POINTER(C.c_uint64)]
         _lib.oracle_free.argtypes = [C.c_void_p]
     return _lib
 
@@ -191,3 +193,15 @@ def remap(len_nt, mask=None):
     if rc != 0:
         raise ValueError("a read is present without its reverse complement (the reference asserts, main.cpp:173)")
     return old[: no.value].copy(), po[: no.value].copy()
+
+
+def cut_triangles(edges, n_nodes: int, max_offset: int) -> np.ndarray:
+    """sortEdgesByIncreasingOffset + cutNonAndWeaklyMetricTriangles: (E', 3) int32 edges sorted by (src, offset, dst)."""
+    lib = _load()
+    e = np.ascontiguousarray(edges, dtype=np.int32).reshape(-1, 3)
+    e = e[np.argsort(e[:, 0], kind="stable")]
+    ne = C.c_uint64(0)
+    p = lib.oracle_cut_triangles(e.ctypes.data, e.shape[0], n_nodes, max_offset, C.byref(ne))
+    out = np.ctypeslib.as_array(p, shape=(max(ne.value, 1) * 3,))[: ne.value * 3].reshape(-1, 3).copy()
+    lib.oracle_free(p)
+    return out

@@ -25,6 +25,7 @@
 #include <GraphCreators/GraphCreatorLI.h>
 #include <IO/ReadPreprocess.h>
 #include <IO/InputReader.h>
+#include <GraphSimplifiers/GraphSimplifier.h>
 #include <AlignmentControllers/AlignmentControllerHybrid.h>
 #include <AlignmentControllers/AlignmentControllerLowErrorRate.h>
 
@@ -312,6 +313,47 @@ int run_read_input(const char *file1, const char *file2, const char *out_path, i
     return 0;
 }
 
+// First step of GraphSimplifier::simplifyGraphOld (GraphSimplifier.cpp:110-130) on a given graph:
+// G->sortEdgesByIncreasingOffset(); simplifier.cutNonAndWeaklyMetricTriangles() with Params::MAX_OFFSET_PARALLEL_PATHS.
+int run_triangles(const char *edges_path, const char *out_path, int max_offset, int threads) {
+    Params::THREADS = threads;
+    Params::MAX_OFFSET_PARALLEL_PATHS = max_offset;
+    FILE *f = fopen(edges_path, "rb");
+    if (!f) die("cannot open edges file");
+    char magic[4];
+    uint32_t n;
+    uint64_t E;
+    if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "ALGE", 4) != 0) die("bad edges magic");
+    if (fread(&n, 4, 1, f) != 1 || fread(&E, 8, 1, f) != 1) die("bad edges header");
+    std::vector<int32_t> t(3 * E);
+    if (E && fread(t.data(), 4, 3 * E, f) != 3 * E) die("short edges");
+    fclose(f);
+    Global::READS.assign(n, nullptr);
+    Global::GRAPH = Graph((int) n);
+    Graph *G = &Global::GRAPH;
+    for (uint64_t i = 0; i < E; i++) G->pushDirectedEdge(t[3 * i], t[3 * i + 1], t[3 * i + 2]);
+    {
+        GraphSimplifier simplifier(Global::GRAPH, Global::READS);
+        G->sortEdgesByIncreasingOffset();
+        simplifier.cutNonAndWeaklyMetricTriangles();
+    }
+    uint64_t E2 = 0;
+    for (int i = 0; i < G->size(); i++) E2 += (*G)[i].size();
+    FILE *o = fopen(out_path, "wb");
+    if (!o) die("cannot open output");
+    fwrite("ALGE", 1, 4, o);
+    fwrite(&n, 4, 1, o);
+    fwrite(&E2, 8, 1, o);
+    for (int i = 0; i < G->size(); i++)
+        for (auto &e : (*G)[i]) {
+            int32_t x[3] = {i, e.first, e.second};
+            fwrite(x, 4, 3, o);
+        }
+    fclose(o);
+    printf("{\"n\": %u, \"edges_in\": %llu, \"edges_out\": %llu}\n", n, (unsigned long long) E, (unsigned long long) E2);
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -327,6 +369,8 @@ int main(int argc, char **argv) {
     if (argc >= 9 && strcmp(argv[1], "supplement") == 0)
         return run_supplement(argv[2], argv[3], argv[4], atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]),
                               argc >= 10 ? atoi(argv[9]) : 1);
+    if (argc >= 5 && strcmp(argv[1], "triangles") == 0)
+        return run_triangles(argv[2], argv[3], atoi(argv[4]), argc >= 6 ? atoi(argv[5]) : 1);
     if (argc >= 5 && strcmp(argv[1], "readinput") == 0)
         return run_read_input(argv[2], argv[3], argv[4], argc >= 6 ? atoi(argv[5]) : 1, argc > 6 ? argc - 6 : 0, argv + 6);
     fprintf(stderr,
@@ -335,7 +379,8 @@ int main(int argc, char **argv) {
             "       %s supplement <reads.algr> <edges_in.alge> <edges_out.alge> <min_overlap_area> <max_offset_pct> "
             "<threshold_pct> <kmer_length_bucket> [threads]\n"
             "       %s prefixreads <reads.algr> <mask.bin> [remove_type 1|2] [threads]\n"
-            "       %s readinput <file1> <file2|-> <reads_out.algr> [threads [reference options, e.g. --rna=1]]\n",
-            argv[0], argv[0], argv[0], argv[0], argv[0]);
+            "       %s readinput <file1> <file2|-> <reads_out.algr> [threads [reference options, e.g. --rna=1]]\n"
+            "       %s triangles <edges_in.alge> <edges_out.alge> <max_offset_parallel_paths> [threads]\n",
+            argv[0], argv[0], argv[0], argv[0], argv[0], argv[0]);
     return 2;
 }

@@ -290,3 +290,23 @@ def front_case(name):
             seqs[k] = seqs[k][: int(rng.integers(24, 44))]
         return _fasta(seqs), None, INPUT_FASTA
     raise KeyError(name)
+
+
+# ---- first simplifier step (cutNonAndWeaklyMetricTriangles) on graphs the reference itself produced ------------------
+# (fixture the input graph comes from, key of its edge array, Params::MAX_OFFSET_PARALLEL_PATHS)
+TRIANGLE_CASES = {"tri_cfg1": ("cfg1_small", "edges", 175), "tri_cfg3": ("cfg3_small", "edges", 262),
+                  "tri_sup_cfg3": ("sup_cfg3", "after", 262), "tri_varlen_dups": ("varlen_dups", "edges", 250),
+                  "tri_periodic": ("periodic_dups", "edges", 250), "tri_periodic_tight": ("periodic_dups", "edges", 20),
+                  "tri_contigs": ("rs_eq_lmin", "edges", 250), "tri_empty": ("empty", "edges", 250)}
+
+
+def triangle_case(name, golden_dir):
+    """-> (edges_in (E, 3) sorted by (src, dst), n_nodes, max_offset)"""
+    import os
+    src, key, mx = TRIANGLE_CASES[name]
+    e = np.load(os.path.join(golden_dir, f"{src}.npz"))[key]
+    if src.startswith("sup_"):
+        n = supplement_case(src)[0].n
+    else:
+        n = build_case(src)[0].n
+    return e, n, mx

@@ -15,7 +15,8 @@ error-rate supplement (GraphCreatorLI, main.cpp:300-355) on the supplement cases
 removal masks of ReadPreprocess::getPrefixReads (both removal types) on the preprocessing cases; `in_*.npz` hold
 Global::READS as the reference's InputReader::readInput leaves it (lengths, packed blocks) for the input files of the
 input cases; `front_*.npz` hold the graph the STOCK binary serialises (--serialize=1, --threads=1) for the files of the
-front cases, i.e. after its own reader, duplicate / prefix-read removal, renumbering and GraphCreatorPrefSuf.
+front cases, i.e. after its own reader, duplicate / prefix-read removal, renumbering and GraphCreatorPrefSuf; `tri_*.npz` hold
+the edges that survive the reference's sortEdgesByIncreasingOffset + cutNonAndWeaklyMetricTriangles on graphs stored above.
 """
 import hashlib
 import os
@@ -27,8 +28,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from oracle import harness  # noqa: E402
-from tests.cases import (CASES, FRONT_CASES, INPUT_CASES, PREPROCESS_CASES, SUPPLEMENT_CASES, build_case,  # noqa: E402
-                         front_case, input_case, preprocess_case, supplement_case, verify_case)
+from tests.cases import (CASES, FRONT_CASES, INPUT_CASES, PREPROCESS_CASES, SUPPLEMENT_CASES, TRIANGLE_CASES, build_case,  # noqa: E402
+                         front_case, input_case, preprocess_case, supplement_case, triangle_case, verify_case)
 
 
 def input_sha(rs) -> str:
@@ -93,6 +94,12 @@ def main():
         n, edges = harness.run_stock_graph(t1, t2, ft)
         np.savez_compressed(os.path.join(HERE, f"{name}.npz"), n=np.array(n), edges=edges, input_sha=np.array(text_sha(t1, t2)))
         print(f"{name}: n={n} E={edges.shape[0]}")
+    # first simplifier step on the graphs stored above (the reference's own sortEdgesByIncreasingOffset + triangle cut)
+    for name in TRIANGLE_CASES:
+        e, n, mx = triangle_case(name, HERE)
+        out = harness.run_cut_triangles(e, n, mx) if n else np.zeros((0, 3), np.int32)
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), edges=out, n_in=np.array(e.shape[0]))
+        print(f"{name}: {e.shape[0]} -> {out.shape[0]} edges")
 
 
 if __name__ == "__main__":
