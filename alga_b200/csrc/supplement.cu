@@ -241,6 +241,10 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
     const int INF = 1000000001;
     const unsigned n_thr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     std::vector<std::vector<int32_t>> tpairs(n_thr);          // pairs found by each thread's share of the buckets
+    std::vector<std::vector<int32_t>> tj(n_thr);              // ... the position j of each pair's second k-mer in its group
+    std::vector<std::vector<uint32_t>> tcnt(n_thr);           // ... pairs per (group, i), in loop order
+    std::vector<int32_t> pair_j;
+    std::vector<uint32_t> pair_cnt;
     std::vector<int32_t> pairs;
     std::vector<uint8_t> verdict;
     std::vector<uint64_t> bm;                                  // branch markers of one group: D rows of ceil(D/64) words
@@ -316,7 +320,11 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
         const double td = now_ms();
         run_threads([&](unsigned t) {
             std::vector<int32_t> &out = tpairs[t];
+            std::vector<int32_t> &outj = tj[t];
+            std::vector<uint32_t> &outc = tcnt[t];
             out.clear();
+            outj.clear();
+            outc.clear();
             const size_t b0 = (size_t) kBucketsSort * t / n_thr, b1 = (size_t) kBucketsSort * (t + 1) / n_thr;
             for (size_t k = b0; k < b1; k++) {
                 size_t p = bstart[k], q = p;
@@ -326,6 +334,7 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
                     const int D = (int) (q - p);
                     for (int i = D - 2; i >= 0; i--) {
                         const Kmer &ki = km[p + (size_t) i];
+                        const size_t before = outj.size();
                         for (int j = i + 1; j < D; j++) {
                             const Kmer &kj = km[p + (size_t) j];
                             int offset = 0;
@@ -335,7 +344,9 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
                             out.push_back((int32_t) ki.read);
                             out.push_back((int32_t) kj.read);
                             out.push_back(offset);
+                            outj.push_back(j);
                         }
+                        outc.push_back((uint32_t) (outj.size() - before));
                     }
                     p = q;
                 }
@@ -350,6 +361,12 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
                 if (!v.empty()) memcpy(pairs.data() + w, v.data(), v.size() * sizeof(int32_t));
                 w += v.size();
             }
+        }
+        pair_j.clear();
+        pair_cnt.clear();
+        for (unsigned t = 0; t < n_thr; t++) {  // thread t took the t-th share of the buckets: concatenation = loop order
+            pair_j.insert(pair_j.end(), tj[t].begin(), tj[t].end());
+            pair_cnt.insert(pair_cnt.end(), tcnt[t].begin(), tcnt[t].end());
         }
         const uint64_t n_pairs = pairs.size() / 3;
         pairs_total += n_pairs;
@@ -371,7 +388,10 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
         t_verify += now_ms() - tb;
         // ---- replay of the ordered loop (:64-84) with the verdicts at hand; sequential: groups share graph rows
         const double te = now_ms();
+        // The pairs that passed the static filters (:43-62) were listed per (group, i) by the enumeration above, so the
+        // loop below only visits those (the filters are not evaluated again).
         uint64_t next = 0;
+        size_t seg = 0;
         for (size_t k = 0; k < (size_t) kBucketsSort; k++) {
             size_t p = bstart[k], q = p;
             const size_t end = bstart[k + 1];
@@ -381,20 +401,17 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
                 const int RW = (D + 63) >> 6;  // words per branch-marker row
                 if (D > 1) bm.assign((size_t) D * RW, 0ull);
                 for (int i = D - 2; i >= 0; i--) {
-                    const Kmer &ki = km[p + (size_t) i];
-                    const int id1 = (int) ki.read;
+                    const uint32_t cnt = pair_cnt[seg++];
+                    if (!cnt) continue;
+                    const int id1 = (int) km[p + (size_t) i].read;
                     auto &row = V[(size_t) id1];
                     // the reference spreads the row into a dense `neighbors` array (:64-66); rows hold one entry per target
                     // and stay short, so the entry is looked up in the row itself -- no random access per pair
                     uint64_t *bi = bm.data() + (size_t) i * RW;
-                    for (int j = i + 1; j < D; j++) {
-                        const Kmer &kj = km[p + (size_t) j];
-                        int offset = 0;
-                        const int f = pair_filter(ki, kj, offset);
-                        if (f == 2) break;
-                        if (f == 1) continue;
-                        const int id2 = (int) kj.read;
-                        const uint8_t can = verdict[(size_t) next++];
+                    for (uint32_t c = 0; c < cnt; c++, next++) {
+                        const int j = pair_j[(size_t) next];
+                        const int id2 = pairs[3 * (size_t) next + 1], offset = pairs[3 * (size_t) next + 2];
+                        const uint8_t can = verdict[(size_t) next];
                         if (!((bi[j >> 6] >> (j & 63)) & 1ull)) {
                             int *cur = nullptr;  // offset of the edge id1 -> id2, if there is one (= neighbors[id2])
                             for (auto &e : row) {
