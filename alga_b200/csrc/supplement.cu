@@ -322,9 +322,13 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
             std::vector<int32_t> &out = tpairs[t];
             std::vector<int32_t> &outj = tj[t];
             std::vector<uint32_t> &outc = tcnt[t];
+            const size_t cap_j = outj.size(), cap_c = outc.size();  // sizes of the previous pass: a good guess for this one
             out.clear();
             outj.clear();
             outc.clear();
+            out.reserve(3 * cap_j + 1024);
+            outj.reserve(cap_j + 1024);
+            outc.reserve(cap_c + 1024);
             const size_t b0 = (size_t) kBucketsSort * t / n_thr, b1 = (size_t) kBucketsSort * (t + 1) / n_thr;
             for (size_t k = b0; k < b1; k++) {
                 size_t p = bstart[k], q = p;
@@ -362,11 +366,15 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
                 w += v.size();
             }
         }
-        pair_j.clear();
-        pair_cnt.clear();
-        for (unsigned t = 0; t < n_thr; t++) {  // thread t took the t-th share of the buckets: concatenation = loop order
-            pair_j.insert(pair_j.end(), tj[t].begin(), tj[t].end());
-            pair_cnt.insert(pair_cnt.end(), tcnt[t].begin(), tcnt[t].end());
+        {  // thread t took the t-th share of the buckets: concatenation = loop order
+            std::vector<size_t> oj(n_thr + 1, 0), oc(n_thr + 1, 0);
+            for (unsigned t = 0; t < n_thr; t++) oj[t + 1] = oj[t] + tj[t].size(), oc[t + 1] = oc[t] + tcnt[t].size();
+            pair_j.resize(oj[n_thr]);
+            pair_cnt.resize(oc[n_thr]);
+            run_threads([&](unsigned t) {
+                if (!tj[t].empty()) memcpy(pair_j.data() + oj[t], tj[t].data(), tj[t].size() * sizeof(int32_t));
+                if (!tcnt[t].empty()) memcpy(pair_cnt.data() + oc[t], tcnt[t].data(), tcnt[t].size() * sizeof(uint32_t));
+            });
         }
         const uint64_t n_pairs = pairs.size() / 3;
         pairs_total += n_pairs;
@@ -391,7 +399,7 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
         // The pairs that passed the static filters (:43-62) were listed per (group, i) by the enumeration above, so the
         // loop below only visits those (the filters are not evaluated again).
         uint64_t next = 0;
-        size_t seg = 0;
+        size_t seg = 0, pf = 0;  // pf: k-mers whose row header has been prefetched
         for (size_t k = 0; k < (size_t) kBucketsSort; k++) {
             size_t p = bstart[k], q = p;
             const size_t end = bstart[k + 1];
@@ -400,6 +408,12 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
                 const int D = (int) (q - p);
                 const int RW = (D + 63) >> 6;  // words per branch-marker row
                 if (D > 1) bm.assign((size_t) D * RW, 0ull);
+                // rows are scattered over the heap: fetch the headers of the next k-mers' rows and the entries of this
+                // group's rows ahead of their use (the loop is bound by these cache misses, not by arithmetic)
+                for (size_t hi = q + 48 < km.size() ? q + 48 : km.size(); pf < hi; pf++)
+                    if (pf >= q) __builtin_prefetch(&V[(size_t) km[pf].read]);
+                if (D > 1)
+                    for (size_t x = p; x < q; x++) __builtin_prefetch(V[(size_t) km[x].read].data());
                 for (int i = D - 2; i >= 0; i--) {
                     const uint32_t cnt = pair_cnt[seg++];
                     if (!cnt) continue;
