@@ -35,9 +35,6 @@ constexpr uint32_t kLenWords = (kMaxLen + 1) / 32;
 constexpr uint64_t kBase = 0x9E3779B97F4A7C15ull;  // odd: code_j * kBase^j mod 2^64
 constexpr uint32_t kDup = 1u, kLonger = 2u;
 
-__device__ __forceinline__ uint32_t code_at(const uint32_t *__restrict__ p, uint32_t j) {
-    return (__ldg(p + (j >> 4)) >> ((j & 15u) * 2u)) & 3u;
-}
 __device__ __forceinline__ uint64_t key_of(uint64_t h, uint32_t len) { return mix64(h ^ ((uint64_t) len * 0xD6E8FEB86659FD93ull)); }
 
 __global__ void length_map_kernel(ReadsDev R, uint32_t *lenmap, uint32_t *too_long) {
@@ -58,9 +55,13 @@ __global__ void insert_reads_kernel(ReadsDev R, SeedTable t) {
         if (len == 0 || len > kMaxLen) continue;
         const uint32_t *p = read_ptr(R, (uint32_t) i);
         uint64_t h = 0, pw = 1;
-        for (uint32_t j = 0; j < len; j++) {
-            h += (uint64_t) code_at(p, j) * pw;
-            pw *= kBase;
+        for (uint32_t j0 = 0; j0 < len; j0 += 16) {  // one block (16 nucleotides) per load
+            uint32_t w = __ldg(p + (j0 >> 4));
+            const uint32_t nj = len - j0 < 16u ? len - j0 : 16u;
+            for (uint32_t j = 0; j < nj; j++, w >>= 2) {
+                h += (uint64_t) (w & 3u) * pw;
+                pw *= kBase;
+            }
         }
         insert_seed(t, key_of(h, len), (uint32_t) i);
     }
@@ -83,17 +84,23 @@ __global__ void probe_prefixes_kernel(ReadsDev R, SeedTable t, const uint32_t *_
         if (len_s == 0 || len_s > kMaxLen) continue;
         const uint32_t *ps = read_ptr(R, s);
         uint64_t h = 0, pw = 1;
-        for (uint32_t j = 0; j < len_s; j++) {
-            h += (uint64_t) code_at(ps, j) * pw;
-            pw *= kBase;
-            const uint32_t l = j + 1;
-            if (!((__ldg(lenmap + (l >> 5)) >> (l & 31u)) & 1u)) continue;  // no read has this length
-            probe_seed(t, key_of(h, l), [&](uint32_t r) {
-                if (r == s || R.len[r] != l) return;
-                if (l == len_s && r > s) return;  // r sorts after s: s does not remove it
-                if (!same_prefix(ps, read_ptr(R, r), l)) return;
-                atomicOr(flags + r, l < len_s ? kLonger : kDup);
-            });
+        uint32_t lm = __ldg(lenmap);  // the word of the length map that holds bit l (reloaded every 32 lengths)
+        for (uint32_t j0 = 0; j0 < len_s; j0 += 16) {  // one block (16 nucleotides) per load
+            uint32_t w = __ldg(ps + (j0 >> 4));
+            const uint32_t nj = len_s - j0 < 16u ? len_s - j0 : 16u;
+            for (uint32_t j = 0; j < nj; j++, w >>= 2) {
+                h += (uint64_t) (w & 3u) * pw;
+                pw *= kBase;
+                const uint32_t l = j0 + j + 1;
+                if ((l & 31u) == 0) lm = __ldg(lenmap + (l >> 5));
+                if (!((lm >> (l & 31u)) & 1u)) continue;  // no read has this length
+                probe_seed(t, key_of(h, l), [&](uint32_t r) {
+                    if (r == s || R.len[r] != l) return;
+                    if (l == len_s && r > s) return;  // r sorts after s: s does not remove it
+                    if (!same_prefix(ps, read_ptr(R, r), l)) return;
+                    atomicOr(flags + r, l < len_s ? kLonger : kDup);
+                });
+            }
         }
     }
 }
