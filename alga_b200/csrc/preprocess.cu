@@ -49,11 +49,41 @@ __global__ void length_map_kernel(ReadsDev R, uint32_t *lenmap, uint32_t *too_lo
     }
 }
 
-__global__ void insert_reads_kernel(ReadsDev R, SeedTable t) {
+// *uniform = the one length that occurs in the read set, or 0 if several do
+__global__ void length_info_kernel(const uint32_t *__restrict__ lenmap, uint32_t *uniform) {
+    __shared__ uint32_t cnt, which;
+    if (threadIdx.x == 0) cnt = 0, which = 0;
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < kLenWords; k += blockDim.x) {
+        const uint32_t w = lenmap[k];
+        if (w) {
+            atomicAdd(&cnt, (uint32_t) __popc(w));
+            atomicMax(&which, 32u * k + (uint32_t) (__ffs(w) - 1));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *uniform = cnt == 1 ? which : 0u;
+}
+
+// All reads have one length (the usual case: equal-length reads after trimming): only duplicates can occur, one lookup per
+// read, and the key needs no rolling structure -- a hash of the blocks, one multiply per 16 nucleotides.
+__device__ __forceinline__ uint64_t block_hash(const uint32_t *__restrict__ p, uint32_t len) {
+    uint64_t h = 0x243F6A8885A308D3ull;
+    const uint32_t nw = (len + 15u) >> 4;
+    for (uint32_t k = 0; k < nw; k++) h = (h ^ __ldg(p + k)) * kBase + (h >> 29);
+    return h;
+}
+
+__global__ void insert_reads_kernel(ReadsDev R, SeedTable t, const uint32_t *__restrict__ uniform) {
+    const uint32_t ulen = *uniform;
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < R.n; i += (uint64_t) gridDim.x * blockDim.x) {
         const uint32_t len = R.len[i];
         if (len == 0 || len > kMaxLen) continue;
         const uint32_t *p = read_ptr(R, (uint32_t) i);
+        if (ulen) {
+            insert_seed(t, key_of(block_hash(p, len), len), (uint32_t) i);
+            continue;
+        }
         uint64_t h = 0, pw = 1;
         for (uint32_t j0 = 0; j0 < len; j0 += 16) {  // one block (16 nucleotides) per load
             uint32_t w = __ldg(p + (j0 >> 4));
@@ -78,11 +108,21 @@ __device__ __forceinline__ bool same_prefix(const uint32_t *__restrict__ ps, con
     return true;
 }
 
-__global__ void probe_prefixes_kernel(ReadsDev R, SeedTable t, const uint32_t *__restrict__ lenmap, uint32_t *flags) {
+__global__ void probe_prefixes_kernel(ReadsDev R, SeedTable t, const uint32_t *__restrict__ lenmap, uint32_t *flags,
+                                      const uint32_t *__restrict__ uniform) {
+    const uint32_t ulen = *uniform;
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < R.n; i += (uint64_t) gridDim.x * blockDim.x) {
         const uint32_t s = (uint32_t) i, len_s = R.len[s];
         if (len_s == 0 || len_s > kMaxLen) continue;
         const uint32_t *ps = read_ptr(R, s);
+        if (ulen) {  // every copy of s with a smaller id is a duplicate (the greatest id of a set of equal reads stays)
+            probe_seed(t, key_of(block_hash(ps, len_s), len_s), [&](uint32_t r) {
+                if (r >= s) return;
+                if (!same_prefix(ps, read_ptr(R, r), len_s)) return;
+                atomicOr(flags + r, kDup);
+            });
+            continue;
+        }
         uint64_t h = 0, pw = 1;
         uint32_t lm = __ldg(lenmap);  // the word of the length map that holds bit l (reloaded every 32 lengths)
         for (uint32_t j0 = 0; j0 < len_s; j0 += 16) {  // one block (16 nucleotides) per load
@@ -119,19 +159,21 @@ __global__ void mark_removed_kernel(const uint32_t *__restrict__ flags, uint32_t
 
 }  // namespace
 
-// flags: n words (zeroed here), lenmap: kLenWords + 1 words (zeroed here; the last word reports a read that is too long)
+// flags: n words (zeroed here), lenmap: prefix_reads_lenmap_words() words (zeroed here; the last word reports a read that is too long)
 void launch_prefix_reads(const ReadsDev &R, const SeedTable &t, int remove_type, uint32_t *lenmap, uint32_t *flags,
                          uint8_t *mask, cudaStream_t s, const LaunchCfg &cfg) {
-    cudaMemsetAsync(lenmap, 0, (size_t) (kLenWords + 1) * 4, s);
+    cudaMemsetAsync(lenmap, 0, (size_t) (kLenWords + 2) * 4, s);
     cudaMemsetAsync(flags, 0, (size_t) (R.n ? R.n : 1) * 4, s);
     cudaMemsetAsync(mask, 0, R.n ? R.n : 1, s);
     if (!R.n) return;
-    length_map_kernel<<<grid_for(R.n, 256, cfg), 256, 0, s>>>(R, lenmap, lenmap + kLenWords);
-    insert_reads_kernel<<<grid_for(R.n, 128, cfg), 128, 0, s>>>(R, t);
-    probe_prefixes_kernel<<<grid_for(R.n, 128, cfg), 128, 0, s>>>(R, t, lenmap, flags);
+    length_map_kernel<<<grid_for(R.n, 256, cfg), 256, 0, s>>>(R, lenmap, lenmap + kLenWords + 1);
+    length_info_kernel<<<1, 256, 0, s>>>(lenmap, lenmap + kLenWords);
+    insert_reads_kernel<<<grid_for(R.n, 128, cfg), 128, 0, s>>>(R, t, lenmap + kLenWords);
+    probe_prefixes_kernel<<<grid_for(R.n, 128, cfg), 128, 0, s>>>(R, t, lenmap, flags, lenmap + kLenWords);
     mark_removed_kernel<<<grid_for(R.n, 256, cfg), 256, 0, s>>>(flags, R.n, remove_type, mask);
-    if (cfg.launches) *cfg.launches += 4;
+    if (cfg.launches) *cfg.launches += 5;
 }
-size_t prefix_reads_lenmap_words() { return kLenWords + 1; }
+// [0, kLenWords) the map, [kLenWords] the uniform length (or 0), [kLenWords + 1] "a read is too long"
+size_t prefix_reads_lenmap_words() { return kLenWords + 2; }
 
 }  // namespace alga
