@@ -176,7 +176,8 @@ def test_files_to_graph_matches_stock_binary(gpu, name, how):
     assert np.array_equal(og.graph.edges(), g["edges"])
 
 
-@pytest.mark.parametrize("name", ["in_fasta_se", "in_fasta_pe", "in_fastq_pe", "in_long", "in_no_eol", "in_truncated", "in_empty"])
+@pytest.mark.parametrize("name", ["in_fasta_se", "in_fasta_pe", "in_fastq_pe", "in_plain", "in_long", "in_no_eol", "in_truncated",
+                                  "in_empty"])
 def test_files_to_graph_matches_oracle_pipeline(gpu, name):
     """The fused call against the same path composed from the oracle's pieces: renumbered reads, pairedReadOffset, the
     removal of short reads, parameters and the edge set (inputs with N reads, repeats, short reads, ragged lengths)."""
@@ -192,3 +193,40 @@ def test_files_to_graph_matches_oracle_pipeline(gpu, name):
     assert np.array_equal(og.graph.edges(), edges)
     old, _ = oracle.remap(raw.len_nt, oracle.prefix_reads(raw, 2))
     assert np.array_equal(og.old_id, old)
+
+
+def test_files_to_graph_errors_leave_the_library_usable(gpu):
+    """A failing call (bad character, unequal mate files) must not poison the cached workspace of the next one."""
+    t1, t2, ft = front_case("front_pe")
+    g = np.load(os.path.join(GOLD, "front_pe.npz"))
+    cut = t1.index(b"\n>", 2000) + 1  # a record boundary
+    bad = t1[:cut] + b">x\nACGTACGTacgtACGTACGTACGTACGT\n" + t1[cut:]
+    for _ in range(2):
+        with pytest.raises(_lib.AlgaGpuError) as e:
+            build_overlap_graph(bad, t2, ft)
+        assert "character" in str(e.value)
+        with pytest.raises(_lib.AlgaGpuError):
+            build_overlap_graph(t1, t2[: len(t2) // 2], ft)
+        og = build_overlap_graph(t1, t2, ft)
+        assert og.reads.n == int(g["n"]) and np.array_equal(og.graph.edges(), g["edges"])
+
+
+def test_files_to_graph_overrides_and_remove_types(gpu):
+    """-l style overrides of the derived parameters and the other REMOVE_PREF_READS_TYPE settings, against the oracle's pieces."""
+    from alga_b200.input_reader import driver_params
+    from tests.test_input_cpu import gather
+    t1, t2, ft = front_case("front_se")
+    raw, _ = oracle.read_input(t1, t2, ft)
+    for remove_type in (1, 0):
+        og = build_overlap_graph(t1, t2, ft, remove_type=remove_type)
+        prm = driver_params(raw)
+        mask = oracle.prefix_reads(raw, 1) if remove_type else None
+        old, po = oracle.remap(raw.len_nt, mask)
+        rs2 = gather(raw, old)
+        ln = rs2.len_nt.copy()
+        ln[ln < 3 + prm["li_kmer_length"]] = 0
+        want = oracle.prefsuf(ReadSet(rs2.words, rs2.word_off, ln), prm["min_overlap"], prm["rs_min_overlap"])
+        assert np.array_equal(og.old_id, old) and np.array_equal(og.paired_offset, po)
+        assert np.array_equal(og.graph.edges(), want)
+    og = build_overlap_graph(t1, t2, ft, min_overlap=40, rs_min_overlap=70)
+    assert og.params["min_overlap"] == 40 and og.params["rs_min_overlap"] == 70 and og.params["li_kmer_length"] == 40
