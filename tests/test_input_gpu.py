@@ -230,3 +230,16 @@ def test_files_to_graph_overrides_and_remove_types(gpu):
         assert np.array_equal(og.graph.edges(), want)
     og = build_overlap_graph(t1, t2, ft, min_overlap=40, rs_min_overlap=70)
     assert og.params["min_overlap"] == 40 and og.params["rs_min_overlap"] == 70 and og.params["li_kmer_length"] == 40
+
+
+def test_read_input_offsets_beyond_4_gib(gpu):
+    """Records that start behind byte 2^32 of the file (a 4 GiB header line in front of them): positions are 64-bit from the
+    mark kernels to the packing.  Pageable text, so the chunked upload is exercised with hundreds of chunks as well."""
+    rng = np.random.default_rng(9)
+    seqs = [_seq(rng.integers(0, 4, size=int(rng.integers(60, 160)))) for _ in range(300)]
+    tail = _fasta(seqs[1:])
+    text = b">" + b"x" * (2**32 + 12345) + b"\n" + seqs[0] + b"\n" + tail
+    got = InputReader(FASTA).readInput(text)
+    del text
+    want, _ = oracle.read_input(b">h\n" + seqs[0] + b"\n" + tail, None, oracle.INPUT_FASTA)
+    assert_same_reads(got, want.len_nt, want.word_off, want.words)
