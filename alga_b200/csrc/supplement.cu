@@ -148,6 +148,74 @@ double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+struct Pinned {  // page-locked host buffer freed on scope exit
+    void *p = nullptr;
+    size_t cap = 0;
+    ~Pinned() {
+        if (p) cudaFreeHost(p);
+    }
+    int ensure(size_t bytes) {
+        if (bytes <= cap && p) return ALGA_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr, cap = 0;
+        const size_t want = bytes + bytes / 4 + 64;
+        SCK(cudaMallocHost(&p, want));
+        cap = want;
+        return ALGA_OK;
+    }
+    template <class T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+// The static filters of GraphCreatorPairwiseKmerBranch.cpp:43-62 for the ordered pair (i, j) of one group:
+// 0 = candidate, 1 = skip j, 2 = stop this i.
+struct PairFilter {
+    int min_offset, max_offset_pct, min_overlap_area;
+};
+__host__ __device__ inline int pair_filter_of(const Kmer &ki, const Kmer &kj, const PairFilter &F, int &offset) {
+    if (ki.read == kj.read) return 1;
+    offset = ki.ind - kj.ind;
+    if (offset < F.min_offset) return 1;
+    if (100ll * offset > (long long) F.max_offset_pct * (long long) ki.read_len) return 2;
+    const int a = (int) ki.read_len, b = (int) kj.read_len + offset;
+    const int overlap = (a < b ? a : b) - offset;
+    if (overlap < F.min_overlap_area) return 1;
+    if ((int) kj.read_len + offset - (int) ki.read_len < 0) return 1;  // Read::getRightOffset
+    return 0;
+}
+
+// Pair enumeration on the sorted k-mer array (one thread per k-mer x, which plays i; j runs over the rest of its group,
+// i.e. while the hash stays the same): first the number of pairs that pass the filters, then -- at the offsets a scan
+// made of the counts -- the pairs themselves as (read_i, read_j, offset) for canAlign plus the position of j.
+template <bool FILL>
+__global__ void enumerate_pairs_kernel(const Kmer *__restrict__ km, uint32_t nk, PairFilter F, uint32_t *__restrict__ cnt,
+                                       const uint64_t *__restrict__ off, int32_t *__restrict__ pairs, uint32_t *__restrict__ pj) {
+    for (uint64_t x = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; x < nk; x += (uint64_t) gridDim.x * blockDim.x) {
+        const Kmer ki = km[x];
+        uint64_t w = FILL ? off[x] : 0;
+        uint32_t c = 0;
+        for (uint64_t j = x + 1; j < nk; j++) {
+            const Kmer kj = km[j];
+            if (kj.hash != ki.hash) break;
+            int offset = 0;
+            const int f = pair_filter_of(ki, kj, F, offset);
+            if (f == 2) break;
+            if (f == 1) continue;
+            if (FILL) {
+                pairs[3 * w] = (int32_t) ki.read;
+                pairs[3 * w + 1] = (int32_t) kj.read;
+                pairs[3 * w + 2] = offset;
+                pj[w] = (uint32_t) j;
+                w++;
+            }
+            c++;
+        }
+        if (!FILL) cnt[x] = c;
+    }
+}
+
 }  // namespace
 
 const char *supplement_last_error() { return g_sup_err; }
@@ -235,35 +303,20 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
     // Host side, flat: all k-mers of a pass in ONE array ordered by bucket (counting sort that keeps the reference's fill
     // order inside a bucket: reads by id, k-mers by interval), std::sort on each bucket's range -- the same sequence,
     // comparator and algorithm as std::sort on the reference's per-bucket vectors, hence the same tie order.
-    std::vector<Kmer> km;                                     // k-mers of the pass, bucket-major
+    Pinned km_buf;                                            // k-mers of the pass, bucket-major (page-locked: it is uploaded)
     std::vector<uint32_t> bstart((size_t) kBucketsSort + 1);  // bucket -> first k-mer
     std::vector<uint32_t> kbucket;                            // scratch: bucket of every k-mer in input order
     const int INF = 1000000001;
     const unsigned n_thr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    std::vector<std::vector<int32_t>> tpairs(n_thr);          // pairs found by each thread's share of the buckets
-    std::vector<std::vector<int32_t>> tj(n_thr);              // ... the position j of each pair's second k-mer in its group
-    std::vector<std::vector<uint32_t>> tcnt(n_thr);           // ... pairs per (group, i), in loop order
-    std::vector<int32_t> pair_j;
-    std::vector<uint32_t> pair_cnt;
-    std::vector<int32_t> pairs;
-    std::vector<uint8_t> verdict;
+    // pair enumeration on the device: per k-mer x (as i) the range [pair_off[x], pair_off[x + 1]) of its pairs
+    Buf d_km, d_cnt, d_poff, d_pj, scan_ws;
+    Pinned h_poff, h_pj, h_verdict;
     std::vector<uint64_t> bm;                                  // branch markers of one group: D rows of ceil(D/64) words
     double gpu_ms = 0, t_kmers = 0, t_sort = 0, t_enum = 0, t_verify = 0, t_replay = 0;
     uint64_t pairs_total = 0;
     int32_t prio[4] = {0, 1, 2, 3};
 
-    // the static filters of GraphCreatorPairwiseKmerBranch.cpp:43-62 for the ordered pair (i, j) of one group:
-    // 0 = candidate, 1 = skip j, 2 = stop this i
-    auto pair_filter = [&](const Kmer &ki, const Kmer &kj, int &offset) -> int {
-        if (ki.read == kj.read) return 1;
-        offset = ki.ind - kj.ind;
-        if (offset < sp->min_offset) return 1;
-        if (100ll * offset > (long long) sp->max_offset_pct * (long long) ki.read_len) return 2;
-        const int overlap = std::min((int) ki.read_len, (int) kj.read_len + offset) - offset;
-        if (overlap < sp->min_overlap_area) return 1;
-        if ((int) kj.read_len + offset - (int) ki.read_len < 0) return 1;  // Read::getRightOffset
-        return 0;
-    };
+    const PairFilter pf_params{sp->min_offset, sp->max_offset_pct, sp->min_overlap_area};
     auto run_threads = [&](auto &&fn) {  // fn(t): bucket range [t, t+1) * kBucketsSort / n_thr
         std::vector<std::thread> th;
         for (unsigned t = 1; t < n_thr; t++) th.emplace_back([&fn, t] { fn(t); });
@@ -301,7 +354,8 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
             nk++;
         }
         for (size_t k = 0; k < (size_t) kBucketsSort; k++) bstart[k + 1] += bstart[k];
-        km.resize(nk);
+        if (km_buf.ensure((nk ? nk : 1) * sizeof(Kmer))) return ALGA_E_NOMEM;
+        Kmer *km = km_buf.as<Kmer>();
         {
             std::vector<uint32_t> cursor(bstart.begin(), bstart.end() - 1);
             for (size_t slot = 0; slot < n_slots; slot++) {
@@ -313,93 +367,56 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
         run_threads([&](unsigned t) {
             const size_t b0 = (size_t) kBucketsSort * t / n_thr, b1 = (size_t) kBucketsSort * (t + 1) / n_thr;
             for (size_t k = b0; k < b1; k++)
-                if (bstart[k + 1] - bstart[k] > 1) std::sort(km.begin() + bstart[k], km.begin() + bstart[k + 1]);
+                if (bstart[k + 1] - bstart[k] > 1) std::sort(km + bstart[k], km + bstart[k + 1]);
         });
         t_sort += now_ms() - tc;
-        // ---- every pair that passes the static filters, in loop order (buckets, groups, i descending, j ascending)
+        // ---- every pair that passes the static filters (:43-62), on the device: count per k-mer, scan, fill
         const double td = now_ms();
-        run_threads([&](unsigned t) {
-            std::vector<int32_t> &out = tpairs[t];
-            std::vector<int32_t> &outj = tj[t];
-            std::vector<uint32_t> &outc = tcnt[t];
-            const size_t cap_j = outj.size(), cap_c = outc.size();  // sizes of the previous pass: a good guess for this one
-            out.clear();
-            outj.clear();
-            outc.clear();
-            out.reserve(3 * cap_j + 1024);
-            outj.reserve(cap_j + 1024);
-            outc.reserve(cap_c + 1024);
-            const size_t b0 = (size_t) kBucketsSort * t / n_thr, b1 = (size_t) kBucketsSort * (t + 1) / n_thr;
-            for (size_t k = b0; k < b1; k++) {
-                size_t p = bstart[k], q = p;
-                const size_t end = bstart[k + 1];
-                while (p < end) {
-                    while (q < end && km[q].hash == km[p].hash) q++;
-                    const int D = (int) (q - p);
-                    for (int i = D - 2; i >= 0; i--) {
-                        const Kmer &ki = km[p + (size_t) i];
-                        const size_t before = outj.size();
-                        for (int j = i + 1; j < D; j++) {
-                            const Kmer &kj = km[p + (size_t) j];
-                            int offset = 0;
-                            const int f = pair_filter(ki, kj, offset);
-                            if (f == 2) break;
-                            if (f == 1) continue;
-                            out.push_back((int32_t) ki.read);
-                            out.push_back((int32_t) kj.read);
-                            out.push_back(offset);
-                            outj.push_back(j);
-                        }
-                        outc.push_back((uint32_t) (outj.size() - before));
-                    }
-                    p = q;
-                }
-            }
-        });
-        size_t total3 = 0;
-        for (auto &v : tpairs) total3 += v.size();
-        pairs.resize(total3);
-        {
-            size_t w = 0;
-            for (auto &v : tpairs) {
-                if (!v.empty()) memcpy(pairs.data() + w, v.data(), v.size() * sizeof(int32_t));
-                w += v.size();
-            }
+        uint64_t n_pairs = 0;
+        uint64_t *pair_off = nullptr;
+        if (nk) {
+            if (d_km.alloc(nk * sizeof(Kmer)) || d_cnt.alloc(nk * 4) || d_poff.alloc((nk + 1) * 8) ||
+                scan_ws.alloc(scan_workspace_bytes(nk)) || h_poff.ensure((nk + 1) * 8))
+                return ALGA_E_NOMEM;
+            SCK(cudaMemcpy(d_km.p, km, nk * sizeof(Kmer), cudaMemcpyHostToDevice));
+            const int grid = grid_for(nk, 128, cfg, 16);
+            enumerate_pairs_kernel<false><<<grid, 128>>>(d_km.as<Kmer>(), (uint32_t) nk, pf_params, d_cnt.as<uint32_t>(), nullptr,
+                                                         nullptr, nullptr);
+            launch_scan_u64(d_cnt.as<uint32_t>(), d_poff.as<uint64_t>(), nk, scan_ws.p, 0, cfg);
+            SCK(cudaGetLastError());
+            SCK(cudaMemcpy(h_poff.p, d_poff.p, (nk + 1) * 8, cudaMemcpyDeviceToHost));
+            pair_off = h_poff.as<uint64_t>();
+            n_pairs = pair_off[nk];
+            launches += 1;
         }
-        {  // thread t took the t-th share of the buckets: concatenation = loop order
-            std::vector<size_t> oj(n_thr + 1, 0), oc(n_thr + 1, 0);
-            for (unsigned t = 0; t < n_thr; t++) oj[t + 1] = oj[t] + tj[t].size(), oc[t + 1] = oc[t] + tcnt[t].size();
-            pair_j.resize(oj[n_thr]);
-            pair_cnt.resize(oc[n_thr]);
-            run_threads([&](unsigned t) {
-                if (!tj[t].empty()) memcpy(pair_j.data() + oj[t], tj[t].data(), tj[t].size() * sizeof(int32_t));
-                if (!tcnt[t].empty()) memcpy(pair_cnt.data() + oc[t], tcnt[t].data(), tcnt[t].size() * sizeof(uint32_t));
-            });
-        }
-        const uint64_t n_pairs = pairs.size() / 3;
         pairs_total += n_pairs;
         t_enum += now_ms() - td;
-        // ---- canAlign of all of them in one batch on the GPU
+        // ---- the pairs themselves and canAlign of all of them in one batch, still on the device
         const double tb = now_ms();
-        verdict.assign((size_t) n_pairs, 0);
         if (n_pairs) {
             if (n_pairs > pairs_cap) {
                 pairs_cap = (size_t) n_pairs + n_pairs / 4;
-                if (d_pairs.alloc(pairs_cap * 12) || d_verdict.alloc(pairs_cap)) return ALGA_E_NOMEM;
+                if (d_pairs.alloc(pairs_cap * 12) || d_verdict.alloc(pairs_cap) || d_pj.alloc(pairs_cap * 4)) return ALGA_E_NOMEM;
             }
-            SCK(cudaMemcpy(d_pairs.p, pairs.data(), (size_t) n_pairs * 12, cudaMemcpyHostToDevice));
+            if (h_pj.ensure((size_t) n_pairs * 4) || h_verdict.ensure((size_t) n_pairs)) return ALGA_E_NOMEM;
+            enumerate_pairs_kernel<true><<<grid_for(nk, 128, cfg, 16), 128>>>(d_km.as<Kmer>(), (uint32_t) nk, pf_params, nullptr,
+                                                                              d_poff.as<uint64_t>(), d_pairs.as<int32_t>(),
+                                                                              d_pj.as<uint32_t>());
+            launches += 1;
             launch_verify_pairs(R, d_pairs.as<int32_t>(), n_pairs, vd, d_verdict.as<uint8_t>(), 0, cfg);
             SCK(cudaGetLastError());
-            SCK(cudaMemcpy(verdict.data(), d_verdict.p, (size_t) n_pairs, cudaMemcpyDeviceToHost));
+            SCK(cudaMemcpy(h_pj.p, d_pj.p, (size_t) n_pairs * 4, cudaMemcpyDeviceToHost));
+            SCK(cudaMemcpy(h_verdict.p, d_verdict.p, (size_t) n_pairs, cudaMemcpyDeviceToHost));
         }
-        gpu_ms += now_ms() - tb;
+        const uint32_t *pair_j = h_pj.as<uint32_t>();
+        const uint8_t *verdict = h_verdict.as<uint8_t>();
+        gpu_ms += now_ms() - td;
         t_verify += now_ms() - tb;
         // ---- replay of the ordered loop (:64-84) with the verdicts at hand; sequential: groups share graph rows
         const double te = now_ms();
-        // The pairs that passed the static filters (:43-62) were listed per (group, i) by the enumeration above, so the
-        // loop below only visits those (the filters are not evaluated again).
-        uint64_t next = 0;
-        size_t seg = 0, pf = 0;  // pf: k-mers whose row header has been prefetched
+        // The pairs that passed the static filters were listed per k-mer (as i) by the enumeration above, so the loop below
+        // only visits those; the pair's offset and second read follow from the two k-mers.
+        size_t pf = 0;  // k-mers whose row header has been prefetched
         for (size_t k = 0; k < (size_t) kBucketsSort; k++) {
             size_t p = bstart[k], q = p;
             const size_t end = bstart[k + 1];
@@ -410,22 +427,25 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
                 if (D > 1) bm.assign((size_t) D * RW, 0ull);
                 // rows are scattered over the heap: fetch the headers of the next k-mers' rows and the entries of this
                 // group's rows ahead of their use (the loop is bound by these cache misses, not by arithmetic)
-                for (size_t hi = q + 48 < km.size() ? q + 48 : km.size(); pf < hi; pf++)
+                for (size_t hi_pf = q + 48 < nk ? q + 48 : nk; pf < hi_pf; pf++)
                     if (pf >= q) __builtin_prefetch(&V[(size_t) km[pf].read]);
                 if (D > 1)
                     for (size_t x = p; x < q; x++) __builtin_prefetch(V[(size_t) km[x].read].data());
                 for (int i = D - 2; i >= 0; i--) {
-                    const uint32_t cnt = pair_cnt[seg++];
-                    if (!cnt) continue;
-                    const int id1 = (int) km[p + (size_t) i].read;
+                    const size_t x = p + (size_t) i;
+                    const uint64_t c0 = pair_off[x], c1 = pair_off[x + 1];
+                    if (c0 == c1) continue;
+                    const Kmer &ki = km[x];
+                    const int id1 = (int) ki.read;
                     auto &row = V[(size_t) id1];
                     // the reference spreads the row into a dense `neighbors` array (:64-66); rows hold one entry per target
                     // and stay short, so the entry is looked up in the row itself -- no random access per pair
                     uint64_t *bi = bm.data() + (size_t) i * RW;
-                    for (uint32_t c = 0; c < cnt; c++, next++) {
-                        const int j = pair_j[(size_t) next];
-                        const int id2 = pairs[3 * (size_t) next + 1], offset = pairs[3 * (size_t) next + 2];
-                        const uint8_t can = verdict[(size_t) next];
+                    for (uint64_t c = c0; c < c1; c++) {
+                        const Kmer &kj = km[pair_j[c]];
+                        const int j = (int) (pair_j[c] - p);
+                        const int id2 = (int) kj.read, offset = ki.ind - kj.ind;
+                        const uint8_t can = verdict[c];
                         if (!((bi[j >> 6] >> (j & 63)) & 1ull)) {
                             int *cur = nullptr;  // offset of the edge id1 -> id2, if there is one (= neighbors[id2])
                             for (auto &e : row) {
