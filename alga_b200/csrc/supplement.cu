@@ -7,14 +7,15 @@
 //
 //     GPU   LI k-mers of every dead-end read            (Read.cpp:145-226; 70-bit rolling minimum per interval)
 //     host  scatter into the 2^20 hash-range buckets, std::sort per bucket (GraphCreatorKmerBased.cpp:94-106,
-//           202-259: the tie order inside a bucket is libstdc++'s, exactly as in the reference), and enumeration of
-//           every pair that passes the static filters of GraphCreatorPairwiseKmerBranch.cpp:43-62
-//     GPU   canAlign of all those pairs in one batch    (AlignmentControllerLowErrorRate.cpp:15-49, one pair per warp)
+//           202-259: the tie order inside a bucket is libstdc++'s, exactly as in the reference)
+//     GPU   enumeration of every pair that passes the static filters of GraphCreatorPairwiseKmerBranch.cpp:43-62
+//           (one thread per k-mer: count, scan, fill) and canAlign of all those pairs in one batch
+//           (AlignmentControllerLowErrorRate.cpp:15-49, one pair per warp); the pair list stays on the device
 //     host  replay of the ordered loop with the verdicts at hand (:64-84), Graph::addDirectedEdge,
 //           retainOnlySmallestOffset
 //
-// four times, with Read::priorities rotated after each pass (GraphCreatorLI.cpp:18-28).  No CPU fallback: the two
-// kernels are the only implementation of the k-mer minimum and of canAlign in this library.
+// four times, with Read::priorities rotated after each pass (GraphCreatorLI.cpp:18-28).  No CPU fallback: the kernels
+// are the only implementation of the k-mer minimum, of the pair filters and of canAlign in this library.
 #include <algorithm>
 #include <chrono>
 #include <cmath>

@@ -400,7 +400,7 @@ def run_ours(args):
         g2 = li.startAlignmentGraphCreation()
         supplement = {"ms": 1e3 * (time.perf_counter() - ts), "edges_before": int(g.n_edges), "edges_after": int(g2.n_edges),
                       "params": sp, **li.timing,
-                      "note": "alga_gpu_supplement: LI k-mers + canAlign on the GPU, bucket sort + ordered replay on the host"}
+                      "note": "alga_gpu_supplement: LI k-mers, pair enumeration and canAlign on the GPU, bucket sort + ordered replay on the host"}
 
     preprocess = None
     if world == 1 and args.with_preprocess:

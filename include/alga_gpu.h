@@ -223,8 +223,9 @@ int alga_gpu_verify_pairs(const alga_reads *reads, const int32_t *pairs, uint64_
  * Drop-in for main.cpp:300-355 (runs when --error_rate > 0.01): GraphCreatorLI / GraphCreatorPairwiseKmerBranch over the
  * dead-end reads of the graph produced by alga_gpu_prefsuf_build, four passes with rotated nucleotide priorities,
  * followed by Graph::retainOnlySmallestOffset (main.cpp:346).  LI k-mer extraction (Read.cpp:145-226) and all canAlign
- * calls (AlignmentControllerHybrid.cpp:46-83) run on the GPU; the bucket sort and the order-dependent edge replay
- * (GraphCreatorKmerBased.cpp:94-136, GraphCreatorPairwiseKmerBranch.cpp:16-97) run on the host with libstdc++'s
+ * calls (AlignmentControllerHybrid.cpp:46-83) run on the GPU, and so does the enumeration of the candidate pairs with the
+ * static filters of GraphCreatorPairwiseKmerBranch.cpp:43-62; the bucket sort and the order-dependent edge replay
+ * (GraphCreatorKmerBased.cpp:94-136, GraphCreatorPairwiseKmerBranch.cpp:64-97) run on the host with libstdc++'s
  * std::sort, so ties inside a bucket fall exactly as in a reference built with the same toolchain. */
 typedef struct {
     int32_t max_offset_pct;     /* Params::MAX_OFFSET_CONSIDERED_FOR_ALIGNMENT = (1 - SCALE) * avg_len / 2 (main.cpp:335) */
@@ -239,7 +240,7 @@ typedef struct {
 } alga_sup_params;
 /* graph_in: Graph::V after main.cpp:291 (host CSR); graph_out: Graph::V after main.cpp:346 (malloc'ed host CSR, release
  * with alga_gpu_free_csr).  timing (may be NULL): h2d_ms, device_ms (kernels + their transfers), total_ms,
- * kernel_launches; stage_ms[0..4] = LI k-mers, bucket scatter + sort, pair enumeration, canAlign batch, ordered replay
+ * kernel_launches; stage_ms[0..4] = LI k-mers, bucket scatter + sort (host), pair enumeration, canAlign batch, ordered replay (host)
  * (summed over the four passes); stage_ms[5] = dead-end reads that took part, stage_ms[6] = pairs verified. */
 int alga_gpu_supplement(const alga_reads *reads, const alga_csr *graph_in, const alga_sup_params *params,
                         alga_csr *graph_out, alga_timing *timing);
