@@ -402,6 +402,30 @@ def run_ours(args):
                       "params": sp, **li.timing,
                       "note": "alga_gpu_supplement: LI k-mers, pair enumeration and canAlign on the GPU, bucket sort + ordered replay on the host"}
 
+    triangles = None
+    if world == 1 and args.with_triangles:
+        # the first simplifier step (sortEdgesByIncreasingOffset + cutNonAndWeaklyMetricTriangles) on the
+        # graph just built (after the supplement where it ran), host to host
+        from alga_b200.graph_creator import GraphSimplifier
+
+        gin = g2 if supplement else g
+        LEN = int(float(w.reads.len_nt[w.reads.len_nt > 0].mean())) + 2 * synth.TRIM
+        mopp = max(250, int(1.75 * LEN))  # Params::MAX_OFFSET_PARALLEL_PATHS, main.cpp:95
+        edges_in = gin.edges().copy()
+        n_in = int(gin.n_edges)
+        GraphSimplifier(gin, mopp, device=local).cutNonAndWeaklyMetricTriangles()  # warm-up
+        gs = GraphSimplifier(gin, mopp, device=local)
+        ts = time.perf_counter()
+        gout = gs.cutNonAndWeaklyMetricTriangles()
+        triangles = {"ms": 1e3 * (time.perf_counter() - ts), "edges_before": n_in, "edges_after": int(gout.n_edges),
+                     "max_offset_parallel_paths": mopp, **gs.timing, "call": "alga_gpu_cut_triangles (host buffers)"}
+        from oracle import harness as _h
+        if _h.available() and not args.no_cpu:
+            t0c = time.perf_counter()
+            ref = _h.run_cut_triangles(edges_in, w.reads.n, mopp, threads=_cpu_threads())
+            triangles["cpu_reference"] = {"seconds_incl_io": time.perf_counter() - t0c, "cores": _cpu_threads(), "edges_after": int(ref.shape[0]),
+                                          "note": "oracle/_ref harness: the reference's own GraphSimplifier step on the same graph, file IO included"}
+
     preprocess = None
     if world == 1 and args.with_preprocess:
         # ReadPreprocess::getPrefixReads on the strand-reads BEFORE duplicate removal, host to host
@@ -500,6 +524,8 @@ def run_ours(args):
     }
     if supplement:
         line["supplement"] = supplement
+    if triangles:
+        line["triangles"] = triangles
     if preprocess:
         line["preprocess"] = preprocess
     if input_leg:
@@ -522,6 +548,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--with-preprocess", action="store_true",
                     help="also time ReadPreprocess::getPrefixReads (alga_gpu_prefix_reads) on the reads before dedupe")
+    ap.add_argument("--with-triangles", action="store_true",
+                    help="also time the first simplifier step (alga_gpu_cut_triangles) on the graph just built")
     ap.add_argument("--with-input", action="store_true",
                     help="also time InputReader::readInput (alga_gpu_read_input) and the files-to-graph path on FASTA text of the workload")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
