@@ -1758,6 +1758,24 @@ int alga_gpu_files_to_graph(const uint8_t *text1, uint64_t n1, const uint8_t *te
 }
 
 // ---- first simplifier step (simplify.cu) ------------------------------------------------------------------------------
+namespace {
+struct TriangleWs {  // process-wide cached workspace, as for the graph build and the input stage
+    int device = -1;
+    DevBuf row, nbr, off, keep, kept, new_row, onbr, ooff, big, nbig, tn, to, scan_ws;
+    HostBuf h_row, h_nbr, h_off;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    void release() {
+        for (DevBuf *b : {&row, &nbr, &off, &keep, &kept, &new_row, &onbr, &ooff, &big, &nbig, &tn, &to, &scan_ws}) b->release();
+        for (HostBuf *b : {&h_row, &h_nbr, &h_off}) b->release();
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        e0 = e1 = nullptr;
+    }
+};
+std::mutex g_tri_mutex;
+TriangleWs g_tri;
+}  // namespace
+
 int alga_gpu_cut_triangles(const alga_csr *gin, int32_t max_offset, int32_t device, alga_csr *gout, alga_timing *timing) {
     if (!gin || !gout) return fail(ALGA_E_INVALID, "null argument");
     const uint32_t n = gin->n_reads;
@@ -1765,90 +1783,90 @@ int alga_gpu_cut_triangles(const alga_csr *gin, int32_t max_offset, int32_t devi
     if (n && !gin->row_off) return fail(ALGA_E_INVALID, "row_off must not be null");
     if (E && (!gin->nbr || !gin->off)) return fail(ALGA_E_INVALID, "nbr / off must not be null");
     if (n && gin->row_off[n] != E) return fail(ALGA_E_INVALID, "row_off[n] differs from n_edges");
-    memset(gout, 0, sizeof(*gout));
+    std::lock_guard<std::mutex> lock(g_tri_mutex);
     const double t0 = now_ms();
     LaunchCfg cfg;
     uint64_t launches = 0;
     cfg.launches = &launches;
     CKR(pick_device(device, &cfg));
-    DevBuf d_row, d_nbr, d_off, d_keep, d_kept, d_new_row, d_onbr, d_ooff, d_big, d_nbig, d_tn, d_to, scan_ws;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    TriangleWs &w = g_tri;
+    if (w.device != device) w.release();
+    w.device = device;
+    if (!w.e0) CK(cudaEventCreate(&w.e0));
+    if (!w.e1) CK(cudaEventCreate(&w.e1));
+    // the input may be the borrowed result of an earlier call: copy it to the device before the staging buffers are reused
+    CKR(w.row.ensure(((size_t) n + 1) * 8));
+    CKR(w.nbr.ensure((size_t) (E ? E : 1) * 4));
+    CKR(w.off.ensure((size_t) (E ? E : 1) * 4));
+    if (n) CK(cudaMemcpyAsync(w.row.p, gin->row_off, ((size_t) n + 1) * 8, cudaMemcpyHostToDevice, 0));
+    if (E) {
+        CK(cudaMemcpyAsync(w.nbr.p, gin->nbr, (size_t) E * 4, cudaMemcpyHostToDevice, 0));
+        CK(cudaMemcpyAsync(w.off.p, gin->off, (size_t) E * 4, cudaMemcpyHostToDevice, 0));
+    }
+    CK(cudaStreamSynchronize(0));
+    const double t1 = now_ms();
+    memset(gout, 0, sizeof(*gout));
+    gout->n_reads = n;
+    gout->borrowed = 1;
+    CKR(w.h_row.ensure(((size_t) n + 1) * 8));
+    gout->row_off = (uint64_t *) w.h_row.p;
+    memset(gout->row_off, 0, ((size_t) n + 1) * 8);
     float dev_ms = 0;
-    double h2d_ms = 0, d2h_ms = 0;
-    int r = [&]() -> int {
-        gout->n_reads = n;
-        gout->row_off = (uint64_t *) calloc((size_t) n + 1, 8);
-        if (!gout->row_off) return fail(ALGA_E_NOMEM, "host allocation failed");
-        if (!n || !E) return ALGA_OK;
-        CKR(d_row.ensure(((size_t) n + 1) * 8));
-        CKR(d_nbr.ensure((size_t) E * 4));
-        CKR(d_off.ensure((size_t) E * 4));
-        CKR(d_keep.ensure((size_t) E));
-        CKR(d_kept.ensure((size_t) n * 4));
-        CKR(d_new_row.ensure(((size_t) n + 1) * 8));
-        CKR(scan_ws.ensure(scan_workspace_bytes(n)));
-        CK(cudaMemcpy(d_row.p, gin->row_off, ((size_t) n + 1) * 8, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(d_nbr.p, gin->nbr, (size_t) E * 4, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(d_off.p, gin->off, (size_t) E * 4, cudaMemcpyHostToDevice));
-        h2d_ms = now_ms() - t0;
-        CK(cudaEventCreate(&e0));
-        CK(cudaEventCreate(&e1));
-        CK(cudaEventRecord(e0, 0));
-        launch_triangle_marks(d_row.as<uint64_t>(), d_nbr.as<int32_t>(), d_off.as<int32_t>(), n, max_offset, d_keep.as<uint8_t>(),
-                              d_kept.as<uint32_t>(), 0, cfg);
-        launch_scan_u64(d_kept.as<uint32_t>(), d_new_row.as<uint64_t>(), n, scan_ws.p, 0, cfg);
+    uint64_t E2 = 0;
+    if (n && E) {
+        CKR(w.keep.ensure((size_t) E));
+        CKR(w.kept.ensure((size_t) n * 4));
+        CKR(w.new_row.ensure(((size_t) n + 1) * 8));
+        CKR(w.scan_ws.ensure(scan_workspace_bytes(n)));
+        CKR(w.big.ensure((size_t) n * 4));
+        CKR(w.nbig.ensure(4));
+        CK(cudaEventRecord(w.e0, 0));
+        launch_triangle_marks(w.row.as<uint64_t>(), w.nbr.as<int32_t>(), w.off.as<int32_t>(), n, max_offset, w.keep.as<uint8_t>(),
+                              w.kept.as<uint32_t>(), 0, cfg);
+        launch_scan_u64(w.kept.as<uint32_t>(), w.new_row.as<uint64_t>(), n, w.scan_ws.p, 0, cfg);
         CK(cudaGetLastError());
-        uint64_t E2 = 0;
-        CK(cudaMemcpy(&E2, d_new_row.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost));
-        CKR(d_onbr.ensure((size_t) (E2 ? E2 : 1) * 4));
-        CKR(d_ooff.ensure((size_t) (E2 ? E2 : 1) * 4));
-        CKR(d_big.ensure((size_t) n * 4));
-        CKR(d_nbig.ensure(4));
-        CK(cudaMemsetAsync(d_nbig.p, 0, 4, 0));
-        launch_triangle_compact(d_row.as<uint64_t>(), d_nbr.as<int32_t>(), d_off.as<int32_t>(), d_keep.as<uint8_t>(), n,
-                                d_new_row.as<uint64_t>(), d_onbr.as<int32_t>(), d_ooff.as<int32_t>(), 0, cfg);
+        CK(cudaMemcpy(&E2, w.new_row.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost));
+        CKR(w.onbr.ensure((size_t) (E2 ? E2 : 1) * 4));
+        CKR(w.ooff.ensure((size_t) (E2 ? E2 : 1) * 4));
+        CK(cudaMemsetAsync(w.nbig.p, 0, 4, 0));
+        launch_triangle_compact(w.row.as<uint64_t>(), w.nbr.as<int32_t>(), w.off.as<int32_t>(), w.keep.as<uint8_t>(), n,
+                                w.new_row.as<uint64_t>(), w.onbr.as<int32_t>(), w.ooff.as<int32_t>(), 0, cfg);
         // Graph::sortEdgesByIncreasingOffset: rows by (offset, neighbour) -- the (first, second) row sort with the arrays swapped
-        launch_sort_rows(d_new_row.as<uint64_t>(), n, d_ooff.as<int32_t>(), d_onbr.as<int32_t>(), d_big.as<uint32_t>(),
-                         d_nbig.as<uint32_t>(), 0, cfg);
+        launch_sort_rows(w.new_row.as<uint64_t>(), n, w.ooff.as<int32_t>(), w.onbr.as<int32_t>(), w.big.as<uint32_t>(),
+                         w.nbig.as<uint32_t>(), 0, cfg);
         CK(cudaGetLastError());
         uint32_t n_big = 0;
-        CK(cudaMemcpy(&n_big, d_nbig.p, 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&n_big, w.nbig.p, 4, cudaMemcpyDeviceToHost));
         if (n_big) {
-            CKR(d_tn.ensure((size_t) (E2 ? E2 : 1) * 4));
-            CKR(d_to.ensure((size_t) (E2 ? E2 : 1) * 4));
-            launch_sort_big_rows(d_new_row.as<uint64_t>(), d_big.as<uint32_t>(), n_big, d_ooff.as<int32_t>(), d_onbr.as<int32_t>(),
-                                 d_tn.as<int32_t>(), d_to.as<int32_t>(), 0, cfg);
+            CKR(w.tn.ensure((size_t) (E2 ? E2 : 1) * 4));
+            CKR(w.to.ensure((size_t) (E2 ? E2 : 1) * 4));
+            launch_sort_big_rows(w.new_row.as<uint64_t>(), w.big.as<uint32_t>(), n_big, w.ooff.as<int32_t>(), w.onbr.as<int32_t>(),
+                                 w.tn.as<int32_t>(), w.to.as<int32_t>(), 0, cfg);
             CK(cudaGetLastError());
         }
-        CK(cudaEventRecord(e1, 0));
-        CK(cudaEventSynchronize(e1));
-        CK(cudaEventElapsedTime(&dev_ms, e0, e1));
-        const double t1 = now_ms();
-        gout->n_edges = E2;
-        gout->nbr = (int32_t *) malloc((size_t) (E2 ? E2 : 1) * 4);
-        gout->off = (int32_t *) malloc((size_t) (E2 ? E2 : 1) * 4);
-        if (!gout->nbr || !gout->off) return fail(ALGA_E_NOMEM, "host allocation failed");
-        CK(cudaMemcpy(gout->row_off, d_new_row.p, ((size_t) n + 1) * 8, cudaMemcpyDeviceToHost));
+        CK(cudaEventRecord(w.e1, 0));
+        CK(cudaEventSynchronize(w.e1));
+        CK(cudaEventElapsedTime(&dev_ms, w.e0, w.e1));
+    }
+    const double t2 = now_ms();
+    CKR(w.h_nbr.ensure((size_t) (E2 ? E2 : 1) * 4));
+    CKR(w.h_off.ensure((size_t) (E2 ? E2 : 1) * 4));
+    gout->n_edges = E2;
+    gout->nbr = (int32_t *) w.h_nbr.p;
+    gout->off = (int32_t *) w.h_off.p;
+    if (n && E) {
+        CK(cudaMemcpyAsync(gout->row_off, w.new_row.p, ((size_t) n + 1) * 8, cudaMemcpyDeviceToHost, 0));
         if (E2) {
-            CK(cudaMemcpy(gout->nbr, d_onbr.p, (size_t) E2 * 4, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(gout->off, d_ooff.p, (size_t) E2 * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpyAsync(gout->nbr, w.onbr.p, (size_t) E2 * 4, cudaMemcpyDeviceToHost, 0));
+            CK(cudaMemcpyAsync(gout->off, w.ooff.p, (size_t) E2 * 4, cudaMemcpyDeviceToHost, 0));
         }
-        d2h_ms = now_ms() - t1;
-        return ALGA_OK;
-    }();
-    if (e0) cudaEventDestroy(e0);
-    if (e1) cudaEventDestroy(e1);
-    for (DevBuf *b : {&d_row, &d_nbr, &d_off, &d_keep, &d_kept, &d_new_row, &d_onbr, &d_ooff, &d_big, &d_nbig, &d_tn, &d_to, &scan_ws})
-        b->release();
-    if (r != ALGA_OK) {
-        alga_gpu_free_csr(gout);
-        return r;
+        CK(cudaStreamSynchronize(0));
     }
     if (timing) {
         memset(timing, 0, sizeof(*timing));
-        timing->h2d_ms = h2d_ms;
+        timing->h2d_ms = t1 - t0;
         timing->device_ms = dev_ms;
-        timing->d2h_ms = d2h_ms;
+        timing->d2h_ms = now_ms() - t2;
         timing->total_ms = now_ms() - t0;
         timing->kernel_launches = launches;
     }

@@ -344,8 +344,8 @@ int alga_gpu_files_to_graph(const uint8_t *text1, uint64_t n1, const uint8_t *te
  * (GraphSimplifier.cpp:228-349) as simplifyGraphOld runs them first (GraphSimplifier.cpp:110-130): the edge i -> b of
  * offset w <= max_offset (Params::MAX_OFFSET_PARALLEL_PATHS, main.cpp:95) is removed iff the shortest two-hop path
  * i -> a -> b has length exactly w; all decisions are taken on the input graph.  graph_in: host CSR with rows sorted by
- * neighbour (what alga_gpu_prefsuf_build / alga_gpu_supplement return).  graph_out: malloc'ed host CSR (release with
- * alga_gpu_free_csr), rows sorted by (offset, neighbour) -- the order sortEdgesByIncreasingOffset leaves; the reference's
+ * neighbour (what alga_gpu_prefsuf_build / alga_gpu_supplement return).  graph_out: host CSR in borrowed page-locked
+ * buffers (valid until the next call of this function; release with alga_gpu_free_csr), rows sorted by (offset, neighbour) -- the order sortEdgesByIncreasingOffset leaves; the reference's
  * swap-and-pop removal leaves the surviving entries of a row in another order, the edge set is the same. */
 int alga_gpu_cut_triangles(const alga_csr *graph_in, int32_t max_offset, int32_t device, alga_csr *graph_out,
                            alga_timing *timing /* may be NULL */);
