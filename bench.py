@@ -495,6 +495,8 @@ def run_ours(args):
             if best is None or og.timing["total_ms"] < best[1].timing["total_ms"]:
                 best = (msg, og)
         msg, og = best
+        if args.workload != "cfg3" and args.scale == 1.0:  # same generator and seed as the main workload: the same graph must come out
+            assert (og.reads.n, og.graph.n_edges) == (n_nodes_total, n_edges), (og.reads.n, og.graph.n_edges, n_nodes_total, n_edges)
         input_leg["files_to_graph"] = {"ms_python": msg, "nodes": og.reads.n, "edges": og.graph.n_edges, "params": og.params,
                                        **og.timing, "records_per_s": n_rec / (og.timing["total_ms"] / 1e3),
                                        "h2d_bytes": nbytes, "d2h_bytes": int(og.reads.words.nbytes + og.reads.len_nt.nbytes * 2 + og.reads.n

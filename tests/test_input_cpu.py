@@ -120,3 +120,11 @@ def test_files_to_graph_matches_stock_binary(name):
     assert rs.n == int(g["n"])
     assert np.array_equal(edges, g["edges"])
     assert po.shape[0] == rs.n
+
+
+def test_file_type_follows_the_extension():
+    """Params.cpp:332-335."""
+    from alga_b200.input_reader import FASTA, FASTQ, PLAIN, file_type_of
+    assert file_type_of("/data/x_1.fasta") == FASTA and file_type_of("reads.pfasta") == FASTA
+    assert file_type_of("a.b/reads.fastq") == FASTQ and file_type_of("reads.fq") == FASTQ
+    assert file_type_of("reads.txt") == PLAIN and file_type_of("dir.v2/reads") == PLAIN and file_type_of("reads.fa") == PLAIN
