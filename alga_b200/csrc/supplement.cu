@@ -21,6 +21,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <utility>
@@ -313,6 +314,15 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
     Buf d_km, d_cnt, d_poff, d_pj, scan_ws;
     Pinned h_poff, h_pj, h_verdict;
     std::vector<uint64_t> bm;                                  // branch markers of one group: D rows of ceil(D/64) words
+    struct Group {
+        uint32_t p, q, level;  // k-mers [p, q) of equal hash; see the replay below
+    };
+    std::vector<Group> grp, by_level;
+    std::vector<size_t> level_start;
+    std::vector<uint32_t> last_level(n ? n : 1, 0u);           // per read: level of the last group it was a source in
+    std::vector<std::vector<uint64_t>> tbm(n_thr);             // branch markers per worker thread
+    const bool serial_replay = getenv("ALGA_SUP_SERIAL") != nullptr;  // A/B switch: groups strictly one after the other
+    uint64_t levels_total = 0;
     double gpu_ms = 0, t_kmers = 0, t_sort = 0, t_enum = 0, t_verify = 0, t_replay = 0;
     uint64_t pairs_total = 0;
     int32_t prio[4] = {0, 1, 2, 3};
@@ -415,64 +425,109 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
         t_verify += now_ms() - tb;
         // ---- replay of the ordered loop (:64-84) with the verdicts at hand; sequential: groups share graph rows
         const double te = now_ms();
-        // The pairs that passed the static filters were listed per k-mer (as i) by the enumeration above, so the loop below
-        // only visits those; the pair's offset and second read follow from the two k-mers.
-        size_t pf = 0;  // k-mers whose row header has been prefetched
-        for (size_t k = 0; k < (size_t) kBucketsSort; k++) {
+        // The pairs that passed the static filters were listed per k-mer (as i) by the enumeration above, so a group only
+        // visits those; the pair's offset and second read follow from the two k-mers.
+        //
+        // A group reads and writes nothing but the rows of its own source reads (the k-mers i that have pairs) and its own
+        // branch markers, so two groups depend on each other only if they share a source read, and then their order matters.
+        // Levels: level(g) = 1 + the highest level of an earlier group that shares a source read with g.  Groups of one
+        // level are independent and run in parallel; the levels run one after the other -- every row sees its groups in
+        // exactly the order of the sequential loop.
+        auto process_group = [&](size_t p, size_t q, std::vector<uint64_t> &marks) {
+            const int D = (int) (q - p);
+            const int RW = (D + 63) >> 6;  // words per branch-marker row
+            marks.assign((size_t) D * RW, 0ull);
+            for (int i = D - 2; i >= 0; i--) {
+                const size_t x = p + (size_t) i;
+                const uint64_t c0 = pair_off[x], c1 = pair_off[x + 1];
+                if (c0 == c1) continue;
+                const Kmer &ki = km[x];
+                const int id1 = (int) ki.read;
+                auto &row = V[(size_t) id1];
+                // the reference spreads the row into a dense `neighbors` array (:64-66); rows hold one entry per target
+                // and stay short, so the entry is looked up in the row itself -- no random access per pair
+                uint64_t *bi = marks.data() + (size_t) i * RW;
+                for (uint64_t c = c0; c < c1; c++) {
+                    const Kmer &kj = km[pair_j[c]];
+                    const int j = (int) (pair_j[c] - p);
+                    const int id2 = (int) kj.read, offset = ki.ind - kj.ind;
+                    const uint8_t can = verdict[c];
+                    if (!((bi[j >> 6] >> (j & 63)) & 1ull)) {
+                        int *cur = nullptr;  // offset of the edge id1 -> id2, if there is one (= neighbors[id2])
+                        for (auto &e : row) {
+                            if (e.first == id2) {
+                                cur = &e.second;
+                                break;
+                            }
+                        }
+                        int cur_off = cur ? *cur : INF;
+                        if (cur_off > offset && can) {
+                            // Graph::addDirectedEdge (Graph.cpp:53-71): one entry per target, smallest offset
+                            if (cur) *cur = offset;
+                            else row.push_back({id2, offset});
+                            cur_off = offset;
+                        }
+                        if (cur_off != INF) {
+                            bi[j >> 6] |= 1ull << (j & 63);
+                            const uint64_t *bj = marks.data() + (size_t) j * RW;
+                            for (int t = 0; t < RW; t++) bi[t] |= bj[t];
+                        }
+                    }
+                }
+            }
+        };
+        // groups that have pairs at all, in loop order, with their levels
+        grp.clear();
+        std::fill(last_level.begin(), last_level.end(), 0u);
+        uint32_t n_levels = 0;
+        for (size_t k = 0; k < (size_t) kBucketsSort && n_pairs; k++) {
             size_t p = bstart[k], q = p;
             const size_t end = bstart[k + 1];
             while (p < end) {
                 while (q < end && km[q].hash == km[p].hash) q++;
-                const int D = (int) (q - p);
-                const int RW = (D + 63) >> 6;  // words per branch-marker row
-                if (D > 1) bm.assign((size_t) D * RW, 0ull);
-                // rows are scattered over the heap: fetch the headers of the next k-mers' rows and the entries of this
-                // group's rows ahead of their use (the loop is bound by these cache misses, not by arithmetic)
-                for (size_t hi_pf = q + 48 < nk ? q + 48 : nk; pf < hi_pf; pf++)
-                    if (pf >= q) __builtin_prefetch(&V[(size_t) km[pf].read]);
-                if (D > 1)
-                    for (size_t x = p; x < q; x++) __builtin_prefetch(V[(size_t) km[x].read].data());
-                for (int i = D - 2; i >= 0; i--) {
-                    const size_t x = p + (size_t) i;
-                    const uint64_t c0 = pair_off[x], c1 = pair_off[x + 1];
-                    if (c0 == c1) continue;
-                    const Kmer &ki = km[x];
-                    const int id1 = (int) ki.read;
-                    auto &row = V[(size_t) id1];
-                    // the reference spreads the row into a dense `neighbors` array (:64-66); rows hold one entry per target
-                    // and stay short, so the entry is looked up in the row itself -- no random access per pair
-                    uint64_t *bi = bm.data() + (size_t) i * RW;
-                    for (uint64_t c = c0; c < c1; c++) {
-                        const Kmer &kj = km[pair_j[c]];
-                        const int j = (int) (pair_j[c] - p);
-                        const int id2 = (int) kj.read, offset = ki.ind - kj.ind;
-                        const uint8_t can = verdict[c];
-                        if (!((bi[j >> 6] >> (j & 63)) & 1ull)) {
-                            int *cur = nullptr;  // offset of the edge id1 -> id2, if there is one (= neighbors[id2])
-                            for (auto &e : row) {
-                                if (e.first == id2) {
-                                    cur = &e.second;
-                                    break;
-                                }
-                            }
-                            int cur_off = cur ? *cur : INF;
-                            if (cur_off > offset && can) {
-                                // Graph::addDirectedEdge (Graph.cpp:53-71): one entry per target, smallest offset
-                                if (cur) *cur = offset;
-                                else row.push_back({id2, offset});
-                                cur_off = offset;
-                            }
-                            if (cur_off != INF) {
-                                bi[j >> 6] |= 1ull << (j & 63);
-                                const uint64_t *bj = bm.data() + (size_t) j * RW;
-                                for (int t = 0; t < RW; t++) bi[t] |= bj[t];
-                            }
-                        }
-                    }
+                if (q - p > 1 && pair_off[q - 1] > pair_off[p]) {  // the last k-mer of a group never plays i
+                    uint32_t lvl = 0;
+                    for (size_t x = p; x + 1 < q; x++)
+                        if (pair_off[x + 1] > pair_off[x]) lvl = std::max(lvl, last_level[(size_t) km[x].read]);
+                    lvl++;
+                    for (size_t x = p; x + 1 < q; x++)
+                        if (pair_off[x + 1] > pair_off[x]) last_level[(size_t) km[x].read] = lvl;
+                    grp.push_back(Group{(uint32_t) p, (uint32_t) q, lvl});
+                    n_levels = std::max(n_levels, lvl);
                 }
                 p = q;
             }
         }
+        if (serial_replay) {
+            for (const Group &g : grp) process_group(g.p, g.q, bm);
+        } else {
+            // counting sort by level (stable: loop order inside a level, which only matters for locality)
+            level_start.assign((size_t) n_levels + 2, 0);
+            for (const Group &g : grp) level_start[(size_t) g.level + 1]++;
+            for (size_t l = 0; l + 1 < level_start.size(); l++) level_start[l + 1] += level_start[l];
+            by_level.resize(grp.size());
+            {
+                std::vector<size_t> cur(level_start.begin(), level_start.end() - 1);
+                for (const Group &g : grp) by_level[cur[g.level]++] = g;
+            }
+            for (uint32_t l = 1; l <= n_levels; l++) {
+                const size_t a = level_start[l], b = level_start[(size_t) l + 1];
+                if (b - a < 4096) {  // not worth waking the threads
+                    for (size_t z = a; z < b; z++) process_group(by_level[z].p, by_level[z].q, bm);
+                    continue;
+                }
+                run_threads([&](unsigned t) {
+                    std::vector<uint64_t> &marks = tbm[t];
+                    const size_t z0 = a + (b - a) * t / n_thr, z1 = a + (b - a) * (t + 1) / n_thr;
+                    for (size_t z = z0; z < z1; z++) {
+                        if (z + 1 < z1)  // rows are scattered over the heap: fetch the next group's row headers early
+                            for (size_t x = by_level[z + 1].p; x < by_level[z + 1].q; x++) __builtin_prefetch(&V[(size_t) km[x].read]);
+                        process_group(by_level[z].p, by_level[z].q, marks);
+                    }
+                });
+            }
+        }
+        levels_total += n_levels;
         // ---- retainOnlySmallestOffset (GraphCreatorKmerBased.cpp:87; main.cpp:346 after the last pass)
         run_threads([&](unsigned t) {
             const size_t r0 = (size_t) n * t / n_thr, r1 = (size_t) n * (t + 1) / n_thr;
@@ -529,6 +584,7 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
         tm->stage_ms[4] = t_replay;  // ordered replay + row dedupe (host)
         tm->stage_ms[5] = (double) n_ids;        // diagnostics: dead-end reads that took part,
         tm->stage_ms[6] = (double) pairs_total;  // pairs verified on the GPU over the four passes
+        tm->stage_ms[7] = (double) levels_total; // dependency levels of the replay over the four passes
     }
     return ALGA_OK;
 }

@@ -251,7 +251,7 @@ class GraphCreatorLI:
                        "kernel_launches": tm.kernel_launches,
                        "stage_ms": dict(zip(("li_kmers", "bucket_sort", "enumerate", "can_align", "replay"), list(tm.stage_ms)[:5])),
                        "n_dead_end_reads": int(tm.stage_ms[5]),
-                       "n_pairs_verified": int(tm.stage_ms[6])}
+                       "n_pairs_verified": int(tm.stage_ms[6]), "replay_levels": int(tm.stage_ms[7])}
         return self.graph
 
 
