@@ -116,15 +116,20 @@ int sup_fail(int code, const char *fmt, ...) {
                             #call, cudaGetErrorString(e_), __FILE__, __LINE__);                                \
     } while (0)
 
-struct Buf {  // device buffer freed on scope exit
+struct Buf {  // device buffer freed on scope exit; alloc() only ever grows it (a cudaFree + cudaMalloc per pass cost up to
+              // 0.5 s on the B200 box)
     void *p = nullptr;
+    size_t cap = 0;
     ~Buf() {
         if (p) cudaFree(p);
     }
     int alloc(size_t bytes) {
+        if (p && bytes <= cap) return ALGA_OK;
         if (p) cudaFree(p);
-        p = nullptr;
-        SCK(cudaMalloc(&p, bytes ? bytes : 16));
+        p = nullptr, cap = 0;
+        const size_t want = (bytes ? bytes : 16) + bytes / 8;
+        SCK(cudaMalloc(&p, want));
+        cap = want;
         return ALGA_OK;
     }
     template <class T>
@@ -322,6 +327,7 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
     std::vector<uint32_t> last_level(n ? n : 1, 0u);           // per read: level of the last group it was a source in
     std::vector<std::vector<uint64_t>> tbm(n_thr);             // branch markers per worker thread
     const bool serial_replay = getenv("ALGA_SUP_SERIAL") != nullptr;  // A/B switch: groups strictly one after the other
+    const bool trace = getenv("ALGA_SUP_TRACE") != nullptr;           // per-pass timing of the enumeration on stderr
     uint64_t levels_total = 0;
     double gpu_ms = 0, t_kmers = 0, t_sort = 0, t_enum = 0, t_verify = 0, t_replay = 0;
     uint64_t pairs_total = 0;
@@ -389,13 +395,20 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
             if (d_km.alloc(nk * sizeof(Kmer)) || d_cnt.alloc(nk * 4) || d_poff.alloc((nk + 1) * 8) ||
                 scan_ws.alloc(scan_workspace_bytes(nk)) || h_poff.ensure((nk + 1) * 8))
                 return ALGA_E_NOMEM;
+            const double tq0 = now_ms();
             SCK(cudaMemcpy(d_km.p, km, nk * sizeof(Kmer), cudaMemcpyHostToDevice));
+            const double tq1 = now_ms();
             const int grid = grid_for(nk, 128, cfg, 16);
             enumerate_pairs_kernel<false><<<grid, 128>>>(d_km.as<Kmer>(), (uint32_t) nk, pf_params, d_cnt.as<uint32_t>(), nullptr,
                                                          nullptr, nullptr);
+            if (trace) SCK(cudaDeviceSynchronize());
+            const double tq2 = now_ms();
             launch_scan_u64(d_cnt.as<uint32_t>(), d_poff.as<uint64_t>(), nk, scan_ws.p, 0, cfg);
             SCK(cudaGetLastError());
             SCK(cudaMemcpy(h_poff.p, d_poff.p, (nk + 1) * 8, cudaMemcpyDeviceToHost));
+            if (trace)
+                fprintf(stderr, "alga_gpu supplement pass %d: nk %zu, alloc %.1f ms, upload %.1f ms, count kernel %.1f ms, scan + read-back %.1f ms\n",
+                        pass, nk, tq0 - td, tq1 - tq0, tq2 - tq1, now_ms() - tq2);
             pair_off = h_poff.as<uint64_t>();
             n_pairs = pair_off[nk];
             launches += 1;
