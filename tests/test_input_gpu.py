@@ -243,3 +243,26 @@ def test_read_input_offsets_beyond_4_gib(gpu):
     del text
     want, _ = oracle.read_input(b">h\n" + seqs[0] + b"\n" + tail, None, oracle.INPUT_FASTA)
     assert_same_reads(got, want.len_nt, want.word_off, want.words)
+
+
+def test_build_graph_cli_writes_the_file_alga_loads(gpu, tmp_path):
+    """python -m alga_b200 build-graph: the graph file of the zero-code-change boundary (main.cpp:242), from the input files."""
+    import json
+    import subprocess
+    import sys
+
+    from alga_b200.graph_file import graph_file_name, read_graph
+
+    t1, t2, ft = front_case("front_pe")
+    (tmp_path / "x_1.fasta").write_bytes(t1)
+    (tmp_path / "x_2.fasta").write_bytes(t2)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "alga_b200", "build-graph", "--file1", str(tmp_path / "x_1.fasta"), "--file2",
+                        str(tmp_path / "x_2.fasta"), "--out-dir", str(tmp_path)], cwd=root, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    g = np.load(os.path.join(GOLD, "front_pe.npz"))
+    back = read_graph(str(tmp_path / graph_file_name("x_1.fasta")))
+    assert info["nodes"] == back.n == int(g["n"])
+    assert np.array_equal(back.edges(), g["edges"])
