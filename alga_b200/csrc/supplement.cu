@@ -359,30 +359,36 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
         const size_t n_slots = (size_t) n_ids * IV;
         kbucket.resize(n_slots);
         std::fill(bstart.begin(), bstart.end(), 0u);
-        size_t nk = 0;
-        for (size_t slot = 0; slot < n_slots; slot++) {
-            if (hi[slot] < 0) {
-                kbucket[slot] = 0xFFFFFFFFu;
-                continue;
+        // bucket of every k-mer (threads over slot ranges) ...
+        run_threads([&](unsigned t) {
+            const size_t s0 = n_slots * t / n_thr, s1 = n_slots * (t + 1) / n_thr;
+            for (size_t slot = s0; slot < s1; slot++)
+                kbucket[slot] = hi[slot] < 0 ? 0xFFFFFFFFu
+                                             : (uint32_t) (int) ((kBucketsSort - 1) * ((double) hh[slot] / B));  // GraphCreatorKmerBased.cpp:233
+        });
+        // ... bucket sizes (threads over bucket ranges: every thread scans all slots and counts its own buckets) ...
+        run_threads([&](unsigned t) {
+            const uint32_t b0 = (uint32_t) ((size_t) kBucketsSort * t / n_thr), b1 = (uint32_t) ((size_t) kBucketsSort * (t + 1) / n_thr);
+            for (size_t slot = 0; slot < n_slots; slot++) {
+                const uint32_t b = kbucket[slot];
+                if (b >= b0 && b < b1) bstart[(size_t) b + 1]++;
             }
-            const uint32_t ind = (uint32_t) (int) ((kBucketsSort - 1) * ((double) hh[slot] / B));  // GraphCreatorKmerBased.cpp:233
-            kbucket[slot] = ind;
-            bstart[(size_t) ind + 1]++;
-            nk++;
-        }
+        });
         for (size_t k = 0; k < (size_t) kBucketsSort; k++) bstart[k + 1] += bstart[k];
+        const size_t nk = bstart[(size_t) kBucketsSort];
         if (km_buf.ensure((nk ? nk : 1) * sizeof(Kmer))) return ALGA_E_NOMEM;
         Kmer *km = km_buf.as<Kmer>();
-        {
-            std::vector<uint32_t> cursor(bstart.begin(), bstart.end() - 1);
-            for (size_t slot = 0; slot < n_slots; slot++) {
-                if (kbucket[slot] == 0xFFFFFFFFu) continue;
-                const uint32_t id = ids[slot / (size_t) IV];
-                km[cursor[kbucket[slot]]++] = Kmer{id, hh[slot], hi[slot], h->len_nt[id]};
-            }
-        }
+        // ... placement in slot order (= the reference's fill order inside a bucket: reads by id, k-mers by interval), again
+        // with every thread scanning all slots for its own bucket range, and std::sort of each bucket
         run_threads([&](unsigned t) {
-            const size_t b0 = (size_t) kBucketsSort * t / n_thr, b1 = (size_t) kBucketsSort * (t + 1) / n_thr;
+            const uint32_t b0 = (uint32_t) ((size_t) kBucketsSort * t / n_thr), b1 = (uint32_t) ((size_t) kBucketsSort * (t + 1) / n_thr);
+            std::vector<uint32_t> cursor(bstart.begin() + b0, bstart.begin() + b1);
+            for (size_t slot = 0; slot < n_slots; slot++) {
+                const uint32_t b = kbucket[slot];
+                if (b < b0 || b >= b1) continue;
+                const uint32_t id = ids[slot / (size_t) IV];
+                km[cursor[b - b0]++] = Kmer{id, hh[slot], hi[slot], h->len_nt[id]};
+            }
             for (size_t k = b0; k < b1; k++)
                 if (bstart[k + 1] - bstart[k] > 1) std::sort(km + bstart[k], km + bstart[k + 1]);
         });
