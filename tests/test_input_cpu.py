@@ -128,3 +128,80 @@ def test_file_type_follows_the_extension():
     assert file_type_of("/data/x_1.fasta") == FASTA and file_type_of("reads.pfasta") == FASTA
     assert file_type_of("a.b/reads.fastq") == FASTQ and file_type_of("reads.fq") == FASTQ
     assert file_type_of("reads.txt") == PLAIN and file_type_of("dir.v2/reads") == PLAIN and file_type_of("reads.fa") == PLAIN
+
+
+@pytest.mark.skipif(not harness.available(), reason="oracle/_ref not built")
+def test_read_input_oracle_matches_reference_on_random_files():
+    """Random small files with every oddity the reader has a rule for (spaces, short lines, N, U, repeats, empty lines, missing
+    final newline, FASTQ quality noise): the oracle must produce exactly the reference's Global::READS -- or fail where it exits."""
+    n_checked = n_failed = 0
+    for trial, (t1, t2, ft, paired) in enumerate(random_input_files(2024, 40)):
+        try:
+            ref = harness.run_read_input(t1, t2, ft)
+        except RuntimeError:
+            ref = None
+        try:
+            got, _ = oracle.read_input(t1, t2, ft)
+        except ValueError:
+            got = None
+        if ref is None:
+            # the reference died: a bad character, or -- with unequal mate files -- its out-of-range interleave (undefined)
+            n_failed += 1
+            assert got is None or paired, f"trial {trial}: the reference exits, the oracle does not"
+            continue
+        if got is None:
+            assert paired, f"trial {trial}: the oracle fails, the reference does not"  # unequal mate files only
+            continue
+        assert same_reads(got, ref.len_nt, ref.word_off, ref.words), f"trial {trial} (type {ft}, paired {paired})"
+        n_checked += 1
+    assert n_checked >= 20
+
+
+def random_input_files(seed, n_trials):
+    """Small random input files of all three types with the reader's special cases sprinkled in -> (text1, text2, type, paired)."""
+    rng = np.random.default_rng(seed)
+    nt = b"ACGT"
+
+    def seq():
+        u = rng.random()
+        ln = int(rng.integers(1, 60)) if u < 0.25 else int(rng.integers(60, 200))
+        s = bytes(nt[i] for i in rng.integers(0, 4, size=ln))
+        if u > 0.9:
+            per = int(rng.integers(1, 25))
+            s = (s[:per] * (ln // per + 1))[:ln]
+        if rng.random() < 0.1:
+            k = int(rng.integers(0, len(s)))
+            s = s[:k] + b"N" + s[k + 1:]
+        if rng.random() < 0.1:
+            s = s.replace(b"T", b"U")
+        if rng.random() < 0.1:
+            s = b" " * int(rng.integers(1, 4)) + s
+        if rng.random() < 0.1:
+            s = s + b" extra words"
+        return s
+
+    for trial in range(n_trials):
+        ft = int(rng.integers(0, 3))
+        paired = rng.random() < 0.5
+        n = int(rng.integers(0, 12))
+        texts = []
+        for _ in range(2 if paired else 1):
+            recs = []
+            for i in range(n):
+                s = seq()
+                if rng.random() < 0.03:
+                    s = b""                      # reading stops here (InputReader.cpp:284)
+                if rng.random() < 0.02:
+                    s = s[:1] + b"x" + s[2:]     # the reference exits (InputReader.cpp:324-327)
+                if ft == oracle.INPUT_FASTA:
+                    recs.append(b">r%d some text\n" % i + s + b"\n")
+                elif ft == oracle.INPUT_FASTQ:
+                    q = bytes(rng.integers(33, 74, size=len(s), dtype=np.uint8).tolist())
+                    recs.append(b"@r%d\n" % i + s + b"\n+\n" + q + b"\n")
+                else:
+                    recs.append(s.split(b" ")[-1 if s.startswith(b" ") else 0] + [b"\n", b" ", b"\t", b"\n\n"][int(rng.integers(0, 4))])
+            t = b"".join(recs)
+            if t.endswith(b"\n") and rng.random() < 0.3:
+                t = t[:-1]
+            texts.append(t)
+        yield texts[0], (texts[1] if paired else None), ft, paired

@@ -266,3 +266,26 @@ def test_build_graph_cli_writes_the_file_alga_loads(gpu, tmp_path):
     back = read_graph(str(tmp_path / graph_file_name("x_1.fasta")))
     assert info["nodes"] == back.n == int(g["n"])
     assert np.array_equal(back.edges(), g["edges"])
+
+
+def test_read_input_random_files(gpu):
+    """The random small files of the CPU suite (all three types, spaces, short lines, N, U, repeats, empty lines, bad characters,
+    unequal mate files): the CUDA reader and the oracle agree on the reads, and fail on the same inputs."""
+    from tests.test_input_cpu import random_input_files
+    n_ok = n_err = 0
+    for trial, (t1, t2, ft, paired) in enumerate(random_input_files(77, 120)):
+        try:
+            want, _ = oracle.read_input(t1, t2, ft)
+        except ValueError:
+            want = None
+        try:
+            got = InputReader(ft).readInput(t1, t2)
+        except _lib.AlgaGpuError:
+            got = None
+        assert (got is None) == (want is None), f"trial {trial} (type {ft}, paired {paired})"
+        if want is None:
+            n_err += 1
+            continue
+        assert_same_reads(got, want.len_nt, want.word_off, want.words)
+        n_ok += 1
+    assert n_ok >= 60 and n_err >= 1
