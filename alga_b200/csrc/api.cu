@@ -262,6 +262,14 @@ void size_table(SeedTable &t, uint32_t entries, uint32_t n_reads, int world = 1)
     t.id_bits = bits;
     t.id_mask = (uint32_t) ((1ull << bits) - 1ull);
     t.tag_mask = (uint32_t) ((1ull << (32 - bits)) - 1ull);
+    t.min_m = 0;
+}
+
+// Experimental, off unless ALGA_PS_MINIMIZER=<m> is set: buckets chosen by the minimizer of the seed
+// window (its smallest m-mer) instead of by the window, for seed tables far beyond L2.  Needs a seed of at least m + 4.
+uint32_t minimizer_setting(int seed_nt) {
+    static const int m = getenv("ALGA_PS_MINIMIZER") ? atoi(getenv("ALGA_PS_MINIMIZER")) : 0;
+    return (m >= 8 && m <= 28 && seed_nt >= m + 4) ? (uint32_t) m : 0u;
 }
 
 // s2 != nullptr: everything that concerns the suffix table goes to s2
@@ -269,6 +277,7 @@ int stage_index_begin(alga_ps_plan *plan, cudaStream_t s, cudaStream_t s2 = null
     if (!plan->bound) return fail(ALGA_E_INVALID, "no read set bound to the plan");
     size_table(plan->Tp, plan->stats.n_prefix, plan->R.n);
     size_table(plan->Ts, plan->stats.n_suffix, plan->R.n);
+    plan->Tp.min_m = plan->Ts.min_m = minimizer_setting(plan->P.seed_nt);
     const size_t bp = (size_t) plan->Tp.n_buckets * kSlotsPerBucket * 4, bs = (size_t) plan->Ts.n_buckets * kSlotsPerBucket * 4;
     CKR(plan->tp.ensure(bp));
     CKR(plan->ts.ensure(bs));
@@ -678,6 +687,7 @@ int check_shard(alga_ps_plan *plan, const alga_ps_shard *sh, uint32_t *lo, uint3
     if (sh->table_prefix && sh->table_suffix) {  // the caller's (sliced, exchanged) seed tables are the plan's tables
         size_table(plan->Tp, sh->n_total, sh->n_total, sh->world);
         size_table(plan->Ts, sh->n_total, sh->n_total, sh->world);
+        plan->Tp.min_m = plan->Ts.min_m = minimizer_setting(plan->P.seed_nt);
         plan->Tp.slots = (uint32_t *) sh->table_prefix;
         plan->Ts.slots = (uint32_t *) sh->table_suffix;
         plan->index_valid = true;

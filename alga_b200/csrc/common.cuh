@@ -166,6 +166,9 @@ struct SeedTable {
     uint32_t id_bits;   // bits of a read id, <= 31 (edge arrays carry int32 ids)
     uint32_t id_mask;   // (1 << id_bits) - 1
     uint32_t tag_mask;  // (1 << (32 - id_bits)) - 1; the all-ones tag is never used, so no entry equals kEmptySlot
+    uint32_t min_m;     // 0: the bucket is chosen by the hash of the seed window.  m > 0 (experimental): by
+                        // the minimizer of the window -- its smallest scrambled m-mer -- so that the windows a read probes at
+                        // consecutive lengths share buckets; the window hash stays the tag
 };
 
 // 32 bits of a packed read starting at bit position `bit`.
@@ -240,6 +243,28 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 __device__ __forceinline__ uint32_t bucket_of(uint64_t h, uint32_t n_buckets) {
     return __umulhi((uint32_t) (h >> 32), n_buckets);
 }
+// Minimizer of a seed window (`win` = its 2 * seed_nt bits): the smallest scrambled m-mer.  Equal windows have equal
+// minimizers, so they still meet in one bucket; neighbouring windows of a read mostly share theirs.
+__device__ __forceinline__ uint32_t window_minimizer(uint64_t win, uint32_t seed_nt, uint32_t m) {
+    const uint64_t mask = (1ull << (2u * m)) - 1ull;  // m < 32
+    uint32_t best = 0xFFFFFFFFu;
+    for (uint32_t j = 0; j + m <= seed_nt; j++) {
+        const uint64_t x = (win >> (2u * j)) & mask;
+        uint32_t v = ((uint32_t) x ^ ((uint32_t) (x >> 32) * 0x85EBCA6Bu)) * 0x9E3779B1u;
+        v ^= v >> 15;
+        best = min(best, v);
+    }
+    return best;
+}
+// bucket of a seed window with hash h
+template <bool MINI>
+__device__ __forceinline__ uint32_t bucket_index(const SeedTable &t, uint64_t win, uint64_t h, uint32_t seed_nt) {
+    if (!MINI) return bucket_of(h, t.n_buckets);
+    return bucket_of(mix64((uint64_t) window_minimizer(win, seed_nt, t.min_m)), t.n_buckets);
+}
+__device__ __forceinline__ uint32_t bucket_index_rt(const SeedTable &t, uint64_t win, uint64_t h, uint32_t seed_nt) {
+    return t.min_m ? bucket_index<true>(t, win, h, seed_nt) : bucket_of(h, t.n_buckets);
+}
 // next bucket of a chain (rare path)
 __device__ __forceinline__ uint32_t next_bucket(const SeedTable &t, uint32_t bk) {
     const uint32_t nb = bk + 1;
@@ -269,9 +294,20 @@ __device__ __forceinline__ void load_bucket_na(const uint32_t *__restrict__ p, u
 
 // Walk the bucket chain of hash h and call f(read_id) for every entry whose tag matches.
 template <class F>
+__device__ __forceinline__ void probe_seed_at(const SeedTable &t, uint64_t h, uint32_t bk, F &&f);
+template <class F>
 __device__ __forceinline__ void probe_seed(const SeedTable &t, uint64_t h, F &&f) {
+    probe_seed_at(t, h, bucket_of(h, t.n_buckets), f);
+}
+// the same for a seed window `win` of seed_nt nucleotides (honours t.min_m)
+template <class F>
+__device__ __forceinline__ void probe_seed_window(const SeedTable &t, uint64_t win, uint32_t seed_nt, F &&f) {
+    const uint64_t h = mix64(win);
+    probe_seed_at(t, h, bucket_index_rt(t, win, h, seed_nt), f);
+}
+template <class F>
+__device__ __forceinline__ void probe_seed_at(const SeedTable &t, uint64_t h, uint32_t bk, F &&f) {
     const uint32_t tag = tag_of(t, h);
-    uint32_t bk = bucket_of(h, t.n_buckets);
     while (true) {
         uint32_t e[8];
         load_bucket(t.slots + (uint64_t) bk * kSlotsPerBucket, e);
@@ -284,9 +320,12 @@ __device__ __forceinline__ void probe_seed(const SeedTable &t, uint64_t h, F &&f
     }
 }
 
+__device__ __forceinline__ void insert_seed_at(const SeedTable &t, uint64_t h, uint32_t bk, uint32_t id);
 __device__ __forceinline__ void insert_seed(const SeedTable &t, uint64_t h, uint32_t id) {
+    insert_seed_at(t, h, bucket_of(h, t.n_buckets), id);
+}
+__device__ __forceinline__ void insert_seed_at(const SeedTable &t, uint64_t h, uint32_t bk, uint32_t id) {
     const uint32_t entry = tag_of(t, h) | id;
-    uint32_t bk = bucket_of(h, t.n_buckets);
     while (true) {
         uint32_t *base = t.slots + (uint64_t) bk * kSlotsPerBucket;
         // one look at the whole bucket (L2), then CAS from its first empty slot on: buckets fill front to back

@@ -68,14 +68,14 @@ __global__ void build_index_kernel(ReadsDev R, PsDev P, SeedTable tp, SeedTable 
         if (len == 0 || (int64_t) len < P.lmin) continue;
         const uint32_t *p = read_ptr(R, (uint32_t) i);
         if ((which & 1) && flag_to(R, (uint32_t) i)) {
-            const uint64_t h = mix64(bits64(p, 0) & P.seed_mask);
-            const uint32_t bk = bucket_of(h, tp.n_buckets);
-            if (bk >= b_lo && bk < b_hi) insert_seed(tp, h, (uint32_t) i);
+            const uint64_t win = bits64(p, 0) & P.seed_mask, h = mix64(win);
+            const uint32_t bk = bucket_index_rt(tp, win, h, (uint32_t) P.seed_nt);
+            if (bk >= b_lo && bk < b_hi) insert_seed_at(tp, h, bk, (uint32_t) i);
         }
         if ((which & 2) && flag_from(R, (uint32_t) i) && (int64_t) len - P.min_offset >= P.lmin) {
-            const uint64_t h = mix64(bits64(p, 2u * (len - (uint32_t) P.seed_nt)) & P.seed_mask);
-            const uint32_t bk = bucket_of(h, ts.n_buckets);
-            if (bk >= b_lo && bk < b_hi) insert_seed(ts, h, (uint32_t) i);
+            const uint64_t win = bits64(p, 2u * (len - (uint32_t) P.seed_nt)) & P.seed_mask, h = mix64(win);
+            const uint32_t bk = bucket_index_rt(ts, win, h, (uint32_t) P.seed_nt);
+            if (bk >= b_lo && bk < b_hi) insert_seed_at(ts, h, bk, (uint32_t) i);
         }
     }
 }
@@ -200,7 +200,7 @@ __device__ __forceinline__ void phase1_generic_read(const ReadsDev &R, const See
             if (L >= P.lmin) {
                 const uint32_t o = lenb - (uint32_t) L;
                 const uint64_t w = bits64(pb, 2u * o) & P.seed_mask;
-                probe_seed(T, mix64(w), [&](uint32_t c) {
+                probe_seed_window(T, w, (uint32_t) P.seed_nt, [&](uint32_t c) {
                     if (c == b) return;
                     if ((int64_t) R.len[c] < L) return;
                     // prefix(c, L) == suffix(b, L)
@@ -352,7 +352,7 @@ __device__ __forceinline__ uint32_t scan_hits(const ReadsDev &R, const SeedTable
     uint32_t best = kNone;
     int nh = 0;
     const uint64_t w = bits64(pc, 2u * (uint32_t) (L - P.seed_nt)) & P.seed_mask;
-    probe_seed(T, mix64(w), [&](uint32_t b) {
+    probe_seed_window(T, w, (uint32_t) P.seed_nt, [&](uint32_t b) {
         if (b == c || (int64_t) b <= floor_b) return;
         const uint32_t lenb = R.len[b];
         if ((int64_t) lenb - P.min_offset < L) return;

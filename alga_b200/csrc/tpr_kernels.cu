@@ -271,7 +271,7 @@ __device__ __forceinline__ bool verify_own_prefix(const ReadsDev &R, const uint3
 // (about 11 of the 34 possible) a deep prefetch ring mostly fetches buckets nobody tests, so this kernel keeps ONE
 // bucket in flight per lane, in registers.  Shared memory per warp: own reads [32][wp].
 // id_list != nullptr: second pass -- the reads are id_list[0 .. *n_list) instead of [lo, hi)
-template <bool FAST, int MAXM>
+template <bool FAST, int MAXM, bool MINI>
 __global__ void __launch_bounds__(kTpr, ALGA_P1_BLOCKS)
 phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, const uint32_t *__restrict__ id_list,
                   const uint32_t *__restrict__ n_list, int wp, Phase1Out out, uint32_t *__restrict__ hard_queue,
@@ -324,9 +324,9 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
             wb = (int) (p >> 5);
             sh = p & 31u;
             w0 = own[wb], w1 = own[wb + 1], w2 = own[wb + 2];
-            const uint64_t h = mix64(window_key(w0, w1, w2, sh) & P.seed_mask);
+            const uint64_t win = window_key(w0, w1, w2, sh) & P.seed_mask, h = mix64(win);
             tag = tag_of(T, h);
-            bk = bucket_of(h, T.n_buckets);
+            bk = bucket_index<MINI>(T, win, h, (uint32_t) P.seed_nt);
             load_bucket_na(T.slots + (uint64_t) bk * kSlotsPerBucket, e, pol);
         }
         while (true) {
@@ -348,9 +348,9 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
                             wb++;
                             w0 = w1, w1 = w2, w2 = own[wb + 2];
                         }
-                        const uint64_t h = mix64(window_key(w0, w1, w2, sh) & P.seed_mask);
+                        const uint64_t win = window_key(w0, w1, w2, sh) & P.seed_mask, h = mix64(win);
                         tag = tag_of(T, h);
-                        bk = bucket_of(h, T.n_buckets);
+                        bk = bucket_index<MINI>(T, win, h, (uint32_t) P.seed_nt);
                         load_bucket_na(T.slots + (uint64_t) bk * kSlotsPerBucket, e, pol);
                     } else {
                         more = false;
@@ -521,7 +521,7 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
 // Shared memory per warp: own reads [32][wp] | bucket ring [kRing2][2][32] x 16 B | queue: ids [kQ2][32],
 // heads [kQ2][2][32], lengths [kQ2][32] (u16).
 // id_list != nullptr: second pass -- the targets are id_list[0 .. *n_list) instead of [lo, hi)
-template <bool FAST, int MAXM>
+template <bool FAST, int MAXM, bool MINI>
 __global__ void __launch_bounds__(kTpr, ALGA_P2_BLOCKS)
 phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, const uint32_t *__restrict__ id_list,
                   const uint32_t *__restrict__ n_list, int wp, RowsView rows, Phase2Out out, int force_hard) {
@@ -582,9 +582,9 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
         for (int j = 0; j < kRing2; j++) tagr[j] = 0, bkr[j] = 0;
         auto prefetch = [&](int slot, uint32_t &tag_out, uint32_t &bk_out) {
             if (walk && Lp >= l_lo) {
-                const uint64_t h = mix64(window_key(w0, w1, w2, sh) & P.seed_mask);
+                const uint64_t win = window_key(w0, w1, w2, sh) & P.seed_mask, h = mix64(win);
                 tag_out = tag_of(T, h);
-                bk_out = bucket_of(h, T.n_buckets);
+                bk_out = bucket_index<MINI>(T, win, h, (uint32_t) P.seed_nt);
                 cp_async_bucket(ring + ((slot * 2) * 32 + lane) * 4, ring + ((slot * 2 + 1) * 32 + lane) * 4,
                                 T.slots + (uint64_t) bk_out * kSlotsPerBucket, pol);
                 Lp--;
@@ -841,12 +841,14 @@ void launch_phase1_tpr(const ReadsDev &R, const SeedTable &prefix, const PsDev &
     const bool fast = P.uniform_len && !R.word_off;
     if (!id_list) {
         const int grid = warp_tile_grid(hi - lo, cfg, ALGA_P1_BLOCKS);
-        auto k = fast ? phase1_tpr_kernel<true, 2> : phase1_tpr_kernel<false, 2>;
+        auto k = prefix.min_m ? (fast ? phase1_tpr_kernel<true, 2, true> : phase1_tpr_kernel<false, 2, true>)
+                              : (fast ? phase1_tpr_kernel<true, 2, false> : phase1_tpr_kernel<false, 2, false>);
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         k<<<grid, kTpr, smem, s>>>(R, prefix, P, lo, hi, nullptr, nullptr, wp, out, hard_queue, n_hard, force_hard);
     } else {
         const int grid = warp_tile_grid(std::min<uint64_t>(hi - lo, (uint64_t) cfg.sm_count * kTpr * 2), cfg, 2);
-        auto k = fast ? phase1_tpr_kernel<true, 4> : phase1_tpr_kernel<false, 4>;
+        auto k = prefix.min_m ? (fast ? phase1_tpr_kernel<true, 4, true> : phase1_tpr_kernel<false, 4, true>)
+                              : (fast ? phase1_tpr_kernel<true, 4, false> : phase1_tpr_kernel<false, 4, false>);
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         k<<<grid, kTpr, smem, s>>>(R, prefix, P, lo, hi, id_list, n_list, wp, out, hard_queue, n_hard, force_hard);
     }
@@ -869,12 +871,14 @@ void launch_phase2_tpr(const ReadsDev &R, const SeedTable &suffix, const PsDev &
     const bool fast = P.uniform_len && !R.word_off;
     if (!id_list) {
         const int grid = warp_tile_grid(hi - lo, cfg, ALGA_P2_BLOCKS);
-        auto k = fast ? phase2_tpr_kernel<true, 2> : phase2_tpr_kernel<false, 2>;
+        auto k = suffix.min_m ? (fast ? phase2_tpr_kernel<true, 2, true> : phase2_tpr_kernel<false, 2, true>)
+                              : (fast ? phase2_tpr_kernel<true, 2, false> : phase2_tpr_kernel<false, 2, false>);
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         k<<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, nullptr, nullptr, wp, rows, out, force_hard);
     } else {
         const int grid = warp_tile_grid(std::min<uint64_t>(hi - lo, (uint64_t) cfg.sm_count * kTpr * 2), cfg, 2);
-        auto k = fast ? phase2_tpr_kernel<true, 4> : phase2_tpr_kernel<false, 4>;
+        auto k = suffix.min_m ? (fast ? phase2_tpr_kernel<true, 4, true> : phase2_tpr_kernel<false, 4, true>)
+                              : (fast ? phase2_tpr_kernel<true, 4, false> : phase2_tpr_kernel<false, 4, false>);
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         k<<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, id_list, n_list, wp, rows, out, force_hard);
     }
