@@ -207,3 +207,23 @@ def run_cut_triangles(edges_in, n_nodes: int, max_offset: int, threads=1) -> np.
         subprocess.run([HARNESS, "triangles", ip, op, str(max_offset), str(threads)], check=True, stdout=subprocess.DEVNULL,
                        stderr=subprocess.DEVNULL, cwd=d)
         return read_edges(op)
+
+
+def run_driver_paired_offsets(text1: bytes, text2: bytes | None = None, file_type=1, threads=1) -> np.ndarray:
+    """Run the reference's whole driver (its main(), compiled as a function) on the given files and return
+    Global::pairedReadOffset as the renumbering of main.cpp:150-232 left it."""
+    if not available():
+        raise RuntimeError("oracle/_ref/alga_ref_harness is not built (make -C oracle ref)")
+    with tempfile.TemporaryDirectory() as d:
+        f1 = "x_1." + _EXT[file_type]
+        open(os.path.join(d, f1), "wb").write(text1)
+        args = ["--file1=" + f1]
+        if text2 is not None:
+            f2 = "x_2." + _EXT[file_type]
+            open(os.path.join(d, f2), "wb").write(text2)
+            args.append("--file2=" + f2)
+        args += [f"--threads={threads}", "--output=contigs.fasta"]
+        subprocess.run([HARNESS, "driver", "po.bin"] + args, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=d)
+        raw = np.fromfile(os.path.join(d, "po.bin"), dtype=np.uint8)
+        n = int(raw[:4].view("<u4")[0])
+        return raw[4 : 4 + n].copy()

@@ -37,6 +37,8 @@
 #include <string>
 #include <vector>
 
+int alga_reference_main(int argc, char **argv);  // the reference's main() (oracle/Makefile: -Dmain=alga_reference_main)
+
 namespace {
 
 struct ReadsFile {
@@ -354,6 +356,26 @@ int run_triangles(const char *edges_path, const char *out_path, int max_offset, 
     return 0;
 }
 
+// The whole unmodified driver (main.cpp:57-779) on the given reference options; afterwards Global::pairedReadOffset -- filled
+// once by the renumbering at main.cpp:150-232 and only read later (Read.cpp:262) -- is written out: u32 n, n bytes.
+int run_driver(const char *out_path, int argc, char **argv) {
+    std::vector<char *> av;
+    static char name[] = "ALGA";
+    av.push_back(name);
+    for (int i = 0; i < argc; i++) av.push_back(argv[i]);
+    av.push_back(nullptr);
+    const int rc = alga_reference_main((int) av.size() - 1, av.data());
+    if (rc != 0) return rc;
+    FILE *o = fopen(out_path, "wb");
+    if (!o) die("cannot open output");
+    const uint32_t n = (uint32_t) Global::pairedReadOffset.size();
+    fwrite(&n, 4, 1, o);
+    if (n) fwrite(Global::pairedReadOffset.data(), 1, n, o);
+    fclose(o);
+    printf("{\"paired_offsets\": %u}\n", n);
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -369,6 +391,7 @@ int main(int argc, char **argv) {
     if (argc >= 9 && strcmp(argv[1], "supplement") == 0)
         return run_supplement(argv[2], argv[3], argv[4], atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]),
                               argc >= 10 ? atoi(argv[9]) : 1);
+    if (argc >= 4 && strcmp(argv[1], "driver") == 0) return run_driver(argv[2], argc - 3, argv + 3);
     if (argc >= 5 && strcmp(argv[1], "triangles") == 0)
         return run_triangles(argv[2], argv[3], atoi(argv[4]), argc >= 6 ? atoi(argv[5]) : 1);
     if (argc >= 5 && strcmp(argv[1], "readinput") == 0)
@@ -380,7 +403,8 @@ int main(int argc, char **argv) {
             "<threshold_pct> <kmer_length_bucket> [threads]\n"
             "       %s prefixreads <reads.algr> <mask.bin> [remove_type 1|2] [threads]\n"
             "       %s readinput <file1> <file2|-> <reads_out.algr> [threads [reference options, e.g. --rna=1]]\n"
-            "       %s triangles <edges_in.alge> <edges_out.alge> <max_offset_parallel_paths> [threads]\n",
-            argv[0], argv[0], argv[0], argv[0], argv[0], argv[0]);
+            "       %s triangles <edges_in.alge> <edges_out.alge> <max_offset_parallel_paths> [threads]\n"
+            "       %s driver <paired_offsets_out.bin> <reference options: --file1=... --threads=1 --output=...>\n",
+            argv[0], argv[0], argv[0], argv[0], argv[0], argv[0], argv[0]);
     return 2;
 }

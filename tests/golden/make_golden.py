@@ -15,7 +15,8 @@ error-rate supplement (GraphCreatorLI, main.cpp:300-355) on the supplement cases
 removal masks of ReadPreprocess::getPrefixReads (both removal types) on the preprocessing cases; `in_*.npz` hold
 Global::READS as the reference's InputReader::readInput leaves it (lengths, packed blocks) for the input files of the
 input cases; `front_*.npz` hold the graph the STOCK binary serialises (--serialize=1, --threads=1) for the files of the
-front cases, i.e. after its own reader, duplicate / prefix-read removal, renumbering and GraphCreatorPrefSuf; `tri_*.npz` hold
+front cases, i.e. after its own reader, duplicate / prefix-read removal, renumbering and GraphCreatorPrefSuf, plus
+Global::pairedReadOffset as the reference's own main() leaves it (harness mode `driver`); `tri_*.npz` hold
 the edges that survive the reference's sortEdgesByIncreasingOffset + cutNonAndWeaklyMetricTriangles on graphs stored above.
 """
 import hashlib
@@ -92,7 +93,9 @@ def main():
     for name in FRONT_CASES:
         t1, t2, ft = front_case(name)
         n, edges = harness.run_stock_graph(t1, t2, ft)
-        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), n=np.array(n), edges=edges, input_sha=np.array(text_sha(t1, t2)))
+        po = harness.run_driver_paired_offsets(t1, t2, ft)  # Global::pairedReadOffset after the reference's own main()
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), n=np.array(n), edges=edges, paired_offset=po,
+                            input_sha=np.array(text_sha(t1, t2)))
         print(f"{name}: n={n} E={edges.shape[0]}")
     # first simplifier step on the graphs stored above (the reference's own sortEdgesByIncreasingOffset + triangle cut)
     for name in TRIANGLE_CASES:

@@ -119,7 +119,7 @@ def test_files_to_graph_matches_stock_binary(name):
     rs, po, edges = oracle_front(t1, t2, ft)
     assert rs.n == int(g["n"])
     assert np.array_equal(edges, g["edges"])
-    assert po.shape[0] == rs.n
+    assert np.array_equal(po, g["paired_offset"])  # Global::pairedReadOffset after the reference's own main()
 
 
 def test_file_type_follows_the_extension():
