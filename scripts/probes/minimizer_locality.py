@@ -64,6 +64,17 @@ def main():
             over8 = (cnt > 8).sum() / cnt.shape[0]
             print(f"  m = {m:2d} (w = {w:2d})  {name} table: {cnt.shape[0]} distinct minimizers for {n} entries, entries per minimizer "
                   f"mean {cnt.mean():.2f}  p99 {np.percentile(cnt, 99):.0f}  max {cnt.max()}  > 8 slots: {100 * over8:.2f} % of the runs")
+            # the table as the library sizes it (n / 2 buckets of 8 slots, open addressing): what a probe meets in its FIRST bucket
+            for load in (2, 1):
+                nb = max(64, n // load)
+                bucket = ((col * np.uint64(0xC2B2AE3D27D4EB4F)) >> np.uint64(32)) * np.uint64(nb) >> np.uint64(32)
+                fill = np.bincount(bucket.astype(np.int64), minlength=nb)
+                full = (fill >= 8)
+                # entries that do not fit their home bucket spill into the chain; probes whose home bucket is full walk it
+                entries_in_full = fill[full].sum() / n
+                print(f"      {nb} buckets ({load} entries per bucket on average): home buckets with >= 8 entries {100 * full.mean():.2f} %, "
+                      f"holding {100 * entries_in_full:.1f} % of the entries (window-hash buckets at the same size: "
+                      f"{100 * (np.random.default_rng(0).poisson(load, nb) >= 8).mean():.2f} %)")
         print(f"  m = {m:2d}: distinct minimizers among the probes of a read: phase 2 (29 windows) mean {d2.mean():.2f} p99 "
               f"{np.percentile(d2, 99):.0f};  phase 1 first 11 windows mean {d1.mean():.2f}, all 34 mean {d1a.mean():.2f}")
 
