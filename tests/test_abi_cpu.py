@@ -66,3 +66,18 @@ def test_invalid_arguments_are_rejected():
     assert lib.alga_gpu_prefsuf_build(None, None, None, None) == -1
     assert lib.alga_ps_plan_run(None, None) == -1
     assert b"null" in lib.alga_gpu_last_error()
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/alga_gpu.h is the boundary: it must compile as C99 and as C++14 on its own (no CUDA, no torch types)."""
+    import shutil
+    import subprocess
+
+    if not shutil.which("gcc") or not shutil.which("g++"):
+        pytest.skip("no host compiler")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "alga_gpu.h"\nint main(void) { alga_reads r; alga_csr g; alga_driver_params p; alga_overlap_graph o;'
+                   ' (void) r; (void) g; (void) p; (void) o; return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)], check=True)
+    subprocess.run(["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)], check=True)
