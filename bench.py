@@ -451,7 +451,6 @@ def run_ours(args):
                       "reads_per_s": raw.n / (ms / 1e3), "call": "alga_gpu_prefix_reads (host buffers)"}
         from oracle import harness as _h
         if _h.available() and not args.no_cpu:
-            import subprocess as _sp, tempfile as _tf
             sub = _rs.ReadSet(raw.words[: (raw.n // 8) * int(raw.word_off[1])], raw.word_off[: raw.n // 8 + 1], raw.len_nt[: raw.n // 8])
             t0c = time.perf_counter()
             _h.run_prefix_reads(sub, 2, threads=_cpu_threads())

@@ -1,5 +1,5 @@
 """Files-to-graph on config-2-sized FASTA text, a few calls -- the command the ncu launch list of the input stage is taken from."""
-import sys, os, time
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from alga_b200 import synth

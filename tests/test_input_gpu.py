@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from alga_b200 import _lib, synth
-from alga_b200.input_reader import (FASTA, FASTQ, InputReader, PinnedText, build_overlap_graph, build_overlap_graph_staged,
+from alga_b200.input_reader import (FASTA, InputReader, PinnedText, build_overlap_graph, build_overlap_graph_staged,
                                     remap_reads)
 from alga_b200.readset import ReadSet
 from oracle import oracle
