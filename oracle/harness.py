@@ -175,7 +175,7 @@ def read_graph_file(path) -> np.ndarray:
     return n, sort_edges(e)
 
 
-def run_stock_graph(text1: bytes, text2: bytes | None = None, file_type=1, threads=1):
+def run_stock_graph(text1: bytes, text2: bytes | None = None, file_type=1, threads=1, extra=()):
     """The stock ALGA binary (main.cpp:57-293) with --serialize=1 on the given files: (n_nodes, edges) of the graph it
     writes after GraphCreatorPrefSuf + retainOnlySmallestOffset, i.e. on the ids left by the reference's own reader,
     duplicate removal and renumbering."""
@@ -189,7 +189,7 @@ def run_stock_graph(text1: bytes, text2: bytes | None = None, file_type=1, threa
             f2 = "x_2." + _EXT[file_type]
             open(os.path.join(d, f2), "wb").write(text2)
             args.append("--file2=" + f2)
-        args += [f"--threads={threads}", "--output=contigs.fasta", "--serialize=1"]
+        args += [f"--threads={threads}", "--output=contigs.fasta", "--serialize=1", *extra]
         subprocess.run(args, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=d)
         g = [x for x in os.listdir(d) if x.endswith("_beforeSimplifier.graph")]
         assert len(g) == 1, g

@@ -205,3 +205,22 @@ def random_input_files(seed, n_trials):
                 t = t[:-1]
             texts.append(t)
         yield texts[0], (texts[1] if paired else None), ft, paired
+
+
+@pytest.mark.skipif(not os.path.isfile(harness.STOCK), reason="oracle/_ref/ALGA not built")
+def test_minimum_overlap_override_follows_the_driver():
+    """`-l 40` (Params.cpp:488-497, main.cpp:112-115): minimum overlap 40, RSOEMO = (40 + LEN) / 2, LI_KMER_LENGTH = 40 -- the
+    rule alga_gpu_files_to_graph applies for alga_driver_params.min_overlap > 0, checked against the stock binary's graph."""
+    t1, t2, ft = front_case("front_short")
+    n_ref, e_ref = harness.run_stock_graph(t1, t2, ft, extra=("-l", "40"))
+    rs, _ = oracle.read_input(t1, t2, ft)
+    alive = rs.len_nt[rs.len_nt > 0]
+    LEN = int(alive.astype(np.float64).sum() / alive.shape[0]) + 6
+    lmin, rsmin, li = 40, (40 + LEN) // 2, 40
+    old, _ = oracle.remap(rs.len_nt, oracle.prefix_reads(rs, 2))
+    rs2 = gather(rs, old)
+    ln = rs2.len_nt.copy()
+    ln[ln < 3 + li] = 0
+    edges = harness.sort_edges(oracle.prefsuf(ReadSet(rs2.words, rs2.word_off, ln), lmin, rsmin))
+    assert rs2.n == n_ref
+    assert np.array_equal(edges, e_ref)
