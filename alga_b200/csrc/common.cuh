@@ -256,6 +256,55 @@ __device__ __forceinline__ uint32_t window_minimizer(uint64_t win, uint32_t seed
     }
     return best;
 }
+// the scrambled m-mer at position j of a window, and the minimum over the window, for host and device (the kernels use
+// window_minimizer above; tests/minimizer_check.cu compares the sliding form below with this one on the CPU)
+__host__ __device__ __forceinline__ uint32_t scrambled_mmer(uint64_t win, uint32_t j, uint32_t m) {
+    const uint64_t x = (win >> (2u * j)) & ((1ull << (2u * m)) - 1ull);  // m < 32
+    uint32_t v = ((uint32_t) x ^ ((uint32_t) (x >> 32) * 0x85EBCA6Bu)) * 0x9E3779B1u;
+    return v ^ (v >> 15);
+}
+__host__ __device__ __forceinline__ uint32_t window_minimizer_ref(uint64_t win, uint32_t seed_nt, uint32_t m) {
+    uint32_t best = 0xFFFFFFFFu;
+    for (uint32_t j = 0; j + m <= seed_nt; j++) {
+        const uint32_t v = scrambled_mmer(win, j, m);
+        best = v < best ? v : best;
+    }
+    return best;
+}
+// The same minimum kept up to date while the window moves by one nucleotide per step (the probe loops of the fast kernels
+// walk the overlap lengths that way): one new m-mer per step, a rescan only when the minimum itself leaves the window.
+// Not wired into the kernels yet; tests/test_minimizer_cpu.py checks it against window_minimizer_ref.
+struct SlidingMinimizer {
+    uint32_t best;  // smallest scrambled m-mer of the current window
+    int pos;        // position j of (one occurrence of) it, 0 = the m-mer at the low end of the window
+    __host__ __device__ void reset(uint64_t win, uint32_t seed_nt, uint32_t m) {
+        best = 0xFFFFFFFFu, pos = 0;
+        for (uint32_t j = 0; j + m <= seed_nt; j++) {
+            const uint32_t v = scrambled_mmer(win, j, m);
+            if (v < best) best = v, pos = (int) j;
+        }
+    }
+    // the window now starts one nucleotide further into the read (its low m-mer left, a new one entered at the high end)
+    __host__ __device__ uint32_t slide_up(uint64_t win, uint32_t seed_nt, uint32_t m) {
+        if (--pos < 0) {
+            reset(win, seed_nt, m);
+        } else {
+            const uint32_t v = scrambled_mmer(win, seed_nt - m, m);
+            if (v < best) best = v, pos = (int) (seed_nt - m);
+        }
+        return best;
+    }
+    // the window now starts one nucleotide earlier (its high m-mer left, a new one entered at the low end)
+    __host__ __device__ uint32_t slide_down(uint64_t win, uint32_t seed_nt, uint32_t m) {
+        if (++pos > (int) (seed_nt - m)) {
+            reset(win, seed_nt, m);
+        } else {
+            const uint32_t v = scrambled_mmer(win, 0, m);
+            if (v <= best) best = v, pos = 0;
+        }
+        return best;
+    }
+};
 // bucket of a seed window with hash h
 template <bool MINI>
 __device__ __forceinline__ uint32_t bucket_index(const SeedTable &t, uint64_t win, uint64_t h, uint32_t seed_nt) {
