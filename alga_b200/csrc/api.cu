@@ -278,6 +278,7 @@ int stage_index_begin(alga_ps_plan *plan, cudaStream_t s, cudaStream_t s2 = null
     size_table(plan->Tp, plan->stats.n_prefix, plan->R.n);
     size_table(plan->Ts, plan->stats.n_suffix, plan->R.n);
     plan->Tp.min_m = plan->Ts.min_m = minimizer_setting(plan->P.seed_nt);
+    plan->cfg.min_slide = plan->Tp.min_m && getenv("ALGA_PS_MINIMIZER_SLIDE") != nullptr;  // experimental, not validated on a GPU yet
     const size_t bp = (size_t) plan->Tp.n_buckets * kSlotsPerBucket * 4, bs = (size_t) plan->Ts.n_buckets * kSlotsPerBucket * 4;
     CKR(plan->tp.ensure(bp));
     CKR(plan->ts.ensure(bs));

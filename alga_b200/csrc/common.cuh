@@ -306,13 +306,13 @@ struct SlidingMinimizer {
     }
 };
 // bucket of a seed window with hash h
-template <bool MINI>
+template <int MINI>  // 0: by the window hash, != 0: by the minimizer of the window
 __device__ __forceinline__ uint32_t bucket_index(const SeedTable &t, uint64_t win, uint64_t h, uint32_t seed_nt) {
-    if (!MINI) return bucket_of(h, t.n_buckets);
+    if (MINI == 0) return bucket_of(h, t.n_buckets);
     return bucket_of(mix64((uint64_t) window_minimizer(win, seed_nt, t.min_m)), t.n_buckets);
 }
 __device__ __forceinline__ uint32_t bucket_index_rt(const SeedTable &t, uint64_t win, uint64_t h, uint32_t seed_nt) {
-    return t.min_m ? bucket_index<true>(t, win, h, seed_nt) : bucket_of(h, t.n_buckets);
+    return t.min_m ? bucket_index<1>(t, win, h, seed_nt) : bucket_of(h, t.n_buckets);
 }
 // next bucket of a chain (rare path)
 __device__ __forceinline__ uint32_t next_bucket(const SeedTable &t, uint32_t bk) {

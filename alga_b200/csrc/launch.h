@@ -10,6 +10,8 @@ namespace alga {
 struct LaunchCfg {
     int sm_count = 148;
     uint64_t *launches = nullptr;  // incremented once per kernel launch
+    bool min_slide = false;        // experimental, with SeedTable::min_m != 0 only: the fast kernels keep the minimizer of the
+                                   // seed window up to date while it slides (SlidingMinimizer) instead of recomputing it
 };
 
 // --- read-set statistics: max length, eligible prefix/suffix counts ----------------------------

@@ -271,7 +271,7 @@ __device__ __forceinline__ bool verify_own_prefix(const ReadsDev &R, const uint3
 // (about 11 of the 34 possible) a deep prefetch ring mostly fetches buckets nobody tests, so this kernel keeps ONE
 // bucket in flight per lane, in registers.  Shared memory per warp: own reads [32][wp].
 // id_list != nullptr: second pass -- the reads are id_list[0 .. *n_list) instead of [lo, hi)
-template <bool FAST, int MAXM, bool MINI>
+template <bool FAST, int MAXM, int MINI>  // MINI: 0 window-hash buckets, 1 minimizer buckets, 2 ... with a sliding minimum
 __global__ void __launch_bounds__(kTpr, ALGA_P1_BLOCKS)
 phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, const uint32_t *__restrict__ id_list,
                   const uint32_t *__restrict__ n_list, int wp, Phase1Out out, uint32_t *__restrict__ hard_queue,
@@ -319,6 +319,8 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
         bool more = active;
         uint32_t e[8], tag = 0, bk = 0, w0 = 0, w1 = 0, w2 = 0, sh = 0;
         int wb = 0;
+        SlidingMinimizer smin;  // MINI == 2 only: the window moves up by one nucleotide per length
+        smin.best = 0, smin.pos = 0;
         if (more) {
             const uint32_t p = 2u * (lenb - (uint32_t) Lc);
             wb = (int) (p >> 5);
@@ -326,7 +328,12 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
             w0 = own[wb], w1 = own[wb + 1], w2 = own[wb + 2];
             const uint64_t win = window_key(w0, w1, w2, sh) & P.seed_mask, h = mix64(win);
             tag = tag_of(T, h);
-            bk = bucket_index<MINI>(T, win, h, (uint32_t) P.seed_nt);
+            if (MINI == 2) {
+                smin.reset(win, (uint32_t) P.seed_nt, T.min_m);
+                bk = bucket_of(mix64((uint64_t) smin.best), T.n_buckets);
+            } else {
+                bk = bucket_index<MINI>(T, win, h, (uint32_t) P.seed_nt);
+            }
             load_bucket_na(T.slots + (uint64_t) bk * kSlotsPerBucket, e, pol);
         }
         while (true) {
@@ -338,6 +345,7 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
                     const uint32_t m = bucket_min(e, tag);
                     uint32_t cm[MAXM];
                     int n = 0;
+                    const bool e7_walked = MINI == 2 && e[7] != kEmptySlot;  // a full bucket: probe_matches may load its chain into e[]
                     if (m <= T.id_mask || e[7] != kEmptySlot) probe_matches<MAXM>(T, e, tag, bk, m, cm, n);
                     const int32_t L = Lc;
                     Lc--;
@@ -350,8 +358,18 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
                         }
                         const uint64_t win = window_key(w0, w1, w2, sh) & P.seed_mask, h = mix64(win);
                         tag = tag_of(T, h);
-                        bk = bucket_index<MINI>(T, win, h, (uint32_t) P.seed_nt);
-                        load_bucket_na(T.slots + (uint64_t) bk * kSlotsPerBucket, e, pol);
+                        if (MINI == 2) {
+                            const uint32_t bk_new = bucket_of(mix64((uint64_t) smin.slide_up(win, (uint32_t) P.seed_nt, T.min_m)), T.n_buckets);
+                            // the same bucket as for the previous length (the usual case) is still in e[]: nothing to fetch,
+                            // unless probe_matches walked its chain and left another bucket there
+                            if (bk_new != bk || e7_walked) {
+                                bk = bk_new;
+                                load_bucket_na(T.slots + (uint64_t) bk * kSlotsPerBucket, e, pol);
+                            }
+                        } else {
+                            bk = bucket_index<MINI>(T, win, h, (uint32_t) P.seed_nt);
+                            load_bucket_na(T.slots + (uint64_t) bk * kSlotsPerBucket, e, pol);
+                        }
                     } else {
                         more = false;
                     }
@@ -521,7 +539,7 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
 // Shared memory per warp: own reads [32][wp] | bucket ring [kRing2][2][32] x 16 B | queue: ids [kQ2][32],
 // heads [kQ2][2][32], lengths [kQ2][32] (u16).
 // id_list != nullptr: second pass -- the targets are id_list[0 .. *n_list) instead of [lo, hi)
-template <bool FAST, int MAXM, bool MINI>
+template <bool FAST, int MAXM, int MINI>  // MINI: 0 window-hash buckets, 1 minimizer buckets, 2 ... with a sliding minimum
 __global__ void __launch_bounds__(kTpr, ALGA_P2_BLOCKS)
 phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, const uint32_t *__restrict__ id_list,
                   const uint32_t *__restrict__ n_list, int wp, RowsView rows, Phase2Out out, int force_hard) {
@@ -572,6 +590,9 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
         uint32_t tagr[kRing2], bkr[kRing2], w0 = 0, w1 = 0, w2 = 0, sh = 0;
         int wb = 0;
         int32_t Lp = l_hi;  // next length to prefetch; (w0, w1, w2, sh, wb) = register window at Lp
+        SlidingMinimizer smin;  // MINI == 2 only
+        smin.best = 0, smin.pos = 0;
+        bool smin_on = false;
         if (walk) {
             const uint32_t p = 2u * (uint32_t) (l_hi - P.seed_nt);
             wb = (int) (p >> 5);
@@ -584,7 +605,14 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
             if (walk && Lp >= l_lo) {
                 const uint64_t win = window_key(w0, w1, w2, sh) & P.seed_mask, h = mix64(win);
                 tag_out = tag_of(T, h);
-                bk_out = bucket_index<MINI>(T, win, h, (uint32_t) P.seed_nt);
+                if (MINI == 2) {  // the window moves down by one nucleotide per call
+                    if (smin_on) smin.slide_down(win, (uint32_t) P.seed_nt, T.min_m);
+                    else smin.reset(win, (uint32_t) P.seed_nt, T.min_m);
+                    smin_on = true;
+                    bk_out = bucket_of(mix64((uint64_t) smin.best), T.n_buckets);
+                } else {
+                    bk_out = bucket_index<MINI>(T, win, h, (uint32_t) P.seed_nt);
+                }
                 cp_async_bucket(ring + ((slot * 2) * 32 + lane) * 4, ring + ((slot * 2 + 1) * 32 + lane) * 4,
                                 T.slots + (uint64_t) bk_out * kSlotsPerBucket, pol);
                 Lp--;
@@ -841,14 +869,16 @@ void launch_phase1_tpr(const ReadsDev &R, const SeedTable &prefix, const PsDev &
     const bool fast = P.uniform_len && !R.word_off;
     if (!id_list) {
         const int grid = warp_tile_grid(hi - lo, cfg, ALGA_P1_BLOCKS);
-        auto k = prefix.min_m ? (fast ? phase1_tpr_kernel<true, 2, true> : phase1_tpr_kernel<false, 2, true>)
-                              : (fast ? phase1_tpr_kernel<true, 2, false> : phase1_tpr_kernel<false, 2, false>);
+        auto k = !prefix.min_m ? (fast ? phase1_tpr_kernel<true, 2, 0> : phase1_tpr_kernel<false, 2, 0>)
+                 : !cfg.min_slide ? (fast ? phase1_tpr_kernel<true, 2, 1> : phase1_tpr_kernel<false, 2, 1>)
+                                  : (fast ? phase1_tpr_kernel<true, 2, 2> : phase1_tpr_kernel<false, 2, 2>);
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         k<<<grid, kTpr, smem, s>>>(R, prefix, P, lo, hi, nullptr, nullptr, wp, out, hard_queue, n_hard, force_hard);
     } else {
         const int grid = warp_tile_grid(std::min<uint64_t>(hi - lo, (uint64_t) cfg.sm_count * kTpr * 2), cfg, 2);
-        auto k = prefix.min_m ? (fast ? phase1_tpr_kernel<true, 4, true> : phase1_tpr_kernel<false, 4, true>)
-                              : (fast ? phase1_tpr_kernel<true, 4, false> : phase1_tpr_kernel<false, 4, false>);
+        auto k = !prefix.min_m ? (fast ? phase1_tpr_kernel<true, 4, 0> : phase1_tpr_kernel<false, 4, 0>)
+                 : !cfg.min_slide ? (fast ? phase1_tpr_kernel<true, 4, 1> : phase1_tpr_kernel<false, 4, 1>)
+                                  : (fast ? phase1_tpr_kernel<true, 4, 2> : phase1_tpr_kernel<false, 4, 2>);
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         k<<<grid, kTpr, smem, s>>>(R, prefix, P, lo, hi, id_list, n_list, wp, out, hard_queue, n_hard, force_hard);
     }
@@ -871,14 +901,16 @@ void launch_phase2_tpr(const ReadsDev &R, const SeedTable &suffix, const PsDev &
     const bool fast = P.uniform_len && !R.word_off;
     if (!id_list) {
         const int grid = warp_tile_grid(hi - lo, cfg, ALGA_P2_BLOCKS);
-        auto k = suffix.min_m ? (fast ? phase2_tpr_kernel<true, 2, true> : phase2_tpr_kernel<false, 2, true>)
-                              : (fast ? phase2_tpr_kernel<true, 2, false> : phase2_tpr_kernel<false, 2, false>);
+        auto k = !suffix.min_m ? (fast ? phase2_tpr_kernel<true, 2, 0> : phase2_tpr_kernel<false, 2, 0>)
+                 : !cfg.min_slide ? (fast ? phase2_tpr_kernel<true, 2, 1> : phase2_tpr_kernel<false, 2, 1>)
+                                  : (fast ? phase2_tpr_kernel<true, 2, 2> : phase2_tpr_kernel<false, 2, 2>);
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         k<<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, nullptr, nullptr, wp, rows, out, force_hard);
     } else {
         const int grid = warp_tile_grid(std::min<uint64_t>(hi - lo, (uint64_t) cfg.sm_count * kTpr * 2), cfg, 2);
-        auto k = suffix.min_m ? (fast ? phase2_tpr_kernel<true, 4, true> : phase2_tpr_kernel<false, 4, true>)
-                              : (fast ? phase2_tpr_kernel<true, 4, false> : phase2_tpr_kernel<false, 4, false>);
+        auto k = !suffix.min_m ? (fast ? phase2_tpr_kernel<true, 4, 0> : phase2_tpr_kernel<false, 4, 0>)
+                 : !cfg.min_slide ? (fast ? phase2_tpr_kernel<true, 4, 1> : phase2_tpr_kernel<false, 4, 1>)
+                                  : (fast ? phase2_tpr_kernel<true, 4, 2> : phase2_tpr_kernel<false, 4, 2>);
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         k<<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, id_list, n_list, wp, rows, out, force_hard);
     }
