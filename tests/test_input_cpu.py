@@ -224,3 +224,26 @@ def test_minimum_overlap_override_follows_the_driver():
     edges = harness.sort_edges(oracle.prefsuf(ReadSet(rs2.words, rs2.word_off, ln), lmin, rsmin))
     assert rs2.n == n_ref
     assert np.array_equal(edges, e_ref)
+
+
+@pytest.mark.skipif(not harness.available(), reason="oracle/_ref not built")
+def test_paired_read_offsets_match_the_reference_driver_on_random_sets():
+    """Global::pairedReadOffset after the reference's own main() (harness mode `driver`) against the oracle's renumbering, on small
+    random paired and single-end sets with N reads, repeats and duplicates (so that mates lose their partners in every way)."""
+    from alga_b200 import synth
+    from tests.cases import _fasta, _seq, _spice
+    for seed in range(6):
+        rng = np.random.default_rng(900 + seed)
+        g = synth.make_genome(6_000, rng)
+        if seed % 2 == 0:
+            m1, m2 = synth.sample_paired_end(g, 120, 25, rng, 0.0)
+            t1 = _fasta(_spice([_seq(r) for r in m1], rng, p_n=0.08, p_str=0.05, p_short=0.0, p_space=0.0))
+            t2 = _fasta(_spice([_seq(r) for r in m2], rng, p_n=0.08, p_str=0.05, p_short=0.0, p_space=0.0), b"m")
+        else:
+            m = synth.sample_single_end(g, 100, 25, rng, 0.0)
+            t1, t2 = _fasta(_spice([_seq(r) for r in m], rng, p_n=0.08, p_str=0.05, p_short=0.0, p_space=0.0)), None
+        po_ref = harness.run_driver_paired_offsets(t1, t2, oracle.INPUT_FASTA)
+        rs, _ = oracle.read_input(t1, t2, oracle.INPUT_FASTA)
+        _, po = oracle.remap(rs.len_nt, oracle.prefix_reads(rs, 2))
+        assert np.array_equal(po, po_ref), f"seed {seed}"
+        assert set(np.unique(po).tolist()) <= {0, 1, 2} and (po == 0).any()
