@@ -41,3 +41,20 @@ def test_cut_triangles_small_cases():
     e2 = np.array([[0, 1, 2], [0, 2, 12], [1, 2, 7]], np.int32)
     assert oracle.cut_triangles(e2, 3, 250).shape[0] == 3
     assert oracle.cut_triangles(np.zeros((0, 3), np.int32), 0, 250).shape[0] == 0
+
+
+@pytest.mark.skipif(not harness.available(), reason="oracle/_ref not built")
+def test_cut_triangles_oracle_matches_reference_on_random_graphs():
+    """Dense random graphs (many triangles, equal and unequal two-hop lengths, self loops, parallel entries with different offsets)."""
+    rng = np.random.default_rng(31)
+    for trial in range(12):
+        n = int(rng.integers(5, 80))
+        e = rng.integers(0, n, size=(int(rng.integers(1, 6 * n)), 2))
+        w = rng.integers(1, 25, size=(e.shape[0], 1))
+        edges = np.concatenate([e, w], axis=1).astype(np.int32)
+        if trial % 3:
+            edges = np.unique(edges, axis=0)  # otherwise: exact duplicates stay in
+        mx = int(rng.integers(5, 60))
+        want = harness.run_cut_triangles(edges, n, mx)
+        got = harness.sort_edges(oracle.cut_triangles(edges, n, mx))
+        assert np.array_equal(got, want), f"trial {trial}"
