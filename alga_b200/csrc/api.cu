@@ -46,16 +46,18 @@ int fail(int code, const char *fmt, ...) {
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    // Every buffer keeps kReadPadBytes of readable slack behind the requested size, also when a cached allocation is
+    // reused: the compare / window loads of the kernels read up to ~9 words past a packed read (common.cuh kReadPadBytes).
     int ensure(size_t bytes) {
-        if (bytes <= cap && p) return ALGA_OK;
+        if (p && bytes + kReadPadBytes <= cap) return ALGA_OK;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
+        size_t want = bytes + bytes / 8 + 2 * kReadPadBytes;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) {
             cudaGetLastError();
-            want = bytes + 256;
+            want = bytes + kReadPadBytes;
             e = cudaMalloc(&p, want);
         }
         if (e != cudaSuccess) {
@@ -528,11 +530,11 @@ int alga_ps_plan_upload_reads(alga_ps_plan *plan, const alga_reads *h) {
     CKR(use_device(plan));
     const uint32_t n = h->n_reads;
     const uint64_t n_words = h->word_off ? h->word_off[n] : (uint64_t) n * h->stride_words;
-    CKR(plan->words.ensure((size_t) n_words * 4 + 16));
+    CKR(plan->words.ensure((size_t) n_words * 4 + kReadPadBytes));
     CKR(plan->len.ensure((size_t) (n ? n : 1) * 4));
     cudaStream_t s = 0;
     CK(cudaMemcpyAsync(plan->words.p, h->words, (size_t) n_words * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemsetAsync((char *) plan->words.p + (size_t) n_words * 4, 0, 16, s));
+    CK(cudaMemsetAsync((char *) plan->words.p + (size_t) n_words * 4, 0, kReadPadBytes, s));
     CK(cudaMemcpyAsync(plan->len.p, h->len_nt, (size_t) n * 4, cudaMemcpyHostToDevice, s));
     alga_reads d = *h;
     d.words = plan->words.as<uint32_t>();
@@ -1059,10 +1061,10 @@ struct TmpReads {
         if (n && (!h->words || !h->len_nt)) return fail(ALGA_E_INVALID, "words / len_nt must not be null");
         if (!h->word_off && h->stride_words == 0 && n) return fail(ALGA_E_INVALID, "word_off is null and stride_words is 0");
         const uint64_t n_words = h->word_off ? h->word_off[n] : (uint64_t) n * h->stride_words;
-        CKR(words.ensure((size_t) n_words * 4 + 16));
+        CKR(words.ensure((size_t) n_words * 4 + kReadPadBytes));
         CKR(len.ensure((size_t) (n ? n : 1) * 4));
         CK(cudaMemcpy(words.p, h->words, (size_t) n_words * 4, cudaMemcpyHostToDevice));
-        CK(cudaMemset((char *) words.p + (size_t) n_words * 4, 0, 16));
+        CK(cudaMemset((char *) words.p + (size_t) n_words * 4, 0, kReadPadBytes));
         CK(cudaMemcpy(len.p, h->len_nt, (size_t) n * 4, cudaMemcpyHostToDevice));
         R.words = words.as<uint32_t>();
         R.len = len.as<uint32_t>();

@@ -77,14 +77,17 @@ class ShardedPrefSuf:
     """
 
     def __init__(self, min_overlap, rs_min_overlap, min_offset, max_len_cap, device, rank, world, len_nt, n_shard, words_per_read,
-                 group=None):
+                 group=None, n_total=None):
         import torch.distributed._symmetric_memory as symm
 
         self.rank, self.world = rank, world
         self.group = group if group is not None else dist.group.WORLD
         self.device = device
         self.len_nt, self.n_shard, self.W = len_nt, n_shard, words_per_read
-        self.n_total = n_shard * world
+        # rank r owns the reads [r * n_shard, min((r + 1) * n_shard, n_total)): the last ranks may own fewer (or none)
+        self.n_total = n_shard * world if n_total is None else int(n_total)
+        assert (world - 1) * n_shard < self.n_total <= world * n_shard or self.n_total <= n_shard, (n_shard, world, n_total)
+        self._err = None
         self.plan = PrefSufPlan(min_overlap, rs_min_overlap, min_offset, max_len_cap, device=device)
         # peer-mapped buffers
         self.shard_sym = symm.empty(n_shard * words_per_read, dtype=torch.int32, device=device)
@@ -105,7 +108,7 @@ class ShardedPrefSuf:
         self._shard = PrefSufPlan.shard_struct(rank, world, n_shard, self.n_total, list(self._h_ws.buffer_ptrs),
                                                self.tp_sym.data_ptr(), self.ts_sym.data_ptr())
         # replicated read set + its binding (no pass over the reads: they arrive during the build)
-        self._full = torch.zeros(self.n_total * words_per_read + READ_PAD_BYTES // 4, dtype=torch.int32, device=device)
+        self._full = torch.zeros(n_shard * world * words_per_read + READ_PAD_BYTES // 4, dtype=torch.int32, device=device)
         self._len = torch.full((self.n_total,), len_nt, dtype=torch.int32, device=device)
         self._reads = DeviceReads.from_tensors(self._full, self._len, stride=words_per_read, n=self.n_total, max_len=len_nt)
         self.plan.bind_uniform(self._reads, len_nt)
@@ -117,7 +120,8 @@ class ShardedPrefSuf:
 
     def load_shard(self, shard_words: torch.Tensor):
         """Put this rank's packed reads ([n_shard, W] int32, device or pinned host) into its peer-visible buffer."""
-        self.shard_sym.copy_(shard_words.reshape(-1), non_blocking=True)
+        flat = shard_words.reshape(-1)
+        self.shard_sym[: flat.numel()].copy_(flat, non_blocking=True)
 
     def run(self):
         """One build over the shards currently in the ranks' peer-visible buffers."""
@@ -136,7 +140,8 @@ class ShardedPrefSuf:
                 ev.record()
             main.wait_event(ev)
             # seeds of the arrived shard that fall into this rank's slice of the bucket space
-            self.plan.shard_index_range(self._shard, p * n, (p + 1) * n, first=(k == 0))
+            self._stage(lambda: self.plan.shard_index_range(self._shard, min(p * n, self.n_total), min((p + 1) * n, self.n_total),
+                                                             first=(k == 0)))
         self._h_ws.barrier()  # every rank's slice is complete
         marks[1].record()
         ev_slices = torch.cuda.Event()
@@ -151,18 +156,38 @@ class ShardedPrefSuf:
                     mine[p * sb:(p + 1) * sb].copy_(tabs[p][p * sb:(p + 1) * sb], non_blocking=True)
                 ev.record()
         main.wait_event(ev_tp)  # the suffix table keeps arriving while phase 1 runs
-        self.plan.shard_phase1(self._shard)
+        self._stage(lambda: self.plan.shard_phase1(self._shard))
         marks[2].record()
         self._h_ws.barrier()
         main.wait_event(ev_ts)
-        self.plan.shard_phase2(self._shard)
+        self._stage(lambda: self.plan.shard_phase2(self._shard))
         marks[3].record()
         self._h_ws.barrier()
         marks[4].record()
-        self.plan.shard_csr(self._shard)
+        self._stage(lambda: self.plan.shard_csr(self._shard))
         marks[5].record()
         self._ev = marks
         self._launches = self.plan.stats()["kernel_launches"]
+        self._raise_together()
+
+    def _stage(self, fn):
+        """A stage that fails on ONE rank (e.g. ALGA_E_CAPACITY) must not leave the others waiting at the next barrier:
+        the error is kept, the rank walks through the remaining barriers without computing, and ``_raise_together``
+        makes every rank raise after the last one."""
+        if self._err is None:
+            try:
+                fn()
+            except Exception as e:  # noqa: BLE001
+                self._err = e
+
+    def _raise_together(self):
+        flag = torch.tensor([0 if self._err is None else 1], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        if int(flag.item()):
+            err, self._err = self._err, None
+            if err is not None:
+                raise err
+            raise RuntimeError("sharded build failed on another rank (the build may be run again: plans grow their buffers)")
 
     def stats(self) -> dict:
         names = ("gather+index", "slices+phase1", "barrier+pull+phase2", "barrier", "pull+csr")

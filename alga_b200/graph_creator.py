@@ -62,11 +62,12 @@ def _reads_struct(reads: ReadSet, stride: int | None = None) -> _lib.Reads:
                       reads.align_from.ctypes.data, reads.align_to.ctypes.data)
 
 
-def _csr_to_graph(csr: _lib.Csr) -> Graph:
-    """Borrowed (page-locked, library-owned) results are wrapped without a copy: they stay valid until the next
-    build in this process, exactly like the alga_csr they came from."""
+def _csr_to_graph(csr: _lib.Csr, borrow: bool = False) -> Graph:
+    """Results are COPIED out of the library's buffers by default.  ``borrow=True`` wraps a borrowed (page-locked,
+    library-owned) result without a copy: such a Graph aliases process-wide staging memory and is valid only until the next
+    build / supplement / triangle cut in this process (exactly like the ``alga_csr`` it came from, include/alga_gpu.h)."""
     n, e = csr.n_reads, csr.n_edges
-    keep = (lambda a: a) if csr.borrowed else (lambda a: a.copy())
+    keep = (lambda a: a) if (csr.borrowed and borrow) else (lambda a: a.copy())
     row_off = keep(np.ctypeslib.as_array(csr.row_off, shape=(n + 1,)))
     if e:
         nbr = keep(np.ctypeslib.as_array(csr.nbr, shape=(e,)))
@@ -107,7 +108,8 @@ class GraphCreatorPrefSuf:
 
     def __init__(self, reads: ReadSet, min_overlap: int, rs_min_overlap: int, min_offset: int = 0,
                  max_len_cap: int = 500, device: int = 0, list_cap: int = 0, pinned: bool = False,
-                 force_generic: bool = False):
+                 force_generic: bool = False, borrow: bool = False):
+        self.borrow = borrow  # True: results alias the library's page-locked staging until the next build (_csr_to_graph)
         self.params = _lib.PsParams(min_overlap, rs_min_overlap, min_offset, max_len_cap, device, list_cap,
                                     _lib.PS_FORCE_GENERIC if force_generic else 0)
         self._pins = []
@@ -150,7 +152,7 @@ class GraphCreatorPrefSuf:
         tm = _lib.Timing()
         _lib.check(lib.alga_gpu_prefsuf_build(C.byref(st), C.byref(self.params), C.byref(csr), C.byref(tm)))
         try:
-            self.graph = _csr_to_graph(csr)
+            self.graph = _csr_to_graph(csr, self.borrow)
         finally:
             lib.alga_gpu_free_csr(C.byref(csr))
         self.timing = {k: getattr(tm, k) for k, _ in _lib.Timing._fields_ if k != "stage_ms"}
@@ -211,6 +213,16 @@ def li_kmers(reads: ReadSet, ids: np.ndarray, priorities=(0, 1, 2, 3), kmer_leng
     _lib.check(lib.alga_gpu_li_kmers(C.byref(st), ids.ctypes.data, ids.shape[0], pr.ctypes.data, kmer_length, intervals,
                                      device, h.ctypes.data, ind.ctypes.data))
     return h, ind
+
+
+def supplement_params(avg_len: float, error_rate_pct: int = 2, scale: float = 0.55):
+    """Params of the supplement as the reference driver derives them (main.cpp:93-115, 332-340), float arithmetic as there."""
+    LEN = int(avg_len) + 6
+    L = int(np.float32(LEN) * np.float32(scale))
+    return dict(threshold_pct=99 - error_rate_pct,
+                max_offset_pct=int((np.float32(1.0) - np.float32(scale)) * np.float32(avg_len) / 2),
+                min_overlap_area=int((np.float32(1.0) + np.float32(scale)) * np.float32(avg_len) / 2),
+                kmer_length_bucket=min(2 * L // 3, 60))
 
 
 class GraphCreatorLI:

@@ -16,6 +16,7 @@ before the graph creator sees it:
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -171,6 +172,23 @@ class Workload:
 
 def make_workload(name: str, genome_size: int, read_len: int, coverage: float, paired: bool, seed: int,
                   error: float = 0.0, repeats: int = 0) -> Workload:
+    cache = os.environ.get("ALGA_SYNTH_CACHE")  # experiments on the GPU box: several processes, one generation
+    if cache:
+        path = os.path.join(cache, f"synth_{genome_size}_{read_len}_{coverage}_{int(paired)}_{seed}_{error}_{repeats}.npz")
+        if os.path.exists(path):
+            z = np.load(path)
+            rs = ReadSet(z["words"], z["word_off"], z["len_nt"])
+            return Workload(name, rs, PrefSufParams(int(z["p"][0]), int(z["p"][1])), int(z["p"][2]), genome_size)
+        w = _make_workload(name, genome_size, read_len, coverage, paired, seed, error, repeats)
+        os.makedirs(cache, exist_ok=True)
+        np.savez(path, words=w.reads.words, word_off=w.reads.word_off, len_nt=w.reads.len_nt,
+                 p=np.array([w.params.min_overlap, w.params.rs_min_overlap, w.records], np.int64))
+        return w
+    return _make_workload(name, genome_size, read_len, coverage, paired, seed, error, repeats)
+
+
+def _make_workload(name: str, genome_size: int, read_len: int, coverage: float, paired: bool, seed: int,
+                   error: float = 0.0, repeats: int = 0) -> Workload:
     rng = np.random.default_rng(seed)
     genome = make_genome(genome_size, rng, repeats=repeats)
     if paired:

@@ -1,20 +1,24 @@
 #!/usr/bin/env python
 """Benchmark of the overlap-graph hot path (GraphCreatorPrefSuf + retainOnlySmallestOffset).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4|cfg1|cfg2|cfg3|cfg5]
 
-A "step" is one complete overlap-graph build over one synthetic read set (SURVEY.md §8-d generator):
-packed reads resident in HBM -> CSR adjacency resident in HBM.  Metric: graph nodes (strand-reads) per second.
+A "step" is one complete overlap-graph build over one synthetic read set: packed reads resident in HBM -> CSR adjacency
+resident in HBM.  Metric: graph nodes (strand-reads) per second.
 
-* N = 1 : BASELINE.json configs[1] (4.6 Mbp genome, 2x150 bp, 50x, error-free; seed 2).
-* N > 1 : weak scaling -- N chromosomes of 4.6 Mbp (seeds 2 + 100 r), read ids interleaved so that every
-          rank's id range holds reads of every chromosome; each rank starts with its own shard of the packed
-          reads in HBM.  The timed region contains the NVLink pull of the other ranks' shards overlapped with the
-          (replicated) index build, phase 1, phase 2 and the CSR assembly; the two edge exchanges happen inside
-          those kernels over peer memory (alga_b200/distributed.py), separated by three stream-ordered barriers.
+* workload: BASELINE.json configs[3] by default -- the configuration north_star states its targets on (100 Mbp genome,
+  2x150 bp, 50x, error-free, seed 4: 56.7 M strand-reads, fits one GPU) -- at every N: N = 1 is the whole read set on one
+  GPU, N > 1 the SAME read set split into contiguous read-id ranges ("scaling": "strong", north_star's 1/2/4/8 sweep).
+  The read set comes from the counter-based generator alga_b200/synth_dev.py (SURVEY.md 8-d distributions, integer only,
+  identical on CPU and GPU), run on each rank's own GPU in a few seconds.
+* parity: after the timed loop the graph the LAST timed step left in HBM is digested on the device (alga_b200/edge_hash.py,
+  order-independent 128-bit sum over (source, target, offset); per-rank digests of disjoint row ranges add up) and compared
+  with the digest of the graph the UNMODIFIED reference built from the same read set (tests/golden/full_<workload>_<gen>.json,
+  written by tests/golden/make_full_golden.py through oracle/_ref).  "parity": true | false | null (no golden for this
+  workload / scale); false makes the run exit non-zero.
 * --impl reference : the reference's own CPU GraphCreatorPrefSuf (oracle/_ref/alga_ref_harness = the unmodified
-          reference sources behind a file-reading main; else the plain-C oracle port), all host threads, on a
-          bounded sample of the same workload.
+  reference sources behind a file-reading main; else the plain-C oracle port), all host threads, on a bounded sample
+  (genome-scaled: same read length and coverage) of the same workload; the sample is named in cpu_baseline.sample.
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definition of every key.
 """
@@ -110,6 +114,29 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------------
+# workloads
+def golden_for(workload: str, gen: str, scale: float):
+    """The reference's own result for this read set (tests/golden/full_*.json), or None."""
+    tag = workload if scale == 1.0 else f"{workload}_at_{scale:g}"
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", f"full_{tag}_{gen}.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def host_workload(workload: str, gen: str, scale: float):
+    """-> (ReadSet, params, name, records, genome_size) on the host (CPU legs, small scales)."""
+    from alga_b200 import synth, synth_dev
+
+    if gen == "np":
+        w = synth.make_config(workload, scale)
+        return w.reads, w.params, w.name, w.records, w.genome_size
+    w = synth_dev.make_config(workload, scale)
+    return w.to_readset(), w.params, w.name, w.records, w.genome_size
+
+
+# --------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference's CPU graph creator on a bounded sample
 def _cpu_threads() -> int:
     try:
@@ -131,17 +158,25 @@ def _cpu_build(reads, params, threads):
     return time.perf_counter() - t, "port", 1
 
 
-def cpu_sample(workload: str, target_s: float):
-    """Pick a genome-scale so that one CPU build of the sample takes about target_s; returns (Workload, calib)."""
+def cpu_sample(workload: str, gen: str, target_s: float):
+    """Pick a genome scale so that one CPU build of the sample takes about target_s; -> (host workload tuple, calib)."""
     from alga_b200 import synth
 
     threads = _cpu_threads()
-    probe = synth.make_config(workload, scale=0.01 if workload != "cfg1" else 0.05)
-    s, kind, used = _cpu_build(probe.reads, probe.params, threads)
-    rate = probe.reads.n / max(s, 1e-3)  # nodes/s on the tiny probe (pessimistic for the threaded reference)
-    full_nodes = probe.reads.n / (0.01 if workload != "cfg1" else 0.05)
-    scale = min(1.0, max(0.01, rate * target_s / full_nodes))
-    return synth.make_config(workload, scale=scale), dict(kind=kind, threads=used, scale=scale)
+    gsize = synth.CONFIGS[workload]["genome_size"]
+    s0 = min(1.0, 50_000 / gsize)
+    probe = host_workload(workload, gen, s0)
+    s, kind, used = _cpu_build(probe[0], probe[1], threads)
+    rate = probe[0].n / max(s, 1e-3)  # nodes/s on the tiny probe (pessimistic for the threaded reference)
+    full_nodes = probe[0].n / s0
+    scale = min(1.0, max(s0, rate * target_s / full_nodes))
+    return host_workload(workload, gen, scale), dict(kind=kind, threads=used, scale=scale)
+
+
+def _sample_text(hw, cal) -> str:
+    reads, _params, name, records, gsize = hw
+    return (f"{name}: genome scale {cal['scale']:.4g} of the named workload = {reads.n} nodes ({records} records, genome {gsize} bp, "
+            f"same read length and coverage), region main.cpp:282-291 timed by steady_clock inside the harness")
 
 
 def run_reference(args):
@@ -150,22 +185,21 @@ def run_reference(args):
         return 0
     total = args.steps + args.warmup
     target = min(10.0, max(1.0, 150.0 / max(total, 1)))
-    w, cal = cpu_sample(args.workload, target)
+    hw, cal = cpu_sample(args.workload, args.gen, target)
     times = []
     for i in range(total):
-        s, kind, used = _cpu_build(w.reads, w.params, cal["threads"])
+        s, kind, used = _cpu_build(hw[0], hw[1], cal["threads"])
         if i >= args.warmup:
             times.append(s)
     ms = 1e3 * float(np.mean(times))
-    value = w.reads.n / (ms / 1e3)
-    sample = (f"{w.name}: {w.reads.n} nodes ({w.records} records, genome {w.genome_size} bp), region main.cpp:282-291 "
-              f"timed by steady_clock inside the harness")
+    value = hw[0].n / (ms / 1e3)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64/u32 (polynomial hashes mod 1e18+3, 1e9+7)", "data": "synthetic",
-        "config": workload_config(args.workload, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cal["threads"], "kind": cal["kind"], "sample": sample},
+        "config": workload_config(args.workload, args.gpus, args.scale, args.gen),
+        "sample_scale": cal["scale"], "sample_nodes": hw[0].n,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cal["threads"], "kind": cal["kind"], "sample": _sample_text(hw, cal)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -173,19 +207,18 @@ def run_reference(args):
     return 0
 
 
-def workload_config(workload: str, n_gpus: int, scale: float = 1.0, strong: bool = False) -> dict:
+def workload_config(workload: str, n_gpus: int, scale: float = 1.0, gen: str = "dev") -> dict:
     from alga_b200 import synth
 
     kw = synth.CONFIGS[workload]
     desc = (f"{workload}{'' if scale == 1.0 else f' at genome scale {scale:g}'}: synthetic {kw['genome_size'] * scale / 1e6:g} Mbp random genome, "
             f"{'2x' if kw['paired'] else ''}{kw['read_len']} bp {'paired' if kw['paired'] else 'single-end'} reads at "
-            f"{kw['coverage']}x, error {kw.get('error', 0.0):g}, --error_rate=0 (GraphCreatorPrefSuf only)")
-    if n_gpus > 1 and strong:
+            f"{kw['coverage']}x, error {kw.get('error', 0.0):g}, seed {kw['seed']}, --error_rate=0 (GraphCreatorPrefSuf only); generator "
+            f"{'alga_b200/synth_dev.py (counter-based)' if gen == 'dev' else 'alga_b200/synth.py (NumPy default_rng)'}")
+    if n_gpus > 1:
         desc += f"; strong scaling: the same read set, contiguous read-id ranges over {n_gpus} ranks"
-    elif n_gpus > 1:
-        desc += f"; weak scaling: {n_gpus} such chromosomes (seeds {kw['seed']}+100r), reads interleaved over ranks"
     return {"workload": desc, "l2": "explicit flush (256 MiB write) between timed steps; step inputs+index also exceed L2",
-            "sharding": "1 GPU" if n_gpus == 1 else f"read-id ranges over {n_gpus} GPUs, replicated packed reads + seed index"}
+            "sharding": "1 GPU" if n_gpus == 1 else f"read-id ranges over {n_gpus} GPUs"}
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -193,8 +226,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from alga_b200 import _lib, synth
-    from alga_b200.plan import DeviceReads, PrefSufPlan
+    from alga_b200 import _lib, edge_hash, synth, synth_dev
+    from alga_b200.plan import READ_PAD_BYTES, DeviceReads, PrefSufPlan
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -210,61 +243,56 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    kw = dict(synth.CONFIGS[args.workload])
-    kw["genome_size"] = max(20_000, int(kw["genome_size"] * args.scale))
-    strong = args.scaling == "strong"
-    if not strong:
-        kw["seed"] = kw["seed"] + 100 * rank  # weak scaling: every rank brings its own chromosome
+    # ---- the read set, generated on this rank's GPU (every rank generates the same one) ----------------------
     t0 = time.time()
-    strong_words = None
-    if strong and world > 1:
-        # one read set for all ranks: rank 0 generates it (host memory!), the packed words travel over NCCL
-        meta = [None]
-        if rank == 0:
-            w = synth.make_workload(args.workload, **kw)
-            W_ = int(w.reads.word_off[1] - w.reads.word_off[0])
-            meta = [dict(n=w.reads.n, W=W_, len_nt=int(w.reads.len_nt[0]), params=w.params, records=w.records)]
-        dist.broadcast_object_list(meta, src=0)
-        m = meta[0]
-        strong_words = torch.empty((m["n"], m["W"]), dtype=torch.int32, device=dev)
-        if rank == 0:
-            strong_words.copy_(torch.from_numpy(w.reads.words.view(np.int32).reshape(m["n"], m["W"])))
-        dist.broadcast(strong_words, src=0)
-        params, len_nt, n_records = m["params"], m["len_nt"], m["records"]
+    if args.gen == "dev":
+        dw = synth_dev.make_config(args.workload, args.scale, device=dev)
+        words2d, len_nt, params, n_records = dw.words, dw.len_nt, dw.params, dw.records
+        del dw
     else:
-        w = synth.make_workload(args.workload, **kw)
-        params = w.params
-        len_nt = int(w.reads.len_nt[0])
-        n_records = w.records
+        w = synth.make_config(args.workload, args.scale)
+        assert int(w.reads.len_nt.min()) == int(w.reads.len_nt.max()), "bench.py runs equal-length read sets"
+        W_ = int(w.reads.word_off[1] - w.reads.word_off[0])
+        words2d = torch.from_numpy(w.reads.words.view(np.int32).reshape(w.reads.n, W_)).to(dev)
+        len_nt, params, n_records = int(w.reads.len_nt[0]), w.params, w.records
+    torch.cuda.synchronize(dev)
     gen_s = time.time() - t0
+    n_nodes_total, W = int(words2d.shape[0]), int(words2d.shape[1])
+    torch.cuda.empty_cache()
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     clocks = ClockSampler(local)
 
     if world == 1:
-        n_nodes_total = w.reads.n
-        dreads = DeviceReads(w.reads, dev)
+        flat = torch.zeros(n_nodes_total * W + READ_PAD_BYTES // 4, dtype=torch.int32, device=dev)
+        flat[: n_nodes_total * W].copy_(words2d.reshape(-1))
+        lens = torch.full((n_nodes_total,), len_nt, dtype=torch.int32, device=dev)
+        dreads = DeviceReads.from_tensors(flat, lens, stride=W, n=n_nodes_total, max_len=len_nt)
+        host_words = words2d.cpu().numpy().view(np.uint32).reshape(-1) if args.e2e_steps != 0 else None  # for the e2e leg
+        del words2d
+        torch.cuda.empty_cache()
         plan = PrefSufPlan(params.min_overlap, params.rs_min_overlap, params.min_offset, params.max_len_cap, device=dev)
         plan.bind(dreads)
+        row_lo = 0
 
         def step():
             plan.run()
 
         def step_stats():
             return plan.stats()
-    else:
-        from alga_b200.distributed import ShardedPrefSuf, interleave_shards
 
-        if strong:  # rank r takes the r-th contiguous id range
-            n_nodes_total = (strong_words.shape[0] // (2 * world)) * 2 * world
-            per = n_nodes_total // world
-            shard_words = strong_words[rank * per:(rank + 1) * per].clone()
-            del strong_words
-        else:
-            shard_words, n_nodes_total = interleave_shards(w.reads, rank, world, dev)
+        def result_device():
+            return plan.result_device()
+    else:
+        from alga_b200.distributed import ShardedPrefSuf
+
+        per = ((n_nodes_total + world - 1) // world + 1) & ~1  # reads per rank (even: twins stay together); the last rank has fewer
+        row_lo = min(rank * per, n_nodes_total)
+        shard_words = words2d[row_lo:min(row_lo + per, n_nodes_total)].clone()
+        del words2d
+        torch.cuda.empty_cache()
         sp = ShardedPrefSuf(params.min_overlap, params.rs_min_overlap, params.min_offset, params.max_len_cap, dev,
-                            rank, world, len_nt=len_nt, n_shard=int(shard_words.shape[0]),
-                            words_per_read=int(shard_words.shape[1]))
+                            rank, world, len_nt=len_nt, n_shard=per, words_per_read=W, n_total=n_nodes_total)
         sp.load_shard(shard_words)  # the rank's packed reads, resident in its peer-visible HBM buffer
 
         def step():
@@ -272,6 +300,9 @@ def run_ours(args):
 
         def step_stats():
             return sp.stats()
+
+        def result_device():
+            return sp.result_device()
 
     def barrier():
         if world > 1:
@@ -309,54 +340,69 @@ def run_ours(args):
     dev_ms = float(t.item())
     ms_per_step = dev_ms / args.steps
     value = n_nodes_total / (ms_per_step / 1e3)
-    if world == 1:
-        n_edges = plan.n_edges()
-    else:
-        n_edges = sp.total_edges()
+
+    # ---- parity gate: digest of the graph the last timed step built, against the reference's own graph --------
+    ro, nb, of = result_device()
+    dg = edge_hash.digest_csr(ro, nb, of, first_row=row_lo)
+    n_edges = int(nb.numel())
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, (dg, n_edges))
+        dg, n_edges = (0, 0), 0
+        for d_, e_ in parts:
+            dg, n_edges = edge_hash.add(dg, d_), n_edges + e_
+    digest = [f"{dg[0]:016x}", f"{dg[1]:016x}"]
+    gold = golden_for(args.workload, args.gen, args.scale)
+    parity, parity_note = None, "no reference golden for this workload / scale (tests/golden/make_full_golden.py makes one)"
+    if gold is not None:
+        parity = bool(gold["nodes"] == n_nodes_total and gold["edges"] == n_edges and gold["digest"] == digest)
+        parity_note = (f"edge-set digest of the last timed step vs the unmodified reference at --threads={gold['threads']} "
+                       f"(tests/golden/full_*.json: {gold['nodes']} nodes, {gold['edges']} edges)")
 
     # ---- e2e: the reference-facing call (GraphCreatorPrefSuf over alga_gpu_prefsuf_build) with host buffers ----
     e2e = None
-    if world == 1:
+    if world == 1 and host_words is not None:
         from alga_b200.graph_creator import GraphCreatorPrefSuf
+        from alga_b200.readset import ReadSet
 
-        gc = GraphCreatorPrefSuf(w.reads, params.min_overlap, params.rs_min_overlap, params.min_offset,
-                                 params.max_len_cap, device=local, pinned=True)
-        for _ in range(max(1, min(args.warmup, 3))):
+        hreads = ReadSet(host_words, np.arange(n_nodes_total + 1, dtype=np.uint64) * np.uint64(W),
+                         np.full(n_nodes_total, len_nt, np.uint32))
+        # borrow=True: the result stays in the library's page-locked staging, as the C++ shim reads it
+        gc = GraphCreatorPrefSuf(hreads, params.min_overlap, params.rs_min_overlap, params.min_offset,
+                                 params.max_len_cap, device=local, pinned=True, borrow=True)
+        del hreads, host_words
+        for _ in range(2):
             gc.startAlignmentGraphCreation()
         torch.cuda.synchronize(dev)
-        k_e2e = max(1, min(args.steps, 10))
+        k_e2e = args.e2e_steps if args.e2e_steps > 0 else max(1, min(args.steps, 10 if n_nodes_total < 10_000_000 else 5))
         ts = time.perf_counter()
         for _ in range(k_e2e):
             g = gc.startAlignmentGraphCreation()
         torch.cuda.synchronize(dev)
         e2e_ms = 1e3 * (time.perf_counter() - ts) / k_e2e
         assert g.n_edges == n_edges, (g.n_edges, n_edges)
-        h2d = int(w.reads.words.nbytes + w.reads.len_nt.nbytes + w.reads.align_from.nbytes + w.reads.align_to.nbytes)
+        r_ = gc.reads
+        h2d = int(r_.words.nbytes + r_.len_nt.nbytes + gc.alignFrom.nbytes + gc.alignTo.nbytes)
         d2h = int(g.row_off.nbytes + g.nbr.nbytes + g.off.nbytes)
         e2e = {"value": n_nodes_total / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": k_e2e,
                "call": "alga_b200.GraphCreatorPrefSuf.startAlignmentGraphCreation -> alga_gpu_prefsuf_build (host buffers)",
                "timing": gc.timing}
-    else:
+    elif world > 1:
         e2e = sp.e2e(shard_words, steps=max(1, min(args.steps, 5)), n_nodes_total=n_nodes_total)
 
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
-        return 0
+        return 0 if parity is not False else 3
 
     peak, peak_src = measured_peak_gbs()
     b_alg = alg_bytes_per_node(len_nt, params.min_overlap, n_edges / max(n_nodes_total, 1))
     nodes_per_gpu = n_nodes_total / world
     achieved = nodes_per_gpu * b_alg / (ms_per_step / 1e3) / 1e9
     stages = {k: v / args.steps for k, v in stage_acc.items()}
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f)
-    except Exception:
-        pass
+    traffic = measured_traffic(args.workload, args.scale, world)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (traffic or {}).get("pipeline_dram_bytes_per_step"), "peak_source": peak_src,
                 "kernel": "whole device pipeline of one step (index + phase1 + phase2 + csr), per GPU",
@@ -372,27 +418,30 @@ def run_ours(args):
         b1 = 64 * n_l1
         k2 = nodes_per_gpu * b2 / (stages["phase2"] / 1e3) / 1e9
         k1 = nodes_per_gpu * b1 / (stages["phase1"] / 1e3) / 1e9
-        roofline["dominant_kernel"] = {"kernel": "phase2_tpr_kernel (+ its spill kernels; 51 % of the step)", "bound": "hbm",
+        share2, share1 = stages["phase2"] / ms_per_step, stages["phase1"] / ms_per_step
+        roofline["dominant_kernel"] = {"kernel": f"phase 2 (+ its spill kernels; {100 * share2:.0f} % of the step)", "bound": "hbm",
                                        "achieved": k2, "peak": peak, "unit": "GB/s", "frac": k2 / peak,
                                        "alg_bytes_per_node": b2, "ms": stages["phase2"],
-                                       "traffic": (traffic or {}).get("phase2_tpr_kernel")}
-        roofline["second_kernel"] = {"kernel": "phase1_tpr_kernel (+ its queue kernel; 37 % of the step)", "bound": "hbm",
+                                       "traffic": (traffic or {}).get("phase2")}
+        roofline["second_kernel"] = {"kernel": f"phase 1 (+ its queue kernel; {100 * share1:.0f} % of the step)", "bound": "hbm",
                                      "achieved": k1, "peak": peak, "unit": "GB/s", "frac": k1 / peak,
                                      "alg_bytes_per_node": b1, "ms": stages["phase1"],
-                                     "traffic": (traffic or {}).get("phase1_tpr_kernel")}
+                                     "traffic": (traffic or {}).get("phase1")}
 
     cpu = None
     if world == 1 and not args.no_cpu:
-        sample, cal = cpu_sample(args.workload, 12.0)
-        s, kind, used = _cpu_build(sample.reads, sample.params, cal["threads"])
-        cpu = {"value": sample.reads.n / s, "unit": UNIT, "cores": used, "kind": kind, "seconds": s,
-               "sample": f"{sample.name}: {sample.reads.n} nodes, one build, region main.cpp:282-291 (steady_clock)"}
+        hw, cal = cpu_sample(args.workload, args.gen, 12.0)
+        s, kind, used = _cpu_build(hw[0], hw[1], cal["threads"])
+        cpu = {"value": hw[0].n / s, "unit": UNIT, "cores": used, "kind": kind, "seconds": s, "sample": _sample_text(hw, cal)}
 
+    legs_ok = world == 1 and args.gen == "np"
+    if (args.with_input or args.with_preprocess or args.with_triangles or args.workload == "cfg3") and not legs_ok:
+        print("bench.py: the optional legs (--with-*, supplement) need --gen np on one GPU; skipped", file=sys.stderr)
     supplement = None
-    if world == 1 and args.workload == "cfg3":
+    if legs_ok and args.workload == "cfg3":
         # BASELINE configs[2]: the error-rate supplement (main.cpp:300-355) on top of the graph just built, host to host
         from alga_b200.graph_creator import GraphCreatorLI
-        from tests.cases import supplement_params
+        from alga_b200.graph_creator import supplement_params
 
         sp = supplement_params(float(w.reads.len_nt.mean()))
         li = GraphCreatorLI(w.reads, g, **sp, device=local)
@@ -403,7 +452,7 @@ def run_ours(args):
                       "note": "alga_gpu_supplement: LI k-mers, pair enumeration and canAlign on the GPU, bucket sort + ordered replay on the host"}
 
     triangles = None
-    if world == 1 and args.with_triangles:
+    if legs_ok and args.with_triangles:
         # the first simplifier step (sortEdgesByIncreasingOffset + cutNonAndWeaklyMetricTriangles) on the
         # graph just built (after the supplement where it ran), host to host
         from alga_b200.graph_creator import GraphSimplifier
@@ -427,7 +476,7 @@ def run_ours(args):
                                           "note": "oracle/_ref harness: the reference's own GraphSimplifier step on the same graph, file IO included"}
 
     preprocess = None
-    if world == 1 and args.with_preprocess:
+    if legs_ok and args.with_preprocess:
         # ReadPreprocess::getPrefixReads on the strand-reads BEFORE duplicate removal, host to host
         from alga_b200 import readset as _rs
         from alga_b200.graph_creator import ReadPreprocess
@@ -458,7 +507,7 @@ def run_ours(args):
                                            "note": "oracle/_ref harness: ReadPreprocess::getPrefixReads on 1/8 of the reads, file IO included"}
 
     input_leg = None
-    if world == 1 and args.with_input:
+    if legs_ok and args.with_input:
         # the files of the workload through InputReader::readInput on the GPU (alga_gpu_read_input), and
         # the whole driver path main.cpp:82-291 (reader, prefix-read removal, renumbering, GraphCreatorPrefSuf), host to host
         from alga_b200.input_reader import FASTA, InputReader, build_overlap_graph
@@ -517,10 +566,11 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64 (2-bit packed words, exact compare)", "data": "synthetic",
-        "config": workload_config(args.workload, world, args.scale, strong),
-        "nodes": n_nodes_total, "records": n_records * (1 if strong else world), "edges": n_edges, "gen_s": gen_s, "wall_s_timed_region": wall_s,
+        "config": workload_config(args.workload, world, args.scale, args.gen),
+        "nodes": n_nodes_total, "records": n_records, "edges": n_edges, "parity": parity, "parity_note": parity_note,
+        "edge_digest": digest, "gen_s": gen_s, "wall_s_timed_region": wall_s,
         "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }
     if supplement:
@@ -535,7 +585,22 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity is False:
+        print("bench.py: PARITY FAILED -- the edge set differs from the reference's", file=sys.stderr)
+        return 3
     return 0
+
+
+def measured_traffic(workload: str, scale: float, world: int):
+    """ncu DRAM bytes of one step (profiles/traffic_r2.json), only if it was captured for this very workload and N."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_r2.json")) as f:
+            t = json.load(f)
+        if t.get("workload") == workload and float(t.get("scale", 1.0)) == float(scale) and int(t.get("n_gpus", 1)) == world:
+            return t
+    except Exception:
+        pass
+    return None
 
 
 def main():
@@ -544,8 +609,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--workload", default="cfg4", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--gen", default="dev", choices=["dev", "np"],
+                    help="read-set generator: dev = synth_dev (counter-based, on the GPU), np = synth (NumPy, host)")
     ap.add_argument("--scale", type=float, default=1.0, help="genome scale of the GPU workload (1.0 = the named config)")
+    ap.add_argument("--e2e-steps", type=int, default=-1, help="timed steps of the host-buffer leg (0 = skip it)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--with-preprocess", action="store_true",
                     help="also time ReadPreprocess::getPrefixReads (alga_gpu_prefix_reads) on the reads before dedupe")
@@ -553,8 +621,6 @@ def main():
                     help="also time the first simplifier step (alga_gpu_cut_triangles) on the graph just built")
     ap.add_argument("--with-input", action="store_true",
                     help="also time InputReader::readInput (alga_gpu_read_input) and the files-to-graph path on FASTA text of the workload")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = N chromosomes of the workload (default), strong = the one workload split N ways")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)

@@ -4,6 +4,7 @@ from __future__ import annotations
 import numpy as np
 
 from alga_b200 import readset, synth
+from alga_b200.graph_creator import supplement_params  # noqa: F401  (re-exported for the tests)
 
 
 def _periodic(seed, n_reads, dedupe):
@@ -129,16 +130,6 @@ def verify_case(seed=31, n_reads=4000, genome=20000, read_len=144, error=0.01):
     pairs = np.array([p for p in pairs if p[2] >= 0], dtype=np.int32)
     vp = dict(threshold_pct=97, max_offset_pct=32, min_overlap_area=111, min_offset=0)
     return rs, pairs, vp
-
-
-def supplement_params(avg_len: float, error_rate_pct: int = 2, scale: float = 0.55):
-    """Params of the supplement as the reference driver derives them (main.cpp:93-115, 332-340), float arithmetic as there."""
-    LEN = int(avg_len) + 6
-    L = int(np.float32(LEN) * np.float32(scale))
-    return dict(threshold_pct=99 - error_rate_pct,
-                max_offset_pct=int((np.float32(1.0) - np.float32(scale)) * np.float32(avg_len) / 2),
-                min_overlap_area=int((np.float32(1.0) + np.float32(scale)) * np.float32(avg_len) / 2),
-                kmer_length_bucket=min(2 * L // 3, 60))
 
 
 SUPPLEMENT_CASES = ["sup_cfg3", "sup_varlen"]
