@@ -142,6 +142,7 @@ struct alga_ps_plan {
 
     // owned copies (upload path)
     DevBuf words, word_off, len, from, to;
+    DevBuf slots;  // sector-aligned copy of a fixed-stride, equal-length read set (alga_ps_plan_run), what the fast kernels read
     // workspace
     DevBuf stats_d, counters_d, tp, ts, rows, over, list1, hard1, hard1b, spill_queue2, indeg, rev_off, rev, triples, triples1, outdeg, scan_ws,
         spill_queue, caps, spill_off, spill_store, row_off, nbr, off, big_rows, tmp_nbr, tmp_off;
@@ -163,7 +164,7 @@ struct alga_ps_plan {
     cudaEvent_t ev_stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     ~alga_ps_plan() {
-        DevBuf *all[] = {&words, &word_off, &len, &from, &to, &stats_d, &counters_d, &tp, &ts, &rows, &over, &list1, &hard1, &hard1b, &spill_queue2, &indeg, &rev_off, &rev,
+        DevBuf *all[] = {&words, &word_off, &len, &from, &to, &slots, &stats_d, &counters_d, &tp, &ts, &rows, &over, &list1, &hard1, &hard1b, &spill_queue2, &indeg, &rev_off, &rev,
                          &triples, &triples1, &outdeg, &scan_ws, &spill_queue, &caps, &spill_off, &spill_store, &row_off,
                          &nbr, &off, &big_rows, &tmp_nbr, &tmp_off};
         for (DevBuf *b : all) b->release();
@@ -861,8 +862,26 @@ int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
     const int force = plan->params.flags & ALGA_PS_FORCE_GENERIC;
     Counters *dc = plan->counters_d.as<Counters>();
     if (plan->over_cap < kOverScanMax) plan->over_cap = n / 8 + 65536;
+    // Equal-length reads at a fixed stride (the usual case): the kernels work on a copy whose read slots start on 32-byte
+    // sector boundaries, so that a candidate read is fetched with one or two 32-byte requests instead of a dozen 4-byte
+    // ones (common.cuh load8_na).  The copy is part of the timed pipeline: the caller's layout is the reference's.
+    struct RestoreReads {
+        alga_ps_plan *p;
+        ReadsDev r;
+        ~RestoreReads() { p->R = r; }
+    } restore_reads{plan, plan->R};
+    const bool repack = plan->P.uniform_len && !plan->R.word_off && n &&
+                        (plan->R.stride != aligned_stride_words((plan->P.uniform_len + 15u) / 16u) || ((uintptr_t) plan->R.words & 31u));
     for (int attempt = 0;; attempt++) {
         CK(cudaEventRecord(plan->ev0, s));
+        if (repack) {
+            const uint32_t W = (plan->P.uniform_len + 15u) / 16u, S = aligned_stride_words(W);
+            CKR(plan->slots.ensure((size_t) n * S * 4 + kReadPadBytes));
+            launch_repack_reads(restore_reads.r.words, restore_reads.r.stride, W, n, plan->slots.as<uint32_t>(), S, s, plan->cfg);
+            CK(cudaMemsetAsync(plan->slots.as<char>() + (size_t) n * S * 4, 0, kReadPadBytes, s));
+            plan->R.words = plan->slots.as<uint32_t>();
+            plan->R.stride = S;
+        }
         // seed index: the prefix table on this stream, the suffix table -- first needed by phase 2 -- on a side stream,
         // so its build overlaps phase 1
         CK(cudaEventRecord(plan->ev_fork, s));

@@ -341,6 +341,18 @@ __device__ __forceinline__ void load_bucket_na(const uint32_t *__restrict__ p, u
                  : "l"(p), "l"(policy));
 }
 
+// Eight consecutive words of a packed read from a 32-byte aligned address: ONE request to the memory system.  On B200 a
+// random access that misses L2 costs the same whatever its size up to a sector (39.4 G requests/s, measured:
+// scripts/probes/random_requests.cu), and L2 does not merge concurrent misses to one sector -- eight 4-byte loads of a
+// sector that is still on its way are eight DRAM reads.  Not allocated in L1 (random data is never reused there).
+__device__ __forceinline__ void load8_na(const uint32_t *__restrict__ p, uint32_t (&e)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(e[0]), "=r"(e[1]), "=r"(e[2]), "=r"(e[3]), "=r"(e[4]), "=r"(e[5]), "=r"(e[6]), "=r"(e[7])
+                 : "l"(p));
+}
+// words per read slot of the aligned copy the fast kernels work on: a multiple of one sector
+__host__ __device__ __forceinline__ uint32_t aligned_stride_words(uint32_t words) { return (words + 7u) & ~7u; }
+
 // Walk the bucket chain of hash h and call f(read_id) for every entry whose tag matches.
 template <class F>
 __device__ __forceinline__ void probe_seed_at(const SeedTable &t, uint64_t h, uint32_t bk, F &&f);

@@ -128,6 +128,9 @@ void launch_scan_u64(const uint32_t *in, uint64_t *out, uint64_t n, void *worksp
 void launch_fill_u64(uint64_t *p, uint64_t v, uint64_t n, cudaStream_t s, const LaunchCfg &cfg);
 void launch_pack_reads(const uint8_t *ascii, uint32_t n_reads, uint32_t len_nt, uint32_t *words, cudaStream_t s,
                        const LaunchCfg &cfg);
+// copy of a fixed-stride read set at another stride (`words` words per read are copied, the rest of the slot is zero)
+void launch_repack_reads(const uint32_t *in, uint32_t stride_in, uint32_t words, uint64_t n_reads, uint32_t *out,
+                         uint32_t stride_out, cudaStream_t s, const LaunchCfg &cfg);
 void launch_fingerprints(const ReadsDev &R, int L, uint64_t *pre64, uint32_t *pre32, uint64_t *suf64,
                          uint32_t *suf32, cudaStream_t s, const LaunchCfg &cfg);
 struct VerifyDev {

@@ -159,7 +159,27 @@ verify_pairs_kernel(ReadsDev R, const int32_t *__restrict__ pairs, uint64_t n_pa
     }
 }
 
+// Aligned copy of a fixed-stride read set: read i -> out[i * stride_out .. + words), zero up to the stride.  One thread
+// per output word: loads and stores are coalesced (consecutive threads, consecutive addresses on both sides up to the
+// stride change).
+__global__ void repack_reads_kernel(const uint32_t *__restrict__ in, uint32_t stride_in, uint32_t words, uint64_t n_reads,
+                                    uint32_t *__restrict__ out, uint32_t stride_out) {
+    const uint64_t total = n_reads * stride_out;
+    for (uint64_t j = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; j < total; j += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t i = j / stride_out;
+        const uint32_t w = (uint32_t) (j - i * stride_out);
+        out[j] = w < words ? __ldg(in + i * stride_in + w) : 0u;
+    }
+}
+
 }  // namespace
+
+void launch_repack_reads(const uint32_t *in, uint32_t stride_in, uint32_t words, uint64_t n_reads, uint32_t *out,
+                         uint32_t stride_out, cudaStream_t s, const LaunchCfg &cfg) {
+    if (!n_reads) return;
+    repack_reads_kernel<<<grid_for(n_reads * stride_out, 256, cfg, 8), 256, 0, s>>>(in, stride_in, words, n_reads, out, stride_out);
+    bump(cfg);
+}
 
 void launch_pack_reads(const uint8_t *ascii, uint32_t n_reads, uint32_t len_nt, uint32_t *words, cudaStream_t s,
                        const LaunchCfg &cfg) {

@@ -43,7 +43,7 @@ constexpr int kTpr = 128;     // threads per block = 4 independent warps
 constexpr int kWarps = kTpr / 32;
 // tuning knobs (scripts/build_variant.sh builds A/B variants with -D...)
 #ifndef ALGA_P1_BLOCKS
-#define ALGA_P1_BLOCKS 6
+#define ALGA_P1_BLOCKS 5
 #endif
 #ifndef ALGA_P2_BLOCKS
 #define ALGA_P2_BLOCKS 4
@@ -80,20 +80,9 @@ __device__ __forceinline__ uint64_t l2_evict_last_policy() {
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
-__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gmem_src) {
+__device__ __forceinline__ void cp_async8(uint64_t *smem_dst, const uint32_t *gmem_src) {  // 8-byte aligned on both sides
     const uint32_t d = (uint32_t) __cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-// one 32-byte bucket -> two 16-byte chunks of the ring (L2 only, kept in L2 with priority)
-__device__ __forceinline__ void cp_async_bucket(uint32_t *dst_lo, uint32_t *dst_hi, const uint32_t *bucket, uint64_t pol) {
-    const uint32_t d0 = (uint32_t) __cvta_generic_to_shared(dst_lo), d1 = (uint32_t) __cvta_generic_to_shared(dst_hi);
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d0), "l"(bucket), "l"(pol) : "memory");
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d1), "l"(bucket + 4), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -188,9 +177,24 @@ __device__ __forceinline__ void stage_warp(const ReadsDev &R, uint32_t *wown, in
         const uint32_t nw = FAST ? ((uint32_t) lane < n_valid ? (uint32_t) sw : 0u) : my_words;
         for (int w = 0; w < wp; w++) own[w] = (uint32_t) w < nw ? __ldg(p + w) : 0u;
     } else if (FAST) {
-        for (int w = sw; w < wp; w++) own[w] = 0u;
+        for (int w = min(sw, (int) R.stride); w < wp; w++) own[w] = 0u;
         const uint32_t *base = R.words + first * R.stride;
-        if ((uint32_t) sw == R.stride) {
+        if ((R.stride & 3u) == 0 && ((uintptr_t) base & 15u) == 0) {
+            // sector-aligned slots: the tile is one contiguous range, 16 bytes per lane and load
+            const uint32_t q_per_read = R.stride >> 2, total = n_valid * q_per_read;
+            const uint4 *b4 = reinterpret_cast<const uint4 *>(base);
+            for (uint32_t j = lane; j < total; j += 32) {
+                const uint32_t r = j / q_per_read, w = (j - r * q_per_read) << 2;
+                if (w < (uint32_t) sw) {
+                    const uint4 v = __ldg(b4 + j);
+                    uint32_t *d = wown + r * wp + w;
+                    d[0] = v.x;
+                    if (w + 1 < (uint32_t) sw) d[1] = v.y;
+                    if (w + 2 < (uint32_t) sw) d[2] = v.z;
+                    if (w + 3 < (uint32_t) sw) d[3] = v.w;
+                }
+            }
+        } else if ((uint32_t) sw == R.stride) {
             const uint32_t total = n_valid * (uint32_t) sw;
             uint32_t r = (uint32_t) lane / (uint32_t) sw, w = (uint32_t) lane - r * (uint32_t) sw;
             const uint32_t dr = 32u / (uint32_t) sw, dw = 32u - dr * (uint32_t) sw;
@@ -256,6 +260,43 @@ __device__ __forceinline__ bool verify_own_prefix(const ReadsDev &R, const uint3
                 uint32_t x = __funnelshift_r(g[j], g[j + 1], sh) ^ own[k];
                 if (k == nw - 1 && (nbits & 31u)) x &= (1u << (nbits & 31u)) - 1u;
                 diff |= x;
+            }
+        }
+        if (diff) return false;
+    }
+    return true;
+}
+
+// The same test for sector-aligned read slots (fast path): the candidate's words arrive as whole 32-byte sectors, one
+// request each, and stay unshifted in registers; the OWN read (shared memory, any index is cheap there) is shifted up
+// by the offset instead.  Word j of the candidate lines up with bits [32 j - 2 o, +32) of the own read.
+__device__ __forceinline__ bool verify_own_prefix_aligned(const ReadsDev &R, const uint32_t *own, uint32_t cand, uint32_t o,
+                                                          int32_t L) {
+    const uint32_t *pb = R.words + (uint64_t) cand * R.stride;
+    const int32_t nb = 2 * L, sh2 = 2 * (int32_t) o;
+    const int32_t n_words = (sh2 + nb + 31) >> 5;  // candidate words that hold compared bits
+    for (int32_t s0 = 0; s0 < n_words; s0 += 16) {  // two sectors per round, both requested before the first compare
+        uint32_t g[2][8];
+        load8_na(pb + s0, g[0]);
+        if (s0 + 8 < n_words) load8_na(pb + s0 + 8, g[1]);
+        uint32_t diff = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int32_t p = 32 * (s0 + 8 * h + j) - sh2;  // own-read bit that meets bit 0 of this candidate word
+                if (s0 + 8 * h < n_words && p + 32 > 0 && p < nb) {
+                    uint32_t cw, mask = 0xFFFFFFFFu;
+                    if (p >= 0) {
+                        const uint32_t w = (uint32_t) p >> 5;
+                        cw = __funnelshift_r(own[w], own[w + 1], (uint32_t) p & 31u);
+                    } else {
+                        cw = own[0] << (uint32_t) (-p);
+                        mask <<= (uint32_t) (-p);
+                    }
+                    if (nb - p < 32) mask &= (1u << (uint32_t) (nb - p)) - 1u;
+                    diff |= (g[h][j] ^ cw) & mask;
+                }
             }
         }
         if (diff) return false;
@@ -405,16 +446,26 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
                     uint32_t diff[kBatch];
 #pragma unroll
                     for (int k = 0; k < kBatch; k++) diff[k] = 0u;
-                    for (int k0 = 0; k0 < nw_max; k0 += 4) {
-                        uint32_t g[kBatch][4];
+                    // FAST: read slots are sector aligned, eight words of a candidate = ONE 32-byte request (a prefix of up
+                    // to 128 nucleotides is a single request; 4-byte loads of a sector that is still on its way from DRAM
+                    // would each fetch it again)
+                    constexpr int kChunk = FAST ? 8 : 4;
+                    for (int k0 = 0; k0 < nw_max; k0 += kChunk) {
+                        uint32_t g[kBatch][kChunk];
 #pragma unroll
                         for (int k = 0; k < kBatch; k++) {
                             if (base + k < np_max) {
                                 const bool on = base + k < np && !hard;
                                 const uint32_t *pcand = read_ptr(R, on ? pc[base + k] : b);
                                 const int nw = on ? (2 * pl[base + k] + 31) >> 5 : 0;
+                                if constexpr (FAST) {
 #pragma unroll
-                                for (int j = 0; j < 4; j++) g[k][j] = k0 + j < nw ? __ldg(pcand + k0 + j) : 0u;
+                                    for (int j = 0; j < kChunk; j++) g[k][j] = 0u;
+                                    if (k0 < nw) load8_na(pcand + k0, reinterpret_cast<uint32_t(&)[8]>(g[k]));
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < kChunk; j++) g[k][j] = k0 + j < nw ? __ldg(pcand + k0 + j) : 0u;
+                                }
                             }
                         }
 #pragma unroll
@@ -424,7 +475,7 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
                                 const uint32_t o2 = 2u * (lenb - (uint32_t) pl[base + k]), shv = o2 & 31u;
                                 const uint32_t *ow = own + (o2 >> 5);
 #pragma unroll
-                                for (int j = 0; j < 4; j++) {
+                                for (int j = 0; j < kChunk; j++) {
                                     const uint32_t w = (uint32_t) (k0 + j);
                                     if (w < nw) {
                                         uint32_t x = __funnelshift_r(ow[w], ow[w + 1], shv) ^ g[k][j];
@@ -536,8 +587,10 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
 // test is dropped without ever comparing its overlap.  Entries of the transposed phase-1 graph (rows) are tested
 // against the survivors at the end.
 //
-// Shared memory per warp: own reads [32][wp] | bucket ring [kRing2][2][32] x 16 B | queue: ids [kQ2][32],
-// heads [kQ2][2][32], lengths [kQ2][32] (u16).
+// Shared memory per warp: own reads [32][wp] | queue: ids [kQ2][32], heads [kQ2][32] (u64), lengths [kQ2][32] (u16).
+// The buckets of the next kRing2 lengths are in flight in REGISTERS, one 32-byte request each (LDG.E.256): two 16-byte
+// cp.async of one sector are two requests, and L2 fetches a sector that is still on its way from DRAM once per request
+// (scripts/probes/random_requests.cu: 19.8 vs 39.4 G buckets/s).
 // id_list != nullptr: second pass -- the targets are id_list[0 .. *n_list) instead of [lo, hi)
 template <bool FAST, int MAXM, int MINI>  // MINI: 0 window-hash buckets, 1 minimizer buckets, 2 ... with a sliding minimum
 __global__ void __launch_bounds__(kTpr, ALGA_P2_BLOCKS)
@@ -546,13 +599,12 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
     extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int own_words = ((kWarps * 32 * wp + 3) & ~3);
-    constexpr int kRingWords = kRing2 * 2 * 32 * 4, kQueueWords = kQ2 * 32 * 3 + kQ2 * 32 / 2;
+    constexpr int kQueueWords = kQ2 * 32 * 3 + kQ2 * 32 / 2;
     uint32_t *wown = smem + wib * 32 * wp;
     const uint32_t *own = wown + lane * wp;
-    uint32_t *ring = smem + own_words + wib * kRingWords;  // [slot][half][lane] x 4 words
-    uint32_t *q_id = smem + own_words + kWarps * kRingWords + wib * kQueueWords + lane;  // q_id[k * 32]
-    uint32_t *q_t = q_id + kQ2 * 32;                                                     // q_t[(2k | 2k+1) * 32]
-    uint16_t *q_l = reinterpret_cast<uint16_t *>(q_id - lane + kQ2 * 32 * 3) + lane;      // q_l[k * 32]
+    uint32_t *q_id = smem + own_words + wib * kQueueWords + lane;                                // q_id[k * 32]
+    uint64_t *q_t = reinterpret_cast<uint64_t *>(q_id - lane + kQ2 * 32) + lane;                 // q_t[k * 32]: first 64 bits of the hit read
+    uint16_t *q_l = reinterpret_cast<uint16_t *>(q_id - lane + kQ2 * 32 * 3) + lane;             // q_l[k * 32]
     const uint64_t pol = l2_evict_last_policy();
     const int32_t l_lo = P.rs > P.lmin ? P.rs : P.lmin;
     const bool csr = rows_are_csr(rows);
@@ -587,7 +639,7 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
         int qn = 0;
         const bool walk = active && !hard;
         const int n_iter = warp_max(walk ? l_hi - l_lo + 1 : 0);
-        uint32_t tagr[kRing2], bkr[kRing2], w0 = 0, w1 = 0, w2 = 0, sh = 0;
+        uint32_t er[kRing2][8], tagr[kRing2], bkr[kRing2], w0 = 0, w1 = 0, w2 = 0, sh = 0;
         int wb = 0;
         int32_t Lp = l_hi;  // next length to prefetch; (w0, w1, w2, sh, wb) = register window at Lp
         SlidingMinimizer smin;  // MINI == 2 only
@@ -600,8 +652,12 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
             w0 = own[wb], w1 = own[wb + 1], w2 = own[wb + 2];
         }
 #pragma unroll
-        for (int j = 0; j < kRing2; j++) tagr[j] = 0, bkr[j] = 0;
-        auto prefetch = [&](int slot, uint32_t &tag_out, uint32_t &bk_out) {
+        for (int j = 0; j < kRing2; j++) {
+            tagr[j] = 0, bkr[j] = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) er[j][q] = kEmptySlot;
+        }
+        auto prefetch = [&](uint32_t (&e_out)[8], uint32_t &tag_out, uint32_t &bk_out) {
             if (walk && Lp >= l_lo) {
                 const uint64_t win = window_key(w0, w1, w2, sh) & P.seed_mask, h = mix64(win);
                 tag_out = tag_of(T, h);
@@ -613,8 +669,7 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
                 } else {
                     bk_out = bucket_index<MINI>(T, win, h, (uint32_t) P.seed_nt);
                 }
-                cp_async_bucket(ring + ((slot * 2) * 32 + lane) * 4, ring + ((slot * 2 + 1) * 32 + lane) * 4,
-                                T.slots + (uint64_t) bk_out * kSlotsPerBucket, pol);
+                load_bucket_na(T.slots + (uint64_t) bk_out * kSlotsPerBucket, e_out, pol);
                 Lp--;
                 if (sh == 0u) {  // slide the window down by one nucleotide
                     sh = 32u;
@@ -623,29 +678,24 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
                 }
                 sh -= 2u;
             }
-            cp_async_commit();
         };
 #pragma unroll
-        for (int j = 0; j < kRing2; j++) prefetch(j, tagr[j], bkr[j]);
+        for (int j = 0; j < kRing2; j++) prefetch(er[j], tagr[j], bkr[j]);
 
         for (int it0 = 0; it0 < n_iter; it0 += kRing2) {
 #pragma unroll
             for (int j = 0; j < kRing2; j++) {
                 const int32_t L = l_hi - (it0 + j);
                 if (walk && L >= l_lo) {
-                    cp_async_wait_group<kRing2 - 1>();
                     uint32_t e[8];
-                    {
-                        const uint4 a = *reinterpret_cast<const uint4 *>(ring + ((j * 2) * 32 + lane) * 4);
-                        const uint4 d = *reinterpret_cast<const uint4 *>(ring + ((j * 2 + 1) * 32 + lane) * 4);
-                        e[0] = a.x, e[1] = a.y, e[2] = a.z, e[3] = a.w, e[4] = d.x, e[5] = d.y, e[6] = d.z, e[7] = d.w;
-                    }
+#pragma unroll
+                    for (int q = 0; q < 8; q++) e[q] = er[j][q];
                     const uint32_t tag = tagr[j], bk = bkr[j];
                     const uint32_t m = bucket_min(e, tag);
                     uint32_t bm[MAXM];
                     int n = 0;
                     if (!hard && (m <= T.id_mask || e[7] != kEmptySlot)) probe_matches<MAXM>(T, e, tag, bk, m, bm, n);
-                    prefetch(j, tagr[j], bkr[j]);
+                    prefetch(er[j], tagr[j], bkr[j]);
                     if (n > MAXM) {
                         hard = true;
                     } else if (n) {  // walking backwards: within one length the larger source id arrived later: bm[] is descending
@@ -661,11 +711,7 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
                             }
                             q_id[qn * 32] = cand;
                             q_l[qn * 32] = (uint16_t) L;
-                            if (FAST) {
-                                const uint32_t *pb = R.words + (uint64_t) cand * R.stride;
-                                cp_async4(q_t + (2 * qn) * 32, pb);
-                                cp_async4(q_t + (2 * qn + 1) * 32, pb + 1);
-                            }
+                            if (FAST) cp_async8(q_t + qn * 32, R.words + (uint64_t) cand * R.stride);  // one request
                             qn++;
                         }
                     }
@@ -696,7 +742,7 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
                         hard = true;
                     } else {
                         if (FAST) {
-                            const uint64_t head = (uint64_t) q_t[(2 * k) * 32] | ((uint64_t) q_t[(2 * k + 1) * 32] << 32);
+                            const uint64_t head = q_t[k * 32];
                             t = o ? head << (64u - 2u * o) : 0ull;
                         } else {
                             t = overhang_tail(read_ptr(R, cand), o);
@@ -717,7 +763,7 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
             }
             if (__any_sync(kFull, want)) {
                 if (want) {
-                    if (verify_own_prefix(R, own, cand, o, L)) {
+                    if (FAST ? verify_own_prefix_aligned(R, own, cand, o, L) : verify_own_prefix(R, own, cand, o, L)) {
                         if (ns >= kSurv) {
                             hard = true;
                         } else {
@@ -736,19 +782,36 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
         // ---- in-neighbours from phase 1 (row of the transposed graph): kept unless a surviving arrival removes them
         uint32_t rowmask = 0;
         if (part && !hard) {
-            for (uint32_t r = 0; r < deg; r++) {
-                const RevEntry en = row[r];
-                const uint32_t oa = (uint32_t) en.o;
-                const uint32_t lena = FAST ? lenc : R.len[(uint32_t) en.b];
-                bool removed = false;
-#pragma unroll
-                for (int s = 0; s < kSurv; s++) {
-                    if (s < ns && s_o[s] > 0 && oa >= s_o[s] &&
-                        (FAST || (int64_t) s_len[s] + (int64_t) (oa - s_o[s]) - (int64_t) lena >= 0) &&
-                        ((en.t ^ s_t[s]) >> (64u - 2u * s_o[s])) == 0)
-                        removed = true;
+            const bool pairs = !csr && (rows.cap & 1u) == 0;  // fixed-capacity rows start on a sector: two entries per request
+            for (uint32_t r0 = 0; r0 < deg; r0 += 2) {
+                RevEntry en2[2];
+                if (pairs) {
+                    uint32_t q[8];
+                    load8_na(reinterpret_cast<const uint32_t *>(row + r0), q);
+                    en2[0].b = (int32_t) q[0], en2[0].o = (int32_t) q[1], en2[0].t = (uint64_t) q[2] | ((uint64_t) q[3] << 32);
+                    en2[1].b = (int32_t) q[4], en2[1].o = (int32_t) q[5], en2[1].t = (uint64_t) q[6] | ((uint64_t) q[7] << 32);
+                } else {
+                    en2[0] = row[r0];
+                    en2[1] = r0 + 1 < deg ? row[r0 + 1] : en2[0];
                 }
-                if (!removed) rowmask |= 1u << r;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t r = r0 + h;
+                    if (r < deg) {
+                        const RevEntry en = en2[h];
+                        const uint32_t oa = (uint32_t) en.o;
+                        const uint32_t lena = FAST ? lenc : R.len[(uint32_t) en.b];
+                        bool removed = false;
+#pragma unroll
+                        for (int s = 0; s < kSurv; s++) {
+                            if (s < ns && s_o[s] > 0 && oa >= s_o[s] &&
+                                (FAST || (int64_t) s_len[s] + (int64_t) (oa - s_o[s]) - (int64_t) lena >= 0) &&
+                                ((en.t ^ s_t[s]) >> (64u - 2u * s_o[s])) == 0)
+                                removed = true;
+                        }
+                        if (!removed) rowmask |= 1u << r;
+                    }
+                }
             }
             // Same-id replacement rule (an arrival of read x also removes any older entry of x): whatever is about
             // to be emitted must be the only occurrence of its read among the arrivals and the row, else the
@@ -850,6 +913,12 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
     }
 }
 
+// the FAST instantiations: equal-length reads, none removed, no flags, read slots on 32-byte sector boundaries
+// (alga_ps_plan_run makes such a copy; other callers fall back to the general instantiations)
+inline bool fast_layout(const ReadsDev &R, const PsDev &P) {
+    return P.uniform_len && !R.word_off && (R.stride & 7u) == 0 && ((uintptr_t) R.words & 31u) == 0;
+}
+
 inline int stride_words(int words) {
     return (words + 2) | 1;  // two pad words; odd stride: lanes of a warp fall into distinct banks
 }
@@ -866,7 +935,7 @@ void launch_phase1_tpr(const ReadsDev &R, const SeedTable &prefix, const PsDev &
     if (w > kOwnWords) w = kOwnWords;
     const int wp = stride_words(w);
     const size_t smem = (size_t) kWarps * 32 * wp * sizeof(uint32_t);
-    const bool fast = P.uniform_len && !R.word_off;
+    const bool fast = fast_layout(R, P);
     if (!id_list) {
         const int grid = warp_tile_grid(hi - lo, cfg, ALGA_P1_BLOCKS);
         auto k = !prefix.min_m ? (fast ? phase1_tpr_kernel<true, 2, 0> : phase1_tpr_kernel<false, 2, 0>)
@@ -896,9 +965,8 @@ void launch_phase2_tpr(const ReadsDev &R, const SeedTable &suffix, const PsDev &
     const int have = (int) ((max_len_nt + 15u) >> 4);
     if (w > have) w = have;
     const int wp = stride_words(w);
-    const size_t smem = (size_t) (((kWarps * 32 * wp + 3) & ~3) + kWarps * (kRing2 * 2 * 32 * 4) +
-                                  kWarps * (kQ2 * 32 * 3 + kQ2 * 32 / 2)) * sizeof(uint32_t);
-    const bool fast = P.uniform_len && !R.word_off;
+    const size_t smem = (size_t) (((kWarps * 32 * wp + 3) & ~3) + kWarps * (kQ2 * 32 * 3 + kQ2 * 32 / 2)) * sizeof(uint32_t);
+    const bool fast = fast_layout(R, P);
     if (!id_list) {
         const int grid = warp_tile_grid(hi - lo, cfg, ALGA_P2_BLOCKS);
         auto k = !suffix.min_m ? (fast ? phase2_tpr_kernel<true, 2, 0> : phase2_tpr_kernel<false, 2, 0>)
