@@ -245,50 +245,46 @@ int compute_stats(alga_ps_plan *plan, cudaStream_t s, uint32_t max_len_hint) {
 }
 
 uint32_t buckets_for(uint32_t entries) {
-    // mean occupancy 2 of 8 slots: P(bucket full) ~ 1e-3, so a probe rarely chains into a second sector
-    static const int load = [] {  // tuning knob: mean entries per 8-slot bucket
+    // mean occupancy 3 of kBucketCap = 20 slots.  Minimizer buckets fill unevenly -- all reads that start within a few
+    // nucleotides of one another share theirs -- so a probe meets 5-6 entries on average and an overflowing bucket in
+    // about 0.2 % of the cases (scripts/probes/minimizer_locality.py); 4 would triple that.
+    static const int load = [] {  // tuning knob: mean entries per bucket
         const char *e = getenv("ALGA_PS_BUCKET_LOAD");
-        const int v = e ? atoi(e) : 2;
-        return v >= 1 && v <= 6 ? v : 2;
+        const int v = e ? atoi(e) : 3;
+        return v >= 1 && v <= 12 ? v : 3;
     }();
     uint64_t nb = ((uint64_t) entries + load - 1) / load;
     if (nb < 64) nb = 64;
     return (uint32_t) nb;
 }
 
-void size_table(SeedTable &t, uint32_t entries, uint32_t n_reads, int world = 1) {
+void size_table(SeedTable &t, uint32_t entries, int world = 1) {
     t.n_buckets = buckets_for(entries);
     if (world > 1) t.n_buckets = (t.n_buckets + world - 1) / world * world;
     t.slice = t.n_buckets / (world > 1 ? world : 1);
-    uint32_t bits = 1;
-    while (bits < 31 && (1ull << bits) < (uint64_t) n_reads) bits++;
-    t.id_bits = bits;
-    t.id_mask = (uint32_t) ((1ull << bits) - 1ull);
-    t.tag_mask = (uint32_t) ((1ull << (32 - bits)) - 1ull);
     t.min_m = 0;
 }
 
-// Experimental, off unless ALGA_PS_MINIMIZER=<m> is set: buckets chosen by the minimizer of the seed
-// window (its smallest m-mer) instead of by the window, for seed tables far beyond L2.  Needs a seed of at least m + 4.
-uint32_t minimizer_setting(int seed_nt) {
-    static const int m = getenv("ALGA_PS_MINIMIZER") ? atoi(getenv("ALGA_PS_MINIMIZER")) : 0;
-    return (m >= 8 && m <= 28 && seed_nt >= m + 4) ? (uint32_t) m : 0u;
-}
+// m of the minimizer that chooses the bucket of a seed window (common.cuh SeedTable): seed_nt - 12, i.e. 13 m-mers per window
+// (the fast kernels keep exactly that many in registers, tpr_kernels.cu kNM): 20 for the usual 32-nucleotide seed.  Seeds
+// shorter than 16 nucleotides (min_overlap < 16) are their own minimizer -- every window its own bucket, as in a plain hash
+// table -- and are left to the generic kernels (fast_seed()).
+uint32_t minimizer_setting(int seed_nt) { return (uint32_t) (seed_nt >= 16 ? seed_nt - 12 : seed_nt); }
+bool fast_seed(const alga_ps_plan *plan) { return plan->P.seed_nt >= 16; }
 
 // s2 != nullptr: everything that concerns the suffix table goes to s2
 int stage_index_begin(alga_ps_plan *plan, cudaStream_t s, cudaStream_t s2 = nullptr) {
     if (!plan->bound) return fail(ALGA_E_INVALID, "no read set bound to the plan");
-    size_table(plan->Tp, plan->stats.n_prefix, plan->R.n);
-    size_table(plan->Ts, plan->stats.n_suffix, plan->R.n);
+    size_table(plan->Tp, plan->stats.n_prefix);
+    size_table(plan->Ts, plan->stats.n_suffix);
     plan->Tp.min_m = plan->Ts.min_m = minimizer_setting(plan->P.seed_nt);
-    plan->cfg.min_slide = plan->Tp.min_m && getenv("ALGA_PS_MINIMIZER_SLIDE") != nullptr;  // experimental, not validated on a GPU yet
-    const size_t bp = (size_t) plan->Tp.n_buckets * kSlotsPerBucket * 4, bs = (size_t) plan->Ts.n_buckets * kSlotsPerBucket * 4;
+    const size_t bp = (size_t) plan->Tp.n_buckets * kBucketWords * 4, bs = (size_t) plan->Ts.n_buckets * kBucketWords * 4;
     CKR(plan->tp.ensure(bp));
     CKR(plan->ts.ensure(bs));
     plan->Tp.slots = plan->tp.as<uint32_t>();
     plan->Ts.slots = plan->ts.as<uint32_t>();
-    CK(cudaMemsetAsync(plan->tp.p, 0xFF, bp, s));
-    CK(cudaMemsetAsync(plan->ts.p, 0xFF, bs, s2 ? s2 : s));
+    CK(cudaMemsetAsync(plan->tp.p, 0, bp, s));
+    CK(cudaMemsetAsync(plan->ts.p, 0, bs, s2 ? s2 : s));
     return ALGA_OK;
 }
 
@@ -309,7 +305,7 @@ int run_phase1(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const Phase1Out &p1
     CKR(plan->hard1b.ensure((size_t) (n ? n : 1) * 4));
     CK(cudaMemsetAsync(&dc->n_hard1, 0, 4, s));
     CK(cudaMemsetAsync(&dc->n_hard1b, 0, 4, s));
-    const int force = plan->params.flags & ALGA_PS_FORCE_GENERIC;
+    const int force = (plan->params.flags & ALGA_PS_FORCE_GENERIC) || !fast_seed(plan);
     launch_phase1_tpr(plan->R, plan->Tp, plan->P, plan->stats.max_len, lo, hi, nullptr, nullptr, p1,
                       plan->hard1.as<uint32_t>(), &dc->n_hard1, force, s, plan->cfg);
     const uint32_t *q2 = nullptr, *nq2 = nullptr;
@@ -347,9 +343,9 @@ int run_phase2(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const RowsView &row
             launch_phase2(plan->R, plan->Ts, plan->P, lo, hi, rows, list_cap, out, s, plan->cfg);
         else
             launch_phase2_tpr(plan->R, plan->Ts, plan->P, plan->stats.max_len, lo, hi, nullptr, nullptr, rows, out,
-                              plan->params.flags & ALGA_PS_FORCE_GENERIC, s, plan->cfg);
+                              (plan->params.flags & ALGA_PS_FORCE_GENERIC) || !fast_seed(plan), s, plan->cfg);
         const uint32_t *spill_q = plan->spill_queue.as<uint32_t>();
-        const bool second_pass = plan->params.list_cap <= 0 && !(plan->params.flags & ALGA_PS_FORCE_GENERIC);
+        const bool second_pass = false;  // the fast kernel queues every match of a window now: nothing a second fast pass could add
         if (second_pass) {  // what the first pass gave up on, once more with four matches per window
             Phase2Out out2 = out;
             out2.spill_queue = plan->spill_queue2.as<uint32_t>();
@@ -689,8 +685,8 @@ int check_shard(alga_ps_plan *plan, const alga_ps_shard *sh, uint32_t *lo, uint3
         if (!sh->peer_ws[p]) return fail(ALGA_E_INVALID, "null workspace pointer for rank %d", p);
     if (plan->swap_direction) return fail(ALGA_E_INVALID, "rs_min_overlap beyond the longest read is not supported in sharded runs");
     if (sh->table_prefix && sh->table_suffix) {  // the caller's (sliced, exchanged) seed tables are the plan's tables
-        size_table(plan->Tp, sh->n_total, sh->n_total, sh->world);
-        size_table(plan->Ts, sh->n_total, sh->n_total, sh->world);
+        size_table(plan->Tp, sh->n_total, sh->world);
+        size_table(plan->Ts, sh->n_total, sh->world);
         plan->Tp.min_m = plan->Ts.min_m = minimizer_setting(plan->P.seed_nt);
         plan->Tp.slots = (uint32_t *) sh->table_prefix;
         plan->Ts.slots = (uint32_t *) sh->table_suffix;
@@ -707,8 +703,8 @@ uint64_t alga_ps_shard_ws_bytes(uint32_t n_shard, int32_t world) { return shard_
 
 uint64_t alga_ps_shard_table_bytes(uint32_t n_total, int32_t world) {
     SeedTable t{};
-    size_table(t, n_total, n_total, world);
-    return (uint64_t) t.n_buckets * kSlotsPerBucket * 4;
+    size_table(t, n_total, world);
+    return (uint64_t) t.n_buckets * kBucketWords * 4;
 }
 
 int alga_ps_shard_index_range(alga_ps_plan *plan, const alga_ps_shard *sh, uint32_t lo, uint32_t hi, int first, void *stream) {
@@ -718,16 +714,17 @@ int alga_ps_shard_index_range(alga_ps_plan *plan, const alga_ps_shard *sh, uint3
     if (lo > hi || hi > plan->R.n) return fail(ALGA_E_INVALID, "bad range [%u,%u)", lo, hi);
     CKR(use_device(plan));
     cudaStream_t s = (cudaStream_t) stream;
-    size_table(plan->Tp, sh->n_total, sh->n_total, sh->world);
-    size_table(plan->Ts, sh->n_total, sh->n_total, sh->world);
+    size_table(plan->Tp, sh->n_total, sh->world);
+    size_table(plan->Ts, sh->n_total, sh->world);
+    plan->Tp.min_m = plan->Ts.min_m = minimizer_setting(plan->P.seed_nt);
     plan->Tp.slots = (uint32_t *) sh->table_prefix;
     plan->Ts.slots = (uint32_t *) sh->table_suffix;
     const uint32_t slice = plan->Tp.slice, b_lo = (uint32_t) sh->rank * slice, b_hi = b_lo + slice;
     if (first) {
         plan->launches = 0;
-        const size_t off = (size_t) b_lo * kSlotsPerBucket * 4, bytes = (size_t) slice * kSlotsPerBucket * 4;
-        CK(cudaMemsetAsync((char *) sh->table_prefix + off, 0xFF, bytes, s));
-        CK(cudaMemsetAsync((char *) sh->table_suffix + off, 0xFF, bytes, s));
+        const size_t off = (size_t) b_lo * kBucketWords * 4, bytes = (size_t) slice * kBucketWords * 4;
+        CK(cudaMemsetAsync((char *) sh->table_prefix + off, 0, bytes, s));
+        CK(cudaMemsetAsync((char *) sh->table_suffix + off, 0, bytes, s));
     }
     launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, lo, hi, b_lo, b_hi, s, plan->cfg);
     CK(cudaGetLastError());
@@ -1214,8 +1211,8 @@ int alga_gpu_prefix_reads(const alga_reads *reads, int32_t remove_type, int32_t 
     float dev_ms = 0;
     int r = [&]() -> int {
         SeedTable T{};
-        size_table(T, n, n);
-        const size_t tb = (size_t) T.n_buckets * kSlotsPerBucket * 4;
+        size_table(T, n);
+        const size_t tb = (size_t) T.n_buckets * kBucketWords * 4;
         CKR(table.ensure(tb));
         CKR(lenmap.ensure(prefix_reads_lenmap_words() * 4));
         CKR(flags.ensure((size_t) (n ? n : 1) * 4));
@@ -1224,7 +1221,7 @@ int alga_gpu_prefix_reads(const alga_reads *reads, int32_t remove_type, int32_t 
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
         CK(cudaEventRecord(e0, 0));
-        CK(cudaMemsetAsync(table.p, 0xFF, tb, 0));
+        CK(cudaMemsetAsync(table.p, 0, tb, 0));
         launch_prefix_reads(t.R, T, remove_type, lenmap.as<uint32_t>(), flags.as<uint32_t>(), dmask.as<uint8_t>(), 0, cfg);
         CK(cudaGetLastError());
         CK(cudaEventRecord(e1, 0));
@@ -1542,14 +1539,14 @@ int fe_remap(FrontEnd &fe, const ReadsDev &R, const uint8_t *d_mask, uint32_t st
 int fe_prefix_reads(FrontEnd &fe, int remove_type, const LaunchCfg &cfg) {
     const uint32_t n = fe.n;
     SeedTable T{};
-    size_table(T, n, n);
-    const size_t tb = (size_t) T.n_buckets * kSlotsPerBucket * 4;
+    size_table(T, n);
+    const size_t tb = (size_t) T.n_buckets * kBucketWords * 4;
     CKR(fe.table.ensure(tb));
     CKR(fe.lenmap.ensure(prefix_reads_lenmap_words() * 4));
     CKR(fe.flags.ensure((size_t) (n ? n : 1) * 4));
     CKR(fe.mask.ensure(n ? n : 1));
     T.slots = fe.table.as<uint32_t>();
-    CK(cudaMemsetAsync(fe.table.p, 0xFF, tb, 0));
+    CK(cudaMemsetAsync(fe.table.p, 0, tb, 0));
     launch_prefix_reads(fe.raw(), T, remove_type, fe.lenmap.as<uint32_t>(), fe.flags.as<uint32_t>(), fe.mask.as<uint8_t>(), 0, cfg);
     CK(cudaGetLastError());
     uint32_t too_long = 0;

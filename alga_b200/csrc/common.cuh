@@ -5,9 +5,9 @@
 
 namespace alga {
 
-constexpr uint32_t kEmptySlot = 0xFFFFFFFFu;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
-constexpr int kSlotsPerBucket = 8;  // 8 x 4 B = one 32-byte DRAM sector
+constexpr int kBucketWords = 32;  // a bucket of the seed index = 128 bytes = one L2 line
+constexpr int kBucketCap = 20;    // entries per bucket
 constexpr int kSmallEdgesKept = 3;  // SOES, GraphCreatorPrefSuf.h:62
 constexpr int kHeadWords = 4;       // cached head of a read: first 64 nucleotides
 constexpr int kHeadNt = kHeadWords * 16;
@@ -155,20 +155,25 @@ __device__ __forceinline__ const RevEntry *get_row(const RowsView &v, bool csr, 
     return v.rows + (uint64_t) i * v.cap;
 }
 
-// Seed index: open addressing, one 32-byte sector per bucket, 8 entries of (tag << id_bits) | read id.  The tag
-// takes whatever bits the read id leaves free (10 bits for 4 M reads, 5 for 128 M); a false tag hit only costs an
-// exact compare.  Buckets are sized for a mean occupancy of 2 of 8, so a probe almost never leaves its first sector.
+// Seed index.  A bucket is one 128-byte L2 line:
+//     word 0        number of inserts that chose this bucket (beyond kBucketCap: they went on to the next bucket)
+//     word 1        unused
+//     words 2..11   20 tags, 16 bits each (tag_of(); 0 = empty slot)
+//     words 12..31  20 read ids
+// Why a whole line: on B200 a random access that misses L2 costs one REQUEST whatever it carries -- 39 G requests/s for
+// 32-byte sectors and 38 G/s for whole 128-byte lines when the lanes of ONE load instruction cover the line
+// (scripts/probes/random_coop.cu) -- so the unit worth fetching is the line.  Why so many entries: the bucket of a seed
+// window is chosen by the MINIMIZER of the window (its smallest scrambled m-mer), not by the window: equal windows still
+// meet in one bucket, and the windows a read probes at consecutive overlap lengths share theirs (5 distinct buckets for
+// the 29 lengths of phase 2 with m = 20), but all reads that start within a few nucleotides of one another land in the
+// same bucket too -- 5 entries on average where a probe looks, more than 20 in 0.2 % of the probes (then the chain goes on
+// in the next bucket).  The 16-bit tag is taken from the hash of the whole window.
 struct SeedTable {
     uint32_t *slots;
     uint32_t n_buckets;
-    uint32_t slice;     // chains wrap inside slices of this many buckets (= n_buckets unless the build is sharded: rank
-                        // r fills the buckets [r * slice, (r + 1) * slice) and the ranks then exchange slices)
-    uint32_t id_bits;   // bits of a read id, <= 31 (edge arrays carry int32 ids)
-    uint32_t id_mask;   // (1 << id_bits) - 1
-    uint32_t tag_mask;  // (1 << (32 - id_bits)) - 1; the all-ones tag is never used, so no entry equals kEmptySlot
-    uint32_t min_m;     // 0: the bucket is chosen by the hash of the seed window.  m > 0 (experimental): by
-                        // the minimizer of the window -- its smallest scrambled m-mer -- so that the windows a read probes at
-                        // consecutive lengths share buckets; the window hash stays the tag
+    uint32_t slice;  // chains wrap inside slices of this many buckets (= n_buckets unless the build is sharded: rank
+                     // r fills the buckets [r * slice, (r + 1) * slice) and the ranks then exchange slices)
+    uint32_t min_m;  // m of the minimizer; 0: the bucket is chosen by the hash of the key itself (dictionary use, preprocess.cu)
 };
 
 // 32 bits of a packed read starting at bit position `bit`.
@@ -305,40 +310,73 @@ struct SlidingMinimizer {
         return best;
     }
 };
-// bucket of a seed window with hash h
-template <int MINI>  // 0: by the window hash, != 0: by the minimizer of the window
-__device__ __forceinline__ uint32_t bucket_index(const SeedTable &t, uint64_t win, uint64_t h, uint32_t seed_nt) {
-    if (MINI == 0) return bucket_of(h, t.n_buckets);
-    return bucket_of(mix64((uint64_t) window_minimizer(win, seed_nt, t.min_m)), t.n_buckets);
-}
+// bucket of a seed window `win` (seed_nt nucleotides) with hash h
 __device__ __forceinline__ uint32_t bucket_index_rt(const SeedTable &t, uint64_t win, uint64_t h, uint32_t seed_nt) {
-    return t.min_m ? bucket_index<1>(t, win, h, seed_nt) : bucket_of(h, t.n_buckets);
+    if (!t.min_m) return bucket_of(h, t.n_buckets);
+    return bucket_of(mix64((uint64_t) window_minimizer(win, seed_nt, t.min_m)), t.n_buckets);
 }
 // next bucket of a chain (rare path)
 __device__ __forceinline__ uint32_t next_bucket(const SeedTable &t, uint32_t bk) {
     const uint32_t nb = bk + 1;
     return nb % t.slice == 0 ? nb - t.slice : nb;
 }
-// tag already shifted into entry position (the bits of an entry above the read id)
-__device__ __forceinline__ uint32_t tag_of(const SeedTable &t, uint64_t h) {
-    uint32_t tag = (uint32_t) h >> t.id_bits;
-    if (tag == t.tag_mask) tag = 0;
-    return tag << t.id_bits;
+// 16-bit tag of a key with hash h: the bit pattern of a positive NORMAL half-precision number (exponent field 1 .. 30), so
+// that two tags per word can be compared with one HSET2 (__heq2_mask) -- the integer SIMD compares (__vcmpeq2) are emulated
+// with half a dozen instructions on sm_100.  30 720 values; never 0 (0 marks an empty slot).
+__device__ __forceinline__ uint32_t tag_of(uint64_t h) {
+    const uint32_t x = (uint32_t) (h >> 16) & 0xFFFFu;
+    return ((1u + (((x >> 10) * 30u) >> 6)) << 10) | (x & 0x3FFu);
 }
 
-// One 32-byte bucket = one 256-bit load (LDG.E.256 on sm_100a).
-__device__ __forceinline__ void load_bucket(const uint32_t *__restrict__ p, uint32_t (&e)[8]) {
-    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(e[0]), "=r"(e[1]), "=r"(e[2]), "=r"(e[3]), "=r"(e[4]), "=r"(e[5]), "=r"(e[6]), "=r"(e[7])
-                 : "l"(p));
+// Walk the bucket chain that starts at bucket bk and call f(read_id) for every entry whose tag matches.  General form:
+// plain loads, any caller (generic kernels, dictionary of preprocess.cu, chains of the fast kernels).
+template <class F>
+__device__ __forceinline__ void probe_seed_at(const SeedTable &t, uint64_t h, uint32_t bk, F &&f) {
+    const uint32_t tag = tag_of(h);
+    while (true) {
+        const uint32_t *b = t.slots + (uint64_t) bk * kBucketWords;
+        const uint4 q0 = __ldg(reinterpret_cast<const uint4 *>(b));
+        const uint32_t cnt = q0.x, n = cnt < (uint32_t) kBucketCap ? cnt : (uint32_t) kBucketCap;
+        if (n) {
+            const uint4 q1 = __ldg(reinterpret_cast<const uint4 *>(b) + 1), q2 = __ldg(reinterpret_cast<const uint4 *>(b) + 2);
+            const uint32_t tw[10] = {q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+            for (int k = 0; k < 10; k++) {
+                if ((tw[k] & 0xFFFFu) == tag && (uint32_t) (2 * k) < n) f(__ldg(b + 12 + 2 * k));
+                if ((tw[k] >> 16) == tag && (uint32_t) (2 * k + 1) < n) f(__ldg(b + 13 + 2 * k));
+            }
+        }
+        if (cnt <= (uint32_t) kBucketCap) return;
+        bk = next_bucket(t, bk);
+    }
+}
+template <class F>
+__device__ __forceinline__ void probe_seed(const SeedTable &t, uint64_t h, F &&f) {
+    probe_seed_at(t, h, bucket_of(h, t.n_buckets), f);
+}
+// the same for a seed window `win` of seed_nt nucleotides (honours t.min_m)
+template <class F>
+__device__ __forceinline__ void probe_seed_window(const SeedTable &t, uint64_t win, uint32_t seed_nt, F &&f) {
+    const uint64_t h = mix64(win);
+    probe_seed_at(t, h, bucket_index_rt(t, win, h, seed_nt), f);
 }
 
-// The same load for the hot probe loops: not allocated in L1 (a random bucket is never reused there, and filling L1
-// lines with them halves the rate -- measured with cp.async.ca against .cg in phase 2), kept in L2 with priority.
-__device__ __forceinline__ void load_bucket_na(const uint32_t *__restrict__ p, uint32_t (&e)[8], uint64_t policy) {
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-                 : "=r"(e[0]), "=r"(e[1]), "=r"(e[2]), "=r"(e[3]), "=r"(e[4]), "=r"(e[5]), "=r"(e[6]), "=r"(e[7])
-                 : "l"(p), "l"(policy));
+// The table must be zeroed before the first insert.  One atomic (claims a slot) + two stores into the same line.
+__device__ __forceinline__ void insert_seed_at(const SeedTable &t, uint64_t h, uint32_t bk, uint32_t id) {
+    const uint32_t tag = tag_of(h);
+    while (true) {
+        uint32_t *b = t.slots + (uint64_t) bk * kBucketWords;
+        const uint32_t pos = atomicAdd(b, 1u);
+        if (pos < (uint32_t) kBucketCap) {
+            reinterpret_cast<uint16_t *>(b + 2)[pos] = (uint16_t) tag;
+            b[12 + pos] = id;
+            return;
+        }
+        bk = next_bucket(t, bk);
+    }
+}
+__device__ __forceinline__ void insert_seed(const SeedTable &t, uint64_t h, uint32_t id) {
+    insert_seed_at(t, h, bucket_of(h, t.n_buckets), id);
 }
 
 // Eight consecutive words of a packed read from a 32-byte aligned address: ONE request to the memory system.  On B200 a
@@ -352,59 +390,6 @@ __device__ __forceinline__ void load8_na(const uint32_t *__restrict__ p, uint32_
 }
 // words per read slot of the aligned copy the fast kernels work on: a multiple of one sector
 __host__ __device__ __forceinline__ uint32_t aligned_stride_words(uint32_t words) { return (words + 7u) & ~7u; }
-
-// Walk the bucket chain of hash h and call f(read_id) for every entry whose tag matches.
-template <class F>
-__device__ __forceinline__ void probe_seed_at(const SeedTable &t, uint64_t h, uint32_t bk, F &&f);
-template <class F>
-__device__ __forceinline__ void probe_seed(const SeedTable &t, uint64_t h, F &&f) {
-    probe_seed_at(t, h, bucket_of(h, t.n_buckets), f);
-}
-// the same for a seed window `win` of seed_nt nucleotides (honours t.min_m)
-template <class F>
-__device__ __forceinline__ void probe_seed_window(const SeedTable &t, uint64_t win, uint32_t seed_nt, F &&f) {
-    const uint64_t h = mix64(win);
-    probe_seed_at(t, h, bucket_index_rt(t, win, h, seed_nt), f);
-}
-template <class F>
-__device__ __forceinline__ void probe_seed_at(const SeedTable &t, uint64_t h, uint32_t bk, F &&f) {
-    const uint32_t tag = tag_of(t, h);
-    while (true) {
-        uint32_t e[8];
-        load_bucket(t.slots + (uint64_t) bk * kSlotsPerBucket, e);
-#pragma unroll
-        for (int s = 0; s < kSlotsPerBucket; s++) {
-            if (e[s] == kEmptySlot) return;
-            if ((e[s] ^ tag) <= t.id_mask) f(e[s] & t.id_mask);
-        }
-        bk = next_bucket(t, bk);
-    }
-}
-
-__device__ __forceinline__ void insert_seed_at(const SeedTable &t, uint64_t h, uint32_t bk, uint32_t id);
-__device__ __forceinline__ void insert_seed(const SeedTable &t, uint64_t h, uint32_t id) {
-    insert_seed_at(t, h, bucket_of(h, t.n_buckets), id);
-}
-__device__ __forceinline__ void insert_seed_at(const SeedTable &t, uint64_t h, uint32_t bk, uint32_t id) {
-    const uint32_t entry = tag_of(t, h) | id;
-    while (true) {
-        uint32_t *base = t.slots + (uint64_t) bk * kSlotsPerBucket;
-        // one look at the whole bucket (L2), then CAS from its first empty slot on: buckets fill front to back
-        const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(base)), b = __ldcg(reinterpret_cast<const uint4 *>(base) + 1);
-        int s = 8;
-        if (a.x == kEmptySlot) s = 0;
-        else if (a.y == kEmptySlot) s = 1;
-        else if (a.z == kEmptySlot) s = 2;
-        else if (a.w == kEmptySlot) s = 3;
-        else if (b.x == kEmptySlot) s = 4;
-        else if (b.y == kEmptySlot) s = 5;
-        else if (b.z == kEmptySlot) s = 6;
-        else if (b.w == kEmptySlot) s = 7;
-        for (; s < kSlotsPerBucket; s++)
-            if (atomicCAS(base + s, kEmptySlot, entry) == kEmptySlot) return;
-        bk = next_bucket(t, bk);
-    }
-}
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kOwnWords = 32;  // staged part of a read in the fast kernels: 512 nucleotides

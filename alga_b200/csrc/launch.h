@@ -10,8 +10,6 @@ namespace alga {
 struct LaunchCfg {
     int sm_count = 148;
     uint64_t *launches = nullptr;  // incremented once per kernel launch
-    bool min_slide = false;        // experimental, with SeedTable::min_m != 0 only: the fast kernels keep the minimizer of the
-                                   // seed window up to date while it slides (SlidingMinimizer) instead of recomputing it
 };
 
 // --- read-set statistics: max length, eligible prefix/suffix counts ----------------------------
@@ -140,7 +138,7 @@ void launch_verify_pairs(const ReadsDev &R, const int32_t *pairs, uint64_t n_pai
                          uint8_t *verdict, cudaStream_t s, const LaunchCfg &cfg);
 
 // --- ReadPreprocess::getPrefixReads (preprocess.cu): mask[i] = 1 for duplicates / prefix reads (+ reverse complements)
-// t: an empty (all 0xFF) table sized for R.n entries; lenmap: prefix_reads_lenmap_words() words; flags: R.n words.
+// t: an empty (zeroed) table sized for R.n entries; lenmap: prefix_reads_lenmap_words() words; flags: R.n words.
 // lenmap[last] != 0 afterwards: a read is longer than the 65 535 nucleotides the length map covers.
 void launch_prefix_reads(const ReadsDev &R, const SeedTable &t, int remove_type, uint32_t *lenmap, uint32_t *flags,
                          uint8_t *mask, cudaStream_t s, const LaunchCfg &cfg);

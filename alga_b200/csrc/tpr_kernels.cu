@@ -3,34 +3,36 @@
 // One THREAD owns one read, one WARP owns a tile of 32 consecutive reads (no block-level barriers).  The work of a
 // read is split into two loops with very different instruction mixes:
 //
-//   probe    walk the overlap lengths, one 32-byte bucket of the seed index per length.  The K-nucleotide seed
-//            window slides through a 96-bit register window over the read staged in shared memory (two funnel
-//            shifts per length), the hash is four IMADs.  Random buckets must not pass through L1 (filling its
-//            lines with them halves the rate: 2.5 vs 1.4 ms in phase 2) and are the one structure worth keeping in
-//            L2 (evict_last).  Phase 2 fetches them by cp.async.cg (2 x 16 bytes) into a per-thread ring in shared
-//            memory kRing2 lengths ahead of their use, so kRing2 random sectors per thread are in flight without
-//            costing registers; phase 1, whose lanes stop after about a third of their lengths, keeps one bucket in
-//            flight in registers (LDG.E.NA.256).  A bucket is tested with eight XOR + a min tree (an entry with the
-//            right tag XORs to its bare read id, everything else to something larger).  Tag hits (0.3 per length)
-//            are only QUEUED; in phase 2 the first 64 bits of the hit read (all its overhang tail needs) follow by
-//            cp.async as well.
+//   probe    walk the overlap lengths.  The bucket of a K-nucleotide seed window is chosen by the MINIMIZER of the window
+//            (common.cuh SeedTable), so consecutive lengths form RUNS that share one 128-byte bucket: about five runs for
+//            the 29 lengths of phase 2, two or three for the dozen lengths phase 1 looks at.  Per round every lane works
+//            on ONE run: its bucket was fetched kDepth rounds earlier by the whole warp -- eight cp.async instructions,
+//            each covering four buckets with eight consecutive 16-byte lanes, i.e. one request per 128-byte line (a
+//            random access costs one request whatever it carries: scripts/probes/random_coop.cu) -- into a staging area
+//            in shared memory; the lane then tests the 16-bit tags of the bucket against the window hash of every length
+//            of the run (SIMD halfword compares).  All lanes of a warp therefore wait for memory once per RUN, not once
+//            per length: with one bucket per length the warp moved at the pace of "some lane has a load outstanding",
+//            i.e. one DRAM latency per length (ncu at config-4 size: 61 us per tile in phase 1).  Tag hits are only
+//            QUEUED; in phase 2 the first 64 bits of the hit read (all its overhang tail needs) follow by cp.async.
 //   resolve  take the queued hits in order.  Exact 2-bit compares of whole overlaps are thread-local: every lane
-//            verifies its own candidate, words of the candidate straight from L1/L2, words of the own read from
-//            shared memory -- at 3 candidates per read in phase 1 nearly all lanes are busy.
+//            verifies its own candidate -- read slots are sector aligned, a candidate arrives in one or two 32-byte
+//            requests -- against its own read in shared memory.
 //
 // Two passes: the first over all reads allows two tag matches per window; reads that see more (same start position,
 // different sequencing errors) are queued, and a queue of at least kSecondPassMin reads is run again with four
 // matches per window (template parameter MAXM) before the rest goes to the generic kernels.
 //
-// History (profiles/): the first thread-per-read version interleaved probe and resolve per
-// length and verified with warp-cooperative groups; ncu showed it issue-bound at 300-440 warp instructions per
-// (warp, length) with 9 of 32 lanes inside the hit branch (r01d).  Splitting the loops (r01h) halved the
-// instructions and left the kernels latency-bound on the bucket loads (27 % of the stall samples at 20 warps per
-// SM, one bucket in flight per thread); the cp.async ring (r01i) removed that.
+// History (profiles/): r01d interleaved probe and resolve per length (issue-bound); r01h split the
+// loops; r01i fetched one 32-byte bucket per length through a cp.async ring (2.7 ms for config 2, but 148 ms for config 4:
+// ncu showed 158 DRAM sectors per read in phase 2, most of them the same sector fetched again by 4- and 16-byte loads,
+// and one exposed DRAM latency per length in phase 1); r2a cut the requests (sector-aligned read slots, 32-byte loads:
+// 115 ms); this version probes by runs.
 //
 // Reads the fast path cannot take at all (longer than 512 nt, a window with more than four tag matches, offsets above
 // 32, more queued arrivals than fit, a source id that occurs twice for one target, ...) go to the generic kernels of
 // prefsuf_kernels.cu, which replay GraphCreatorPrefSuf.cpp:356-488 literally.
+#include <cuda_fp16.h>
+
 #include <algorithm>
 
 #include "launch.h"
@@ -39,25 +41,28 @@ namespace alga {
 
 namespace {
 
-constexpr int kTpr = 128;     // threads per block = 4 independent warps
-constexpr int kWarps = kTpr / 32;
+constexpr int kTpr = 64;      // threads per block = 2 independent warps (no block-level barriers: small blocks only make the
+constexpr int kWarps = kTpr / 32;  // shared-memory budget of an SM divisible)
 // tuning knobs (scripts/build_variant.sh builds A/B variants with -D...)
 #ifndef ALGA_P1_BLOCKS
-#define ALGA_P1_BLOCKS 5
+#define ALGA_P1_BLOCKS 8
 #endif
 #ifndef ALGA_P2_BLOCKS
-#define ALGA_P2_BLOCKS 4
+#define ALGA_P2_BLOCKS 7
 #endif
 #ifndef ALGA_Q2
-#define ALGA_Q2 20
-#endif
-#ifndef ALGA_RING2
-#define ALGA_RING2 3
+#define ALGA_Q2 16
 #endif
 constexpr int kQ2 = ALGA_Q2;  // arrivals queued per target in phase 2
 constexpr int kSurv = 4;      // surviving arrivals kept in registers per target
 constexpr int kRowFast = 32;  // longest transposed row the fast phase-2 kernel takes
-constexpr int kRing2 = ALGA_RING2;     // buckets in flight per thread in phase 2 (static ring index: the loop is unrolled)
+constexpr int kDepth = 2;     // runs (= buckets) in flight per lane
+constexpr int kStageSlotWords = 3 * 32 * 4;             // one staging slot of a warp: [piece][lane] x 16 bytes = the count and the
+                                                        // tags (first 48 bytes) of 32 buckets; ids are read where a tag matches
+constexpr int kStageWords = kDepth * kStageSlotWords;   // per warp
+constexpr int kNM = 13;        // m-mers per seed window: the index is built with m = seed_nt - 12 (api.cu minimizer_setting)
+constexpr int kMaxRuns = 16;   // runs per read the fast kernels keep (reads with more go to the generic kernels)
+constexpr int kRunWords = kMaxRuns * 32 + kMaxRuns * 8;  // per warp: bucket [kMaxRuns][32] (u32) + first length index [kMaxRuns][32] (u8)
 
 inline int warp_tile_grid(uint64_t n_items, const LaunchCfg &cfg, int blocks_per_sm) {
     uint64_t need = (n_items + kTpr - 1) / kTpr;
@@ -84,35 +89,114 @@ __device__ __forceinline__ void cp_async8(uint64_t *smem_dst, const uint32_t *gm
     const uint32_t d = (uint32_t) __cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(uint32_t *smem_dst, const uint32_t *gmem_src, uint64_t pol) {
+    const uint32_t d = (uint32_t) __cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// ---- bucket evaluation ----------------------------------------------------------------------------------------
-// An entry with the probed tag XORs to its bare read id (<= id_mask), any other entry to something larger: the
-// minimum over the bucket is the smallest matching id, if there is one.
-__device__ __forceinline__ uint32_t bucket_min(const uint32_t (&e)[8], uint32_t tag) {
-    uint32_t m = e[0] ^ tag;
-#pragma unroll
-    for (int s = 1; s < kSlotsPerBucket; s++) m = min(m, e[s] ^ tag);
-    return m;
+// ---- runs of overlap lengths that share a bucket --------------------------------------------------------------
+// seed window of the own read (shared memory) for overlap length L.  UP (phase 1): the window starts at len - L, it moves
+// up the read as L falls; else (phase 2): it ends at L, it moves down.
+template <bool UP>
+__device__ __forceinline__ uint64_t seed_window(const uint32_t *own, const PsDev &P, uint32_t len, int32_t L) {
+    const uint32_t p = UP ? 2u * (len - (uint32_t) L) : 2u * (uint32_t) (L - P.seed_nt);
+    return sbits64(own, p) & P.seed_mask;
 }
 
-// ids of the entries of one bucket whose tag matches (the first kMaxMatch) and how many there are; true if the bucket
-// is full
-// (MAXM = reads that share a K-nucleotide seed and overlap at one length, i.e. start at the same position: 2 in the
-// first pass over all reads, 4 in the second pass over the reads the first one gave up on)
-template <int MAXM>
-__device__ __forceinline__ bool eval_bucket(const SeedTable &t, const uint32_t (&e)[8], uint32_t tag, uint32_t (&c)[MAXM],
-                                            int &n) {
+// The walk over the overlap lengths l_hi, l_hi - 1, ... l_lo of one read, cut into runs of lengths whose seed windows have
+// the same minimizer (= the same bucket): run k starts at length l_hi - first[k] and uses bucket bk[k].  All lanes step
+// through their lengths together: the kNM scrambled m-mers of the current window sit in registers (slot = position mod
+// kNM, static because the loop is unrolled by kNM), a step replaces one of them and takes the minimum of all -- no
+// data-dependent rescan, so no lane waits for another one's.  Returns the number of runs (may exceed kMaxRuns: the
+// caller gives the read up); the table of the warp is indexed [k * 32 + lane].
+template <bool UP>
+__device__ __forceinline__ int find_runs(const uint32_t *own, const PsDev &P, const SeedTable &T, uint32_t len, int32_t l_hi,
+                                         int32_t l_lo, bool on, uint32_t *run_bk, uint8_t *run_first, int lane) {
+    const int n_len = on ? l_hi - l_lo + 1 : 0;
+    const int n_max = warp_max(n_len);
+    const uint32_t m = T.min_m;
+    const int32_t s0 = UP ? (int32_t) len - l_hi : l_hi - P.seed_nt;  // first nucleotide of the window of length l_hi
+    auto mmer = [&](int32_t pos) { return scrambled_mmer(sbits64(own, 2u * (uint32_t) pos), 0, m); };
+    uint32_t H[kNM];
+    // slot j: UP -- position s0 + j (the window moves up: at step t position s0 + t - 1 leaves, it sits in slot (t - 1) % kNM);
+    //         else -- position s0 + kNM - 1 - j (the window moves down: position s0 - t + kNM leaves, slot (t - 1) % kNM)
 #pragma unroll
-    for (int s = 0; s < kSlotsPerBucket; s++) {
-        if ((e[s] ^ tag) <= t.id_mask) {
+    for (int j = 0; j < kNM; j++) H[j] = on ? mmer(UP ? s0 + j : s0 + kNM - 1 - j) : 0u;
+    auto ring_min = [&]() {
+        uint32_t v = H[0];
 #pragma unroll
-            for (int k = 0; k < MAXM; k++)
-                if (k == n) c[k] = e[s] & t.id_mask;
-            n++;
+        for (int j = 1; j < kNM; j++) v = min(v, H[j]);
+        return v;
+    };
+    uint32_t prev = ring_min();
+    int n_runs = 0;
+    if (on) {
+        run_bk[lane] = bucket_of(mix64((uint64_t) prev), T.n_buckets);
+        run_first[lane] = 0;
+        n_runs = 1;
+    }
+    for (int tb = 0; tb * kNM + 1 < n_max; tb++) {
+#pragma unroll
+        for (int j = 0; j < kNM; j++) {
+            const int t = tb * kNM + j + 1;
+            if (t < n_max) {  // the same for all lanes
+                const bool act = t < n_len;
+                if (act) H[j] = mmer(UP ? s0 + t + kNM - 1 : s0 - t);
+                const uint32_t v = ring_min();
+                if (act && v != prev) {
+                    prev = v;
+                    if (n_runs < kMaxRuns) {
+                        run_bk[n_runs * 32 + lane] = bucket_of(mix64((uint64_t) v), T.n_buckets);
+                        run_first[n_runs * 32 + lane] = (uint8_t) t;
+                    }
+                    n_runs++;
+                }
+            }
         }
     }
-    return e[kSlotsPerBucket - 1] != kEmptySlot;  // buckets fill front to back: a full one chains on
+    return n_runs;
+}
+
+// Warp-collective fetch: every lane with `need` gets the first 48 bytes (count + tags) of its 128-byte bucket `bk` into its
+// place of the staging slot.  Four instructions; in each, three consecutive lanes cover the 3 x 16 bytes of one bucket: one
+// request per bucket.
+__device__ __forceinline__ void fetch_buckets(const SeedTable &T, uint32_t *slot, bool need, uint32_t bk, int lane, uint64_t pol) {
+    const unsigned needm = __ballot_sync(kFull, need);
+    if (needm) {
+        const int grp = lane / 3, piece = lane - 3 * grp;  // lanes 30, 31 idle
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int owner = 10 * i + grp;
+            const uint32_t obk = __shfl_sync(kFull, bk, owner & 31);
+            if (grp < 10 && owner < 32 && ((needm >> owner) & 1u))
+                cp_async16(slot + ((piece * 32 + owner) << 2), T.slots + (uint64_t) obk * kBucketWords + piece * 4, pol);
+        }
+    }
+    cp_async_commit();
+}
+// this lane's piece p (16 bytes) of a staged bucket
+__device__ __forceinline__ uint4 staged_piece(const uint32_t *slot, int p, int lane) {
+    return *reinterpret_cast<const uint4 *>(slot + ((p * 32 + lane) << 2));
+}
+// id of entry i of bucket bk (the line was fetched a moment ago: an L2 hit)
+__device__ __forceinline__ uint32_t entry_id(const SeedTable &T, uint32_t bk, int i) {
+    return __ldg(T.slots + (uint64_t) bk * kBucketWords + 12 + i);
+}
+struct BucketTags {
+    uint32_t cnt;     // inserts that chose the bucket (> kBucketCap: the chain goes on in the next bucket)
+    uint32_t tw[10];  // two 16-bit tags per word
+};
+__device__ __forceinline__ void load_tags(const uint32_t *slot, int lane, BucketTags &b) {
+    const uint4 q0 = staged_piece(slot, 0, lane), q1 = staged_piece(slot, 1, lane), q2 = staged_piece(slot, 2, lane);
+    b.cnt = q0.x;
+    b.tw[0] = q0.z, b.tw[1] = q0.w, b.tw[2] = q1.x, b.tw[3] = q1.y, b.tw[4] = q1.z, b.tw[5] = q1.w;
+    b.tw[6] = q2.x, b.tw[7] = q2.y, b.tw[8] = q2.z, b.tw[9] = q2.w;
 }
 
 __device__ __forceinline__ void order_desc(uint32_t &a, uint32_t &b) {
@@ -120,30 +204,40 @@ __device__ __forceinline__ void order_desc(uint32_t &a, uint32_t &b) {
     a = hi, b = lo;
 }
 
-// Matches of a probe whose first bucket is in e[] and holds at least one match or is full, largest id first (the order
-// of arrival inside one overlap length, seen backwards).  The common case -- one match, bucket not full -- is answered
-// by the minimum alone; otherwise collect the matches and walk the chain.  n > MAXM: the caller gives up.
-template <int MAXM>
-__device__ __forceinline__ void probe_matches(const SeedTable &t, uint32_t (&e)[8], uint32_t tag, uint32_t bk, uint32_t m,
-                                              uint32_t (&c)[MAXM], int &n) {
-    int cnt = 0;
+// Entries of the staged bucket whose tag equals that of a window with hash h: bit k = entry 2 k, bit 16 + k = entry 2 k + 1.
+__device__ __forceinline__ uint32_t match_mask(const BucketTags &b, uint64_t h) {
+    const uint32_t tt = tag_of(h) * 0x10001u;
+    const __half2 t2 = *reinterpret_cast<const __half2 *>(&tt);
+    uint32_t acc = 0;
 #pragma unroll
-    for (int s = 0; s < kSlotsPerBucket; s++) cnt += ((e[s] ^ tag) <= t.id_mask) ? 1 : 0;
-    const bool full = e[kSlotsPerBucket - 1] != kEmptySlot;
+    for (int k = 0; k < 10; k++) {
+        const uint32_t w = b.tw[k];
+        acc += (__heq2_mask(*reinterpret_cast<const __half2 *>(&w), t2) & 0x00010001u) << k;  // distinct bits: + is |
+    }
+    return acc;
+}
+// The reads behind a match mask -- and behind the chain of the bucket, if it overflowed -- : ids in c[0 .. min(n, MAXM)),
+// largest first (the order of arrival inside one overlap length, seen backwards).  n > MAXM: the caller gives up.
+// (MAXM = reads that share a K-nucleotide seed and overlap at one length, i.e. start at the same position: 2 in the first
+// pass over all reads, 4 in the second pass over the reads the first one gave up on.)
+template <int MAXM>
+__device__ __forceinline__ void collect_matches(const SeedTable &T, const BucketTags &b, uint32_t bk, uint64_t h, uint32_t mask,
+                                                uint32_t (&c)[MAXM], int &n) {
+    n = 0;
 #pragma unroll
     for (int k = 0; k < MAXM; k++) c[k] = 0u;
-    if (cnt == 1 && !full) {
-        n = 1;
-        c[0] = m;
-        return;
+    auto add = [&](uint32_t id) {
+#pragma unroll
+        for (int k = 0; k < MAXM; k++)
+            if (k == n) c[k] = id;
+        n++;
+    };
+    while (mask) {
+        const int bit = __ffs(mask) - 1;
+        mask &= mask - 1;
+        add(entry_id(T, bk, ((bit & 15) << 1) | (bit >> 4)));
     }
-    n = 0;
-    bool more = eval_bucket<MAXM>(t, e, tag, c, n);
-    while (more) {
-        bk = next_bucket(t, bk);
-        load_bucket(t.slots + (uint64_t) bk * kSlotsPerBucket, e);
-        more = eval_bucket<MAXM>(t, e, tag, c, n);
-    }
+    if (b.cnt > (uint32_t) kBucketCap) probe_seed_at(T, h, next_bucket(T, bk), add);  // rare: plain loads
     if (n > 1 && n <= MAXM) {  // unused slots hold 0 and sink to the end (n says how many are real)
         if (MAXM == 2) {
             order_desc(c[0], c[1]);
@@ -156,11 +250,6 @@ __device__ __forceinline__ void probe_matches(const SeedTable &t, uint32_t (&e)[
             order_desc(c[1], c[MAXM - 2]);
         }
     }
-}
-
-// 64 bits of the staged read starting `s` bits into the register window (w0, w1, w2)
-__device__ __forceinline__ uint64_t window_key(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t s) {
-    return (uint64_t) __funnelshift_r(w0, w1, s) | ((uint64_t) __funnelshift_r(w1, w2, s) << 32);
 }
 
 // Stage the (up to 32) reads of a warp's tile: `sw` words each at stride `wp`, the rest of the stride zeroed.
@@ -216,31 +305,6 @@ __device__ __forceinline__ void stage_warp(const ReadsDev &R, uint32_t *wown, in
         for (int w = 0; w < wp; w++) own[w] = (uint32_t) w < my_words ? __ldg(p + w) : 0u;
     }
     __syncwarp();
-}
-
-// prefix(cand, L) == own[o .. o + L) ?   (phase 1: suffix of the own read against the prefix of the candidate)
-__device__ __forceinline__ bool verify_own_suffix(const ReadsDev &R, const uint32_t *own, uint32_t cand, uint32_t o,
-                                                  int32_t L) {
-    const uint32_t *pc = read_ptr(R, cand);
-    const uint32_t nbits = 2u * (uint32_t) L, nw = (nbits + 31u) >> 5, sh = (2u * o) & 31u;
-    const uint32_t *ow = own + ((2u * o) >> 5);
-    for (uint32_t k0 = 0; k0 < nw; k0 += 4) {
-        uint32_t g[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) g[j] = k0 + j < nw ? __ldg(pc + k0 + j) : 0u;
-        uint32_t diff = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t k = k0 + j;
-            if (k < nw) {
-                uint32_t x = __funnelshift_r(ow[k], ow[k + 1], sh) ^ g[j];
-                if (k == nw - 1 && (nbits & 31u)) x &= (1u << (nbits & 31u)) - 1u;
-                diff |= x;
-            }
-        }
-        if (diff) return false;
-    }
-    return true;
 }
 
 // cand[o .. o + L) == own[0 .. L) ?   (phase 2: suffix of the candidate against the prefix of the own read)
@@ -308,19 +372,24 @@ __device__ __forceinline__ bool verify_own_prefix_aligned(const ReadsDev &R, con
 // Phase 1 (GraphCreatorPrefSuf.cpp:397-402 in closed form): source read b walks L from min(rs-1, len) downwards
 // and keeps the first 3 confirmed (L, c) -- within one L the larger c first -- = "the last 3 pushes".
 //
-// Lanes pause once they hold 3 candidates, so their positions in the walk differ; with so few lengths per read
-// (about 11 of the 34 possible) a deep prefetch ring mostly fetches buckets nobody tests, so this kernel keeps ONE
-// bucket in flight per lane, in registers.  Shared memory per warp: own reads [32][wp].
+// A lane stops walking once it holds 3 candidates (confirmed + pending) -- in the middle of a run if need be, the run
+// then stays in its staging slot -- and goes on only if the exact compares reject some of them.  The lanes of a warp
+// therefore stand at different runs; `head` says which of its two staging slots holds the older run of a lane.
+// Shared memory per warp: own reads [32][wp] | staging [kDepth][8][32] x 16 B | run table.
 // id_list != nullptr: second pass -- the reads are id_list[0 .. *n_list) instead of [lo, hi)
-template <bool FAST, int MAXM, int MINI>  // MINI: 0 window-hash buckets, 1 minimizer buckets, 2 ... with a sliding minimum
+template <bool FAST, int MAXM>
 __global__ void __launch_bounds__(kTpr, ALGA_P1_BLOCKS)
 phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, const uint32_t *__restrict__ id_list,
                   const uint32_t *__restrict__ n_list, int wp, Phase1Out out, uint32_t *__restrict__ hard_queue,
                   uint32_t *n_hard, int force_hard) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int own_words = ((kWarps * 32 * wp + 3) & ~3);
     uint32_t *wown = smem + wib * 32 * wp;
     const uint32_t *own = wown + lane * wp;
+    uint32_t *stage = smem + own_words + wib * kStageWords;
+    uint32_t *run_bk = smem + own_words + kWarps * kStageWords + wib * kRunWords;
+    uint8_t *run_first = reinterpret_cast<uint8_t *>(run_bk + kMaxRuns * 32);
     const bool listed = id_list != nullptr;
     const uint64_t n_items = listed ? (uint64_t) *n_list : (uint64_t) (hi - lo);
     if (listed && n_items < kSecondPassMin) return;  // a short queue is cheaper in the generic kernel (one tile = 40 us)
@@ -355,85 +424,63 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
 #pragma unroll
         for (int k = 0; k < kPend; k++) pc[k] = 0, pl[k] = 0;
 
-        // probe state: the bucket of length `Lc` is in flight in e[]
-        int32_t Lc = l_hi;
-        bool more = active;
-        uint32_t e[8], tag = 0, bk = 0, w0 = 0, w1 = 0, w2 = 0, sh = 0;
-        int wb = 0;
-        SlidingMinimizer smin;  // MINI == 2 only: the window moves up by one nucleotide per length
-        smin.best = 0, smin.pos = 0;
-        if (more) {
-            const uint32_t p = 2u * (lenb - (uint32_t) Lc);
-            wb = (int) (p >> 5);
-            sh = p & 31u;
-            w0 = own[wb], w1 = own[wb + 1], w2 = own[wb + 2];
-            const uint64_t win = window_key(w0, w1, w2, sh) & P.seed_mask, h = mix64(win);
-            tag = tag_of(T, h);
-            if (MINI == 2) {
-                smin.reset(win, (uint32_t) P.seed_nt, T.min_m);
-                bk = bucket_of(mix64((uint64_t) smin.best), T.n_buckets);
-            } else {
-                bk = bucket_index<MINI>(T, win, h, (uint32_t) P.seed_nt);
-            }
-            load_bucket_na(T.slots + (uint64_t) bk * kSlotsPerBucket, e, pol);
+        // the walk of every lane, cut into runs (shared-memory table of the warp)
+        int n_runs = find_runs<true>(own, P, T, lenb, l_hi, P.lmin, active, run_bk, run_first, lane);
+        if (n_runs > kMaxRuns || (active && l_hi - P.lmin > 255)) {
+            hard = true;
+            n_runs = 0;
         }
+        __syncwarp();
+        // run k lives in staging slot k & 1.  kc: the run this lane consumes next (from length Lc on), kf: the run it fetches
+        // next; kc <= kf <= kc + 2.  Round j (the same for all lanes) serves the runs of parity j.
+        int kc = 0, kf = 0;
+        int32_t Lc = l_hi;
+        int j = 0;
         while (true) {
-            // ---- probe until every lane has 3 candidates (confirmed + pending) or ran out of lengths
+            // ---- probe, at most one run per lane and round, until every lane has 3 candidates (confirmed + pending) or ran out
             while (true) {
-                const bool need = more && !hard && conf + np < kSmallEdgesKept;
+                const bool need = active && !hard && conf + np < kSmallEdgesKept && kc < n_runs;
                 if (!__any_sync(kFull, need)) break;
-                if (need) {
-                    const uint32_t m = bucket_min(e, tag);
-                    uint32_t cm[MAXM];
-                    int n = 0;
-                    const bool e7_walked = MINI == 2 && e[7] != kEmptySlot;  // a full bucket: probe_matches may load its chain into e[]
-                    if (m <= T.id_mask || e[7] != kEmptySlot) probe_matches<MAXM>(T, e, tag, bk, m, cm, n);
-                    const int32_t L = Lc;
-                    Lc--;
-                    if (Lc >= P.lmin) {  // slide the window by one nucleotide, next bucket goes in flight
-                        sh += 2u;
-                        if (sh == 32u) {
-                            sh = 0u;
-                            wb++;
-                            w0 = w1, w1 = w2, w2 = own[wb + 2];
-                        }
-                        const uint64_t win = window_key(w0, w1, w2, sh) & P.seed_mask, h = mix64(win);
-                        tag = tag_of(T, h);
-                        if (MINI == 2) {
-                            const uint32_t bk_new = bucket_of(mix64((uint64_t) smin.slide_up(win, (uint32_t) P.seed_nt, T.min_m)), T.n_buckets);
-                            // the same bucket as for the previous length (the usual case) is still in e[]: nothing to fetch,
-                            // unless probe_matches walked its chain and left another bucket there
-                            if (bk_new != bk || e7_walked) {
-                                bk = bk_new;
-                                load_bucket_na(T.slots + (uint64_t) bk * kSlotsPerBucket, e, pol);
-                            }
-                        } else {
-                            bk = bucket_index<MINI>(T, win, h, (uint32_t) P.seed_nt);
-                            load_bucket_na(T.slots + (uint64_t) bk * kSlotsPerBucket, e, pol);
-                        }
-                    } else {
-                        more = false;
-                    }
-                    if (n > MAXM) {
-                        hard = true;
-                    } else if (n) {  // within one length the larger target id is the later push: cm[] is descending
+                cp_async_wait_group<kDepth - 1>();  // every fetch but the latest has landed (this lane's part of it)
+                __syncwarp();                       // ... and everybody else's
+                uint32_t *slot = stage + j * kStageSlotWords;
+                if (need && (kc & 1) == j && kf > kc) {
+                    BucketTags bt;
+                    load_tags(slot, lane, bt);
+                    const uint32_t bk = run_bk[kc * 32 + lane];
+                    const int32_t l_last = kc + 1 < n_runs ? l_hi - (int32_t) run_first[(kc + 1) * 32 + lane] + 1 : P.lmin;
+                    int32_t L = Lc;
+                    for (; L >= l_last && conf + np < kSmallEdgesKept && !hard; L--) {
+                        const uint64_t h = mix64(seed_window<true>(own, P, lenb, L));
+                        const uint32_t mask = match_mask(bt, h);
+                        if (mask || bt.cnt > (uint32_t) kBucketCap) {
+                            uint32_t cm[MAXM];
+                            int n = 0;
+                            collect_matches<MAXM>(T, bt, bk, h, mask, cm, n);
+                            if (n > MAXM) {
+                                hard = true;
+                            } else {  // within one length the larger target id is the later push: cm[] is descending
 #pragma unroll
-                        for (int k = 0; k < kPend; k++)
-                            if (k == np) pc[k] = cm[0], pl[k] = L;
-                        np++;
-                        if (n > 1) {  // several reads start with this seed (rare without sequencing errors)
+                                for (int q = 0; q < MAXM; q++) {
+                                    if (q < n) {
 #pragma unroll
-                            for (int j = 1; j < MAXM; j++) {
-                                if (j < n) {
-#pragma unroll
-                                    for (int k = 0; k < kPend; k++)
-                                        if (k == np) pc[k] = cm[j], pl[k] = L;
-                                    np++;
+                                        for (int k = 0; k < kPend; k++)
+                                            if (k == np) pc[k] = cm[q], pl[k] = L;
+                                        np++;
+                                    }
                                 }
                             }
                         }
                     }
+                    Lc = L;  // enough candidates for now: the rest of the run waits in its slot
+                    if (L < l_last) kc++;  // the run is used up
                 }
+                __syncwarp();  // nobody reads this slot any more
+                // fetch ahead: the next run of parity j, if its slot is free and the lane still looks for candidates
+                const bool fetch = active && !hard && kf < n_runs && (kf & 1) == j && kf < kc + 2 && conf + np < kSmallEdgesKept;
+                fetch_buckets(T, slot, fetch, fetch ? run_bk[kf * 32 + lane] : 0u, lane, pol);
+                if (fetch) kf++;
+                j ^= 1;
             }
             // ---- confirm the pending candidates, every lane its own, kBatch at a time: the words of a whole batch are
             // requested before the first compare, so their (random, mostly DRAM) latencies overlap
@@ -503,6 +550,8 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
             }
             np = 0;
         }
+
+        cp_async_wait_all();  // buckets fetched ahead and never used must have landed before the next tile reuses the slots
 
         // ---- emit
         if (out.mode == 0) {
@@ -587,12 +636,10 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
 // test is dropped without ever comparing its overlap.  Entries of the transposed phase-1 graph (rows) are tested
 // against the survivors at the end.
 //
-// Shared memory per warp: own reads [32][wp] | queue: ids [kQ2][32], heads [kQ2][32] (u64), lengths [kQ2][32] (u16).
-// The buckets of the next kRing2 lengths are in flight in REGISTERS, one 32-byte request each (LDG.E.256): two 16-byte
-// cp.async of one sector are two requests, and L2 fetches a sector that is still on its way from DRAM once per request
-// (scripts/probes/random_requests.cu: 19.8 vs 39.4 G buckets/s).
+// Shared memory per warp: own reads [32][wp] | staging [kDepth][8][32] x 16 B | queue: ids [kQ2][32], heads [kQ2][32]
+// (u64), lengths [kQ2][32] (u16).  Every lane walks all its runs, run k of every lane sits in staging slot k & 1.
 // id_list != nullptr: second pass -- the targets are id_list[0 .. *n_list) instead of [lo, hi)
-template <bool FAST, int MAXM, int MINI>  // MINI: 0 window-hash buckets, 1 minimizer buckets, 2 ... with a sliding minimum
+template <bool FAST, int MAXM>
 __global__ void __launch_bounds__(kTpr, ALGA_P2_BLOCKS)
 phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, const uint32_t *__restrict__ id_list,
                   const uint32_t *__restrict__ n_list, int wp, RowsView rows, Phase2Out out, int force_hard) {
@@ -602,7 +649,11 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
     constexpr int kQueueWords = kQ2 * 32 * 3 + kQ2 * 32 / 2;
     uint32_t *wown = smem + wib * 32 * wp;
     const uint32_t *own = wown + lane * wp;
-    uint32_t *q_id = smem + own_words + wib * kQueueWords + lane;                                // q_id[k * 32]
+    uint32_t *stage = smem + own_words + wib * kStageWords;
+    uint32_t *run_bk = smem + own_words + kWarps * kStageWords + wib * kRunWords;
+    uint8_t *run_first = reinterpret_cast<uint8_t *>(run_bk + kMaxRuns * 32);
+    uint32_t *ctl = smem + own_words + kWarps * (kStageWords + kRunWords) + wib * 64;  // queue lengths [32] | overflow flags [32]
+    uint32_t *q_id = smem + own_words + kWarps * (kStageWords + kRunWords + 64) + wib * kQueueWords + lane;  // q_id[k * 32]
     uint64_t *q_t = reinterpret_cast<uint64_t *>(q_id - lane + kQ2 * 32) + lane;                 // q_t[k * 32]: first 64 bits of the hit read
     uint16_t *q_l = reinterpret_cast<uint16_t *>(q_id - lane + kQ2 * 32 * 3) + lane;             // q_l[k * 32]
     const uint64_t pol = l2_evict_last_policy();
@@ -635,90 +686,118 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
             stage_warp<FAST>(R, wown, wp, wp - 2, first, n_valid, nw, lane, listed, c);
         }
 
-        // ---- probe: queue every tag hit (b, L); FAST: the first 64 bits of b follow by cp.async
+        // ---- probe: queue every tag hit (b, L); FAST: the first 64 bits of b follow by cp.async.
+        // The lengths of run k of all 32 reads of the tile form one flat list of (read, length) items that the lanes of
+        // the warp share out among themselves -- a lane works on whatever item comes next, not on "its" read (the reads
+        // and the staged buckets sit in shared memory, any lane reaches them) -- so every lane is busy in every step
+        // although the runs of the reads differ in length (one read per lane kept 11 of 32 lanes busy: ncu, r2c).
         int qn = 0;
         const bool walk = active && !hard;
-        const int n_iter = warp_max(walk ? l_hi - l_lo + 1 : 0);
-        uint32_t er[kRing2][8], tagr[kRing2], bkr[kRing2], w0 = 0, w1 = 0, w2 = 0, sh = 0;
-        int wb = 0;
-        int32_t Lp = l_hi;  // next length to prefetch; (w0, w1, w2, sh, wb) = register window at Lp
-        SlidingMinimizer smin;  // MINI == 2 only
-        smin.best = 0, smin.pos = 0;
-        bool smin_on = false;
-        if (walk) {
-            const uint32_t p = 2u * (uint32_t) (l_hi - P.seed_nt);
-            wb = (int) (p >> 5);
-            sh = p & 31u;
-            w0 = own[wb], w1 = own[wb + 1], w2 = own[wb + 2];
+        int n_runs = find_runs<false>(own, P, T, lenc, l_hi, l_lo, walk, run_bk, run_first, lane);
+        if (n_runs > kMaxRuns || (walk && l_hi - l_lo > 255)) {
+            hard = true;
+            n_runs = 0;
         }
-#pragma unroll
-        for (int j = 0; j < kRing2; j++) {
-            tagr[j] = 0, bkr[j] = 0;
-#pragma unroll
-            for (int q = 0; q < 8; q++) er[j][q] = kEmptySlot;
-        }
-        auto prefetch = [&](uint32_t (&e_out)[8], uint32_t &tag_out, uint32_t &bk_out) {
-            if (walk && Lp >= l_lo) {
-                const uint64_t win = window_key(w0, w1, w2, sh) & P.seed_mask, h = mix64(win);
-                tag_out = tag_of(T, h);
-                if (MINI == 2) {  // the window moves down by one nucleotide per call
-                    if (smin_on) smin.slide_down(win, (uint32_t) P.seed_nt, T.min_m);
-                    else smin.reset(win, (uint32_t) P.seed_nt, T.min_m);
-                    smin_on = true;
-                    bk_out = bucket_of(mix64((uint64_t) smin.best), T.n_buckets);
-                } else {
-                    bk_out = bucket_index<MINI>(T, win, h, (uint32_t) P.seed_nt);
-                }
-                load_bucket_na(T.slots + (uint64_t) bk_out * kSlotsPerBucket, e_out, pol);
-                Lp--;
-                if (sh == 0u) {  // slide the window down by one nucleotide
-                    sh = 32u;
-                    wb--;
-                    w2 = w1, w1 = w0, w0 = wb >= 0 ? own[wb] : 0u;
-                }
-                sh -= 2u;
+        ctl[lane] = 0u;       // arrivals queued for the read of this lane (by any lane)
+        ctl[32 + lane] = 0u;  // ... more than the queue holds
+        __syncwarp();
+        const bool on = walk && !hard;
+        uint32_t *q_id0 = q_id - lane;
+        uint64_t *q_t0 = q_t - lane;
+        uint16_t *q_l0 = q_l - lane;
+        // run k lives in staging slot k & 1; round t fetches run t and works through run t - 2 of every read
+        for (int t = 0;; t++) {
+            const int j = t & 1, kc = t - 2;
+            if (!__any_sync(kFull, on && kc < n_runs)) break;
+            cp_async_wait_group<kDepth - 1>();  // every fetch but the latest has landed (this lane's part of it)
+            __syncwarp();                       // ... and everybody else's
+            uint32_t *slot = stage + j * kStageSlotWords;
+            int n_mine = 0;        // lengths of run kc of the read of this lane
+            int32_t lf_mine = 0;   // ... the first (longest) of them
+            if (on && kc >= 0 && kc < n_runs) {
+                const int f0 = run_first[kc * 32 + lane];
+                const int f1 = kc + 1 < n_runs ? (int) run_first[(kc + 1) * 32 + lane] : l_hi - l_lo + 1;
+                n_mine = f1 - f0;
+                lf_mine = l_hi - f0;
             }
-        };
-#pragma unroll
-        for (int j = 0; j < kRing2; j++) prefetch(er[j], tagr[j], bkr[j]);
-
-        for (int it0 = 0; it0 < n_iter; it0 += kRing2) {
-#pragma unroll
-            for (int j = 0; j < kRing2; j++) {
-                const int32_t L = l_hi - (it0 + j);
-                if (walk && L >= l_lo) {
-                    uint32_t e[8];
-#pragma unroll
-                    for (int q = 0; q < 8; q++) e[q] = er[j][q];
-                    const uint32_t tag = tagr[j], bk = bkr[j];
-                    const uint32_t m = bucket_min(e, tag);
-                    uint32_t bm[MAXM];
-                    int n = 0;
-                    if (!hard && (m <= T.id_mask || e[7] != kEmptySlot)) probe_matches<MAXM>(T, e, tag, bk, m, bm, n);
-                    prefetch(er[j], tagr[j], bkr[j]);
-                    if (n > MAXM) {
-                        hard = true;
-                    } else if (n) {  // walking backwards: within one length the larger source id arrived later: bm[] is descending
-                        for (int k = 0; k < n; k++) {  // n == 1 unless several reads end with this seed
-                            uint32_t cand = bm[0];
-#pragma unroll
-                            for (int t = 1; t < MAXM; t++)
-                                if (t == k) cand = bm[t];
-                            if (cand == c) continue;
-                            if (qn >= kQ2) {
-                                hard = true;
-                                break;
-                            }
-                            q_id[qn * 32] = cand;
-                            q_l[qn * 32] = (uint16_t) L;
-                            if (FAST) cp_async8(q_t + qn * 32, R.words + (uint64_t) cand * R.stride);  // one request
-                            qn++;
+            int incl = n_mine;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(kFull, incl, d);
+                if (lane >= d) incl += y;
+            }
+            const int total = __shfl_sync(kFull, incl, 31), off_mine = incl - n_mine;
+            // the reads that take part in this round, in lane order: lane i holds the lane of the i-th of them
+            const unsigned activem = __ballot_sync(kFull, n_mine > 0);
+            const int nth = (int) __fns(activem, 0, lane + 1);
+            for (int base = 0; base < total; base += 32) {
+                const int item = base + lane;
+                // the read of this item = the last participating read whose first item is not beyond it: reads that start
+                // inside this window of 32 items mark their place, the others are counted
+                const bool inwin = n_mine > 0 && off_mine >= base && off_mine < base + 32;
+                const unsigned marks = __reduce_or_sync(kFull, inwin ? 1u << (off_mine - base) : 0u);
+                const int before = __popc(__ballot_sync(kFull, n_mine > 0 && off_mine < base));
+                const int rank = before + __popc(marks & (0xFFFFFFFFu >> (31 - lane))) - 1;
+                const int r = __shfl_sync(kFull, nth, rank & 31);
+                const int off_r = __shfl_sync(kFull, off_mine, r);
+                const int32_t lf_r = __shfl_sync(kFull, lf_mine, r);
+                const uint32_t c_r = __shfl_sync(kFull, c, r);
+                if (item < total) {
+                    const int32_t L = lf_r - (item - off_r);
+                    const uint64_t h = mix64(seed_window<false>(wown + r * wp, P, 0u, L));
+                    BucketTags bt;
+                    load_tags(slot, r, bt);
+                    auto push = [&](uint32_t cand) {
+                        if (cand == c_r) return;
+                        const uint32_t pos = atomicAdd(ctl + r, 1u);
+                        if (pos < (uint32_t) kQ2) {
+                            q_id0[pos * 32 + r] = cand;
+                            q_l0[pos * 32 + r] = (uint16_t) L;
+                            if (FAST) cp_async8(q_t0 + pos * 32 + r, R.words + (uint64_t) cand * R.stride);  // one request
+                        } else {
+                            ctl[32 + r] = 1u;
                         }
+                    };
+                    uint32_t mask = match_mask(bt, h);
+                    const uint32_t bk_r = (mask || bt.cnt > (uint32_t) kBucketCap) ? run_bk[kc * 32 + r] : 0u;
+                    while (mask) {
+                        const int bit = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        push(entry_id(T, bk_r, ((bit & 15) << 1) | (bit >> 4)));
                     }
+                    if (bt.cnt > (uint32_t) kBucketCap) probe_seed_at(T, h, next_bucket(T, bk_r), push);  // rare
                 }
             }
+            __syncwarp();  // nobody reads this slot any more
+            const bool fetch = on && t < n_runs;
+            fetch_buckets(T, slot, fetch, fetch ? run_bk[t * 32 + lane] : 0u, lane, pol);
         }
         cp_async_wait_all();
+        __syncwarp();
+        qn = (int) min(ctl[lane], (uint32_t) kQ2);
+        if (ctl[32 + lane]) hard = true;
+        // The items of a step were queued in no particular order: bring the queue of every read into the order of arrival
+        // seen backwards -- longer overlap first, within one length the larger source id first (insertion sort: the queue
+        // is almost in order, only the arrivals of one step are mixed).
+        {
+            const int q_top = warp_max(hard ? 0 : qn);
+            for (int i = 1; i < q_top; i++) {
+                if (i < qn && !hard) {
+                    const uint32_t id_i = q_id[i * 32];
+                    const uint16_t l_i = q_l[i * 32];
+                    const uint64_t t_i = q_t[i * 32];
+                    int k = i - 1;
+                    while (k >= 0 && (q_l[k * 32] < l_i || (q_l[k * 32] == l_i && q_id[k * 32] < id_i))) {
+                        q_id[(k + 1) * 32] = q_id[k * 32];
+                        q_l[(k + 1) * 32] = q_l[k * 32];
+                        q_t[(k + 1) * 32] = q_t[k * 32];
+                        k--;
+                    }
+                    q_id[(k + 1) * 32] = id_i;
+                    q_l[(k + 1) * 32] = l_i;
+                    q_t[(k + 1) * 32] = t_i;
+                }
+            }
+        }
 
         // ---- resolve the queued arrivals, last arrival first
         int ns = 0;
@@ -934,20 +1013,16 @@ void launch_phase1_tpr(const ReadsDev &R, const SeedTable &prefix, const PsDev &
     int w = (int) ((max_len_nt + 15u) >> 4);
     if (w > kOwnWords) w = kOwnWords;
     const int wp = stride_words(w);
-    const size_t smem = (size_t) kWarps * 32 * wp * sizeof(uint32_t);
+    const size_t smem = (size_t) (((kWarps * 32 * wp + 3) & ~3) + kWarps * (kStageWords + kRunWords)) * sizeof(uint32_t);
     const bool fast = fast_layout(R, P);
     if (!id_list) {
         const int grid = warp_tile_grid(hi - lo, cfg, ALGA_P1_BLOCKS);
-        auto k = !prefix.min_m ? (fast ? phase1_tpr_kernel<true, 2, 0> : phase1_tpr_kernel<false, 2, 0>)
-                 : !cfg.min_slide ? (fast ? phase1_tpr_kernel<true, 2, 1> : phase1_tpr_kernel<false, 2, 1>)
-                                  : (fast ? phase1_tpr_kernel<true, 2, 2> : phase1_tpr_kernel<false, 2, 2>);
+        auto k = fast ? phase1_tpr_kernel<true, 2> : phase1_tpr_kernel<false, 2>;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         k<<<grid, kTpr, smem, s>>>(R, prefix, P, lo, hi, nullptr, nullptr, wp, out, hard_queue, n_hard, force_hard);
     } else {
         const int grid = warp_tile_grid(std::min<uint64_t>(hi - lo, (uint64_t) cfg.sm_count * kTpr * 2), cfg, 2);
-        auto k = !prefix.min_m ? (fast ? phase1_tpr_kernel<true, 4, 0> : phase1_tpr_kernel<false, 4, 0>)
-                 : !cfg.min_slide ? (fast ? phase1_tpr_kernel<true, 4, 1> : phase1_tpr_kernel<false, 4, 1>)
-                                  : (fast ? phase1_tpr_kernel<true, 4, 2> : phase1_tpr_kernel<false, 4, 2>);
+        auto k = fast ? phase1_tpr_kernel<true, 4> : phase1_tpr_kernel<false, 4>;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         k<<<grid, kTpr, smem, s>>>(R, prefix, P, lo, hi, id_list, n_list, wp, out, hard_queue, n_hard, force_hard);
     }
@@ -965,20 +1040,17 @@ void launch_phase2_tpr(const ReadsDev &R, const SeedTable &suffix, const PsDev &
     const int have = (int) ((max_len_nt + 15u) >> 4);
     if (w > have) w = have;
     const int wp = stride_words(w);
-    const size_t smem = (size_t) (((kWarps * 32 * wp + 3) & ~3) + kWarps * (kQ2 * 32 * 3 + kQ2 * 32 / 2)) * sizeof(uint32_t);
+    const size_t smem = (size_t) (((kWarps * 32 * wp + 3) & ~3) + kWarps * (kStageWords + kRunWords + 64) +
+                                  kWarps * (kQ2 * 32 * 3 + kQ2 * 32 / 2)) * sizeof(uint32_t);
     const bool fast = fast_layout(R, P);
     if (!id_list) {
         const int grid = warp_tile_grid(hi - lo, cfg, ALGA_P2_BLOCKS);
-        auto k = !suffix.min_m ? (fast ? phase2_tpr_kernel<true, 2, 0> : phase2_tpr_kernel<false, 2, 0>)
-                 : !cfg.min_slide ? (fast ? phase2_tpr_kernel<true, 2, 1> : phase2_tpr_kernel<false, 2, 1>)
-                                  : (fast ? phase2_tpr_kernel<true, 2, 2> : phase2_tpr_kernel<false, 2, 2>);
+        auto k = fast ? phase2_tpr_kernel<true, 2> : phase2_tpr_kernel<false, 2>;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         k<<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, nullptr, nullptr, wp, rows, out, force_hard);
     } else {
         const int grid = warp_tile_grid(std::min<uint64_t>(hi - lo, (uint64_t) cfg.sm_count * kTpr * 2), cfg, 2);
-        auto k = !suffix.min_m ? (fast ? phase2_tpr_kernel<true, 4, 0> : phase2_tpr_kernel<false, 4, 0>)
-                 : !cfg.min_slide ? (fast ? phase2_tpr_kernel<true, 4, 1> : phase2_tpr_kernel<false, 4, 1>)
-                                  : (fast ? phase2_tpr_kernel<true, 4, 2> : phase2_tpr_kernel<false, 4, 2>);
+        auto k = fast ? phase2_tpr_kernel<true, 4> : phase2_tpr_kernel<false, 4>;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         k<<<grid, kTpr, smem, s>>>(R, suffix, P, lo, hi, id_list, n_list, wp, rows, out, force_hard);
     }
