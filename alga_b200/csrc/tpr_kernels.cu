@@ -57,8 +57,7 @@ constexpr int kQ2 = ALGA_Q2;  // arrivals queued per target in phase 2
 constexpr int kSurv = 4;      // surviving arrivals kept in registers per target
 constexpr int kRowFast = 32;  // longest transposed row the fast phase-2 kernel takes
 constexpr int kDepth = 2;     // runs (= buckets) in flight per lane
-constexpr int kStageSlotWords = 3 * 32 * 4;             // one staging slot of a warp: [piece][lane] x 16 bytes = the count and the
-                                                        // tags (first 48 bytes) of 32 buckets; ids are read where a tag matches
+constexpr int kStageSlotWords = 8 * 32 * 4;             // one staging slot of a warp: [piece][lane] x 16 bytes = 32 buckets
 constexpr int kStageWords = kDepth * kStageSlotWords;   // per warp
 constexpr int kNM = 13;        // m-mers per seed window: the index is built with m = seed_nt - 12 (api.cu minimizer_setting)
 constexpr int kMaxRuns = 16;   // runs per read the fast kernels keep (reads with more go to the generic kernels)
@@ -163,18 +162,19 @@ __device__ __forceinline__ int find_runs(const uint32_t *own, const PsDev &P, co
     return n_runs;
 }
 
-// Warp-collective fetch: every lane with `need` gets the first 48 bytes (count + tags) of its 128-byte bucket `bk` into its
-// place of the staging slot.  Four instructions; in each, three consecutive lanes cover the 3 x 16 bytes of one bucket: one
-// request per bucket.
+// Warp-collective fetch: every lane with `need` gets its 128-byte bucket `bk` into its place of the staging slot.  Eight
+// instructions; in each, the 8 lanes 8q .. 8q+7 cover the 8 x 16 bytes of the bucket of lane 4 i + q: one request per line
+// (the ids must come with the tags: a line of which only the first 48 bytes were asked for arrives without its upper
+// sectors, and the ids of the matching entries then cost a DRAM round trip each -- measured, r2d).
 __device__ __forceinline__ void fetch_buckets(const SeedTable &T, uint32_t *slot, bool need, uint32_t bk, int lane, uint64_t pol) {
     const unsigned needm = __ballot_sync(kFull, need);
     if (needm) {
-        const int grp = lane / 3, piece = lane - 3 * grp;  // lanes 30, 31 idle
+        const int piece = lane & 7;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int owner = 10 * i + grp;
-            const uint32_t obk = __shfl_sync(kFull, bk, owner & 31);
-            if (grp < 10 && owner < 32 && ((needm >> owner) & 1u))
+        for (int i = 0; i < 8; i++) {
+            const int owner = 4 * i + (lane >> 3);
+            const uint32_t obk = __shfl_sync(kFull, bk, owner);
+            if ((needm >> owner) & 1u)
                 cp_async16(slot + ((piece * 32 + owner) << 2), T.slots + (uint64_t) obk * kBucketWords + piece * 4, pol);
         }
     }
@@ -184,9 +184,9 @@ __device__ __forceinline__ void fetch_buckets(const SeedTable &T, uint32_t *slot
 __device__ __forceinline__ uint4 staged_piece(const uint32_t *slot, int p, int lane) {
     return *reinterpret_cast<const uint4 *>(slot + ((p * 32 + lane) << 2));
 }
-// id of entry i of bucket bk (the line was fetched a moment ago: an L2 hit)
-__device__ __forceinline__ uint32_t entry_id(const SeedTable &T, uint32_t bk, int i) {
-    return __ldg(T.slots + (uint64_t) bk * kBucketWords + 12 + i);
+// id of entry i of the staged bucket of lane `lane`
+__device__ __forceinline__ uint32_t staged_id(const uint32_t *slot, int i, int lane) {
+    return slot[(((3 + (i >> 2)) * 32 + lane) << 2) + (i & 3)];
 }
 struct BucketTags {
     uint32_t cnt;     // inserts that chose the bucket (> kBucketCap: the chain goes on in the next bucket)
@@ -221,8 +221,8 @@ __device__ __forceinline__ uint32_t match_mask(const BucketTags &b, uint64_t h) 
 // (MAXM = reads that share a K-nucleotide seed and overlap at one length, i.e. start at the same position: 2 in the first
 // pass over all reads, 4 in the second pass over the reads the first one gave up on.)
 template <int MAXM>
-__device__ __forceinline__ void collect_matches(const SeedTable &T, const BucketTags &b, uint32_t bk, uint64_t h, uint32_t mask,
-                                                uint32_t (&c)[MAXM], int &n) {
+__device__ __forceinline__ void collect_matches(const SeedTable &T, const BucketTags &b, const uint32_t *slot, int lane, uint32_t bk,
+                                                uint64_t h, uint32_t mask, uint32_t (&c)[MAXM], int &n) {
     n = 0;
 #pragma unroll
     for (int k = 0; k < MAXM; k++) c[k] = 0u;
@@ -235,7 +235,7 @@ __device__ __forceinline__ void collect_matches(const SeedTable &T, const Bucket
     while (mask) {
         const int bit = __ffs(mask) - 1;
         mask &= mask - 1;
-        add(entry_id(T, bk, ((bit & 15) << 1) | (bit >> 4)));
+        add(staged_id(slot, ((bit & 15) << 1) | (bit >> 4), lane));
     }
     if (b.cnt > (uint32_t) kBucketCap) probe_seed_at(T, h, next_bucket(T, bk), add);  // rare: plain loads
     if (n > 1 && n <= MAXM) {  // unused slots hold 0 and sink to the end (n says how many are real)
@@ -456,7 +456,7 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
                         if (mask || bt.cnt > (uint32_t) kBucketCap) {
                             uint32_t cm[MAXM];
                             int n = 0;
-                            collect_matches<MAXM>(T, bt, bk, h, mask, cm, n);
+                            collect_matches<MAXM>(T, bt, slot, lane, bk, h, mask, cm, n);
                             if (n > MAXM) {
                                 hard = true;
                             } else {  // within one length the larger target id is the later push: cm[] is descending
@@ -646,16 +646,17 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
     extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int own_words = ((kWarps * 32 * wp + 3) & ~3);
-    constexpr int kQueueWords = kQ2 * 32 * 3 + kQ2 * 32 / 2;
+    constexpr int kQueueWords = kQ2 * 32 + kQ2 * 32 / 2;  // ids + lengths (u16); the heads (u64) reuse the staging area
     uint32_t *wown = smem + wib * 32 * wp;
     const uint32_t *own = wown + lane * wp;
     uint32_t *stage = smem + own_words + wib * kStageWords;
     uint32_t *run_bk = smem + own_words + kWarps * kStageWords + wib * kRunWords;
     uint8_t *run_first = reinterpret_cast<uint8_t *>(run_bk + kMaxRuns * 32);
-    uint32_t *ctl = smem + own_words + kWarps * (kStageWords + kRunWords) + wib * 64;  // queue lengths [32] | overflow flags [32]
-    uint32_t *q_id = smem + own_words + kWarps * (kStageWords + kRunWords + 64) + wib * kQueueWords + lane;  // q_id[k * 32]
-    uint64_t *q_t = reinterpret_cast<uint64_t *>(q_id - lane + kQ2 * 32) + lane;                 // q_t[k * 32]: first 64 bits of the hit read
-    uint16_t *q_l = reinterpret_cast<uint16_t *>(q_id - lane + kQ2 * 32 * 3) + lane;             // q_l[k * 32]
+    uint32_t *ctl = smem + own_words + kWarps * (kStageWords + kRunWords) + wib * 72;  // queue lengths [32] | overflow flags [32] | lanes [32] (u8)
+    uint32_t *q_id = smem + own_words + kWarps * (kStageWords + kRunWords + 72) + wib * kQueueWords + lane;  // q_id[k * 32]
+    uint16_t *q_l = reinterpret_cast<uint16_t *>(q_id - lane + kQ2 * 32) + lane;                 // q_l[k * 32]
+    uint64_t *q_t = reinterpret_cast<uint64_t *>(stage) + lane;                                  // q_t[k * 32]: first 64 bits of the hit read
+    static_assert(kQ2 * 32 * 2 <= kStageWords, "the heads of the queued reads must fit the staging area");
     const uint64_t pol = l2_evict_last_policy();
     const int32_t l_lo = P.rs > P.lmin ? P.rs : P.lmin;
     const bool csr = rows_are_csr(rows);
@@ -703,7 +704,6 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
         __syncwarp();
         const bool on = walk && !hard;
         uint32_t *q_id0 = q_id - lane;
-        uint64_t *q_t0 = q_t - lane;
         uint16_t *q_l0 = q_l - lane;
         // run k lives in staging slot k & 1; round t fetches run t and works through run t - 2 of every read
         for (int t = 0;; t++) {
@@ -728,7 +728,9 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
             const int total = __shfl_sync(kFull, incl, 31), off_mine = incl - n_mine;
             // the reads that take part in this round, in lane order: lane i holds the lane of the i-th of them
             const unsigned activem = __ballot_sync(kFull, n_mine > 0);
-            const int nth = (int) __fns(activem, 0, lane + 1);
+            uint8_t *nth = reinterpret_cast<uint8_t *>(ctl + 64);
+            if (n_mine > 0) nth[__popc(activem & ((1u << lane) - 1u))] = (uint8_t) lane;
+            __syncwarp();
             for (int base = 0; base < total; base += 32) {
                 const int item = base + lane;
                 // the read of this item = the last participating read whose first item is not beyond it: reads that start
@@ -737,7 +739,7 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
                 const unsigned marks = __reduce_or_sync(kFull, inwin ? 1u << (off_mine - base) : 0u);
                 const int before = __popc(__ballot_sync(kFull, n_mine > 0 && off_mine < base));
                 const int rank = before + __popc(marks & (0xFFFFFFFFu >> (31 - lane))) - 1;
-                const int r = __shfl_sync(kFull, nth, rank & 31);
+                const int r = nth[rank & 31];
                 const int off_r = __shfl_sync(kFull, off_mine, r);
                 const int32_t lf_r = __shfl_sync(kFull, lf_mine, r);
                 const uint32_t c_r = __shfl_sync(kFull, c, r);
@@ -752,19 +754,17 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
                         if (pos < (uint32_t) kQ2) {
                             q_id0[pos * 32 + r] = cand;
                             q_l0[pos * 32 + r] = (uint16_t) L;
-                            if (FAST) cp_async8(q_t0 + pos * 32 + r, R.words + (uint64_t) cand * R.stride);  // one request
                         } else {
                             ctl[32 + r] = 1u;
                         }
                     };
                     uint32_t mask = match_mask(bt, h);
-                    const uint32_t bk_r = (mask || bt.cnt > (uint32_t) kBucketCap) ? run_bk[kc * 32 + r] : 0u;
                     while (mask) {
                         const int bit = __ffs(mask) - 1;
                         mask &= mask - 1;
-                        push(entry_id(T, bk_r, ((bit & 15) << 1) | (bit >> 4)));
+                        push(staged_id(slot, ((bit & 15) << 1) | (bit >> 4), r));
                     }
-                    if (bt.cnt > (uint32_t) kBucketCap) probe_seed_at(T, h, next_bucket(T, bk_r), push);  // rare
+                    if (bt.cnt > (uint32_t) kBucketCap) probe_seed_at(T, h, next_bucket(T, run_bk[kc * 32 + r]), push);  // rare
                 }
             }
             __syncwarp();  // nobody reads this slot any more
@@ -784,18 +784,22 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
                 if (i < qn && !hard) {
                     const uint32_t id_i = q_id[i * 32];
                     const uint16_t l_i = q_l[i * 32];
-                    const uint64_t t_i = q_t[i * 32];
                     int k = i - 1;
                     while (k >= 0 && (q_l[k * 32] < l_i || (q_l[k * 32] == l_i && q_id[k * 32] < id_i))) {
                         q_id[(k + 1) * 32] = q_id[k * 32];
                         q_l[(k + 1) * 32] = q_l[k * 32];
-                        q_t[(k + 1) * 32] = q_t[k * 32];
                         k--;
                     }
                     q_id[(k + 1) * 32] = id_i;
                     q_l[(k + 1) * 32] = l_i;
-                    q_t[(k + 1) * 32] = t_i;
                 }
+            }
+            // FAST: the first 64 bits of every queued read (all its overhang tail needs), one 8-byte request each, all in
+            // flight together; they land in the staging area, which the probe no longer needs
+            if (FAST) {
+                for (int k = 0; k < q_top; k++)
+                    if (k < qn && !hard) cp_async8(q_t + k * 32, R.words + (uint64_t) q_id[k * 32] * R.stride);
+                cp_async_wait_all();
             }
         }
 
@@ -1040,8 +1044,8 @@ void launch_phase2_tpr(const ReadsDev &R, const SeedTable &suffix, const PsDev &
     const int have = (int) ((max_len_nt + 15u) >> 4);
     if (w > have) w = have;
     const int wp = stride_words(w);
-    const size_t smem = (size_t) (((kWarps * 32 * wp + 3) & ~3) + kWarps * (kStageWords + kRunWords + 64) +
-                                  kWarps * (kQ2 * 32 * 3 + kQ2 * 32 / 2)) * sizeof(uint32_t);
+    const size_t smem = (size_t) (((kWarps * 32 * wp + 3) & ~3) + kWarps * (kStageWords + kRunWords + 72) +
+                                  kWarps * (kQ2 * 32 + kQ2 * 32 / 2)) * sizeof(uint32_t);
     const bool fast = fast_layout(R, P);
     if (!id_list) {
         const int grid = warp_tile_grid(hi - lo, cfg, ALGA_P2_BLOCKS);

@@ -108,9 +108,13 @@ class ShardedPrefSuf:
         self._shard = PrefSufPlan.shard_struct(rank, world, n_shard, self.n_total, list(self._h_ws.buffer_ptrs),
                                                self.tp_sym.data_ptr(), self.ts_sym.data_ptr())
         # replicated read set + its binding (no pass over the reads: they arrive during the build)
-        self._full = torch.zeros(n_shard * world * words_per_read + READ_PAD_BYTES // 4, dtype=torch.int32, device=device)
+        # (the shards travel in the caller's compact layout; the replicated copy has one sector-aligned slot per read, which is
+        # what the fast kernels want: common.cuh aligned_stride_words)
+        self.S = (words_per_read + 7) & ~7
+        self._full = torch.zeros(n_shard * world * self.S + READ_PAD_BYTES // 4, dtype=torch.int32, device=device)
+        self._slots = self._full[: n_shard * world * self.S].view(n_shard * world, self.S)
         self._len = torch.full((self.n_total,), len_nt, dtype=torch.int32, device=device)
-        self._reads = DeviceReads.from_tensors(self._full, self._len, stride=words_per_read, n=self.n_total, max_len=len_nt)
+        self._reads = DeviceReads.from_tensors(self._full, self._len, stride=self.S, n=self.n_total, max_len=len_nt)
         self.plan.bind_uniform(self._reads, len_nt)
         self._copy_stream = torch.cuda.Stream(device=device)
         self._ev = None
@@ -133,10 +137,10 @@ class ShardedPrefSuf:
         self._copy_stream.wait_stream(main)
         for k in range(self.world):
             p = (self.rank + k) % self.world
-            dst = self._full[p * n * W:(p + 1) * n * W]
+            dst = self._slots[p * n:(p + 1) * n, :W]
             ev = torch.cuda.Event()
             with torch.cuda.stream(self._copy_stream):
-                dst.copy_(self._peer_shards[p], non_blocking=True)
+                dst.copy_(self._peer_shards[p].view(n, W), non_blocking=True)  # NVLink read, written into the read slots
                 ev.record()
             main.wait_event(ev)
             # seeds of the arrived shard that fall into this rank's slice of the bucket space

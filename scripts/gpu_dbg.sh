@@ -14,5 +14,3 @@ except Exception as e:
 PY
   tail -2 gpurun_out/dbg_$wl.err
 done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'phase1_tpr|phase2_tpr' -s 4 -c 4 \
-   -f -o gpurun_out/prof_r2c_cfg2 python bench.py --workload cfg2 --steps 1 --warmup 1 --no-cpu --e2e-steps 0 > gpurun_out/ncu_r2c.log 2>&1; echo "ncu rc=$?"

@@ -21,19 +21,20 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.02
     w = synth.make_config("cfg2", scale=scale)
-    n = (w.reads.n // (2 * world)) * 2 * world
-    W = int(w.reads.word_off[1] - w.reads.word_off[0])
-    rs = readset.ReadSet(w.reads.words[: n * W], w.reads.word_off[: n + 1], w.reads.len_nt[:n])
-    n_shard = n // world
+    rs = w.reads
+    n = rs.n  # not a multiple of the world size in general: the last rank owns fewer reads
+    W = int(rs.word_off[1] - rs.word_off[0])
+    n_shard = ((n + world - 1) // world + 1) & ~1
+    lo, hi = min(rank * n_shard, n), min((rank + 1) * n_shard, n)
     words = torch.from_numpy(rs.words.view(np.int32).reshape(n, W))
     sp = ShardedPrefSuf(w.params.min_overlap, w.params.rs_min_overlap, 0, w.params.max_len_cap, dev, rank, world,
-                        len_nt=int(rs.len_nt[0]), n_shard=n_shard, words_per_read=W)
-    sp.load_shard(words[rank * n_shard:(rank + 1) * n_shard].to(dev))
+                        len_nt=int(rs.len_nt[0]), n_shard=n_shard, words_per_read=W, n_total=n)
+    sp.load_shard(words[lo:hi].to(dev))
     ok = True
     for _ in range(2):  # the workspaces are reused across builds
         sp.run()
         e = sp.plan.result_host().edges()
-        e[:, 0] += rank * n_shard
+        e[:, 0] += lo
         parts = [None] * world
         dist.all_gather_object(parts, e)
         if rank == 0:
