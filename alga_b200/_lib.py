@@ -89,6 +89,7 @@ class OverlapGraphOut(C.Structure):
 _P = C.c_void_p
 SYMBOLS = {
     "alga_gpu_prefsuf_build": (C.c_int, [C.POINTER(Reads), C.POINTER(PsParams), C.POINTER(Csr), C.POINTER(Timing)]),
+    "alga_gpu_prefsuf_build_multi": (C.c_int, [C.POINTER(Reads), C.POINTER(PsParams), C.c_int32, C.POINTER(Csr), C.POINTER(Timing)]),
     "alga_gpu_free_csr": (None, [C.POINTER(Csr)]),
     "alga_ps_plan_create": (C.c_int, [C.POINTER(_P), C.POINTER(PsParams)]),
     "alga_ps_plan_destroy": (None, [_P]),
@@ -105,6 +106,9 @@ SYMBOLS = {
     "alga_ps_shard_ws_bytes": (C.c_uint64, [C.c_uint32, C.c_int32]),
     "alga_ps_shard_table_bytes": (C.c_uint64, [C.c_uint32, C.c_int32]),
     "alga_ps_shard_index_range": (C.c_int, [_P, C.POINTER(Shard), C.c_uint32, C.c_uint32, C.c_int, _P]),
+    "alga_ps_shard_seed_keys": (C.c_int, [_P, C.POINTER(Shard), _P, C.c_uint32, C.c_uint32, _P, _P]),
+    "alga_ps_shard_index_keys": (C.c_int, [_P, C.POINTER(Shard), _P, C.c_uint32, C.c_uint32, C.c_int, _P]),
+    "alga_ps_set_bucket_load": (None, [C.c_int32]),
     "alga_ps_shard_phase1": (C.c_int, [_P, C.POINTER(Shard), _P]),
     "alga_ps_shard_phase2": (C.c_int, [_P, C.POINTER(Shard), _P]),
     "alga_ps_shard_csr": (C.c_int, [_P, C.POINTER(Shard), _P]),

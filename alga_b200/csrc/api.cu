@@ -244,15 +244,19 @@ int compute_stats(alga_ps_plan *plan, cudaStream_t s, uint32_t max_len_hint) {
     return resolve_params(plan);
 }
 
+int g_bucket_load = 0;  // alga_ps_set_bucket_load(); 0 = default
+
 uint32_t buckets_for(uint32_t entries) {
     // mean occupancy 3 of kBucketCap = 20 slots.  Minimizer buckets fill unevenly -- all reads that start within a few
     // nucleotides of one another share theirs -- so a probe meets 5-6 entries on average and an overflowing bucket in
-    // about 0.2 % of the cases (scripts/probes/minimizer_locality.py); 4 would triple that.
-    static const int load = [] {  // tuning knob: mean entries per bucket
+    // about 0.2 % of the cases (scripts/probes/minimizer_locality.py); 4 would triple that.  Sharded builds, which ship
+    // their table slices over NVLink, may prefer denser tables (alga_ps_set_bucket_load).
+    static const int env_load = [] {
         const char *e = getenv("ALGA_PS_BUCKET_LOAD");
-        const int v = e ? atoi(e) : 3;
-        return v >= 1 && v <= 12 ? v : 3;
+        const int v = e ? atoi(e) : 0;
+        return v >= 1 && v <= 12 ? v : 0;
     }();
+    const int load = g_bucket_load ? g_bucket_load : (env_load ? env_load : 3);
     uint64_t nb = ((uint64_t) entries + load - 1) / load;
     if (nb < 64) nb = 64;
     return (uint32_t) nb;
@@ -269,7 +273,7 @@ void size_table(SeedTable &t, uint32_t entries, int world = 1) {
 // (the fast kernels keep exactly that many in registers, tpr_kernels.cu kNM): 20 for the usual 32-nucleotide seed.  Seeds
 // shorter than 16 nucleotides (min_overlap < 16) are their own minimizer -- every window its own bucket, as in a plain hash
 // table -- and are left to the generic kernels (fast_seed()).
-uint32_t minimizer_setting(int seed_nt) { return (uint32_t) (seed_nt >= 16 ? seed_nt - 12 : seed_nt); }
+uint32_t minimizer_setting(int seed_nt) { return (uint32_t) (seed_nt >= 16 ? seed_nt - (kNM - 1) : seed_nt); }
 bool fast_seed(const alga_ps_plan *plan) { return plan->P.seed_nt >= 16; }
 
 // s2 != nullptr: everything that concerns the suffix table goes to s2
@@ -412,8 +416,14 @@ int stage_csr(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int32_t *tripl
     CKR(plan->nbr.ensure((size_t) (n_tr ? n_tr : 1) * 4));
     CKR(plan->off.ensure((size_t) (n_tr ? n_tr : 1) * 4));
     CKR(plan->big_rows.ensure((size_t) (n ? n : 1) * 4));
-    launch_scatter_csr(triples, n_tr, lo, hi, swap, plan->row_off.as<uint64_t>(), outdeg, plan->nbr.as<int32_t>(),
-                       plan->off.as<int32_t>(), s, plan->cfg);
+    if (n_tr < 0xFFFFFFFFull) {
+        CKR(plan->tmp_nbr.ensure((size_t) (n_tr ? n_tr : 1) * 8));
+        launch_scatter_csr_pairs(triples, n_tr, lo, hi, swap, plan->row_off.as<uint64_t>(), outdeg, plan->tmp_nbr.p,
+                                 plan->nbr.as<int32_t>(), plan->off.as<int32_t>(), s, plan->cfg);
+    } else {
+        launch_scatter_csr(triples, n_tr, lo, hi, swap, plan->row_off.as<uint64_t>(), outdeg, plan->nbr.as<int32_t>(),
+                           plan->off.as<int32_t>(), s, plan->cfg);
+    }
     Counters *dc = plan->counters_d.as<Counters>();
     CK(cudaMemsetAsync(&dc->n_big, 0, 4, s));
     launch_sort_rows(plan->row_off.as<uint64_t>(), n, plan->nbr.as<int32_t>(), plan->off.as<int32_t>(),
@@ -436,6 +446,10 @@ int stage_csr(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int32_t *tripl
 }
 
 }  // namespace
+
+namespace alga {
+int set_error(int code, const char *msg) { return fail(code, "%s", msg); }  // for the other translation units
+}
 
 // ================================================================================================
 extern "C" {
@@ -731,6 +745,50 @@ int alga_ps_shard_index_range(alga_ps_plan *plan, const alga_ps_shard *sh, uint3
     plan->index_valid = true;
     return ALGA_OK;
 }
+
+int alga_ps_shard_seed_keys(alga_ps_plan *plan, const alga_ps_shard *sh, const uint32_t *shard_words, uint32_t stride_words,
+                            uint32_t n_reads, uint32_t *keys, void *stream) {
+    uint32_t my_lo, my_hi;
+    CKR(check_shard(plan, sh, &my_lo, &my_hi));
+    if (!plan->P.uniform_len) return fail(ALGA_E_INVALID, "seed records need equal-length reads");
+    if (n_reads && (!shard_words || !keys || stride_words == 0)) return fail(ALGA_E_INVALID, "null argument");
+    CKR(use_device(plan));
+    size_table(plan->Tp, sh->n_total, sh->world);
+    size_table(plan->Ts, sh->n_total, sh->world);
+    plan->Tp.min_m = plan->Ts.min_m = minimizer_setting(plan->P.seed_nt);
+    launch_seed_keys(shard_words, stride_words, n_reads, plan->P, plan->Tp, plan->Ts, keys, (cudaStream_t) stream, plan->cfg);
+    CK(cudaGetLastError());
+    return ALGA_OK;
+}
+
+int alga_ps_shard_index_keys(alga_ps_plan *plan, const alga_ps_shard *sh, const uint32_t *keys, uint32_t lo, uint32_t hi, int first,
+                             void *stream) {
+    uint32_t my_lo, my_hi;
+    CKR(check_shard(plan, sh, &my_lo, &my_hi));
+    if (!sh->table_prefix || !sh->table_suffix) return fail(ALGA_E_INVALID, "null seed table pointer");
+    if (lo > hi || hi > plan->R.n) return fail(ALGA_E_INVALID, "bad range [%u,%u)", lo, hi);
+    if (hi > lo && !keys) return fail(ALGA_E_INVALID, "null seed records");
+    CKR(use_device(plan));
+    cudaStream_t s = (cudaStream_t) stream;
+    size_table(plan->Tp, sh->n_total, sh->world);
+    size_table(plan->Ts, sh->n_total, sh->world);
+    plan->Tp.min_m = plan->Ts.min_m = minimizer_setting(plan->P.seed_nt);
+    plan->Tp.slots = (uint32_t *) sh->table_prefix;
+    plan->Ts.slots = (uint32_t *) sh->table_suffix;
+    const uint32_t slice = plan->Tp.slice, b_lo = (uint32_t) sh->rank * slice, b_hi = b_lo + slice;
+    if (first) {
+        plan->launches = 0;
+        const size_t off = (size_t) b_lo * kBucketWords * 4, bytes = (size_t) slice * kBucketWords * 4;
+        CK(cudaMemsetAsync((char *) sh->table_prefix + off, 0, bytes, s));
+        CK(cudaMemsetAsync((char *) sh->table_suffix + off, 0, bytes, s));
+    }
+    launch_index_keys(keys, lo, hi - lo, plan->Tp, plan->Ts, b_lo, b_hi, s, plan->cfg);
+    CK(cudaGetLastError());
+    plan->index_valid = true;
+    return ALGA_OK;
+}
+
+void alga_ps_set_bucket_load(int32_t load) { g_bucket_load = load >= 1 && load <= 12 ? load : 0; }
 
 int alga_ps_shard_phase1(alga_ps_plan *plan, const alga_ps_shard *sh, void *stream) {
     uint32_t lo, hi;

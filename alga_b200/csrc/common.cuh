@@ -8,6 +8,10 @@ namespace alga {
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr int kBucketWords = 32;  // a bucket of the seed index = 128 bytes = one L2 line
 constexpr int kBucketCap = 20;    // entries per bucket
+#ifndef ALGA_NM
+#define ALGA_NM 9
+#endif
+constexpr int kNM = ALGA_NM;      // m-mers per seed window: the minimizer is taken over m = seed_nt - (kNM - 1) nucleotides
 constexpr int kSmallEdgesKept = 3;  // SOES, GraphCreatorPrefSuf.h:62
 constexpr int kHeadWords = 4;       // cached head of a read: first 64 nucleotides
 constexpr int kHeadNt = kHeadWords * 16;
@@ -362,8 +366,7 @@ __device__ __forceinline__ void probe_seed_window(const SeedTable &t, uint64_t w
 }
 
 // The table must be zeroed before the first insert.  One atomic (claims a slot) + two stores into the same line.
-__device__ __forceinline__ void insert_seed_at(const SeedTable &t, uint64_t h, uint32_t bk, uint32_t id) {
-    const uint32_t tag = tag_of(h);
+__device__ __forceinline__ void insert_tag_at(const SeedTable &t, uint32_t tag, uint32_t bk, uint32_t id) {
     while (true) {
         uint32_t *b = t.slots + (uint64_t) bk * kBucketWords;
         const uint32_t pos = atomicAdd(b, 1u);
@@ -374,6 +377,9 @@ __device__ __forceinline__ void insert_seed_at(const SeedTable &t, uint64_t h, u
         }
         bk = next_bucket(t, bk);
     }
+}
+__device__ __forceinline__ void insert_seed_at(const SeedTable &t, uint64_t h, uint32_t bk, uint32_t id) {
+    insert_tag_at(t, tag_of(h), bk, id);
 }
 __device__ __forceinline__ void insert_seed(const SeedTable &t, uint64_t h, uint32_t id) {
     insert_seed_at(t, h, bucket_of(h, t.n_buckets), id);

@@ -29,6 +29,13 @@ void launch_read_stats(const ReadsDev &R, int lmin, int min_offset, ReadStats *d
 void launch_build_index(const ReadsDev &R, const PsDev &P, SeedTable prefix, SeedTable suffix, uint32_t lo, uint32_t hi,
                         uint32_t b_lo, uint32_t b_hi, cudaStream_t s, const LaunchCfg &cfg, int which = 3);
 
+// sharded build of equal-length reads: seed records (bucket prefix side, bucket suffix side, the two 16-bit tags: 12 bytes) of
+// `n` reads in the caller's fixed-stride layout, and the inserts out of such records into the bucket range [b_lo, b_hi)
+void launch_seed_keys(const uint32_t *words, uint32_t stride, uint32_t n, const PsDev &P, SeedTable prefix, SeedTable suffix,
+                      uint32_t *keys, cudaStream_t s, const LaunchCfg &cfg);
+void launch_index_keys(const uint32_t *keys, uint32_t first_id, uint32_t n, SeedTable prefix, SeedTable suffix, uint32_t b_lo,
+                       uint32_t b_hi, cudaStream_t s, const LaunchCfg &cfg);
+
 // --- sharded runs: read what the peers produced for this rank out of their exchange workspaces (NVLink) ----
 // seg[p] / cnt[p]: peer p's segment for this rank and its entry count (device pointers valid in this process)
 void launch_pull_rows(const void *const *seg, const uint32_t *const *cnt, int world, uint32_t cap, uint32_t n_expected,
@@ -109,6 +116,9 @@ void launch_count_sources(const int32_t *triples, uint64_t n, uint32_t lo, uint3
 void launch_scatter_csr(const int32_t *triples, uint64_t n, uint32_t lo, uint32_t hi, int swap,
                         const uint64_t *row_off, uint32_t *cursor, int32_t *nbr, int32_t *off, cudaStream_t s,
                         const LaunchCfg &cfg);
+// the same with fewer random accesses (n < 2^32): `cursor` (row sizes on entry) and `pairs` (n x 8 bytes) are scratch
+void launch_scatter_csr_pairs(const int32_t *triples, uint64_t n, uint32_t lo, uint32_t hi, int swap, const uint64_t *row_off,
+                              uint32_t *cursor, void *pairs, int32_t *nbr, int32_t *off, cudaStream_t s, const LaunchCfg &cfg);
 // sort every row by (nbr, off); rows longer than 32 go through `big_rows` (queue of row ids) and tmp buffers
 void launch_sort_rows(const uint64_t *row_off, uint32_t n_rows, int32_t *nbr, int32_t *off, uint32_t *big_rows,
                       uint32_t *n_big, cudaStream_t s, const LaunchCfg &cfg);

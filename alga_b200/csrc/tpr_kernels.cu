@@ -59,7 +59,6 @@ constexpr int kRowFast = 32;  // longest transposed row the fast phase-2 kernel 
 constexpr int kDepth = 2;     // runs (= buckets) in flight per lane
 constexpr int kStageSlotWords = 8 * 32 * 4;             // one staging slot of a warp: [piece][lane] x 16 bytes = 32 buckets
 constexpr int kStageWords = kDepth * kStageSlotWords;   // per warp
-constexpr int kNM = 13;        // m-mers per seed window: the index is built with m = seed_nt - 12 (api.cu minimizer_setting)
 constexpr int kMaxRuns = 16;   // runs per read the fast kernels keep (reads with more go to the generic kernels)
 constexpr int kRunWords = kMaxRuns * 32 + kMaxRuns * 8;  // per warp: bucket [kMaxRuns][32] (u32) + first length index [kMaxRuns][32] (u8)
 
@@ -127,11 +126,15 @@ __device__ __forceinline__ int find_runs(const uint32_t *own, const PsDev &P, co
     //         else -- position s0 + kNM - 1 - j (the window moves down: position s0 - t + kNM leaves, slot (t - 1) % kNM)
 #pragma unroll
     for (int j = 0; j < kNM; j++) H[j] = on ? mmer(UP ? s0 + j : s0 + kNM - 1 - j) : 0u;
-    auto ring_min = [&]() {
-        uint32_t v = H[0];
+    auto ring_min = [&]() {  // a tree, not a chain: the minimum is on the critical path of every step
+        uint32_t v[kNM];
 #pragma unroll
-        for (int j = 1; j < kNM; j++) v = min(v, H[j]);
-        return v;
+        for (int j = 0; j < kNM; j++) v[j] = H[j];
+#pragma unroll
+        for (int w = 1; w < kNM; w <<= 1)
+#pragma unroll
+            for (int j = 0; j + w < kNM; j += 2 * w) v[j] = min(v[j], v[j + w]);
+        return v[0];
     };
     uint32_t prev = ring_min();
     int n_runs = 0;

@@ -77,7 +77,7 @@ class ShardedPrefSuf:
     """
 
     def __init__(self, min_overlap, rs_min_overlap, min_offset, max_len_cap, device, rank, world, len_nt, n_shard, words_per_read,
-                 group=None, n_total=None):
+                 group=None, n_total=None, bucket_load=None):
         import torch.distributed._symmetric_memory as symm
 
         self.rank, self.world = rank, world
@@ -89,6 +89,11 @@ class ShardedPrefSuf:
         assert (world - 1) * n_shard < self.n_total <= world * n_shard or self.n_total <= n_shard, (n_shard, world, n_total)
         self._err = None
         self.plan = PrefSufPlan(min_overlap, rs_min_overlap, min_offset, max_len_cap, device=device)
+        # the table slices travel over NVLink: from 4 ranks on denser tables (6 instead of 3 entries per bucket on average,
+        # half the bytes) pay for the longer bucket chains
+        if bucket_load is None:
+            bucket_load = 6 if world >= 4 else 0
+        self.plan.lib.alga_ps_set_bucket_load(int(bucket_load))
         # peer-mapped buffers
         self.shard_sym = symm.empty(n_shard * words_per_read, dtype=torch.int32, device=device)
         self.ws_sym = symm.empty(self.plan.shard_ws_bytes(n_shard, world), dtype=torch.uint8, device=device)
@@ -96,6 +101,7 @@ class ShardedPrefSuf:
         self._h_shard = symm.rendezvous(self.shard_sym, self.group)
         self._h_ws = symm.rendezvous(self.ws_sym, self.group)
         self._peer_shards = [self._h_shard.get_buffer(p, (n_shard * words_per_read,), torch.int32) for p in range(world)]
+        self._compact = torch.empty(n_shard * world * words_per_read, dtype=torch.int32, device=device)  # landing zone of the pulls
         # seed tables: every rank fills its slice of the bucket space, the slices are then copied from each other
         tb = self.plan.shard_table_bytes(self.n_total, world)
         self._slice_bytes = tb // world
@@ -137,12 +143,13 @@ class ShardedPrefSuf:
         self._copy_stream.wait_stream(main)
         for k in range(self.world):
             p = (self.rank + k) % self.world
-            dst = self._slots[p * n:(p + 1) * n, :W]
+            stage = self._compact[p * n * W:(p + 1) * n * W]
             ev = torch.cuda.Event()
             with torch.cuda.stream(self._copy_stream):
-                dst.copy_(self._peer_shards[p].view(n, W), non_blocking=True)  # NVLink read, written into the read slots
+                stage.copy_(self._peer_shards[p], non_blocking=True)  # DMA over NVLink, contiguous on both sides
                 ev.record()
             main.wait_event(ev)
+            self._slots[p * n:(p + 1) * n, :W].copy_(stage.view(n, W))  # local: into the sector-aligned read slots
             # seeds of the arrived shard that fall into this rank's slice of the bucket space
             self._stage(lambda: self.plan.shard_index_range(self._shard, min(p * n, self.n_total), min((p + 1) * n, self.n_total),
                                                              first=(k == 0)))

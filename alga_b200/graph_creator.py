@@ -108,7 +108,8 @@ class GraphCreatorPrefSuf:
 
     def __init__(self, reads: ReadSet, min_overlap: int, rs_min_overlap: int, min_offset: int = 0,
                  max_len_cap: int = 500, device: int = 0, list_cap: int = 0, pinned: bool = False,
-                 force_generic: bool = False, borrow: bool = False):
+                 force_generic: bool = False, borrow: bool = False, n_gpus: int = 1):
+        self.n_gpus = n_gpus  # > 1: alga_gpu_prefsuf_build_multi (one process, up to n_gpus GPUs of the box)
         self.borrow = borrow  # True: results alias the library's page-locked staging until the next build (_csr_to_graph)
         self.params = _lib.PsParams(min_overlap, rs_min_overlap, min_offset, max_len_cap, device, list_cap,
                                     _lib.PS_FORCE_GENERIC if force_generic else 0)
@@ -150,7 +151,10 @@ class GraphCreatorPrefSuf:
                         r.len_nt.ctypes.data, self.alignFrom.ctypes.data, self.alignTo.ctypes.data)
         csr = _lib.Csr()
         tm = _lib.Timing()
-        _lib.check(lib.alga_gpu_prefsuf_build(C.byref(st), C.byref(self.params), C.byref(csr), C.byref(tm)))
+        if self.n_gpus > 1:
+            _lib.check(lib.alga_gpu_prefsuf_build_multi(C.byref(st), C.byref(self.params), self.n_gpus, C.byref(csr), C.byref(tm)))
+        else:
+            _lib.check(lib.alga_gpu_prefsuf_build(C.byref(st), C.byref(self.params), C.byref(csr), C.byref(tm)))
         try:
             self.graph = _csr_to_graph(csr, self.borrow)
         finally:
@@ -159,6 +163,7 @@ class GraphCreatorPrefSuf:
         self.timing["stage_ms"] = dict(zip(("index", "phase1", "transpose", "phase2", "csr"), list(tm.stage_ms)[:5]))
         self.timing["n_row_overflow"] = int(tm.stage_ms[5])
         self.timing["n_hard_sources"] = int(tm.stage_ms[6])
+        self.timing["n_gpus_used"] = int(tm.stage_ms[7])  # alga_gpu_prefsuf_build_multi only (else 0)
         return self.graph
 
     def clear(self):

@@ -170,6 +170,16 @@ class PrefSufPlan:
     def shard_index_range(self, sh: _lib.Shard, lo: int, hi: int, first: bool):
         _lib.check(self.lib.alga_ps_shard_index_range(self._h, C.byref(sh), lo, hi, 1 if first else 0, self._stream()))
 
+    def shard_seed_keys(self, sh: _lib.Shard, shard_words: torch.Tensor, stride: int, n_reads: int, keys: torch.Tensor):
+        """12-byte seed records of this rank's own reads (``shard_words``: their packed words at ``stride`` words per read)."""
+        _lib.check(self.lib.alga_ps_shard_seed_keys(self._h, C.byref(sh), shard_words.data_ptr(), stride, n_reads, keys.data_ptr(),
+                                                    self._stream()))
+
+    def shard_index_keys(self, sh: _lib.Shard, keys: torch.Tensor, lo: int, hi: int, first: bool):
+        """Insert the seeds of the reads [lo, hi) that fall into this rank's slice, out of their seed records ``keys``."""
+        _lib.check(self.lib.alga_ps_shard_index_keys(self._h, C.byref(sh), keys.data_ptr() if hi > lo else None, lo, hi,
+                                                     1 if first else 0, self._stream()))
+
     def shard_phase1(self, sh: _lib.Shard):
         _lib.check(self.lib.alga_ps_shard_phase1(self._h, C.byref(sh), self._stream()))
 

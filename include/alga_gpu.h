@@ -98,6 +98,15 @@ int alga_gpu_prefsuf_build(const alga_reads *reads, const alga_ps_params *params
                            alga_timing *timing /* may be NULL */);
 void alga_gpu_free_csr(alga_csr *csr);
 
+/* The same build on up to n_gpus GPUs of the box, from ONE process (one host thread per GPU, peer memory over NVLink
+ * between them): what the reference's single-process driver binds to use more than one GPU (shim: ALGA_GPU_DEVICES=<n>).
+ * Rank r owns the reads [r * n_shard, (r + 1) * n_shard); the stages are those of alga_ps_shard_* below.  The sharded kernels
+ * take equal-length reads at a fixed stride, none removed, no flags cleared -- what main.cpp:249-282 hands over for
+ * equal-length input; any other read set (and n_gpus <= 1, and fewer than 4096 reads) is built on params->device alone.
+ * The result arrays are malloc'ed (not borrowed); timing->stage_ms[7] = number of GPUs used. */
+int alga_gpu_prefsuf_build_multi(const alga_reads *reads, const alga_ps_params *params, int32_t n_gpus, alga_csr *out,
+                                 alga_timing *timing /* may be NULL */);
+
 /* ---- staged, device-resident interface (bench, multi-GPU harness) ------------------------- */
 /* A plan owns the device workspace of one GPU.  Device pointers passed in are borrowed. */
 typedef struct alga_ps_plan alga_ps_plan;
@@ -168,6 +177,18 @@ uint64_t alga_ps_shard_ws_bytes(uint32_t n_shard, int32_t world);
 uint64_t alga_ps_shard_table_bytes(uint32_t n_total, int32_t world);
 int alga_ps_shard_index_range(alga_ps_plan *plan, const alga_ps_shard *shard, uint32_t lo, uint32_t hi, int first,
                               void *stream);
+/* The same build with the seeds computed once per read instead of once per read and rank (equal-length reads):
+ * alga_ps_shard_seed_keys writes one 12-byte record per read of `shard_words` (n_reads reads at stride_words 32-bit words,
+ * the caller's layout, e.g. this rank's own shard) to `keys` -- {bucket on the prefix side, bucket on the suffix side, the two
+ * 16-bit tags} -- which the caller makes readable by the peers; alga_ps_shard_index_keys inserts, out of the records `keys`
+ * of the reads [lo, hi), the seeds that fall into this rank's slice (first != 0 clears the slice first). */
+int alga_ps_shard_seed_keys(alga_ps_plan *plan, const alga_ps_shard *shard, const uint32_t *shard_words, uint32_t stride_words,
+                            uint32_t n_reads, uint32_t *keys, void *stream);
+int alga_ps_shard_index_keys(alga_ps_plan *plan, const alga_ps_shard *shard, const uint32_t *keys, uint32_t lo, uint32_t hi,
+                             int first, void *stream);
+/* Mean entries per 20-slot bucket of the seed tables built from now on (1 .. 12; 0 = the default, 3).  Sharded builds ship
+ * their table slices over NVLink and may prefer denser tables; call it on every rank before alga_ps_shard_table_bytes. */
+void alga_ps_set_bucket_load(int32_t load);
 int alga_ps_shard_phase1(alga_ps_plan *plan, const alga_ps_shard *shard, void *stream);
 int alga_ps_shard_phase2(alga_ps_plan *plan, const alga_ps_shard *shard, void *stream);
 int alga_ps_shard_csr(alga_ps_plan *plan, const alga_ps_shard *shard, void *stream);

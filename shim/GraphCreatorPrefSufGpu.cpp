@@ -99,9 +99,14 @@ void GraphCreatorPrefSuf::startAlignmentGraphCreation() {
     const char *dev = getenv("ALGA_GPU_DEVICE");
     p.device = dev ? atoi(dev) : 0;
 
+    // ALGA_GPU_DEVICES=<n>: use up to n GPUs of the box (equal-length read sets; anything else runs on one GPU)
+    const char *ndev = getenv("ALGA_GPU_DEVICES");
+    const int n_gpus = ndev ? atoi(ndev) : 1;
+
     alga_csr g;
     alga_timing t;
-    if (alga_gpu_prefsuf_build(&in, &p, &g, &t) != ALGA_OK) {
+    const int rc = n_gpus > 1 ? alga_gpu_prefsuf_build_multi(&in, &p, n_gpus, &g, &t) : alga_gpu_prefsuf_build(&in, &p, &g, &t);
+    if (rc != ALGA_OK) {
         std::cerr << "alga_gpu_prefsuf_build failed: " << alga_gpu_last_error() << std::endl;
         exit(1);
     }
