@@ -40,8 +40,9 @@ def _contigs(path):
     return sorted(min(s, s.translate(comp)[::-1]) for s in seqs)
 
 
-def _run(binary, cwd, args):
-    r = subprocess.run([binary] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+def _run(binary, cwd, args, env=None):
+    r = subprocess.run([binary] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600,
+                       env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stdout[-3000:]
     return r.stdout
 
@@ -71,6 +72,28 @@ def test_contigs_identical_through_reference_driver(gpu, tmp_path, paired, error
             assert "alga_gpu preprocess:" in log, "the GPU preprocess shim did not run"
             if extra:
                 assert "alga_gpu supplement:" in log, "the GPU supplement shim did not run"
+        outs[name] = _contigs(d / "contigs.fasta")
+    assert len(outs["stock"]) > 0
+    assert outs["gpu"] == outs["stock"]
+
+
+@pytest.mark.skipif(not (os.path.isfile(STOCK) and os.path.isfile(GPU)), reason="oracle/_ref binaries not built")
+def test_contigs_identical_with_several_gpus(gpu, tmp_path):
+    """ALGA_GPU_DEVICES=8: the reference's single-process driver on all GPUs of the box through alga_gpu_prefsuf_build_multi
+    (equal-length reads; the second GraphCreatorPrefSuf call, on contigs of ragged lengths, runs on one GPU).  With a single
+    GPU on the box the same call falls back to it."""
+    rng = np.random.default_rng(78)
+    genome = synth.make_genome(120_000, rng)
+    m1, m2 = synth.sample_paired_end(genome, 150, 40, rng, 0.0)
+    outs = {}
+    for name, binary, env in (("stock", STOCK, None), ("gpu", GPU, {"ALGA_GPU_DEVICES": "8"})):
+        d = tmp_path / name
+        d.mkdir()
+        _write_fasta(d / "x_1.fasta", m1)
+        _write_fasta(d / "x_2.fasta", m2)
+        log = _run(binary, d, ["--file1=x_1.fasta", "--file2=x_2.fasta", "--threads=1", "--output=contigs.fasta"], env)
+        if name == "gpu":
+            assert "alga_gpu:" in log, "the GPU shim did not run"
         outs[name] = _contigs(d / "contigs.fasta")
     assert len(outs["stock"]) > 0
     assert outs["gpu"] == outs["stock"]
