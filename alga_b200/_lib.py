@@ -52,7 +52,8 @@ class Shard(C.Structure):
 
 class VerifyParams(C.Structure):
     _fields_ = [("max_offset_pct", C.c_int32), ("min_offset", C.c_int32), ("min_overlap_area", C.c_int32),
-                ("threshold_pct", C.c_int32), ("same_ends", C.c_int32), ("device", C.c_int32)]
+                ("threshold_pct", C.c_int32), ("same_ends", C.c_int32), ("device", C.c_int32), ("lcs_rate_pct", C.c_int32),
+                ("lcs_band", C.c_int32)]
 
 
 class SupParams(C.Structure):

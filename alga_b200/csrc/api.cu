@@ -1231,6 +1231,8 @@ int alga_gpu_pack_reads(const uint8_t *ascii, uint32_t n_reads, uint32_t len_nt,
 int alga_gpu_verify_pairs(const alga_reads *reads, const int32_t *pairs, uint64_t n_pairs,
                           const alga_verify_params *params, uint8_t *verdict) {
     if (!reads || !params || (n_pairs && (!pairs || !verdict))) return fail(ALGA_E_INVALID, "null argument");
+    if (params->lcs_rate_pct > 0 && (params->lcs_band < 0 || params->lcs_band > 8))
+        return fail(ALGA_E_INVALID, "lcs_band must be 0 .. 8 (got %d)", params->lcs_band);
     LaunchCfg cfg;
     CKR(pick_device(params->device, &cfg));
     TmpReads t;
@@ -1241,7 +1243,7 @@ int alga_gpu_verify_pairs(const alga_reads *reads, const int32_t *pairs, uint64_
         CKR(dv.ensure((size_t) (n_pairs ? n_pairs : 1)));
         CK(cudaMemcpy(dp.p, pairs, (size_t) n_pairs * 12, cudaMemcpyHostToDevice));
         VerifyDev V{params->max_offset_pct, params->min_offset, params->min_overlap_area, params->threshold_pct,
-                    params->same_ends};
+                    params->same_ends, params->lcs_rate_pct, params->lcs_band};
         launch_verify_pairs(t.R, dp.as<int32_t>(), n_pairs, V, dv.as<uint8_t>(), 0, cfg);
         CK(cudaGetLastError());
         CK(cudaMemcpy(verdict, dv.p, (size_t) n_pairs, cudaMemcpyDeviceToHost));

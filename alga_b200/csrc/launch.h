@@ -143,6 +143,7 @@ void launch_fingerprints(const ReadsDev &R, int L, uint64_t *pre64, uint32_t *pr
                          uint32_t *suf32, cudaStream_t s, const LaunchCfg &cfg);
 struct VerifyDev {
     int32_t max_offset_pct, min_offset, min_overlap_area, threshold_pct, same_ends;
+    int32_t lcs_rate_pct, lcs_band;  // lcs_rate_pct > 0: pairs the low-error test rejects go on to the banded LCS
 };
 void launch_verify_pairs(const ReadsDev &R, const int32_t *pairs, uint64_t n_pairs, const VerifyDev &V,
                          uint8_t *verdict, cudaStream_t s, const LaunchCfg &cfg);

@@ -154,8 +154,67 @@ verify_pairs_kernel(ReadsDev R, const int32_t *__restrict__ pairs, uint64_t n_pa
                 const int64_t sim = (2 * ov - (int64_t) diff) >> 1;
                 v = 100 * sim >= (int64_t) V.threshold_pct * ov ? 1 : 0;
             }
+            if (ok && !v && V.lcs_rate_pct > 0) v = 2;  // passed the filters, failed the low-error test: on to the banded LCS
             verdict[i] = v;
         }
+    }
+}
+
+// AlignmentControllerLCS::canAlign (AlignmentControllerLCS.cpp:30-59) for the pairs marked 2 above: longest common subsequence
+// inside the band |q - (p - offset)| <= E (calculateLCS :61-150), accepted iff 100 * lcs > rate * overlap.  A row of the
+// band depends on the row before and, cell by cell, on its left neighbour, so one pair is one sequential walk: one THREAD per
+// pair, the two rows of 2E + 3 cells in registers (cells the reference never wrote read as 0 there: its table is a hash map).
+constexpr int kLcsMaxBand = 8;
+__device__ __forceinline__ uint32_t nt_of(const uint32_t *__restrict__ p, int64_t pos) {
+    return (__ldg(p + (pos >> 4)) >> (2 * (pos & 15))) & 3u;
+}
+__global__ void __launch_bounds__(128)
+lcs_pairs_kernel(ReadsDev R, const int32_t *__restrict__ pairs, uint64_t n_pairs, VerifyDev V, uint8_t *__restrict__ verdict) {
+    const int E = V.lcs_band;
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_pairs; i += (uint64_t) gridDim.x * blockDim.x) {
+        if (verdict[i] != 2) continue;
+        const int32_t a = pairs[3 * i], b = pairs[3 * i + 1], off = pairs[3 * i + 2];
+        const int64_t la = R.len[a], lb = R.len[b];
+        const int64_t ov = (la < lb + off ? la : lb + off) - off;
+        const uint32_t *pa = read_ptr(R, (uint32_t) a), *pb = read_ptr(R, (uint32_t) b);
+        int32_t prev[2 * kLcsMaxBand + 3], cur[2 * kLcsMaxBand + 3];  // index d + E + 1, d = q - (p - off)
+#pragma unroll
+        for (int k = 0; k < 2 * kLcsMaxBand + 3; k++) prev[k] = cur[k] = 0;
+        const int64_t p_beg = off - E > 0 ? off - E : 0;
+        const int64_t p_last = la - 1 < lb - 1 + off ? la - 1 : lb - 1 + off;
+        for (int64_t pp = p_beg; pp <= p_last; pp++) {
+            const uint32_t ca = nt_of(pa, pp);
+#pragma unroll
+            for (int k = 0; k < 2 * kLcsMaxBand + 3; k++) {
+                const int d = k - E - 1;
+                int32_t v = 0;
+                if (k >= 1 && k <= 2 * E + 1) {
+                    const int64_t q = pp - off + d;
+                    if (q >= 0 && q <= lb - 1) {
+                        if (ca == nt_of(pb, q)) {
+                            v = (pp > 0 && q > 0) ? prev[k] + 1 : 1;
+                        } else {
+                            if (pp > 0) v = max(v, prev[k + 1 < 2 * kLcsMaxBand + 3 ? k + 1 : k]);
+                            if (q > 0) v = max(v, cur[k - 1]);
+                        }
+                    }
+                }
+                cur[k] = v;
+            }
+#pragma unroll
+            for (int k = 0; k < 2 * kLcsMaxBand + 3; k++) prev[k] = cur[k];
+        }
+        int64_t lcs = 0;
+        if (p_last >= p_beg) {
+            const int64_t q_last = lb - 1 < p_last - off + E ? lb - 1 : p_last - off + E;
+            const int64_t d = q_last - (p_last - off);
+            if (d >= -E && d <= E) {
+#pragma unroll
+                for (int k = 0; k < 2 * kLcsMaxBand + 3; k++)
+                    if (k == (int) d + E + 1) lcs = prev[k];
+            }
+        }
+        verdict[i] = 100 * lcs > (int64_t) V.lcs_rate_pct * ov ? 1 : 0;
     }
 }
 
@@ -203,6 +262,10 @@ void launch_verify_pairs(const ReadsDev &R, const int32_t *pairs, uint64_t n_pai
     if (!n_pairs) return;
     verify_pairs_kernel<<<grid_for(n_pairs, 8, cfg, 8), 256, 0, s>>>(R, pairs, n_pairs, V, verdict);
     bump(cfg);
+    if (V.lcs_rate_pct > 0) {
+        lcs_pairs_kernel<<<grid_for(n_pairs, 128, cfg, 8), 128, 0, s>>>(R, pairs, n_pairs, V, verdict);
+        bump(cfg);
+    }
 }
 
 }  // namespace alga

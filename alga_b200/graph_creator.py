@@ -194,13 +194,15 @@ def pack_reads(ascii_reads: np.ndarray, device: int = 0) -> np.ndarray:
 
 
 def verify_pairs(reads: ReadSet, pairs: np.ndarray, threshold_pct: int, max_offset_pct: int, min_overlap_area: int,
-                 min_offset: int = 0, same_ends: int = 3, device: int = 0) -> np.ndarray:
-    """Batch ``AlignmentControllerHybrid::canAlign`` (AlignmentControllerHybrid.cpp:46-83)."""
+                 min_offset: int = 0, same_ends: int = 3, device: int = 0, lcs_rate_pct: int = 0, lcs_band: int = 2) -> np.ndarray:
+    """Batch ``AlignmentControllerHybrid::canAlign`` (AlignmentControllerHybrid.cpp:46-83).  ``lcs_rate_pct`` > 0 is
+    ``Params::USE_ACLER_INSTEAD_OF_ACLCS = 0`` with that ``MINIMAL_OVERLAP_RATE_FOR_LCS``: pairs the low-error test rejects go on
+    to the banded LCS of ``AlignmentControllerLCS`` (band ``lcs_band`` = ``MAX_ERROR_RATE_FOR_LCS``)."""
     lib = _lib.load()
     pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 3)
     out = np.zeros(pairs.shape[0], np.uint8)
     st = _reads_struct(reads)
-    vp = _lib.VerifyParams(max_offset_pct, min_offset, min_overlap_area, threshold_pct, same_ends, device)
+    vp = _lib.VerifyParams(max_offset_pct, min_offset, min_overlap_area, threshold_pct, same_ends, device, lcs_rate_pct, lcs_band)
     _lib.check(lib.alga_gpu_verify_pairs(C.byref(st), pairs.ctypes.data, pairs.shape[0], C.byref(vp), out.ctypes.data))
     return out
 

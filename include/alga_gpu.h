@@ -233,6 +233,11 @@ typedef struct {
     int32_t threshold_pct;    /* Params::MINIMAL_OVERLAP_FOR_LCS_LOW_ERROR */
     int32_t same_ends;        /* Params::ALIGNMENT_CONTROLLER_SAME_ENDS_LENGTH */
     int32_t device;
+    int32_t lcs_rate_pct;     /* 0: Params::USE_ACLER_INSTEAD_OF_ACLCS = 1, the reference's default (Params.cpp:703): the verdict of
+                                 the low-error test stands.  > 0: USE_ACLER_INSTEAD_OF_ACLCS = 0 and this is
+                                 Params::MINIMAL_OVERLAP_RATE_FOR_LCS: pairs the low-error test rejects go on to the banded LCS of
+                                 AlignmentControllerLCS::canAlign (AlignmentControllerLCS.cpp:30-59, 61-150) */
+    int32_t lcs_band;         /* Params::MAX_ERROR_RATE_FOR_LCS (2): |q - (p - offset)| <= lcs_band; at most 8 */
 } alga_verify_params;
 
 /* pairs: n_pairs x (a, b, offset) int32 triples; verdict[i] = canAlign(reads[a], reads[b], offset).

@@ -65,7 +65,7 @@ def run_prefsuf(reads, min_overlap, rs_min_overlap, min_offset=0, threads=1, wan
     return edges, info
 
 
-def run_verify(reads, pairs, thr, max_offset_pct, min_overlap_area, min_offset=0) -> np.ndarray:
+def run_verify(reads, pairs, thr, max_offset_pct, min_overlap_area, min_offset=0, lcs_rate_pct=0, lcs_band=2) -> np.ndarray:
     """Run the reference's AlignmentControllerHybrid::canAlign on (a, b, offset) triples."""
     if not available():
         raise RuntimeError("oracle/_ref/alga_ref_harness is not built (make -C oracle ref)")
@@ -79,7 +79,8 @@ def run_verify(reads, pairs, thr, max_offset_pct, min_overlap_area, min_offset=0
             f.write(b"ALGP")
             f.write(struct.pack("<Q4i", pairs.shape[0], thr, max_offset_pct, min_overlap_area, min_offset))
             f.write(pairs.tobytes())
-        subprocess.run([HARNESS, "verify", rp, pp, vp], check=True, stdout=subprocess.DEVNULL,
+        extra = [str(lcs_rate_pct), str(lcs_band)] if lcs_rate_pct > 0 else []  # USE_ACLER_INSTEAD_OF_ACLCS = 0
+        subprocess.run([HARNESS, "verify", rp, pp, vp] + extra, check=True, stdout=subprocess.DEVNULL,
                        stderr=subprocess.DEVNULL, cwd=d)
         return np.fromfile(vp, dtype=np.uint8)
 

@@ -42,6 +42,9 @@ typedef struct {
     int32_t min_overlap_area; /* Params::MIN_OVERLAP_AREA */
     int32_t threshold_pct;    /* Params::MINIMAL_OVERLAP_FOR_LCS_LOW_ERROR */
     int32_t same_ends;        /* Params::ALIGNMENT_CONTROLLER_SAME_ENDS_LENGTH (3) */
+    int32_t lcs_rate_pct;     /* 0: USE_ACLER_INSTEAD_OF_ACLCS = 1 (the default); > 0: USE_ACLER_INSTEAD_OF_ACLCS = 0 and this is
+                                 Params::MINIMAL_OVERLAP_RATE_FOR_LCS -- pairs the low-error test rejects go on to the banded LCS */
+    int32_t lcs_band;         /* Params::MAX_ERROR_RATE_FOR_LCS (2) */
 } oracle_verify_params;
 
 void oracle_verify_pairs(const oracle_reads *r, const int32_t *pairs, uint64_t n_pairs,

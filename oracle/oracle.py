@@ -18,7 +18,7 @@ class _Reads(C.Structure):
 
 class _VerifyParams(C.Structure):
     _fields_ = [("max_offset_pct", C.c_int32), ("min_offset", C.c_int32), ("min_overlap_area", C.c_int32),
-                ("threshold_pct", C.c_int32), ("same_ends", C.c_int32)]
+                ("threshold_pct", C.c_int32), ("same_ends", C.c_int32), ("lcs_rate_pct", C.c_int32), ("lcs_band", C.c_int32)]
 
 
 class _SupParams(C.Structure):
@@ -105,11 +105,11 @@ def fingerprints(reads, L):
     return p64, p32, s64, s32
 
 
-def verify_pairs(reads, pairs, threshold_pct, max_offset_pct, min_overlap_area, min_offset=0, same_ends=3):
+def verify_pairs(reads, pairs, threshold_pct, max_offset_pct, min_overlap_area, min_offset=0, same_ends=3, lcs_rate_pct=0, lcs_band=2):
     lib = _load()
     rs = _reads_struct(reads)
     pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 3)
-    vp = _VerifyParams(max_offset_pct, min_offset, min_overlap_area, threshold_pct, same_ends)
+    vp = _VerifyParams(max_offset_pct, min_offset, min_overlap_area, threshold_pct, same_ends, lcs_rate_pct, lcs_band)
     out = np.zeros(pairs.shape[0], np.uint8)
     lib.oracle_verify_pairs(C.byref(rs), pairs.ctypes.data, pairs.shape[0], C.byref(vp), out.ctypes.data)
     return out

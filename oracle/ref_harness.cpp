@@ -152,7 +152,7 @@ int run_prefsuf(const char *in_path, const char *out_path, int threads) {
 // pairs file: "ALGP", u64 n, i32 thr (MINIMAL_OVERLAP_FOR_LCS_LOW_ERROR), i32 max_offset_pct
 // (MAX_OFFSET_CONSIDERED_FOR_ALIGNMENT), i32 min_overlap_area (MIN_OVERLAP_AREA), i32 min_offset,
 // then n x (i32 a, i32 b, i32 off)
-int run_verify(const char *in_path, const char *pairs_path, const char *out_path) {
+int run_verify(const char *in_path, const char *pairs_path, const char *out_path, int lcs_rate = 0, int lcs_band = 2) {
     ReadsFile r = load_reads(in_path);
     Params::THREADS = 1;
     build_reads(r);
@@ -170,6 +170,11 @@ int run_verify(const char *in_path, const char *pairs_path, const char *out_path
     Params::MAX_OFFSET_CONSIDERED_FOR_ALIGNMENT = hp[1];
     Params::MIN_OVERLAP_AREA = hp[2];
     Params::MIN_OFFSET_FOR_ALIGNMENT = hp[3];
+    if (lcs_rate > 0) {  // pairs the low-error test rejects go on to AlignmentControllerLCS (AlignmentControllerHybrid.cpp:72-76)
+        Params::USE_ACLER_INSTEAD_OF_ACLCS = 0;
+        Params::MINIMAL_OVERLAP_RATE_FOR_LCS = lcs_rate;
+        Params::MAX_ERROR_RATE_FOR_LCS = lcs_band;
+    }
     AlignmentControllerHybrid ac;
     std::vector<uint8_t> verdict(n);
     for (uint64_t i = 0; i < n; i++) {
@@ -385,7 +390,8 @@ int main(int argc, char **argv) {
         int threads = argc >= 5 ? atoi(argv[4]) : 1;
         return run_prefsuf(argv[2], argv[3], threads);
     }
-    if (argc >= 5 && strcmp(argv[1], "verify") == 0) return run_verify(argv[2], argv[3], argv[4]);
+    if (argc >= 5 && strcmp(argv[1], "verify") == 0)
+        return run_verify(argv[2], argv[3], argv[4], argc >= 6 ? atoi(argv[5]) : 0, argc >= 7 ? atoi(argv[6]) : 2);
     if (argc >= 4 && strcmp(argv[1], "prefixreads") == 0)
         return run_prefix_reads(argv[2], argv[3], argc >= 5 ? atoi(argv[4]) : 2, argc >= 6 ? atoi(argv[5]) : 1);
     if (argc >= 9 && strcmp(argv[1], "supplement") == 0)
@@ -398,7 +404,7 @@ int main(int argc, char **argv) {
         return run_read_input(argv[2], argv[3], argv[4], argc >= 6 ? atoi(argv[5]) : 1, argc > 6 ? argc - 6 : 0, argv + 6);
     fprintf(stderr,
             "usage: %s prefsuf <reads.algr> <edges.alge|-> [threads]\n"
-            "       %s verify  <reads.algr> <pairs.algp> <verdict.bin>\n"
+            "       %s verify  <reads.algr> <pairs.algp> <verdict.bin> [lcs_rate_pct [lcs_band]]\n"
             "       %s supplement <reads.algr> <edges_in.alge> <edges_out.alge> <min_overlap_area> <max_offset_pct> "
             "<threshold_pct> <kmer_length_bucket> [threads]\n"
             "       %s prefixreads <reads.algr> <mask.bin> [remove_type 1|2] [threads]\n"

@@ -97,6 +97,10 @@ CASES = ["cfg1_small", "cfg2_small", "cfg3_small", "cfg5_small", "varlen", "varl
          "long_reads_rs", "periodic_dups", "periodic", "short_lmin", "tiny", "empty", "all_null"]
 
 
+# (MINIMAL_OVERLAP_RATE_FOR_LCS, MAX_ERROR_RATE_FOR_LCS) settings of the banded-LCS fixtures (the reference's defaults: 95, 2)
+LCS_SETTINGS = [(95, 2), (90, 1), (99, 3), (95, 0)]
+
+
 def verify_case(seed=31, n_reads=4000, genome=20000, read_len=144, error=0.01):
     """Candidate pairs for AlignmentControllerHybrid::canAlign: overlapping same-strand reads with 1 %
     substitutions (true offsets, offsets off by one, random pairs), supplement parameters of config 3

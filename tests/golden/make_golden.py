@@ -29,7 +29,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from oracle import harness  # noqa: E402
-from tests.cases import (CASES, FRONT_CASES, INPUT_CASES, PREPROCESS_CASES, SUPPLEMENT_CASES, TRIANGLE_CASES, build_case,  # noqa: E402
+from tests.cases import (LCS_SETTINGS, CASES, FRONT_CASES, INPUT_CASES, PREPROCESS_CASES, SUPPLEMENT_CASES, TRIANGLE_CASES, build_case,  # noqa: E402
                          front_case, input_case, preprocess_case, supplement_case, triangle_case, verify_case)
 
 
@@ -65,6 +65,14 @@ def main():
     np.savez_compressed(os.path.join(HERE, "verify_pairs.npz"), pairs=pairs, verdict=verdict,
                         input_sha=np.array(input_sha(rs)))
     print(f"verify_pairs: {pairs.shape[0]} pairs, {int(verdict.sum())} accepted")
+    # the same pairs with Params::USE_ACLER_INSTEAD_OF_ACLCS = 0: what the low-error test rejects goes on to the banded LCS
+    # (AlignmentControllerLCS.cpp:30-150), for a few (MINIMAL_OVERLAP_RATE_FOR_LCS, MAX_ERROR_RATE_FOR_LCS) settings
+    lcs = {}
+    for rate, band in LCS_SETTINGS:
+        lcs[f"v_{rate}_{band}"] = harness.run_verify(rs, pairs, vp["threshold_pct"], vp["max_offset_pct"], vp["min_overlap_area"],
+                                                     vp["min_offset"], lcs_rate_pct=rate, lcs_band=band)
+        print(f"verify_pairs_lcs rate {rate} band {band}: {int(lcs[f'v_{rate}_{band}'].sum())} accepted")
+    np.savez_compressed(os.path.join(HERE, "verify_pairs_lcs.npz"), input_sha=np.array(input_sha(rs)), **lcs)
     # error-rate supplement (main.cpp:300-355, --threads=1) on top of the reference's own pre-supplement graph
     for name in SUPPLEMENT_CASES:
         rs, lmin, rsmin, sp = supplement_case(name)

@@ -140,3 +140,17 @@ def test_oracle_prefix_reads_matches_reference_golden(name):
 def test_oracle_prefix_reads_matches_reference_live():
     rs = preprocess_case("pre_varlen")
     assert np.array_equal(oracle.prefix_reads(rs, 2), harness.run_prefix_reads(rs, 2))
+
+
+def test_oracle_banded_lcs_matches_reference_golden():
+    """USE_ACLER_INSTEAD_OF_ACLCS = 0: pairs the low-error test rejects go on to AlignmentControllerLCS (banded LCS)."""
+    from tests.cases import LCS_SETTINGS
+
+    rs, pairs, vp = verify_case()
+    z = np.load(os.path.join(GOLDEN, "verify_pairs_lcs.npz"))
+    base = oracle.verify_pairs(rs, pairs, **vp)
+    for rate, band in LCS_SETTINGS:
+        got = oracle.verify_pairs(rs, pairs, lcs_rate_pct=rate, lcs_band=band, **vp)
+        assert np.array_equal(got, z[f"v_{rate}_{band}"]), (rate, band)
+        assert (got >= base).all()  # the LCS only ever adds verdicts
+    assert int(z["v_95_2"].sum()) > int(base.sum())

@@ -35,6 +35,23 @@ def test_pack_reads_matches_host_packing(gpu, n, ln):
     assert np.array_equal(pack_reads(ascii_), readset.pack_matrix(codes))
 
 
+def test_verify_pairs_banded_lcs_matches_reference(gpu):
+    """alga_gpu_verify_pairs with lcs_rate_pct > 0 (USE_ACLER_INSTEAD_OF_ACLCS = 0): the banded LCS of AlignmentControllerLCS on
+    the pairs the low-error test rejects, against the verdicts of the unmodified reference and the oracle."""
+    import os
+
+    from tests.cases import LCS_SETTINGS
+
+    rs, pairs, vp = verify_case()
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "verify_pairs_lcs.npz"))
+    for rate, band in LCS_SETTINGS:
+        got = verify_pairs(rs, pairs, lcs_rate_pct=rate, lcs_band=band, **vp)
+        assert np.array_equal(got, z[f"v_{rate}_{band}"]), (rate, band)
+        assert np.array_equal(got, oracle.verify_pairs(rs, pairs, lcs_rate_pct=rate, lcs_band=band, **vp))
+    with pytest.raises(Exception):
+        verify_pairs(rs, pairs[:10], lcs_rate_pct=95, lcs_band=9, **vp)
+
+
 def test_verify_pairs_matches_oracle(gpu):
     rs, pairs, vp = verify_case()
     want = oracle.verify_pairs(rs, pairs, **vp)
