@@ -105,6 +105,7 @@ class ShardedPrefSuf:
         # seed tables: every rank fills its slice of the bucket space, the slices are then copied from each other
         tb = self.plan.shard_table_bytes(self.n_total, world)
         self._slice_bytes = tb // world
+        self.table_bytes = tb  # one seed table (bench.py: NVLink accounting)
         self.tp_sym = symm.empty(tb, dtype=torch.uint8, device=device)
         self.ts_sym = symm.empty(tb, dtype=torch.uint8, device=device)
         self._h_tp = symm.rendezvous(self.tp_sym, self.group)

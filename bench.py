@@ -408,6 +408,16 @@ def run_ours(args):
                 "kernel": "whole device pipeline of one step (index + phase1 + phase2 + csr), per GPU",
                 "alg_bytes_per_node": b_alg, "nodes_per_gpu": nodes_per_gpu, "stage_ms": stages, "diag": diag,
                 "traffic_detail": traffic}
+    if world > 1:
+        # what crosses NVLink per rank and step, from the sizes of what is pulled (alga_b200/distributed.py): the other ranks' read
+        # shards, their slices of the two seed tables, the phase-1 edges addressed to this rank (24 B) and the surviving edges
+        # whose source it owns (12 B).  `achieved` divides by the WHOLE step (transfers overlap the kernels), so it is a lower
+        # bound of the rate on the wire.
+        rem = (world - 1) / world
+        nv_bytes = (n_nodes_total * W * 4 * rem + 2 * sp.table_bytes * rem + 3 * nodes_per_gpu * 24 * rem + (n_edges / world) * 12 * rem)
+        roofline["nvlink"] = {"bytes_per_step_per_rank": nv_bytes, "achieved_gbs": nv_bytes / (ms_per_step / 1e3) / 1e9, "peak_gbs": 900.0,
+                              "frac": nv_bytes / (ms_per_step / 1e3) / 1e9 / 900.0,
+                              "note": "read shards + seed-table slices + exchanged edges pulled by one rank, over the whole step time"}
     if world == 1 and stages.get("phase2"):
         # the dominant kernels on their own: algorithmic bytes of their share of the overlap lengths (SURVEY.md 8-d:
         # 64 B per node and length, + the CSR output for phase 2) over their CUDA-event time inside this run
