@@ -27,6 +27,8 @@
 #include <utility>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "../../include/alga_gpu.h"
 #include "launch.h"
 
@@ -150,6 +152,53 @@ struct Kmer {
         return false;
     }
 };
+
+// ---- the k-mers of a pass in the reference's final order, on the device --------------------------------------------------
+// The reference scatters the k-mers into 2^20 hash-range buckets in read / interval order and runs std::sort on every bucket
+// (GraphCreatorKmerBased.cpp:94-106, 139-179, comparator Kmer.cpp:58-64: hash up, position down, read length up).  The bucket
+// number is monotone in the hash, so the order of all k-mers is the order by (hash, position desc, length) -- a stable radix
+// sort -- EXCEPT among k-mers whose three keys tie: where those end up is a property of libstdc++'s introsort applied to the
+// bucket in its fill order.  So: sort on the device, find the buckets that hold a fully tied pair (a few hundred of 10^5
+// groups), and re-sort just those on the host exactly as the reference does (fill order = slot order).
+__host__ __device__ __forceinline__ uint32_t kmer_bucket(uint64_t hash) {  // GraphCreatorKmerBased.cpp:233
+    return (uint32_t) (int) ((1048576ll - 1) * ((double) hash / (double) kMaxHash));
+}
+__global__ void kmer_flags_kernel(const int32_t *__restrict__ ind, uint32_t n_slots, uint32_t *__restrict__ flag) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t) gridDim.x * blockDim.x)
+        flag[i] = ind[i] >= 0 ? 1u : 0u;
+}
+__global__ void kmer_fill_kernel(const uint32_t *__restrict__ ids, const uint64_t *__restrict__ hash, const int32_t *__restrict__ ind,
+                                 const uint32_t *__restrict__ len, uint32_t IV, uint32_t n_slots, const uint32_t *__restrict__ pos,
+                                 Kmer *__restrict__ A, uint64_t *__restrict__ key_lo, uint64_t *__restrict__ key_hi,
+                                 uint32_t *__restrict__ idx) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t) gridDim.x * blockDim.x) {
+        if (ind[i] < 0) continue;
+        const uint32_t p = pos[i], id = ids[i / IV];
+        const Kmer k{id, hash[i], ind[i], len[id]};
+        A[p] = k;
+        key_lo[p] = ((uint64_t) (0xFFFFFFFFu - (uint32_t) k.ind) << 32) | k.read_len;  // position down, read length up
+        key_hi[p] = k.hash;
+        idx[p] = p;
+    }
+}
+__global__ void gather_u64_kernel(const uint64_t *__restrict__ src, const uint32_t *__restrict__ idx, uint32_t n, uint64_t *__restrict__ dst) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) dst[i] = src[idx[i]];
+}
+// B = A in sorted order; buckets that hold two k-mers with equal (hash, position, length) go to `tied` (with repetitions)
+__global__ void kmer_gather_kernel(const Kmer *__restrict__ A, const uint32_t *__restrict__ idx, uint32_t n, Kmer *__restrict__ B,
+                                   uint32_t *__restrict__ tied, uint32_t *n_tied, uint32_t tied_cap) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const Kmer k = A[idx[i]];
+        B[i] = k;
+        if (i > 0) {
+            const Kmer q = A[idx[i - 1]];
+            if (q.hash == k.hash && q.ind == k.ind && q.read_len == k.read_len) {
+                const uint32_t t = atomicAdd(n_tied, 1u);
+                if (t < tied_cap) tied[t] = kmer_bucket(k.hash);
+            }
+        }
+    }
+}
 
 double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -302,21 +351,19 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
     if (d_ids.alloc((size_t) n_ids * 4) || d_hash.alloc((size_t) n_ids * IV * 8) || d_ind.alloc((size_t) n_ids * IV * 4))
         return ALGA_E_NOMEM;
     if (n_ids) SCK(cudaMemcpy(d_ids.p, ids.data(), (size_t) n_ids * 4, cudaMemcpyHostToDevice));
-    std::vector<uint64_t> hh((size_t) n_ids * IV);
-    std::vector<int32_t> hi((size_t) n_ids * IV);
     VerifyDev vd{sp->max_offset_pct, sp->min_offset, sp->min_overlap_area, sp->threshold_pct, sp->same_ends};
 
-    const long long kBucketsSort = 1048576ll;  // GraphCreatorKmerBased.cpp:140
     // Host side, flat: all k-mers of a pass in ONE array ordered by bucket (counting sort that keeps the reference's fill
     // order inside a bucket: reads by id, k-mers by interval), std::sort on each bucket's range -- the same sequence,
     // comparator and algorithm as std::sort on the reference's per-bucket vectors, hence the same tie order.
     Pinned km_buf;                                            // k-mers of the pass, bucket-major (page-locked: it is uploaded)
-    std::vector<uint32_t> bstart((size_t) kBucketsSort + 1);  // bucket -> first k-mer
-    std::vector<uint32_t> kbucket;                            // scratch: bucket of every k-mer in input order
     const int INF = 1000000001;
     const unsigned n_thr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     // pair enumeration on the device: per k-mer x (as i) the range [pair_off[x], pair_off[x + 1]) of its pairs
     Buf d_km, d_cnt, d_poff, d_pj, scan_ws;
+    Buf d_flag, d_pos, d_sort;  // the sort of the k-mers (d_sort: one arena)
+    constexpr uint32_t kTiedCap = 1u << 16;                                    // tied pairs listed per pass (more: found on the host)
+    uint64_t n_tied_buckets = 0;
     Pinned h_poff, h_pj, h_verdict;
     std::vector<uint64_t> bm;                                  // branch markers of one group: D rows of ceil(D/64) words
     struct Group {
@@ -347,51 +394,104 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
         if (int rc = run_li_kmers(R, d_ids.as<uint32_t>(), n_ids, prio, sp->kmer_length, IV, d_hash.as<uint64_t>(),
                                   d_ind.as<int32_t>(), 0, cfg))
             return rc;
-        if (n_ids) {
-            SCK(cudaMemcpy(hh.data(), d_hash.p, hh.size() * 8, cudaMemcpyDeviceToHost));
-            SCK(cudaMemcpy(hi.data(), d_ind.p, hi.size() * 4, cudaMemcpyDeviceToHost));
-        }
+        SCK(cudaDeviceSynchronize());
         gpu_ms += now_ms() - ta;
         t_kmers += now_ms() - ta;
-        // ---- buckets in the reference's fill order, std::sort per bucket
+        // ---- the k-mers in the reference's order: stable radix sort on the device, host re-sort of the buckets with tied keys
         const double tc = now_ms();
-        const double B = (double) kMaxHash;
         const size_t n_slots = (size_t) n_ids * IV;
-        kbucket.resize(n_slots);
-        std::fill(bstart.begin(), bstart.end(), 0u);
-        // bucket of every k-mer (threads over slot ranges) ...
-        run_threads([&](unsigned t) {
-            const size_t s0 = n_slots * t / n_thr, s1 = n_slots * (t + 1) / n_thr;
-            for (size_t slot = s0; slot < s1; slot++)
-                kbucket[slot] = hi[slot] < 0 ? 0xFFFFFFFFu
-                                             : (uint32_t) (int) ((kBucketsSort - 1) * ((double) hh[slot] / B));  // GraphCreatorKmerBased.cpp:233
-        });
-        // ... bucket sizes (threads over bucket ranges: every thread scans all slots and counts its own buckets) ...
-        run_threads([&](unsigned t) {
-            const uint32_t b0 = (uint32_t) ((size_t) kBucketsSort * t / n_thr), b1 = (uint32_t) ((size_t) kBucketsSort * (t + 1) / n_thr);
-            for (size_t slot = 0; slot < n_slots; slot++) {
-                const uint32_t b = kbucket[slot];
-                if (b >= b0 && b < b1) bstart[(size_t) b + 1]++;
-            }
-        });
-        for (size_t k = 0; k < (size_t) kBucketsSort; k++) bstart[k + 1] += bstart[k];
-        const size_t nk = bstart[(size_t) kBucketsSort];
+        size_t nk = 0;
+        Kmer *km = nullptr;
+        if (n_slots) {
+            if (d_flag.alloc(n_slots * 4) || d_pos.alloc((n_slots + 1) * 4) || scan_ws.alloc(scan_workspace_bytes(n_slots))) return ALGA_E_NOMEM;
+            kmer_flags_kernel<<<grid_for(n_slots, 256, cfg, 8), 256>>>(d_ind.as<int32_t>(), (uint32_t) n_slots, d_flag.as<uint32_t>());
+            launch_scan_u32(d_flag.as<uint32_t>(), d_pos.as<uint32_t>(), n_slots, scan_ws.p, 0, cfg);
+            uint32_t nk32 = 0;
+            SCK(cudaMemcpy(&nk32, d_pos.as<uint32_t>() + n_slots, 4, cudaMemcpyDeviceToHost));
+            nk = nk32;
+            launches += 4;
+        }
         if (km_buf.ensure((nk ? nk : 1) * sizeof(Kmer))) return ALGA_E_NOMEM;
-        Kmer *km = km_buf.as<Kmer>();
-        // ... placement in slot order (= the reference's fill order inside a bucket: reads by id, k-mers by interval), again
-        // with every thread scanning all slots for its own bucket range, and std::sort of each bucket
-        run_threads([&](unsigned t) {
-            const uint32_t b0 = (uint32_t) ((size_t) kBucketsSort * t / n_thr), b1 = (uint32_t) ((size_t) kBucketsSort * (t + 1) / n_thr);
-            std::vector<uint32_t> cursor(bstart.begin() + b0, bstart.begin() + b1);
-            for (size_t slot = 0; slot < n_slots; slot++) {
-                const uint32_t b = kbucket[slot];
-                if (b < b0 || b >= b1) continue;
-                const uint32_t id = ids[slot / (size_t) IV];
-                km[cursor[b - b0]++] = Kmer{id, hh[slot], hi[slot], h->len_nt[id]};
+        km = km_buf.as<Kmer>();
+        if (nk) {
+            // one arena for the sort's buffers (every cudaMalloc of this size costs a fraction of a second on the box)
+            size_t tmp_bytes = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint64_t *) nullptr, (uint64_t *) nullptr, (const uint32_t *) nullptr,
+                                            (uint32_t *) nullptr, (int) nk);
+            auto up = [](size_t b) { return (b + 255) & ~(size_t) 255; };
+            const size_t o_kmA = 0, o_k0 = o_kmA + up(nk * sizeof(Kmer)), o_k1 = o_k0 + up(nk * 8), o_k2 = o_k1 + up(nk * 8),
+                         o_i0 = o_k2 + up(nk * 8), o_i1 = o_i0 + up(nk * 4), o_tied = o_i1 + up(nk * 4),
+                         o_cub = o_tied + up(((size_t) kTiedCap + 1) * 4), o_end = o_cub + up(tmp_bytes + 16);
+            if (d_sort.alloc(o_end) || d_km.alloc(nk * sizeof(Kmer))) return ALGA_E_NOMEM;
+            char *const sb = d_sort.as<char>();
+            Kmer *const p_kmA = (Kmer *) (sb + o_kmA);
+            uint64_t *const p_k0 = (uint64_t *) (sb + o_k0), *const p_k1 = (uint64_t *) (sb + o_k1), *const p_k2 = (uint64_t *) (sb + o_k2);
+            uint32_t *const p_i0 = (uint32_t *) (sb + o_i0), *const p_i1 = (uint32_t *) (sb + o_i1), *const p_tied = (uint32_t *) (sb + o_tied);
+            void *const p_cub = sb + o_cub;
+            const double ts0 = now_ms();
+            kmer_fill_kernel<<<grid_for(n_slots, 256, cfg, 8), 256>>>(d_ids.as<uint32_t>(), d_hash.as<uint64_t>(), d_ind.as<int32_t>(), R.len,
+                                                                      (uint32_t) IV, (uint32_t) n_slots, d_pos.as<uint32_t>(), p_kmA, p_k0, p_k1, p_i0);
+            // least significant key first: (position desc, length asc), then the hash; both sorts are stable
+            SCK(cub::DeviceRadixSort::SortPairs(p_cub, tmp_bytes, (const uint64_t *) p_k0, p_k2, (const uint32_t *) p_i0, p_i1, (int) nk));
+            gather_u64_kernel<<<grid_for(nk, 256, cfg, 8), 256>>>(p_k1, p_i1, (uint32_t) nk, p_k0);
+            SCK(cub::DeviceRadixSort::SortPairs(p_cub, tmp_bytes, (const uint64_t *) p_k0, p_k2, (const uint32_t *) p_i1, p_i0, (int) nk));
+            SCK(cudaMemset(p_tied + kTiedCap, 0, 4));
+            kmer_gather_kernel<<<grid_for(nk, 256, cfg, 8), 256>>>(p_kmA, p_i0, (uint32_t) nk, d_km.as<Kmer>(), p_tied, p_tied + kTiedCap, kTiedCap);
+            SCK(cudaGetLastError());
+            launches += 5;
+            if (trace) SCK(cudaDeviceSynchronize());
+            const double ts1 = now_ms();
+            SCK(cudaMemcpy(km, d_km.p, nk * sizeof(Kmer), cudaMemcpyDeviceToHost));
+            const double ts2 = now_ms();
+            uint32_t n_tied = 0;
+            SCK(cudaMemcpy(&n_tied, p_tied + kTiedCap, 4, cudaMemcpyDeviceToHost));
+            std::vector<uint32_t> tied(std::min<uint32_t>(n_tied, kTiedCap));
+            if (!tied.empty()) SCK(cudaMemcpy(tied.data(), p_tied, tied.size() * 4, cudaMemcpyDeviceToHost));
+            std::vector<uint32_t> rank;  // fill-order rank (= position in the unsorted array) of every k-mer, fetched only if needed
+            if (n_tied > kTiedCap) {     // more tied buckets than the list holds: every bucket is suspect
+                tied.clear();
+                for (size_t x = 1; x < nk; x++)
+                    if (km[x].hash == km[x - 1].hash && km[x].ind == km[x - 1].ind && km[x].read_len == km[x - 1].read_len)
+                        tied.push_back(kmer_bucket(km[x].hash));
             }
-            for (size_t k = b0; k < b1; k++)
-                if (bstart[k + 1] - bstart[k] > 1) std::sort(km + bstart[k], km + bstart[k + 1]);
-        });
+            std::sort(tied.begin(), tied.end());
+            tied.erase(std::unique(tied.begin(), tied.end()), tied.end());
+            if (!tied.empty()) {
+                rank.resize(nk);
+                SCK(cudaMemcpy(rank.data(), p_i0, nk * 4, cudaMemcpyDeviceToHost));
+                // (with sequencing errors reads that start at the same position are no duplicates any more but still share
+                // their k-mers: a quarter of the buckets of config 3 hold a tie -- the buckets are small, the threads share them)
+                const Kmer *km_c = km;
+                run_threads([&](unsigned t) {
+                    std::vector<std::pair<uint32_t, Kmer>> tmp;
+                    const size_t z0 = tied.size() * t / n_thr, z1 = tied.size() * (t + 1) / n_thr;
+                    for (size_t z = z0; z < z1; z++) {
+                        const uint32_t bkt = tied[z];
+                        // the bucket's range in the sorted array (the bucket number is monotone in the hash)
+                        size_t lo = 0, hi = nk;
+                        while (lo < hi) {
+                            const size_t mid = (lo + hi) / 2;
+                            if (kmer_bucket(km_c[mid].hash) < bkt) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        size_t e = lo;
+                        while (e < nk && kmer_bucket(km_c[e].hash) == bkt) e++;
+                        tmp.clear();
+                        for (size_t x = lo; x < e; x++) tmp.emplace_back(rank[x], km_c[x]);
+                        std::sort(tmp.begin(), tmp.end(),
+                                  [](const std::pair<uint32_t, Kmer> &a, const std::pair<uint32_t, Kmer> &b) { return a.first < b.first; });
+                        for (size_t x = lo; x < e; x++) km[x] = tmp[x - lo].second;  // the bucket as the reference fills it
+                        std::sort(km + lo, km + e);                                   // ... and sorts it (GraphCreatorKmerBased.cpp:99)
+                    }
+                });
+                SCK(cudaMemcpy(d_km.p, km, nk * sizeof(Kmer), cudaMemcpyHostToDevice));  // the re-sorted buckets, in one go
+            }
+            n_tied_buckets += tied.size();
+            if (trace)
+                fprintf(stderr, "alga_gpu supplement pass %d sort: alloc %.1f ms, device sort %.1f ms, read-back %.1f ms, %u tied (%zu buckets) fixed in %.1f ms\n",
+                        pass, ts0 - tc, ts1 - ts0, ts2 - ts1, n_tied, tied.size(), now_ms() - ts2);
+        }
+        gpu_ms += now_ms() - tc;
         t_sort += now_ms() - tc;
         // ---- every pair that passes the static filters (:43-62), on the device: count per k-mer, scan, fill
         const double td = now_ms();
@@ -402,7 +502,7 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
                 scan_ws.alloc(scan_workspace_bytes(nk)) || h_poff.ensure((nk + 1) * 8))
                 return ALGA_E_NOMEM;
             const double tq0 = now_ms();
-            SCK(cudaMemcpy(d_km.p, km, nk * sizeof(Kmer), cudaMemcpyHostToDevice));
+            // (the sorted k-mers are on the device already)
             const double tq1 = now_ms();
             const int grid = grid_for(nk, 128, cfg, 16);
             enumerate_pairs_kernel<false><<<grid, 128>>>(d_km.as<Kmer>(), (uint32_t) nk, pf_params, d_cnt.as<uint32_t>(), nullptr,
@@ -499,9 +599,9 @@ int supplement_impl(const alga_reads *h, const alga_csr *gin, const alga_sup_par
         grp.clear();
         std::fill(last_level.begin(), last_level.end(), 0u);
         uint32_t n_levels = 0;
-        for (size_t k = 0; k < (size_t) kBucketsSort && n_pairs; k++) {
-            size_t p = bstart[k], q = p;
-            const size_t end = bstart[k + 1];
+        if (n_pairs) {  // groups = runs of equal hash (a run never spans two of the reference's buckets: the bucket follows from the hash)
+            size_t p = 0, q = 0;
+            const size_t end = nk;
             while (p < end) {
                 while (q < end && km[q].hash == km[p].hash) q++;
                 if (q - p > 1 && pair_off[q - 1] > pair_off[p]) {  // the last k-mer of a group never plays i

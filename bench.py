@@ -459,7 +459,7 @@ def run_ours(args):
         g2 = li.startAlignmentGraphCreation()
         supplement = {"ms": 1e3 * (time.perf_counter() - ts), "edges_before": int(g.n_edges), "edges_after": int(g2.n_edges),
                       "params": sp, **li.timing,
-                      "note": "alga_gpu_supplement: LI k-mers, pair enumeration and canAlign on the GPU, bucket sort + ordered replay on the host"}
+                      "note": "alga_gpu_supplement: LI k-mers, pair enumeration and canAlign on the GPU, k-mer sort on the GPU (tied buckets re-sorted on the host), ordered replay on the host"}
 
     triangles = None
     if legs_ok and args.with_triangles:

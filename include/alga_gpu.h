@@ -250,9 +250,10 @@ int alga_gpu_verify_pairs(const alga_reads *reads, const int32_t *pairs, uint64_
  * dead-end reads of the graph produced by alga_gpu_prefsuf_build, four passes with rotated nucleotide priorities,
  * followed by Graph::retainOnlySmallestOffset (main.cpp:346).  LI k-mer extraction (Read.cpp:145-226) and all canAlign
  * calls (AlignmentControllerHybrid.cpp:46-83) run on the GPU, and so does the enumeration of the candidate pairs with the
- * static filters of GraphCreatorPairwiseKmerBranch.cpp:43-62; the bucket sort and the order-dependent edge replay
- * (GraphCreatorKmerBased.cpp:94-136, GraphCreatorPairwiseKmerBranch.cpp:64-97) run on the host with libstdc++'s
- * std::sort, so ties inside a bucket fall exactly as in a reference built with the same toolchain. */
+ * static filters of GraphCreatorPairwiseKmerBranch.cpp:43-62.  The sort of the k-mers (GraphCreatorKmerBased.cpp:94-101)
+ * is a stable radix sort on the GPU; only the hash-range buckets that hold k-mers tied in every key are put back into the
+ * reference's fill order and sorted with libstdc++'s std::sort on the host, so ties fall exactly as in a reference built
+ * with the same toolchain.  The order-dependent edge replay (GraphCreatorPairwiseKmerBranch.cpp:64-97) runs on the host. */
 typedef struct {
     int32_t max_offset_pct;     /* Params::MAX_OFFSET_CONSIDERED_FOR_ALIGNMENT = (1 - SCALE) * avg_len / 2 (main.cpp:335) */
     int32_t min_offset;         /* Params::MIN_OFFSET_FOR_ALIGNMENT */

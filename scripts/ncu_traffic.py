@@ -6,6 +6,7 @@ builds -> profiles/traffic_r2.json: DRAM bytes and time per kernel of ONE build 
 """
 import collections
 import csv
+import re
 import json
 import sys
 
@@ -13,7 +14,7 @@ path, workload, scale, n_gpus = sys.argv[1], sys.argv[2], float(sys.argv[3]), in
 rows = list(csv.DictReader([l for l in open(path) if not l.startswith("==")]))
 launches = collections.OrderedDict()  # launch id -> {name, metrics}
 for r in rows:
-    e = launches.setdefault(r["ID"], {"name": r["Kernel Name"].replace("unnamed>::", ""), "m": {}})
+    e = launches.setdefault(r["ID"], {"name": re.sub(r"^(void )?alga::(<unnamed>::)?", "", r["Kernel Name"]), "m": {}})
     v = float(r["Metric Value"].replace(",", ""))
     u = r["Metric Unit"]
     if r["Metric Name"] == "gpu__time_duration.sum":

@@ -5,7 +5,7 @@
 // (include/GraphCreators/GraphCreatorLI.h:14-38 -- constructor, createAlignmentsForKmers, startAlignmentGraphCreation;
 // setAlignFrom / setAlignTo are inline in the header and forward to `graphCreator`) keeps its name and signature, so
 // main.cpp:306-350 runs unchanged.  This file contains no algorithm: it gathers vector<Read*> and Graph::V into the
-// layouts of include/alga_gpu.h, calls alga_gpu_supplement (LI k-mers and canAlign on the GPU, bucket sort and ordered
+// layouts of include/alga_gpu.h, calls alga_gpu_supplement (LI k-mers, their sort and canAlign on the GPU, ordered
 // edge replay on the host) and copies the returned rows into Graph::V.
 //
 // Contract reproduced from the reference (file:line in /root/reference):

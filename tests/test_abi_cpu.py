@@ -35,7 +35,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.PsParams) == 28
     assert C.sizeof(_lib.Csr) == 48
     assert C.sizeof(_lib.Timing) == 48 + 64
-    assert C.sizeof(_lib.VerifyParams) == 24
+    assert C.sizeof(_lib.VerifyParams) == 32  # + lcs_rate_pct, lcs_band
     assert C.sizeof(_lib.InputParams) == 24
     assert C.sizeof(_lib.ReadSetOut) == 88
     assert C.sizeof(_lib.DriverParams) == 40
