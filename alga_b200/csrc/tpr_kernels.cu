@@ -109,9 +109,12 @@ __device__ __forceinline__ uint64_t seed_window(const uint32_t *own, const PsDev
 
 // The walk over the overlap lengths l_hi, l_hi - 1, ... l_lo of one read, cut into runs of lengths whose seed windows have
 // the same minimizer (= the same bucket): run k starts at length l_hi - first[k] and uses bucket bk[k].  All lanes step
-// through their lengths together: the kNM scrambled m-mers of the current window sit in registers (slot = position mod
-// kNM, static because the loop is unrolled by kNM), a step replaces one of them and takes the minimum of all -- no
-// data-dependent rescan, so no lane waits for another one's.  Returns the number of runs (may exceed kMaxRuns: the
+// through their lengths together: the kNM scrambled m-mers of the current window sit in registers, oldest first; a step
+// shifts them down by one, appends the m-mer that enters the window and takes the minimum of all -- no data-dependent
+// rescan, so no lane waits for another one's.  ONE rolled loop does the first window and the steps: the version unrolled
+// by kNM (m-mers in fixed slots, no shifting) was a third of the instructions either phase kernel keeps hot -- 10 KB of
+// 35 KB -- and the kernels were bound by instruction fetch (32 KB instruction cache per SM; ncu r2f: 19 % of the fetches of
+// phase 2 missed it and kept the GPC's instruction cache 93 % busy).  Returns the number of runs (may exceed kMaxRuns: the
 // caller gives the read up); the table of the warp is indexed [k * 32 + lane].
 template <bool UP>
 __device__ __forceinline__ int find_runs(const uint32_t *own, const PsDev &P, const SeedTable &T, uint32_t len, int32_t l_hi,
@@ -119,46 +122,38 @@ __device__ __forceinline__ int find_runs(const uint32_t *own, const PsDev &P, co
     const int n_len = on ? l_hi - l_lo + 1 : 0;
     const int n_max = warp_max(n_len);
     const uint32_t m = T.min_m;
-    const int32_t s0 = UP ? (int32_t) len - l_hi : l_hi - P.seed_nt;  // first nucleotide of the window of length l_hi
-    auto mmer = [&](int32_t pos) { return scrambled_mmer(sbits64(own, 2u * (uint32_t) pos), 0, m); };
+    // m-mer i of the walk: the window of length l_hi holds i = 0 .. kNM - 1, step t brings in i = kNM - 1 + t and drops i = t - 1.
+    // UP (phase 1): the window starts at len - l_hi and moves up; else (phase 2): it ends at l_hi and moves down
+    const int32_t p0 = UP ? (int32_t) len - l_hi : l_hi - P.seed_nt + kNM - 1;
     uint32_t H[kNM];
-    // slot j: UP -- position s0 + j (the window moves up: at step t position s0 + t - 1 leaves, it sits in slot (t - 1) % kNM);
-    //         else -- position s0 + kNM - 1 - j (the window moves down: position s0 - t + kNM leaves, slot (t - 1) % kNM)
 #pragma unroll
-    for (int j = 0; j < kNM; j++) H[j] = on ? mmer(UP ? s0 + j : s0 + kNM - 1 - j) : 0u;
-    auto ring_min = [&]() {  // a tree, not a chain: the minimum is on the critical path of every step
-        uint32_t v[kNM];
-#pragma unroll
-        for (int j = 0; j < kNM; j++) v[j] = H[j];
-#pragma unroll
-        for (int w = 1; w < kNM; w <<= 1)
-#pragma unroll
-            for (int j = 0; j + w < kNM; j += 2 * w) v[j] = min(v[j], v[j + w]);
-        return v[0];
-    };
-    uint32_t prev = ring_min();
+    for (int j = 0; j < kNM; j++) H[j] = 0xFFFFFFFFu;
+    uint32_t prev = 0;
     int n_runs = 0;
-    if (on) {
-        run_bk[lane] = bucket_of(mix64((uint64_t) prev), T.n_buckets);
-        run_first[lane] = 0;
-        n_runs = 1;
-    }
-    for (int tb = 0; tb * kNM + 1 < n_max; tb++) {
+#pragma unroll 1
+    for (int i = 0; i < kNM - 1 + n_max; i++) {
+        const int t = i - (kNM - 1);
+        const bool act = n_len > 0 && t < n_len;
+        const int32_t pos = act ? (UP ? p0 + i : p0 - i) : 0;
+        const uint32_t hm = scrambled_mmer(sbits64(own, 2u * (uint32_t) pos), 0, m);
 #pragma unroll
-        for (int j = 0; j < kNM; j++) {
-            const int t = tb * kNM + j + 1;
-            if (t < n_max) {  // the same for all lanes
-                const bool act = t < n_len;
-                if (act) H[j] = mmer(UP ? s0 + t + kNM - 1 : s0 - t);
-                const uint32_t v = ring_min();
-                if (act && v != prev) {
-                    prev = v;
-                    if (n_runs < kMaxRuns) {
-                        run_bk[n_runs * 32 + lane] = bucket_of(mix64((uint64_t) v), T.n_buckets);
-                        run_first[n_runs * 32 + lane] = (uint8_t) t;
-                    }
-                    n_runs++;
+        for (int j = 0; j + 1 < kNM; j++) H[j] = H[j + 1];
+        H[kNM - 1] = hm;
+        if (t >= 0) {  // the same for all lanes
+            uint32_t v[kNM];  // a tree, not a chain: the minimum is on the critical path of every step
+#pragma unroll
+            for (int j = 0; j < kNM; j++) v[j] = H[j];
+#pragma unroll
+            for (int w = 1; w < kNM; w <<= 1)
+#pragma unroll
+                for (int j = 0; j + w < kNM; j += 2 * w) v[j] = min(v[j], v[j + w]);
+            if (act && (t == 0 || v[0] != prev)) {
+                prev = v[0];
+                if (n_runs < kMaxRuns) {
+                    run_bk[n_runs * 32 + lane] = bucket_of(mix64((uint64_t) v[0]), T.n_buckets);
+                    run_first[n_runs * 32 + lane] = (uint8_t) t;
                 }
+                n_runs++;
             }
         }
     }
@@ -572,7 +567,9 @@ phase1_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
                         r.o = (int32_t) so[k];
                         r.t = overhang_tail_own(own, so[k]);
                         if (pos[k] < out.row_cap) {
-                            out.rows[(uint64_t) (c - out.c_base) * out.row_cap + pos[k]] = r;
+                            // one 16-byte store = one request (the member-wise copy was two 8-byte stores: ncu r2f, 340 M requests)
+                            *reinterpret_cast<uint4 *>(out.rows + (uint64_t) (c - out.c_base) * out.row_cap + pos[k]) =
+                                make_uint4((uint32_t) r.b, (uint32_t) r.o, (uint32_t) r.t, (uint32_t) (r.t >> 32));
                         } else {
                             const uint32_t i = atomicAdd(out.n_list, 1u);
                             if (i < out.list_cap) {
