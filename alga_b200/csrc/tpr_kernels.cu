@@ -34,6 +34,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "launch.h"
 
@@ -59,7 +60,10 @@ constexpr int kRowFast = 32;  // longest transposed row the fast phase-2 kernel 
 constexpr int kDepth = 2;     // runs (= buckets) in flight per lane
 constexpr int kStageSlotWords = 8 * 32 * 4;             // one staging slot of a warp: [piece][lane] x 16 bytes = 32 buckets
 constexpr int kStageWords = kDepth * kStageSlotWords;   // per warp
-constexpr int kMaxRuns = 16;   // runs per read the fast kernels keep (reads with more go to the generic kernels)
+#ifndef ALGA_MAXRUNS
+#define ALGA_MAXRUNS 16
+#endif
+constexpr int kMaxRuns = ALGA_MAXRUNS;   // runs per read the fast kernels keep (reads with more go to the generic kernels)
 constexpr int kRunWords = kMaxRuns * 32 + kMaxRuns * 8;  // per warp: bucket [kMaxRuns][32] (u32) + first length index [kMaxRuns][32] (u8)
 
 inline int warp_tile_grid(uint64_t n_items, const LaunchCfg &cfg, int blocks_per_sm) {
@@ -214,6 +218,17 @@ __device__ __forceinline__ uint32_t match_mask(const BucketTags &b, uint64_t h) 
     }
     return acc;
 }
+// Rare path, kept out of line (inlined, the twenty compare-and-call sites of probe_seed_at sit in the middle of the hottest loop
+// of either kernel): the reads in the bucket chain from bk on whose tag matches that of h -> ids[0 .. min(n, cap)); returns n.
+__device__ __noinline__ int chain_matches(SeedTable T, uint64_t h, uint32_t bk, uint32_t *ids, int cap) {
+    int n = 0;
+    probe_seed_at(T, h, bk, [&](uint32_t id) {
+        if (n < cap) ids[n] = id;
+        n++;
+    });
+    return n;
+}
+
 // The reads behind a match mask -- and behind the chain of the bucket, if it overflowed -- : ids in c[0 .. min(n, MAXM)),
 // largest first (the order of arrival inside one overlap length, seen backwards).  n > MAXM: the caller gives up.
 // (MAXM = reads that share a K-nucleotide seed and overlap at one length, i.e. start at the same position: 2 in the first
@@ -235,7 +250,11 @@ __device__ __forceinline__ void collect_matches(const SeedTable &T, const Bucket
         mask &= mask - 1;
         add(staged_id(slot, ((bit & 15) << 1) | (bit >> 4), lane));
     }
-    if (b.cnt > (uint32_t) kBucketCap) probe_seed_at(T, h, next_bucket(T, bk), add);  // rare: plain loads
+    if (b.cnt > (uint32_t) kBucketCap) {  // rare: plain loads
+        uint32_t ids[MAXM + 1];
+        const int m = chain_matches(T, h, next_bucket(T, bk), ids, MAXM + 1);
+        for (int i = 0; i < m && i < MAXM + 1; i++) add(ids[i]);
+    }
     if (n > 1 && n <= MAXM) {  // unused slots hold 0 and sink to the end (n says how many are real)
         if (MAXM == 2) {
             order_desc(c[0], c[1]);
@@ -337,31 +356,36 @@ __device__ __forceinline__ bool verify_own_prefix_aligned(const ReadsDev &R, con
     const uint32_t *pb = R.words + (uint64_t) cand * R.stride;
     const int32_t nb = 2 * L, sh2 = 2 * (int32_t) o;
     const int32_t n_words = (sh2 + nb + 31) >> 5;  // candidate words that hold compared bits
-    for (int32_t s0 = 0; s0 < n_words; s0 += 16) {  // two sectors per round, both requested before the first compare
-        uint32_t g[2][8];
-        load8_na(pb + s0, g[0]);
-        if (s0 + 8 < n_words) load8_na(pb + s0 + 8, g[1]);
+    // one sector per round, the next one requested before this one is compared (one compare block in the code: the kernels
+    // are short of instruction cache: find_runs)
+    uint32_t g[8], gn[8];
+    load8_na(pb, g);
+#pragma unroll 1
+    for (int32_t s0 = 0; s0 < n_words; s0 += 8) {
+        const bool more = s0 + 8 < n_words;
+        if (more) load8_na(pb + s0 + 8, gn);
         uint32_t diff = 0;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int32_t p = 32 * (s0 + 8 * h + j) - sh2;  // own-read bit that meets bit 0 of this candidate word
-                if (s0 + 8 * h < n_words && p + 32 > 0 && p < nb) {
-                    uint32_t cw, mask = 0xFFFFFFFFu;
-                    if (p >= 0) {
-                        const uint32_t w = (uint32_t) p >> 5;
-                        cw = __funnelshift_r(own[w], own[w + 1], (uint32_t) p & 31u);
-                    } else {
-                        cw = own[0] << (uint32_t) (-p);
-                        mask <<= (uint32_t) (-p);
-                    }
-                    if (nb - p < 32) mask &= (1u << (uint32_t) (nb - p)) - 1u;
-                    diff |= (g[h][j] ^ cw) & mask;
+        for (int j = 0; j < 8; j++) {
+            const int32_t p = 32 * (s0 + j) - sh2;  // own-read bit that meets bit 0 of this candidate word
+            if (p + 32 > 0 && p < nb) {
+                uint32_t cw, mask = 0xFFFFFFFFu;
+                if (p >= 0) {
+                    const uint32_t w = (uint32_t) p >> 5;
+                    cw = __funnelshift_r(own[w], own[w + 1], (uint32_t) p & 31u);
+                } else {
+                    cw = own[0] << (uint32_t) (-p);
+                    mask <<= (uint32_t) (-p);
                 }
+                if (nb - p < 32) mask &= (1u << (uint32_t) (nb - p)) - 1u;
+                diff |= (g[j] ^ cw) & mask;
             }
         }
         if (diff) return false;
+        if (more) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) g[j] = gn[j];
+        }
     }
     return true;
 }
@@ -764,7 +788,12 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
                         mask &= mask - 1;
                         push(staged_id(slot, ((bit & 15) << 1) | (bit >> 4), r));
                     }
-                    if (bt.cnt > (uint32_t) kBucketCap) probe_seed_at(T, h, next_bucket(T, run_bk[kc * 32 + r]), push);  // rare
+                    if (bt.cnt > (uint32_t) kBucketCap) {  // rare
+                        uint32_t ids[8];
+                        const int m = chain_matches(T, h, next_bucket(T, run_bk[kc * 32 + r]), ids, 8);
+                        if (m > 8) ctl[32 + r] = 1u;  // the generic kernel takes the read
+                        for (int i = 0; i < m && i < 8; i++) push(ids[i]);
+                    }
                 }
             }
             __syncwarp();  // nobody reads this slot any more
@@ -797,6 +826,7 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
             // FAST: the first 64 bits of every queued read (all its overhang tail needs), one 8-byte request each, all in
             // flight together; they land in the staging area, which the probe no longer needs
             if (FAST) {
+#pragma unroll 1
                 for (int k = 0; k < q_top; k++)
                     if (k < qn && !hard) cp_async8(q_t + k * 32, R.words + (uint64_t) q_id[k * 32] * R.stride);
                 cp_async_wait_all();
@@ -911,6 +941,7 @@ phase2_tpr_kernel(ReadsDev R, SeedTable T, PsDev P, uint32_t lo, uint32_t hi, co
                 int cnt[kSurv];
 #pragma unroll
                 for (int s = 0; s < kSurv; s++) cnt[s] = 0;
+#pragma unroll 1
                 for (int k = 0; k < qn; k++) {
                     const uint32_t v = q_id[k * 32];
 #pragma unroll

@@ -11,7 +11,8 @@ KEYS = ['Kernel Name', 'Grid Size', 'Block Size', 'gpu__time_duration.sum', 'dra
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__thread_inst_executed_per_inst_executed.ratio',
         'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum',
         'lts__t_sectors_srcunit_tex_op_read.sum', 'lts__t_sectors_srcunit_tex_op_read_lookup_hit.sum',
-        'lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum']
+        'lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum', 'sm__icc_requests.sum', 'sm__icc_request_hit_rate.pct',
+        'gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed']
 
 
 def main(path):
