@@ -145,7 +145,7 @@ struct alga_ps_plan {
     DevBuf slots;  // sector-aligned copy of a fixed-stride, equal-length read set (alga_ps_plan_run), what the fast kernels read
     // workspace
     DevBuf stats_d, counters_d, tp, ts, rows, over, list1, hard1, hard1b, spill_queue2, indeg, rev_off, rev, triples, triples1, outdeg, scan_ws,
-        spill_queue, caps, spill_off, spill_store, row_off, nbr, off, big_rows, tmp_nbr, tmp_off;
+        spill_queue, caps, spill_off, spill_store, row_off, nbr, off, big_rows, tmp_nbr, tmp_off, sort_ws[3];  // sort_ws: prefix index, suffix index, CSR
     uint32_t over_cap = 0;
     uint32_t row_cap = kRowCapDefault;  // ALGA_PS_ROW_CAP (testing: small rows force the overflow paths)
     SeedTable Tp{}, Ts{};
@@ -166,7 +166,7 @@ struct alga_ps_plan {
     ~alga_ps_plan() {
         DevBuf *all[] = {&words, &word_off, &len, &from, &to, &slots, &stats_d, &counters_d, &tp, &ts, &rows, &over, &list1, &hard1, &hard1b, &spill_queue2, &indeg, &rev_off, &rev,
                          &triples, &triples1, &outdeg, &scan_ws, &spill_queue, &caps, &spill_off, &spill_store, &row_off,
-                         &nbr, &off, &big_rows, &tmp_nbr, &tmp_off};
+                         &nbr, &off, &big_rows, &tmp_nbr, &tmp_off, &sort_ws[0], &sort_ws[1], &sort_ws[2]};
         for (DevBuf *b : all) b->release();
         h_row_off.release();
         h_nbr.release();
@@ -292,6 +292,13 @@ int stage_index_begin(alga_ps_plan *plan, cudaStream_t s, cudaStream_t s2 = null
     return ALGA_OK;
 }
 
+// The index build and the CSR assembly by sorting (sorted_stages.cu) instead of by random atomics; ALGA_PS_SORTED=0 keeps the
+// scatter kernels (A/B, and the path the sharded build still takes).
+bool sorted_stages() {
+    static const bool on = !(getenv("ALGA_PS_SORTED") && atoi(getenv("ALGA_PS_SORTED")) == 0);
+    return on;
+}
+
 int stage_index(alga_ps_plan *plan, cudaStream_t s) {
     CKR(stage_index_begin(plan, s));
     launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, 0, plan->R.n, 0u, 0xFFFFFFFFu, s, plan->cfg);
@@ -397,10 +404,47 @@ int build_rev_from_counts(alga_ps_plan *plan, uint32_t n_targets, cudaStream_t s
     return ALGA_OK;
 }
 
+// rows in place (unsorted), their total on its way into *plan->h_u64: sort every row by (neighbour, offset), publish the result
+int finish_csr(alga_ps_plan *plan, uint32_t lo, uint32_t hi, uint64_t n_tr, cudaStream_t s) {
+    const uint32_t n = hi - lo;
+    Counters *dc = plan->counters_d.as<Counters>();
+    CK(cudaMemsetAsync(&dc->n_big, 0, 4, s));
+    launch_sort_rows(plan->row_off.as<uint64_t>(), n, plan->nbr.as<int32_t>(), plan->off.as<int32_t>(),
+                     plan->big_rows.as<uint32_t>(), &dc->n_big, s, plan->cfg);
+    CK(cudaGetLastError());
+    CKR(read_counters(plan, s));
+    if (plan->h_counters->n_big) {
+        CKR(plan->tmp_nbr.ensure((size_t) n_tr * 4));
+        CKR(plan->tmp_off.ensure((size_t) n_tr * 4));
+        launch_sort_big_rows(plan->row_off.as<uint64_t>(), plan->big_rows.as<uint32_t>(), plan->h_counters->n_big,
+                             plan->nbr.as<int32_t>(), plan->off.as<int32_t>(), plan->tmp_nbr.as<int32_t>(),
+                             plan->tmp_off.as<int32_t>(), s, plan->cfg);
+        CK(cudaGetLastError());
+    }
+    if (plan->h_counters->n_big) CK(cudaStreamSynchronize(s));
+    plan->n_edges = *plan->h_u64;
+    plan->res_lo = lo;
+    plan->res_hi = hi;
+    return ALGA_OK;
+}
+
 // outdeg_ready: plan->outdeg already holds the row sizes, indexed by global read id
 int stage_csr(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int32_t *triples, uint64_t n_tr, int swap,
               bool outdeg_ready, cudaStream_t s) {
     const uint32_t n = hi - lo;
+    if (sorted_stages() && n_tr < 0x7FFFFFFFull) {
+        // rows by sorting the edges on their source: sequential traffic instead of one atomic + one random store per edge
+        CKR(plan->row_off.ensure(((size_t) n + 1) * 8));
+        CKR(plan->nbr.ensure((size_t) (n_tr ? n_tr : 1) * 4));
+        CKR(plan->off.ensure((size_t) (n_tr ? n_tr : 1) * 4));
+        CKR(plan->big_rows.ensure((size_t) (n ? n : 1) * 4));
+        CKR(plan->sort_ws[2].ensure(sorted_csr_workspace_bytes(n_tr)));
+        if (launch_sorted_csr(triples, n_tr, lo, hi, swap, plan->sort_ws[2].p, plan->row_off.as<uint64_t>(), plan->nbr.as<int32_t>(),
+                              plan->off.as<int32_t>(), s, plan->cfg))
+            return fail(ALGA_E_CUDA, "CSR: radix sort failed");
+        CKR(plan_peek(plan, plan->h_u64, plan->row_off.as<uint64_t>() + n, 8, s));  // read with the counters
+        return finish_csr(plan, lo, hi, n_tr, s);
+    }
     CKR(plan->outdeg.ensure((size_t) (plan->R.n ? plan->R.n : 1) * 4));
     uint32_t *outdeg = plan->outdeg.as<uint32_t>();
     if (!outdeg_ready) {
@@ -424,25 +468,7 @@ int stage_csr(alga_ps_plan *plan, uint32_t lo, uint32_t hi, const int32_t *tripl
         launch_scatter_csr(triples, n_tr, lo, hi, swap, plan->row_off.as<uint64_t>(), outdeg, plan->nbr.as<int32_t>(),
                            plan->off.as<int32_t>(), s, plan->cfg);
     }
-    Counters *dc = plan->counters_d.as<Counters>();
-    CK(cudaMemsetAsync(&dc->n_big, 0, 4, s));
-    launch_sort_rows(plan->row_off.as<uint64_t>(), n, plan->nbr.as<int32_t>(), plan->off.as<int32_t>(),
-                     plan->big_rows.as<uint32_t>(), &dc->n_big, s, plan->cfg);
-    CK(cudaGetLastError());
-    CKR(read_counters(plan, s));
-    if (plan->h_counters->n_big) {
-        CKR(plan->tmp_nbr.ensure((size_t) n_tr * 4));
-        CKR(plan->tmp_off.ensure((size_t) n_tr * 4));
-        launch_sort_big_rows(plan->row_off.as<uint64_t>(), plan->big_rows.as<uint32_t>(), plan->h_counters->n_big,
-                             plan->nbr.as<int32_t>(), plan->off.as<int32_t>(), plan->tmp_nbr.as<int32_t>(),
-                             plan->tmp_off.as<int32_t>(), s, plan->cfg);
-        CK(cudaGetLastError());
-    }
-    if (plan->h_counters->n_big) CK(cudaStreamSynchronize(s));
-    plan->n_edges = *plan->h_u64;
-    plan->res_lo = lo;
-    plan->res_hi = hi;
-    return ALGA_OK;
+    return finish_csr(plan, lo, hi, n_tr, s);
 }
 
 }  // namespace
@@ -942,8 +968,17 @@ int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
         CK(cudaEventRecord(plan->ev_fork, s));
         CK(cudaStreamWaitEvent(plan->side, plan->ev_fork, 0));
         CKR(stage_index_begin(plan, s, plan->side));
-        launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, 0, n, 0u, 0xFFFFFFFFu, s, plan->cfg, 1);
-        launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, 0, n, 0u, 0xFFFFFFFFu, plan->side, plan->cfg, 2);
+        if (sorted_stages() && n < 0x7FFFFFFFu) {
+            const size_t wsb = sorted_index_workspace_bytes(n);
+            CKR(plan->sort_ws[0].ensure(wsb));
+            CKR(plan->sort_ws[1].ensure(wsb));
+            if (launch_sorted_index(plan->R, plan->P, plan->Tp, 0, n, plan->sort_ws[0].p, s, plan->cfg) ||
+                launch_sorted_index(plan->R, plan->P, plan->Ts, 1, n, plan->sort_ws[1].p, plan->side, plan->cfg))
+                return fail(ALGA_E_CUDA, "seed index: radix sort failed");
+        } else {
+            launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, 0, n, 0u, 0xFFFFFFFFu, s, plan->cfg, 1);
+            launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, 0, n, 0u, 0xFFFFFFFFu, plan->side, plan->cfg, 2);
+        }
         CK(cudaGetLastError());
         CK(cudaEventRecord(plan->ev_join, plan->side));
         plan->index_valid = true;
@@ -970,7 +1005,7 @@ int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
         CK(cudaEventRecord(plan->ev_stage[2], s));
         // phase 2 with fused out-degree counting (not in the reversed-result corner)
         CKR(plan->outdeg.ensure((size_t) (n ? n : 1) * 4));
-        const bool fuse_outdeg = !plan->swap_direction;
+        const bool fuse_outdeg = !plan->swap_direction && !sorted_stages();  // (the sorted CSR needs no row sizes)
         const RowsView view{plan->indeg.as<uint32_t>(), plan->rows.as<RevEntry>(), plan->row_cap, &dc->n_over,
                             plan->over.as<Edge1>(), plan->rev_off.as<uint32_t>(), plan->rev.as<RevEntry>()};
         CKR(run_phase2(plan, 0, n, view, fuse_outdeg ? plan->outdeg.as<uint32_t>() : nullptr, s));

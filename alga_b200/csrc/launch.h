@@ -110,6 +110,16 @@ void launch_phase2_spill(const ReadsDev &R, const SeedTable &suffix, const PsDev
                          const uint32_t *queue, uint32_t n_queue, const uint64_t *spill_off, uint32_t *spill_store,
                          const Phase2Out &out, cudaStream_t s, const LaunchCfg &cfg);
 
+// --- the scatter-shaped stages done by sorting (sorted_stages.cu): seed index of one side (0 = prefix table, 1 = suffix table) over
+// the reads [0, n), into a cleared table; CSR rows [lo, hi) (+ row_off, unsorted inside a row) out of n triples.  n < 2^31 each;
+// `ws` = *_workspace_bytes() of scratch.  Return 0 or a cudaError_t of the sort.
+size_t sorted_index_workspace_bytes(uint32_t n_reads);
+int launch_sorted_index(const ReadsDev &R, const PsDev &P, const SeedTable &T, int side, uint32_t n, void *ws, cudaStream_t s,
+                        const LaunchCfg &cfg);
+size_t sorted_csr_workspace_bytes(uint64_t n_edges);
+int launch_sorted_csr(const int32_t *triples, uint64_t n, uint32_t lo, uint32_t hi, int swap, void *ws, uint64_t *row_off,
+                      int32_t *nbr, int32_t *off, cudaStream_t s, const LaunchCfg &cfg);
+
 // --- CSR assembly -----------------------------------------------------------------------------
 void launch_count_sources(const int32_t *triples, uint64_t n, uint32_t lo, uint32_t hi, int swap, uint32_t *outdeg,
                           cudaStream_t s, const LaunchCfg &cfg);

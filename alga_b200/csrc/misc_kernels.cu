@@ -219,15 +219,22 @@ lcs_pairs_kernel(ReadsDev R, const int32_t *__restrict__ pairs, uint64_t n_pairs
 }
 
 // Aligned copy of a fixed-stride read set: read i -> out[i * stride_out .. + words), zero up to the stride.  One thread
-// per output word: loads and stores are coalesced (consecutive threads, consecutive addresses on both sides up to the
-// stride change).
+// per 16 bytes of output (stride_out is a multiple of 8 words, `out` 16-byte aligned): four 4-byte loads -- consecutive
+// threads, consecutive addresses up to the stride change -- and one 16-byte store.
 __global__ void repack_reads_kernel(const uint32_t *__restrict__ in, uint32_t stride_in, uint32_t words, uint64_t n_reads,
                                     uint32_t *__restrict__ out, uint32_t stride_out) {
-    const uint64_t total = n_reads * stride_out;
+    const uint32_t q_per_read = stride_out >> 2;
+    const uint64_t total = n_reads * q_per_read;
     for (uint64_t j = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; j < total; j += (uint64_t) gridDim.x * blockDim.x) {
-        const uint64_t i = j / stride_out;
-        const uint32_t w = (uint32_t) (j - i * stride_out);
-        out[j] = w < words ? __ldg(in + i * stride_in + w) : 0u;
+        const uint64_t i = j / q_per_read;
+        const uint32_t w = (uint32_t) (j - i * q_per_read) << 2;
+        const uint32_t *p = in + i * stride_in + w;
+        uint4 v;
+        v.x = w < words ? __ldg(p) : 0u;
+        v.y = w + 1 < words ? __ldg(p + 1) : 0u;
+        v.z = w + 2 < words ? __ldg(p + 2) : 0u;
+        v.w = w + 3 < words ? __ldg(p + 3) : 0u;
+        reinterpret_cast<uint4 *>(out)[j] = v;
     }
 }
 
@@ -236,7 +243,7 @@ __global__ void repack_reads_kernel(const uint32_t *__restrict__ in, uint32_t st
 void launch_repack_reads(const uint32_t *in, uint32_t stride_in, uint32_t words, uint64_t n_reads, uint32_t *out,
                          uint32_t stride_out, cudaStream_t s, const LaunchCfg &cfg) {
     if (!n_reads) return;
-    repack_reads_kernel<<<grid_for(n_reads * stride_out, 256, cfg, 8), 256, 0, s>>>(in, stride_in, words, n_reads, out, stride_out);
+    repack_reads_kernel<<<grid_for(n_reads * (stride_out >> 2), 256, cfg, 8), 256, 0, s>>>(in, stride_in, words, n_reads, out, stride_out);
     bump(cfg);
 }
 

@@ -3,7 +3,7 @@
 name=$1; flags=$2
 cd "$(dirname "$0")/../alga_b200/csrc" || exit 1
 mkdir -p build_$name
-for f in api prefsuf_kernels tpr_kernels misc_kernels supplement preprocess input simplify multi; do
+for f in api prefsuf_kernels tpr_kernels misc_kernels supplement preprocess input simplify multi sorted_stages; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -Xptxas -v $flags -c $f.cu -o build_$name/$f.o 2> build_$name/$f.log &
 done
 wait
