@@ -1945,6 +1945,23 @@ int alga_gpu_cut_triangles(const alga_csr *gin, int32_t max_offset, int32_t devi
         CKR(w.big.ensure((size_t) n * 4));
         CKR(w.nbig.ensure(4));
         CK(cudaEventRecord(w.e0, 0));
+        // the marking kernel bisects row a for neighbour b: rows sorted by (neighbour, offset).  A graph built here arrives that
+        // way, the OUTPUT of this call -- sorted by (offset, neighbour) -- or a reference graph after sortEdgesByIncreasingOffset
+        // does not: sort the device copy first (the decision per entry does not depend on the order inside a row, and the
+        // result is sorted by (offset, neighbour) below whatever came in).  No-op pass for sorted rows.
+        CK(cudaMemsetAsync(w.nbig.p, 0, 4, 0));
+        launch_sort_rows(w.row.as<uint64_t>(), n, w.nbr.as<int32_t>(), w.off.as<int32_t>(), w.big.as<uint32_t>(), w.nbig.as<uint32_t>(), 0, cfg);
+        {
+            uint32_t n_big_in = 0;
+            CK(cudaMemcpy(&n_big_in, w.nbig.p, 4, cudaMemcpyDeviceToHost));
+            if (n_big_in) {
+                CKR(w.tn.ensure((size_t) E * 4));
+                CKR(w.to.ensure((size_t) E * 4));
+                launch_sort_big_rows(w.row.as<uint64_t>(), w.big.as<uint32_t>(), n_big_in, w.nbr.as<int32_t>(), w.off.as<int32_t>(),
+                                     w.tn.as<int32_t>(), w.to.as<int32_t>(), 0, cfg);
+                CK(cudaGetLastError());
+            }
+        }
         launch_triangle_marks(w.row.as<uint64_t>(), w.nbr.as<int32_t>(), w.off.as<int32_t>(), n, max_offset, w.keep.as<uint8_t>(),
                               w.kept.as<uint32_t>(), 0, cfg);
         launch_scan_u64(w.kept.as<uint32_t>(), w.new_row.as<uint64_t>(), n, w.scan_ws.p, 0, cfg);

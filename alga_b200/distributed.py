@@ -12,6 +12,8 @@ libalga_gpu.so.
 """
 from __future__ import annotations
 
+import os
+
 import time
 
 import numpy as np
@@ -77,7 +79,7 @@ class ShardedPrefSuf:
     """
 
     def __init__(self, min_overlap, rs_min_overlap, min_offset, max_len_cap, device, rank, world, len_nt, n_shard, words_per_read,
-                 group=None, n_total=None, bucket_load=None):
+                 group=None, n_total=None, bucket_load=None, seed_keys=None):
         import torch.distributed._symmetric_memory as symm
 
         self.rank, self.world = rank, world
@@ -123,7 +125,22 @@ class ShardedPrefSuf:
         self._len = torch.full((self.n_total,), len_nt, dtype=torch.int32, device=device)
         self._reads = DeviceReads.from_tensors(self._full, self._len, stride=self.S, n=self.n_total, max_len=len_nt)
         self.plan.bind_uniform(self._reads, len_nt)
-        self._copy_stream = torch.cuda.Stream(device=device)
+        # seed records: every rank computes bucket and tag of the two seeds of ITS reads once and the peers pull the 12-byte records
+        # with the shard, instead of every rank deriving the minimizers of all reads for its slice (world times the work).
+        # Measured (config 4, r2): 54.6 against 54.9 ms on 2 GPUs, 19.0 against 18.0 ms on 8 -- the stage is bound by the pulls, and the
+        # records add a third to them -- so it is OFF unless asked for (ALGA_SHARD_SEED_KEYS=1).
+        if seed_keys is None:
+            seed_keys = os.environ.get("ALGA_SHARD_SEED_KEYS") == "1"
+        self.seed_keys = bool(seed_keys)
+        if self.seed_keys:
+            self.keys_sym = symm.empty(n_shard * 3, dtype=torch.int32, device=device)
+            self._h_keys = symm.rendezvous(self.keys_sym, self.group)
+            self._peer_keys = [self._h_keys.get_buffer(p, (n_shard * 3,), torch.int32) for p in range(world)]
+            self._keys = torch.empty(world * n_shard * 3, dtype=torch.int32, device=device)  # landing zone of the pulls
+        # pulls over NVLink are DMA copies on a copy stream, one at a time.  Cutting every pull into chunks on several streams
+        # (several copy engines) was measured and is SLOWER when all GPUs pull at once: 8 GPUs, config 4: 18.0 ms with one stream,
+        # 19.5 with two, 22.4 with four (2 GPUs: 54.5 / 55.8 with four).  ALGA_SHARD_COPY_STREAMS=<n> for experiments.
+        self._copy_streams = [torch.cuda.Stream(device=device) for _ in range(max(1, int(os.environ.get("ALGA_SHARD_COPY_STREAMS", "1"))))]
         self._ev = None
         self._launches = 0
         torch.cuda.synchronize(device)
@@ -140,38 +157,52 @@ class ShardedPrefSuf:
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         n, W = self.n_shard, self.W
         marks[0].record()
-        self._h_shard.barrier()  # every rank's shard is in place (and nobody still reads the previous one)
-        self._copy_stream.wait_stream(main)
+        if self.seed_keys:
+            self._h_shard.barrier()  # nobody still reads the previous build's records
+            lo_own, hi_own = min(self.rank * n, self.n_total), min((self.rank + 1) * n, self.n_total)
+            self._stage(lambda: self.plan.shard_seed_keys(self._shard, self.shard_sym, W, hi_own - lo_own, self.keys_sym))
+        self._h_shard.barrier()  # every rank's shard (and its seed records) in place, and nobody still reads the previous one
+        for st in self._copy_streams:
+            st.wait_stream(main)
+        pulls = []
+        for k in range(self.world):  # all pulls are queued at once, peer by peer; the main stream follows them
+            p = (self.rank + k) % self.world
+            evs = []
+            if self.seed_keys:
+                evs += self._pull(self._keys[p * n * 3:(p + 1) * n * 3], self._peer_keys[p])
+            evs += self._pull(self._compact[p * n * W:(p + 1) * n * W], self._peer_shards[p])  # DMA over NVLink, contiguous on both sides
+            pulls.append(evs)
         for k in range(self.world):
             p = (self.rank + k) % self.world
             stage = self._compact[p * n * W:(p + 1) * n * W]
-            ev = torch.cuda.Event()
-            with torch.cuda.stream(self._copy_stream):
-                stage.copy_(self._peer_shards[p], non_blocking=True)  # DMA over NVLink, contiguous on both sides
-                ev.record()
-            main.wait_event(ev)
+            for ev in pulls[k]:
+                main.wait_event(ev)
             self._slots[p * n:(p + 1) * n, :W].copy_(stage.view(n, W))  # local: into the sector-aligned read slots
             # seeds of the arrived shard that fall into this rank's slice of the bucket space
-            self._stage(lambda: self.plan.shard_index_range(self._shard, min(p * n, self.n_total), min((p + 1) * n, self.n_total),
-                                                             first=(k == 0)))
+            lo_p, hi_p = min(p * n, self.n_total), min((p + 1) * n, self.n_total)
+            if self.seed_keys:
+                self._stage(lambda: self.plan.shard_index_keys(self._shard, self._keys[p * n * 3:], lo_p, hi_p, first=(k == 0)))
+            else:
+                self._stage(lambda: self.plan.shard_index_range(self._shard, lo_p, hi_p, first=(k == 0)))
         self._h_ws.barrier()  # every rank's slice is complete
         marks[1].record()
         ev_slices = torch.cuda.Event()
         ev_slices.record(main)
-        ev_tp, ev_ts = torch.cuda.Event(), torch.cuda.Event()
         sb = self._slice_bytes
-        with torch.cuda.stream(self._copy_stream):
-            self._copy_stream.wait_event(ev_slices)
-            for tabs, mine, ev in ((self._peer_tp, self.tp_sym, ev_tp), (self._peer_ts, self.ts_sym, ev_ts)):
-                for k in range(1, self.world):
-                    p = (self.rank + k) % self.world
-                    mine[p * sb:(p + 1) * sb].copy_(tabs[p][p * sb:(p + 1) * sb], non_blocking=True)
-                ev.record()
-        main.wait_event(ev_tp)  # the suffix table keeps arriving while phase 1 runs
+        for st in self._copy_streams:
+            st.wait_event(ev_slices)
+        ev_tp, ev_ts = [], []
+        for tabs, mine, evs in ((self._peer_tp, self.tp_sym, ev_tp), (self._peer_ts, self.ts_sym, ev_ts)):
+            for k in range(1, self.world):
+                p = (self.rank + k) % self.world
+                evs += self._pull(mine[p * sb:(p + 1) * sb], tabs[p][p * sb:(p + 1) * sb])
+        for ev in ev_tp:
+            main.wait_event(ev)  # the suffix table keeps arriving while phase 1 runs
         self._stage(lambda: self.plan.shard_phase1(self._shard))
         marks[2].record()
         self._h_ws.barrier()
-        main.wait_event(ev_ts)
+        for ev in ev_ts:
+            main.wait_event(ev)
         self._stage(lambda: self.plan.shard_phase2(self._shard))
         marks[3].record()
         self._h_ws.barrier()
@@ -181,6 +212,23 @@ class ShardedPrefSuf:
         self._ev = marks
         self._launches = self.plan.stats()["kernel_launches"]
         self._raise_together()
+
+    def _pull(self, dst: torch.Tensor, src: torch.Tensor) -> list:
+        """dst <- src (1-D, the same length, src in a peer's memory), in chunks spread over the copy streams; -> their events."""
+        total = dst.numel()
+        c = len(self._copy_streams)
+        step = ((total + c - 1) // c + 1023) & ~1023
+        evs = []
+        for i, st in enumerate(self._copy_streams):
+            lo, hi = i * step, min(total, (i + 1) * step)
+            if lo >= hi:
+                break
+            with torch.cuda.stream(st):
+                dst[lo:hi].copy_(src[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+            evs.append(ev)
+        return evs
 
     def _stage(self, fn):
         """A stage that fails on ONE rank (e.g. ALGA_E_CAPACITY) must not leave the others waiting at the next barrier:

@@ -414,7 +414,7 @@ def run_ours(args):
         # whose source it owns (12 B).  `achieved` divides by the WHOLE step (transfers overlap the kernels), so it is a lower
         # bound of the rate on the wire.
         rem = (world - 1) / world
-        nv_bytes = (n_nodes_total * W * 4 * rem + 2 * sp.table_bytes * rem + 3 * nodes_per_gpu * 24 * rem + (n_edges / world) * 12 * rem)
+        nv_bytes = (n_nodes_total * (W * 4 + (12 if sp.seed_keys else 0)) * rem + 2 * sp.table_bytes * rem + 3 * nodes_per_gpu * 24 * rem + (n_edges / world) * 12 * rem)
         roofline["nvlink"] = {"bytes_per_step_per_rank": nv_bytes, "achieved_gbs": nv_bytes / (ms_per_step / 1e3) / 1e9, "peak_gbs": 900.0,
                               "frac": nv_bytes / (ms_per_step / 1e3) / 1e9 / 900.0,
                               "note": "read shards + seed-table slices + exchanged edges pulled by one rank, over the whole step time"}

@@ -44,3 +44,24 @@ def test_cut_triangles_thresholds_and_long_rows(gpu):
     e2 = harness.sort_edges(np.array(rows, np.int32))
     got = GraphSimplifier(graph_of(e2, 120), 250).cutNonAndWeaklyMetricTriangles().edges()
     assert np.array_equal(got, oracle.cut_triangles(e2, 120, 250))
+
+
+def test_cut_triangles_takes_rows_in_any_order(gpu):
+    """The output of a call is sorted by (offset, neighbour); fed back in -- or a reference graph after
+    sortEdgesByIncreasingOffset -- it must give what the oracle gives for the same edge set (the rows are re-sorted on the device)."""
+    e, n, mx = triangle_case("tri_periodic", GOLD)
+    first = GraphSimplifier(graph_of(e, n), mx).cutNonAndWeaklyMetricTriangles()
+    e1 = first.edges()
+    again = GraphSimplifier(first, mx).cutNonAndWeaklyMetricTriangles().edges()  # rows by (offset, neighbour) going in
+    assert np.array_equal(again, oracle.cut_triangles(harness.sort_edges(e1), n, mx))
+    # rows shuffled arbitrarily
+    rng = np.random.default_rng(5)
+    g = graph_of(e, n)
+    nbr, off = g.nbr.copy(), g.off.copy()
+    for i in range(n):
+        s, t = int(g.row_off[i]), int(g.row_off[i + 1])
+        if t - s > 1:
+            p = rng.permutation(t - s)
+            nbr[s:t], off[s:t] = nbr[s:t][p], off[s:t][p]
+    got = GraphSimplifier(Graph(n, g.row_off, nbr, off), mx).cutNonAndWeaklyMetricTriangles().edges()
+    assert np.array_equal(got, oracle.cut_triangles(e, n, mx))
