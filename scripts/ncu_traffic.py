@@ -14,7 +14,7 @@ path, workload, scale, n_gpus = sys.argv[1], sys.argv[2], float(sys.argv[3]), in
 rows = list(csv.DictReader([l for l in open(path) if not l.startswith("==")]))
 launches = collections.OrderedDict()  # launch id -> {name, metrics}
 for r in rows:
-    e = launches.setdefault(r["ID"], {"name": re.sub(r"^(void )?alga::(<unnamed>::)?", "", r["Kernel Name"]), "m": {}})
+    e = launches.setdefault(r["ID"], {"name": re.sub(r"^(void )?(alga::(<unnamed>::)?|CUB_[0-9]+_SM_[0-9]+::)?", "", r["Kernel Name"]), "m": {}})
     v = float(r["Metric Value"].replace(",", ""))
     u = r["Metric Unit"]
     if r["Metric Name"] == "gpu__time_duration.sum":
@@ -23,7 +23,8 @@ for r in rows:
         v = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0) * v  # -> bytes
     e["m"][r["Metric Name"]] = v
 seq = list(launches.values())
-ours = ("repack_reads", "build_index", "phase1_", "phase2_", "rebuild_rows", "over_to_csr", "rows_to_csr", "scan_", "end_cursor",
+ours = ("repack_reads", "build_index", "seed_records", "fill_buckets", "chain_overflow", "csr_records", "csr_rows", "DeviceRadixSort",
+        "phase1_", "phase2_", "rebuild_rows", "over_to_csr", "rows_to_csr", "scan_", "end_cursor",
         "scatter_", "split_pairs", "sort_rows", "sort_big_rows", "count_sources", "peek", "read_stats")
 starts = [i for i, e in enumerate(seq) if e["name"].startswith("repack_reads")]
 if len(starts) < 2:
