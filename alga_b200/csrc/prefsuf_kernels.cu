@@ -156,9 +156,9 @@ __global__ void __launch_bounds__(256) pull_rows_kernel(PeerSegs ps, Phase1Out o
             if (i < count) {
                 const uint32_t ci = (uint32_t) e[j].c - out.c_base;
                 if (pos[j] < out.row_cap) {
-                    RevEntry r;
-                    r.b = e[j].b, r.o = e[j].o, r.t = e[j].t;
-                    out.rows[(uint64_t) ci * out.row_cap + pos[j]] = r;
+                    // one 16-byte store = one request (a member-wise copy of the entry is two)
+                    *reinterpret_cast<uint4 *>(out.rows + (uint64_t) ci * out.row_cap + pos[j]) =
+                        make_uint4((uint32_t) e[j].b, (uint32_t) e[j].o, (uint32_t) e[j].t, (uint32_t) (e[j].t >> 32));
                 } else {
                     const uint32_t k = atomicAdd(out.n_list, 1u);
                     if (k < out.list_cap) {
