@@ -267,8 +267,8 @@ typedef struct {
 } alga_sup_params;
 /* graph_in: Graph::V after main.cpp:291 (host CSR); graph_out: Graph::V after main.cpp:346 (malloc'ed host CSR, release
  * with alga_gpu_free_csr).  timing (may be NULL): h2d_ms, device_ms (kernels + their transfers), total_ms,
- * kernel_launches; stage_ms[0..4] = LI k-mers, bucket scatter + sort (host), pair enumeration, canAlign batch, ordered replay (host)
- * (summed over the four passes); stage_ms[5] = dead-end reads that took part, stage_ms[6] = pairs verified, stage_ms[7] =
+ * kernel_launches; stage_ms[0..4] = LI k-mers, sort of the k-mers (device radix sort + host re-sort of the tied buckets),
+ * pair enumeration, canAlign batch, ordered replay (host) (summed over the four passes); stage_ms[5] = dead-end reads that took part, stage_ms[6] = pairs verified, stage_ms[7] =
  * dependency levels of the replay (groups of k-mers that share no source read run in parallel, level after level). */
 int alga_gpu_supplement(const alga_reads *reads, const alga_csr *graph_in, const alga_sup_params *params,
                         alga_csr *graph_out, alga_timing *timing);
