@@ -760,13 +760,14 @@ int alga_ps_shard_index_range(alga_ps_plan *plan, const alga_ps_shard *sh, uint3
     plan->Tp.slots = (uint32_t *) sh->table_prefix;
     plan->Ts.slots = (uint32_t *) sh->table_suffix;
     const uint32_t slice = plan->Tp.slice, b_lo = (uint32_t) sh->rank * slice, b_hi = b_lo + slice;
-    if (first) {
-        plan->launches = 0;
+    const int which = ((first >> 1) & 3) ? ((first >> 1) & 3) : 3;  // bit 0: prefix table, bit 1: suffix table
+    if (first & 1) {
+        if (which & 1) plan->launches = 0;
         const size_t off = (size_t) b_lo * kBucketWords * 4, bytes = (size_t) slice * kBucketWords * 4;
-        CK(cudaMemsetAsync((char *) sh->table_prefix + off, 0, bytes, s));
-        CK(cudaMemsetAsync((char *) sh->table_suffix + off, 0, bytes, s));
+        if (which & 1) CK(cudaMemsetAsync((char *) sh->table_prefix + off, 0, bytes, s));
+        if (which & 2) CK(cudaMemsetAsync((char *) sh->table_suffix + off, 0, bytes, s));
     }
-    launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, lo, hi, b_lo, b_hi, s, plan->cfg);
+    launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, lo, hi, b_lo, b_hi, s, plan->cfg, which);
     CK(cudaGetLastError());
     plan->index_valid = true;
     return ALGA_OK;

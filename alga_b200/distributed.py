@@ -132,6 +132,10 @@ class ShardedPrefSuf:
         if seed_keys is None:
             seed_keys = os.environ.get("ALGA_SHARD_SEED_KEYS") == "1"
         self.seed_keys = bool(seed_keys)
+        # ALGA_SHARD_PREFIX_FIRST=1: the prefix slices are finished and exchanged first, the suffix slices filled meanwhile in a pass of
+        # their own (phase 1 needs the prefix table only).  Measured: 54.65 against 54.68 ms on 2 GPUs, 18.4 against 17.9 on 8 -- the
+        # second pass over the reads costs what the earlier exchange saves -- so it is off.
+        self.prefix_first = os.environ.get("ALGA_SHARD_PREFIX_FIRST", "0") == "1"
         if self.seed_keys:
             self.keys_sym = symm.empty(n_shard * 3, dtype=torch.int32, device=device)
             self._h_keys = symm.rendezvous(self.keys_sym, self.group)
@@ -182,20 +186,32 @@ class ShardedPrefSuf:
             lo_p, hi_p = min(p * n, self.n_total), min((p + 1) * n, self.n_total)
             if self.seed_keys:
                 self._stage(lambda: self.plan.shard_index_keys(self._shard, self._keys[p * n * 3:], lo_p, hi_p, first=(k == 0)))
-            else:
-                self._stage(lambda: self.plan.shard_index_range(self._shard, lo_p, hi_p, first=(k == 0)))
-        self._h_ws.barrier()  # every rank's slice is complete
-        marks[1].record()
-        ev_slices = torch.cuda.Event()
-        ev_slices.record(main)
+            else:  # prefix_first: the prefix slice only -- the suffix slice is filled while the prefix slices travel
+                self._stage(lambda: self.plan.shard_index_range(self._shard, lo_p, hi_p, first=(k == 0),
+                                                                 which=1 if self.prefix_first else 0))
         sb = self._slice_bytes
-        for st in self._copy_streams:
-            st.wait_event(ev_slices)
         ev_tp, ev_ts = [], []
-        for tabs, mine, evs in ((self._peer_tp, self.tp_sym, ev_tp), (self._peer_ts, self.ts_sym, ev_ts)):
+
+        def exchange(tabs, mine, evs):
+            ev_done = torch.cuda.Event()
+            ev_done.record(main)
+            for st in self._copy_streams:
+                st.wait_event(ev_done)
             for k in range(1, self.world):
                 p = (self.rank + k) % self.world
                 evs += self._pull(mine[p * sb:(p + 1) * sb], tabs[p][p * sb:(p + 1) * sb])
+
+        self._h_ws.barrier()  # every rank's (prefix) slice is complete
+        if self.prefix_first and not self.seed_keys:
+            exchange(self._peer_tp, self.tp_sym, ev_tp)
+            self._stage(lambda: self.plan.shard_index_range(self._shard, 0, self.n_total, first=True, which=2))
+            self._h_ws.barrier()  # every rank's suffix slice is complete
+            marks[1].record()
+            exchange(self._peer_ts, self.ts_sym, ev_ts)
+        else:
+            marks[1].record()
+            exchange(self._peer_tp, self.tp_sym, ev_tp)
+            exchange(self._peer_ts, self.ts_sym, ev_ts)
         for ev in ev_tp:
             main.wait_event(ev)  # the suffix table keeps arriving while phase 1 runs
         self._stage(lambda: self.plan.shard_phase1(self._shard))

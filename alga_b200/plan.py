@@ -167,8 +167,9 @@ class PrefSufPlan:
     def shard_table_bytes(self, n_total: int, world: int) -> int:
         return int(self.lib.alga_ps_shard_table_bytes(n_total, world))
 
-    def shard_index_range(self, sh: _lib.Shard, lo: int, hi: int, first: bool):
-        _lib.check(self.lib.alga_ps_shard_index_range(self._h, C.byref(sh), lo, hi, 1 if first else 0, self._stream()))
+    def shard_index_range(self, sh: _lib.Shard, lo: int, hi: int, first: bool, which: int = 0):
+        """which: 0 = both tables, 1 = the prefix table only, 2 = the suffix table only (alga_gpu.h)."""
+        _lib.check(self.lib.alga_ps_shard_index_range(self._h, C.byref(sh), lo, hi, (1 if first else 0) | (which << 1), self._stream()))
 
     def shard_seed_keys(self, sh: _lib.Shard, shard_words: torch.Tensor, stride: int, n_reads: int, keys: torch.Tensor):
         """12-byte seed records of this rank's own reads (``shard_words``: their packed words at ``stride`` words per read)."""

@@ -170,8 +170,10 @@ typedef struct {
 } alga_ps_shard;
 uint64_t alga_ps_shard_ws_bytes(uint32_t n_shard, int32_t world);
 /* Sharded index build: the bucket space of each table is cut into `world` slices; rank r inserts -- out of the reads
- * [lo, hi) of the (replicated) read set -- the seeds that fall into slice r of ITS copy of the tables (first != 0
- * clears that slice first).  When every rank has inserted all reads, slice r of rank r's tables is final and the
+ * [lo, hi) of the (replicated) read set -- the seeds that fall into slice r of ITS copy of the tables.  `first`: bit 0 set =
+ * clear the slice(s) first; bits 1-2 = which table: 0 both, 1 the prefix table only, 2 the suffix table only (a driver that
+ * finishes the prefix slices first can exchange them while the suffix slices are still being filled: phase 1 needs the
+ * prefix table only).  When every rank has inserted all reads, slice r of rank r's tables is final and the
  * ranks copy each other's slices (bytes [r, r+1) * table_bytes / world of the table buffers); the plan then probes
  * the caller's tables.  Replaces alga_ps_stage_index_range for sharded runs: no rank inserts more than its share. */
 uint64_t alga_ps_shard_table_bytes(uint32_t n_total, int32_t world);

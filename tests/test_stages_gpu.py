@@ -197,7 +197,7 @@ def test_row_overflow_list_regrows(gpu, monkeypatch):
 
 @pytest.mark.parametrize("name", ["cfg2_small", "cfg1_small", "cfg5_small"])
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
-@pytest.mark.parametrize("use_keys", [False, True])
+@pytest.mark.parametrize("use_keys", [False, True, "split"])  # "split": prefix slices first, then the suffix slices in one pass
 def test_sharded_peer_exchange_emulated_ranks(gpu, name, world, use_keys):
     """alga_ps_shard_* with the ranks emulated one after another on one GPU: every rank has its own exchange workspace
     (an ordinary device buffer here, peer-mapped symmetric memory in alga_b200/distributed.py), phase 1 appends to the
@@ -221,17 +221,21 @@ def test_sharded_peer_exchange_emulated_ranks(gpu, name, world, use_keys):
     shards = [plan.shard_struct(r, world, n_shard, n, [w.data_ptr() for w in ws], tp[r].data_ptr(), ts[r].data_ptr())
               for r in range(world)]
     bounds = [min(n, r * n_shard) for r in range(world + 1)]
-    if use_keys:  # the seeds of every read computed once, by its owner (12-byte records), and inserted from the records
+    if use_keys is True:  # the seeds of every read computed once, by its owner (12-byte records), and inserted from the records
         W = dr.stride
         keys = [torch.zeros(max(1, bounds[q + 1] - bounds[q]) * 3, dtype=torch.int32, device=dev) for q in range(world)]
         for q in range(world):
             plan.shard_seed_keys(shards[q], dr.words[bounds[q] * W:], W, bounds[q + 1] - bounds[q], keys[q])
     for r in range(world):  # every rank fills its slice of the bucket space, the reads arriving in pieces
         for q in range(world):
-            if use_keys:
+            if use_keys is True:
                 plan.shard_index_keys(shards[r], keys[q], bounds[q], bounds[q + 1], first=(q == 0))
+            elif use_keys == "split":
+                plan.shard_index_range(shards[r], bounds[q], bounds[q + 1], first=(q == 0), which=1)
             else:
                 plan.shard_index_range(shards[r], bounds[q], bounds[q + 1], first=(q == 0))
+        if use_keys == "split":
+            plan.shard_index_range(shards[r], 0, n, first=True, which=2)
     sb = tb // world
     for r in range(world):  # ... and copies the other ranks' slices
         for q in range(world):
