@@ -26,7 +26,9 @@
 // loops; r01i fetched one 32-byte bucket per length through a cp.async ring (2.7 ms for config 2, but 148 ms for config 4:
 // ncu showed 158 DRAM sectors per read in phase 2, most of them the same sector fetched again by 4- and 16-byte loads,
 // and one exposed DRAM latency per length in phase 1); r2a cut the requests (sector-aligned read slots, 32-byte loads:
-// 115 ms); this version probes by runs.
+// 115 ms); this version probes by runs (99 ms), keeps its hot loops inside the SM's 32 KB instruction cache (find_runs rolled,
+// one compare block per verification, rare paths out of line: 93 ms -- phase 2 had been bound by instruction fetch), and leaves
+// index and CSR to sorted_stages.cu (85 ms).
 //
 // Reads the fast path cannot take at all (longer than 512 nt, a window with more than four tag matches, offsets above
 // 32, more queued arrivals than fit, a source id that occurs twice for one target, ...) go to the generic kernels of
