@@ -354,6 +354,16 @@ def run_ours(args):
     digest = [f"{dg[0]:016x}", f"{dg[1]:016x}"]
     gold = golden_for(args.workload, args.gen, args.scale)
     parity, parity_note = None, "no reference golden for this workload / scale (tests/golden/make_full_golden.py makes one)"
+    selfcheck = None  # config 5: no reference run at that size; the digest of the generic kernels' graph instead (NOT a parity claim)
+    if gold is None:
+        try:
+            tag = args.workload if args.scale == 1.0 else f"{args.workload}_at_{args.scale:g}"
+            with open(os.path.join(ROOT, "tests", "golden", f"selfcheck_{tag}_{args.gen}.json")) as f:
+                sc = json.load(f)
+            selfcheck = bool(sc["nodes"] == n_nodes_total and sc["edges"] == n_edges and sc["digest"] == digest)
+            parity_note += "; selfcheck = the same digest as the generic kernels' graph (tests/golden/selfcheck_*.json)"
+        except Exception:
+            pass
     if gold is not None:
         parity = bool(gold["nodes"] == n_nodes_total and gold["edges"] == n_edges and gold["digest"] == digest)
         parity_note = (f"edge-set digest of the last timed step vs the unmodified reference at --threads={gold['threads']} "
@@ -579,7 +589,7 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64 (2-bit packed words, exact compare)", "data": "synthetic",
         "config": workload_config(args.workload, world, args.scale, args.gen),
-        "nodes": n_nodes_total, "records": n_records, "edges": n_edges, "parity": parity, "parity_note": parity_note,
+        "nodes": n_nodes_total, "records": n_records, "edges": n_edges, "parity": parity, "selfcheck": selfcheck, "parity_note": parity_note,
         "edge_digest": digest, "gen_s": gen_s, "wall_s_timed_region": wall_s,
         "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }
