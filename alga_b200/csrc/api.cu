@@ -277,16 +277,21 @@ uint32_t minimizer_setting(int seed_nt) { return (uint32_t) (seed_nt >= 16 ? see
 bool fast_seed(const alga_ps_plan *plan) { return plan->P.seed_nt >= 16; }
 
 // s2 != nullptr: everything that concerns the suffix table goes to s2
-int stage_index_begin(alga_ps_plan *plan, cudaStream_t s, cudaStream_t s2 = nullptr) {
+int stage_index_size(alga_ps_plan *plan, size_t *bytes_prefix, size_t *bytes_suffix) {  // the two tables, sized and allocated
     if (!plan->bound) return fail(ALGA_E_INVALID, "no read set bound to the plan");
     size_table(plan->Tp, plan->stats.n_prefix);
     size_table(plan->Ts, plan->stats.n_suffix);
     plan->Tp.min_m = plan->Ts.min_m = minimizer_setting(plan->P.seed_nt);
-    const size_t bp = (size_t) plan->Tp.n_buckets * kBucketWords * 4, bs = (size_t) plan->Ts.n_buckets * kBucketWords * 4;
-    CKR(plan->tp.ensure(bp));
-    CKR(plan->ts.ensure(bs));
+    *bytes_prefix = (size_t) plan->Tp.n_buckets * kBucketWords * 4, *bytes_suffix = (size_t) plan->Ts.n_buckets * kBucketWords * 4;
+    CKR(plan->tp.ensure(*bytes_prefix));
+    CKR(plan->ts.ensure(*bytes_suffix));
     plan->Tp.slots = plan->tp.as<uint32_t>();
     plan->Ts.slots = plan->ts.as<uint32_t>();
+    return ALGA_OK;
+}
+int stage_index_begin(alga_ps_plan *plan, cudaStream_t s, cudaStream_t s2 = nullptr) {
+    size_t bp = 0, bs = 0;
+    CKR(stage_index_size(plan, &bp, &bs));
     CK(cudaMemsetAsync(plan->tp.p, 0, bp, s));
     CK(cudaMemsetAsync(plan->ts.p, 0, bs, s2 ? s2 : s));
     return ALGA_OK;
@@ -956,27 +961,40 @@ int alga_ps_plan_run(alga_ps_plan *plan, void *stream) {
                         (plan->R.stride != aligned_stride_words((plan->P.uniform_len + 15u) / 16u) || ((uintptr_t) plan->R.words & 31u));
     for (int attempt = 0;; attempt++) {
         CK(cudaEventRecord(plan->ev0, s));
-        if (repack) {
+        const bool sorted_index = sorted_stages() && n < 0x7FFFFFFFu;
+        auto do_repack = [&]() -> int {
+            if (!repack) return ALGA_OK;
             const uint32_t W = (plan->P.uniform_len + 15u) / 16u, S = aligned_stride_words(W);
             CKR(plan->slots.ensure((size_t) n * S * 4 + kReadPadBytes));
             launch_repack_reads(restore_reads.r.words, restore_reads.r.stride, W, n, plan->slots.as<uint32_t>(), S, s, plan->cfg);
             CK(cudaMemsetAsync(plan->slots.as<char>() + (size_t) n * S * 4, 0, kReadPadBytes, s));
             plan->R.words = plan->slots.as<uint32_t>();
             plan->R.stride = S;
-        }
+            return ALGA_OK;
+        };
         // seed index: the prefix table on this stream, the suffix table -- first needed by phase 2 -- on a side stream,
         // so its build overlaps phase 1
-        CK(cudaEventRecord(plan->ev_fork, s));
-        CK(cudaStreamWaitEvent(plan->side, plan->ev_fork, 0));
-        CKR(stage_index_begin(plan, s, plan->side));
-        if (sorted_stages() && n < 0x7FFFFFFFu) {
+        if (sorted_index) {
+            // the records of both tables in one pass over the reads in the CALLER's layout (36 instead of 2 x 64 bytes per read
+            // of config 4), so that neither the suffix table nor the repack waits for the other
+            size_t bp = 0, bs = 0;
+            CKR(stage_index_size(plan, &bp, &bs));
             const size_t wsb = sorted_index_workspace_bytes(n);
             CKR(plan->sort_ws[0].ensure(wsb));
             CKR(plan->sort_ws[1].ensure(wsb));
-            if (launch_sorted_index(plan->R, plan->P, plan->Tp, 0, n, plan->sort_ws[0].p, s, plan->cfg) ||
-                launch_sorted_index(plan->R, plan->P, plan->Ts, 1, n, plan->sort_ws[1].p, plan->side, plan->cfg))
-                return fail(ALGA_E_CUDA, "seed index: radix sort failed");
+            launch_seed_records(restore_reads.r, plan->P, plan->Tp, plan->Ts, n, plan->sort_ws[0].p, plan->sort_ws[1].p, s, plan->cfg);
+            CK(cudaEventRecord(plan->ev_fork, s));
+            CK(cudaStreamWaitEvent(plan->side, plan->ev_fork, 0));
+            CK(cudaMemsetAsync(plan->ts.p, 0, bs, plan->side));
+            if (launch_sorted_index(plan->Ts, n, plan->sort_ws[1].p, plan->side, plan->cfg)) return fail(ALGA_E_CUDA, "seed index: radix sort failed");
+            CK(cudaMemsetAsync(plan->tp.p, 0, bp, s));
+            CKR(do_repack());
+            if (launch_sorted_index(plan->Tp, n, plan->sort_ws[0].p, s, plan->cfg)) return fail(ALGA_E_CUDA, "seed index: radix sort failed");
         } else {
+            CKR(do_repack());
+            CK(cudaEventRecord(plan->ev_fork, s));
+            CK(cudaStreamWaitEvent(plan->side, plan->ev_fork, 0));
+            CKR(stage_index_begin(plan, s, plan->side));
             launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, 0, n, 0u, 0xFFFFFFFFu, s, plan->cfg, 1);
             launch_build_index(plan->R, plan->P, plan->Tp, plan->Ts, 0, n, 0u, 0xFFFFFFFFu, plan->side, plan->cfg, 2);
         }

@@ -110,12 +110,14 @@ void launch_phase2_spill(const ReadsDev &R, const SeedTable &suffix, const PsDev
                          const uint32_t *queue, uint32_t n_queue, const uint64_t *spill_off, uint32_t *spill_store,
                          const Phase2Out &out, cudaStream_t s, const LaunchCfg &cfg);
 
-// --- the scatter-shaped stages done by sorting (sorted_stages.cu): seed index of one side (0 = prefix table, 1 = suffix table) over
-// the reads [0, n), into a cleared table; CSR rows [lo, hi) (+ row_off, unsorted inside a row) out of n triples.  n < 2^31 each;
-// `ws` = *_workspace_bytes() of scratch.  Return 0 or a cudaError_t of the sort.
+// --- the scatter-shaped stages done by sorting (sorted_stages.cu): seed records of both tables for the reads [0, n) (one pass, R in
+// any layout), then one table out of its records into a cleared table (the two tables may be built on two streams); CSR rows
+// [lo, hi) (+ row_off, unsorted inside a row) out of n triples.  n < 2^31 each; `ws` = *_workspace_bytes() of scratch per table.
+// Return 0 or a cudaError_t of the sort.
 size_t sorted_index_workspace_bytes(uint32_t n_reads);
-int launch_sorted_index(const ReadsDev &R, const PsDev &P, const SeedTable &T, int side, uint32_t n, void *ws, cudaStream_t s,
-                        const LaunchCfg &cfg);
+void launch_seed_records(const ReadsDev &R, const PsDev &P, const SeedTable &Tp, const SeedTable &Ts, uint32_t n, void *ws_prefix,
+                         void *ws_suffix, cudaStream_t s, const LaunchCfg &cfg);
+int launch_sorted_index(const SeedTable &T, uint32_t n, void *ws, cudaStream_t s, const LaunchCfg &cfg);
 size_t sorted_csr_workspace_bytes(uint64_t n_edges);
 int launch_sorted_csr(const int32_t *triples, uint64_t n, uint32_t lo, uint32_t hi, int swap, void *ws, uint64_t *row_off,
                       int32_t *nbr, int32_t *off, cudaStream_t s, const LaunchCfg &cfg);

@@ -36,24 +36,35 @@ inline int grid_1d(uint64_t n, int block, const LaunchCfg &cfg, int per_sm = 8) 
 }
 
 // ---- seed index ------------------------------------------------------------------------------------------------
-// key = bucket, value = read id | tag << 32; reads that do not take part get the bucket number n_buckets (sorts behind all)
-// side 0: prefix table (window at the start of the read), side 1: suffix table (window at its end)
-__global__ void seed_records_kernel(ReadsDev R, PsDev P, SeedTable T, int side, uint32_t n, uint32_t *__restrict__ keys,
-                                    uint64_t *__restrict__ vals) {
+// key = bucket, value = read id | tag << 32; reads that do not take part get the bucket number n_buckets (sorts behind all).
+// Both sides in one pass over the reads (any layout: the caller's compact one will do, so the pass does not wait for the repack):
+// prefix table = window at the start of the read, suffix table = window at its end.
+__global__ void seed_records_kernel(ReadsDev R, PsDev P, SeedTable Tp, SeedTable Ts, uint32_t n, uint32_t *__restrict__ keys_p,
+                                    uint64_t *__restrict__ vals_p, uint32_t *__restrict__ keys_s, uint64_t *__restrict__ vals_s) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
         const uint32_t len = P.uniform_len ? P.uniform_len : R.len[i];
-        bool on = len != 0 && (int64_t) len >= P.lmin;
-        if (on) on = side == 0 ? flag_to(R, (uint32_t) i) : (flag_from(R, (uint32_t) i) && (int64_t) len - P.min_offset >= P.lmin);
-        uint32_t key = T.n_buckets;
+        const bool any = len != 0 && (int64_t) len >= P.lmin;
+        const bool on_p = any && flag_to(R, (uint32_t) i);
+        const bool on_s = any && flag_from(R, (uint32_t) i) && (int64_t) len - P.min_offset >= P.lmin;
+        const uint32_t *p = read_ptr(R, (uint32_t) i);
+        uint32_t key = Tp.n_buckets;
         uint64_t val = i;
-        if (on) {
-            const uint32_t *p = read_ptr(R, (uint32_t) i);
-            const uint64_t win = bits64(p, side == 0 ? 0u : 2u * (len - (uint32_t) P.seed_nt)) & P.seed_mask, h = mix64(win);
-            key = bucket_index_rt(T, win, h, (uint32_t) P.seed_nt);
+        if (on_p) {
+            const uint64_t win = bits64(p, 0u) & P.seed_mask, h = mix64(win);
+            key = bucket_index_rt(Tp, win, h, (uint32_t) P.seed_nt);
             val |= (uint64_t) tag_of(h) << 32;
         }
-        keys[i] = key;
-        vals[i] = val;
+        keys_p[i] = key;
+        vals_p[i] = val;
+        key = Ts.n_buckets;
+        val = i;
+        if (on_s) {
+            const uint64_t win = bits64(p, 2u * (len - (uint32_t) P.seed_nt)) & P.seed_mask, h = mix64(win);
+            key = bucket_index_rt(Ts, win, h, (uint32_t) P.seed_nt);
+            val |= (uint64_t) tag_of(h) << 32;
+        }
+        keys_s[i] = key;
+        vals_s[i] = val;
     }
 }
 
@@ -203,12 +214,18 @@ CsrWs carve_csr(void *ws, uint64_t n) {
 size_t sorted_index_workspace_bytes(uint32_t n_reads) { return carve_index(nullptr, n_reads ? n_reads : 1).total; }
 size_t sorted_csr_workspace_bytes(uint64_t n_edges) { return carve_csr(nullptr, n_edges ? n_edges : 1).total; }
 
-// One table (side 0: prefix, 1: suffix) over the reads [0, n); the table must have been cleared.  n < 2^31.
-int launch_sorted_index(const ReadsDev &R, const PsDev &P, const SeedTable &T, int side, uint32_t n, void *ws, cudaStream_t s,
-                        const LaunchCfg &cfg) {
+// Seed records of both tables for the reads [0, n) (R in any layout) into the two workspaces.  n < 2^31.
+void launch_seed_records(const ReadsDev &R, const PsDev &P, const SeedTable &Tp, const SeedTable &Ts, uint32_t n, void *ws_prefix,
+                         void *ws_suffix, cudaStream_t s, const LaunchCfg &cfg) {
+    if (!n) return;
+    IndexWs wp = carve_index(ws_prefix, n), wq = carve_index(ws_suffix, n);
+    seed_records_kernel<<<grid_1d(n, 256, cfg), 256, 0, s>>>(R, P, Tp, Ts, n, wp.k0, wp.v0, wq.k0, wq.v0);
+    bump(cfg);
+}
+// One table out of its records (launch_seed_records, same workspace); the table must have been cleared.
+int launch_sorted_index(const SeedTable &T, uint32_t n, void *ws, cudaStream_t s, const LaunchCfg &cfg) {
     if (!n) return 0;
     IndexWs w = carve_index(ws, n);
-    seed_records_kernel<<<grid_1d(n, 256, cfg), 256, 0, s>>>(R, P, T, side, n, w.k0, w.v0);
     cub::DoubleBuffer<uint32_t> dk(w.k0, w.k1);
     cub::DoubleBuffer<uint64_t> dv(w.v0, w.v1);
     cudaError_t e = cub::DeviceRadixSort::SortPairs(w.tmp, w.tmp_bytes, dk, dv, (int) n, 0, bits_for(T.n_buckets), s);
@@ -216,7 +233,7 @@ int launch_sorted_index(const ReadsDev &R, const PsDev &P, const SeedTable &T, i
     cudaMemsetAsync(w.n_over, 0, 4, s);
     fill_buckets_kernel<<<grid_1d(n, 256, cfg), 256, 0, s>>>(T, dk.Current(), dv.Current(), n, w.over, w.over_cap, w.n_over);
     chain_overflow_kernel<<<cfg.sm_count, 256, 0, s>>>(T, dk.Current(), dv.Current(), w.over, w.over_cap, w.n_over);
-    bump(cfg, 3);
+    bump(cfg, 2);
     return 0;
 }
 
