@@ -26,9 +26,11 @@ seq = list(launches.values())
 ours = ("repack_reads", "build_index", "seed_records", "fill_buckets", "chain_overflow", "csr_records", "csr_rows", "DeviceRadixSort",
         "phase1_", "phase2_", "rebuild_rows", "over_to_csr", "rows_to_csr", "scan_", "end_cursor",
         "scatter_", "split_pairs", "sort_rows", "sort_big_rows", "count_sources", "peek", "read_stats")
-starts = [i for i, e in enumerate(seq) if e["name"].startswith("repack_reads")]
+# a build starts with the seed records (sorted index: they come before the repack) or, without them, with the repack
+first = "seed_records" if any(e["name"].startswith("seed_records") for e in seq) else "repack_reads"
+starts = [i for i, e in enumerate(seq) if e["name"].startswith(first)]
 if len(starts) < 2:
-    raise SystemExit("expected two builds (two repack_reads launches) in the list")
+    raise SystemExit(f"expected two builds (two {first} launches) in the list")
 build = [e for e in seq[starts[-1]:] if any(e["name"].startswith(o) for o in ours)]
 per = collections.OrderedDict()
 for e in build:
